@@ -1,0 +1,150 @@
+/* seb200.h -- C ABI of libseb200.so: the B200 (sm_100a) generator hot path of
+ * minyoungpark1/Speech-Enhancement (SCP-GAN / CMGAN TSCNet forward + the
+ * power-compressed STFT / iSTFT bracket).
+ *
+ * The reference has no FFI: its "operator API" for this path is the Python
+ * nn.Module protocol (models/generator.py:132-167) plus four DSP helpers
+ * (core/function.py:625-703) and predict() (inference_gan.py:75-100).  Each
+ * entry point below names the reference code it replaces.  INTEGRATION.md
+ * shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C: raw device pointers, ints, a cudaStream_t passed as void*.
+ *   - every buffer is owned by the caller (PyTorch's caching allocator in the
+ *     shipped host code); the library only launches kernels on `stream`, never
+ *     synchronises, allocates or frees => CUDA-graph capturable.
+ *   - return 0 on success, <0 = SEB_E* argument error, >0 = cudaError_t.
+ *     seb200_last_error_string() describes the last failure of this thread.
+ *   - activations are fp32, channels-last: [B, T, F, C]; "tokens" means the
+ *     flattened [B*T*F, C] view.
+ */
+#ifndef SEB200_H
+#define SEB200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SEB200_ABI_VERSION 1
+
+enum {
+  SEB_OK = 0,
+  SEB_EINVAL = -1,      /* bad shape / null pointer */
+  SEB_EALIGN = -2,      /* pointer or stride not 16-byte aligned */
+  SEB_EUNSUPPORTED = -3 /* combination not instantiated */
+};
+
+/* ---- GEMM engine ------------------------------------------------------------
+ * C[M, N] = epilogue( A_loader[M, K] * W[N, K]^T ).  One descriptor covers every
+ * dense contraction on the path: DFT / iDFT (core/function.py:690-691,701-702),
+ * Conv2d of DilatedDenseNet / conv_2 / SPConvTranspose2d (generator.py:18-20,45,83)
+ * as implicit GEMM, and the Linear / pointwise Conv1d layers of ConformerBlock
+ * (conformer.py:87-89,137-140,165,169).
+ */
+enum { SEB_LOAD_ROWS = 0, SEB_LOAD_ROWS_LN = 1, SEB_LOAD_CONV = 2, SEB_LOAD_HANKEL = 3 };
+enum {
+  SEB_EPI_BIAS = 0,     /* out = acc + bias                                  */
+  SEB_EPI_SWISH = 1,    /* v = acc + bias; out = v * sigmoid(v)              */
+  SEB_EPI_GLU = 2,      /* columns interleaved (value, gate): out[n/2] = v * sigmoid(g) */
+  SEB_EPI_RESID = 3,    /* out = alpha * (acc + bias) + resid                */
+  SEB_EPI_SUBPIXEL = 4, /* out[(bt*2Fo + 2w + n/64), n%64] = acc + bias      */
+  SEB_EPI_COMPRESS = 5  /* columns interleaved (re, im): out[m, k, 0..2] = (|X|^.3, re|X|^-.7, im|X|^-.7) */
+};
+enum { SEB_ENGINE_TCGEN05 = 0, SEB_ENGINE_SIMT = 1 };
+
+typedef struct SebGemm {
+  int loader, epilogue;
+  int M, N, K;              /* logical sizes; K as packed (multiple of 64)     */
+  /* A operand */
+  const float* a[4];        /* ROWS*: a[0]; CONV: one pointer per 64-channel slot, newest first; HANKEL: padded signal */
+  long long lda;            /* ROWS*: row stride; HANKEL: samples per utterance row of a[0] */
+  const float* ln_gamma;    /* ROWS_LN (K == 64): LayerNorm(64) weight / bias, eps 1e-5 */
+  const float* ln_beta;
+  int B, T, Fin, Fout;      /* CONV geometry: M = B*T*Fout output pixels; HANKEL: M = B*T, hop 100 */
+  int taps_t, dil, stride_f, nslots; /* CONV: kernel (taps_t, 3), dilation (dil, 1), stride (1, stride_f), pad (dil*(taps_t-1) top, 1 left/right) */
+  /* W operand (see seb200 packing.py / DESIGN.md for the image layouts) */
+  const void* w_tc;         /* tcgen05 image: per (n-tile, k-chunk) bf16 hi|lo, 128B-swizzled K-major */
+  int tc_ntile;             /* rows per n-tile in w_tc (16..256, multiple of 16) */
+  int tc_ntiles;
+  const float* w_simt;      /* fp32 [K][simt_npad] (K-major rows)               */
+  int simt_npad;            /* multiple of 64                                   */
+  const float* bias;        /* [N] or NULL */
+  /* output */
+  float* out; long long ldo;
+  const float* resid; long long ldr; float alpha;
+} SebGemm;
+
+int seb200_gemm(const SebGemm* g, int engine, void* stream);
+
+/* ---- DSP bracket --------------------------------------------------------- */
+/* predict() glue, inference_gan.py:79-87 + torch.stft's reflect padding: per utterance
+ * c = sqrt(L / sum x^2); xpad[b, 0 : Lp+400] = reflect200(wrap_pad(c * x)); c_out[b] = c. */
+int seb200_rms_pad(const float* wave, int B, int L, int Lp, int normalize,
+                   float* xpad, float* c_out, void* stream);
+/* complex64 (B, F, T) spectrogram (torch.stft layout) -> in3 [B, T, F, 3] = (|x|, re, im); generator.py:146-151 */
+int seb200_spec_to_in3(const float* spec_ri, int B, int F, int T, float* in3, void* stream);
+/* in3 [B, T, F, 3] -> complex64 (B, F, T): the layout compressed_stft returns (core/function.py:693) */
+int seb200_in3_to_spec(const float* in3, int B, int F, int T, float* spec_ri, void* stream);
+/* power_uncompress (core/function.py:636-645) of est [B*T, F, 2] into iDFT rows z [B*T, ldz] =
+ * (re_0, im_0, re_1, ...), zero padded to ldz */
+int seb200_decompress_rows(const float* est, int rows, int F, float* z, int ldz, void* stream);
+/* complex64 (B, F, T) -> decompressed iDFT rows z [B*T, ldz] (uncompressed_istft called on its own) */
+int seb200_spec_decompress_rows(const float* spec_ri, int B, int F, int T, float* z, int ldz, void* stream);
+/* torch.istft overlap-add as a deterministic gather: out[b, m] = sum_t frames[b, t, m + 200 - 100 t] * inv_env[m] * (inv_c ? 1/c[b] : 1) */
+int seb200_overlap_add(const float* frames, int B, int T, int ldf, const float* inv_env,
+                       const float* c, float* out, int Lout, int ld_out, void* stream);
+
+/* ---- encoder / decoder bandwidth kernels ---------------------------------- */
+/* DenseEncoder.conv_1[0]: 1x1 conv 3 -> 64 (generator.py:39) on in3 */
+int seb200_conv1x1_in3(const float* in3, long long pixels, const float* w /*[64,3]*/,
+                       const float* bias, float* out, void* stream);
+/* nn.InstanceNorm2d statistics over the (T, F) plane per (b, c): stats[b, c] = (mean, rstd), eps 1e-5, biased var.
+ * x: [B, pix_per_b, C]; workspace: doubles, at least seb200_inorm_workspace_bytes() */
+long long seb200_inorm_workspace_bytes(int B, long long pix_per_b, int C);
+int seb200_inorm_stats(const float* x, int B, long long pix_per_b, int C, float* stats,
+                       void* workspace, long long workspace_bytes, void* stream);
+/* y = PReLU(gamma * (x - mean) * rstd + beta): InstanceNorm2d(affine) + PReLU(C) (generator.py:21-22,40-41) */
+int seb200_inorm_prelu(const float* x, int B, long long pix_per_b, int C, const float* stats,
+                       const float* gamma, const float* beta, const float* slope, float* y, void* stream);
+/* MaskDecoder.conv_1: Conv2d(64 -> 1, (1,2)) on [B*T, 202, 64] -> raw [B*T, 201] (generator.py:100) */
+int seb200_mask_conv(const float* x, long long rows, int Fin, const float* w /*[2][64]: tap-major*/,
+                     float bias, float* out, void* stream);
+/* ComplexDecoder: InstanceNorm(64)+PReLU(64) applied on load, then Conv2d(64 -> 2, (1,2)) (generator.py:127-128) */
+int seb200_complex_conv(const float* x, int B, long long rows_per_b, int Fin, const float* stats,
+                        const float* gamma, const float* beta, const float* slope,
+                        const float* w /*[2 out][2 taps][64]*/, const float* bias /*[2]*/, float* out /*[rows, 201, 2]*/, void* stream);
+/* Mask tail + recombination (generator.py:110-112,158-165): mask = PReLU_f(wf * PReLU(IN(raw)) + bf);
+ * est[.., 0..1] = mask * in3[.., 1..2] + cplx */
+int seb200_mask_recombine(const float* mask_raw, const float* mask_stats /*[B,1,2]*/, int B, long long rows_per_b, int F,
+                          float in_gamma, float in_beta, float slope1, float wf, float bf, const float* slope_f /*[F]*/,
+                          const float* in3, const float* cplx, float* est /*[rows, F, 2]*/, float* mask_out /*optional [rows,F]*/, void* stream);
+/* est [B*T, F, 2] -> two fp32 (B, 1, T, F) tensors (identical memory order: a de-interleave) */
+int seb200_split_ri(const float* est, long long n, float* re, float* im, void* stream);
+
+/* ---- conformer kernels ---------------------------------------------------- */
+/* Token addressing of a sequence set: token(seq, i) = (seq / inner) * outer_stride + (seq % inner) + i * pos_stride.
+ * time conformer (generator.py:69): inner = F', outer_stride = T*F', pos_stride = F', nseq = B*F', n = T
+ * freq conformer (generator.py:71): inner = 1,  outer_stride = F',   pos_stride = 1,  nseq = B*T,  n = F' */
+typedef struct SebSeq { int nseq, n, inner; long long outer_stride, pos_stride; } SebSeq;
+
+/* Attention core with Shaw relative positions (conformer.py:103-122): qkv [tokens, 192] = (q | k | v), heads 4 x 16,
+ * rel_pos_emb [1025, 16]; out [tokens, 64] ('b h n d -> b n (h d)').  variant 0 = tensor-core, 1 = SIMT reference */
+int seb200_attention(const float* qkv, const float* rel_pos_emb, const SebSeq* seq, float* out, int variant, void* stream);
+/* DepthWiseConv1d(128, k=31, pad 15/15) + BatchNorm1d(eval) + Swish along the sequence axis (conformer.py:166-168):
+ * x, y [tokens, 128]; w [31][128] (tap-major); bn_scale/bn_shift fold conv bias, running stats and affine */
+int seb200_dwconv_bn_swish(const float* x, const SebSeq* seq, const float* w, const float* bn_scale,
+                           const float* bn_shift, float* y, void* stream);
+/* post_norm + the TSCB outer residual (conformer.py:211, generator.py:70,72): out = LN(x) * g + b + resid */
+int seb200_layernorm_residual(const float* x, long long tokens, const float* gamma, const float* beta,
+                              const float* resid, float* out, void* stream);
+
+/* ---- misc ------------------------------------------------------------------ */
+int seb200_version(void);
+const char* seb200_last_error_string(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+long long seb200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEB200_H */

@@ -1,0 +1,301 @@
+"""CPU oracle for the SCP-GAN / CMGAN generator hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file is a functional fp32 restatement (torch on CPU, no nn.Module classes,
+no einops) of the reference's algorithm for the path named in BASELINE.json:
+
+    predict()              /root/reference/inference_gan.py:75-100
+    compressed_stft()      /root/reference/core/function.py:685-693
+    power_compress()       /root/reference/core/function.py:625-634
+    TSCNet.forward()       /root/reference/models/generator.py:145-167
+    ConformerBlock.forward /root/reference/models/conformer.py:206-212
+    power_uncompress()     /root/reference/core/function.py:636-645
+    uncompressed_istft()   /root/reference/core/function.py:695-703
+
+It is driven purely by a ``state_dict`` with the reference's 359 keys.  Only
+``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
+``--impl reference`` leg may import it; the product package never does.
+
+Parity pin: the reference ships no golden vectors or tests for this path
+(SURVEY.md section 4), so the oracle is pinned against OUTPUTS OF THE REFERENCE
+ITSELF: ``oracle/make_golden.py`` imports the unmodified reference from
+/root/reference (with the five third-party stubs of ``oracle/ref_import.py``),
+runs ``inference_gan.predict`` and ``TSCNet`` on seeded inputs and commits the
+results under ``tests/golden/``; ``tests/test_oracle.py`` checks this
+restatement against those files (and, when /root/reference is mounted, against
+the live reference, stage by stage).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+N_FFT = 400          # config/default.py:19-23
+HOP = 100
+N_BINS = N_FFT // 2 + 1
+COMPRESS_EXP = 0.3   # core/function.py:628-629
+MAX_POS = 512        # models/conformer.py:81
+HEADS = 4            # models/generator.py:60-65
+DIM_HEAD = 16
+
+SD = Dict[str, torch.Tensor]
+
+
+# ----------------------------------------------------------------------------
+# DSP bracket
+# ----------------------------------------------------------------------------
+def hamming_periodic(n: int = N_FFT) -> torch.Tensor:
+    """torch.hamming_window(n) (periodic): inference_gan.py:78."""
+    k = torch.arange(n, dtype=torch.float64)
+    return (0.54 - 0.46 * torch.cos(2.0 * math.pi * k / n)).to(torch.float32)
+
+
+def stft_frames(x: torch.Tensor, n_fft: int = N_FFT, hop: int = HOP) -> torch.Tensor:
+    """Centre (reflect) padding + framing as torch.stft does it by default
+    (core/function.py:690-691).  x: (B, L) -> (B, T, n_fft), T = L // hop + 1."""
+    pad = n_fft // 2
+    xp = F.pad(x.unsqueeze(1), (pad, pad), mode="reflect").squeeze(1)
+    return xp.unfold(-1, n_fft, hop)
+
+
+def power_compress(spec: torch.Tensor) -> torch.Tensor:
+    """|S|^0.3 * exp(j*angle(S))  (core/function.py:625-634), written the way
+    the reference evaluates it: abs, angle, pow, cos, sin."""
+    mag = spec.abs() ** COMPRESS_EXP
+    ph = spec.angle()
+    return torch.complex(mag * torch.cos(ph), mag * torch.sin(ph))
+
+
+def power_uncompress(spec: torch.Tensor) -> torch.Tensor:
+    """|S|^(1/0.3) * exp(j*angle(S))  (core/function.py:636-645)."""
+    mag = spec.abs() ** (1.0 / COMPRESS_EXP)
+    ph = spec.angle()
+    return torch.complex(mag * torch.cos(ph), mag * torch.sin(ph))
+
+
+def compressed_stft(x: torch.Tensor, n_fft: int = N_FFT, hop: int = HOP,
+                    window: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(B, L) fp32 -> complex64 (B, n_fft/2+1, T).  core/function.py:685-693."""
+    w = hamming_periodic(n_fft) if window is None else window
+    fr = stft_frames(x, n_fft, hop) * w
+    spec = torch.fft.rfft(fr, dim=-1).transpose(1, 2)
+    return power_compress(spec)
+
+
+def uncompressed_istft(spec: torch.Tensor, n_fft: int = N_FFT, hop: int = HOP,
+                       window: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """complex64 (B, F, T) -> (B, hop*(T-1)).  core/function.py:695-703:
+    decompress, irfft, synthesis window, overlap-add, divide by the squared
+    window envelope, trim n_fft/2 at both ends (torch.istft, center=True)."""
+    w = hamming_periodic(n_fft) if window is None else window
+    z = power_uncompress(spec)
+    B, _, T = z.shape
+    fr = torch.fft.irfft(z.transpose(1, 2), n=n_fft, dim=-1) * w      # (B, T, n_fft)
+    full = n_fft + hop * (T - 1)
+    y = torch.zeros(B, full, dtype=fr.dtype)
+    env = torch.zeros(full, dtype=fr.dtype)
+    w2 = w * w
+    for t in range(T):
+        y[:, t * hop:t * hop + n_fft] += fr[:, t]
+        env[t * hop:t * hop + n_fft] += w2
+    half = n_fft // 2
+    return y[:, half:full - half] / env[half:full - half]
+
+
+# ----------------------------------------------------------------------------
+# Generator building blocks (reference layout: (B, C, T, F))
+# ----------------------------------------------------------------------------
+def _inorm(x, sd, p):
+    """nn.InstanceNorm2d(C, affine=True), eps 1e-5, biased plane variance."""
+    return F.instance_norm(x, weight=sd[p + ".weight"], bias=sd[p + ".bias"], eps=1e-5)
+
+
+def _prelu(x, sd, p):
+    return F.prelu(x, sd[p + ".weight"])
+
+
+def dilated_dense(x, sd: SD, p: str, depth: int = 4):
+    """DilatedDenseNet.forward  models/generator.py:24-32."""
+    skip = x
+    out = x
+    for i in range(1, depth + 1):
+        dil = 2 ** (i - 1)
+        h = F.pad(skip, (1, 1, dil, 0))
+        h = F.conv2d(h, sd[f"{p}.conv{i}.weight"], sd[f"{p}.conv{i}.bias"], dilation=(dil, 1))
+        h = _inorm(h, sd, f"{p}.norm{i}")
+        out = _prelu(h, sd, f"{p}.prelu{i}")
+        skip = torch.cat([out, skip], dim=1)
+    return out
+
+
+def dense_encoder(x_in, sd: SD, p: str = "dense_encoder"):
+    """DenseEncoder.forward  models/generator.py:50-54."""
+    h = F.conv2d(x_in, sd[p + ".conv_1.0.weight"], sd[p + ".conv_1.0.bias"])
+    h = _prelu(_inorm(h, sd, p + ".conv_1.1"), sd, p + ".conv_1.2")
+    h = dilated_dense(h, sd, p + ".dilated_dense")
+    h = F.conv2d(h, sd[p + ".conv_2.0.weight"], sd[p + ".conv_2.0.bias"], stride=(1, 2), padding=(0, 1))
+    return _prelu(_inorm(h, sd, p + ".conv_2.1"), sd, p + ".conv_2.2")
+
+
+def _ln(x, sd, p):
+    return F.layer_norm(x, (x.shape[-1],), sd[p + ".weight"], sd[p + ".bias"], 1e-5)
+
+
+def _swish(x):
+    return x * torch.sigmoid(x)
+
+
+def feed_forward(x, sd: SD, p: str):
+    """Scale(0.5, PreNorm(FeedForward))  models/conformer.py:53-71,128-145 (eval: dropout off)."""
+    h = _ln(x, sd, p + ".fn.norm")
+    h = F.linear(h, sd[p + ".fn.fn.net.0.weight"], sd[p + ".fn.fn.net.0.bias"])
+    h = _swish(h)
+    h = F.linear(h, sd[p + ".fn.fn.net.3.weight"], sd[p + ".fn.fn.net.3.bias"])
+    return 0.5 * h
+
+
+def attention(x, sd: SD, p: str, chunk: int = 0):
+    """PreNorm(Attention) with Shaw relative positions  models/conformer.py:96-125.
+    x: (S, n, 64).  ``chunk`` > 0 evaluates the S sequences in groups (the
+    sequences are independent) to bound the (S, h, n, n) memory."""
+    if chunk and x.shape[0] > chunk:
+        return torch.cat([attention(x[i:i + chunk], sd, p) for i in range(0, x.shape[0], chunk)], 0)
+    S, n, _ = x.shape
+    h = _ln(x, sd, p + ".norm")
+    q = F.linear(h, sd[p + ".fn.to_q.weight"])
+    kv = F.linear(h, sd[p + ".fn.to_kv.weight"])
+    k, v = kv[..., :HEADS * DIM_HEAD], kv[..., HEADS * DIM_HEAD:]
+    split = lambda t: t.reshape(S, n, HEADS, DIM_HEAD).permute(0, 2, 1, 3)   # b h n d
+    q, k, v = split(q), split(k), split(v)
+    scale = DIM_HEAD ** -0.5
+    dots = torch.matmul(q, k.transpose(-1, -2)) * scale
+    pos = torch.arange(n)
+    dist = (pos[:, None] - pos[None, :]).clamp(-MAX_POS, MAX_POS) + MAX_POS
+    rel = sd[p + ".fn.rel_pos_emb.weight"][dist]                          # (n, n, d)
+    dots = dots + torch.einsum("bhnd,nrd->bhnr", q, rel) * scale
+    attn = dots.softmax(dim=-1)
+    o = torch.matmul(attn, v).permute(0, 2, 1, 3).reshape(S, n, HEADS * DIM_HEAD)
+    return F.linear(o, sd[p + ".fn.to_out.weight"], sd[p + ".fn.to_out.bias"])
+
+
+def conv_module(x, sd: SD, p: str):
+    """ConformerConvModule (eval)  models/conformer.py:161-172."""
+    h = _ln(x, sd, p + ".net.0").transpose(1, 2)                           # b c n
+    h = F.conv1d(h, sd[p + ".net.2.weight"], sd[p + ".net.2.bias"])
+    a, g = h.chunk(2, dim=1)
+    h = a * torch.sigmoid(g)
+    ks = sd[p + ".net.4.conv.weight"].shape[-1]
+    h = F.pad(h, (ks // 2, ks // 2 - (ks + 1) % 2))
+    h = F.conv1d(h, sd[p + ".net.4.conv.weight"], sd[p + ".net.4.conv.bias"], groups=h.shape[1])
+    h = F.batch_norm(h, sd[p + ".net.5.running_mean"], sd[p + ".net.5.running_var"],
+                     sd[p + ".net.5.weight"], sd[p + ".net.5.bias"], False, 0.0, 1e-5)
+    h = _swish(h)
+    h = F.conv1d(h, sd[p + ".net.7.weight"], sd[p + ".net.7.bias"])
+    return h.transpose(1, 2)
+
+
+def conformer_block(x, sd: SD, p: str, chunk: int = 0):
+    """ConformerBlock.forward  models/conformer.py:206-212."""
+    x = feed_forward(x, sd, p + ".ff1") + x
+    x = attention(x, sd, p + ".attn", chunk) + x
+    x = conv_module(x, sd, p + ".conv") + x
+    x = feed_forward(x, sd, p + ".ff2") + x
+    return _ln(x, sd, p + ".post_norm")
+
+
+def tscb(x, sd: SD, p: str, chunk: int = 0):
+    """TSCB.forward  models/generator.py:67-74.  x: (B, C, T, F)."""
+    b, c, t, f = x.shape
+    xt = x.permute(0, 3, 2, 1).reshape(b * f, t, c)
+    xt = conformer_block(xt, sd, p + ".time_conformer", chunk) + xt
+    xf = xt.reshape(b, f, t, c).permute(0, 2, 1, 3).reshape(b * t, f, c)
+    xf = conformer_block(xf, sd, p + ".freq_conformer", chunk) + xf
+    return xf.reshape(b, t, f, c).permute(0, 3, 1, 2)
+
+
+def sub_pixel(x, sd: SD, p: str, r: int = 2):
+    """SPConvTranspose2d.forward  models/generator.py:85-92."""
+    y = F.conv2d(F.pad(x, (1, 1, 0, 0)), sd[p + ".conv.weight"], sd[p + ".conv.bias"])
+    b, rc, t, w = y.shape
+    y = y.reshape(b, r, rc // r, t, w).permute(0, 2, 3, 4, 1)
+    return y.reshape(b, rc // r, t, w * r)
+
+
+def mask_decoder(x, sd: SD, p: str = "mask_decoder"):
+    """MaskDecoder.forward  models/generator.py:106-112 -> (B, 1, T, F)."""
+    h = dilated_dense(x, sd, p + ".dense_block")
+    h = sub_pixel(h, sd, p + ".sub_pixel")
+    h = F.conv2d(h, sd[p + ".conv_1.weight"], sd[p + ".conv_1.bias"])
+    h = _prelu(_inorm(h, sd, p + ".norm"), sd, p + ".prelu")
+    h = F.conv2d(h, sd[p + ".final_conv.weight"], sd[p + ".final_conv.bias"])
+    h = h.permute(0, 3, 2, 1).squeeze(-1)                                  # (B, F, T)
+    h = F.prelu(h, sd[p + ".prelu_out.weight"])                            # slope per frequency bin
+    return h.permute(0, 2, 1).unsqueeze(1)
+
+
+def complex_decoder(x, sd: SD, p: str = "complex_decoder"):
+    """ComplexDecoder.forward  models/generator.py:124-129 -> (B, 2, T, F)."""
+    h = dilated_dense(x, sd, p + ".dense_block")
+    h = sub_pixel(h, sd, p + ".sub_pixel")
+    h = _prelu(_inorm(h, sd, p + ".norm"), sd, p + ".prelu")
+    return F.conv2d(h, sd[p + ".conv.weight"], sd[p + ".conv.bias"])
+
+
+def tscnet_forward(spec: torch.Tensor, sd: SD, chunk: int = 0, stages: Optional[dict] = None):
+    """TSCNet.forward  models/generator.py:145-167.
+    spec: complex64 (B, 201, T) -> (final_real, final_imag), each (B, 1, T, 201).
+    If ``stages`` is a dict, per-stage tensors are stored in it (reference layout)."""
+    mag = spec.abs().unsqueeze(1).permute(0, 1, 3, 2)
+    ph = spec.angle().unsqueeze(1).permute(0, 1, 3, 2)
+    x_in = torch.cat([mag, spec.real.unsqueeze(1).permute(0, 1, 3, 2),
+                      spec.imag.unsqueeze(1).permute(0, 1, 3, 2)], dim=1)
+    h = dense_encoder(x_in, sd)
+    if stages is not None:
+        stages["x_in"] = x_in
+        stages["encoder"] = h
+    for i in range(1, 5):
+        h = tscb(h, sd, f"TSCB_{i}", chunk)
+        if stages is not None:
+            stages[f"tscb{i}"] = h
+    mask = mask_decoder(h, sd)
+    cplx = complex_decoder(h, sd)
+    out_mag = mask * mag
+    fr = out_mag * torch.cos(ph) + cplx[:, 0:1]
+    fi = out_mag * torch.sin(ph) + cplx[:, 1:2]
+    if stages is not None:
+        stages["mask"] = mask
+        stages["complex"] = cplx
+    return fr, fi
+
+
+# ----------------------------------------------------------------------------
+# wave -> wave  (inference_gan.py:75-100, batched)
+# ----------------------------------------------------------------------------
+def predict(wave: torch.Tensor, sd: SD, chunk: int = 0, stages: Optional[dict] = None) -> torch.Tensor:
+    """(B, L) fp32 noisy -> (B, L) enhanced; every row gets predict()'s
+    per-utterance semantics: RMS normalise, wrap-pad to a multiple of 100,
+    compressed STFT, generator, decompress + iSTFT, un-normalise, trim."""
+    x = wave.to(torch.float32)
+    B, L = x.shape
+    c = torch.sqrt(L / torch.sum(x ** 2.0, dim=-1, keepdim=True))
+    x = x * c
+    pad = int(math.ceil(L / 100)) * 100 - L
+    x = torch.cat([x, x[:, :pad]], dim=-1)
+    spec = compressed_stft(x)
+    if stages is not None:
+        stages["spec"] = spec
+    fr, fi = tscnet_forward(spec, sd, chunk, stages)
+    est = torch.complex(fr.permute(0, 1, 3, 2), fi.permute(0, 1, 3, 2)).squeeze(1)
+    y = uncompressed_istft(est) / c
+    return y[:, :L]
+
+
+def si_sdr(est: torch.Tensor, ref: torch.Tensor) -> torch.Tensor:
+    """Scale-invariant SDR in dB along the last axis (parity metric)."""
+    est = est.double() - est.double().mean(-1, keepdim=True)
+    ref = ref.double() - ref.double().mean(-1, keepdim=True)
+    a = (est * ref).sum(-1, keepdim=True) / (ref * ref).sum(-1, keepdim=True)
+    s = a * ref
+    return 10.0 * torch.log10((s * s).sum(-1) / ((est - s) ** 2).sum(-1))

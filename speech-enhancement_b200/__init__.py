@@ -1,0 +1,33 @@
+"""se_b200 -- B200-native (sm_100a) generator hot path of minyoungpark1/Speech-Enhancement.
+
+Public surface (mirrors the reference's interface for this path):
+
+* ``TSCNet(num_channel=64, num_features=201)``            models/generator.py:132-167
+* ``compressed_stft`` / ``uncompressed_istft``             core/function.py:685-703
+* ``EnhancerB200(model)(noisy)`` / ``.predict(numpy)``     inference_gan.py:75-100
+* ``load_model(path)``                                      inference_gan.py:60-72
+* ``shard_slice`` / ``enhance_sharded``                     batch sharding across ranks (inference has no collective)
+
+The directory is called ``speech-enhancement_b200``; import it as ``se_b200`` (the ``se_b200.py`` shim at the repo root).
+"""
+from .generator import TSCNet
+from .dsp import compressed_stft, uncompressed_istft
+from .enhancer import EnhancerB200
+from .sharding import enhance_sharded, shard_slice
+from . import ops, packing, _lib
+
+
+def load_model(model_path, device="cuda"):
+    """inference_gan.load_model: build TSCNet(64, 201), load ckpt['gen_state_dict'] with the 'module.' prefix stripped, eval()."""
+    import torch
+    model = TSCNet(num_channel=64, num_features=201).to(device)
+    ckpt = torch.load(model_path, map_location=device)
+    sd = ckpt["gen_state_dict"] if "gen_state_dict" in ckpt else ckpt
+    sd = {(k[7:] if k.startswith("module.") else k): v for k, v in sd.items()}
+    model.load_state_dict(sd)
+    model.eval()
+    return model
+
+
+__all__ = ["TSCNet", "compressed_stft", "uncompressed_istft", "EnhancerB200", "load_model", "shard_slice",
+           "enhance_sharded", "ops", "packing"]

@@ -1,0 +1,123 @@
+"""ctypes binding of libseb200.so (include/seb200.h).
+
+There is no CPU fallback: if the shared library is missing it is built with nvcc
+(``build.py``); if that fails, or a call returns non-zero, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libseb200.so")
+
+LOAD_ROWS, LOAD_ROWS_LN, LOAD_CONV, LOAD_HANKEL = 0, 1, 2, 3
+EPI_BIAS, EPI_SWISH, EPI_GLU, EPI_RESID, EPI_SUBPIXEL, EPI_COMPRESS = 0, 1, 2, 3, 4, 5
+ENGINE_TCGEN05, ENGINE_SIMT = 0, 1
+
+_fp = C.c_void_p  # raw device pointers travel as void*
+
+
+class SebGemm(C.Structure):
+    _fields_ = [
+        ("loader", C.c_int), ("epilogue", C.c_int),
+        ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
+        ("a", _fp * 4), ("lda", C.c_longlong),
+        ("ln_gamma", _fp), ("ln_beta", _fp),
+        ("B", C.c_int), ("T", C.c_int), ("Fin", C.c_int), ("Fout", C.c_int),
+        ("taps_t", C.c_int), ("dil", C.c_int), ("stride_f", C.c_int), ("nslots", C.c_int),
+        ("w_tc", _fp), ("tc_ntile", C.c_int), ("tc_ntiles", C.c_int),
+        ("w_simt", _fp), ("simt_npad", C.c_int),
+        ("bias", _fp),
+        ("out", _fp), ("ldo", C.c_longlong),
+        ("resid", _fp), ("ldr", C.c_longlong), ("alpha", C.c_float),
+    ]
+
+
+class SebSeq(C.Structure):
+    _fields_ = [("nseq", C.c_int), ("n", C.c_int), ("inner", C.c_int),
+                ("outer_stride", C.c_longlong), ("pos_stride", C.c_longlong)]
+
+
+_SIGS = {
+    "seb200_gemm": [C.POINTER(SebGemm), C.c_int, _fp],
+    "seb200_rms_pad": [_fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp],
+    "seb200_spec_to_in3": [_fp, C.c_int, C.c_int, C.c_int, _fp, _fp],
+    "seb200_in3_to_spec": [_fp, C.c_int, C.c_int, C.c_int, _fp, _fp],
+    "seb200_decompress_rows": [_fp, C.c_int, C.c_int, _fp, C.c_int, _fp],
+    "seb200_spec_decompress_rows": [_fp, C.c_int, C.c_int, C.c_int, _fp, C.c_int, _fp],
+    "seb200_overlap_add": [_fp, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, C.c_int, C.c_int, _fp],
+    "seb200_conv1x1_in3": [_fp, C.c_longlong, _fp, _fp, _fp, _fp],
+    "seb200_inorm_stats": [_fp, C.c_int, C.c_longlong, C.c_int, _fp, _fp, C.c_longlong, _fp],
+    "seb200_inorm_prelu": [_fp, C.c_int, C.c_longlong, C.c_int, _fp, _fp, _fp, _fp, _fp, _fp],
+    "seb200_mask_conv": [_fp, C.c_longlong, C.c_int, _fp, C.c_float, _fp, _fp],
+    "seb200_complex_conv": [_fp, C.c_int, C.c_longlong, C.c_int, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp],
+    "seb200_mask_recombine": [_fp, _fp, C.c_int, C.c_longlong, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
+                              C.c_float, _fp, _fp, _fp, _fp, _fp, _fp],
+    "seb200_split_ri": [_fp, C.c_longlong, _fp, _fp, _fp],
+    "seb200_attention": [_fp, _fp, C.POINTER(SebSeq), _fp, C.c_int, _fp],
+    "seb200_dwconv_bn_swish": [_fp, C.POINTER(SebSeq), _fp, _fp, _fp, _fp, _fp],
+    "seb200_layernorm_residual": [_fp, C.c_longlong, _fp, _fp, _fp, _fp, _fp],
+}
+EXPORTS = sorted(list(_SIGS) + ["seb200_inorm_workspace_bytes", "seb200_version", "seb200_last_error_string",
+                                "seb200_launch_count"])
+
+_lock = threading.Lock()
+_lib = None
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def load(build_if_missing: bool = True):
+    """dlopen libseb200.so (building it first if absent) and attach signatures."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(_LIB_PATH):
+            if not build_if_missing:
+                raise RuntimeError(f"{_LIB_PATH} is missing: run `python speech-enhancement_b200/build.py`")
+            from . import build as _build
+            _build.build()
+        lib = C.CDLL(_LIB_PATH)
+        for name, args in _SIGS.items():
+            fn = getattr(lib, name)
+            fn.argtypes = args
+            fn.restype = C.c_int
+        lib.seb200_inorm_workspace_bytes.argtypes = [C.c_int, C.c_longlong, C.c_int]
+        lib.seb200_inorm_workspace_bytes.restype = C.c_longlong
+        lib.seb200_version.restype = C.c_int
+        lib.seb200_last_error_string.restype = C.c_char_p
+        lib.seb200_launch_count.restype = C.c_longlong
+        _lib = lib
+        return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().seb200_last_error_string().decode(errors="replace")
+        kind = "argument error" if rc < 0 else "CUDA error"
+        raise RuntimeError(f"{what}: {kind} {rc}: {msg}")
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("se_b200 has no CPU path: tensors must live on a CUDA (sm_100a) device")
+
+
+def launch_count() -> int:
+    return int(load().seb200_launch_count())

@@ -1,0 +1,57 @@
+// common.cuh -- shared helpers for libseb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/seb200.h"
+
+namespace seb {
+
+// ---- error plumbing (never abort, never print: seb200.h conventions) ----------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define SEB_REQUIRE(cond, code, ...)            \
+  do {                                          \
+    if (!(cond)) {                              \
+      seb::set_error(__VA_ARGS__);              \
+      return (code);                            \
+    }                                           \
+  } while (0)
+
+#define SEB_CHECK_LAUNCH(name)                                                  \
+  do {                                                                          \
+    cudaError_t e__ = cudaGetLastError();                                       \
+    if (e__ != cudaSuccess) {                                                   \
+      seb::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));   \
+      return (int)e__;                                                          \
+    }                                                                           \
+    seb::count_launch();                                                        \
+  } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---- small device helpers -------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// fp32 -> (hi, lo) bf16 pair with hi + lo ~= x to ~2^-17 relative (round-to-nearest both)
+__device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+  float2 hf = __bfloat1622float2(h);
+  __nv_bfloat162 l = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
+  hi = *reinterpret_cast<uint32_t*>(&h);
+  lo = *reinterpret_cast<uint32_t*>(&l);
+}
+
+}  // namespace seb

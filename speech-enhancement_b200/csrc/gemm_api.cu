@@ -1,0 +1,108 @@
+// gemm_api.cu -- seb200_gemm: argument checking and dispatch onto the instantiated engine kernels.
+#include "gemm_engine.cuh"
+
+namespace seb {
+
+static GemmArgs to_args(const SebGemm* s) {
+  GemmArgs g;
+  for (int i = 0; i < 4; ++i) g.a[i] = s->a[i];
+  g.lda = s->lda; g.ln_g = s->ln_gamma; g.ln_b = s->ln_beta;
+  g.M = s->M; g.N = s->N; g.K = s->K;
+  g.B = s->B; g.T = s->T; g.Fin = s->Fin; g.Fout = s->Fout;
+  g.taps_t = s->taps_t; g.dil = s->dil; g.stride_f = s->stride_f; g.nslots = s->nslots;
+  g.bias = s->bias; g.out = s->out; g.ldo = s->ldo; g.resid = s->resid; g.ldr = s->ldr; g.alpha = s->alpha;
+  return g;
+}
+
+template <int LK, int EK>
+static int launch_simt(const SebGemm* s, const GemmArgs& g, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_simt_kernel<LK, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SIMT_SMEM);
+    if (e != cudaSuccess) { set_error("gemm simt: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    attr_done = true;
+  }
+  SEB_REQUIRE(s->w_simt && s->simt_npad % 64 == 0 && s->simt_npad >= s->N, SEB_EINVAL, "gemm simt: bad weight image");
+  dim3 grid((g.M + BM - 1) / BM, s->simt_npad / 64);
+  gemm_simt_kernel<LK, EK><<<grid, 256, SIMT_SMEM, st>>>(g, s->w_simt, s->simt_npad);
+  SEB_CHECK_LAUNCH("gemm_simt_kernel");
+  return 0;
+}
+
+template <int NT, int STAGES, int LK, int EK>
+static int launch_tc(const SebGemm* s, const GemmArgs& g, cudaStream_t st) {
+  static bool attr_done = false;
+  constexpr int SMEM = tc_smem_bytes<NT, STAGES>();
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<NT, STAGES, LK, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) { set_error("gemm tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    attr_done = true;
+  }
+  SEB_REQUIRE(s->w_tc && s->tc_ntile == NT && s->tc_ntiles >= 1 && s->tc_ntile * s->tc_ntiles >= s->N, SEB_EINVAL,
+              "gemm tc: weight image has n-tile %d x %d, kernel wants %d covering N=%d", s->tc_ntile, s->tc_ntiles, NT, s->N);
+  SEB_REQUIRE(aligned16(s->w_tc), SEB_EALIGN, "gemm tc: weight image not 16-byte aligned");
+  dim3 grid((g.M + BM - 1) / BM, s->tc_ntiles);
+  gemm_tc_kernel<NT, STAGES, LK, EK><<<grid, TC_THREADS, SMEM, st>>>(g, reinterpret_cast<const uint8_t*>(s->w_tc));
+  SEB_CHECK_LAUNCH("gemm_tc_kernel");
+  return 0;
+}
+
+}  // namespace seb
+
+using namespace seb;
+
+extern "C" int seb200_gemm(const SebGemm* s, int engine, void* stream) {
+  SEB_REQUIRE(s != nullptr, SEB_EINVAL, "gemm: null descriptor");
+  SEB_REQUIRE(s->M > 0 && s->N > 0 && s->K > 0 && s->K % BK == 0, SEB_EINVAL, "gemm: bad sizes M=%d N=%d K=%d", s->M, s->N, s->K);
+  SEB_REQUIRE(s->a[0] && s->out && aligned16(s->a[0]) && aligned16(s->out), SEB_EALIGN, "gemm: a/out null or unaligned");
+  SEB_REQUIRE(s->ldo % 2 == 0, SEB_EALIGN, "gemm: ldo must be even");
+  if (s->loader == SEB_LOAD_ROWS || s->loader == SEB_LOAD_ROWS_LN) {
+    SEB_REQUIRE(s->lda % 4 == 0 && s->lda >= s->K, SEB_EALIGN, "gemm: lda=%lld must be a multiple of 4 and >= K", s->lda);
+  }
+  if (s->loader == SEB_LOAD_ROWS_LN) {
+    SEB_REQUIRE(s->K == 64 && s->ln_gamma && s->ln_beta, SEB_EINVAL, "gemm: LayerNorm loader needs K == 64 and gamma/beta");
+  }
+  if (s->loader == SEB_LOAD_CONV) {
+    SEB_REQUIRE(s->nslots >= 1 && s->nslots <= 4 && (s->taps_t == 1 || s->taps_t == 2) && s->stride_f >= 1 && s->dil >= 1, SEB_EINVAL, "gemm: bad conv geometry");
+    SEB_REQUIRE(s->K == s->taps_t * 3 * s->nslots * 64, SEB_EINVAL, "gemm: conv K=%d != taps*slots*64", s->K);
+    SEB_REQUIRE((long long)s->B * s->T * s->Fout == s->M, SEB_EINVAL, "gemm: conv M != B*T*Fout");
+    for (int i = 0; i < s->nslots; ++i) SEB_REQUIRE(s->a[i] && aligned16(s->a[i]), SEB_EALIGN, "gemm: conv slot %d null/unaligned", i);
+  }
+  if (s->loader == SEB_LOAD_HANKEL) {
+    SEB_REQUIRE(s->Fin > 0 && s->Fin % 8 == 0 && s->Fin <= s->K && s->stride_f % 4 == 0 && s->lda % 4 == 0 && s->T > 0, SEB_EALIGN, "gemm: bad framing geometry");
+  }
+  if (s->epilogue == SEB_EPI_RESID) SEB_REQUIRE(s->resid && s->ldr % 4 == 0 && aligned16(s->resid), SEB_EALIGN, "gemm: residual null/unaligned");
+  if (s->epilogue != SEB_EPI_COMPRESS) SEB_REQUIRE(s->ldo % 4 == 0 || s->epilogue == SEB_EPI_GLU, SEB_EALIGN, "gemm: ldo must be a multiple of 4");
+
+  const GemmArgs g = to_args(s);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int key = s->loader * 16 + s->epilogue;
+  if (engine == SEB_ENGINE_SIMT) {
+    switch (key) {
+      case SEB_LOAD_HANKEL * 16 + SEB_EPI_COMPRESS: return launch_simt<SEB_LOAD_HANKEL, SEB_EPI_COMPRESS>(s, g, st);
+      case SEB_LOAD_ROWS * 16 + SEB_EPI_BIAS:       return launch_simt<SEB_LOAD_ROWS, SEB_EPI_BIAS>(s, g, st);
+      case SEB_LOAD_ROWS * 16 + SEB_EPI_RESID:      return launch_simt<SEB_LOAD_ROWS, SEB_EPI_RESID>(s, g, st);
+      case SEB_LOAD_CONV * 16 + SEB_EPI_BIAS:       return launch_simt<SEB_LOAD_CONV, SEB_EPI_BIAS>(s, g, st);
+      case SEB_LOAD_CONV * 16 + SEB_EPI_SUBPIXEL:   return launch_simt<SEB_LOAD_CONV, SEB_EPI_SUBPIXEL>(s, g, st);
+      case SEB_LOAD_ROWS_LN * 16 + SEB_EPI_SWISH:   return launch_simt<SEB_LOAD_ROWS_LN, SEB_EPI_SWISH>(s, g, st);
+      case SEB_LOAD_ROWS_LN * 16 + SEB_EPI_GLU:     return launch_simt<SEB_LOAD_ROWS_LN, SEB_EPI_GLU>(s, g, st);
+      case SEB_LOAD_ROWS_LN * 16 + SEB_EPI_BIAS:    return launch_simt<SEB_LOAD_ROWS_LN, SEB_EPI_BIAS>(s, g, st);
+      default: break;
+    }
+  } else if (engine == SEB_ENGINE_TCGEN05) {
+    const int nt = s->tc_ntile;
+    switch (key) {
+      case SEB_LOAD_HANKEL * 16 + SEB_EPI_COMPRESS: if (nt == 208) return launch_tc<208, 1, SEB_LOAD_HANKEL, SEB_EPI_COMPRESS>(s, g, st); break;
+      case SEB_LOAD_ROWS * 16 + SEB_EPI_BIAS:       if (nt == 208) return launch_tc<208, 1, SEB_LOAD_ROWS, SEB_EPI_BIAS>(s, g, st); break;
+      case SEB_LOAD_ROWS * 16 + SEB_EPI_RESID:      if (nt == 64)  return launch_tc<64, 2, SEB_LOAD_ROWS, SEB_EPI_RESID>(s, g, st); break;
+      case SEB_LOAD_CONV * 16 + SEB_EPI_BIAS:       if (nt == 64)  return launch_tc<64, 2, SEB_LOAD_CONV, SEB_EPI_BIAS>(s, g, st); break;
+      case SEB_LOAD_CONV * 16 + SEB_EPI_SUBPIXEL:   if (nt == 128) return launch_tc<128, 1, SEB_LOAD_CONV, SEB_EPI_SUBPIXEL>(s, g, st); break;
+      case SEB_LOAD_ROWS_LN * 16 + SEB_EPI_SWISH:   if (nt == 256) return launch_tc<256, 1, SEB_LOAD_ROWS_LN, SEB_EPI_SWISH>(s, g, st); break;
+      case SEB_LOAD_ROWS_LN * 16 + SEB_EPI_GLU:     if (nt == 256) return launch_tc<256, 1, SEB_LOAD_ROWS_LN, SEB_EPI_GLU>(s, g, st); break;
+      case SEB_LOAD_ROWS_LN * 16 + SEB_EPI_BIAS:    if (nt == 192) return launch_tc<192, 1, SEB_LOAD_ROWS_LN, SEB_EPI_BIAS>(s, g, st); break;
+      default: break;
+    }
+  }
+  set_error("gemm: loader %d / epilogue %d / engine %d / n-tile %d is not instantiated", s->loader, s->epilogue, engine, s->tc_ntile);
+  return SEB_EUNSUPPORTED;
+}

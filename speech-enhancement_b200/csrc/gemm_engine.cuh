@@ -1,0 +1,485 @@
+// gemm_engine.cuh -- the dense-contraction engine of libseb200.
+//
+//   C[M, N] = epilogue( loader(A)[M, K] * W[N, K]^T )
+//
+// Two main loops share the same operand loaders and epilogues:
+//   * gemm_tc_kernel   : tcgen05.mma (kind::f16, bf16 operands, fp32 TMEM accumulator).  fp32
+//                        activations are split on the fly into bf16 hi/lo and written to shared
+//                        memory in the UMMA K-major SWIZZLE_128B canonical layout by producer
+//                        warps; weights arrive pre-split / pre-swizzled by one cp.async.bulk
+//                        per stage.  3 MMAs per K-step (hi*hi, hi*lo, lo*hi) give ~2^-17
+//                        relative operand error ("BF16 3-product split").
+//   * gemm_simt_kernel : plain fp32 FFMA tiles.  Bit-for-bit independent of the tensor path;
+//                        used by tests to cross-check it and for the DFT where fp32 is needed.
+#pragma once
+#include "common.cuh"
+
+namespace seb {
+
+struct GemmArgs {
+  const float* a[4];
+  long long lda;
+  const float* ln_g;
+  const float* ln_b;
+  int M, N, K;
+  int B, T, Fin, Fout, taps_t, dil, stride_f, nslots;
+  const float* bias;
+  float* out;
+  long long ldo;
+  const float* resid;
+  long long ldr;
+  float alpha;
+};
+
+constexpr int BM = 128;   // rows (pixels / tokens / frames) per CTA tile
+constexpr int BK = 64;    // K chunk: 64 bf16 = one 128-byte swizzle row
+
+// -------------------------------------------------------------------------------------------
+// Loaders.  256 producer threads cover a 128 x 64 fp32 tile in 4 passes: thread (rloc = tid>>3,
+// sub = tid&7) loads 8 consecutive K values (32 bytes) of row pass*32 + rloc, so 8 adjacent
+// lanes read one 256-byte row segment (coalesced) and own a full row for LayerNorm.
+// -------------------------------------------------------------------------------------------
+template <int KIND> struct Loader;
+
+template <> struct Loader<SEB_LOAD_ROWS> {
+  struct Row { const float* p; };
+  __device__ static void init_row(const GemmArgs& g, int m, Row& r) {
+    r.p = (m < g.M) ? g.a[0] + (long long)m * g.lda : nullptr;
+  }
+  __device__ static void load(const GemmArgs& g, const Row& r, int kc, int sub, float (&v)[8]) {
+    if (r.p) {
+      const float* p = r.p + kc * BK + sub * 8;
+      float4 x = ldg4(p), y = ldg4(p + 4);
+      v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    }
+  }
+};
+
+// LayerNorm(64, eps 1e-5) fused into the load (PreNorm, conformer.py:63-71 and net[0] of the conv module)
+template <> struct Loader<SEB_LOAD_ROWS_LN> {
+  using Row = Loader<SEB_LOAD_ROWS>::Row;
+  __device__ static void init_row(const GemmArgs& g, int m, Row& r) { Loader<SEB_LOAD_ROWS>::init_row(g, m, r); }
+  __device__ static void load(const GemmArgs& g, const Row& r, int kc, int sub, float (&v)[8]) {
+    Loader<SEB_LOAD_ROWS>::load(g, r, kc, sub, v);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += v[i];
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    const float mean = s * (1.0f / 64.0f);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { v[i] -= mean; q += v[i] * v[i]; }
+    q += __shfl_xor_sync(0xffffffffu, q, 1);
+    q += __shfl_xor_sync(0xffffffffu, q, 2);
+    q += __shfl_xor_sync(0xffffffffu, q, 4);
+    const float rstd = 1.0f / sqrtf(q * (1.0f / 64.0f) + 1e-5f);
+    float4 g0 = ldg4(g.ln_g + sub * 8), g1 = ldg4(g.ln_g + sub * 8 + 4);
+    float4 b0 = ldg4(g.ln_b + sub * 8), b1 = ldg4(g.ln_b + sub * 8 + 4);
+    v[0] = v[0] * rstd * g0.x + b0.x; v[1] = v[1] * rstd * g0.y + b0.y;
+    v[2] = v[2] * rstd * g0.z + b0.z; v[3] = v[3] * rstd * g0.w + b0.w;
+    v[4] = v[4] * rstd * g1.x + b1.x; v[5] = v[5] * rstd * g1.y + b1.y;
+    v[6] = v[6] * rstd * g1.z + b1.z; v[7] = v[7] * rstd * g1.w + b1.w;
+  }
+};
+
+// Implicit-GEMM Conv2d on channels-last slots.  K order = (kt, kf, slot, 64 channels); the input
+// of dense layer i is the list of 64-channel tensors [out_{i-1}, ..., out_1, x] (generator.py:31)
+// addressed through g.a[slot] -- the concat is never materialised.
+template <> struct Loader<SEB_LOAD_CONV> {
+  struct Row { int b, t, f; };   // b < 0: row beyond M
+  __device__ static void init_row(const GemmArgs& g, int m, Row& r) {
+    if (m < g.M) {
+      int bt = m / g.Fout;
+      r.f = m - bt * g.Fout;
+      r.b = bt / g.T;
+      r.t = bt - r.b * g.T;
+    } else { r.b = -1; r.t = 0; r.f = 0; }
+  }
+  __device__ static void load(const GemmArgs& g, const Row& r, int kc, int sub, float (&v)[8]) {
+    const int tap = kc / g.nslots;
+    const int slot = kc - tap * g.nslots;
+    const int kt = (g.taps_t == 2) ? tap / 3 : 0;
+    const int kf = tap - kt * 3;
+    const int tt = r.t - (g.taps_t - 1 - kt) * g.dil;
+    const int ff = r.f * g.stride_f + kf - 1;
+    if (r.b >= 0 && tt >= 0 && ff >= 0 && ff < g.Fin) {
+      const float* p = g.a[slot] + (((long long)r.b * g.T + tt) * g.Fin + ff) * 64 + sub * 8;
+      float4 x = ldg4(p), y = ldg4(p + 4);
+      v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    }
+  }
+};
+
+// STFT framing: row (b, t) is the overlapping window xpad[b, t*hop : t*hop + n_fft] (no copy).
+// g.Fin = n_fft (400), g.stride_f = hop (100), g.T = frames per utterance, g.lda = samples per row of xpad.
+template <> struct Loader<SEB_LOAD_HANKEL> {
+  struct Row { const float* p; };
+  __device__ static void init_row(const GemmArgs& g, int m, Row& r) {
+    if (m < g.M) {
+      int b = m / g.T, t = m - b * g.T;
+      r.p = g.a[0] + (long long)b * g.lda + (long long)t * g.stride_f;
+    } else r.p = nullptr;
+  }
+  __device__ static void load(const GemmArgs& g, const Row& r, int kc, int sub, float (&v)[8]) {
+    const int k = kc * BK + sub * 8;
+    if (r.p && k < g.Fin) {
+      float4 x = ldg4(r.p + k), y = ldg4(r.p + k + 4);
+      v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    }
+  }
+};
+
+// -------------------------------------------------------------------------------------------
+// Epilogues: called with 4 consecutive output columns n..n+3 (n % 4 == 0) of row m.
+// -------------------------------------------------------------------------------------------
+template <int KIND> struct Epi;
+
+__device__ __forceinline__ float4 add_bias(const GemmArgs& g, int n, float4 v) {
+  if (g.bias) { float4 b = ldg4(g.bias + n); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
+  return v;
+}
+
+template <> struct Epi<SEB_EPI_BIAS> {
+  __device__ static void apply(const GemmArgs& g, int m, int n, float4 v) {
+    if (m >= g.M || n >= g.N) return;
+    if (n + 4 <= g.N) {
+      st4(g.out + (long long)m * g.ldo + n, add_bias(g, n, v));
+    } else {   // ragged tail (N % 4 != 0 never carries a bias on this path)
+      float t[4] = {v.x, v.y, v.z, v.w};
+      for (int i = 0; i < 4 && n + i < g.N; ++i) g.out[(long long)m * g.ldo + n + i] = t[i] + (g.bias ? g.bias[n + i] : 0.f);
+    }
+  }
+};
+
+template <> struct Epi<SEB_EPI_SWISH> {
+  __device__ static void apply(const GemmArgs& g, int m, int n, float4 v) {
+    if (m >= g.M || n >= g.N) return;
+    v = add_bias(g, n, v);
+    v.x *= sigmoidf_acc(v.x); v.y *= sigmoidf_acc(v.y); v.z *= sigmoidf_acc(v.z); v.w *= sigmoidf_acc(v.w);
+    st4(g.out + (long long)m * g.ldo + n, v);
+  }
+};
+
+template <> struct Epi<SEB_EPI_GLU> {   // packed columns: (value_j, gate_j) adjacent (conformer.py:36-37)
+  __device__ static void apply(const GemmArgs& g, int m, int n, float4 v) {
+    if (m >= g.M || n >= g.N) return;
+    v = add_bias(g, n, v);
+    float2 o = make_float2(v.x * sigmoidf_acc(v.y), v.z * sigmoidf_acc(v.w));
+    *reinterpret_cast<float2*>(g.out + (long long)m * g.ldo + (n >> 1)) = o;
+  }
+};
+
+template <> struct Epi<SEB_EPI_RESID> {
+  __device__ static void apply(const GemmArgs& g, int m, int n, float4 v) {
+    if (m >= g.M || n >= g.N) return;
+    v = add_bias(g, n, v);
+    float4 r = *reinterpret_cast<const float4*>(g.resid + (long long)m * g.ldr + n);
+    v.x = g.alpha * v.x + r.x; v.y = g.alpha * v.y + r.y; v.z = g.alpha * v.z + r.z; v.w = g.alpha * v.w + r.w;
+    st4(g.out + (long long)m * g.ldo + n, v);
+  }
+};
+
+template <> struct Epi<SEB_EPI_SUBPIXEL> {   // generator.py:88-91: out[b, c, t, 2w + r] = y[b, r*64 + c, t, w]
+  __device__ static void apply(const GemmArgs& g, int m, int n, float4 v) {
+    if (m >= g.M || n >= g.N) return;
+    v = add_bias(g, n, v);
+    const int bt = m / g.Fout, w = m - bt * g.Fout;
+    const int r = n >> 6, c = n & 63;
+    st4(g.out + (((long long)bt * (2 * g.Fout)) + 2 * w + r) * 64 + c, v);
+  }
+};
+
+template <> struct Epi<SEB_EPI_COMPRESS> {   // core/function.py:625-634 fused: columns are (re_k, im_k) pairs
+  __device__ static void one(float* o, float re, float im) {
+    const float m2 = re * re + im * im;
+    float magc = 0.f, s = 0.f;
+    if (m2 > 0.f) {
+      const float r = sqrtf(m2);
+      magc = powf(r, 0.3f);
+      s = magc / r;
+    }
+    o[0] = magc; o[1] = re * s; o[2] = im * s;
+  }
+  __device__ static void apply(const GemmArgs& g, int m, int n, float4 v) {
+    if (m >= g.M || n >= g.N) return;
+    float* o = g.out + (long long)m * g.ldo + (n >> 1) * 3;
+    one(o, v.x, v.y);
+    if (n + 2 < g.N) one(o + 3, v.z, v.w);
+  }
+};
+
+// -------------------------------------------------------------------------------------------
+// SIMT main loop (fp32 FFMA).  grid = (ceil(M/128), npad/64), 256 threads, 8x4 outputs / thread.
+// -------------------------------------------------------------------------------------------
+constexpr int SIMT_LDA = BM + 4;
+constexpr int SIMT_SMEM = (BK * SIMT_LDA + BK * 64) * (int)sizeof(float);
+
+template <int LK, int EK>
+__global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmArgs g, const float* __restrict__ w, int npad) {
+  extern __shared__ __align__(16) float smem_f[];
+  float (*As)[SIMT_LDA] = reinterpret_cast<float (*)[SIMT_LDA]>(smem_f);          // [k][m]
+  float (*Ws)[64] = reinterpret_cast<float (*)[64]>(smem_f + BK * SIMT_LDA);      // [k][n]
+  const int tid = threadIdx.x, sub = tid & 7, rloc = tid >> 3;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * 64;
+  typename Loader<LK>::Row rows[4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) Loader<LK>::init_row(g, m0 + p * 32 + rloc, rows[p]);
+  const int tm = tid >> 4, tn = tid & 15;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int nkc = g.K / BK;
+  for (int kc = 0; kc < nkc; ++kc) {
+    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      float v[8];
+      Loader<LK>::load(g, rows[p], kc, sub, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) As[sub * 8 + i][p * 32 + rloc] = v[i];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int idx = tid + j * 256, kr = idx >> 4, nc = (idx & 15) * 4;
+      *reinterpret_cast<float4*>(&Ws[kr][nc]) = ldg4(w + (long long)(kc * BK + kr) * npad + n0 + nc);
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < BK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[k][tm * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[k][tm * 8 + 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Ws[k][tn * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[i][0] = fmaf(a[i], b.x, acc[i][0]);
+        acc[i][1] = fmaf(a[i], b.y, acc[i][1]);
+        acc[i][2] = fmaf(a[i], b.z, acc[i][2]);
+        acc[i][3] = fmaf(a[i], b.w, acc[i][3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    Epi<EK>::apply(g, m0 + tm * 8 + i, n0 + tn * 4, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+}
+
+// -------------------------------------------------------------------------------------------
+// tcgen05 main loop
+// -------------------------------------------------------------------------------------------
+namespace ptx {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a launch error, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 1023u) == 0 && clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+// K-major, SWIZZLE_128B canonical operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);        // start address
+  d |= (uint64_t)1 << 16;                              // leading byte offset (unused for K-major swizzle)
+  d |= (uint64_t)(1024 >> 4) << 32;                    // stride byte offset
+  d |= (uint64_t)1 << 46;                              // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                              // SWIZZLE_128B
+  return d;
+}
+}  // namespace ptx
+
+constexpr int TC_THREADS = 320;        // 8 producer/epilogue warps + MMA warp + weight-copy warp
+constexpr int TC_A_BYTES = BM * 128;   // one bf16 plane of the A tile
+
+template <int NT> constexpr int tc_stage_bytes() { return 2 * TC_A_BYTES + 2 * NT * 128; }
+template <int NT, int STAGES> constexpr int tc_smem_bytes() { return STAGES * tc_stage_bytes<NT>() + 1024; }
+template <int NT> constexpr uint32_t tc_tmem_cols() { return NT <= 32 ? 32 : NT <= 64 ? 64 : NT <= 128 ? 128 : 256; }
+
+template <int NT, int STAGES, int LK, int EK>
+__global__ void __launch_bounds__(TC_THREADS, 2)
+gemm_tc_kernel(const GemmArgs g, const uint8_t* __restrict__ w_tc) {
+  static_assert(NT % 16 == 0 && NT >= 16 && NT <= 256, "UMMA M=128 needs N % 16 == 0, N <= 256");
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t smem_base = ptx::smem_u32(smem);
+  constexpr int STAGE = tc_stage_bytes<NT>();
+  constexpr uint32_t W_BYTES = NT * 128;
+  constexpr uint32_t TMEM_COLS = tc_tmem_cols<NT>();
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * BM;
+  const int ntile = blockIdx.y;
+  const int nkc = g.K / BK;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 256 + 1); ptx::mbar_init(&empty_bar[s], 1); }
+    ptx::mbar_init(&accum_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 8) ptx::tmem_alloc(&tmem_base_s, TMEM_COLS);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp < 8) {
+    // ---------------- producers: fp32 global -> bf16 hi/lo swizzled shared ----------------
+    const int sub = tid & 7, rloc = tid >> 3;
+    typename Loader<LK>::Row rows[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) Loader<LK>::init_row(g, m0 + p * 32 + rloc, rows[p]);
+    for (int kc = 0; kc < nkc; ++kc) {
+      const int s = kc % STAGES;
+      const uint32_t ph = (uint32_t)(kc / STAGES) & 1u;
+      ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
+      uint8_t* a_hi = smem + s * STAGE;
+      uint8_t* a_lo = a_hi + TC_A_BYTES;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        float v[8];
+        Loader<LK>::load(g, rows[p], kc, sub, v);
+        uint4 hi, lo;
+        split_bf16x2(v[0], v[1], hi.x, lo.x);
+        split_bf16x2(v[2], v[3], hi.y, lo.y);
+        split_bf16x2(v[4], v[5], hi.z, lo.z);
+        split_bf16x2(v[6], v[7], hi.w, lo.w);
+        const int r = p * 32 + rloc;
+        const int off = r * 128 + ((sub ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(a_hi + off) = hi;
+        *reinterpret_cast<uint4*>(a_lo + off) = lo;
+      }
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(&full_bar[s]);
+    }
+    // ---------------- epilogue: TMEM -> registers -> global ----------------
+    ptx::mbar_wait(&accum_bar, 0);
+    ptx::tc_fence_after();
+    const int row = (warp & 3) * 32 + lane;
+    const int half = warp >> 2;
+    constexpr int HALF_COLS = NT / 2;            // multiple of 8
+    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(half * HALF_COLS);
+#pragma unroll 1
+    for (int c = 0; c < HALF_COLS; c += 8) {
+      float v[8];
+      ptx::tmem_ld8(taddr + c, v);
+      const int n = ntile * NT + half * HALF_COLS + c;
+      Epi<EK>::apply(g, m0 + row, n, make_float4(v[0], v[1], v[2], v[3]));
+      Epi<EK>::apply(g, m0 + row, n + 4, make_float4(v[4], v[5], v[6], v[7]));
+    }
+    ptx::tc_fence_before();
+  } else if (warp == 8) {
+    // ---------------- MMA issuer (one thread) ----------------
+    if (lane == 0) {
+      constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      for (int kc = 0; kc < nkc; ++kc) {
+        const int s = kc % STAGES;
+        const uint32_t ph = (uint32_t)(kc / STAGES) & 1u;
+        ptx::mbar_wait(&full_bar[s], ph);
+        ptx::tc_fence_after();
+        const uint32_t base = smem_base + s * STAGE;
+        const uint64_t a_hi = ptx::umma_desc_sw128(base);
+        const uint64_t a_lo = ptx::umma_desc_sw128(base + TC_A_BYTES);
+        const uint64_t w_hi = ptx::umma_desc_sw128(base + 2 * TC_A_BYTES);
+        const uint64_t w_lo = ptx::umma_desc_sw128(base + 2 * TC_A_BYTES + W_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t ko = (uint64_t)((k * 32) >> 4);   // 16 bf16 = 32 bytes along K inside the swizzle row
+          ptx::mma_bf16(tmem_base, a_lo + ko, w_hi + ko, IDESC, (kc | k) ? 1u : 0u);
+          ptx::mma_bf16(tmem_base, a_hi + ko, w_lo + ko, IDESC, 1u);
+          ptx::mma_bf16(tmem_base, a_hi + ko, w_hi + ko, IDESC, 1u);
+        }
+        ptx::tc_commit(&empty_bar[s]);
+      }
+      ptx::tc_commit(&accum_bar);
+    }
+  } else {
+    // ---------------- weight stager: one bulk copy (hi|lo image) per stage ----------------
+    if (lane == 0) {
+      const uint8_t* src = w_tc + (size_t)ntile * nkc * (2 * W_BYTES);
+      for (int kc = 0; kc < nkc; ++kc) {
+        const int s = kc % STAGES;
+        const uint32_t ph = (uint32_t)(kc / STAGES) & 1u;
+        ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
+        ptx::mbar_arrive_expect_tx(&full_bar[s], 2 * W_BYTES);
+        ptx::bulk_g2s(smem_base + s * STAGE + 2 * TC_A_BYTES, src + (size_t)kc * (2 * W_BYTES), 2 * W_BYTES, &full_bar[s]);
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 8) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace seb

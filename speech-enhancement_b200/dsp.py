@@ -1,0 +1,98 @@
+"""Power-compressed STFT / iSTFT on the GEMM engine (drop-in for core/function.py:685-703).
+
+``compressed_stft(signal, n_fft, hop_length, window, comp_type='pow')`` and
+``uncompressed_istft(spec, n_fft, hop_length, window, comp_type='pow')`` keep the reference's
+names, argument order and tensor layouts (complex64 ``(B, n_fft/2+1, T)``).  The DFT is a dense
+contraction of the framed signal against a precomputed basis with the analysis window folded
+in; power compression is the GEMM epilogue; the inverse is the mirrored contraction followed by
+a deterministic gather overlap-add.  Only the reference's fixed configuration is supported:
+n_fft=400, hop=100, periodic Hamming window, comp_type='pow' (config/default.py:19-23).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import ops
+from ._lib import EPI_BIAS, EPI_COMPRESS, LOAD_HANKEL, LOAD_ROWS, require_cuda
+from .packing import dft_basis, hamming_periodic, idft_basis, inv_envelope, pack_weight
+
+N_FFT, HOP, N_BINS, LDZ = 400, 100, 201, 448
+
+_cache: Dict[tuple, object] = {}
+
+
+def _bases(device):
+    key = ("bases", str(device))
+    if key not in _cache:
+        _cache[key] = (pack_weight(dft_basis(N_FFT), 208).to(device), pack_weight(idft_basis(N_FFT), 208).to(device))
+    return _cache[key]
+
+
+def _inv_env(T: int, device):
+    key = ("env", str(device), T)
+    if key not in _cache:
+        _cache[key] = inv_envelope(T, N_FFT, HOP).to(device)
+    return _cache[key]
+
+
+def _check_cfg(n_fft, hop, window, comp_type):
+    if n_fft != N_FFT or hop != HOP or comp_type != "pow":
+        raise RuntimeError("se_b200 DSP kernels are specialised for n_fft=400, hop=100, comp_type='pow'")
+    if window is not None:
+        ref = hamming_periodic(N_FFT).to(torch.float32)
+        if window.numel() != N_FFT or not torch.allclose(window.detach().float().cpu(), ref, atol=1e-6):
+            raise RuntimeError("se_b200 DSP kernels fold the periodic Hamming window into the DFT basis; got a different window")
+
+
+def stft_in3(xpad: torch.Tensor, T: int, engine: Optional[str] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """xpad: [B, Lp + 400] reflect-padded signal -> in3 [B, T, 201, 3] = (|Y|, Re Y, Im Y), Y the compressed STFT."""
+    B = xpad.shape[0]
+    fwd, _ = _bases(xpad.device)
+    if out is None:
+        out = torch.empty(B, T, N_BINS, 3, device=xpad.device, dtype=torch.float32)
+    ops.gemm(loader=LOAD_HANKEL, epilogue=EPI_COMPRESS, M=B * T, N=2 * N_BINS, w=fwd, a=[xpad], lda=xpad.shape[1], out=out,
+             ldo=3 * N_BINS, engine=engine or ops.default_engine(),
+             conv=dict(B=B, T=T, Fin=N_FFT, Fout=0, stride_f=HOP))
+    return out
+
+
+def istft_rows(z: torch.Tensor, B: int, T: int, c: Optional[torch.Tensor], engine: Optional[str] = None) -> torch.Tensor:
+    """z: [B*T, 448] decompressed (re, im) rows -> waveform [B, 100*(T-1)] (divided by c[b] if given)."""
+    _, inv = _bases(z.device)
+    frames = torch.empty(B * T, N_FFT, device=z.device, dtype=torch.float32)
+    ops.gemm(loader=LOAD_ROWS, epilogue=EPI_BIAS, M=B * T, N=N_FFT, w=inv, a=[z], lda=LDZ, out=frames, ldo=N_FFT,
+             engine=engine or ops.default_engine())
+    out = torch.empty(B, HOP * (T - 1), device=z.device, dtype=torch.float32)
+    ops.overlap_add(frames, B, T, _inv_env(T, z.device), c, out)
+    return out
+
+
+def compressed_stft(signal: torch.Tensor, n_fft: int = N_FFT, hop_length: int = HOP, window: Optional[torch.Tensor] = None,
+                    comp_type: str = "pow", engine: Optional[str] = None) -> torch.Tensor:
+    """(B, L) fp32 CUDA -> complex64 (B, 201, L/100 + 1); core/function.py:685-693.  L must be a multiple of 100."""
+    require_cuda(signal)
+    _check_cfg(n_fft, hop_length, window, comp_type)
+    x = signal.to(torch.float32).contiguous()
+    if x.dim() == 1:
+        x = x.unsqueeze(0)
+    B, L = x.shape
+    if L % HOP != 0:
+        raise RuntimeError("signal length must be a multiple of hop (predict() pads it, inference_gan.py:83-87)")
+    xpad, _ = ops.rms_pad(x, L, normalize=False)
+    in3 = stft_in3(xpad, L // HOP + 1, engine)
+    return ops.in3_to_spec(in3)
+
+
+def uncompressed_istft(spec: torch.Tensor, n_fft: int = N_FFT, hop_length: int = HOP, window: Optional[torch.Tensor] = None,
+                       comp_type: str = "pow", engine: Optional[str] = None) -> torch.Tensor:
+    """complex64 (B, 201, T) CUDA -> (B, 100*(T-1)); core/function.py:695-703."""
+    require_cuda(spec)
+    _check_cfg(n_fft, hop_length, window, comp_type)
+    B, F, T = spec.shape
+    if F != N_BINS:
+        raise RuntimeError(f"expected {N_BINS} bins")
+    z = torch.empty(B * T, LDZ, device=spec.device, dtype=torch.float32)
+    ops.spec_decompress_rows(spec.to(torch.complex64), z)
+    return istft_rows(z, B, T, None, engine)

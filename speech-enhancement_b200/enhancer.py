@@ -1,0 +1,56 @@
+"""Wave -> wave enhancement with the semantics of the reference's ``predict()`` (inference_gan.py:75-100), batched.
+
+    enh = EnhancerB200(model)            # model: se_b200.TSCNet (weights loaded, on a CUDA device)
+    y = enh(noisy)                       # (B, L) fp32 CUDA -> (B, L)
+    y = enh.predict(noisy_numpy_1d)      # the reference's call shape: 1-D numpy in, 1-D numpy out
+
+Per utterance: c = sqrt(L / sum x^2); x*c; wrap-pad to a multiple of 100; compressed STFT; generator;
+decompress + iSTFT; /c; trim.  STFT, generator and iSTFT share buffers: the STFT epilogue writes the generator's
+3-channel input directly and the generator's output feeds the iDFT rows without a layout change.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import dsp, ops
+from .generator import TSCNet
+
+
+class EnhancerB200(nn.Module):
+    def __init__(self, model: TSCNet, n_fft: int = 400, hop: int = 100):
+        super().__init__()
+        if n_fft != dsp.N_FFT or hop != dsp.HOP:
+            raise ValueError("only the reference configuration N_FFT=400, HOP_SAMPLES=100 is implemented")
+        self.model = model
+        self.dft_engine = None      # None -> same engine as the model
+
+    @torch.no_grad()
+    def forward(self, noisy: torch.Tensor, stages=None) -> torch.Tensor:
+        if not noisy.is_cuda:
+            raise RuntimeError("EnhancerB200 has no CPU path: move the waveform to the GPU first")
+        x = noisy.to(torch.float32).contiguous()
+        if x.dim() == 1:
+            x = x.unsqueeze(0)
+        B, L = x.shape
+        Lp = int(math.ceil(L / dsp.HOP)) * dsp.HOP
+        T = Lp // dsp.HOP + 1
+        eng = self.dft_engine or self.model.engine
+        xpad, c = ops.rms_pad(x, Lp, normalize=True)
+        in3 = dsp.stft_in3(xpad, T, eng)
+        if stages is not None:
+            stages["in3"] = in3
+        est = self.model.forward_in3(in3, stages)
+        z = torch.empty(B * T, dsp.LDZ, device=x.device, dtype=torch.float32)
+        ops.decompress_rows(est, z)
+        y = dsp.istft_rows(z, B, T, c, eng)
+        return y[:, :L]
+
+    def predict(self, noisy_signal: np.ndarray) -> np.ndarray:
+        """inference_gan.predict(model, config, noisy_signal): 1-D numpy -> 1-D numpy of the same length."""
+        dev = next(self.model.parameters()).device
+        x = torch.from_numpy(np.ascontiguousarray(noisy_signal, dtype=np.float32)).to(dev)
+        return self.forward(x.unsqueeze(0))[0].cpu().numpy()

@@ -1,0 +1,376 @@
+"""Drop-in ``TSCNet`` for the SCP-GAN / CMGAN generator, running on libseb200 (sm_100a).
+
+Mirrors the reference's module interface for this path
+(/root/reference/models/generator.py:132-167):
+
+    TSCNet(num_channel=64, num_features=201).forward(x, diffusion_step=None) -> (final_real, final_imag)
+
+* same constructor arguments, same sub-module tree and therefore the same 359
+  ``state_dict`` keys / shapes / dtypes, so ``load_state_dict`` of a reference
+  checkpoint (after inference_gan.py:66-68 strips ``module.``) works unchanged;
+  ``conv.net.5`` is a real ``nn.BatchNorm1d`` so ``SyncBatchNorm.convert_sync_batchnorm``
+  (main_gan.py:154) still finds it.
+* ``forward`` takes the complex64 ``(B, 201, T)`` compressed spectrogram and returns two
+  fp32 ``(B, 1, T, 201)`` tensors, like the reference.
+
+The parameter-holding sub-modules below are containers only: all arithmetic is done by
+the CUDA kernels through ``ops`` in channels-last ``[B, T, F, C]`` fp32.  There is no
+CPU path and no PyTorch-eager fallback; non-CUDA input raises.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import (EPI_BIAS, EPI_GLU, EPI_RESID, EPI_SUBPIXEL, EPI_SWISH, LOAD_CONV, LOAD_ROWS, LOAD_ROWS_LN)
+from .packing import PackedWeight, conv_weight_matrix, glu_interleave, pack_weight
+
+
+# ---------------------------------------------------------------------------------------------
+# parameter containers (names follow the reference so the state_dict is identical)
+# ---------------------------------------------------------------------------------------------
+class _Bag(nn.Module):
+    """A nameable container; the kernels, not these modules, do the computing."""
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("sub-modules of the B200 TSCNet are parameter containers; call TSCNet.forward")
+
+
+def _dense_block(ch: int, depth: int = 4) -> _Bag:
+    """DilatedDenseNet parameters (generator.py:6-22)."""
+    blk = _Bag()
+    for i in range(1, depth + 1):
+        blk.add_module(f"conv{i}", nn.Conv2d(ch * i, ch, kernel_size=(2, 3), dilation=(2 ** (i - 1), 1)))
+        blk.add_module(f"norm{i}", nn.InstanceNorm2d(ch, affine=True))
+        blk.add_module(f"prelu{i}", nn.PReLU(ch))
+    return blk
+
+
+def _feed_forward(dim: int, mult: int, p_drop: float) -> _Bag:
+    """Scale(0.5, PreNorm(dim, FeedForward)) parameters (conformer.py:53-71,128-145) -> keys ``fn.fn.net.{0,3}``, ``fn.norm``."""
+    ff = _Bag()
+    ff.net = nn.Sequential(nn.Linear(dim, dim * mult), nn.Identity(), nn.Dropout(p_drop),
+                           nn.Linear(dim * mult, dim), nn.Dropout(p_drop))
+    pre = _Bag()
+    pre.fn = ff
+    pre.norm = nn.LayerNorm(dim)
+    scale = _Bag()
+    scale.fn = pre
+    return scale
+
+
+def _attention(dim: int, heads: int, dim_head: int, p_drop: float, max_pos: int = 512) -> _Bag:
+    """PreNorm(dim, Attention) parameters (conformer.py:74-94)."""
+    att = _Bag()
+    inner = heads * dim_head
+    att.to_q = nn.Linear(dim, inner, bias=False)
+    att.to_kv = nn.Linear(dim, inner * 2, bias=False)
+    att.to_out = nn.Linear(inner, dim)
+    att.rel_pos_emb = nn.Embedding(2 * max_pos + 1, dim_head)
+    att.dropout = nn.Dropout(p_drop)
+    pre = _Bag()
+    pre.fn = att
+    pre.norm = nn.LayerNorm(dim)
+    return pre
+
+
+def _conv_module(dim: int, expansion: int, ksize: int) -> _Bag:
+    """ConformerConvModule parameters (conformer.py:158-172) -> keys ``net.{0,2,4.conv,5,7}``."""
+    inner = dim * expansion
+    dw = _Bag()
+    dw.conv = nn.Conv1d(inner, inner, ksize, groups=inner)
+    mod = _Bag()
+    mod.net = nn.Sequential(nn.LayerNorm(dim), nn.Identity(), nn.Conv1d(dim, inner * 2, 1), nn.Identity(), dw,
+                            nn.BatchNorm1d(inner), nn.Identity(), nn.Conv1d(inner, dim, 1), nn.Identity(), nn.Dropout(0.0))
+    return mod
+
+
+def _conformer(dim: int) -> _Bag:
+    """ConformerBlock(dim, dim_head=dim//4, heads=4, conv_kernel_size=31, dropout 0.2) (generator.py:60-65)."""
+    blk = _Bag()
+    blk.ff1 = _feed_forward(dim, 4, 0.2)
+    blk.attn = _attention(dim, 4, dim // 4, 0.2)
+    blk.conv = _conv_module(dim, 2, 31)
+    blk.ff2 = _feed_forward(dim, 4, 0.2)
+    blk.post_norm = nn.LayerNorm(dim)
+    return blk
+
+
+def _sub_pixel(ch: int) -> _Bag:
+    sp = _Bag()
+    sp.conv = nn.Conv2d(ch, ch * 2, kernel_size=(1, 3), stride=(1, 1))
+    return sp
+
+
+class TSCNet(nn.Module):
+    def __init__(self, num_channel: int = 64, num_features: int = 201):
+        super().__init__()
+        if num_channel != 64:
+            raise ValueError("the sm_100a kernels are specialised for num_channel=64 (main_gan.py:145, inference_gan.py:61)")
+        ch = num_channel
+        enc = _Bag()
+        enc.conv_1 = nn.Sequential(nn.Conv2d(3, ch, (1, 1), (1, 1)), nn.InstanceNorm2d(ch, affine=True), nn.PReLU(ch))
+        enc.dilated_dense = _dense_block(ch)
+        enc.conv_2 = nn.Sequential(nn.Conv2d(ch, ch, (1, 3), (1, 2), padding=(0, 1)), nn.InstanceNorm2d(ch, affine=True), nn.PReLU(ch))
+        self.dense_encoder = enc
+        for i in range(1, 5):
+            blk = _Bag()
+            blk.time_conformer = _conformer(ch)
+            blk.freq_conformer = _conformer(ch)
+            self.add_module(f"TSCB_{i}", blk)
+        md = _Bag()
+        md.dense_block = _dense_block(ch)
+        md.sub_pixel = _sub_pixel(ch)
+        md.conv_1 = nn.Conv2d(ch, 1, (1, 2))
+        md.norm = nn.InstanceNorm2d(1, affine=True)
+        md.prelu = nn.PReLU(1)
+        md.final_conv = nn.Conv2d(1, 1, (1, 1))
+        md.prelu_out = nn.PReLU(num_features, init=-0.25)
+        self.mask_decoder = md
+        cd = _Bag()
+        cd.dense_block = _dense_block(ch)
+        cd.sub_pixel = _sub_pixel(ch)
+        cd.prelu = nn.PReLU(ch)
+        cd.norm = nn.InstanceNorm2d(ch, affine=True)
+        cd.conv = nn.Conv2d(ch, 2, (1, 2))
+        self.complex_decoder = cd
+
+        self.num_channel = ch
+        self.num_features = num_features
+        self.engine = ops.default_engine()     # "tcgen05" | "simt" main loop of the GEMM engine
+        self.attention_variant = 0             # 0 tensor-core, 1 SIMT cross-check
+        self._packed: Optional[Dict[str, object]] = None
+        self._packed_key = None
+        self._ws: Dict[tuple, Dict[str, torch.Tensor]] = {}
+
+    # -----------------------------------------------------------------------------------------
+    # weight packing (once per parameter version / device)
+    # -----------------------------------------------------------------------------------------
+    def _version_key(self):
+        dev = next(self.parameters()).device
+        return (str(dev), tuple(int(p._version) for p in self.parameters()), tuple(int(b._version) for b in self.buffers()))
+
+    def packed(self) -> Dict[str, object]:
+        key = self._version_key()
+        if self._packed is None or self._packed_key != key:
+            self._packed = self._pack(next(self.parameters()).device)
+            self._packed_key = key
+        return self._packed
+
+    def _pack(self, device) -> Dict[str, object]:
+        sd = {k: v.detach().to("cpu", torch.float32) if v.is_floating_point() else v.detach().cpu() for k, v in self.state_dict().items()}
+        P: Dict[str, object] = {}
+        dev = lambda t: t.contiguous().to(device)
+
+        def dense(prefix):
+            for i in range(1, 5):
+                P[f"{prefix}.conv{i}"] = pack_weight(conv_weight_matrix(sd[f"{prefix}.conv{i}.weight"]), 64, sd[f"{prefix}.conv{i}.bias"]).to(device)
+                for nm in ("norm", "prelu"):
+                    P[f"{prefix}.{nm}{i}.weight"] = dev(sd[f"{prefix}.{nm}{i}.weight"])
+                P[f"{prefix}.norm{i}.bias"] = dev(sd[f"{prefix}.norm{i}.bias"])
+
+        e = "dense_encoder"
+        P[f"{e}.conv_1.w"] = dev(sd[f"{e}.conv_1.0.weight"].reshape(64, 3))
+        P[f"{e}.conv_1.b"] = dev(sd[f"{e}.conv_1.0.bias"])
+        for k in ("conv_1.1.weight", "conv_1.1.bias", "conv_1.2.weight", "conv_2.1.weight", "conv_2.1.bias", "conv_2.2.weight"):
+            P[f"{e}.{k}"] = dev(sd[f"{e}.{k}"])
+        dense(f"{e}.dilated_dense")
+        P[f"{e}.conv_2"] = pack_weight(conv_weight_matrix(sd[f"{e}.conv_2.0.weight"]), 64, sd[f"{e}.conv_2.0.bias"]).to(device)
+
+        for i in range(1, 5):
+            for ax in ("time", "freq"):
+                p = f"TSCB_{i}.{ax}_conformer"
+                for ff in ("ff1", "ff2"):
+                    P[f"{p}.{ff}.w1"] = pack_weight(sd[f"{p}.{ff}.fn.fn.net.0.weight"], 256, sd[f"{p}.{ff}.fn.fn.net.0.bias"]).to(device)
+                    P[f"{p}.{ff}.w2"] = pack_weight(sd[f"{p}.{ff}.fn.fn.net.3.weight"], 64, sd[f"{p}.{ff}.fn.fn.net.3.bias"]).to(device)
+                    P[f"{p}.{ff}.ln"] = (dev(sd[f"{p}.{ff}.fn.norm.weight"]), dev(sd[f"{p}.{ff}.fn.norm.bias"]))
+                wqkv = torch.cat([sd[f"{p}.attn.fn.to_q.weight"], sd[f"{p}.attn.fn.to_kv.weight"]], dim=0)
+                P[f"{p}.attn.qkv"] = pack_weight(wqkv, 192, None).to(device)
+                P[f"{p}.attn.out"] = pack_weight(sd[f"{p}.attn.fn.to_out.weight"], 64, sd[f"{p}.attn.fn.to_out.bias"]).to(device)
+                P[f"{p}.attn.emb"] = dev(sd[f"{p}.attn.fn.rel_pos_emb.weight"])
+                P[f"{p}.attn.ln"] = (dev(sd[f"{p}.attn.norm.weight"]), dev(sd[f"{p}.attn.norm.bias"]))
+                P[f"{p}.conv.ln"] = (dev(sd[f"{p}.conv.net.0.weight"]), dev(sd[f"{p}.conv.net.0.bias"]))
+                w1, b1 = glu_interleave(sd[f"{p}.conv.net.2.weight"].squeeze(-1), sd[f"{p}.conv.net.2.bias"])
+                P[f"{p}.conv.pw1"] = pack_weight(w1, 256, b1).to(device)
+                P[f"{p}.conv.dw"] = dev(sd[f"{p}.conv.net.4.conv.weight"].squeeze(1).t())          # [31][128] tap-major
+                # BatchNorm1d(eval) folded with the depthwise bias: y = scale * conv + shift  (conformer.py:167)
+                scale = sd[f"{p}.conv.net.5.weight"] / torch.sqrt(sd[f"{p}.conv.net.5.running_var"] + 1e-5)
+                shift = sd[f"{p}.conv.net.5.bias"] + (sd[f"{p}.conv.net.4.conv.bias"] - sd[f"{p}.conv.net.5.running_mean"]) * scale
+                P[f"{p}.conv.bn"] = (dev(scale), dev(shift))
+                P[f"{p}.conv.pw2"] = pack_weight(sd[f"{p}.conv.net.7.weight"].squeeze(-1), 64, sd[f"{p}.conv.net.7.bias"]).to(device)
+                P[f"{p}.post_norm"] = (dev(sd[f"{p}.post_norm.weight"]), dev(sd[f"{p}.post_norm.bias"]))
+
+        for d in ("mask_decoder", "complex_decoder"):
+            dense(f"{d}.dense_block")
+            P[f"{d}.sub_pixel"] = pack_weight(conv_weight_matrix(sd[f"{d}.sub_pixel.conv.weight"]), 128, sd[f"{d}.sub_pixel.conv.bias"]).to(device)
+        m = "mask_decoder"
+        P[f"{m}.conv_1.w"] = dev(sd[f"{m}.conv_1.weight"][0, :, 0, :].t())                           # [2 taps][64]
+        P[f"{m}.scalars"] = (float(sd[f"{m}.conv_1.bias"][0]), float(sd[f"{m}.norm.weight"][0]), float(sd[f"{m}.norm.bias"][0]),
+                             float(sd[f"{m}.prelu.weight"][0]), float(sd[f"{m}.final_conv.weight"].reshape(-1)[0]),
+                             float(sd[f"{m}.final_conv.bias"][0]))
+        P[f"{m}.prelu_out"] = dev(sd[f"{m}.prelu_out.weight"])
+        c = "complex_decoder"
+        for k in ("prelu.weight", "norm.weight", "norm.bias", "conv.bias"):
+            P[f"{c}.{k}"] = dev(sd[f"{c}.{k}"])
+        P[f"{c}.conv.w"] = dev(sd[f"{c}.conv.weight"][:, :, 0, :].permute(0, 2, 1))                   # [2 out][2 taps][64]
+        return P
+
+    # -----------------------------------------------------------------------------------------
+    # workspaces: one set of activation buffers per (device, B, T), reused across calls
+    # -----------------------------------------------------------------------------------------
+    def workspace(self, B: int, T: int, device) -> Dict[str, torch.Tensor]:
+        key = (str(device), B, T)
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        F, Fh = self.num_features, (self.num_features - 1) // 2 + 1
+        P, Ph = B * T * F, B * T * Fh
+        f32 = dict(device=device, dtype=torch.float32)
+        ws = {
+            # encoder @F=201: conv_1 output + 4 dense outputs + raw conv output
+            "enc": [torch.empty(P, 64, **f32) for _ in range(5)], "enc_raw": torch.empty(P, 64, **f32),
+            # decoders @F=101: 4 dense outputs + raw, sub-pixel output @F=202
+            "dec": [torch.empty(Ph, 64, **f32) for _ in range(4)], "dec_raw": torch.empty(Ph, 64, **f32),
+            "sp": torch.empty(B * T * 2 * Fh, 64, **f32),
+            # conformer token buffers
+            "x": torch.empty(Ph, 64, **f32), "y": torch.empty(Ph, 64, **f32), "h": torch.empty(Ph, 256, **f32),
+            "qkv": torch.empty(Ph, 192, **f32), "o": torch.empty(Ph, 64, **f32),
+            "u": torch.empty(Ph, 128, **f32), "v": torch.empty(Ph, 128, **f32),
+            # heads
+            "mask_raw": torch.empty(B * T, F, **f32), "cplx": torch.empty(B * T, F, 2, **f32), "est": torch.empty(B * T, F, 2, **f32),
+            "stats": torch.empty(B, 64, 2, **f32), "stats1": torch.empty(B, 1, 2, **f32),
+            "in_ws": ops.inorm_workspace(B, T * 2 * Fh, 64, device),
+        }
+        if len(self._ws) > 4:          # keep the cache small: shapes change rarely in inference
+            self._ws.clear()
+        self._ws[key] = ws
+        return ws
+
+    # -----------------------------------------------------------------------------------------
+    # building blocks
+    # -----------------------------------------------------------------------------------------
+    def _inorm_prelu(self, ws, raw, B, pix_per_b, gamma, beta, slope, out):
+        ops.inorm_stats(raw, B, pix_per_b, 64, ws["stats"], ws["in_ws"])
+        ops.inorm_prelu(raw, B, pix_per_b, ws["stats"], gamma, beta, slope, out)
+        return out
+
+    def _dense(self, P, prefix, ws, x0, outs, raw, B, T, F):
+        """DilatedDenseNet.forward (generator.py:24-32): layer i reads [out_{i-1}, ..., out_1, x0] through slot pointers."""
+        slots = [x0]
+        for i in range(1, 5):
+            w: PackedWeight = P[f"{prefix}.conv{i}"]
+            ops.gemm(loader=LOAD_CONV, epilogue=EPI_BIAS, M=B * T * F, w=w, a=slots, out=raw, ldo=64, engine=self.engine,
+                     conv=dict(B=B, T=T, Fin=F, Fout=F, taps_t=2, dil=2 ** (i - 1), stride_f=1, nslots=i))
+            self._inorm_prelu(ws, raw, B, T * F, P[f"{prefix}.norm{i}.weight"], P[f"{prefix}.norm{i}.bias"], P[f"{prefix}.prelu{i}.weight"], outs[i - 1])
+            slots = [outs[i - 1]] + slots
+        return outs[3]
+
+    def _conformer(self, P, p, ws, x, seq, M):
+        """ConformerBlock.forward + the TSCB outer residual (conformer.py:206-212, generator.py:70,72); x updated in place."""
+        eng = self.engine
+        y, h, qkv, o, u, v = ws["y"], ws["h"], ws["qkv"], ws["o"], ws["u"], ws["v"]
+        # y = x + 0.5 * FF1(LN(x))
+        ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_SWISH, M=M, w=P[f"{p}.ff1.w1"], a=[x], lda=64, ln=P[f"{p}.ff1.ln"], out=h, ldo=256, engine=eng)
+        ops.gemm(loader=LOAD_ROWS, epilogue=EPI_RESID, M=M, w=P[f"{p}.ff1.w2"], a=[h], lda=256, out=y, ldo=64, resid=x, ldr=64, alpha=0.5, engine=eng)
+        # y += Attn(LN(y))
+        ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_BIAS, M=M, w=P[f"{p}.attn.qkv"], a=[y], lda=64, ln=P[f"{p}.attn.ln"], out=qkv, ldo=192, engine=eng)
+        ops.attention(qkv, P[f"{p}.attn.emb"], seq, o, self.attention_variant)
+        ops.gemm(loader=LOAD_ROWS, epilogue=EPI_RESID, M=M, w=P[f"{p}.attn.out"], a=[o], lda=64, out=y, ldo=64, resid=y, ldr=64, alpha=1.0, engine=eng)
+        # y += ConvModule(y)
+        ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_GLU, M=M, w=P[f"{p}.conv.pw1"], a=[y], lda=64, ln=P[f"{p}.conv.ln"], out=u, ldo=128, engine=eng)
+        ops.dwconv_bn_swish(u, seq, P[f"{p}.conv.dw"], P[f"{p}.conv.bn"][0], P[f"{p}.conv.bn"][1], v)
+        ops.gemm(loader=LOAD_ROWS, epilogue=EPI_RESID, M=M, w=P[f"{p}.conv.pw2"], a=[v], lda=128, out=y, ldo=64, resid=y, ldr=64, alpha=1.0, engine=eng)
+        # y += 0.5 * FF2(LN(y))
+        ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_SWISH, M=M, w=P[f"{p}.ff2.w1"], a=[y], lda=64, ln=P[f"{p}.ff2.ln"], out=h, ldo=256, engine=eng)
+        ops.gemm(loader=LOAD_ROWS, epilogue=EPI_RESID, M=M, w=P[f"{p}.ff2.w2"], a=[h], lda=256, out=y, ldo=64, resid=y, ldr=64, alpha=0.5, engine=eng)
+        # x = post_norm(y) + x
+        ops.layernorm_residual(y, P[f"{p}.post_norm"][0], P[f"{p}.post_norm"][1], x, x)
+        return x
+
+    # -----------------------------------------------------------------------------------------
+    # forward
+    # -----------------------------------------------------------------------------------------
+    def forward_in3(self, in3: torch.Tensor, stages: Optional[dict] = None) -> torch.Tensor:
+        """in3: [B, T, F, 3] = (|Y|, Re Y, Im Y) of the compressed spectrogram -> est [B*T, F, 2] (workspace tensor)."""
+        if self.training and torch.is_grad_enabled():
+            raise RuntimeError("the B200 TSCNet implements the inference forward (eval / no_grad); the training step is a later row (SURVEY 8f)")
+        B, T, F, _ = in3.shape
+        if F != self.num_features or F % 2 == 0:
+            raise RuntimeError(f"expected {self.num_features} frequency bins, got {F}")
+        Fh = (F - 1) // 2 + 1
+        dev = in3.device
+        P = self.packed()
+        ws = self.workspace(B, T, dev)
+        eng = self.engine
+        e = "dense_encoder"
+
+        # ---- DenseEncoder (generator.py:50-54)
+        enc, raw = ws["enc"], ws["enc_raw"]
+        ops.conv1x1_in3(in3, P[f"{e}.conv_1.w"], P[f"{e}.conv_1.b"], raw)
+        self._inorm_prelu(ws, raw, B, T * F, P[f"{e}.conv_1.1.weight"], P[f"{e}.conv_1.1.bias"], P[f"{e}.conv_1.2.weight"], enc[0])
+        d4 = self._dense(P, f"{e}.dilated_dense", ws, enc[0], enc[1:5], raw, B, T, F)
+        rawh = ws["dec_raw"]
+        ops.gemm(loader=LOAD_CONV, epilogue=EPI_BIAS, M=B * T * Fh, w=P[f"{e}.conv_2"], a=[d4], out=rawh, ldo=64, engine=eng,
+                 conv=dict(B=B, T=T, Fin=F, Fout=Fh, taps_t=1, dil=1, stride_f=2, nslots=1))
+        x = ws["x"]
+        self._inorm_prelu(ws, rawh, B, T * Fh, P[f"{e}.conv_2.1.weight"], P[f"{e}.conv_2.1.bias"], P[f"{e}.conv_2.2.weight"], x)
+        if stages is not None:
+            stages["encoder"] = x.view(B, T, Fh, 64).clone()
+
+        # ---- 4 x TSCB (generator.py:67-74)
+        M = B * T * Fh
+        seq_t = ops.make_seq(B * Fh, T, Fh, T * Fh, Fh)
+        seq_f = ops.make_seq(B * T, Fh, 1, Fh, 1)
+        for i in range(1, 5):
+            self._conformer(P, f"TSCB_{i}.time_conformer", ws, x, seq_t, M)
+            self._conformer(P, f"TSCB_{i}.freq_conformer", ws, x, seq_f, M)
+            if stages is not None:
+                stages[f"tscb{i}"] = x.view(B, T, Fh, 64).clone()
+
+        # ---- MaskDecoder (generator.py:106-112)
+        m = "mask_decoder"
+        dec, sp = ws["dec"], ws["sp"]
+        d4 = self._dense(P, f"{m}.dense_block", ws, x, dec, rawh, B, T, Fh)
+        ops.gemm(loader=LOAD_CONV, epilogue=EPI_SUBPIXEL, M=M, w=P[f"{m}.sub_pixel"], a=[d4], out=sp, ldo=64, engine=eng,
+                 conv=dict(B=B, T=T, Fin=Fh, Fout=Fh, taps_t=1, dil=1, stride_f=1, nslots=1))
+        b1, g_in, b_in, s1, wf, bf = P[f"{m}.scalars"]
+        ops.mask_conv(sp, B * T, 2 * Fh, P[f"{m}.conv_1.w"], b1, ws["mask_raw"])
+        ops.inorm_stats(ws["mask_raw"], B, T * F, 1, ws["stats1"], ws["in_ws"])
+
+        # ---- ComplexDecoder (generator.py:124-129)
+        c = "complex_decoder"
+        d4 = self._dense(P, f"{c}.dense_block", ws, x, dec, rawh, B, T, Fh)
+        ops.gemm(loader=LOAD_CONV, epilogue=EPI_SUBPIXEL, M=M, w=P[f"{c}.sub_pixel"], a=[d4], out=sp, ldo=64, engine=eng,
+                 conv=dict(B=B, T=T, Fin=Fh, Fout=Fh, taps_t=1, dil=1, stride_f=1, nslots=1))
+        ops.inorm_stats(sp, B, T * 2 * Fh, 64, ws["stats"], ws["in_ws"])
+        ops.complex_conv(sp, B, T, 2 * Fh, ws["stats"], P[f"{c}.norm.weight"], P[f"{c}.norm.bias"], P[f"{c}.prelu.weight"],
+                         P[f"{c}.conv.w"], P[f"{c}.conv.bias"], ws["cplx"])
+
+        # ---- mask tail + recombination (generator.py:110-112,158-165)
+        mask_out = None
+        if stages is not None:
+            mask_out = torch.empty(B, T, F, device=dev, dtype=torch.float32)
+            stages["complex"] = ws["cplx"].view(B, T, F, 2).clone()
+        ops.mask_recombine(ws["mask_raw"], ws["stats1"], B, T, F, (g_in, b_in, s1, wf, bf), P[f"{m}.prelu_out"], in3, ws["cplx"],
+                           ws["est"], mask_out)
+        if stages is not None:
+            stages["mask"] = mask_out
+        return ws["est"]
+
+    def forward(self, x: torch.Tensor, diffusion_step=None):
+        """x: complex64 (B, num_features, T) compressed spectrogram -> (final_real, final_imag), each fp32 (B, 1, T, F)."""
+        if not x.is_cuda:
+            raise RuntimeError("se_b200.TSCNet has no CPU path: input must be a CUDA tensor on an sm_100a device")
+        if not x.is_complex():
+            raise RuntimeError("TSCNet.forward expects the complex compressed spectrogram (B, F, T)")
+        with torch.no_grad():
+            B, F, T = x.shape
+            in3 = ops.spec_to_in3(x.to(torch.complex64))
+            est = self.forward_in3(in3)
+            fr = torch.empty(B, 1, T, F, device=x.device, dtype=torch.float32)
+            fi = torch.empty(B, 1, T, F, device=x.device, dtype=torch.float32)
+            ops.split_ri(est, fr, fi)
+        return fr, fi

@@ -1,0 +1,190 @@
+"""Tensor-level wrappers over the C ABI (one function per exported kernel).
+
+These are the only places where torch tensors meet ``libseb200.so``: every
+wrapper checks device/dtype/contiguity, passes raw pointers plus the current
+CUDA stream, and turns a non-zero return code into ``RuntimeError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import (ENGINE_SIMT, ENGINE_TCGEN05, EPI_BIAS, EPI_COMPRESS, EPI_GLU, EPI_RESID, EPI_SUBPIXEL, EPI_SWISH,
+                   LOAD_CONV, LOAD_HANKEL, LOAD_ROWS, LOAD_ROWS_LN, SebGemm, SebSeq, check, ptr, require_cuda, stream_ptr)
+from .packing import PackedWeight
+
+ENGINES = {"tcgen05": ENGINE_TCGEN05, "simt": ENGINE_SIMT}
+
+
+def default_engine() -> str:
+    return os.environ.get("SEB200_ENGINE", "tcgen05")
+
+
+def _f32c(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise RuntimeError(f"expected contiguous float32 tensors, got {t.dtype} contiguous={t.is_contiguous()}")
+    require_cuda(*ts)
+
+
+def gemm(*, loader: int, epilogue: int, M: int, w: PackedWeight, a: Sequence[torch.Tensor], out: torch.Tensor,
+         ldo: int, N: Optional[int] = None, lda: int = 0, ln: Optional[tuple] = None, conv: Optional[dict] = None,
+         resid: Optional[torch.Tensor] = None, ldr: int = 0, alpha: float = 1.0, engine: str = "tcgen05"):
+    """One launch of the GEMM engine (see include/seb200.h: SebGemm)."""
+    lib = _lib.load()
+    _f32c(out, resid, *a)
+    g = SebGemm()
+    g.loader, g.epilogue = loader, epilogue
+    g.M, g.N, g.K = M, (w.N if N is None else N), w.K
+    for i in range(4):
+        g.a[i] = ptr(a[i]) if i < len(a) else 0
+    g.lda = lda
+    if ln is not None:
+        g.ln_gamma, g.ln_beta = ptr(ln[0]), ptr(ln[1])
+    if conv is not None:
+        g.B, g.T, g.Fin, g.Fout = conv["B"], conv["T"], conv["Fin"], conv["Fout"]
+        g.taps_t, g.dil, g.stride_f, g.nslots = conv.get("taps_t", 1), conv.get("dil", 1), conv.get("stride_f", 1), conv.get("nslots", 1)
+    g.w_tc, g.tc_ntile, g.tc_ntiles = ptr(w.w_tc), w.tc_ntile, w.tc_ntiles
+    g.w_simt, g.simt_npad = ptr(w.w_simt), w.simt_npad
+    g.bias = ptr(w.bias)
+    g.out, g.ldo = ptr(out), ldo
+    g.resid, g.ldr, g.alpha = ptr(resid), ldr, alpha
+    check(lib.seb200_gemm(C.byref(g), ENGINES[engine], stream_ptr()), "seb200_gemm")
+    return out
+
+
+def rms_pad(wave: torch.Tensor, Lp: int, normalize: bool = True):
+    _f32c(wave)
+    B, L = wave.shape
+    xpad = torch.empty(B, Lp + 400, device=wave.device, dtype=torch.float32)
+    c = torch.empty(B, device=wave.device, dtype=torch.float32)
+    check(_lib.load().seb200_rms_pad(ptr(wave), B, L, Lp, int(normalize), ptr(xpad), ptr(c), stream_ptr()), "seb200_rms_pad")
+    return xpad, c
+
+
+def spec_to_in3(spec: torch.Tensor, out: Optional[torch.Tensor] = None):
+    """complex64 (B, F, T) -> in3 [B, T, F, 3]."""
+    require_cuda(spec)
+    if spec.dtype != torch.complex64:
+        raise RuntimeError("spectrogram must be complex64")
+    sr = torch.view_as_real(spec.contiguous())
+    B, F, T = spec.shape
+    if out is None:
+        out = torch.empty(B, T, F, 3, device=spec.device, dtype=torch.float32)
+    check(_lib.load().seb200_spec_to_in3(ptr(sr), B, F, T, ptr(out), stream_ptr()), "seb200_spec_to_in3")
+    return out
+
+
+def in3_to_spec(in3: torch.Tensor):
+    _f32c(in3)
+    B, T, F, _ = in3.shape
+    out = torch.empty(B, F, T, 2, device=in3.device, dtype=torch.float32)
+    check(_lib.load().seb200_in3_to_spec(ptr(in3), B, F, T, ptr(out), stream_ptr()), "seb200_in3_to_spec")
+    return torch.view_as_complex(out)
+
+
+def decompress_rows(est: torch.Tensor, z: torch.Tensor):
+    _f32c(est, z)
+    rows, F = est.shape[0] * est.shape[1], est.shape[2]
+    check(_lib.load().seb200_decompress_rows(ptr(est), rows, F, ptr(z), z.shape[-1], stream_ptr()), "seb200_decompress_rows")
+    return z
+
+
+def spec_decompress_rows(spec: torch.Tensor, z: torch.Tensor):
+    require_cuda(spec)
+    sr = torch.view_as_real(spec.contiguous())
+    B, F, T = spec.shape
+    check(_lib.load().seb200_spec_decompress_rows(ptr(sr), B, F, T, ptr(z), z.shape[-1], stream_ptr()), "seb200_spec_decompress_rows")
+    return z
+
+
+def overlap_add(frames: torch.Tensor, B: int, T: int, inv_env: torch.Tensor, c: Optional[torch.Tensor], out: torch.Tensor):
+    _f32c(frames, inv_env, c, out)
+    Lout = 100 * (T - 1)
+    check(_lib.load().seb200_overlap_add(ptr(frames), B, T, frames.shape[-1], ptr(inv_env), ptr(c), ptr(out), Lout,
+                                         out.shape[-1], stream_ptr()), "seb200_overlap_add")
+    return out
+
+
+def conv1x1_in3(in3, w, bias, out):
+    _f32c(in3, w, bias, out)
+    pixels = in3.numel() // 3
+    check(_lib.load().seb200_conv1x1_in3(ptr(in3), pixels, ptr(w), ptr(bias), ptr(out), stream_ptr()), "seb200_conv1x1_in3")
+    return out
+
+
+def inorm_workspace(B: int, pix_per_b: int, C_: int, device) -> torch.Tensor:
+    nbytes = _lib.load().seb200_inorm_workspace_bytes(B, pix_per_b, C_)
+    return torch.empty((nbytes + 7) // 8, device=device, dtype=torch.float64)
+
+
+def inorm_stats(x, B: int, pix_per_b: int, C_: int, stats, workspace):
+    _f32c(x, stats)
+    check(_lib.load().seb200_inorm_stats(ptr(x), B, pix_per_b, C_, ptr(stats), ptr(workspace), workspace.numel() * 8,
+                                         stream_ptr()), "seb200_inorm_stats")
+    return stats
+
+
+def inorm_prelu(x, B: int, pix_per_b: int, stats, gamma, beta, slope, y):
+    _f32c(x, stats, gamma, beta, slope, y)
+    check(_lib.load().seb200_inorm_prelu(ptr(x), B, pix_per_b, 64, ptr(stats), ptr(gamma), ptr(beta), ptr(slope), ptr(y),
+                                         stream_ptr()), "seb200_inorm_prelu")
+    return y
+
+
+def mask_conv(x, rows: int, Fin: int, w, bias: float, out):
+    _f32c(x, w, out)
+    check(_lib.load().seb200_mask_conv(ptr(x), rows, Fin, ptr(w), float(bias), ptr(out), stream_ptr()), "seb200_mask_conv")
+    return out
+
+
+def complex_conv(x, B: int, rows_per_b: int, Fin: int, stats, gamma, beta, slope, w, bias, out):
+    _f32c(x, stats, gamma, beta, slope, w, bias, out)
+    check(_lib.load().seb200_complex_conv(ptr(x), B, rows_per_b, Fin, ptr(stats), ptr(gamma), ptr(beta), ptr(slope), ptr(w),
+                                          ptr(bias), ptr(out), stream_ptr()), "seb200_complex_conv")
+    return out
+
+
+def mask_recombine(mask_raw, mask_stats, B: int, rows_per_b: int, F: int, scalars, slope_f, in3, cplx, est, mask_out=None):
+    _f32c(mask_raw, mask_stats, slope_f, in3, cplx, est, mask_out)
+    g, b, s1, wf, bf = (float(v) for v in scalars)
+    check(_lib.load().seb200_mask_recombine(ptr(mask_raw), ptr(mask_stats), B, rows_per_b, F, g, b, s1, wf, bf, ptr(slope_f),
+                                            ptr(in3), ptr(cplx), ptr(est), ptr(mask_out), stream_ptr()), "seb200_mask_recombine")
+    return est
+
+
+def split_ri(est, re, im):
+    _f32c(est, re, im)
+    check(_lib.load().seb200_split_ri(ptr(est), est.numel() // 2, ptr(re), ptr(im), stream_ptr()), "seb200_split_ri")
+
+
+def make_seq(nseq: int, n: int, inner: int, outer_stride: int, pos_stride: int) -> SebSeq:
+    s = SebSeq()
+    s.nseq, s.n, s.inner, s.outer_stride, s.pos_stride = nseq, n, inner, outer_stride, pos_stride
+    return s
+
+
+def attention(qkv, rel_pos_emb, seq: SebSeq, out, variant: int = 0):
+    _f32c(qkv, rel_pos_emb, out)
+    check(_lib.load().seb200_attention(ptr(qkv), ptr(rel_pos_emb), C.byref(seq), ptr(out), variant, stream_ptr()), "seb200_attention")
+    return out
+
+
+def dwconv_bn_swish(x, seq: SebSeq, w, bn_scale, bn_shift, y):
+    _f32c(x, w, bn_scale, bn_shift, y)
+    check(_lib.load().seb200_dwconv_bn_swish(ptr(x), C.byref(seq), ptr(w), ptr(bn_scale), ptr(bn_shift), ptr(y), stream_ptr()),
+          "seb200_dwconv_bn_swish")
+    return y
+
+
+def layernorm_residual(x, gamma, beta, resid, out):
+    _f32c(x, gamma, beta, resid, out)
+    check(_lib.load().seb200_layernorm_residual(ptr(x), x.numel() // 64, ptr(gamma), ptr(beta), ptr(resid), ptr(out), stream_ptr()),
+          "seb200_layernorm_residual")
+    return out

@@ -1,0 +1,163 @@
+"""CPU: host-side logic -- state-dict contract, weight packing, the C-ABI surface, error behaviour, sharding."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from conftest import ROOT, rel_max
+from oracle import tscnet_oracle as O, weights
+
+import se_b200
+from se_b200 import packing
+
+
+def test_state_dict_is_the_reference_contract():
+    m = se_b200.TSCNet(num_channel=64, num_features=201)
+    sd = weights.synth_state_dict(0)
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    for k, v in m.state_dict().items():
+        assert v.shape == sd[k].shape and v.dtype == sd[k].dtype, k
+    m.load_state_dict(sd, strict=True)
+    # checkpoints saved from DataParallel/DDP carry 'module.' (inference_gan.py:66-68)
+    bn = m.TSCB_1.time_conformer.conv.net[5]
+    assert isinstance(bn, torch.nn.BatchNorm1d)
+    conv = torch.nn.SyncBatchNorm.convert_sync_batchnorm(m)
+    assert sum(isinstance(x, torch.nn.SyncBatchNorm) for x in conv.modules()) == 8
+
+
+def test_no_cpu_path():
+    m = se_b200.TSCNet().eval()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(torch.zeros(1, 201, 5, dtype=torch.complex64))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        se_b200.EnhancerB200(m)(torch.zeros(1, 800))
+    with pytest.raises(RuntimeError):
+        se_b200.compressed_stft(torch.zeros(1, 800))
+
+
+def test_swizzle_is_an_involution_and_matches_formula():
+    blk = torch.arange(16 * 64, dtype=torch.float32).reshape(16, 64).to(torch.bfloat16)
+    sw = packing.swizzle128(blk)
+    assert torch.equal(packing.swizzle128(sw), blk)
+    raw = sw.view(torch.int16).reshape(-1)
+    src = blk.view(torch.int16)
+    for r in (0, 3, 9, 15):
+        for c in range(8):
+            off = (r * 128 + ((c ^ (r & 7)) << 4)) // 2
+            assert torch.equal(raw[off:off + 8], src[r, c * 8:(c + 1) * 8])
+
+
+def _unpack_tc(pw):
+    img = pw.w_tc.view(torch.bfloat16).reshape(pw.tc_ntiles, pw.K // 64, 2, pw.tc_ntile, 64)
+    W = torch.zeros(pw.tc_ntiles * pw.tc_ntile, pw.K)
+    for j in range(pw.tc_ntiles):
+        for kc in range(pw.K // 64):
+            hi = packing.swizzle128(img[j, kc, 0]).float()
+            lo = packing.swizzle128(img[j, kc, 1]).float()
+            W[j * pw.tc_ntile:(j + 1) * pw.tc_ntile, kc * 64:(kc + 1) * 64] = hi + lo
+    return W
+
+
+def test_pack_weight_images():
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(402, 400, generator=g)
+    pw = packing.pack_weight(w, 208)
+    assert (pw.K, pw.tc_ntiles, pw.simt_npad) == (448, 2, 448)
+    W = _unpack_tc(pw)
+    assert rel_max(W[:402, :400], w) < 2.0 ** -16       # hi + lo keeps ~17 mantissa bits
+    assert W[402:].abs().max() == 0 and W[:, 400:].abs().max() == 0
+    assert torch.equal(pw.w_simt[:400, :402], w.t())
+
+
+def test_split_bf16_three_product_error_model():
+    """CPU emulation of the tensor path's arithmetic (a_hi*b_hi + a_hi*b_lo + a_lo*b_hi, fp32 accumulate)."""
+    g = torch.Generator().manual_seed(1)
+    a, b = torch.randn(256, 384, generator=g), torch.randn(64, 384, generator=g) * 0.07
+    ah, al = packing.split_bf16(a)
+    bh, bl = packing.split_bf16(b)
+    f = lambda x, y: x.float() @ y.float().t()
+    approx = f(ah, bh) + f(ah, bl) + f(al, bh)
+    exact = (a.double() @ b.double().t()).float()
+    assert rel_max(approx, exact) < 3e-5
+    assert rel_max(f(ah, bh), exact) > 1e-3             # single-pass bf16 is not enough
+
+
+def test_dft_bases_match_torch_fft():
+    x = torch.randn(3, 400, generator=torch.Generator().manual_seed(2))
+    w = O.hamming_periodic()
+    S = torch.fft.rfft(x * w, dim=-1)
+    got = (x.double() @ packing.dft_basis().double().t()).reshape(3, 201, 2)
+    assert rel_max(got[..., 0], S.real) < 1e-5 and rel_max(got[..., 1], S.imag) < 1e-5
+    Z = torch.randn(3, 201, dtype=torch.complex64, generator=torch.Generator().manual_seed(3))
+    fr = torch.fft.irfft(Z, n=400, dim=-1) * w
+    z = torch.view_as_real(Z).reshape(3, 402)
+    got = z.double() @ packing.idft_basis().double().t()
+    assert rel_max(got, fr) < 1e-5
+    env = packing.inv_envelope(9)
+    assert env.shape == (800,) and float(env.max()) < 1.0 and float(env.min()) > 0.5
+
+
+def test_abi_exports_every_declared_symbol():
+    lib_path = se_b200._lib.lib_path()
+    if not os.path.exists(lib_path):
+        se_b200._lib.load()            # builds with nvcc (cross-compiles without a GPU)
+    hdr = open(os.path.join(ROOT, "include", "seb200.h")).read()
+    declared = sorted(set(re.findall(r"\b(seb200_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared == se_b200._lib.EXPORTS
+    lib = ctypes.CDLL(lib_path)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.seb200_version() == 1
+
+
+def test_abi_rejects_bad_arguments_without_a_gpu():
+    lib = se_b200._lib.load()
+    assert lib.seb200_gemm(None, 0, None) == -1
+    assert b"null descriptor" in lib.seb200_last_error_string()
+    g = se_b200._lib.SebGemm()
+    g.M, g.N, g.K = 128, 64, 100                       # K not a multiple of 64
+    assert lib.seb200_gemm(ctypes.byref(g), 0, None) == -1
+    assert lib.seb200_rms_pad(None, 1, 100, 100, 1, None, None, None) == -1
+
+
+def test_shard_slice_partitions():
+    for n, g in [(4096, 8), (10, 4), (3, 8), (64, 1)]:
+        idx = []
+        for r in range(g):
+            s = se_b200.shard_slice(n, r, g)
+            idx += list(range(s.start, s.stop))
+        assert idx == list(range(n))
+
+
+_GLOO_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+import se_b200
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+waves = torch.arange(7 * 5, dtype=torch.float32).reshape(7, 5)
+fake = lambda x: x * 2.0 + 1.0                      # stands in for the per-rank CUDA enhancer
+out = se_b200.enhance_sharded(fake, waves, rank, world, micro_batch=2, gather=True)
+assert torch.equal(out, fake(waves)), (rank, out)
+local = se_b200.enhance_sharded(fake, waves, rank, world, micro_batch=3)
+sl = se_b200.shard_slice(7, rank, world)
+assert torch.equal(local, fake(waves[sl]))
+dist.barrier(); dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_sharding_world_size_2_gloo(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29611")
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
+    for p in procs:
+        out, _ = p.communicate(timeout=180)
+        assert p.returncode == 0, out.decode()

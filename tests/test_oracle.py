@@ -1,0 +1,93 @@
+"""CPU: the oracle restatement against the committed golden vectors (produced by the unmodified reference,
+oracle/make_golden.py) and -- when /root/reference is mounted -- against the live reference stage by stage."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_max
+from oracle import ref_import, tscnet_oracle as O, weights
+
+CASES = ["speech_b2_L8000", "noise_b1_L4050_wrap"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_golden(golden, name):
+    g = golden(name)
+    sd = weights.synth_state_dict(int(g["weight_seed"]))
+    noisy = torch.from_numpy(g["noisy"])
+    st = {}
+    with torch.no_grad():
+        y = O.predict(noisy, sd, stages=st)
+    spec_ref = torch.complex(torch.from_numpy(g["spec_real"]), torch.from_numpy(g["spec_imag"]))
+    assert rel_max(torch.view_as_real(st["spec"]), torch.view_as_real(spec_ref)) < 2e-5
+    with torch.no_grad():
+        fr, fi = O.tscnet_forward(spec_ref, sd)
+    assert rel_max(fr, torch.from_numpy(g["final_real"])) < 1e-5
+    assert rel_max(fi, torch.from_numpy(g["final_imag"])) < 1e-5
+    assert rel_max(y, torch.from_numpy(g["enhanced"])) < 2e-5
+    assert y.shape == noisy.shape
+
+
+def test_golden_inputs_are_reproducible(golden):
+    """the committed inputs are exactly what oracle.weights regenerates from the stored seeds"""
+    g = golden("speech_b2_L8000")
+    noisy, clean = weights.synth_wave(2, 8000, int(g["wave_seed"]), "speech")
+    assert np.array_equal(noisy.numpy(), g["noisy"]) and np.array_equal(clean.numpy(), g["clean"])
+
+
+def test_spec_state_dict_contract():
+    spec = weights.tscnet_spec()
+    assert len(spec) == 359
+    sd = weights.synth_state_dict(3)
+    n_params = sum(v.numel() for k, v in sd.items() if not k.endswith(("running_mean", "running_var", "num_batches_tracked")))
+    assert n_params == 1_834_833
+
+
+def test_istft_inverts_stft():
+    x = 0.1 * torch.randn(2, 3200, generator=torch.Generator().manual_seed(0))
+    w = O.hamming_periodic()
+    fr = O.stft_frames(x) * w
+    spec = torch.fft.rfft(fr, dim=-1).transpose(1, 2)
+    y = O.uncompressed_istft(O.power_compress(spec))        # decompress(compress(S)) == S
+    assert rel_max(y, x) < 1e-4
+
+
+def test_attention_chunking_is_exact():
+    sd = weights.synth_state_dict(0)
+    x = torch.randn(6, 37, 64, generator=torch.Generator().manual_seed(1))
+    p = "TSCB_1.time_conformer.attn"
+    with torch.no_grad():
+        a, b = O.attention(x, sd, p), O.attention(x, sd, p, chunk=4)
+    assert torch.equal(a, b)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="/root/reference not mounted")
+def test_oracle_against_live_reference():
+    ref = ref_import.load()
+    torch.manual_seed(0)
+    model = ref.TSCNet(num_channel=64, num_features=201)
+    model.apply(ref.kaiming_init)            # main_gan.py:147
+    model.eval()
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    noisy, _ = weights.synth_wave(1, 6000, 9, "speech")
+    caught = {}
+    hooks = [model.dense_encoder.register_forward_hook(lambda m, i, o: caught.__setitem__("encoder", o)),
+             model.TSCB_2.register_forward_hook(lambda m, i, o: caught.__setitem__("tscb2", o)),
+             model.mask_decoder.register_forward_hook(lambda m, i, o: caught.__setitem__("mask", o)),
+             model.complex_decoder.register_forward_hook(lambda m, i, o: caught.__setitem__("complex", o))]
+    y_ref = ref.predict(model, ref.config, noisy[0].numpy(), device=torch.device("cpu"))
+    for h in hooks:
+        h.remove()
+    st = {}
+    with torch.no_grad():
+        y = O.predict(noisy, sd, stages=st)
+    for k in ("encoder", "tscb2", "mask", "complex"):
+        assert rel_max(st[k], caught[k]) < 1e-5, k
+    assert rel_max(y[0], torch.from_numpy(y_ref)) < 2e-5
+    # long-sequence path with the +-512 clamp active, attention evaluated in chunks
+    x = torch.randn(3, 600, 64, generator=torch.Generator().manual_seed(2))
+    blk = model.TSCB_1.time_conformer
+    with torch.no_grad():
+        a = blk(x)
+        b = O.conformer_block(x, sd, "TSCB_1.time_conformer", chunk=2)
+    assert rel_max(b, a) < 1e-5
