@@ -55,7 +55,6 @@ extern "C" int seb200_gemm(const SebGemm* s, int engine, void* stream) {
   SEB_REQUIRE(s != nullptr, SEB_EINVAL, "gemm: null descriptor");
   SEB_REQUIRE(s->M > 0 && s->N > 0 && s->K > 0 && s->K % BK == 0, SEB_EINVAL, "gemm: bad sizes M=%d N=%d K=%d", s->M, s->N, s->K);
   SEB_REQUIRE(s->a[0] && s->out && aligned16(s->a[0]) && aligned16(s->out), SEB_EALIGN, "gemm: a/out null or unaligned");
-  SEB_REQUIRE(s->ldo % 2 == 0, SEB_EALIGN, "gemm: ldo must be even");
   if (s->loader == SEB_LOAD_ROWS || s->loader == SEB_LOAD_ROWS_LN) {
     SEB_REQUIRE(s->lda % 4 == 0 && s->lda >= s->K, SEB_EALIGN, "gemm: lda=%lld must be a multiple of 4 and >= K", s->lda);
   }
@@ -72,7 +71,8 @@ extern "C" int seb200_gemm(const SebGemm* s, int engine, void* stream) {
     SEB_REQUIRE(s->Fin > 0 && s->Fin % 8 == 0 && s->Fin <= s->K && s->stride_f % 4 == 0 && s->lda % 4 == 0 && s->T > 0, SEB_EALIGN, "gemm: bad framing geometry");
   }
   if (s->epilogue == SEB_EPI_RESID) SEB_REQUIRE(s->resid && s->ldr % 4 == 0 && aligned16(s->resid), SEB_EALIGN, "gemm: residual null/unaligned");
-  if (s->epilogue != SEB_EPI_COMPRESS) SEB_REQUIRE(s->ldo % 4 == 0 || s->epilogue == SEB_EPI_GLU, SEB_EALIGN, "gemm: ldo must be a multiple of 4");
+  if (s->epilogue == SEB_EPI_GLU) SEB_REQUIRE(s->ldo % 2 == 0, SEB_EALIGN, "gemm: ldo must be even");
+  else if (s->epilogue != SEB_EPI_COMPRESS) SEB_REQUIRE(s->ldo % 4 == 0, SEB_EALIGN, "gemm: ldo must be a multiple of 4");
 
   const GemmArgs g = to_args(s);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

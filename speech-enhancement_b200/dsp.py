@@ -19,6 +19,7 @@ from ._lib import EPI_BIAS, EPI_COMPRESS, LOAD_HANKEL, LOAD_ROWS, require_cuda
 from .packing import dft_basis, hamming_periodic, idft_basis, inv_envelope, pack_weight
 
 N_FFT, HOP, N_BINS, LDZ = 400, 100, 201, 448
+DFT_ENGINE = "simt"      # fp32 main loop for the DFTs (see enhancer.py); "tcgen05" selects the split-bf16 tensor path
 
 _cache: Dict[tuple, object] = {}
 
@@ -53,7 +54,7 @@ def stft_in3(xpad: torch.Tensor, T: int, engine: Optional[str] = None, out: Opti
     if out is None:
         out = torch.empty(B, T, N_BINS, 3, device=xpad.device, dtype=torch.float32)
     ops.gemm(loader=LOAD_HANKEL, epilogue=EPI_COMPRESS, M=B * T, N=2 * N_BINS, w=fwd, a=[xpad], lda=xpad.shape[1], out=out,
-             ldo=3 * N_BINS, engine=engine or ops.default_engine(),
+             ldo=3 * N_BINS, engine=engine or DFT_ENGINE, label="stft", k_logical=N_FFT,
              conv=dict(B=B, T=T, Fin=N_FFT, Fout=0, stride_f=HOP))
     return out
 
@@ -63,7 +64,7 @@ def istft_rows(z: torch.Tensor, B: int, T: int, c: Optional[torch.Tensor], engin
     _, inv = _bases(z.device)
     frames = torch.empty(B * T, N_FFT, device=z.device, dtype=torch.float32)
     ops.gemm(loader=LOAD_ROWS, epilogue=EPI_BIAS, M=B * T, N=N_FFT, w=inv, a=[z], lda=LDZ, out=frames, ldo=N_FFT,
-             engine=engine or ops.default_engine())
+             engine=engine or DFT_ENGINE, label="idft", k_logical=2 * N_BINS)
     out = torch.empty(B, HOP * (T - 1), device=z.device, dtype=torch.float32)
     ops.overlap_add(frames, B, T, _inv_env(T, z.device), c, out)
     return out

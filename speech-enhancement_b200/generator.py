@@ -262,7 +262,7 @@ class TSCNet(nn.Module):
         slots = [x0]
         for i in range(1, 5):
             w: PackedWeight = P[f"{prefix}.conv{i}"]
-            ops.gemm(loader=LOAD_CONV, epilogue=EPI_BIAS, M=B * T * F, w=w, a=slots, out=raw, ldo=64, engine=self.engine,
+            ops.gemm(loader=LOAD_CONV, epilogue=EPI_BIAS, M=B * T * F, w=w, a=slots, out=raw, ldo=64, engine=self.engine, label="dconv",
                      conv=dict(B=B, T=T, Fin=F, Fout=F, taps_t=2, dil=2 ** (i - 1), stride_f=1, nslots=i))
             self._inorm_prelu(ws, raw, B, T * F, P[f"{prefix}.norm{i}.weight"], P[f"{prefix}.norm{i}.bias"], P[f"{prefix}.prelu{i}.weight"], outs[i - 1])
             slots = [outs[i - 1]] + slots
@@ -273,19 +273,19 @@ class TSCNet(nn.Module):
         eng = self.engine
         y, h, qkv, o, u, v = ws["y"], ws["h"], ws["qkv"], ws["o"], ws["u"], ws["v"]
         # y = x + 0.5 * FF1(LN(x))
-        ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_SWISH, M=M, w=P[f"{p}.ff1.w1"], a=[x], lda=64, ln=P[f"{p}.ff1.ln"], out=h, ldo=256, engine=eng)
-        ops.gemm(loader=LOAD_ROWS, epilogue=EPI_RESID, M=M, w=P[f"{p}.ff1.w2"], a=[h], lda=256, out=y, ldo=64, resid=x, ldr=64, alpha=0.5, engine=eng)
+        ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_SWISH, M=M, w=P[f"{p}.ff1.w1"], a=[x], lda=64, ln=P[f"{p}.ff1.ln"], out=h, ldo=256, engine=eng, label="ffn1")
+        ops.gemm(loader=LOAD_ROWS, epilogue=EPI_RESID, M=M, w=P[f"{p}.ff1.w2"], a=[h], lda=256, out=y, ldo=64, resid=x, ldr=64, alpha=0.5, engine=eng, label="ffn2")
         # y += Attn(LN(y))
-        ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_BIAS, M=M, w=P[f"{p}.attn.qkv"], a=[y], lda=64, ln=P[f"{p}.attn.ln"], out=qkv, ldo=192, engine=eng)
+        ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_BIAS, M=M, w=P[f"{p}.attn.qkv"], a=[y], lda=64, ln=P[f"{p}.attn.ln"], out=qkv, ldo=192, engine=eng, label="qkv")
         ops.attention(qkv, P[f"{p}.attn.emb"], seq, o, self.attention_variant)
-        ops.gemm(loader=LOAD_ROWS, epilogue=EPI_RESID, M=M, w=P[f"{p}.attn.out"], a=[o], lda=64, out=y, ldo=64, resid=y, ldr=64, alpha=1.0, engine=eng)
+        ops.gemm(loader=LOAD_ROWS, epilogue=EPI_RESID, M=M, w=P[f"{p}.attn.out"], a=[o], lda=64, out=y, ldo=64, resid=y, ldr=64, alpha=1.0, engine=eng, label="attn_out")
         # y += ConvModule(y)
-        ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_GLU, M=M, w=P[f"{p}.conv.pw1"], a=[y], lda=64, ln=P[f"{p}.conv.ln"], out=u, ldo=128, engine=eng)
+        ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_GLU, M=M, w=P[f"{p}.conv.pw1"], a=[y], lda=64, ln=P[f"{p}.conv.ln"], out=u, ldo=128, engine=eng, label="pw1_glu")
         ops.dwconv_bn_swish(u, seq, P[f"{p}.conv.dw"], P[f"{p}.conv.bn"][0], P[f"{p}.conv.bn"][1], v)
-        ops.gemm(loader=LOAD_ROWS, epilogue=EPI_RESID, M=M, w=P[f"{p}.conv.pw2"], a=[v], lda=128, out=y, ldo=64, resid=y, ldr=64, alpha=1.0, engine=eng)
+        ops.gemm(loader=LOAD_ROWS, epilogue=EPI_RESID, M=M, w=P[f"{p}.conv.pw2"], a=[v], lda=128, out=y, ldo=64, resid=y, ldr=64, alpha=1.0, engine=eng, label="pw2")
         # y += 0.5 * FF2(LN(y))
-        ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_SWISH, M=M, w=P[f"{p}.ff2.w1"], a=[y], lda=64, ln=P[f"{p}.ff2.ln"], out=h, ldo=256, engine=eng)
-        ops.gemm(loader=LOAD_ROWS, epilogue=EPI_RESID, M=M, w=P[f"{p}.ff2.w2"], a=[h], lda=256, out=y, ldo=64, resid=y, ldr=64, alpha=0.5, engine=eng)
+        ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_SWISH, M=M, w=P[f"{p}.ff2.w1"], a=[y], lda=64, ln=P[f"{p}.ff2.ln"], out=h, ldo=256, engine=eng, label="ffn1")
+        ops.gemm(loader=LOAD_ROWS, epilogue=EPI_RESID, M=M, w=P[f"{p}.ff2.w2"], a=[h], lda=256, out=y, ldo=64, resid=y, ldr=64, alpha=0.5, engine=eng, label="ffn2")
         # x = post_norm(y) + x
         ops.layernorm_residual(y, P[f"{p}.post_norm"][0], P[f"{p}.post_norm"][1], x, x)
         return x
@@ -313,7 +313,7 @@ class TSCNet(nn.Module):
         self._inorm_prelu(ws, raw, B, T * F, P[f"{e}.conv_1.1.weight"], P[f"{e}.conv_1.1.bias"], P[f"{e}.conv_1.2.weight"], enc[0])
         d4 = self._dense(P, f"{e}.dilated_dense", ws, enc[0], enc[1:5], raw, B, T, F)
         rawh = ws["dec_raw"]
-        ops.gemm(loader=LOAD_CONV, epilogue=EPI_BIAS, M=B * T * Fh, w=P[f"{e}.conv_2"], a=[d4], out=rawh, ldo=64, engine=eng,
+        ops.gemm(loader=LOAD_CONV, epilogue=EPI_BIAS, M=B * T * Fh, w=P[f"{e}.conv_2"], a=[d4], out=rawh, ldo=64, engine=eng, label="conv2",
                  conv=dict(B=B, T=T, Fin=F, Fout=Fh, taps_t=1, dil=1, stride_f=2, nslots=1))
         x = ws["x"]
         self._inorm_prelu(ws, rawh, B, T * Fh, P[f"{e}.conv_2.1.weight"], P[f"{e}.conv_2.1.bias"], P[f"{e}.conv_2.2.weight"], x)
@@ -334,7 +334,7 @@ class TSCNet(nn.Module):
         m = "mask_decoder"
         dec, sp = ws["dec"], ws["sp"]
         d4 = self._dense(P, f"{m}.dense_block", ws, x, dec, rawh, B, T, Fh)
-        ops.gemm(loader=LOAD_CONV, epilogue=EPI_SUBPIXEL, M=M, w=P[f"{m}.sub_pixel"], a=[d4], out=sp, ldo=64, engine=eng,
+        ops.gemm(loader=LOAD_CONV, epilogue=EPI_SUBPIXEL, M=M, w=P[f"{m}.sub_pixel"], a=[d4], out=sp, ldo=64, engine=eng, label="subpixel",
                  conv=dict(B=B, T=T, Fin=Fh, Fout=Fh, taps_t=1, dil=1, stride_f=1, nslots=1))
         b1, g_in, b_in, s1, wf, bf = P[f"{m}.scalars"]
         ops.mask_conv(sp, B * T, 2 * Fh, P[f"{m}.conv_1.w"], b1, ws["mask_raw"])
@@ -343,7 +343,7 @@ class TSCNet(nn.Module):
         # ---- ComplexDecoder (generator.py:124-129)
         c = "complex_decoder"
         d4 = self._dense(P, f"{c}.dense_block", ws, x, dec, rawh, B, T, Fh)
-        ops.gemm(loader=LOAD_CONV, epilogue=EPI_SUBPIXEL, M=M, w=P[f"{c}.sub_pixel"], a=[d4], out=sp, ldo=64, engine=eng,
+        ops.gemm(loader=LOAD_CONV, epilogue=EPI_SUBPIXEL, M=M, w=P[f"{c}.sub_pixel"], a=[d4], out=sp, ldo=64, engine=eng, label="subpixel",
                  conv=dict(B=B, T=T, Fin=Fh, Fout=Fh, taps_t=1, dil=1, stride_f=1, nslots=1))
         ops.inorm_stats(sp, B, T * 2 * Fh, 64, ws["stats"], ws["in_ws"])
         ops.complex_conv(sp, B, T, 2 * Fh, ws["stats"], P[f"{c}.norm.weight"], P[f"{c}.norm.bias"], P[f"{c}.prelu.weight"],

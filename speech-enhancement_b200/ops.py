@@ -20,6 +20,69 @@ from .packing import PackedWeight
 ENGINES = {"tcgen05": ENGINE_TCGEN05, "simt": ENGINE_SIMT}
 
 
+class Profiler:
+    """Per-launch CUDA-event timing on the launching stream, keyed by a kernel label.
+
+    ``with ops.profile(only={"dconv"}) as prof: ...`` brackets every matching launch with two events
+    (a few microseconds of host work each); ``prof.summary()`` returns per-label launch counts, total
+    milliseconds and the algorithmic FLOPs / bytes the wrappers attached to each launch."""
+
+    def __init__(self, only=None):
+        self.only = set(only) if only else None
+        self.records = []
+
+    def begin(self, label, flops, nbytes):
+        if self.only is not None and label not in self.only:
+            return None
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        return (label, flops, nbytes, e0)
+
+    def end(self, tok):
+        if tok is None:
+            return
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        self.records.append(tok + (e1,))
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for label, flops, nbytes, e0, e1 in self.records:
+            d = out.setdefault(label, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            d["launches"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += flops
+            d["bytes"] += nbytes
+        return out
+
+    def __enter__(self):
+        global _PROF
+        self._prev, _PROF = _PROF, self
+        return self
+
+    def __exit__(self, *exc):
+        global _PROF
+        _PROF = self._prev
+        return False
+
+
+_PROF = None
+
+
+def profile(only=None) -> Profiler:
+    return Profiler(only)
+
+
+def _pb(label, flops=0.0, nbytes=0.0):
+    return _PROF.begin(label, flops, nbytes) if _PROF is not None else None
+
+
+def _pe(tok):
+    if tok is not None:
+        _PROF.end(tok)
+
+
 def default_engine() -> str:
     return os.environ.get("SEB200_ENGINE", "tcgen05")
 
@@ -35,7 +98,8 @@ def _f32c(*ts):
 
 def gemm(*, loader: int, epilogue: int, M: int, w: PackedWeight, a: Sequence[torch.Tensor], out: torch.Tensor,
          ldo: int, N: Optional[int] = None, lda: int = 0, ln: Optional[tuple] = None, conv: Optional[dict] = None,
-         resid: Optional[torch.Tensor] = None, ldr: int = 0, alpha: float = 1.0, engine: str = "tcgen05"):
+         resid: Optional[torch.Tensor] = None, ldr: int = 0, alpha: float = 1.0, engine: str = "tcgen05",
+         label: str = "gemm", k_logical: Optional[int] = None):
     """One launch of the GEMM engine (see include/seb200.h: SebGemm)."""
     lib = _lib.load()
     _f32c(out, resid, *a)
@@ -55,7 +119,9 @@ def gemm(*, loader: int, epilogue: int, M: int, w: PackedWeight, a: Sequence[tor
     g.bias = ptr(w.bias)
     g.out, g.ldo = ptr(out), ldo
     g.resid, g.ldr, g.alpha = ptr(resid), ldr, alpha
+    tok = _pb(label, 2.0 * M * g.N * (k_logical or w.K), 4.0 * M * (g.N + (k_logical or w.K))) if _PROF is not None else None
     check(lib.seb200_gemm(C.byref(g), ENGINES[engine], stream_ptr()), "seb200_gemm")
+    _pe(tok)
     return out
 
 
@@ -64,7 +130,9 @@ def rms_pad(wave: torch.Tensor, Lp: int, normalize: bool = True):
     B, L = wave.shape
     xpad = torch.empty(B, Lp + 400, device=wave.device, dtype=torch.float32)
     c = torch.empty(B, device=wave.device, dtype=torch.float32)
+    tok = _pb("rms_pad", 0.0, 8.0 * wave.numel()) if _PROF is not None else None
     check(_lib.load().seb200_rms_pad(ptr(wave), B, L, Lp, int(normalize), ptr(xpad), ptr(c), stream_ptr()), "seb200_rms_pad")
+    _pe(tok)
     return xpad, c
 
 
@@ -77,7 +145,9 @@ def spec_to_in3(spec: torch.Tensor, out: Optional[torch.Tensor] = None):
     B, F, T = spec.shape
     if out is None:
         out = torch.empty(B, T, F, 3, device=spec.device, dtype=torch.float32)
+    tok = _pb("spec_to_in3", 0.0, 20.0 * B * F * T) if _PROF is not None else None
     check(_lib.load().seb200_spec_to_in3(ptr(sr), B, F, T, ptr(out), stream_ptr()), "seb200_spec_to_in3")
+    _pe(tok)
     return out
 
 
@@ -85,14 +155,19 @@ def in3_to_spec(in3: torch.Tensor):
     _f32c(in3)
     B, T, F, _ = in3.shape
     out = torch.empty(B, F, T, 2, device=in3.device, dtype=torch.float32)
+    tok = _pb("in3_to_spec", 0.0, 20.0 * B * F * T) if _PROF is not None else None
     check(_lib.load().seb200_in3_to_spec(ptr(in3), B, F, T, ptr(out), stream_ptr()), "seb200_in3_to_spec")
+    _pe(tok)
     return torch.view_as_complex(out)
 
 
 def decompress_rows(est: torch.Tensor, z: torch.Tensor):
     _f32c(est, z)
-    rows, F = est.shape[0] * est.shape[1], est.shape[2]
+    F = est.shape[-2]                      # est: [..., F, 2]
+    rows = est.numel() // (2 * F)
+    tok = _pb("decompress_rows", 0.0, 4.0 * (est.numel() + z.numel())) if _PROF is not None else None
     check(_lib.load().seb200_decompress_rows(ptr(est), rows, F, ptr(z), z.shape[-1], stream_ptr()), "seb200_decompress_rows")
+    _pe(tok)
     return z
 
 
@@ -100,22 +175,28 @@ def spec_decompress_rows(spec: torch.Tensor, z: torch.Tensor):
     require_cuda(spec)
     sr = torch.view_as_real(spec.contiguous())
     B, F, T = spec.shape
+    tok = _pb("decompress_rows", 0.0, 4.0 * (2 * B * F * T + z.numel())) if _PROF is not None else None
     check(_lib.load().seb200_spec_decompress_rows(ptr(sr), B, F, T, ptr(z), z.shape[-1], stream_ptr()), "seb200_spec_decompress_rows")
+    _pe(tok)
     return z
 
 
 def overlap_add(frames: torch.Tensor, B: int, T: int, inv_env: torch.Tensor, c: Optional[torch.Tensor], out: torch.Tensor):
     _f32c(frames, inv_env, c, out)
     Lout = 100 * (T - 1)
+    tok = _pb("overlap_add", 0.0, 4.0 * (frames.numel() + out.numel())) if _PROF is not None else None
     check(_lib.load().seb200_overlap_add(ptr(frames), B, T, frames.shape[-1], ptr(inv_env), ptr(c), ptr(out), Lout,
                                          out.shape[-1], stream_ptr()), "seb200_overlap_add")
+    _pe(tok)
     return out
 
 
 def conv1x1_in3(in3, w, bias, out):
     _f32c(in3, w, bias, out)
     pixels = in3.numel() // 3
+    tok = _pb("conv1x1_in3", 2.0 * 3 * 64 * pixels, 4.0 * (in3.numel() + out.numel())) if _PROF is not None else None
     check(_lib.load().seb200_conv1x1_in3(ptr(in3), pixels, ptr(w), ptr(bias), ptr(out), stream_ptr()), "seb200_conv1x1_in3")
+    _pe(tok)
     return out
 
 
@@ -126,42 +207,54 @@ def inorm_workspace(B: int, pix_per_b: int, C_: int, device) -> torch.Tensor:
 
 def inorm_stats(x, B: int, pix_per_b: int, C_: int, stats, workspace):
     _f32c(x, stats)
+    tok = _pb("inorm_stats", 0.0, 4.0 * B * pix_per_b * C_) if _PROF is not None else None
     check(_lib.load().seb200_inorm_stats(ptr(x), B, pix_per_b, C_, ptr(stats), ptr(workspace), workspace.numel() * 8,
                                          stream_ptr()), "seb200_inorm_stats")
+    _pe(tok)
     return stats
 
 
 def inorm_prelu(x, B: int, pix_per_b: int, stats, gamma, beta, slope, y):
     _f32c(x, stats, gamma, beta, slope, y)
+    tok = _pb("inorm_prelu", 0.0, 8.0 * B * pix_per_b * 64) if _PROF is not None else None
     check(_lib.load().seb200_inorm_prelu(ptr(x), B, pix_per_b, 64, ptr(stats), ptr(gamma), ptr(beta), ptr(slope), ptr(y),
                                          stream_ptr()), "seb200_inorm_prelu")
+    _pe(tok)
     return y
 
 
 def mask_conv(x, rows: int, Fin: int, w, bias: float, out):
     _f32c(x, w, out)
+    tok = _pb("mask_conv", 2.0 * 128 * rows * (Fin - 1), 4.0 * (rows * Fin * 64 + rows * (Fin - 1))) if _PROF is not None else None
     check(_lib.load().seb200_mask_conv(ptr(x), rows, Fin, ptr(w), float(bias), ptr(out), stream_ptr()), "seb200_mask_conv")
+    _pe(tok)
     return out
 
 
 def complex_conv(x, B: int, rows_per_b: int, Fin: int, stats, gamma, beta, slope, w, bias, out):
     _f32c(x, stats, gamma, beta, slope, w, bias, out)
+    tok = _pb("complex_conv", 2.0 * 256 * B * rows_per_b * (Fin - 1), 4.0 * (B * rows_per_b * Fin * 64 + 2 * B * rows_per_b * (Fin - 1))) if _PROF is not None else None
     check(_lib.load().seb200_complex_conv(ptr(x), B, rows_per_b, Fin, ptr(stats), ptr(gamma), ptr(beta), ptr(slope), ptr(w),
                                           ptr(bias), ptr(out), stream_ptr()), "seb200_complex_conv")
+    _pe(tok)
     return out
 
 
 def mask_recombine(mask_raw, mask_stats, B: int, rows_per_b: int, F: int, scalars, slope_f, in3, cplx, est, mask_out=None):
     _f32c(mask_raw, mask_stats, slope_f, in3, cplx, est, mask_out)
     g, b, s1, wf, bf = (float(v) for v in scalars)
+    tok = _pb("mask_recombine", 0.0, 4.0 * 8 * B * rows_per_b * F) if _PROF is not None else None
     check(_lib.load().seb200_mask_recombine(ptr(mask_raw), ptr(mask_stats), B, rows_per_b, F, g, b, s1, wf, bf, ptr(slope_f),
                                             ptr(in3), ptr(cplx), ptr(est), ptr(mask_out), stream_ptr()), "seb200_mask_recombine")
+    _pe(tok)
     return est
 
 
 def split_ri(est, re, im):
     _f32c(est, re, im)
+    tok = _pb("split_ri", 0.0, 8.0 * est.numel()) if _PROF is not None else None
     check(_lib.load().seb200_split_ri(ptr(est), est.numel() // 2, ptr(re), ptr(im), stream_ptr()), "seb200_split_ri")
+    _pe(tok)
 
 
 def make_seq(nseq: int, n: int, inner: int, outer_stride: int, pos_stride: int) -> SebSeq:
@@ -172,19 +265,25 @@ def make_seq(nseq: int, n: int, inner: int, outer_stride: int, pos_stride: int) 
 
 def attention(qkv, rel_pos_emb, seq: SebSeq, out, variant: int = 0):
     _f32c(qkv, rel_pos_emb, out)
+    tok = _pb("attention", 96.0 * 4 * seq.nseq * seq.n * seq.n, 4.0 * (qkv.numel() + out.numel())) if _PROF is not None else None
     check(_lib.load().seb200_attention(ptr(qkv), ptr(rel_pos_emb), C.byref(seq), ptr(out), variant, stream_ptr()), "seb200_attention")
+    _pe(tok)
     return out
 
 
 def dwconv_bn_swish(x, seq: SebSeq, w, bn_scale, bn_shift, y):
     _f32c(x, w, bn_scale, bn_shift, y)
+    tok = _pb("dwconv", 62.0 * x.numel(), 8.0 * x.numel()) if _PROF is not None else None
     check(_lib.load().seb200_dwconv_bn_swish(ptr(x), C.byref(seq), ptr(w), ptr(bn_scale), ptr(bn_shift), ptr(y), stream_ptr()),
           "seb200_dwconv_bn_swish")
+    _pe(tok)
     return y
 
 
 def layernorm_residual(x, gamma, beta, resid, out):
     _f32c(x, gamma, beta, resid, out)
+    tok = _pb("layernorm_residual", 0.0, 12.0 * x.numel()) if _PROF is not None else None
     check(_lib.load().seb200_layernorm_residual(ptr(x), x.numel() // 64, ptr(gamma), ptr(beta), ptr(resid), ptr(out), stream_ptr()),
           "seb200_layernorm_residual")
+    _pe(tok)
     return out

@@ -1,0 +1,108 @@
+"""GPU: the whole hot path through the drop-in interface against the golden vectors (produced by the unmodified
+reference) and against the oracle, stage by stage.  Tolerances are BASELINE.json's: enhanced waveform within 1e-3
+max-abs relative to signal peak and 0.05 dB SI-SDR; compressed spectrogram within 1e-4 relative."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_max, rel_l2
+from oracle import tscnet_oracle as O, weights
+
+import se_b200
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+WAVE_TOL = 1e-3
+SPEC_TOL = 1e-4
+SISDR_TOL_DB = 0.05
+
+
+def _model(seed, engine):
+    m = se_b200.TSCNet(num_channel=64, num_features=201)
+    m.load_state_dict(weights.synth_state_dict(seed))
+    m = m.to(DEV).eval()
+    m.engine = engine
+    return m
+
+
+@pytest.mark.parametrize("engine", ["simt", "tcgen05"])
+@pytest.mark.parametrize("name", ["speech_b2_L8000", "noise_b1_L4050_wrap"])
+def test_predict_matches_reference_golden(golden, name, engine):
+    g = golden(name)
+    model = _model(int(g["weight_seed"]), engine)
+    enh = se_b200.EnhancerB200(model)
+    noisy = torch.from_numpy(g["noisy"]).to(DEV)
+    stages = {}
+    y = enh(noisy, stages=stages).cpu()
+    ref = torch.from_numpy(g["enhanced"])
+    assert y.shape == ref.shape
+    # compressed spectrogram (STFT epilogue output) vs the reference's compressed_stft
+    in3 = stages["in3"].cpu()
+    spec_ref = torch.stack([torch.from_numpy(g["spec_real"]), torch.from_numpy(g["spec_imag"])], -1).permute(0, 2, 1, 3)
+    assert rel_l2(in3[..., 1:3], spec_ref) < SPEC_TOL
+    # enhanced waveform
+    err = rel_max(y, ref)
+    assert err < WAVE_TOL, f"waveform max-abs/peak {err:.3e}"
+    clean = torch.from_numpy(g["clean"])
+    d = (O.si_sdr(y, clean) - O.si_sdr(ref, clean)).abs().max().item()
+    assert d < SISDR_TOL_DB, f"SI-SDR delta {d:.4f} dB"
+    # 1-D numpy call shape of the reference's predict()
+    y1 = enh.predict(g["noisy"][0])
+    assert y1.shape == g["noisy"][0].shape and np.abs(y1 - g["enhanced"][0]).max() / np.abs(g["enhanced"][0]).max() < WAVE_TOL
+
+
+@pytest.mark.parametrize("engine", ["simt", "tcgen05"])
+def test_module_forward_matches_reference_golden(golden, engine):
+    """TSCNet.forward(complex spectrogram) -> (real, imag), the reference's nn.Module contract."""
+    g = golden("speech_b2_L8000")
+    model = _model(int(g["weight_seed"]), engine)
+    spec = torch.complex(torch.from_numpy(g["spec_real"]), torch.from_numpy(g["spec_imag"])).to(DEV)
+    fr, fi = model(spec)
+    assert fr.shape == (2, 1, 81, 201) and fi.shape == fr.shape and fr.dtype == torch.float32
+    peak = max(np.abs(g["final_real"]).max(), np.abs(g["final_imag"]).max())
+    assert (fr.cpu() - torch.from_numpy(g["final_real"])).abs().max() / peak < WAVE_TOL
+    assert (fi.cpu() - torch.from_numpy(g["final_imag"])).abs().max() / peak < WAVE_TOL
+
+
+@pytest.mark.parametrize("engine", ["simt", "tcgen05"])
+def test_stages_against_oracle(engine):
+    """per-stage parity on a clip long enough for the +-512 relative-position clamp (T = 601 frames)"""
+    sd = weights.synth_state_dict(4)
+    model = _model(4, engine)
+    noisy, _ = weights.synth_wave(1, 60000, seed=11, kind="speech")
+    st_o, st_g = {}, {}
+    with torch.no_grad():
+        y_o = O.predict(noisy, sd, chunk=8, stages=st_o)
+    y_g = se_b200.EnhancerB200(model)(noisy.to(DEV), stages=st_g).cpu()
+    cl = lambda t: t.permute(0, 2, 3, 1)
+    tol = 1e-3          # TF32 attention (~3e-4) dominates; the fp32 path is checked below
+    for k in ("encoder", "tscb1", "tscb2", "tscb3", "tscb4"):
+        assert rel_max(st_g[k].cpu(), cl(st_o[k])) < tol, k
+    assert rel_max(st_g["mask"].cpu(), st_o["mask"][:, 0]) < tol
+    assert rel_max(st_g["complex"].cpu(), cl(st_o["complex"])) < tol
+    assert rel_max(y_g, y_o) < WAVE_TOL
+
+
+def test_fp32_path_is_fp32_exact():
+    """SIMT GEMM engine + SIMT attention: every contraction in fp32 -> agreement with the oracle at fp32 noise level"""
+    sd = weights.synth_state_dict(4)
+    model = _model(4, "simt")
+    model.attention_variant = 1
+    noisy, _ = weights.synth_wave(2, 12000, seed=12, kind="speech")
+    st_o, st_g = {}, {}
+    with torch.no_grad():
+        y_o = O.predict(noisy, sd, stages=st_o)
+    y_g = se_b200.EnhancerB200(model)(noisy.to(DEV), stages=st_g).cpu()
+    assert rel_max(st_g["tscb4"].cpu(), st_o["tscb4"].permute(0, 2, 3, 1)) < 5e-5
+    assert rel_max(y_g, y_o) < 2e-5
+
+
+def test_batch_rows_are_independent():
+    """pure batch sharding: a row enhanced alone equals the same row inside a batch, bit for bit"""
+    model = _model(0, "tcgen05")
+    enh = se_b200.EnhancerB200(model)
+    noisy, _ = weights.synth_wave(3, 4000, seed=21, kind="speech")
+    noisy = noisy.to(DEV)
+    full = enh(noisy).clone()
+    for i in range(3):
+        assert torch.equal(enh(noisy[i:i + 1])[0], full[i])

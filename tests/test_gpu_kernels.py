@@ -1,0 +1,271 @@
+"""GPU: every exported kernel against a plain PyTorch fp32 reference of the same op (or the oracle's function),
+called through the C ABI.  Both main loops of the GEMM engine are exercised: `simt` (fp32 FFMA) and `tcgen05`
+(split-bf16 tensor path); the tensor-core attention is checked against the oracle and against the SIMT variant."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_max, rel_l2
+from oracle import tscnet_oracle as O, weights
+
+import se_b200
+from se_b200 import ops, packing
+from se_b200._lib import (EPI_BIAS, EPI_COMPRESS, EPI_GLU, EPI_RESID, EPI_SUBPIXEL, EPI_SWISH, LOAD_CONV, LOAD_HANKEL,
+                          LOAD_ROWS, LOAD_ROWS_LN)
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+ENGINES = ["simt", "tcgen05"]
+TOL = {"simt": 2e-5, "tcgen05": 1e-4}
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    return (torch.randn(*shape, generator=torch.Generator().manual_seed(seed)) * scale).to(DEV)
+
+
+# ------------------------------------------------------------------------------------------------ GEMM engine
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("K,M", [(64, 300), (128, 128), (256, 1000)])
+def test_gemm_rows_resid(engine, K, M):
+    a, w, b, r = rnd(M, K, seed=1), rnd(64, K, seed=2, scale=K ** -0.5), rnd(64, seed=3), rnd(M, 64, seed=4)
+    pw = packing.pack_weight(w.cpu(), 64, b.cpu()).to(DEV)
+    out = torch.empty(M, 64, device=DEV)
+    ops.gemm(loader=LOAD_ROWS, epilogue=EPI_RESID, M=M, w=pw, a=[a], lda=K, out=out, ldo=64, resid=r, ldr=64, alpha=0.5, engine=engine)
+    ref = 0.5 * (a.double() @ w.double().t() + b.double()) + r.double()
+    assert rel_max(out, ref) < TOL[engine]
+    # in place on the residual buffer (how the conformer uses it)
+    r2 = r.clone()
+    ops.gemm(loader=LOAD_ROWS, epilogue=EPI_RESID, M=M, w=pw, a=[a], lda=K, out=r2, ldo=64, resid=r2, ldr=64, alpha=0.5, engine=engine)
+    assert torch.equal(r2, out)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_gemm_layernorm_loader_epilogues(engine):
+    M = 777
+    x = rnd(M, 64, seed=5, scale=3.0) + 0.7
+    g, be = rnd(64, seed=6, scale=0.2) + 1.0, rnd(64, seed=7, scale=0.2)
+    xn = F.layer_norm(x.double(), (64,), g.double(), be.double(), 1e-5)
+    # Linear 64 -> 256 + Swish
+    w, b = rnd(256, 64, seed=8, scale=0.17), rnd(256, seed=9, scale=0.1)
+    out = torch.empty(M, 256, device=DEV)
+    ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_SWISH, M=M, w=packing.pack_weight(w.cpu(), 256, b.cpu()).to(DEV), a=[x], lda=64, ln=(g, be), out=out, ldo=256, engine=engine)
+    h = xn @ w.double().t() + b.double()
+    assert rel_max(out, h * torch.sigmoid(h)) < TOL[engine]
+    # pointwise conv 64 -> 256 + GLU (interleaved packing)
+    wi, bi = packing.glu_interleave(w.cpu(), b.cpu())
+    out = torch.empty(M, 128, device=DEV)
+    ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_GLU, M=M, w=packing.pack_weight(wi, 256, bi).to(DEV), a=[x], lda=64, ln=(g, be), out=out, ldo=128, engine=engine)
+    assert rel_max(out, h[:, :128] * torch.sigmoid(h[:, 128:])) < TOL[engine]
+    # q | k | v projection, no bias
+    wq = rnd(192, 64, seed=10, scale=0.17)
+    out = torch.empty(M, 192, device=DEV)
+    ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_BIAS, M=M, w=packing.pack_weight(wq.cpu(), 192, None).to(DEV), a=[x], lda=64, ln=(g, be), out=out, ldo=192, engine=engine)
+    assert rel_max(out, xn @ wq.double().t()) < TOL[engine]
+
+
+def _cl(x):      # (B, C, T, F) -> channels-last [B, T, F, C] contiguous
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("layer", [1, 2, 3, 4])
+def test_gemm_dilated_conv(engine, layer):
+    B, T, Fq = 2, 21, 13
+    dil = 2 ** (layer - 1)
+    slots_nchw = [rnd(B, 64, T, Fq, seed=20 + i) for i in range(layer)]            # newest first
+    w = rnd(64, 64 * layer, 2, 3, seed=30, scale=(64 * layer * 6) ** -0.5)
+    b = rnd(64, seed=31, scale=0.1)
+    ref = F.conv2d(F.pad(torch.cat(slots_nchw, 1).double(), (1, 1, dil, 0)), w.double(), b.double(), dilation=(dil, 1))
+    pw = packing.pack_weight(packing.conv_weight_matrix(w.cpu()), 64, b.cpu()).to(DEV)
+    out = torch.empty(B * T * Fq, 64, device=DEV)
+    ops.gemm(loader=LOAD_CONV, epilogue=EPI_BIAS, M=B * T * Fq, w=pw, a=[_cl(s) for s in slots_nchw], out=out, ldo=64, engine=engine,
+             conv=dict(B=B, T=T, Fin=Fq, Fout=Fq, taps_t=2, dil=dil, stride_f=1, nslots=layer))
+    assert rel_max(out.view(B, T, Fq, 64), _cl(ref)) < TOL[engine]
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_gemm_strided_conv_and_subpixel(engine):
+    B, T, Fq = 2, 9, 21
+    Fh = (Fq - 1) // 2 + 1
+    x = rnd(B, 64, T, Fq, seed=40)
+    w, b = rnd(64, 64, 1, 3, seed=41, scale=0.07), rnd(64, seed=42, scale=0.1)
+    ref = F.conv2d(x.double(), w.double(), b.double(), stride=(1, 2), padding=(0, 1))
+    out = torch.empty(B * T * Fh, 64, device=DEV)
+    ops.gemm(loader=LOAD_CONV, epilogue=EPI_BIAS, M=B * T * Fh, w=packing.pack_weight(packing.conv_weight_matrix(w.cpu()), 64, b.cpu()).to(DEV),
+             a=[_cl(x)], out=out, ldo=64, engine=engine, conv=dict(B=B, T=T, Fin=Fq, Fout=Fh, taps_t=1, dil=1, stride_f=2, nslots=1))
+    assert rel_max(out.view(B, T, Fh, 64), _cl(ref)) < TOL[engine]
+    # sub-pixel (generator.py:85-92)
+    xs = rnd(B, 64, T, Fh, seed=43)
+    ws, bs = rnd(128, 64, 1, 3, seed=44, scale=0.07), rnd(128, seed=45, scale=0.1)
+    sd = {"p.conv.weight": ws.cpu(), "p.conv.bias": bs.cpu()}
+    ref = O.sub_pixel(xs.cpu(), sd, "p")
+    out = torch.empty(B * T * 2 * Fh, 64, device=DEV)
+    ops.gemm(loader=LOAD_CONV, epilogue=EPI_SUBPIXEL, M=B * T * Fh, w=packing.pack_weight(packing.conv_weight_matrix(ws.cpu()), 128, bs.cpu()).to(DEV),
+             a=[_cl(xs)], out=out, ldo=64, engine=engine, conv=dict(B=B, T=T, Fin=Fh, Fout=Fh, taps_t=1, dil=1, stride_f=1, nslots=1))
+    assert rel_max(out.view(B, T, 2 * Fh, 64).cpu(), _cl(ref)) < TOL[engine]
+
+
+# ------------------------------------------------------------------------------------------------ DSP bracket
+@pytest.mark.parametrize("engine", ENGINES)
+def test_compressed_stft_matches_oracle(engine):
+    x, _ = weights.synth_wave(3, 4800, seed=3, kind="speech")
+    ref = O.compressed_stft(x)
+    got = se_b200.compressed_stft(x.to(DEV), 400, 100, torch.hamming_window(400).to(DEV), engine=engine).cpu()
+    assert got.shape == ref.shape and got.dtype == torch.complex64
+    # BASELINE tolerance: compressed spectrogram within 1e-4 relative (rel-L2; worst-bin/peak reported alongside)
+    assert rel_l2(torch.view_as_real(got), torch.view_as_real(ref)) < 1e-4
+    assert rel_max(torch.view_as_real(got), torch.view_as_real(ref)) < (2e-4 if engine == "simt" else 1e-3)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_uncompressed_istft_matches_oracle(engine):
+    g = torch.Generator().manual_seed(4)
+    spec = torch.complex(torch.randn(2, 201, 33, generator=g), torch.randn(2, 201, 33, generator=g))
+    ref = O.uncompressed_istft(spec)
+    got = se_b200.uncompressed_istft(spec.to(DEV), 400, 100, torch.hamming_window(400).to(DEV), engine=engine).cpu()
+    assert got.shape == ref.shape
+    assert rel_max(got, ref) < (2e-5 if engine == "simt" else 1e-4)
+
+
+def test_rms_pad_and_layout_kernels():
+    x, _ = weights.synth_wave(3, 1950, seed=5, kind="noise")
+    xpad, c = ops.rms_pad(x.to(DEV), 2000, normalize=True)
+    cr = torch.sqrt(1950 / torch.sum(x ** 2.0, dim=-1))
+    assert rel_max(c.cpu(), cr) < 1e-6
+    xs = x * cr[:, None]
+    xs = torch.cat([xs, xs[:, :50]], -1)
+    ref = F.pad(xs.unsqueeze(1), (200, 200), mode="reflect").squeeze(1)
+    assert rel_max(xpad.cpu(), ref) < 1e-6
+    g = torch.Generator().manual_seed(6)
+    spec = torch.complex(torch.randn(2, 201, 37, generator=g), torch.randn(2, 201, 37, generator=g)).to(DEV)
+    in3 = ops.spec_to_in3(spec)
+    assert torch.equal(in3[..., 1], spec.real.permute(0, 2, 1)) and torch.equal(in3[..., 2], spec.imag.permute(0, 2, 1))
+    assert rel_max(in3[..., 0], spec.abs().permute(0, 2, 1)) < 1e-6
+    assert torch.equal(ops.in3_to_spec(in3), spec)
+
+
+# ------------------------------------------------------------------------------------------------ bandwidth kernels
+def test_conv1x1_inorm_prelu():
+    B, T, Fq = 3, 50, 201
+    in3 = rnd(B, T, Fq, 3, seed=50)
+    w, b = rnd(64, 3, seed=51), rnd(64, seed=52)
+    raw = torch.empty(B * T * Fq, 64, device=DEV)
+    ops.conv1x1_in3(in3, w, b, raw)
+    ref = in3.double() @ w.double().t() + b.double()
+    assert rel_max(raw.view(B, T, Fq, 64), ref) < 1e-6
+    g, be, sl = rnd(64, seed=53) * 0.1 + 1, rnd(64, seed=54) * 0.1, rnd(64, seed=55) * 0.05 + 0.25
+    x = raw.view(B, T * Fq, 64) * 2.0 + 5.0            # a mean well away from zero stresses the variance
+    x = x.contiguous()
+    stats = torch.empty(B, 64, 2, device=DEV)
+    wsb = ops.inorm_workspace(B, T * Fq, 64, DEV)
+    ops.inorm_stats(x, B, T * Fq, 64, stats, wsb)
+    y = torch.empty_like(x)
+    ops.inorm_prelu(x, B, T * Fq, stats, g, be, sl, y)
+    xn = x.permute(0, 2, 1).reshape(B, 64, T, Fq)
+    ref = F.prelu(F.instance_norm(xn.double(), weight=g.double(), bias=be.double(), eps=1e-5), sl.double())
+    assert rel_max(y.view(B, T, Fq, 64), ref.permute(0, 2, 3, 1)) < 1e-5
+    stats2 = torch.empty_like(stats)
+    ops.inorm_stats(x, B, T * Fq, 64, stats2, wsb)
+    assert torch.equal(stats, stats2)                  # deterministic reduction
+
+
+def test_heads_and_recombine():
+    B, T, Fq = 2, 17, 201
+    Fh = 101
+    sd = weights.synth_state_dict(2)
+    sp = rnd(B, 64, T, 2 * Fh, seed=60)
+    in3 = rnd(B, T, Fq, 3, seed=61)
+    spc = _cl(sp)
+    # mask head
+    m = "mask_decoder"
+    mraw = torch.empty(B * T, Fq, device=DEV)
+    ops.mask_conv(spc, B * T, 2 * Fh, sd[f"{m}.conv_1.weight"][0, :, 0, :].t().contiguous().to(DEV), float(sd[f"{m}.conv_1.bias"]), mraw)
+    ref_raw = F.conv2d(sp.cpu().double(), sd[f"{m}.conv_1.weight"].double(), sd[f"{m}.conv_1.bias"].double())
+    assert rel_max(mraw.view(B, T, Fq).cpu(), ref_raw[:, 0]) < 1e-5
+    st1 = torch.empty(B, 1, 2, device=DEV)
+    wsb = ops.inorm_workspace(B, T * 2 * Fh, 64, DEV)
+    ops.inorm_stats(mraw, B, T * Fq, 1, st1, wsb)
+    # complex head
+    c = "complex_decoder"
+    st = torch.empty(B, 64, 2, device=DEV)
+    ops.inorm_stats(spc, B, T * 2 * Fh, 64, st, wsb)
+    cplx = torch.empty(B * T, Fq, 2, device=DEV)
+    ops.complex_conv(spc, B, T, 2 * Fh, st, sd[f"{c}.norm.weight"].to(DEV), sd[f"{c}.norm.bias"].to(DEV), sd[f"{c}.prelu.weight"].to(DEV),
+                     sd[f"{c}.conv.weight"][:, :, 0, :].permute(0, 2, 1).contiguous().to(DEV), sd[f"{c}.conv.bias"].to(DEV), cplx)
+    h = F.prelu(F.instance_norm(sp.cpu(), weight=sd[f"{c}.norm.weight"], bias=sd[f"{c}.norm.bias"], eps=1e-5), sd[f"{c}.prelu.weight"])
+    ref_c = F.conv2d(h, sd[f"{c}.conv.weight"], sd[f"{c}.conv.bias"])                 # (B, 2, T, F)
+    assert rel_max(cplx.view(B, T, Fq, 2).cpu(), ref_c.permute(0, 2, 3, 1)) < 2e-5
+    # recombine
+    est = torch.empty(B * T, Fq, 2, device=DEV)
+    mask = torch.empty(B, T, Fq, device=DEV)
+    scal = (float(sd[f"{m}.norm.weight"]), float(sd[f"{m}.norm.bias"]), float(sd[f"{m}.prelu.weight"]),
+            float(sd[f"{m}.final_conv.weight"]), float(sd[f"{m}.final_conv.bias"]))
+    ops.mask_recombine(mraw, st1, B, T, Fq, scal, sd[f"{m}.prelu_out.weight"].to(DEV), in3, cplx, est, mask)
+    hm = F.prelu(F.instance_norm(ref_raw.float(), weight=sd[f"{m}.norm.weight"], bias=sd[f"{m}.norm.bias"], eps=1e-5), sd[f"{m}.prelu.weight"])
+    hm = F.conv2d(hm, sd[f"{m}.final_conv.weight"], sd[f"{m}.final_conv.bias"]).permute(0, 3, 2, 1).squeeze(-1)
+    ref_mask = F.prelu(hm, sd[f"{m}.prelu_out.weight"]).permute(0, 2, 1)                 # (B, T, F)
+    assert rel_max(mask.cpu(), ref_mask) < 2e-5
+    ref_est = ref_mask.unsqueeze(-1) * in3.cpu()[..., 1:3] + ref_c.permute(0, 2, 3, 1)
+    assert rel_max(est.view(B, T, Fq, 2).cpu(), ref_est) < 2e-5
+    re, im = torch.empty(B, 1, T, Fq, device=DEV), torch.empty(B, 1, T, Fq, device=DEV)
+    ops.split_ri(est, re, im)
+    assert torch.equal(re.view(B, T, Fq), est.view(B, T, Fq, 2)[..., 0]) and torch.equal(im.view(B, T, Fq), est.view(B, T, Fq, 2)[..., 1])
+
+
+def test_layernorm_residual():
+    x, r = rnd(1000, 64, seed=70, scale=2.0) + 1.0, rnd(1000, 64, seed=71)
+    g, b = rnd(64, seed=72) * 0.1 + 1, rnd(64, seed=73) * 0.1
+    out = torch.empty_like(x)
+    ops.layernorm_residual(x, g, b, r, out)
+    assert rel_max(out, F.layer_norm(x.double(), (64,), g.double(), b.double(), 1e-5) + r.double()) < 1e-5
+    r2 = r.clone()
+    ops.layernorm_residual(x, g, b, r2, r2)
+    assert torch.equal(r2, out)
+
+
+# ------------------------------------------------------------------------------------------------ sequence kernels
+def _seq_layouts(B, T, Fh):
+    return {"time": (ops.make_seq(B * Fh, T, Fh, T * Fh, Fh), lambda x: x.permute(0, 2, 1, 3).reshape(B * Fh, T, -1),
+                     lambda y: y.reshape(B, Fh, T, -1).permute(0, 2, 1, 3)),
+            "freq": (ops.make_seq(B * T, Fh, 1, Fh, 1), lambda x: x.reshape(B * T, Fh, -1), lambda y: y.reshape(B, T, Fh, -1))}
+
+
+def _attention_core_ref(qkv_seq, emb):
+    S, n, _ = qkv_seq.shape
+    q, k, v = (qkv_seq[..., i * 64:(i + 1) * 64].reshape(S, n, 4, 16).permute(0, 2, 1, 3).double() for i in range(3))
+    pos = torch.arange(n)
+    dist = (pos[:, None] - pos[None, :]).clamp(-512, 512) + 512
+    dots = (q @ k.transpose(-1, -2) + torch.einsum("bhnd,nrd->bhnr", q, emb.double()[dist])) * 0.25
+    return (dots.softmax(-1) @ v).permute(0, 2, 1, 3).reshape(S, n, 64)
+
+
+@pytest.mark.parametrize("variant", [1, 0])
+@pytest.mark.parametrize("axis,B,T,Fh", [("freq", 2, 5, 101), ("time", 1, 150, 3), ("time", 1, 700, 2), ("freq", 1, 3, 64)])
+def test_attention(variant, axis, B, T, Fh):
+    qkv = rnd(B, T, Fh, 192, seed=80, scale=1.5)
+    emb = rnd(1025, 16, seed=81)
+    seq, to_seq, from_seq = _seq_layouts(B, T, Fh)[axis]
+    out = torch.zeros(B * T * Fh, 64, device=DEV)
+    ops.attention(qkv.view(-1, 192), emb, seq, out, variant)
+    ref = from_seq(_attention_core_ref(to_seq(qkv.cpu()), emb.cpu()))
+    tol = 1e-5 if variant == 1 else 2e-3
+    assert rel_max(out.view(B, T, Fh, 64).cpu(), ref) < tol
+
+
+@pytest.mark.parametrize("axis,B,T,Fh", [("freq", 2, 5, 101), ("time", 2, 130, 3)])
+def test_dwconv_bn_swish(axis, B, T, Fh):
+    sd = weights.synth_state_dict(1)
+    p = "TSCB_1.time_conformer.conv.net"
+    u = rnd(B, T, Fh, 128, seed=90)
+    seq, to_seq, from_seq = _seq_layouts(B, T, Fh)[axis]
+    scale = sd[f"{p}.5.weight"] / torch.sqrt(sd[f"{p}.5.running_var"] + 1e-5)
+    shift = sd[f"{p}.5.bias"] + (sd[f"{p}.4.conv.bias"] - sd[f"{p}.5.running_mean"]) * scale
+    y = torch.empty_like(u)
+    ops.dwconv_bn_swish(u.view(-1, 128), seq, sd[f"{p}.4.conv.weight"].squeeze(1).t().contiguous().to(DEV), scale.to(DEV), shift.to(DEV), y.view(-1, 128))
+    h = to_seq(u.cpu()).transpose(1, 2)
+    h = F.conv1d(F.pad(h, (15, 15)), sd[f"{p}.4.conv.weight"], sd[f"{p}.4.conv.bias"], groups=128)
+    h = F.batch_norm(h, sd[f"{p}.5.running_mean"], sd[f"{p}.5.running_var"], sd[f"{p}.5.weight"], sd[f"{p}.5.bias"], False, 0.0, 1e-5)
+    ref = from_seq((h * torch.sigmoid(h)).transpose(1, 2))
+    assert rel_max(y.cpu(), ref) < 1e-5
