@@ -14,10 +14,18 @@ __global__ void __launch_bounds__(128) dwconv_bn_swish_kernel(const float* __res
   __shared__ float tile[DW_TI + DW_K - 1][DW_C];
   const int seq = blockIdx.x, i0 = blockIdx.y * DW_TI, c = threadIdx.x;
   const long long base = (long long)(seq / sq.inner) * sq.outer_stride + (seq % sq.inner);
-  // stage rows i0-15 .. i0+64+15 (zero outside the sequence)
-  for (int r = 0; r < DW_TI + DW_K - 1; ++r) {
-    const int i = i0 + r - DW_PAD;
-    tile[r][c] = (i >= 0 && i < sq.n) ? __ldg(x + (base + (long long)i * sq.pos_stride) * DW_C + c) : 0.f;
+  // stage rows i0-15 .. i0+64+15 (zero outside the sequence): 32 lanes x float4 cover one 512-byte row
+  {
+    constexpr int NV = (DW_TI + DW_K - 1) * (DW_C / 4);
+    float4* t4 = reinterpret_cast<float4*>(&tile[0][0]);
+#pragma unroll 6
+    for (int idx = threadIdx.x; idx < NV; idx += 128) {
+      const int r = idx >> 5, c4 = idx & 31;
+      const int i = i0 + r - DW_PAD;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i >= 0 && i < sq.n) v = ldg4(x + (base + (long long)i * sq.pos_stride) * DW_C + c4 * 4);
+      t4[idx] = v;
+    }
   }
   float wr[DW_K];
 #pragma unroll

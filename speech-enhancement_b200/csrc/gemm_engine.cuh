@@ -421,20 +421,40 @@ gemm_tc_kernel(const GemmArgs g, const uint8_t* __restrict__ w_tc) {
       ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(&full_bar[s]);
     }
-    // ---------------- epilogue: TMEM -> registers -> global ----------------
+    // ---------------- epilogue: TMEM -> registers -> (warp-private smem transpose) -> global ----------------
+    // tcgen05.ld 32x32b hands every lane one accumulator ROW; storing that way makes each warp-wide store touch 32
+    // different rows (32 half-used sectors per instruction).  The rows are therefore bounced through a 4 KB
+    // XOR-swizzled staging tile in the (now idle) stage-0 operand buffer so that 8 consecutive lanes write 128
+    // contiguous bytes of one row and the epilogue functors see a coalesced (row, column) mapping.
     ptx::mbar_wait(&accum_bar, 0);
     ptx::tc_fence_after();
-    const int row = (warp & 3) * 32 + lane;
-    const int half = warp >> 2;
+    const int wq = warp & 3, half = warp >> 2;
     constexpr int HALF_COLS = NT / 2;            // multiple of 8
-    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(half * HALF_COLS);
+    const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(half * HALF_COLS);
+    float4* stg = reinterpret_cast<float4*>(smem + warp * 4096);    // [32 rows][8 x float4]
 #pragma unroll 1
-    for (int c = 0; c < HALF_COLS; c += 8) {
-      float v[8];
-      ptx::tmem_ld8(taddr + c, v);
-      const int n = ntile * NT + half * HALF_COLS + c;
-      Epi<EK>::apply(g, m0 + row, n, make_float4(v[0], v[1], v[2], v[3]));
-      Epi<EK>::apply(g, m0 + row, n + 4, make_float4(v[4], v[5], v[6], v[7]));
+    for (int c0 = 0; c0 < HALF_COLS; c0 += 32) {
+      const int ncols = (HALF_COLS - c0 < 32) ? HALF_COLS - c0 : 32;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        if (j < ncols) {
+          float v[8];
+          ptx::tmem_ld8(taddr + c0 + j, v);
+          stg[lane * 8 + (((j >> 2) + 0) ^ (lane & 7))] = make_float4(v[0], v[1], v[2], v[3]);
+          stg[lane * 8 + (((j >> 2) + 1) ^ (lane & 7))] = make_float4(v[4], v[5], v[6], v[7]);
+        }
+      }
+      __syncwarp();
+      const int ch = lane & 7;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int R = it * 4 + (lane >> 3);
+        if (ch * 4 < ncols) {
+          const float4 val = stg[R * 8 + (ch ^ (R & 7))];
+          Epi<EK>::apply(g, m0 + wq * 32 + R, ntile * NT + half * HALF_COLS + c0 + ch * 4, val);
+        }
+      }
+      __syncwarp();
     }
     ptx::tc_fence_before();
   } else if (warp == 8) {
