@@ -128,8 +128,11 @@ int seb200_split_ri(const float* est, long long n, float* re, float* im, void* s
 typedef struct SebSeq { int nseq, n, inner; long long outer_stride, pos_stride; } SebSeq;
 
 /* Attention core with Shaw relative positions (conformer.py:103-122): qkv [tokens, 192] = (q | k | v), heads 4 x 16,
- * rel_pos_emb [1025, 16]; out [tokens, 64] ('b h n d -> b n (h d)').  variant 0 = tensor-core, 1 = SIMT reference */
-int seb200_attention(const float* qkv, const float* rel_pos_emb, const SebSeq* seq, float* out, int variant, void* stream);
+ * rel_pos_emb [1025, 16] fp32 and rel_pos_emb_h = the same table rounded to IEEE fp16 (packed once by the host);
+ * out [tokens, 64] ('b h n d -> b n (h d)').  variant 0 = tensor-core (reads rel_pos_emb_h), 1 = fp32 SIMT cross-check
+ * (reads rel_pos_emb) */
+int seb200_attention(const float* qkv, const float* rel_pos_emb, const void* rel_pos_emb_h, const SebSeq* seq, float* out,
+                     int variant, void* stream);
 /* DepthWiseConv1d(128, k=31, pad 15/15) + BatchNorm1d(eval) + Swish along the sequence axis (conformer.py:166-168):
  * x, y [tokens, 128]; w [31][128] (tap-major); bn_scale/bn_shift fold conv bias, running stats and affine */
 int seb200_dwconv_bn_swish(const float* x, const SebSeq* seq, const float* w, const float* bn_scale,

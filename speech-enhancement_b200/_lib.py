@@ -58,7 +58,7 @@ _SIGS = {
     "seb200_mask_recombine": [_fp, _fp, C.c_int, C.c_longlong, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
                               C.c_float, _fp, _fp, _fp, _fp, _fp, _fp],
     "seb200_split_ri": [_fp, C.c_longlong, _fp, _fp, _fp],
-    "seb200_attention": [_fp, _fp, C.POINTER(SebSeq), _fp, C.c_int, _fp],
+    "seb200_attention": [_fp, _fp, _fp, C.POINTER(SebSeq), _fp, C.c_int, _fp],
     "seb200_dwconv_bn_swish": [_fp, C.POINTER(SebSeq), _fp, _fp, _fp, _fp, _fp],
     "seb200_layernorm_residual": [_fp, C.c_longlong, _fp, _fp, _fp, _fp, _fp],
 }

@@ -3,12 +3,13 @@
 //
 //   dots[i, j] = scale * q_i . (k_j + E[clamp(i - j, -512, 512) + 512]),   out_i = softmax_j(dots) . v
 //
-// variant 0: tensor-core kernel (mma.sync m16n8k8 TF32, fp32 accumulate, online softmax).  The rel-pos term of a
-//            16 x 64 score tile is a second small GEMM  R = Q . E_window^T  (80 distinct offsets) followed by a
+// variant 0: tensor-core kernel (mma.sync m16n8k16 FP16 operands, fp32 accumulate, online softmax).  The rel-pos term
+//            of a 32 x 64 score tile is a second small GEMM  R = Q . E_window^T  (96 distinct offsets) followed by a
 //            skewed read  S[i, j] += R[i, i - j - dlo]  through a warp-private shared-memory staging buffer.
-//            TF32 (10-bit mantissa) is sufficient for the three attention contractions.
+//            A 10-bit mantissa is sufficient for the three attention contractions.
 // variant 1: one-thread-per-query fp32 kernel; slow, used by the tests to cross-check variant 0.
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace seb {
 
@@ -92,64 +93,75 @@ __global__ void __launch_bounds__(ATS_BQ) attention_simt_kernel(const float* __r
 }
 
 // ------------------------------------------------------------------------------------------------
-// variant 0: TF32 mma.sync flash attention with the rel-pos GEMM + skew
+// variant 0: FP16 mma.sync (m16n8k16, fp32 accumulate) flash attention with the rel-pos GEMM + skew
+//
+// CTA = 4 warps; a warp owns 32 query rows (two 16-row MMA tiles that share every B fragment) of one (sequence,
+// head).  Per 64-key tile: S = Q K^T (16 MMAs), R = Q E_window^T over the 96 distinct offsets of a 32 x 64 tile
+// (20 MMAs, E fragments straight from the fp16 table through L1), skew-add through a warp-private fp32 staging
+// tile, online softmax with ex2.approx, O += P V (16 MMAs, V staged transposed).  fp16 operands carry the same
+// 10-bit mantissa as TF32 (sufficient: SURVEY appendix B.1b); q is pre-scaled so logits stay far inside fp16 range.
+// The grid is flat with the query block as the fastest index, so the CTAs that share a sequence's K/V run together
+// and the re-reads hit L2.
 // ------------------------------------------------------------------------------------------------
-constexpr int AT_BQ = 64, AT_BK = 64, AT_LD = 20, AT_RLD = 84, AT_RW = 80;
+constexpr int A2_BK = 64, A2_KLD = 24 /*halfs*/, A2_VLD = 72 /*halfs*/, A2_RLD = 104 /*floats*/, A2_WROWS = 32;
+constexpr int A2_SMEM = A2_BK * A2_KLD * 2 + AT_D * A2_VLD * 2 + 4 * A2_WROWS * A2_RLD * 4;
 
-__device__ __forceinline__ uint32_t f2tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+__device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
-__global__ void __launch_bounds__(128) attention_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ E,
-                                                           const SebSeq sq, float* __restrict__ out) {
-  extern __shared__ __align__(16) float sm[];
-  const int seq = blockIdx.x >> 2, h = blockIdx.x & 3, i0 = blockIdx.y * AT_BQ;
-  const int n = sq.n;
+__global__ void __launch_bounds__(128, 3) attention_f16_kernel(const float* __restrict__ qkv, const __half* __restrict__ Eh,
+                                                              const SebSeq sq, int nqb, float* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  __half* Ks = reinterpret_cast<__half*>(smraw);                       // [64][24]
+  __half* Vt = Ks + A2_BK * A2_KLD;                                    // [16][72]   (V transposed: d-major)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  float* Rs = reinterpret_cast<float*>(Vt + AT_D * A2_VLD) + warp * A2_WROWS * A2_RLD;   // [32][104] per warp
+  const int sh = blockIdx.x / nqb, qb = blockIdx.x - sh * nqb;
+  const int seq = sh >> 2, h = sh & 3;
+  const int n = sq.n;
   const long long base = seq_base(sq, seq);
-  int e_lo = i0 - (n - 1); if (e_lo < -AT_MAXPOS) e_lo = -AT_MAXPOS;
-  int e_hi = i0 + AT_BQ - 1; if (e_hi > AT_MAXPOS) e_hi = AT_MAXPOS;
-  const int erows = e_hi - e_lo + 1;
-  uint32_t* Es = reinterpret_cast<uint32_t*>(sm);          // [erows][20] tf32
-  uint32_t* Ks = Es + erows * AT_LD;                        // [64][20]
-  uint32_t* Vs = Ks + AT_BK * AT_LD;                        // [64][20]
-  float* Rs = reinterpret_cast<float*>(Vs + AT_BK * AT_LD) + warp * 16 * AT_RLD;   // [16][84] per warp
+  const int iw = (qb * 4 + warp) * A2_WROWS;          // first query row of this warp
+  const bool warp_live = iw < n;
 
-  for (int idx = tid; idx < erows * 4; idx += 128) {
-    const int r = idx >> 2, part = idx & 3;
-    const float4 v = ldg4(E + (long long)(e_lo + AT_MAXPOS + r) * AT_D + part * 4);
-    *reinterpret_cast<uint4*>(Es + r * AT_LD + part * 4) = make_uint4(f2tf32(v.x), f2tf32(v.y), f2tf32(v.z), f2tf32(v.w));
-  }
-
-  // Q fragments (pre-scaled by dim_head^-0.5 * log2(e): softmax evaluated with exp2)
-  const int iw = i0 + warp * 16;
+  // Q fragments, pre-scaled by dim_head^-0.5 * log2(e)
   const float qs = 0.25f * 1.4426950408889634f;
   uint32_t qa[2][4];
-  {
-    int r0 = iw + g, r1 = iw + g + 8;
-    if (r0 >= n) r0 = n - 1;
-    if (r1 >= n) r1 = n - 1;
-    const float* q0 = qkv + (base + (long long)r0 * sq.pos_stride) * AT_ROW + h * AT_D;
-    const float* q1 = qkv + (base + (long long)r1 * sq.pos_stride) * AT_ROW + h * AT_D;
 #pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
-      qa[ks][0] = f2tf32(__ldg(q0 + ks * 8 + t) * qs);
-      qa[ks][1] = f2tf32(__ldg(q1 + ks * 8 + t) * qs);
-      qa[ks][2] = f2tf32(__ldg(q0 + ks * 8 + t + 4) * qs);
-      qa[ks][3] = f2tf32(__ldg(q1 + ks * 8 + t + 4) * qs);
-    }
+  for (int mt = 0; mt < 2; ++mt) {
+    int r0 = iw + mt * 16 + g, r1 = r0 + 8;
+    r0 = r0 < n ? r0 : n - 1;
+    r1 = r1 < n ? r1 : n - 1;
+    const float* q0 = qkv + (base + (long long)r0 * sq.pos_stride) * AT_ROW + h * AT_D + 2 * t;
+    const float* q1 = qkv + (base + (long long)r1 * sq.pos_stride) * AT_ROW + h * AT_D + 2 * t;
+    const float2 a = __ldg(reinterpret_cast<const float2*>(q0)), b = __ldg(reinterpret_cast<const float2*>(q1));
+    const float2 c = __ldg(reinterpret_cast<const float2*>(q0 + 8)), d = __ldg(reinterpret_cast<const float2*>(q1 + 8));
+    qa[mt][0] = pack_h2(a.x * qs, a.y * qs); qa[mt][1] = pack_h2(b.x * qs, b.y * qs);
+    qa[mt][2] = pack_h2(c.x * qs, c.y * qs); qa[mt][3] = pack_h2(d.x * qs, d.y * qs);
   }
-  float o[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
-  float mrow[2] = {-1e30f, -1e30f}, lrow[2] = {0.f, 0.f};
+  float o[2][2][4];
+  float mrow[2][2], lrow[2][2];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int x = 0; x < 2; ++x) {
+      mrow[mt][x] = -1e30f; lrow[mt][x] = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[mt][x][e] = 0.f;
+    }
 
-  for (int j0 = 0; j0 < n; j0 += AT_BK) {
+  for (int j0 = 0; j0 < n; j0 += A2_BK) {
     __syncthreads();
 #pragma unroll
     for (int rep = 0; rep < 2; ++rep) {
@@ -159,99 +171,134 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const float* __restr
         const float* p = qkv + (base + (long long)j * sq.pos_stride) * AT_ROW + h * AT_D + part * 4;
         kv = ldg4(p + 64); vv = ldg4(p + 128);
       }
-      *reinterpret_cast<uint4*>(Ks + key * AT_LD + part * 4) = make_uint4(f2tf32(kv.x), f2tf32(kv.y), f2tf32(kv.z), f2tf32(kv.w));
-      *reinterpret_cast<uint4*>(Vs + key * AT_LD + part * 4) = make_uint4(f2tf32(vv.x), f2tf32(vv.y), f2tf32(vv.z), f2tf32(vv.w));
+      *reinterpret_cast<uint2*>(Ks + key * A2_KLD + part * 4) = make_uint2(pack_h2(kv.x, kv.y), pack_h2(kv.z, kv.w));
+      Vt[(part * 4 + 0) * A2_VLD + key] = __float2half_rn(vv.x);
+      Vt[(part * 4 + 1) * A2_VLD + key] = __float2half_rn(vv.y);
+      Vt[(part * 4 + 2) * A2_VLD + key] = __float2half_rn(vv.z);
+      Vt[(part * 4 + 3) * A2_VLD + key] = __float2half_rn(vv.w);
     }
     __syncthreads();
+    if (!warp_live) continue;
 
-    // content scores S = Q K^T : 16 x 64 per warp
-    float s[8][4];
+    // ---- content scores: S[mt] = Q[mt] K^T  (16 x 64 each)
+    float s[2][8][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+      const uint32_t* kr = reinterpret_cast<const uint32_t*>(Ks + (nt * 8 + g) * A2_KLD) + t;
+      const uint32_t b0 = kr[0], b1 = kr[4];
 #pragma unroll
-      for (int ks = 0; ks < 2; ++ks) {
-        const uint32_t* kr = Ks + (nt * 8 + g) * AT_LD + ks * 8 + t;
-        mma_tf32(s[nt], qa[ks], kr[0], kr[4]);
+      for (int mt = 0; mt < 2; ++mt) {
+        s[mt][nt][0] = s[mt][nt][1] = s[mt][nt][2] = s[mt][nt][3] = 0.f;
+        mma_f16(s[mt][nt], qa[mt], b0, b1);
       }
     }
-    // relative-position scores R[r, dd] = q_r . E[clamp(dlo + dd)],  dd in [0, 80)
+    // ---- relative-position scores: R[r, dd] = q_r . E[clamp(dlo + dd)], dd in [0, 96)
     const int dlo = iw - j0 - 64;
 #pragma unroll
-    for (int nt = 0; nt < AT_RW / 8; ++nt) {
+    for (int nt = 0; nt < 12; ++nt) {
       int d = dlo + nt * 8 + g;
-      d = d < e_lo ? e_lo : (d > e_hi ? e_hi : d);
-      const uint32_t* er = Es + (d - e_lo) * AT_LD + t;
-      float r4[4] = {0.f, 0.f, 0.f, 0.f};
-      mma_tf32(r4, qa[0], er[0], er[4]);
-      mma_tf32(r4, qa[1], er[8], er[12]);
-      *reinterpret_cast<float2*>(Rs + g * AT_RLD + nt * 8 + 2 * t) = make_float2(r4[0], r4[1]);
-      *reinterpret_cast<float2*>(Rs + (g + 8) * AT_RLD + nt * 8 + 2 * t) = make_float2(r4[2], r4[3]);
-    }
-    __syncwarp();
-    // skew: S[r, c] += R[r, 64 + r - c]; mask keys beyond the sequence
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int r = g + ((e >> 1) << 3), c = nt * 8 + 2 * t + (e & 1);
-        const float v = s[nt][e] + Rs[r * AT_RLD + 64 + r - c];
-        s[nt][e] = (j0 + c < n) ? v : -1e30f;
+      d = d < -AT_MAXPOS ? -AT_MAXPOS : (d > AT_MAXPOS ? AT_MAXPOS : d);
+      const uint32_t* er = reinterpret_cast<const uint32_t*>(Eh + (d + AT_MAXPOS) * AT_D) + t;
+      const uint32_t e0 = __ldg(er), e1 = __ldg(er + 4);
+      if (nt < 10) {        // rows 0..15 use offsets 1..79
+        float r4[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_f16(r4, qa[0], e0, e1);
+        *reinterpret_cast<float2*>(Rs + g * A2_RLD + nt * 8 + 2 * t) = make_float2(r4[0], r4[1]);
+        *reinterpret_cast<float2*>(Rs + (g + 8) * A2_RLD + nt * 8 + 2 * t) = make_float2(r4[2], r4[3]);
+      }
+      if (nt >= 2) {        // rows 16..31 use offsets 17..95
+        float r4[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_f16(r4, qa[1], e0, e1);
+        *reinterpret_cast<float2*>(Rs + (16 + g) * A2_RLD + nt * 8 + 2 * t) = make_float2(r4[0], r4[1]);
+        *reinterpret_cast<float2*>(Rs + (24 + g) * A2_RLD + nt * 8 + 2 * t) = make_float2(r4[2], r4[3]);
       }
     }
     __syncwarp();
-    // online softmax (rows g and g+8 of this warp's slab)
+    // ---- skew: S[r, c] += R[r, 64 + r - c]
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int r = mt * 16 + g + ((e >> 1) << 3), c = nt * 8 + 2 * t + (e & 1);
+          s[mt][nt][e] += Rs[r * A2_RLD + 64 + r - c];
+        }
+    __syncwarp();
+    if (j0 + A2_BK > n) {   // mask keys beyond the sequence (last tile only)
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (j0 + nt * 8 + 2 * t + (e & 1) >= n) s[mt][nt][e] = -1e30f;
+    }
+    // ---- online softmax (base-2)
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int rh = 0; rh < 2; ++rh) {
+        float mx = -1e30f;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) mx = fmaxf(mx, fmaxf(s[mt][nt][2 * rh], s[mt][nt][2 * rh + 1]));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        const float mn = fmaxf(mrow[mt][rh], mx);
+        const float corr = ex2_approx(mrow[mt][rh] - mn);
+        mrow[mt][rh] = mn;
+        float sum = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          const float p0 = ex2_approx(s[mt][nt][2 * rh] - mn), p1 = ex2_approx(s[mt][nt][2 * rh + 1] - mn);
+          s[mt][nt][2 * rh] = p0; s[mt][nt][2 * rh + 1] = p1;
+          sum += p0 + p1;
+        }
+        lrow[mt][rh] = lrow[mt][rh] * corr + sum;
+        o[mt][0][2 * rh] *= corr; o[mt][0][2 * rh + 1] *= corr;
+        o[mt][1][2 * rh] *= corr; o[mt][1][2 * rh + 1] *= corr;
+      }
+    // ---- O += P V  (k = 16 keys per step; C fragments of two adjacent S n-tiles form one A fragment)
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t vb[2][2];
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb) {
+        const uint32_t* vr = reinterpret_cast<const uint32_t*>(Vt + (nb * 8 + g) * A2_VLD + ks * 16) + t;
+        vb[nb][0] = vr[0]; vb[nb][1] = vr[4];
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const uint32_t pa[4] = {pack_h2(s[mt][2 * ks][0], s[mt][2 * ks][1]), pack_h2(s[mt][2 * ks][2], s[mt][2 * ks][3]),
+                                pack_h2(s[mt][2 * ks + 1][0], s[mt][2 * ks + 1][1]), pack_h2(s[mt][2 * ks + 1][2], s[mt][2 * ks + 1][3])};
+        mma_f16(o[mt][0], pa, vb[0][0], vb[0][1]);
+        mma_f16(o[mt][1], pa, vb[1][0], vb[1][1]);
+      }
+    }
+  }
+  if (!warp_live) return;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
     for (int rh = 0; rh < 2; ++rh) {
-      float mx = -1e30f;
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) mx = fmaxf(mx, fmaxf(s[nt][2 * rh], s[nt][2 * rh + 1]));
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-      const float mn = fmaxf(mrow[rh], mx);
-      const float corr = exp2f(mrow[rh] - mn);
-      mrow[rh] = mn;
-      float sum = 0.f;
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        const float p0 = exp2f(s[nt][2 * rh] - mn), p1 = exp2f(s[nt][2 * rh + 1] - mn);
-        s[nt][2 * rh] = p0; s[nt][2 * rh + 1] = p1;
-        sum += p0 + p1;
+      float l = lrow[mt][rh];
+      l += __shfl_xor_sync(0xffffffffu, l, 1);
+      l += __shfl_xor_sync(0xffffffffu, l, 2);
+      const int i = iw + mt * 16 + g + 8 * rh;
+      if (i < n) {
+        const float inv = 1.0f / l;
+        float* op = out + (base + (long long)i * sq.pos_stride) * 64 + h * AT_D + 2 * t;
+        *reinterpret_cast<float2*>(op) = make_float2(o[mt][0][2 * rh] * inv, o[mt][0][2 * rh + 1] * inv);
+        *reinterpret_cast<float2*>(op + 8) = make_float2(o[mt][1][2 * rh] * inv, o[mt][1][2 * rh + 1] * inv);
       }
-      lrow[rh] = lrow[rh] * corr + sum;
-      o[0][2 * rh] *= corr; o[0][2 * rh + 1] *= corr;
-      o[1][2 * rh] *= corr; o[1][2 * rh + 1] *= corr;
     }
-    // O += P V.  The C-fragment columns (2t, 2t+1) of an 8-key block are fed as A-fragment k-slots (t, t+4); V rows
-    // are read with the same key permutation, so the sum over keys is unchanged.
-#pragma unroll
-    for (int kb = 0; kb < 8; ++kb) {
-      uint32_t pa[4] = {f2tf32(s[kb][0]), f2tf32(s[kb][2]), f2tf32(s[kb][1]), f2tf32(s[kb][3])};
-      const uint32_t* v0 = Vs + (kb * 8 + 2 * t) * AT_LD + g;
-      mma_tf32(o[0], pa, v0[0], v0[AT_LD]);
-      mma_tf32(o[1], pa, v0[8], v0[AT_LD + 8]);
-    }
-  }
-#pragma unroll
-  for (int rh = 0; rh < 2; ++rh) {
-    float l = lrow[rh];
-    l += __shfl_xor_sync(0xffffffffu, l, 1);
-    l += __shfl_xor_sync(0xffffffffu, l, 2);
-    const int i = iw + g + 8 * rh;
-    if (i < n) {
-      const float inv = 1.0f / l;
-      float* op = out + (base + (long long)i * sq.pos_stride) * 64 + h * AT_D + 2 * t;
-      *reinterpret_cast<float2*>(op) = make_float2(o[0][2 * rh] * inv, o[0][2 * rh + 1] * inv);
-      *reinterpret_cast<float2*>(op + 8) = make_float2(o[1][2 * rh] * inv, o[1][2 * rh + 1] * inv);
-    }
-  }
 }
 
 }  // namespace seb
 
 using namespace seb;
 
-extern "C" int seb200_attention(const float* qkv, const float* rel_pos_emb, const SebSeq* seq, float* out, int variant, void* stream) {
+extern "C" int seb200_attention(const float* qkv, const float* rel_pos_emb, const void* rel_pos_emb_h, const SebSeq* seq, float* out, int variant, void* stream) {
   SEB_REQUIRE(qkv && rel_pos_emb && seq && out && aligned16(qkv) && aligned16(out) && aligned16(rel_pos_emb), SEB_EINVAL, "attention: null/unaligned argument");
   SEB_REQUIRE(seq->nseq > 0 && seq->n > 0 && seq->inner > 0 && seq->nseq <= (1 << 28), SEB_EINVAL, "attention: bad sequence descriptor");
   const int n = seq->n;
@@ -267,13 +314,17 @@ extern "C" int seb200_attention(const float* qkv, const float* rel_pos_emb, cons
     SEB_CHECK_LAUNCH("attention_simt_kernel");
     return 0;
   }
-  int erows = n + AT_BQ - 1; if (erows > 2 * AT_MAXPOS + 1) erows = 2 * AT_MAXPOS + 1;
-  const int smem = (erows * AT_LD + 2 * AT_BK * AT_LD + 4 * 16 * AT_RLD) * (int)sizeof(float);
-  cudaError_t e = cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e != cudaSuccess) { set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-  dim3 grid(seq->nseq * AT_H, (n + AT_BQ - 1) / AT_BQ);
-  SEB_REQUIRE(grid.y <= 65535u, SEB_EINVAL, "attention: sequence too long");
-  attention_mma_kernel<<<grid, 128, smem, st>>>(qkv, rel_pos_emb, *seq, out);
-  SEB_CHECK_LAUNCH("attention_mma_kernel");
+  SEB_REQUIRE(rel_pos_emb_h && aligned16(rel_pos_emb_h), SEB_EINVAL, "attention: the tensor-core variant needs the fp16 copy of rel_pos_emb");
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(attention_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM);
+    if (e != cudaSuccess) { set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    attr_done = true;
+  }
+  const int nqb = ((n + A2_WROWS - 1) / A2_WROWS + 3) / 4;
+  const long long nblocks = (long long)seq->nseq * AT_H * nqb;
+  SEB_REQUIRE(nblocks < 2147483647LL, SEB_EINVAL, "attention: grid too large");
+  attention_f16_kernel<<<(unsigned)nblocks, 128, A2_SMEM, st>>>(qkv, reinterpret_cast<const __half*>(rel_pos_emb_h), *seq, nqb, out);
+  SEB_CHECK_LAUNCH("attention_f16_kernel");
   return 0;
 }

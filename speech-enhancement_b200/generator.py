@@ -191,6 +191,7 @@ class TSCNet(nn.Module):
                 P[f"{p}.attn.qkv"] = pack_weight(wqkv, 192, None).to(device)
                 P[f"{p}.attn.out"] = pack_weight(sd[f"{p}.attn.fn.to_out.weight"], 64, sd[f"{p}.attn.fn.to_out.bias"]).to(device)
                 P[f"{p}.attn.emb"] = dev(sd[f"{p}.attn.fn.rel_pos_emb.weight"])
+                P[f"{p}.attn.emb_h"] = dev(sd[f"{p}.attn.fn.rel_pos_emb.weight"].to(torch.float16))
                 P[f"{p}.attn.ln"] = (dev(sd[f"{p}.attn.norm.weight"]), dev(sd[f"{p}.attn.norm.bias"]))
                 P[f"{p}.conv.ln"] = (dev(sd[f"{p}.conv.net.0.weight"]), dev(sd[f"{p}.conv.net.0.bias"]))
                 w1, b1 = glu_interleave(sd[f"{p}.conv.net.2.weight"].squeeze(-1), sd[f"{p}.conv.net.2.bias"])
@@ -277,7 +278,7 @@ class TSCNet(nn.Module):
         ops.gemm(loader=LOAD_ROWS, epilogue=EPI_RESID, M=M, w=P[f"{p}.ff1.w2"], a=[h], lda=256, out=y, ldo=64, resid=x, ldr=64, alpha=0.5, engine=eng, label="ffn2")
         # y += Attn(LN(y))
         ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_BIAS, M=M, w=P[f"{p}.attn.qkv"], a=[y], lda=64, ln=P[f"{p}.attn.ln"], out=qkv, ldo=192, engine=eng, label="qkv")
-        ops.attention(qkv, P[f"{p}.attn.emb"], seq, o, self.attention_variant)
+        ops.attention(qkv, P[f"{p}.attn.emb"], seq, o, self.attention_variant, P[f"{p}.attn.emb_h"])
         ops.gemm(loader=LOAD_ROWS, epilogue=EPI_RESID, M=M, w=P[f"{p}.attn.out"], a=[o], lda=64, out=y, ldo=64, resid=y, ldr=64, alpha=1.0, engine=eng, label="attn_out")
         # y += ConvModule(y)
         ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_GLU, M=M, w=P[f"{p}.conv.pw1"], a=[y], lda=64, ln=P[f"{p}.conv.ln"], out=u, ldo=128, engine=eng, label="pw1_glu")

@@ -263,10 +263,15 @@ def make_seq(nseq: int, n: int, inner: int, outer_stride: int, pos_stride: int) 
     return s
 
 
-def attention(qkv, rel_pos_emb, seq: SebSeq, out, variant: int = 0):
+def attention(qkv, rel_pos_emb, seq: SebSeq, out, variant: int = 0, rel_pos_emb_h=None):
     _f32c(qkv, rel_pos_emb, out)
+    if variant == 0:
+        if rel_pos_emb_h is None:
+            rel_pos_emb_h = rel_pos_emb.to(torch.float16)
+        if rel_pos_emb_h.dtype != torch.float16 or not rel_pos_emb_h.is_contiguous():
+            raise RuntimeError("rel_pos_emb_h must be a contiguous float16 copy of the embedding table")
     tok = _pb("attention", 96.0 * 4 * seq.nseq * seq.n * seq.n, 4.0 * (qkv.numel() + out.numel())) if _PROF is not None else None
-    check(_lib.load().seb200_attention(ptr(qkv), ptr(rel_pos_emb), C.byref(seq), ptr(out), variant, stream_ptr()), "seb200_attention")
+    check(_lib.load().seb200_attention(ptr(qkv), ptr(rel_pos_emb), ptr(rel_pos_emb_h), C.byref(seq), ptr(out), variant, stream_ptr()), "seb200_attention")
     _pe(tok)
     return out
 
