@@ -76,6 +76,20 @@ typedef struct SebGemm {
 
 int seb200_gemm(const SebGemm* g, int engine, void* stream);
 
+/* Fused conformer feed-forward half-step on tcgen05 (conformer.py:53-71,128-145,207,210 [+ :211, generator.py:70,72]):
+ *   y = x + alpha * (W2 . swish(W1 . LayerNorm(x) + b1) + b2);   out = post_gamma ? LayerNorm_post(y) + resid2 : y
+ * x, out, resid2: [tokens, 64] fp32 (out may alias x or resid2); w1_tc / w2_tc: tcgen05 images of W1 [256, 64] and
+ * W2 [64, 256] packed with n-tile 64 (see packing.py); the 256-wide hidden activation stays in TMEM / shared memory. */
+typedef struct SebFfn {
+  const float* x; float* out; long long tokens;
+  const float* ln_gamma; const float* ln_beta;
+  const void* w1_tc; const float* b1;
+  const void* w2_tc; const float* b2;
+  float alpha;
+  const float* post_gamma; const float* post_beta; const float* resid2;   /* optional (all three or none) */
+} SebFfn;
+int seb200_ffn_fused(const SebFfn* f, void* stream);
+
 /* ---- DSP bracket --------------------------------------------------------- */
 /* predict() glue, inference_gan.py:79-87 + torch.stft's reflect padding: per utterance
  * c = sqrt(L / sum x^2); xpad[b, 0 : Lp+400] = reflect200(wrap_pad(c * x)); c_out[b] = c. */

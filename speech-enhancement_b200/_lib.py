@@ -37,6 +37,12 @@ class SebGemm(C.Structure):
     ]
 
 
+class SebFfn(C.Structure):
+    _fields_ = [("x", _fp), ("out", _fp), ("tokens", C.c_longlong), ("ln_gamma", _fp), ("ln_beta", _fp),
+                ("w1_tc", _fp), ("b1", _fp), ("w2_tc", _fp), ("b2", _fp), ("alpha", C.c_float),
+                ("post_gamma", _fp), ("post_beta", _fp), ("resid2", _fp)]
+
+
 class SebSeq(C.Structure):
     _fields_ = [("nseq", C.c_int), ("n", C.c_int), ("inner", C.c_int),
                 ("outer_stride", C.c_longlong), ("pos_stride", C.c_longlong)]
@@ -44,6 +50,7 @@ class SebSeq(C.Structure):
 
 _SIGS = {
     "seb200_gemm": [C.POINTER(SebGemm), C.c_int, _fp],
+    "seb200_ffn_fused": [C.POINTER(SebFfn), _fp],
     "seb200_rms_pad": [_fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp],
     "seb200_spec_to_in3": [_fp, C.c_int, C.c_int, C.c_int, _fp, _fp],
     "seb200_in3_to_spec": [_fp, C.c_int, C.c_int, C.c_int, _fp, _fp],

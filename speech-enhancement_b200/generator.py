@@ -184,7 +184,7 @@ class TSCNet(nn.Module):
             for ax in ("time", "freq"):
                 p = f"TSCB_{i}.{ax}_conformer"
                 for ff in ("ff1", "ff2"):
-                    P[f"{p}.{ff}.w1"] = pack_weight(sd[f"{p}.{ff}.fn.fn.net.0.weight"], 256, sd[f"{p}.{ff}.fn.fn.net.0.bias"]).to(device)
+                    P[f"{p}.{ff}.w1"] = pack_weight(sd[f"{p}.{ff}.fn.fn.net.0.weight"], 64, sd[f"{p}.{ff}.fn.fn.net.0.bias"]).to(device)
                     P[f"{p}.{ff}.w2"] = pack_weight(sd[f"{p}.{ff}.fn.fn.net.3.weight"], 64, sd[f"{p}.{ff}.fn.fn.net.3.bias"]).to(device)
                     P[f"{p}.{ff}.ln"] = (dev(sd[f"{p}.{ff}.fn.norm.weight"]), dev(sd[f"{p}.{ff}.fn.norm.bias"]))
                 wqkv = torch.cat([sd[f"{p}.attn.fn.to_q.weight"], sd[f"{p}.attn.fn.to_kv.weight"]], dim=0)
@@ -273,9 +273,13 @@ class TSCNet(nn.Module):
         """ConformerBlock.forward + the TSCB outer residual (conformer.py:206-212, generator.py:70,72); x updated in place."""
         eng = self.engine
         y, h, qkv, o, u, v = ws["y"], ws["h"], ws["qkv"], ws["o"], ws["u"], ws["v"]
+        fused = eng == "tcgen05"
         # y = x + 0.5 * FF1(LN(x))
-        ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_SWISH, M=M, w=P[f"{p}.ff1.w1"], a=[x], lda=64, ln=P[f"{p}.ff1.ln"], out=h, ldo=256, engine=eng, label="ffn1")
-        ops.gemm(loader=LOAD_ROWS, epilogue=EPI_RESID, M=M, w=P[f"{p}.ff1.w2"], a=[h], lda=256, out=y, ldo=64, resid=x, ldr=64, alpha=0.5, engine=eng, label="ffn2")
+        if fused:
+            ops.ffn_fused(x, y, P[f"{p}.ff1.ln"], P[f"{p}.ff1.w1"], P[f"{p}.ff1.w2"], 0.5)
+        else:
+            ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_SWISH, M=M, w=P[f"{p}.ff1.w1"], a=[x], lda=64, ln=P[f"{p}.ff1.ln"], out=h, ldo=256, engine=eng, label="ffn1")
+            ops.gemm(loader=LOAD_ROWS, epilogue=EPI_RESID, M=M, w=P[f"{p}.ff1.w2"], a=[h], lda=256, out=y, ldo=64, resid=x, ldr=64, alpha=0.5, engine=eng, label="ffn2")
         # y += Attn(LN(y))
         ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_BIAS, M=M, w=P[f"{p}.attn.qkv"], a=[y], lda=64, ln=P[f"{p}.attn.ln"], out=qkv, ldo=192, engine=eng, label="qkv")
         ops.attention(qkv, P[f"{p}.attn.emb"], seq, o, self.attention_variant, P[f"{p}.attn.emb_h"])
@@ -284,11 +288,13 @@ class TSCNet(nn.Module):
         ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_GLU, M=M, w=P[f"{p}.conv.pw1"], a=[y], lda=64, ln=P[f"{p}.conv.ln"], out=u, ldo=128, engine=eng, label="pw1_glu")
         ops.dwconv_bn_swish(u, seq, P[f"{p}.conv.dw"], P[f"{p}.conv.bn"][0], P[f"{p}.conv.bn"][1], v)
         ops.gemm(loader=LOAD_ROWS, epilogue=EPI_RESID, M=M, w=P[f"{p}.conv.pw2"], a=[v], lda=128, out=y, ldo=64, resid=y, ldr=64, alpha=1.0, engine=eng, label="pw2")
-        # y += 0.5 * FF2(LN(y))
-        ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_SWISH, M=M, w=P[f"{p}.ff2.w1"], a=[y], lda=64, ln=P[f"{p}.ff2.ln"], out=h, ldo=256, engine=eng, label="ffn1")
-        ops.gemm(loader=LOAD_ROWS, epilogue=EPI_RESID, M=M, w=P[f"{p}.ff2.w2"], a=[h], lda=256, out=y, ldo=64, resid=y, ldr=64, alpha=0.5, engine=eng, label="ffn2")
-        # x = post_norm(y) + x
-        ops.layernorm_residual(y, P[f"{p}.post_norm"][0], P[f"{p}.post_norm"][1], x, x)
+        # x = post_norm(y + 0.5 * FF2(LN(y))) + x
+        if fused:
+            ops.ffn_fused(y, x, P[f"{p}.ff2.ln"], P[f"{p}.ff2.w1"], P[f"{p}.ff2.w2"], 0.5, post=P[f"{p}.post_norm"], resid2=x)
+        else:
+            ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_SWISH, M=M, w=P[f"{p}.ff2.w1"], a=[y], lda=64, ln=P[f"{p}.ff2.ln"], out=h, ldo=256, engine=eng, label="ffn1")
+            ops.gemm(loader=LOAD_ROWS, epilogue=EPI_RESID, M=M, w=P[f"{p}.ff2.w2"], a=[h], lda=256, out=y, ldo=64, resid=y, ldr=64, alpha=0.5, engine=eng, label="ffn2")
+            ops.layernorm_residual(y, P[f"{p}.post_norm"][0], P[f"{p}.post_norm"][1], x, x)
         return x
 
     # -----------------------------------------------------------------------------------------

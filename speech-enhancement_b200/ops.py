@@ -14,7 +14,7 @@ import torch
 
 from . import _lib
 from ._lib import (ENGINE_SIMT, ENGINE_TCGEN05, EPI_BIAS, EPI_COMPRESS, EPI_GLU, EPI_RESID, EPI_SUBPIXEL, EPI_SWISH,
-                   LOAD_CONV, LOAD_HANKEL, LOAD_ROWS, LOAD_ROWS_LN, SebGemm, SebSeq, check, ptr, require_cuda, stream_ptr)
+                   LOAD_CONV, LOAD_HANKEL, LOAD_ROWS, LOAD_ROWS_LN, SebFfn, SebGemm, SebSeq, check, ptr, require_cuda, stream_ptr)
 from .packing import PackedWeight
 
 ENGINES = {"tcgen05": ENGINE_TCGEN05, "simt": ENGINE_SIMT}
@@ -121,6 +121,24 @@ def gemm(*, loader: int, epilogue: int, M: int, w: PackedWeight, a: Sequence[tor
     g.resid, g.ldr, g.alpha = ptr(resid), ldr, alpha
     tok = _pb(label, 2.0 * M * g.N * (k_logical or w.K), 4.0 * M * (g.N + (k_logical or w.K))) if _PROF is not None else None
     check(lib.seb200_gemm(C.byref(g), ENGINES[engine], stream_ptr()), "seb200_gemm")
+    _pe(tok)
+    return out
+
+
+def ffn_fused(x, out, ln, w1: PackedWeight, w2: PackedWeight, alpha: float = 0.5, post=None, resid2=None):
+    """y = x + alpha * FF(LN(x)); with ``post=(gamma, beta)``: out = LN_post(y) + resid2.  One tcgen05 kernel."""
+    _f32c(x, out, resid2)
+    if w1.tc_ntile != 64 or w2.tc_ntile != 64 or w1.N != 256 or w2.N != 64 or w1.K != 64 or w2.K != 256:
+        raise RuntimeError("ffn_fused expects W1 [256,64] and W2 [64,256] packed with n-tile 64")
+    f = SebFfn()
+    f.x, f.out, f.tokens = ptr(x), ptr(out), x.numel() // 64
+    f.ln_gamma, f.ln_beta = ptr(ln[0]), ptr(ln[1])
+    f.w1_tc, f.b1, f.w2_tc, f.b2 = ptr(w1.w_tc), ptr(w1.bias), ptr(w2.w_tc), ptr(w2.bias)
+    f.alpha = alpha
+    if post is not None:
+        f.post_gamma, f.post_beta, f.resid2 = ptr(post[0]), ptr(post[1]), ptr(resid2)
+    tok = _pb("ffn_fused", 2.0 * 2 * 64 * 256 * f.tokens, 4.0 * 64 * f.tokens * (3 if post is None else 4)) if _PROF is not None else None
+    check(_lib.load().seb200_ffn_fused(C.byref(f), stream_ptr()), "seb200_ffn_fused")
     _pe(tok)
     return out
 

@@ -65,6 +65,31 @@ def test_gemm_layernorm_loader_epilogues(engine):
     assert rel_max(out, xn @ wq.double().t()) < TOL[engine]
 
 
+@pytest.mark.parametrize("M", [128, 777, 40000])
+def test_ffn_fused_tcgen05(M):
+    """LayerNorm -> 64->256 -> Swish -> 256->64 -> *0.5 + x (-> post_norm + residual) in one tcgen05 kernel"""
+    x = rnd(M, 64, seed=11, scale=2.0) + 0.3
+    g, be = rnd(64, seed=12, scale=0.2) + 1.0, rnd(64, seed=13, scale=0.2)
+    w1, b1 = rnd(256, 64, seed=14, scale=0.17), rnd(256, seed=15, scale=0.1)
+    w2, b2 = rnd(64, 256, seed=16, scale=0.09), rnd(64, seed=17, scale=0.1)
+    pg, pb, r2 = rnd(64, seed=18, scale=0.2) + 1.0, rnd(64, seed=19, scale=0.2), rnd(M, 64, seed=20)
+    pw1 = packing.pack_weight(w1.cpu(), 64, b1.cpu()).to(DEV)
+    pw2 = packing.pack_weight(w2.cpu(), 64, b2.cpu()).to(DEV)
+    xd = x.double()
+    h = F.layer_norm(xd, (64,), g.double(), be.double(), 1e-5) @ w1.double().t() + b1.double()
+    y_ref = xd + 0.5 * ((h * torch.sigmoid(h)) @ w2.double().t() + b2.double())
+    y = torch.empty_like(x)
+    ops.ffn_fused(x, y, (g, be), pw1, pw2, 0.5)
+    assert rel_max(y, y_ref) < TOL["tcgen05"]
+    xi = x.clone()
+    ops.ffn_fused(xi, xi, (g, be), pw1, pw2, 0.5)                     # in place
+    assert torch.equal(xi, y)
+    out_ref = F.layer_norm(y_ref, (64,), pg.double(), pb.double(), 1e-5) + r2.double()
+    r2i = r2.clone()
+    ops.ffn_fused(x, r2i, (g, be), pw1, pw2, 0.5, post=(pg, pb), resid2=r2i)   # out aliases resid2 (how the conformer calls it)
+    assert rel_max(r2i, out_ref) < TOL["tcgen05"]
+
+
 def _cl(x):      # (B, C, T, F) -> channels-last [B, T, F, C] contiguous
     return x.permute(0, 2, 3, 1).contiguous()
 
