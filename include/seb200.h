@@ -48,7 +48,8 @@ enum {
   SEB_EPI_GLU = 2,      /* columns interleaved (value, gate): out[n/2] = v * sigmoid(g) */
   SEB_EPI_RESID = 3,    /* out = alpha * (acc + bias) + resid                */
   SEB_EPI_SUBPIXEL = 4, /* out[(bt*2Fo + 2w + n/64), n%64] = acc + bias      */
-  SEB_EPI_COMPRESS = 5  /* columns interleaved (re, im): out[m, k, 0..2] = (|X|^.3, re|X|^-.7, im|X|^-.7) */
+  SEB_EPI_COMPRESS = 5, /* columns interleaved (re, im): out[m, k, 0..2] = (|X|^.3, re|X|^-.7, im|X|^-.7) */
+  SEB_EPI_QKV_F16 = 6   /* out is __half [M, 192] = (q * 0.25 * log2(e) | k | v): input of seb200_attention variant 0 */
 };
 enum { SEB_ENGINE_TCGEN05 = 0, SEB_ENGINE_SIMT = 1 };
 
@@ -141,11 +142,12 @@ int seb200_split_ri(const float* est, long long n, float* re, float* im, void* s
  * freq conformer (generator.py:71): inner = 1,  outer_stride = F',   pos_stride = 1,  nseq = B*T,  n = F' */
 typedef struct SebSeq { int nseq, n, inner; long long outer_stride, pos_stride; } SebSeq;
 
-/* Attention core with Shaw relative positions (conformer.py:103-122): qkv [tokens, 192] = (q | k | v), heads 4 x 16,
- * rel_pos_emb [1025, 16] fp32 and rel_pos_emb_h = the same table rounded to IEEE fp16 (packed once by the host);
- * out [tokens, 64] ('b h n d -> b n (h d)').  variant 0 = tensor-core (reads rel_pos_emb_h), 1 = fp32 SIMT cross-check
- * (reads rel_pos_emb) */
-int seb200_attention(const float* qkv, const float* rel_pos_emb, const void* rel_pos_emb_h, const SebSeq* seq, float* out,
+/* Attention core with Shaw relative positions (conformer.py:103-122): qkv [tokens, 192] = (q | k | v), heads 4 x 16;
+ * out [tokens, 64] fp32 ('b h n d -> b n (h d)').
+ *   variant 0 (tensor cores): qkv is __half, q pre-scaled by 0.25 * log2(e) (SEB_EPI_QKV_F16 writes it);
+ *                             rel_pos_emb_h = rel_pos_emb [1025, 16] rounded to IEEE fp16 (packed once by the host)
+ *   variant 1 (fp32 SIMT cross-check): qkv is float, unscaled; rel_pos_emb [1025, 16] fp32 */
+int seb200_attention(const void* qkv, const float* rel_pos_emb, const void* rel_pos_emb_h, const SebSeq* seq, float* out,
                      int variant, void* stream);
 /* DepthWiseConv1d(128, k=31, pad 15/15) + BatchNorm1d(eval) + Swish along the sequence axis (conformer.py:166-168):
  * x, y [tokens, 128]; w [31][128] (tap-major); bn_scale/bn_shift fold conv bias, running stats and affine */

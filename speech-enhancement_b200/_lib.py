@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libseb200.so")
 
 LOAD_ROWS, LOAD_ROWS_LN, LOAD_CONV, LOAD_HANKEL = 0, 1, 2, 3
-EPI_BIAS, EPI_SWISH, EPI_GLU, EPI_RESID, EPI_SUBPIXEL, EPI_COMPRESS = 0, 1, 2, 3, 4, 5
+EPI_BIAS, EPI_SWISH, EPI_GLU, EPI_RESID, EPI_SUBPIXEL, EPI_COMPRESS, EPI_QKV_F16 = 0, 1, 2, 3, 4, 5, 6
 ENGINE_TCGEN05, ENGINE_SIMT = 0, 1
 
 _fp = C.c_void_p  # raw device pointers travel as void*

@@ -95,16 +95,20 @@ __global__ void __launch_bounds__(ATS_BQ) attention_simt_kernel(const float* __r
 // ------------------------------------------------------------------------------------------------
 // variant 0: FP16 mma.sync (m16n8k16, fp32 accumulate) flash attention with the rel-pos GEMM + skew
 //
+// Input is the fp16 projection [tokens, 192] = (q * dim_head^-0.5 * log2 e | k | v) written by the QKV GEMM epilogue.
 // CTA = 4 warps; a warp owns 32 query rows (two 16-row MMA tiles that share every B fragment) of one (sequence,
-// head).  Per 64-key tile: S = Q K^T (16 MMAs), R = Q E_window^T over the 96 distinct offsets of a 32 x 64 tile
+// head).  K/V tiles stream through a cp.async double buffer (no register staging, no conversion); B fragments come
+// from ldmatrix (.trans for V); a ones column appended to V makes the P V product deliver the softmax row sums.  Per 64-key tile: S = Q K^T (16 MMAs), R = Q E_window^T over the 96 distinct offsets of a 32 x 64 tile
 // (20 MMAs, E fragments straight from the fp16 table through L1), skew-add through a warp-private fp32 staging
 // tile, online softmax with ex2.approx, O += P V (16 MMAs, V staged transposed).  fp16 operands carry the same
 // 10-bit mantissa as TF32 (sufficient: SURVEY appendix B.1b); q is pre-scaled so logits stay far inside fp16 range.
 // The grid is flat with the query block as the fastest index, so the CTAs that share a sequence's K/V run together
 // and the re-reads hit L2.
 // ------------------------------------------------------------------------------------------------
-constexpr int A2_BK = 64, A2_KLD = 24 /*halfs*/, A2_VLD = 72 /*halfs*/, A2_RLD = 104 /*floats*/, A2_WROWS = 32;
-constexpr int A2_SMEM = A2_BK * A2_KLD * 2 + AT_D * A2_VLD * 2 + 4 * A2_WROWS * A2_RLD * 4;
+constexpr int A2_BK = 64, A2_LD = 24 /*halfs per K / V row (16 + pad: conflict-free ldmatrix)*/, A2_RLD = 104 /*floats*/, A2_WROWS = 32;
+constexpr int A2_TILE_H = A2_BK * A2_LD;                                   // halfs per K (or V) tile
+constexpr int A2_SMEM = 2 * 2 * A2_TILE_H * 2 + 4 * A2_WROWS * A2_RLD * 4;   // double-buffered K,V + R staging
+constexpr int AT_ROWH = 192;                                               // fp16 qkv row: q(64) | k(64) | v(64)
 
 __device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -120,76 +124,98 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
+               ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
 
-__global__ void __launch_bounds__(128, 3) attention_f16_kernel(const float* __restrict__ qkv, const __half* __restrict__ Eh,
+__global__ void __launch_bounds__(128, 3) attention_f16_kernel(const __half* __restrict__ qkvh, const __half* __restrict__ Eh,
                                                               const SebSeq sq, int nqb, float* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smraw[];
-  __half* Ks = reinterpret_cast<__half*>(smraw);                       // [64][24]
-  __half* Vt = Ks + A2_BK * A2_KLD;                                    // [16][72]   (V transposed: d-major)
+  __half* KV = reinterpret_cast<__half*>(smraw);                       // [buf 2][K | V][64][24]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  float* Rs = reinterpret_cast<float*>(Vt + AT_D * A2_VLD) + warp * A2_WROWS * A2_RLD;   // [32][104] per warp
+  float* Rs = reinterpret_cast<float*>(KV + 4 * A2_TILE_H) + warp * A2_WROWS * A2_RLD;   // [32][104] per warp
   const int sh = blockIdx.x / nqb, qb = blockIdx.x - sh * nqb;
   const int seq = sh >> 2, h = sh & 3;
   const int n = sq.n;
   const long long base = seq_base(sq, seq);
+  const __half* hbase = qkvh + h * AT_D;
   const int iw = (qb * 4 + warp) * A2_WROWS;          // first query row of this warp
   const bool warp_live = iw < n;
 
-  // Q fragments, pre-scaled by dim_head^-0.5 * log2(e)
-  const float qs = 0.25f * 1.4426950408889634f;
+  // K/V tile loader: 64 keys x (2 + 2) 16-byte chunks, 2 cp.async per thread; keys past the sequence are zero-filled
+  auto issue_tile = [&](int tile) {
+    __half* dstb = KV + (tile & 1) * 2 * A2_TILE_H;
+#pragma unroll
+    for (int rep = 0; rep < 2; ++rep) {
+      const int idx = tid + rep * 128, key = idx >> 2, c = idx & 3;
+      const int j = tile * A2_BK + key;
+      const int jj = j < n ? j : n - 1;
+      const __half* src = hbase + (base + (long long)jj * sq.pos_stride) * AT_ROWH + 64 + (c >> 1) * 64 + (c & 1) * 8;
+      cp_async16(dstb + (c >> 1) * A2_TILE_H + key * A2_LD + (c & 1) * 8, src, j < n ? 16 : 0);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  const int ntiles = (n + A2_BK - 1) / A2_BK;
+  issue_tile(0);
+
+  // Q fragments (already scaled by dim_head^-0.5 * log2(e) and rounded to fp16 by the projection epilogue)
   uint32_t qa[2][4];
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt) {
     int r0 = iw + mt * 16 + g, r1 = r0 + 8;
     r0 = r0 < n ? r0 : n - 1;
     r1 = r1 < n ? r1 : n - 1;
-    const float* q0 = qkv + (base + (long long)r0 * sq.pos_stride) * AT_ROW + h * AT_D + 2 * t;
-    const float* q1 = qkv + (base + (long long)r1 * sq.pos_stride) * AT_ROW + h * AT_D + 2 * t;
-    const float2 a = __ldg(reinterpret_cast<const float2*>(q0)), b = __ldg(reinterpret_cast<const float2*>(q1));
-    const float2 c = __ldg(reinterpret_cast<const float2*>(q0 + 8)), d = __ldg(reinterpret_cast<const float2*>(q1 + 8));
-    qa[mt][0] = pack_h2(a.x * qs, a.y * qs); qa[mt][1] = pack_h2(b.x * qs, b.y * qs);
-    qa[mt][2] = pack_h2(c.x * qs, c.y * qs); qa[mt][3] = pack_h2(d.x * qs, d.y * qs);
+    const uint32_t* q0 = reinterpret_cast<const uint32_t*>(hbase + (base + (long long)r0 * sq.pos_stride) * AT_ROWH) + t;
+    const uint32_t* q1 = reinterpret_cast<const uint32_t*>(hbase + (base + (long long)r1 * sq.pos_stride) * AT_ROWH) + t;
+    qa[mt][0] = __ldg(q0); qa[mt][1] = __ldg(q1); qa[mt][2] = __ldg(q0 + 4); qa[mt][3] = __ldg(q1 + 4);
   }
-  float o[2][2][4];
-  float mrow[2][2], lrow[2][2];
+  // o[mt][0..1]: output columns 0-7 / 8-15; o[mt][2]: a ones column appended to V, so column 0 carries sum_j p_ij
+  float o[2][3][4];
+  float mrow[2][2];
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+  for (int mt = 0; mt < 2; ++mt) {
+    mrow[mt][0] = mrow[mt][1] = -1e30f;
 #pragma unroll
-    for (int x = 0; x < 2; ++x) {
-      mrow[mt][x] = -1e30f; lrow[mt][x] = 0.f;
+    for (int x = 0; x < 3; ++x)
 #pragma unroll
       for (int e = 0; e < 4; ++e) o[mt][x][e] = 0.f;
-    }
+  }
+  const uint32_t ones = (g == 0) ? 0x3C003C00u : 0u;
+  // ldmatrix lane addressing (in halfs, relative to a tile): matrix i = lane >> 3, row = lane & 7
+  const int lm_i = lane >> 3, lm_r = lane & 7;
+  const int k_off = ((lm_i >> 1) * 8 + lm_r) * A2_LD + (lm_i & 1) * 8;        // K: (n-tile pair, d half)
+  const int v_off = ((lm_i & 1) * 8 + lm_r) * A2_LD + (lm_i >> 1) * 8;        // V (transposed load): (key half, d half)
 
-  for (int j0 = 0; j0 < n; j0 += A2_BK) {
+  for (int tile = 0; tile < ntiles; ++tile) {
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
-#pragma unroll
-    for (int rep = 0; rep < 2; ++rep) {
-      const int idx = tid + rep * 128, key = idx >> 2, part = idx & 3, j = j0 + key;
-      float4 kv = make_float4(0, 0, 0, 0), vv = kv;
-      if (j < n) {
-        const float* p = qkv + (base + (long long)j * sq.pos_stride) * AT_ROW + h * AT_D + part * 4;
-        kv = ldg4(p + 64); vv = ldg4(p + 128);
-      }
-      *reinterpret_cast<uint2*>(Ks + key * A2_KLD + part * 4) = make_uint2(pack_h2(kv.x, kv.y), pack_h2(kv.z, kv.w));
-      Vt[(part * 4 + 0) * A2_VLD + key] = __float2half_rn(vv.x);
-      Vt[(part * 4 + 1) * A2_VLD + key] = __float2half_rn(vv.y);
-      Vt[(part * 4 + 2) * A2_VLD + key] = __float2half_rn(vv.z);
-      Vt[(part * 4 + 3) * A2_VLD + key] = __float2half_rn(vv.w);
-    }
-    __syncthreads();
+    if (tile + 1 < ntiles) issue_tile(tile + 1);
     if (!warp_live) continue;
+    const int j0 = tile * A2_BK;
+    const __half* Ks = KV + (tile & 1) * 2 * A2_TILE_H;
+    const __half* Vs = Ks + A2_TILE_H;
 
     // ---- content scores: S[mt] = Q[mt] K^T  (16 x 64 each)
     float s[2][8][4];
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      const uint32_t* kr = reinterpret_cast<const uint32_t*>(Ks + (nt * 8 + g) * A2_KLD) + t;
-      const uint32_t b0 = kr[0], b1 = kr[4];
+    for (int np = 0; np < 4; ++np) {
+      uint32_t kb[4];
+      ldsm_x4(kb, Ks + np * 16 * A2_LD + k_off);
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
-        s[mt][nt][0] = s[mt][nt][1] = s[mt][nt][2] = s[mt][nt][3] = 0.f;
-        mma_f16(s[mt][nt], qa[mt], b0, b1);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { s[mt][2 * np][e] = 0.f; s[mt][2 * np + 1][e] = 0.f; }
+        mma_f16(s[mt][2 * np], qa[mt], kb[0], kb[1]);
+        mma_f16(s[mt][2 * np + 1], qa[mt], kb[2], kb[3]);
       }
     }
     // ---- relative-position scores: R[r, dd] = q_r . E[clamp(dlo + dd)], dd in [0, 96)
@@ -234,7 +260,7 @@ __global__ void __launch_bounds__(128, 3) attention_f16_kernel(const float* __re
           for (int e = 0; e < 4; ++e)
             if (j0 + nt * 8 + 2 * t + (e & 1) >= n) s[mt][nt][e] = -1e30f;
     }
-    // ---- online softmax (base-2)
+    // ---- online softmax (base-2); the row sums come out of the P V product (ones column)
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -247,32 +273,26 @@ __global__ void __launch_bounds__(128, 3) attention_f16_kernel(const float* __re
         const float mn = fmaxf(mrow[mt][rh], mx);
         const float corr = ex2_approx(mrow[mt][rh] - mn);
         mrow[mt][rh] = mn;
-        float sum = 0.f;
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
-          const float p0 = ex2_approx(s[mt][nt][2 * rh] - mn), p1 = ex2_approx(s[mt][nt][2 * rh + 1] - mn);
-          s[mt][nt][2 * rh] = p0; s[mt][nt][2 * rh + 1] = p1;
-          sum += p0 + p1;
+          s[mt][nt][2 * rh] = ex2_approx(s[mt][nt][2 * rh] - mn);
+          s[mt][nt][2 * rh + 1] = ex2_approx(s[mt][nt][2 * rh + 1] - mn);
         }
-        lrow[mt][rh] = lrow[mt][rh] * corr + sum;
-        o[mt][0][2 * rh] *= corr; o[mt][0][2 * rh + 1] *= corr;
-        o[mt][1][2 * rh] *= corr; o[mt][1][2 * rh + 1] *= corr;
+#pragma unroll
+        for (int x = 0; x < 3; ++x) { o[mt][x][2 * rh] *= corr; o[mt][x][2 * rh + 1] *= corr; }
       }
-    // ---- O += P V  (k = 16 keys per step; C fragments of two adjacent S n-tiles form one A fragment)
+    // ---- O += P [V | 1]  (k = 16 keys per step; C fragments of two adjacent S n-tiles form one A fragment)
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
-      uint32_t vb[2][2];
-#pragma unroll
-      for (int nb = 0; nb < 2; ++nb) {
-        const uint32_t* vr = reinterpret_cast<const uint32_t*>(Vt + (nb * 8 + g) * A2_VLD + ks * 16) + t;
-        vb[nb][0] = vr[0]; vb[nb][1] = vr[4];
-      }
+      uint32_t vb[4];
+      ldsm_x4_trans(vb, Vs + ks * 16 * A2_LD + v_off);
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
         const uint32_t pa[4] = {pack_h2(s[mt][2 * ks][0], s[mt][2 * ks][1]), pack_h2(s[mt][2 * ks][2], s[mt][2 * ks][3]),
                                 pack_h2(s[mt][2 * ks + 1][0], s[mt][2 * ks + 1][1]), pack_h2(s[mt][2 * ks + 1][2], s[mt][2 * ks + 1][3])};
-        mma_f16(o[mt][0], pa, vb[0][0], vb[0][1]);
-        mma_f16(o[mt][1], pa, vb[1][0], vb[1][1]);
+        mma_f16(o[mt][0], pa, vb[0], vb[1]);
+        mma_f16(o[mt][1], pa, vb[2], vb[3]);
+        mma_f16(o[mt][2], pa, ones, ones);
       }
     }
   }
@@ -281,9 +301,7 @@ __global__ void __launch_bounds__(128, 3) attention_f16_kernel(const float* __re
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
     for (int rh = 0; rh < 2; ++rh) {
-      float l = lrow[mt][rh];
-      l += __shfl_xor_sync(0xffffffffu, l, 1);
-      l += __shfl_xor_sync(0xffffffffu, l, 2);
+      const float l = __shfl_sync(0xffffffffu, o[mt][2][2 * rh], lane & ~3);   // column 0 lives on lane t == 0
       const int i = iw + mt * 16 + g + 8 * rh;
       if (i < n) {
         const float inv = 1.0f / l;
@@ -298,8 +316,9 @@ __global__ void __launch_bounds__(128, 3) attention_f16_kernel(const float* __re
 
 using namespace seb;
 
-extern "C" int seb200_attention(const float* qkv, const float* rel_pos_emb, const void* rel_pos_emb_h, const SebSeq* seq, float* out, int variant, void* stream) {
-  SEB_REQUIRE(qkv && rel_pos_emb && seq && out && aligned16(qkv) && aligned16(out) && aligned16(rel_pos_emb), SEB_EINVAL, "attention: null/unaligned argument");
+extern "C" int seb200_attention(const void* qkv, const float* rel_pos_emb, const void* rel_pos_emb_h, const SebSeq* seq, float* out, int variant, void* stream) {
+  SEB_REQUIRE(qkv && seq && out && aligned16(qkv) && aligned16(out), SEB_EINVAL, "attention: null/unaligned argument");
+  if (variant == 1) SEB_REQUIRE(rel_pos_emb && aligned16(rel_pos_emb), SEB_EINVAL, "attention: the fp32 variant needs rel_pos_emb");
   SEB_REQUIRE(seq->nseq > 0 && seq->n > 0 && seq->inner > 0 && seq->nseq <= (1 << 28), SEB_EINVAL, "attention: bad sequence descriptor");
   const int n = seq->n;
   cudaStream_t st = (cudaStream_t)stream;
@@ -310,7 +329,7 @@ extern "C" int seb200_attention(const float* qkv, const float* rel_pos_emb, cons
     if (e != cudaSuccess) { set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     dim3 grid(seq->nseq * AT_H, (n + ATS_BQ - 1) / ATS_BQ);
     SEB_REQUIRE(grid.y <= 65535u, SEB_EINVAL, "attention: sequence too long");
-    attention_simt_kernel<<<grid, ATS_BQ, smem, st>>>(qkv, rel_pos_emb, *seq, out);
+    attention_simt_kernel<<<grid, ATS_BQ, smem, st>>>(reinterpret_cast<const float*>(qkv), rel_pos_emb, *seq, out);
     SEB_CHECK_LAUNCH("attention_simt_kernel");
     return 0;
   }
@@ -324,7 +343,7 @@ extern "C" int seb200_attention(const float* qkv, const float* rel_pos_emb, cons
   const int nqb = ((n + A2_WROWS - 1) / A2_WROWS + 3) / 4;
   const long long nblocks = (long long)seq->nseq * AT_H * nqb;
   SEB_REQUIRE(nblocks < 2147483647LL, SEB_EINVAL, "attention: grid too large");
-  attention_f16_kernel<<<(unsigned)nblocks, 128, A2_SMEM, st>>>(qkv, reinterpret_cast<const __half*>(rel_pos_emb_h), *seq, nqb, out);
+  attention_f16_kernel<<<(unsigned)nblocks, 128, A2_SMEM, st>>>(reinterpret_cast<const __half*>(qkv), reinterpret_cast<const __half*>(rel_pos_emb_h), *seq, nqb, out);
   SEB_CHECK_LAUNCH("attention_f16_kernel");
   return 0;
 }

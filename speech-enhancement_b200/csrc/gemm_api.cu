@@ -73,6 +73,7 @@ extern "C" int seb200_gemm(const SebGemm* s, int engine, void* stream) {
   if (s->epilogue == SEB_EPI_RESID) SEB_REQUIRE(s->resid && s->ldr % 4 == 0 && aligned16(s->resid), SEB_EALIGN, "gemm: residual null/unaligned");
   if (s->epilogue == SEB_EPI_GLU) SEB_REQUIRE(s->ldo % 2 == 0, SEB_EALIGN, "gemm: ldo must be even");
   else if (s->epilogue != SEB_EPI_COMPRESS) SEB_REQUIRE(s->ldo % 4 == 0, SEB_EALIGN, "gemm: ldo must be a multiple of 4");
+  if (s->epilogue == SEB_EPI_QKV_F16) SEB_REQUIRE(s->N == 192 && s->ldo == 192, SEB_EINVAL, "gemm: the fp16 q|k|v epilogue needs N == ldo == 192");
 
   const GemmArgs g = to_args(s);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -87,6 +88,7 @@ extern "C" int seb200_gemm(const SebGemm* s, int engine, void* stream) {
       case SEB_LOAD_ROWS_LN * 16 + SEB_EPI_SWISH:   return launch_simt<SEB_LOAD_ROWS_LN, SEB_EPI_SWISH>(s, g, st);
       case SEB_LOAD_ROWS_LN * 16 + SEB_EPI_GLU:     return launch_simt<SEB_LOAD_ROWS_LN, SEB_EPI_GLU>(s, g, st);
       case SEB_LOAD_ROWS_LN * 16 + SEB_EPI_BIAS:    return launch_simt<SEB_LOAD_ROWS_LN, SEB_EPI_BIAS>(s, g, st);
+      case SEB_LOAD_ROWS_LN * 16 + SEB_EPI_QKV_F16: return launch_simt<SEB_LOAD_ROWS_LN, SEB_EPI_QKV_F16>(s, g, st);
       default: break;
     }
   } else if (engine == SEB_ENGINE_TCGEN05) {
@@ -100,6 +102,7 @@ extern "C" int seb200_gemm(const SebGemm* s, int engine, void* stream) {
       case SEB_LOAD_ROWS_LN * 16 + SEB_EPI_SWISH:   if (nt == 256) return launch_tc<256, 1, SEB_LOAD_ROWS_LN, SEB_EPI_SWISH>(s, g, st); break;
       case SEB_LOAD_ROWS_LN * 16 + SEB_EPI_GLU:     if (nt == 256) return launch_tc<256, 1, SEB_LOAD_ROWS_LN, SEB_EPI_GLU>(s, g, st); break;
       case SEB_LOAD_ROWS_LN * 16 + SEB_EPI_BIAS:    if (nt == 192) return launch_tc<192, 1, SEB_LOAD_ROWS_LN, SEB_EPI_BIAS>(s, g, st); break;
+      case SEB_LOAD_ROWS_LN * 16 + SEB_EPI_QKV_F16: if (nt == 192) return launch_tc<192, 1, SEB_LOAD_ROWS_LN, SEB_EPI_QKV_F16>(s, g, st); break;
       default: break;
     }
   }

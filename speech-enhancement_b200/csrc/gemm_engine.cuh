@@ -219,6 +219,18 @@ template <> struct Epi<SEB_EPI_COMPRESS> {   // core/function.py:625-634 fused: 
   }
 };
 
+// q | k | v projection for the tensor-core attention: fp16 output [tokens, 192]; the q third is pre-scaled by
+// dim_head^-0.5 * log2(e) (conformer.py:103,110 scale both logit terms by dim_head^-0.5; softmax is evaluated base 2)
+template <> struct Epi<SEB_EPI_QKV_F16> {
+  __device__ static void apply(const GemmArgs& g, int m, int n, float4 v) {
+    if (m >= g.M || n >= g.N) return;
+    const float sc = (n < 64) ? 0.25f * 1.4426950408889634f : 1.0f;
+    __half2 a = __floats2half2_rn(v.x * sc, v.y * sc), b = __floats2half2_rn(v.z * sc, v.w * sc);
+    uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(g.out) + (long long)m * g.ldo + n) = pk;
+  }
+};
+
 // -------------------------------------------------------------------------------------------
 // SIMT main loop (fp32 FFMA).  grid = (ceil(M/128), npad/64), 256 threads, 8x4 outputs / thread.
 // -------------------------------------------------------------------------------------------

@@ -25,7 +25,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from ._lib import (EPI_BIAS, EPI_GLU, EPI_RESID, EPI_SUBPIXEL, EPI_SWISH, LOAD_CONV, LOAD_ROWS, LOAD_ROWS_LN)
+from ._lib import (EPI_BIAS, EPI_GLU, EPI_QKV_F16, EPI_RESID, EPI_SUBPIXEL, EPI_SWISH, LOAD_CONV, LOAD_ROWS, LOAD_ROWS_LN)
 from .packing import PackedWeight, conv_weight_matrix, glu_interleave, pack_weight
 
 
@@ -238,7 +238,7 @@ class TSCNet(nn.Module):
             "sp": torch.empty(B * T * 2 * Fh, 64, **f32),
             # conformer token buffers
             "x": torch.empty(Ph, 64, **f32), "y": torch.empty(Ph, 64, **f32), "h": torch.empty(Ph, 256, **f32),
-            "qkv": torch.empty(Ph, 192, **f32), "o": torch.empty(Ph, 64, **f32),
+            "qkv": torch.empty(Ph, 192, **f32), "o": torch.empty(Ph, 64, **f32),       # qkv doubles as the fp16 [Ph, 192] buffer
             "u": torch.empty(Ph, 128, **f32), "v": torch.empty(Ph, 128, **f32),
             # heads
             "mask_raw": torch.empty(B * T, F, **f32), "cplx": torch.empty(B * T, F, 2, **f32), "est": torch.empty(B * T, F, 2, **f32),
@@ -281,8 +281,13 @@ class TSCNet(nn.Module):
             ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_SWISH, M=M, w=P[f"{p}.ff1.w1"], a=[x], lda=64, ln=P[f"{p}.ff1.ln"], out=h, ldo=256, engine=eng, label="ffn1")
             ops.gemm(loader=LOAD_ROWS, epilogue=EPI_RESID, M=M, w=P[f"{p}.ff1.w2"], a=[h], lda=256, out=y, ldo=64, resid=x, ldr=64, alpha=0.5, engine=eng, label="ffn2")
         # y += Attn(LN(y))
-        ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_BIAS, M=M, w=P[f"{p}.attn.qkv"], a=[y], lda=64, ln=P[f"{p}.attn.ln"], out=qkv, ldo=192, engine=eng, label="qkv")
-        ops.attention(qkv, P[f"{p}.attn.emb"], seq, o, self.attention_variant, P[f"{p}.attn.emb_h"])
+        if self.attention_variant == 0:      # fp16 projection (q pre-scaled) feeding the tensor-core attention
+            qkv_h = qkv.view(-1).view(torch.float16)[:M * 192].view(M, 192)
+            ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_QKV_F16, M=M, w=P[f"{p}.attn.qkv"], a=[y], lda=64, ln=P[f"{p}.attn.ln"], out=qkv_h, ldo=192, engine=eng, label="qkv")
+            ops.attention(qkv_h, P[f"{p}.attn.emb"], seq, o, 0, P[f"{p}.attn.emb_h"])
+        else:                                # fp32 projection + fp32 SIMT attention (cross-check path)
+            ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_BIAS, M=M, w=P[f"{p}.attn.qkv"], a=[y], lda=64, ln=P[f"{p}.attn.ln"], out=qkv, ldo=192, engine=eng, label="qkv")
+            ops.attention(qkv, P[f"{p}.attn.emb"], seq, o, 1)
         ops.gemm(loader=LOAD_ROWS, epilogue=EPI_RESID, M=M, w=P[f"{p}.attn.out"], a=[o], lda=64, out=y, ldo=64, resid=y, ldr=64, alpha=1.0, engine=eng, label="attn_out")
         # y += ConvModule(y)
         ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_GLU, M=M, w=P[f"{p}.conv.pw1"], a=[y], lda=64, ln=P[f"{p}.conv.ln"], out=u, ldo=128, engine=eng, label="pw1_glu")

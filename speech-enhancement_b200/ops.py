@@ -13,7 +13,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import (ENGINE_SIMT, ENGINE_TCGEN05, EPI_BIAS, EPI_COMPRESS, EPI_GLU, EPI_RESID, EPI_SUBPIXEL, EPI_SWISH,
+from ._lib import (ENGINE_SIMT, ENGINE_TCGEN05, EPI_BIAS, EPI_COMPRESS, EPI_GLU, EPI_QKV_F16, EPI_RESID, EPI_SUBPIXEL, EPI_SWISH,
                    LOAD_CONV, LOAD_HANKEL, LOAD_ROWS, LOAD_ROWS_LN, SebFfn, SebGemm, SebSeq, check, ptr, require_cuda, stream_ptr)
 from .packing import PackedWeight
 
@@ -102,7 +102,12 @@ def gemm(*, loader: int, epilogue: int, M: int, w: PackedWeight, a: Sequence[tor
          label: str = "gemm", k_logical: Optional[int] = None):
     """One launch of the GEMM engine (see include/seb200.h: SebGemm)."""
     lib = _lib.load()
-    _f32c(out, resid, *a)
+    if epilogue == EPI_QKV_F16:
+        if out.dtype != torch.float16 or not out.is_contiguous():
+            raise RuntimeError("the fp16 q|k|v epilogue writes a contiguous float16 [M, 192] tensor")
+        _f32c(resid, *a)
+    else:
+        _f32c(out, resid, *a)
     g = SebGemm()
     g.loader, g.epilogue = loader, epilogue
     g.M, g.N, g.K = M, (w.N if N is None else N), w.K
@@ -282,13 +287,19 @@ def make_seq(nseq: int, n: int, inner: int, outer_stride: int, pos_stride: int) 
 
 
 def attention(qkv, rel_pos_emb, seq: SebSeq, out, variant: int = 0, rel_pos_emb_h=None):
-    _f32c(qkv, rel_pos_emb, out)
+    """variant 0: qkv float16 [tokens, 192] with q pre-scaled (EPI_QKV_F16); variant 1: qkv float32, unscaled."""
+    _f32c(rel_pos_emb, out)
+    require_cuda(qkv)
     if variant == 0:
+        if qkv.dtype != torch.float16 or not qkv.is_contiguous():
+            raise RuntimeError("tensor-core attention reads the float16 q|k|v projection")
         if rel_pos_emb_h is None:
             rel_pos_emb_h = rel_pos_emb.to(torch.float16)
         if rel_pos_emb_h.dtype != torch.float16 or not rel_pos_emb_h.is_contiguous():
             raise RuntimeError("rel_pos_emb_h must be a contiguous float16 copy of the embedding table")
-    tok = _pb("attention", 96.0 * 4 * seq.nseq * seq.n * seq.n, 4.0 * (qkv.numel() + out.numel())) if _PROF is not None else None
+    else:
+        _f32c(qkv)
+    tok = _pb("attention", 96.0 * 4 * seq.nseq * seq.n * seq.n, (2.0 if variant == 0 else 4.0) * qkv.numel() + 4.0 * out.numel()) if _PROF is not None else None
     check(_lib.load().seb200_attention(ptr(qkv), ptr(rel_pos_emb), ptr(rel_pos_emb_h), C.byref(seq), ptr(out), variant, stream_ptr()), "seb200_attention")
     _pe(tok)
     return out

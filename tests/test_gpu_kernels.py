@@ -12,7 +12,7 @@ from oracle import tscnet_oracle as O, weights
 
 import se_b200
 from se_b200 import ops, packing
-from se_b200._lib import (EPI_BIAS, EPI_COMPRESS, EPI_GLU, EPI_RESID, EPI_SUBPIXEL, EPI_SWISH, LOAD_CONV, LOAD_HANKEL,
+from se_b200._lib import (EPI_BIAS, EPI_COMPRESS, EPI_GLU, EPI_QKV_F16, EPI_RESID, EPI_SUBPIXEL, EPI_SWISH, LOAD_CONV, LOAD_HANKEL,
                           LOAD_ROWS, LOAD_ROWS_LN)
 
 pytestmark = pytest.mark.gpu
@@ -63,6 +63,12 @@ def test_gemm_layernorm_loader_epilogues(engine):
     out = torch.empty(M, 192, device=DEV)
     ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_BIAS, M=M, w=packing.pack_weight(wq.cpu(), 192, None).to(DEV), a=[x], lda=64, ln=(g, be), out=out, ldo=192, engine=engine)
     assert rel_max(out, xn @ wq.double().t()) < TOL[engine]
+    # the same projection in the fp16 layout the tensor-core attention reads (q pre-scaled)
+    outh = torch.empty(M, 192, device=DEV, dtype=torch.float16)
+    ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_QKV_F16, M=M, w=packing.pack_weight(wq.cpu(), 192, None).to(DEV), a=[x], lda=64, ln=(g, be), out=outh, ldo=192, engine=engine)
+    refh = xn @ wq.double().t()
+    refh[:, :64] *= 0.25 * 1.4426950408889634
+    assert rel_max(outh.double(), refh) < 1e-3
 
 
 @pytest.mark.parametrize("M", [128, 777, 40000])
@@ -273,7 +279,10 @@ def test_attention(variant, axis, B, T, Fh):
     emb = rnd(1025, 16, seed=81)
     seq, to_seq, from_seq = _seq_layouts(B, T, Fh)[axis]
     out = torch.zeros(B * T * Fh, 64, device=DEV)
-    ops.attention(qkv.view(-1, 192), emb, seq, out, variant)
+    inp = qkv.view(-1, 192)
+    if variant == 0:      # what SEB_EPI_QKV_F16 writes: fp16, q pre-scaled by dim_head^-0.5 * log2(e)
+        inp = torch.cat([inp[:, :64] * (0.25 * 1.4426950408889634), inp[:, 64:]], 1).to(torch.float16).contiguous()
+    ops.attention(inp, emb, seq, out, variant)
     ref = from_seq(_attention_core_ref(to_seq(qkv.cpu()), emb.cpu()))
     tol = 1e-5 if variant == 1 else 2e-3
     assert rel_max(out.view(B, T, Fh, 64).cpu(), ref) < tol
