@@ -41,7 +41,8 @@ enum {
  * as implicit GEMM, and the Linear / pointwise Conv1d layers of ConformerBlock
  * (conformer.py:87-89,137-140,165,169).
  */
-enum { SEB_LOAD_ROWS = 0, SEB_LOAD_ROWS_LN = 1, SEB_LOAD_CONV = 2, SEB_LOAD_HANKEL = 3 };
+enum { SEB_LOAD_ROWS = 0, SEB_LOAD_ROWS_LN = 1, SEB_LOAD_CONV = 2, SEB_LOAD_HANKEL = 3,
+       SEB_LOAD_CONV_SPLIT = 4 /* CONV on pre-split inputs: every pixel = 64 bf16 hi + 64 bf16 lo (256 bytes); tcgen05 engine only */ };
 enum {
   SEB_EPI_BIAS = 0,     /* out = acc + bias                                  */
   SEB_EPI_SWISH = 1,    /* v = acc + bias; out = v * sigmoid(v)              */
@@ -118,9 +119,12 @@ int seb200_conv1x1_in3(const float* in3, long long pixels, const float* w /*[64,
 long long seb200_inorm_workspace_bytes(int B, long long pix_per_b, int C);
 int seb200_inorm_stats(const float* x, int B, long long pix_per_b, int C, float* stats,
                        void* workspace, long long workspace_bytes, void* stream);
-/* y = PReLU(gamma * (x - mean) * rstd + beta): InstanceNorm2d(affine) + PReLU(C) (generator.py:21-22,40-41) */
+/* y = PReLU(gamma * (x - mean) * rstd + beta): InstanceNorm2d(affine) + PReLU(C) (generator.py:21-22,40-41).
+ * out_format 0: y is fp32 [B, pix, 64]; 1: y is the pre-split conv-input format (per pixel 64 bf16 hi | 64 bf16 lo) */
 int seb200_inorm_prelu(const float* x, int B, long long pix_per_b, int C, const float* stats,
-                       const float* gamma, const float* beta, const float* slope, float* y, void* stream);
+                       const float* gamma, const float* beta, const float* slope, void* y, int out_format, void* stream);
+/* fp32 [pixels, 64] -> pre-split conv-input format (the decoders read the TSCB output this way) */
+int seb200_split_planes(const float* x, long long pixels, void* y, void* stream);
 /* MaskDecoder.conv_1: Conv2d(64 -> 1, (1,2)) on [B*T, 202, 64] -> raw [B*T, 201] (generator.py:100) */
 int seb200_mask_conv(const float* x, long long rows, int Fin, const float* w /*[2][64]: tap-major*/,
                      float bias, float* out, void* stream);

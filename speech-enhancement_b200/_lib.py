@@ -14,7 +14,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libseb200.so")
 
-LOAD_ROWS, LOAD_ROWS_LN, LOAD_CONV, LOAD_HANKEL = 0, 1, 2, 3
+LOAD_ROWS, LOAD_ROWS_LN, LOAD_CONV, LOAD_HANKEL, LOAD_CONV_SPLIT = 0, 1, 2, 3, 4
 EPI_BIAS, EPI_SWISH, EPI_GLU, EPI_RESID, EPI_SUBPIXEL, EPI_COMPRESS, EPI_QKV_F16 = 0, 1, 2, 3, 4, 5, 6
 ENGINE_TCGEN05, ENGINE_SIMT = 0, 1
 
@@ -59,7 +59,8 @@ _SIGS = {
     "seb200_overlap_add": [_fp, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, C.c_int, C.c_int, _fp],
     "seb200_conv1x1_in3": [_fp, C.c_longlong, _fp, _fp, _fp, _fp],
     "seb200_inorm_stats": [_fp, C.c_int, C.c_longlong, C.c_int, _fp, _fp, C.c_longlong, _fp],
-    "seb200_inorm_prelu": [_fp, C.c_int, C.c_longlong, C.c_int, _fp, _fp, _fp, _fp, _fp, _fp],
+    "seb200_inorm_prelu": [_fp, C.c_int, C.c_longlong, C.c_int, _fp, _fp, _fp, _fp, _fp, C.c_int, _fp],
+    "seb200_split_planes": [_fp, C.c_longlong, _fp, _fp],
     "seb200_mask_conv": [_fp, C.c_longlong, C.c_int, _fp, C.c_float, _fp, _fp],
     "seb200_complex_conv": [_fp, C.c_int, C.c_longlong, C.c_int, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp],
     "seb200_mask_recombine": [_fp, _fp, C.c_int, C.c_longlong, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,

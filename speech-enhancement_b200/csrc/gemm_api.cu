@@ -47,6 +47,24 @@ static int launch_tc(const SebGemm* s, const GemmArgs& g, cudaStream_t st) {
   return 0;
 }
 
+template <int NT, int STAGES, int EK>
+static int launch_conv_split(const SebGemm* s, const GemmArgs& g, cudaStream_t st) {
+  static bool attr_done = false;
+  constexpr int SMEM = tc_smem_bytes<NT, STAGES>();
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_split_tc_kernel<NT, STAGES, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) { set_error("conv split: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    attr_done = true;
+  }
+  SEB_REQUIRE(s->w_tc && s->tc_ntile == NT && s->tc_ntiles >= 1 && s->tc_ntile * s->tc_ntiles >= s->N && aligned16(s->w_tc), SEB_EINVAL,
+              "conv split: weight image has n-tile %d x %d, kernel wants %d covering N=%d", s->tc_ntile, s->tc_ntiles, NT, s->N);
+  SEB_REQUIRE(s->T < 32768 && s->Fout < 65536, SEB_EINVAL, "conv split: T/F too large for the packed row index");
+  dim3 grid((g.M + BM - 1) / BM, s->tc_ntiles);
+  conv_split_tc_kernel<NT, STAGES, EK><<<grid, TC_THREADS, SMEM, st>>>(g, reinterpret_cast<const uint8_t*>(s->w_tc));
+  SEB_CHECK_LAUNCH("conv_split_tc_kernel");
+  return 0;
+}
+
 }  // namespace seb
 
 using namespace seb;
@@ -61,7 +79,7 @@ extern "C" int seb200_gemm(const SebGemm* s, int engine, void* stream) {
   if (s->loader == SEB_LOAD_ROWS_LN) {
     SEB_REQUIRE(s->K == 64 && s->ln_gamma && s->ln_beta, SEB_EINVAL, "gemm: LayerNorm loader needs K == 64 and gamma/beta");
   }
-  if (s->loader == SEB_LOAD_CONV) {
+  if (s->loader == SEB_LOAD_CONV || s->loader == SEB_LOAD_CONV_SPLIT) {
     SEB_REQUIRE(s->nslots >= 1 && s->nslots <= 4 && (s->taps_t == 1 || s->taps_t == 2) && s->stride_f >= 1 && s->dil >= 1, SEB_EINVAL, "gemm: bad conv geometry");
     SEB_REQUIRE(s->K == s->taps_t * 3 * s->nslots * 64, SEB_EINVAL, "gemm: conv K=%d != taps*slots*64", s->K);
     SEB_REQUIRE((long long)s->B * s->T * s->Fout == s->M, SEB_EINVAL, "gemm: conv M != B*T*Fout");
@@ -94,6 +112,8 @@ extern "C" int seb200_gemm(const SebGemm* s, int engine, void* stream) {
   } else if (engine == SEB_ENGINE_TCGEN05) {
     const int nt = s->tc_ntile;
     switch (key) {
+      case SEB_LOAD_CONV_SPLIT * 16 + SEB_EPI_BIAS:     if (nt == 64)  return launch_conv_split<64, 2, SEB_EPI_BIAS>(s, g, st); break;
+      case SEB_LOAD_CONV_SPLIT * 16 + SEB_EPI_SUBPIXEL: if (nt == 128) return launch_conv_split<128, 1, SEB_EPI_SUBPIXEL>(s, g, st); break;
       case SEB_LOAD_HANKEL * 16 + SEB_EPI_COMPRESS: if (nt == 208) return launch_tc<208, 1, SEB_LOAD_HANKEL, SEB_EPI_COMPRESS>(s, g, st); break;
       case SEB_LOAD_ROWS * 16 + SEB_EPI_BIAS:       if (nt == 208) return launch_tc<208, 1, SEB_LOAD_ROWS, SEB_EPI_BIAS>(s, g, st); break;
       case SEB_LOAD_ROWS * 16 + SEB_EPI_RESID:      if (nt == 64)  return launch_tc<64, 2, SEB_LOAD_ROWS, SEB_EPI_RESID>(s, g, st); break;

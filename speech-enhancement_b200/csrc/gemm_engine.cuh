@@ -516,4 +516,177 @@ gemm_tc_kernel(const GemmArgs g, const uint8_t* __restrict__ w_tc) {
   }
 }
 
+
+// -------------------------------------------------------------------------------------------
+// Implicit-GEMM convolution on PRE-SPLIT activations (SEB_LOAD_CONV_SPLIT).
+//
+// The producers of conv inputs (inorm_prelu / split_planes) store every pixel as 256 bytes: 64 bf16 `hi` then
+// 64 bf16 `lo` with hi + lo == x to 2^-17 -- the same bytes as fp32, but already the two MMA operands.  The loader
+// is then a pure copy: 16-byte cp.async (zero-filled outside the image) straight into the swizzled UMMA tile, no
+// register pass, no conversion; a software-pipelined wait_group + fence.proxy.async hands each stage to the
+// tensor pipe.  Same mbarrier ring, weight stager, MMA issuer and epilogue as gemm_tc_kernel.
+// -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+
+template <int NT, int STAGES, int EK>
+__global__ void __launch_bounds__(TC_THREADS, 2)
+conv_split_tc_kernel(const GemmArgs g, const uint8_t* __restrict__ w_tc) {
+  static_assert(STAGES == 1 || STAGES == 2, "producer lag is STAGES - 1 with a literal wait_group");
+  static_assert(NT % 16 == 0 && NT >= 16 && NT <= 256, "UMMA M=128 needs N % 16 == 0, N <= 256");
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t smem_base = ptx::smem_u32(smem);
+  constexpr int STAGE = tc_stage_bytes<NT>();
+  constexpr uint32_t W_BYTES = NT * 128;
+  constexpr uint32_t TMEM_COLS = tc_tmem_cols<NT>();
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * BM;
+  const int ntile = blockIdx.y;
+  const int nkc = g.K / BK;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 8 + 1); ptx::mbar_init(&empty_bar[s], 1); }
+    ptx::mbar_init(&accum_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 8) ptx::tmem_alloc(&tmem_base_s, TMEM_COLS);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp < 8) {
+    // ---------------- producers: cp.async of pre-split bf16 planes ----------------
+    // lane -> (16-byte chunk c = lane & 7, plane = (lane >> 3) & 1, row-in-pair = lane >> 4): one warp instruction
+    // copies 2 pixels x 256 contiguous bytes; pass p covers rows p*16 + warp*2 + (lane >> 4).
+    const int c = lane & 7, plane = (lane >> 3) & 1, r0 = warp * 2 + (lane >> 4);
+    long long pix[8];        // flat input pixel index of the centre tap (or -1 for rows beyond M)
+    int tf[8];               // (t << 16) | f
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      const int m = m0 + p * 16 + r0;
+      if (m < g.M) {
+        const int bt = m / g.Fout, f = m - bt * g.Fout, b = bt / g.T, t = bt - b * g.T;
+        pix[p] = ((long long)b * g.T + t) * g.Fin + (long long)f * g.stride_f;
+        tf[p] = (t << 16) | f;
+      } else { pix[p] = -1; tf[p] = 0; }
+    }
+    const uint32_t dst0 = (uint32_t)(plane * TC_A_BYTES + r0 * 128 + ((c ^ (r0 & 7)) << 4));   // + p * 2048 per pass
+    const int src_lane_off = plane * 128 + c * 16;                                             // bytes inside a pixel
+    for (int kc = 0; kc < nkc; ++kc) {
+      const int s = kc % STAGES;
+      const uint32_t ph = (uint32_t)(kc / STAGES) & 1u;
+      ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
+      const int tap = kc / g.nslots, slot = kc - tap * g.nslots;
+      const int kt = (g.taps_t == 2) ? tap / 3 : 0, kf = tap - kt * 3;
+      const int dt = (g.taps_t - 1 - kt) * g.dil, df = kf - 1;
+      const uint8_t* src_base = reinterpret_cast<const uint8_t*>(g.a[slot]) + src_lane_off;
+      const long long dpix = (long long)df - (long long)dt * g.Fin;
+      const uint32_t dst = smem_base + s * STAGE + dst0;
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        const int t = tf[p] >> 16, f = tf[p] & 0xffff;
+        const int ff = f * g.stride_f + df;
+        const bool ok = pix[p] >= 0 && t >= dt && ff >= 0 && ff < g.Fin;
+        const long long q = ok ? pix[p] + dpix : 0;
+        cp_async16_zfill(dst + p * 2048, src_base + q * 256, ok ? 16u : 0u);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      // keep LAG = STAGES - 1 copy groups in flight: chunk kc - LAG has landed -> publish it to the MMA issuer
+      constexpr int LAG = STAGES - 1;
+      if (kc >= LAG) {
+        if (LAG == 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
+        else asm volatile("cp.async.wait_group 1;" ::: "memory");
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&full_bar[(kc - LAG) % STAGES]);
+      }
+    }
+    if (STAGES > 1) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&full_bar[(nkc - 1) % STAGES]);
+    }
+
+    // ---------------- epilogue (identical to gemm_tc_kernel) ----------------
+    ptx::mbar_wait(&accum_bar, 0);
+    ptx::tc_fence_after();
+    const int wq = warp & 3, half = warp >> 2;
+    constexpr int HALF_COLS = NT / 2;
+    const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(half * HALF_COLS);
+    float4* stg = reinterpret_cast<float4*>(smem + warp * 4096);
+#pragma unroll 1
+    for (int c0 = 0; c0 < HALF_COLS; c0 += 32) {
+      const int ncols = (HALF_COLS - c0 < 32) ? HALF_COLS - c0 : 32;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        if (j < ncols) {
+          float v[8];
+          ptx::tmem_ld8(taddr + c0 + j, v);
+          stg[lane * 8 + (((j >> 2) + 0) ^ (lane & 7))] = make_float4(v[0], v[1], v[2], v[3]);
+          stg[lane * 8 + (((j >> 2) + 1) ^ (lane & 7))] = make_float4(v[4], v[5], v[6], v[7]);
+        }
+      }
+      __syncwarp();
+      const int ch = lane & 7;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int R = it * 4 + (lane >> 3);
+        if (ch * 4 < ncols) {
+          const float4 val = stg[R * 8 + (ch ^ (R & 7))];
+          Epi<EK>::apply(g, m0 + wq * 32 + R, ntile * NT + half * HALF_COLS + c0 + ch * 4, val);
+        }
+      }
+      __syncwarp();
+    }
+    ptx::tc_fence_before();
+  } else if (warp == 8) {
+    if (lane == 0) {
+      constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      for (int kc = 0; kc < nkc; ++kc) {
+        const int s = kc % STAGES;
+        const uint32_t ph = (uint32_t)(kc / STAGES) & 1u;
+        ptx::mbar_wait(&full_bar[s], ph);
+        ptx::tc_fence_after();
+        const uint32_t base = smem_base + s * STAGE;
+        const uint64_t a_hi = ptx::umma_desc_sw128(base);
+        const uint64_t a_lo = ptx::umma_desc_sw128(base + TC_A_BYTES);
+        const uint64_t w_hi = ptx::umma_desc_sw128(base + 2 * TC_A_BYTES);
+        const uint64_t w_lo = ptx::umma_desc_sw128(base + 2 * TC_A_BYTES + W_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t ko = (uint64_t)((k * 32) >> 4);
+          ptx::mma_bf16(tmem_base, a_lo + ko, w_hi + ko, IDESC, (kc | k) ? 1u : 0u);
+          ptx::mma_bf16(tmem_base, a_hi + ko, w_lo + ko, IDESC, 1u);
+          ptx::mma_bf16(tmem_base, a_hi + ko, w_hi + ko, IDESC, 1u);
+        }
+        ptx::tc_commit(&empty_bar[s]);
+      }
+      ptx::tc_commit(&accum_bar);
+    }
+  } else {
+    if (lane == 0) {
+      const uint8_t* src = w_tc + (size_t)ntile * nkc * (2 * W_BYTES);
+      for (int kc = 0; kc < nkc; ++kc) {
+        const int s = kc % STAGES;
+        const uint32_t ph = (uint32_t)(kc / STAGES) & 1u;
+        ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
+        ptx::mbar_arrive_expect_tx(&full_bar[s], 2 * W_BYTES);
+        ptx::bulk_g2s(smem_base + s * STAGE + 2 * TC_A_BYTES, src + (size_t)kc * (2 * W_BYTES), 2 * W_BYTES, &full_bar[s]);
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 8) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
 }  // namespace seb

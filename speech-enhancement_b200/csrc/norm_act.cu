@@ -106,10 +106,20 @@ __global__ void inorm_finalize_kernel(const double* __restrict__ part, int chunk
 }
 
 // ---- y = PReLU(gamma * (x - mean) * rstd + beta), C = 64 ------------------------------------
+// SPLIT = false: fp32 output.  SPLIT = true: the pre-split conv-input format, per pixel 64 bf16 hi | 64 bf16 lo.
+__device__ __forceinline__ void store_split4(uint8_t* pixel_base, int cq, float4 v) {
+  uint32_t h0, l0, h1, l1;
+  split_bf16x2(v.x, v.y, h0, l0);
+  split_bf16x2(v.z, v.w, h1, l1);
+  *reinterpret_cast<uint2*>(pixel_base + cq * 8) = make_uint2(h0, h1);
+  *reinterpret_cast<uint2*>(pixel_base + 128 + cq * 8) = make_uint2(l0, l1);
+}
+
+template <bool SPLIT>
 __global__ void __launch_bounds__(256) inorm_prelu_kernel(const float* __restrict__ x, long long pix_per_b,
                                                          const float* __restrict__ stats, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, const float* __restrict__ slope,
-                                                         float* __restrict__ y) {
+                                                         void* __restrict__ yv) {
   const int b = blockIdx.y, cq = threadIdx.x & 15;
   float sc[4], sh[4], sl[4];
 #pragma unroll
@@ -121,14 +131,21 @@ __global__ void __launch_bounds__(256) inorm_prelu_kernel(const float* __restric
     sl[j] = slope[c];
   }
   const float* xb = x + (long long)b * pix_per_b * 64;
-  float* yb = y + (long long)b * pix_per_b * 64;
   for (long long p = (long long)blockIdx.x * 16 + (threadIdx.x >> 4); p < pix_per_b; p += (long long)gridDim.x * 16) {
     float4 v = ldg4(xb + p * 64 + cq * 4);
     v.x = fmaf(v.x, sc[0], sh[0]); v.y = fmaf(v.y, sc[1], sh[1]); v.z = fmaf(v.z, sc[2], sh[2]); v.w = fmaf(v.w, sc[3], sh[3]);
     v.x = v.x >= 0.f ? v.x : v.x * sl[0]; v.y = v.y >= 0.f ? v.y : v.y * sl[1];
     v.z = v.z >= 0.f ? v.z : v.z * sl[2]; v.w = v.w >= 0.f ? v.w : v.w * sl[3];
-    st4(yb + p * 64 + cq * 4, v);
+    const long long gp = (long long)b * pix_per_b + p;
+    if (SPLIT) store_split4(reinterpret_cast<uint8_t*>(yv) + gp * 256, cq, v);
+    else st4(reinterpret_cast<float*>(yv) + gp * 64 + cq * 4, v);
   }
+}
+
+__global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ x, long long pixels, uint8_t* __restrict__ y) {
+  const int cq = threadIdx.x & 15;
+  for (long long p = (long long)blockIdx.x * 16 + (threadIdx.x >> 4); p < pixels; p += (long long)gridDim.x * 16)
+    store_split4(y + p * 256, cq, ldg4(x + p * 64 + cq * 4));
 }
 
 // ---- MaskDecoder.conv_1: Conv2d(64 -> 1, (1,2)); one warp per output pixel pair of rows ------------
@@ -301,11 +318,20 @@ extern "C" int seb200_inorm_stats(const float* x, int B, long long pix_per_b, in
 }
 
 extern "C" int seb200_inorm_prelu(const float* x, int B, long long pix_per_b, int C, const float* stats, const float* gamma,
-                                  const float* beta, const float* slope, float* y, void* stream) {
+                                  const float* beta, const float* slope, void* y, int out_format, void* stream) {
   SEB_REQUIRE(x && y && stats && gamma && beta && slope && B > 0 && B < 65536 && C == 64 && aligned16(x) && aligned16(y), SEB_EINVAL, "inorm_prelu: bad arguments");
+  SEB_REQUIRE(out_format == 0 || out_format == 1, SEB_EINVAL, "inorm_prelu: out_format must be 0 (fp32) or 1 (split bf16)");
   dim3 grid(grid_for(pix_per_b, 16 * 8, 148 * 16 / (B < 16 ? B : 16) + 1), B);
-  inorm_prelu_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, pix_per_b, stats, gamma, beta, slope, y);
+  if (out_format == 1) inorm_prelu_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, pix_per_b, stats, gamma, beta, slope, y);
+  else inorm_prelu_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, pix_per_b, stats, gamma, beta, slope, y);
   SEB_CHECK_LAUNCH("inorm_prelu_kernel");
+  return 0;
+}
+
+extern "C" int seb200_split_planes(const float* x, long long pixels, void* y, void* stream) {
+  SEB_REQUIRE(x && y && pixels > 0 && aligned16(x) && aligned16(y), SEB_EINVAL, "split_planes: bad arguments");
+  split_planes_kernel<<<grid_for(pixels, 16 * 8), 256, 0, (cudaStream_t)stream>>>(x, pixels, reinterpret_cast<uint8_t*>(y));
+  SEB_CHECK_LAUNCH("split_planes_kernel");
   return 0;
 }
 

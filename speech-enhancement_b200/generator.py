@@ -25,7 +25,8 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from ._lib import (EPI_BIAS, EPI_GLU, EPI_QKV_F16, EPI_RESID, EPI_SUBPIXEL, EPI_SWISH, LOAD_CONV, LOAD_ROWS, LOAD_ROWS_LN)
+from ._lib import (EPI_BIAS, EPI_GLU, EPI_QKV_F16, EPI_RESID, EPI_SUBPIXEL, EPI_SWISH, LOAD_CONV, LOAD_CONV_SPLIT, LOAD_ROWS,
+                   LOAD_ROWS_LN)
 from .packing import PackedWeight, conv_weight_matrix, glu_interleave, pack_weight
 
 
@@ -236,6 +237,7 @@ class TSCNet(nn.Module):
             # decoders @F=101: 4 dense outputs + raw, sub-pixel output @F=202
             "dec": [torch.empty(Ph, 64, **f32) for _ in range(4)], "dec_raw": torch.empty(Ph, 64, **f32),
             "sp": torch.empty(B * T * 2 * Fh, 64, **f32),
+            "xs": torch.empty(Ph, 64, **f32),          # TSCB output re-written in the pre-split conv-input format
             # conformer token buffers
             "x": torch.empty(Ph, 64, **f32), "y": torch.empty(Ph, 64, **f32), "h": torch.empty(Ph, 256, **f32),
             "qkv": torch.empty(Ph, 192, **f32), "o": torch.empty(Ph, 64, **f32),       # qkv doubles as the fp16 [Ph, 192] buffer
@@ -258,12 +260,23 @@ class TSCNet(nn.Module):
         ops.inorm_prelu(raw, B, pix_per_b, ws["stats"], gamma, beta, slope, out)
         return out
 
+    @staticmethod
+    def _as_split(t: torch.Tensor) -> torch.Tensor:
+        """fp32 [P, 64] storage viewed as the pre-split conv-input format: bfloat16 [P, 2, 64] (hi | lo), same bytes."""
+        return t.view(torch.bfloat16).view(t.shape[0], 2, 64)
+
+    def _conv_in(self, t: torch.Tensor) -> torch.Tensor:
+        """the form in which conv inputs are stored / read for the active GEMM main loop"""
+        return self._as_split(t) if self.engine == "tcgen05" else t
+
     def _dense(self, P, prefix, ws, x0, outs, raw, B, T, F):
-        """DilatedDenseNet.forward (generator.py:24-32): layer i reads [out_{i-1}, ..., out_1, x0] through slot pointers."""
+        """DilatedDenseNet.forward (generator.py:24-32): layer i reads [out_{i-1}, ..., out_1, x0] through slot pointers.
+        x0 / outs are conv-input tensors (pre-split bf16 on the tcgen05 engine, fp32 on the fp32 loop)."""
+        loader = LOAD_CONV_SPLIT if self.engine == "tcgen05" else LOAD_CONV
         slots = [x0]
         for i in range(1, 5):
             w: PackedWeight = P[f"{prefix}.conv{i}"]
-            ops.gemm(loader=LOAD_CONV, epilogue=EPI_BIAS, M=B * T * F, w=w, a=slots, out=raw, ldo=64, engine=self.engine, label="dconv",
+            ops.gemm(loader=loader, epilogue=EPI_BIAS, M=B * T * F, w=w, a=slots, out=raw, ldo=64, engine=self.engine, label="dconv",
                      conv=dict(B=B, T=T, Fin=F, Fout=F, taps_t=2, dil=2 ** (i - 1), stride_f=1, nslots=i))
             self._inorm_prelu(ws, raw, B, T * F, P[f"{prefix}.norm{i}.weight"], P[f"{prefix}.norm{i}.bias"], P[f"{prefix}.prelu{i}.weight"], outs[i - 1])
             slots = [outs[i - 1]] + slots
@@ -320,12 +333,14 @@ class TSCNet(nn.Module):
         e = "dense_encoder"
 
         # ---- DenseEncoder (generator.py:50-54)
-        enc, raw = ws["enc"], ws["enc_raw"]
+        tc = eng == "tcgen05"
+        conv_loader = LOAD_CONV_SPLIT if tc else LOAD_CONV
+        enc, raw = [self._conv_in(t) for t in ws["enc"]], ws["enc_raw"]
         ops.conv1x1_in3(in3, P[f"{e}.conv_1.w"], P[f"{e}.conv_1.b"], raw)
         self._inorm_prelu(ws, raw, B, T * F, P[f"{e}.conv_1.1.weight"], P[f"{e}.conv_1.1.bias"], P[f"{e}.conv_1.2.weight"], enc[0])
         d4 = self._dense(P, f"{e}.dilated_dense", ws, enc[0], enc[1:5], raw, B, T, F)
         rawh = ws["dec_raw"]
-        ops.gemm(loader=LOAD_CONV, epilogue=EPI_BIAS, M=B * T * Fh, w=P[f"{e}.conv_2"], a=[d4], out=rawh, ldo=64, engine=eng, label="conv2",
+        ops.gemm(loader=conv_loader, epilogue=EPI_BIAS, M=B * T * Fh, w=P[f"{e}.conv_2"], a=[d4], out=rawh, ldo=64, engine=eng, label="conv2",
                  conv=dict(B=B, T=T, Fin=F, Fout=Fh, taps_t=1, dil=1, stride_f=2, nslots=1))
         x = ws["x"]
         self._inorm_prelu(ws, rawh, B, T * Fh, P[f"{e}.conv_2.1.weight"], P[f"{e}.conv_2.1.bias"], P[f"{e}.conv_2.2.weight"], x)
@@ -344,9 +359,10 @@ class TSCNet(nn.Module):
 
         # ---- MaskDecoder (generator.py:106-112)
         m = "mask_decoder"
-        dec, sp = ws["dec"], ws["sp"]
-        d4 = self._dense(P, f"{m}.dense_block", ws, x, dec, rawh, B, T, Fh)
-        ops.gemm(loader=LOAD_CONV, epilogue=EPI_SUBPIXEL, M=M, w=P[f"{m}.sub_pixel"], a=[d4], out=sp, ldo=64, engine=eng, label="subpixel",
+        dec, sp = [self._conv_in(t) for t in ws["dec"]], ws["sp"]
+        x0 = ops.split_planes(x, self._as_split(ws["xs"])) if tc else x      # both decoders read the TSCB output as a conv input
+        d4 = self._dense(P, f"{m}.dense_block", ws, x0, dec, rawh, B, T, Fh)
+        ops.gemm(loader=conv_loader, epilogue=EPI_SUBPIXEL, M=M, w=P[f"{m}.sub_pixel"], a=[d4], out=sp, ldo=64, engine=eng, label="subpixel",
                  conv=dict(B=B, T=T, Fin=Fh, Fout=Fh, taps_t=1, dil=1, stride_f=1, nslots=1))
         b1, g_in, b_in, s1, wf, bf = P[f"{m}.scalars"]
         ops.mask_conv(sp, B * T, 2 * Fh, P[f"{m}.conv_1.w"], b1, ws["mask_raw"])
@@ -354,8 +370,8 @@ class TSCNet(nn.Module):
 
         # ---- ComplexDecoder (generator.py:124-129)
         c = "complex_decoder"
-        d4 = self._dense(P, f"{c}.dense_block", ws, x, dec, rawh, B, T, Fh)
-        ops.gemm(loader=LOAD_CONV, epilogue=EPI_SUBPIXEL, M=M, w=P[f"{c}.sub_pixel"], a=[d4], out=sp, ldo=64, engine=eng, label="subpixel",
+        d4 = self._dense(P, f"{c}.dense_block", ws, x0, dec, rawh, B, T, Fh)
+        ops.gemm(loader=conv_loader, epilogue=EPI_SUBPIXEL, M=M, w=P[f"{c}.sub_pixel"], a=[d4], out=sp, ldo=64, engine=eng, label="subpixel",
                  conv=dict(B=B, T=T, Fin=Fh, Fout=Fh, taps_t=1, dil=1, stride_f=1, nslots=1))
         ops.inorm_stats(sp, B, T * 2 * Fh, 64, ws["stats"], ws["in_ws"])
         ops.complex_conv(sp, B, T, 2 * Fh, ws["stats"], P[f"{c}.norm.weight"], P[f"{c}.norm.bias"], P[f"{c}.prelu.weight"],

@@ -14,7 +14,7 @@ import torch
 
 from . import _lib
 from ._lib import (ENGINE_SIMT, ENGINE_TCGEN05, EPI_BIAS, EPI_COMPRESS, EPI_GLU, EPI_QKV_F16, EPI_RESID, EPI_SUBPIXEL, EPI_SWISH,
-                   LOAD_CONV, LOAD_HANKEL, LOAD_ROWS, LOAD_ROWS_LN, SebFfn, SebGemm, SebSeq, check, ptr, require_cuda, stream_ptr)
+                   LOAD_CONV, LOAD_CONV_SPLIT, LOAD_HANKEL, LOAD_ROWS, LOAD_ROWS_LN, SebFfn, SebGemm, SebSeq, check, ptr, require_cuda, stream_ptr)
 from .packing import PackedWeight
 
 ENGINES = {"tcgen05": ENGINE_TCGEN05, "simt": ENGINE_SIMT}
@@ -106,6 +106,11 @@ def gemm(*, loader: int, epilogue: int, M: int, w: PackedWeight, a: Sequence[tor
         if out.dtype != torch.float16 or not out.is_contiguous():
             raise RuntimeError("the fp16 q|k|v epilogue writes a contiguous float16 [M, 192] tensor")
         _f32c(resid, *a)
+    elif loader == LOAD_CONV_SPLIT:
+        for t in a:
+            if t.dtype != torch.bfloat16 or not t.is_contiguous() or not t.is_cuda:
+                raise RuntimeError("LOAD_CONV_SPLIT reads contiguous CUDA bfloat16 [pixels, 2, 64] (hi | lo) tensors")
+        _f32c(out, resid)
     else:
         _f32c(out, resid, *a)
     g = SebGemm()
@@ -238,10 +243,27 @@ def inorm_stats(x, B: int, pix_per_b: int, C_: int, stats, workspace):
 
 
 def inorm_prelu(x, B: int, pix_per_b: int, stats, gamma, beta, slope, y):
-    _f32c(x, stats, gamma, beta, slope, y)
+    """y fp32 [.., 64] or, when y is bfloat16 [pixels, 2, 64], the pre-split conv-input format (hi | lo per pixel)."""
+    _f32c(x, stats, gamma, beta, slope)
+    split = y.dtype == torch.bfloat16
+    if not split:
+        _f32c(y)
+    elif not (y.is_contiguous() and y.is_cuda):
+        raise RuntimeError("split output must be a contiguous CUDA bfloat16 tensor")
     tok = _pb("inorm_prelu", 0.0, 8.0 * B * pix_per_b * 64) if _PROF is not None else None
     check(_lib.load().seb200_inorm_prelu(ptr(x), B, pix_per_b, 64, ptr(stats), ptr(gamma), ptr(beta), ptr(slope), ptr(y),
-                                         stream_ptr()), "seb200_inorm_prelu")
+                                         int(split), stream_ptr()), "seb200_inorm_prelu")
+    _pe(tok)
+    return y
+
+
+def split_planes(x, y):
+    """fp32 [pixels, 64] -> bfloat16 [pixels, 2, 64] (hi | lo), hi + lo == x to 2^-17."""
+    _f32c(x)
+    if y.dtype != torch.bfloat16 or not y.is_contiguous() or not y.is_cuda:
+        raise RuntimeError("split output must be a contiguous CUDA bfloat16 tensor")
+    tok = _pb("split_planes", 0.0, 8.0 * x.numel()) if _PROF is not None else None
+    check(_lib.load().seb200_split_planes(ptr(x), x.numel() // 64, ptr(y), stream_ptr()), "seb200_split_planes")
     _pe(tok)
     return y
 

@@ -12,8 +12,8 @@ from oracle import tscnet_oracle as O, weights
 
 import se_b200
 from se_b200 import ops, packing
-from se_b200._lib import (EPI_BIAS, EPI_COMPRESS, EPI_GLU, EPI_QKV_F16, EPI_RESID, EPI_SUBPIXEL, EPI_SWISH, LOAD_CONV, LOAD_HANKEL,
-                          LOAD_ROWS, LOAD_ROWS_LN)
+from se_b200._lib import (EPI_BIAS, EPI_COMPRESS, EPI_GLU, EPI_QKV_F16, EPI_RESID, EPI_SUBPIXEL, EPI_SWISH, LOAD_CONV, LOAD_CONV_SPLIT,
+                          LOAD_HANKEL, LOAD_ROWS, LOAD_ROWS_LN)
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -116,6 +116,45 @@ def test_gemm_dilated_conv(engine, layer):
     assert rel_max(out.view(B, T, Fq, 64), _cl(ref)) < TOL[engine]
 
 
+def _split(x_cl):      # fp32 [.., 64] -> pre-split conv-input format via the kernel
+    flat = x_cl.reshape(-1, 64).contiguous()
+    y = torch.empty(flat.shape[0], 2, 64, device=DEV, dtype=torch.bfloat16)
+    ops.split_planes(flat, y)
+    assert rel_max(y.float().sum(1), flat) < 2.0 ** -16
+    return y
+
+
+@pytest.mark.parametrize("layer,B,T,Fq", [(1, 2, 21, 13), (3, 1, 40, 101), (4, 2, 30, 201)])
+def test_conv_on_presplit_activations_tcgen05(layer, B, T, Fq):
+    """cp.async loader on (hi | lo) bf16 inputs: dilated dense conv, strided conv_2 and the sub-pixel conv"""
+    dil = 2 ** (layer - 1)
+    slots_nchw = [rnd(B, 64, T, Fq, seed=120 + i) for i in range(layer)]
+    w = rnd(64, 64 * layer, 2, 3, seed=130, scale=(64 * layer * 6) ** -0.5)
+    b = rnd(64, seed=131, scale=0.1)
+    ref = F.conv2d(F.pad(torch.cat(slots_nchw, 1).double(), (1, 1, dil, 0)), w.double(), b.double(), dilation=(dil, 1))
+    pw = packing.pack_weight(packing.conv_weight_matrix(w.cpu()), 64, b.cpu()).to(DEV)
+    out = torch.empty(B * T * Fq, 64, device=DEV)
+    ops.gemm(loader=LOAD_CONV_SPLIT, epilogue=EPI_BIAS, M=B * T * Fq, w=pw, a=[_split(_cl(s_)) for s_ in slots_nchw], out=out, ldo=64,
+             engine="tcgen05", conv=dict(B=B, T=T, Fin=Fq, Fout=Fq, taps_t=2, dil=dil, stride_f=1, nslots=layer))
+    assert rel_max(out.view(B, T, Fq, 64), _cl(ref)) < TOL["tcgen05"]
+    if layer != 1:
+        return
+    Fh = (Fq - 1) // 2 + 1
+    x = slots_nchw[0]
+    w2, b2 = rnd(64, 64, 1, 3, seed=141, scale=0.07), rnd(64, seed=142, scale=0.1)
+    ref = F.conv2d(x.double(), w2.double(), b2.double(), stride=(1, 2), padding=(0, 1))
+    out = torch.empty(B * T * Fh, 64, device=DEV)
+    ops.gemm(loader=LOAD_CONV_SPLIT, epilogue=EPI_BIAS, M=B * T * Fh, w=packing.pack_weight(packing.conv_weight_matrix(w2.cpu()), 64, b2.cpu()).to(DEV),
+             a=[_split(_cl(x))], out=out, ldo=64, engine="tcgen05", conv=dict(B=B, T=T, Fin=Fq, Fout=Fh, taps_t=1, dil=1, stride_f=2, nslots=1))
+    assert rel_max(out.view(B, T, Fh, 64), _cl(ref)) < TOL["tcgen05"]
+    ws_, bs = rnd(128, 64, 1, 3, seed=144, scale=0.07), rnd(128, seed=145, scale=0.1)
+    ref = O.sub_pixel(x.cpu(), {"p.conv.weight": ws_.cpu(), "p.conv.bias": bs.cpu()}, "p")
+    out = torch.empty(B * T * 2 * Fq, 64, device=DEV)
+    ops.gemm(loader=LOAD_CONV_SPLIT, epilogue=EPI_SUBPIXEL, M=B * T * Fq, w=packing.pack_weight(packing.conv_weight_matrix(ws_.cpu()), 128, bs.cpu()).to(DEV),
+             a=[_split(_cl(x))], out=out, ldo=64, engine="tcgen05", conv=dict(B=B, T=T, Fin=Fq, Fout=Fq, taps_t=1, dil=1, stride_f=1, nslots=1))
+    assert rel_max(out.view(B, T, 2 * Fq, 64).cpu(), _cl(ref)) < TOL["tcgen05"]
+
+
 @pytest.mark.parametrize("engine", ENGINES)
 def test_gemm_strided_conv_and_subpixel(engine):
     B, T, Fq = 2, 9, 21
@@ -197,6 +236,9 @@ def test_conv1x1_inorm_prelu():
     xn = x.permute(0, 2, 1).reshape(B, 64, T, Fq)
     ref = F.prelu(F.instance_norm(xn.double(), weight=g.double(), bias=be.double(), eps=1e-5), sl.double())
     assert rel_max(y.view(B, T, Fq, 64), ref.permute(0, 2, 3, 1)) < 1e-5
+    ys = torch.empty(B * T * Fq, 2, 64, device=DEV, dtype=torch.bfloat16)          # pre-split conv-input format
+    ops.inorm_prelu(x, B, T * Fq, stats, g, be, sl, ys)
+    assert rel_max(ys.float().sum(1).view(B, T * Fq, 64), y) < 2.0 ** -16
     stats2 = torch.empty_like(stats)
     ops.inorm_stats(x, B, T * Fq, 64, stats2, wsb)
     assert torch.equal(stats, stats2)                  # deterministic reduction
