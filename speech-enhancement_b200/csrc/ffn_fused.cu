@@ -11,8 +11,7 @@
 //                          epilogue warps: tcgen05.ld acc1 -> +b1 -> swish -> bf16 hi/lo -> smem H (K-chunk q of GEMM 2)
 //                          MMA2(q): acc2 (TMEM, 64 cols) += H . W2[:, 64q:64q+64]^T
 //   final                : tcgen05.ld acc2 -> smem transpose -> coalesced: *alpha + b2 + x (-> LayerNorm + resid2) -> store
-// acc1 is double buffered, so MMA1(q+1) overlaps the Swish epilogue of chunk q; weights stream through 16 KB
-// single-slot rings with cp.async.bulk + mbarriers.  96 KB smem and 256 TMEM columns per CTA -> 2 CTAs per SM.
+// acc1 is double buffered, so MMA1(q+1) overlaps the Swish epilogue of chunk q.
 #include "gemm_engine.cuh"
 
 namespace seb {
@@ -26,152 +25,197 @@ struct FfnArgs {
   const float* pn_g; const float* pn_b; const float* resid2;
 };
 
-constexpr int FF_THREADS = 320;
+// ---- persistent, warp-specialised version ----------------------------------------------------------------------
+// One CTA per SM loops over 128-token tiles.  Both weight images (W1 and W2, hi|lo, 128 KB) are loaded ONCE and stay
+// resident in shared memory; 4 loader warps run ahead (LayerNorm + split of the next tile into a double-buffered
+// A operand); 8 epilogue warps do the Swish mid-epilogues and the final store; 1 thread issues every tcgen05.mma.
+// acc1 and acc2 are double buffered in TMEM, so MMA1 of tile i+1 overlaps the final epilogue of tile i.
+constexpr int FF_LOAD_WARPS = 4, FF_EPI_WARPS = 16;
+constexpr int FF_EPI_THREADS = FF_EPI_WARPS * 32;
+constexpr int FF_CG = FF_EPI_WARPS / 4;            // column groups: each epilogue thread owns one row x (64 / FF_CG) columns
+constexpr int FF_CPT = 64 / FF_CG;                 // columns per thread per quarter (16)
+constexpr int FF_THREADS = (FF_LOAD_WARPS + FF_EPI_WARPS + 2) * 32;     // + MMA warp + weight warp = 704
 constexpr int FF_PLANE = BM * 128;                 // 16 KB: one bf16 plane of a 128 x 64 operand tile
 constexpr int FF_WBLK = 2 * 64 * 128;              // 16 KB: hi|lo image of a 64-row x 64-k weight block
-constexpr int FF_SMEM = 1024 + 2 * FF_PLANE + FF_WBLK + 2 * FF_PLANE + FF_WBLK;
+constexpr int FF_SMEM = 1024 + 2 * (2 * FF_PLANE) /*A x2*/ + 4 * FF_WBLK /*W1*/ + 4 * FF_WBLK /*W2*/ + 2 * FF_PLANE /*H*/;
 
-__global__ void __launch_bounds__(FF_THREADS, 2) ffn_fused_kernel(const FfnArgs a) {
+__global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t a_full, w1_full, w1_empty, w2_full, w2_empty, h_full, h_empty, acc1_full[2], acc1_empty[2], acc2_full;
+  __shared__ uint64_t a_full[2], a_empty[2], w_full, acc1_full[2], acc1_empty[2], h_full, h_empty, acc2_full[2], acc2_empty[2];
   __shared__ uint32_t tmem_base_s;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA = smem;                       // A hi | lo   (32 KB)   -- reused as the fp32 staging tile at the end
-  uint8_t* sW1 = sA + 2 * FF_PLANE;         // W1 block hi | lo (16 KB)
-  uint8_t* sH = sW1 + FF_WBLK;              // H hi | lo   (32 KB)
-  uint8_t* sW2 = sH + 2 * FF_PLANE;         // W2 block hi | lo (16 KB)
+  uint8_t* sA = smem;                           // [2][hi | lo]            64 KB
+  uint8_t* sW1 = sA + 4 * FF_PLANE;             // 4 blocks x (hi | lo)    64 KB
+  uint8_t* sW2 = sW1 + 4 * FF_WBLK;             // 4 blocks x (hi | lo)    64 KB
+  uint8_t* sH = sW2 + 4 * FF_WBLK;              // hi | lo                 32 KB  (also the fp32 staging tile of the final store)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.x * BM;
+  const int ntiles = (a.M + BM - 1) / BM;
+  const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (tid == 0) {
-    ptx::mbar_init(&a_full, 256);
-    ptx::mbar_init(&w1_full, 1); ptx::mbar_init(&w1_empty, 1);
-    ptx::mbar_init(&w2_full, 1); ptx::mbar_init(&w2_empty, 1);
-    ptx::mbar_init(&h_full, 256); ptx::mbar_init(&h_empty, 1);
-    ptx::mbar_init(&acc1_full[0], 1); ptx::mbar_init(&acc1_full[1], 1);
-    ptx::mbar_init(&acc1_empty[0], 256); ptx::mbar_init(&acc1_empty[1], 256);
-    ptx::mbar_init(&acc2_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&a_full[i], FF_LOAD_WARPS * 32); ptx::mbar_init(&a_empty[i], 1);
+      ptx::mbar_init(&acc1_full[i], 1); ptx::mbar_init(&acc1_empty[i], FF_EPI_WARPS * 32);
+      ptx::mbar_init(&acc2_full[i], 1); ptx::mbar_init(&acc2_empty[i], FF_EPI_WARPS * 32);
+    }
+    ptx::mbar_init(&w_full, 1);
+    ptx::mbar_init(&h_full, FF_EPI_WARPS * 32); ptx::mbar_init(&h_empty, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 8) ptx::tmem_alloc(&tmem_base_s, 256);
+  if (warp == FF_LOAD_WARPS + FF_EPI_WARPS) ptx::tmem_alloc(&tmem_base_s, 256);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t tmem_base = tmem_base_s;     // acc1[b] at column 64 b, acc2[b] at column 128 + 64 b
 
-  if (warp < 8) {
-    // ---------------- A operand: LayerNorm(x) split to bf16 hi/lo ----------------
-    {
-      GemmArgs g;
-      g.a[0] = a.x; g.lda = 64; g.M = a.M; g.ln_g = a.ln_g; g.ln_b = a.ln_b;
-      const int sub = tid & 7, rloc = tid >> 3;
-#pragma unroll
-      for (int p = 0; p < 4; ++p) {
+  if (warp < FF_LOAD_WARPS) {
+    // ================= loaders: x -> LayerNorm -> bf16 hi/lo -> swizzled A[s] =================
+    GemmArgs g;
+    g.a[0] = a.x; g.lda = 64; g.M = a.M; g.ln_g = a.ln_g; g.ln_b = a.ln_b;
+    const int sub = tid & 7, rloc = tid >> 3;          // 16 rows per pass, 8 passes
+    for (int it = 0; it < my_tiles; ++it) {
+      const int m0 = ((int)blockIdx.x + it * (int)gridDim.x) * BM;
+      const int s = it & 1;
+      // pull the NEXT tile's rows (and its residual rows) into L2 now: 128 loader threads x 2 (x 2) 128-byte lines,
+      // so the demand loads below find their data on chip and DRAM always has a full tile in flight per SM
+      if (it + 1 < my_tiles) {
+        const long long nrow = (long long)(m0 + (int)gridDim.x * BM) * 64;
+        const long long off = nrow + (long long)tid * 64;            // floats: 2 lines of 32 floats per thread
+        if ((nrow >> 6) + (tid >> 0) * 1 < (long long)a.M) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.x + off));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.x + off + 32));
+          if (a.resid2 && a.resid2 != a.x) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.resid2 + off));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.resid2 + off + 32));
+          }
+        }
+      }
+      ptx::mbar_wait(&a_empty[s], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+      uint8_t* dA = sA + s * 2 * FF_PLANE;
+#pragma unroll 4
+      for (int p = 0; p < 8; ++p) {
+        const int r = p * 16 + rloc;
         Loader<SEB_LOAD_ROWS_LN>::Row row;
-        Loader<SEB_LOAD_ROWS_LN>::init_row(g, m0 + p * 32 + rloc, row);
+        Loader<SEB_LOAD_ROWS_LN>::init_row(g, m0 + r, row);
         float v[8];
         Loader<SEB_LOAD_ROWS_LN>::load(g, row, 0, sub, v);
         uint4 hi, lo;
         split_bf16x2(v[0], v[1], hi.x, lo.x); split_bf16x2(v[2], v[3], hi.y, lo.y);
         split_bf16x2(v[4], v[5], hi.z, lo.z); split_bf16x2(v[6], v[7], hi.w, lo.w);
-        const int r = p * 32 + rloc;
         const int off = r * 128 + ((sub ^ (r & 7)) << 4);
-        *reinterpret_cast<uint4*>(sA + off) = hi;
-        *reinterpret_cast<uint4*>(sA + FF_PLANE + off) = lo;
+        *reinterpret_cast<uint4*>(dA + off) = hi;
+        *reinterpret_cast<uint4*>(dA + FF_PLANE + off) = lo;
       }
       ptx::fence_proxy_async_smem();
-      ptx::mbar_arrive(&a_full);
+      ptx::mbar_arrive(&a_full[s]);
     }
-    // ---------------- mid epilogue: acc1 -> +b1 -> swish -> H operand ----------------
-    const int wq = warp & 3, half = warp >> 2;
+  } else if (warp < FF_LOAD_WARPS + FF_EPI_WARPS) {
+    // ================= epilogue warps =================
+    const int ew = warp - FF_LOAD_WARPS;                // 0..15
+    const int wq = warp & 3, cg = ew >> 2;              // TMEM lane quarter (hardware: warp % 4), column group
     const int row = wq * 32 + lane;
-#pragma unroll 1
-    for (int q = 0; q < 4; ++q) {
-      const int b = q & 1;
-      ptx::mbar_wait(&acc1_full[b], (uint32_t)(q >> 1) & 1u);
-      ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(b * 64 + half * 32);
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        float t8[8];
-        ptx::tmem_ld8(taddr + j, t8);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[j + i] = t8[i];
-      }
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&acc1_empty[b]);
-      const float* bias = a.b1 + q * 64 + half * 32;
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 bb = ldg4(bias + j);
-        v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
-      }
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] *= sigmoidf_acc(v[j]);
-      ptx::mbar_wait(&h_empty, (uint32_t)(q & 1) ^ 1u);
-#pragma unroll
-      for (int c8 = 0; c8 < 4; ++c8) {
-        uint4 hi, lo;
-        split_bf16x2(v[c8 * 8 + 0], v[c8 * 8 + 1], hi.x, lo.x); split_bf16x2(v[c8 * 8 + 2], v[c8 * 8 + 3], hi.y, lo.y);
-        split_bf16x2(v[c8 * 8 + 4], v[c8 * 8 + 5], hi.z, lo.z); split_bf16x2(v[c8 * 8 + 6], v[c8 * 8 + 7], hi.w, lo.w);
-        const int c = half * 4 + c8;
-        const int off = row * 128 + ((c ^ (row & 7)) << 4);
-        *reinterpret_cast<uint4*>(sH + off) = hi;
-        *reinterpret_cast<uint4*>(sH + FF_PLANE + off) = lo;
-      }
-      ptx::fence_proxy_async_smem();
-      ptx::mbar_arrive(&h_full);
-    }
-    // ---------------- final epilogue ----------------
-    ptx::mbar_wait(&acc2_full, 0);
-    ptx::tc_fence_after();
-    float4* stg = reinterpret_cast<float4*>(sA);           // [128 rows][16 x float4], chunk index XOR (row & 7)
-    {
-      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(128 + half * 32);
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        float t8[8];
-        ptx::tmem_ld8(taddr + j, t8);
-        const int c0 = half * 8 + (j >> 2);
-        stg[row * 16 + ((c0 + 0) ^ (row & 7))] = make_float4(t8[0], t8[1], t8[2], t8[3]);
-        stg[row * 16 + ((c0 + 1) ^ (row & 7))] = make_float4(t8[4], t8[5], t8[6], t8[7]);
-      }
-    }
-    ptx::tc_fence_before();
-    asm volatile("bar.sync 1, 256;" ::: "memory");
     const int cq = lane & 15;
     const float4 b2 = ldg4(a.b2 + cq * 4);
     float4 pg = make_float4(0, 0, 0, 0), pb = pg;
     if (a.pn_g) { pg = ldg4(a.pn_g + cq * 4); pb = ldg4(a.pn_b + cq * 4); }
-#pragma unroll 2
-    for (int it = 0; it < 8; ++it) {
-      const int R = it * 16 + warp * 2 + (lane >> 4);
-      const int m = m0 + R;
-      const bool ok = m < a.M;
-      float4 acc = stg[R * 16 + (cq ^ (R & 7))];
-      float4 xv = ok ? *reinterpret_cast<const float4*>(a.x + (long long)m * 64 + cq * 4) : make_float4(0, 0, 0, 0);
-      float4 y;
-      y.x = fmaf(a.alpha, acc.x + b2.x, xv.x); y.y = fmaf(a.alpha, acc.y + b2.y, xv.y);
-      y.z = fmaf(a.alpha, acc.z + b2.z, xv.z); y.w = fmaf(a.alpha, acc.w + b2.w, xv.w);
-      if (a.pn_g) {       // post_norm + outer residual (uniform branch)
-        float s = y.x + y.y + y.z + y.w;
+    float4* stg = reinterpret_cast<float4*>(sH);        // [128 rows][16 x float4], chunk index XOR (row & 7)
+    for (int it = 0; it < my_tiles; ++it) {
+      const int m0 = ((int)blockIdx.x + it * (int)gridDim.x) * BM;
+      const int ab = it & 1;
+      // ---- mid epilogues: acc1 -> +b1 -> swish -> H operand (K-chunk q of GEMM 2)
+#pragma unroll 1
+      for (int q = 0; q < 4; ++q) {
+        const int b = q & 1;
+        const uint32_t u1 = (uint32_t)(2 * it + (q >> 1)), uh = (uint32_t)(4 * it + q);
+        const float* bias = a.b1 + q * 64 + cg * FF_CPT;
+        float4 bb[FF_CPT / 4];
 #pragma unroll
-        for (int o = 1; o < 16; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        const float mean = s * (1.0f / 64.0f);
-        y.x -= mean; y.y -= mean; y.z -= mean; y.w -= mean;
-        float qv = y.x * y.x + y.y * y.y + y.z * y.z + y.w * y.w;
+        for (int j = 0; j < FF_CPT / 4; ++j) bb[j] = ldg4(bias + 4 * j);
+        ptx::mbar_wait(&acc1_full[b], u1 & 1u);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(b * 64 + cg * FF_CPT);
+        float v[FF_CPT];
 #pragma unroll
-        for (int o = 1; o < 16; o <<= 1) qv += __shfl_xor_sync(0xffffffffu, qv, o);
-        const float rstd = 1.0f / sqrtf(qv * (1.0f / 64.0f) + 1e-5f);
-        float4 r2 = ok ? *reinterpret_cast<const float4*>(a.resid2 + (long long)m * 64 + cq * 4) : make_float4(0, 0, 0, 0);
-        y.x = y.x * rstd * pg.x + pb.x + r2.x; y.y = y.y * rstd * pg.y + pb.y + r2.y;
-        y.z = y.z * rstd * pg.z + pb.z + r2.z; y.w = y.w * rstd * pg.w + pb.w + r2.w;
+        for (int j = 0; j < FF_CPT; j += 8) {
+          float t8[8];
+          ptx::tmem_ld8(taddr + j, t8);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[j + i] = t8[i];
+        }
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&acc1_empty[b]);
+#pragma unroll
+        for (int j = 0; j < FF_CPT / 4; ++j) { v[4 * j] += bb[j].x; v[4 * j + 1] += bb[j].y; v[4 * j + 2] += bb[j].z; v[4 * j + 3] += bb[j].w; }
+#pragma unroll
+        for (int j = 0; j < FF_CPT; ++j) v[j] *= sigmoidf_acc(v[j]);
+        ptx::mbar_wait(&h_empty, (uh & 1u) ^ 1u);
+#pragma unroll
+        for (int c8 = 0; c8 < FF_CPT / 8; ++c8) {
+          uint4 hi, lo;
+          split_bf16x2(v[c8 * 8 + 0], v[c8 * 8 + 1], hi.x, lo.x); split_bf16x2(v[c8 * 8 + 2], v[c8 * 8 + 3], hi.y, lo.y);
+          split_bf16x2(v[c8 * 8 + 4], v[c8 * 8 + 5], hi.z, lo.z); split_bf16x2(v[c8 * 8 + 6], v[c8 * 8 + 7], hi.w, lo.w);
+          const int c = cg * (FF_CPT / 8) + c8;
+          const int off = row * 128 + ((c ^ (row & 7)) << 4);
+          *reinterpret_cast<uint4*>(sH + off) = hi;
+          *reinterpret_cast<uint4*>(sH + FF_PLANE + off) = lo;
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive(&h_full);
       }
-      if (ok) st4(a.out + (long long)m * 64 + cq * 4, y);
+      // ---- final epilogue: acc2 -> staging (H buffer: every MMA2 of this tile has completed) -> coalesced store
+      // issue the residual loads first: they do not depend on the accumulator
+      float4 xv[128 / (FF_EPI_WARPS * 2)], r2v[128 / (FF_EPI_WARPS * 2)];
+#pragma unroll
+      for (int i8 = 0; i8 < 128 / (FF_EPI_WARPS * 2); ++i8) {
+        const int m = m0 + i8 * (FF_EPI_WARPS * 2) + ew * 2 + (lane >> 4);
+        const bool ok = m < a.M;
+        xv[i8] = ok ? *reinterpret_cast<const float4*>(a.x + (long long)m * 64 + cq * 4) : make_float4(0, 0, 0, 0);
+        r2v[i8] = (ok && a.pn_g) ? *reinterpret_cast<const float4*>(a.resid2 + (long long)m * 64 + cq * 4) : make_float4(0, 0, 0, 0);
+      }
+      ptx::mbar_wait(&acc2_full[ab], (uint32_t)(it >> 1) & 1u);
+      ptx::tc_fence_after();
+      {
+        const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(128 + ab * 64 + cg * FF_CPT);
+#pragma unroll
+        for (int j = 0; j < FF_CPT; j += 8) {
+          float t8[8];
+          ptx::tmem_ld8(taddr + j, t8);
+          const int c0 = cg * (FF_CPT / 4) + (j >> 2);
+          stg[row * 16 + ((c0 + 0) ^ (row & 7))] = make_float4(t8[0], t8[1], t8[2], t8[3]);
+          stg[row * 16 + ((c0 + 1) ^ (row & 7))] = make_float4(t8[4], t8[5], t8[6], t8[7]);
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&acc2_empty[ab]);
+      asm volatile("bar.sync 1, %0;" ::"n"(FF_EPI_THREADS) : "memory");
+#pragma unroll
+      for (int i8 = 0; i8 < 128 / (FF_EPI_WARPS * 2); ++i8) {
+        const int R = i8 * (FF_EPI_WARPS * 2) + ew * 2 + (lane >> 4);
+        const int m = m0 + R;
+        const bool ok = m < a.M;
+        const float4 acc = stg[R * 16 + (cq ^ (R & 7))];
+        float4 y;
+        y.x = fmaf(a.alpha, acc.x + b2.x, xv[i8].x); y.y = fmaf(a.alpha, acc.y + b2.y, xv[i8].y);
+        y.z = fmaf(a.alpha, acc.z + b2.z, xv[i8].z); y.w = fmaf(a.alpha, acc.w + b2.w, xv[i8].w);
+        if (a.pn_g) {       // post_norm + outer residual (uniform branch)
+          float sm = y.x + y.y + y.z + y.w;
+#pragma unroll
+          for (int o = 1; o < 16; o <<= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+          const float mean = sm * (1.0f / 64.0f);
+          y.x -= mean; y.y -= mean; y.z -= mean; y.w -= mean;
+          float qv = y.x * y.x + y.y * y.y + y.z * y.z + y.w * y.w;
+#pragma unroll
+          for (int o = 1; o < 16; o <<= 1) qv += __shfl_xor_sync(0xffffffffu, qv, o);
+          const float rstd = 1.0f / sqrtf(qv * (1.0f / 64.0f) + 1e-5f);
+          y.x = y.x * rstd * pg.x + pb.x + r2v[i8].x; y.y = y.y * rstd * pg.y + pb.y + r2v[i8].y;
+          y.z = y.z * rstd * pg.z + pb.z + r2v[i8].z; y.w = y.w * rstd * pg.w + pb.w + r2v[i8].w;
+        }
+        if (ok) st4(a.out + (long long)m * 64 + cq * 4, y);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(FF_EPI_THREADS) : "memory");     // staging tile is overwritten by the next tile's H chunk
     }
-  } else if (warp == 8) {
-    // ---------------- MMA issuer ----------------
+  } else if (warp == FF_LOAD_WARPS + FF_EPI_WARPS) {
+    // ================= MMA issuer =================
     if (lane == 0) {
       constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       const uint32_t uA = ptx::smem_u32(sA), uW1 = ptx::smem_u32(sW1), uH = ptx::smem_u32(sH), uW2 = ptx::smem_u32(sW2);
@@ -186,47 +230,47 @@ __global__ void __launch_bounds__(FF_THREADS, 2) ffn_fused_kernel(const FfnArgs 
           ptx::mma_bf16(d_tmem, a_hi + ko, w_hi + ko, IDESC, 1u);
         }
       };
-      auto mma1 = [&](int q) {
-        ptx::mbar_wait(&w1_full, (uint32_t)q & 1u);
-        ptx::mbar_wait(&acc1_empty[q & 1], ((uint32_t)(q >> 1) & 1u) ^ 1u);
+      ptx::mbar_wait(&w_full, 0);
+      for (int it = 0; it < my_tiles; ++it) {
+        const int s = it & 1, ab = it & 1;
+        auto mma1 = [&](int q) {
+          const uint32_t u1 = (uint32_t)(2 * it + (q >> 1));
+          ptx::mbar_wait(&acc1_empty[q & 1], (u1 & 1u) ^ 1u);
+          ptx::tc_fence_after();
+          gemm64(tmem_base + (uint32_t)((q & 1) * 64), uA + s * 2 * FF_PLANE, uW1 + q * FF_WBLK, true);
+          ptx::tc_commit(&acc1_full[q & 1]);
+          if (q == 3) ptx::tc_commit(&a_empty[s]);
+        };
+        auto mma2 = [&](int q) {
+          const uint32_t uh = (uint32_t)(4 * it + q);
+          ptx::mbar_wait(&h_full, uh & 1u);
+          ptx::tc_fence_after();
+          gemm64(tmem_base + 128u + (uint32_t)(ab * 64), uH, uW2 + q * FF_WBLK, q == 0);
+          ptx::tc_commit(&h_empty);
+          if (q == 3) ptx::tc_commit(&acc2_full[ab]);
+        };
+        ptx::mbar_wait(&a_full[s], (uint32_t)(it >> 1) & 1u);
+        ptx::mbar_wait(&acc2_empty[ab], ((uint32_t)(it >> 1) & 1u) ^ 1u);
         ptx::tc_fence_after();
-        gemm64(tmem_base + (uint32_t)((q & 1) * 64), uA, uW1, true);
-        ptx::tc_commit(&w1_empty);
-        ptx::tc_commit(&acc1_full[q & 1]);
-      };
-      auto mma2 = [&](int q) {
-        ptx::mbar_wait(&h_full, (uint32_t)q & 1u);
-        ptx::mbar_wait(&w2_full, (uint32_t)q & 1u);
-        ptx::tc_fence_after();
-        gemm64(tmem_base + 128u, uH, uW2, q == 0);
-        ptx::tc_commit(&h_empty);
-        ptx::tc_commit(&w2_empty);
-        if (q == 3) ptx::tc_commit(&acc2_full);
-      };
-      ptx::mbar_wait(&a_full, 0);
-      ptx::tc_fence_after();
-      mma1(0);
-      for (int q = 0; q < 4; ++q) {
-        if (q < 3) mma1(q + 1);
-        mma2(q);
+        mma1(0);
+        for (int q = 0; q < 4; ++q) {
+          if (q < 3) mma1(q + 1);
+          mma2(q);
+        }
       }
     }
   } else {
-    // ---------------- weight stager ----------------
-    if (lane == 0) {
-      const uint32_t uW1 = ptx::smem_u32(sW1), uW2 = ptx::smem_u32(sW2);
+    // ================= weights: loaded once, resident for the whole kernel =================
+    if (lane == 0 && my_tiles > 0) {
+      ptx::mbar_arrive_expect_tx(&w_full, 8 * FF_WBLK);
       for (int q = 0; q < 4; ++q) {
-        ptx::mbar_wait(&w1_empty, ((uint32_t)q & 1u) ^ 1u);
-        ptx::mbar_arrive_expect_tx(&w1_full, FF_WBLK);
-        ptx::bulk_g2s(uW1, a.w1 + (size_t)q * FF_WBLK, FF_WBLK, &w1_full);
-        ptx::mbar_wait(&w2_empty, ((uint32_t)q & 1u) ^ 1u);
-        ptx::mbar_arrive_expect_tx(&w2_full, FF_WBLK);
-        ptx::bulk_g2s(uW2, a.w2 + (size_t)q * FF_WBLK, FF_WBLK, &w2_full);
+        ptx::bulk_g2s(ptx::smem_u32(sW1) + q * FF_WBLK, a.w1 + (size_t)q * FF_WBLK, FF_WBLK, &w_full);
+        ptx::bulk_g2s(ptx::smem_u32(sW2) + q * FF_WBLK, a.w2 + (size_t)q * FF_WBLK, FF_WBLK, &w_full);
       }
     }
   }
   __syncthreads();
-  if (warp == 8) {
+  if (warp == FF_LOAD_WARPS + FF_EPI_WARPS) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 256);
   }
@@ -252,7 +296,14 @@ extern "C" int seb200_ffn_fused(const SebFfn* f, void* stream) {
   a.w1 = reinterpret_cast<const uint8_t*>(f->w1_tc); a.b1 = f->b1;
   a.w2 = reinterpret_cast<const uint8_t*>(f->w2_tc); a.b2 = f->b2;
   a.alpha = f->alpha; a.pn_g = f->post_gamma; a.pn_b = f->post_beta; a.resid2 = f->resid2;
-  const unsigned grid = (unsigned)((f->tokens + BM - 1) / BM);
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+  }
+  const long long ntiles = (f->tokens + BM - 1) / BM;
+  const unsigned grid = (unsigned)(ntiles < num_sms ? ntiles : num_sms);      // persistent: one CTA per SM
   ffn_fused_kernel<<<grid, FF_THREADS, FF_SMEM, (cudaStream_t)stream>>>(a);
   SEB_CHECK_LAUNCH("ffn_fused_kernel");
   return 0;
