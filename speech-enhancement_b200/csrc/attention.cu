@@ -8,7 +8,7 @@
 //            skewed read  S[i, j] += R[i, i - j - dlo]  through a warp-private shared-memory staging buffer.
 //            A 10-bit mantissa is sufficient for the three attention contractions.
 // variant 1: one-thread-per-query fp32 kernel; slow, used by the tests to cross-check variant 0.
-#include "common.cuh"
+#include "gemm_engine.cuh"   // ptx:: mbarrier helpers
 #include <cuda_fp16.h>
 
 namespace seb {
@@ -107,7 +107,8 @@ __global__ void __launch_bounds__(ATS_BQ) attention_simt_kernel(const float* __r
 // ------------------------------------------------------------------------------------------------
 constexpr int A2_BK = 64, A2_LD = 24 /*halfs per K / V row (16 + pad: conflict-free ldmatrix)*/, A2_RLD = 104 /*floats*/, A2_WROWS = 32;
 constexpr int A2_TILE_H = A2_BK * A2_LD;                                   // halfs per K (or V) tile
-constexpr int A2_SMEM = 2 * 2 * A2_TILE_H * 2 + 4 * A2_WROWS * A2_RLD * 4;   // double-buffered K,V + R staging
+constexpr int A2_STAGES = 3;
+constexpr int A2_SMEM = A2_STAGES * 2 * A2_TILE_H * 2 + 4 * A2_WROWS * A2_RLD * 4;   // K,V ring + R staging
 constexpr int AT_ROWH = 192;                                               // fp16 qkv row: q(64) | k(64) | v(64)
 
 __device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -140,9 +141,10 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_b
 __global__ void __launch_bounds__(128, 3) attention_f16_kernel(const __half* __restrict__ qkvh, const __half* __restrict__ Eh,
                                                               const SebSeq sq, int nqb, float* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smraw[];
-  __half* KV = reinterpret_cast<__half*>(smraw);                       // [buf 2][K | V][64][24]
+  __shared__ uint64_t full_bar[A2_STAGES], empty_bar[A2_STAGES];
+  __half* KV = reinterpret_cast<__half*>(smraw);                       // [stage][K | V][64][24]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  float* Rs = reinterpret_cast<float*>(KV + 4 * A2_TILE_H) + warp * A2_WROWS * A2_RLD;   // [32][104] per warp
+  float* Rs = reinterpret_cast<float*>(KV + A2_STAGES * 2 * A2_TILE_H) + warp * A2_WROWS * A2_RLD;   // [32][104] per warp
   const int sh = blockIdx.x / nqb, qb = blockIdx.x - sh * nqb;
   const int seq = sh >> 2, h = sh & 3;
   const int n = sq.n;
@@ -152,8 +154,16 @@ __global__ void __launch_bounds__(128, 3) attention_f16_kernel(const __half* __r
   const bool warp_live = iw < n;
 
   // K/V tile loader: 64 keys x (2 + 2) 16-byte chunks, 2 cp.async per thread; keys past the sequence are zero-filled
+  // The ring is mbarrier-driven (no CTA-wide barrier per tile): every thread's cp.asyncs arrive on full[stage] when they
+  // land, every warp arrives on empty[stage] when it has finished reading, so warps may drift apart by up to a tile.
+  if (tid == 0) {
+    for (int i = 0; i < A2_STAGES; ++i) { ptx::mbar_init(&full_bar[i], 128); ptx::mbar_init(&empty_bar[i], 4); }
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
   auto issue_tile = [&](int tile) {
-    __half* dstb = KV + (tile & 1) * 2 * A2_TILE_H;
+    const int stage = tile % A2_STAGES;
+    __half* dstb = KV + stage * 2 * A2_TILE_H;
 #pragma unroll
     for (int rep = 0; rep < 2; ++rep) {
       const int idx = tid + rep * 128, key = idx >> 2, c = idx & 3;
@@ -162,10 +172,11 @@ __global__ void __launch_bounds__(128, 3) attention_f16_kernel(const __half* __r
       const __half* src = hbase + (base + (long long)jj * sq.pos_stride) * AT_ROWH + 64 + (c >> 1) * 64 + (c & 1) * 8;
       cp_async16(dstb + (c >> 1) * A2_TILE_H + key * A2_LD + (c & 1) * 8, src, j < n ? 16 : 0);
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(ptx::smem_u32(&full_bar[stage])) : "memory");
   };
   const int ntiles = (n + A2_BK - 1) / A2_BK;
   issue_tile(0);
+  if (ntiles > 1) issue_tile(1);
 
   // Q fragments (already scaled by dim_head^-0.5 * log2(e) and rounded to fp16 by the projection epilogue)
   uint32_t qa[2][4];
@@ -196,13 +207,16 @@ __global__ void __launch_bounds__(128, 3) attention_f16_kernel(const __half* __r
   const int v_off = ((lm_i & 1) * 8 + lm_r) * A2_LD + (lm_i >> 1) * 8;        // V (transposed load): (key half, d half)
 
   for (int tile = 0; tile < ntiles; ++tile) {
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    __syncthreads();
-    if (tile + 1 < ntiles) issue_tile(tile + 1);
-    if (!warp_live) continue;
+    const int stage = tile % A2_STAGES;
+    if (tile + 2 < ntiles) {        // refill the stage that tile - 1 used, once all four warps have released it
+      if (tile >= 1) ptx::mbar_wait(&empty_bar[(tile + 2) % A2_STAGES], (uint32_t)((tile - 1) / A2_STAGES) & 1u);
+      issue_tile(tile + 2);
+    }
+    ptx::mbar_wait(&full_bar[stage], (uint32_t)(tile / A2_STAGES) & 1u);
     const int j0 = tile * A2_BK;
-    const __half* Ks = KV + (tile & 1) * 2 * A2_TILE_H;
+    const __half* Ks = KV + stage * 2 * A2_TILE_H;
     const __half* Vs = Ks + A2_TILE_H;
+    if (warp_live) {
 
     // ---- content scores: S[mt] = Q[mt] K^T  (16 x 64 each)
     float s[2][8][4];
@@ -240,7 +254,8 @@ __global__ void __launch_bounds__(128, 3) attention_f16_kernel(const __half* __r
       }
     }
     __syncwarp();
-    // ---- skew: S[r, c] += R[r, 64 + r - c]
+    // ---- skew: S[r, c] += R[r, 64 + r - c]  (initialising the accumulators from R instead was measured slower: it
+    //      puts the shared-memory round trip in front of the content MMAs)
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -295,6 +310,9 @@ __global__ void __launch_bounds__(128, 3) attention_f16_kernel(const __half* __r
         mma_f16(o[mt][2], pa, ones, ones);
       }
     }
+    }   // warp_live
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&empty_bar[stage]);
   }
   if (!warp_live) return;
 #pragma unroll

@@ -1,18 +1,24 @@
 // dwconv.cu -- DepthWiseConv1d(128, k=31, zero pad 15/15) + BatchNorm1d(eval, folded) + Swish along the sequence
 // axis (conformer.py:166-168).  One CTA = 64 positions x 128 channels of one sequence; thread = channel; the
 // (64+30) x 128 input tile is staged in shared memory (coalesced 512-byte rows), each thread produces 8 outputs per
-// pass from a 38-value register window (38 LDS per 248 FMA).
+// pass from a 38-row register window with packed fp32x2 FMAs (two channels per instruction).
 #include "common.cuh"
 
 namespace seb {
 
 constexpr int DW_TI = 64, DW_K = 31, DW_PAD = 15, DW_C = 128;
 
-__global__ void __launch_bounds__(128) dwconv_bn_swish_kernel(const float* __restrict__ x, const SebSeq sq,
-                                                             const float* __restrict__ w, const float* __restrict__ bn_scale,
-                                                             const float* __restrict__ bn_shift, float* __restrict__ y) {
-  __shared__ float tile[DW_TI + DW_K - 1][DW_C];
-  const int seq = blockIdx.x, i0 = blockIdx.y * DW_TI, c = threadIdx.x;
+// Thread = (channel pair, half of the 64 positions).  All arithmetic is packed fp32x2 (FFMA2, sm_100): two channels per
+// instruction.  Per group of 8 outputs the 38-row input window is consumed in two tap halves so that only 23 float2
+// of it are live next to the 31 float2 taps.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
+__global__ void __launch_bounds__(128, 3) dwconv_bn_swish_kernel(const float* __restrict__ x, const SebSeq sq,
+                                                                const float* __restrict__ w, const float* __restrict__ bn_scale,
+                                                                const float* __restrict__ bn_shift, float* __restrict__ y) {
+  __shared__ __align__(16) float tile[DW_TI + DW_K - 1][DW_C];
+  const int seq = blockIdx.x, i0 = blockIdx.y * DW_TI;
+  const int cp = threadIdx.x & 63, ph = threadIdx.x >> 6;
   const long long base = (long long)(seq / sq.inner) * sq.outer_stride + (seq % sq.inner);
   // stage rows i0-15 .. i0+64+15 (zero outside the sequence): 32 lanes x float4 cover one 512-byte row
   {
@@ -27,26 +33,44 @@ __global__ void __launch_bounds__(128) dwconv_bn_swish_kernel(const float* __res
       t4[idx] = v;
     }
   }
-  float wr[DW_K];
+  float2 wr[DW_K];
 #pragma unroll
-  for (int k = 0; k < DW_K; ++k) wr[k] = __ldg(w + k * DW_C + c);
-  const float sc = bn_scale[c], sh = bn_shift[c];
+  for (int k = 0; k < DW_K; ++k) wr[k] = __ldg(reinterpret_cast<const float2*>(w + k * DW_C) + cp);
+  const float2 sc = __ldg(reinterpret_cast<const float2*>(bn_scale) + cp), sh = __ldg(reinterpret_cast<const float2*>(bn_shift) + cp);
   __syncthreads();
+  const float2* t2 = reinterpret_cast<const float2*>(&tile[0][0]) + cp;      // row stride DW_C / 2 float2
 #pragma unroll 1
-  for (int g = 0; g < DW_TI; g += 8) {
-    if (i0 + g >= sq.n) break;
-    float win[8 + DW_K - 1];
+  for (int gi = 0; gi < 4; ++gi) {
+    const int gpos = ph * 32 + gi * 8;              // first output position of this group inside the tile
+    if (i0 + gpos >= sq.n) break;
+    float2 acc[8];
 #pragma unroll
-    for (int r = 0; r < 8 + DW_K - 1; ++r) win[r] = tile[g + r][c];
+    for (int o = 0; o < 8; ++o) acc[o] = make_float2(0.f, 0.f);
+    {   // taps 0..15 use window rows gpos .. gpos+22
+      float2 win[23];
+#pragma unroll
+      for (int r = 0; r < 23; ++r) win[r] = t2[(gpos + r) * (DW_C / 2)];
+#pragma unroll
+      for (int k = 0; k < 16; ++k)
+#pragma unroll
+        for (int o = 0; o < 8; ++o) acc[o] = ffma2(wr[k], win[o + k], acc[o]);
+    }
+    {   // taps 16..30 use window rows gpos+16 .. gpos+37
+      float2 win[22];
+#pragma unroll
+      for (int r = 0; r < 22; ++r) win[r] = t2[(gpos + 16 + r) * (DW_C / 2)];
+#pragma unroll
+      for (int k = 16; k < DW_K; ++k)
+#pragma unroll
+        for (int o = 0; o < 8; ++o) acc[o] = ffma2(wr[k], win[o + k - 16], acc[o]);
+    }
 #pragma unroll
     for (int o = 0; o < 8; ++o) {
-      float acc = 0.f;
-#pragma unroll
-      for (int k = 0; k < DW_K; ++k) acc = fmaf(wr[k], win[o + k], acc);
-      const int i = i0 + g + o;
+      const int i = i0 + gpos + o;
       if (i < sq.n) {
-        float v = fmaf(acc, sc, sh);
-        y[(base + (long long)i * sq.pos_stride) * DW_C + c] = v * sigmoidf_acc(v);
+        float2 v = ffma2(acc[o], sc, sh);
+        v.x *= sigmoidf_acc(v.x); v.y *= sigmoidf_acc(v.y);
+        *reinterpret_cast<float2*>(y + (base + (long long)i * sq.pos_stride) * DW_C + cp * 2) = v;
       }
     }
   }
