@@ -29,12 +29,12 @@ static int launch_simt(const SebGemm* s, const GemmArgs& g, cudaStream_t st) {
   return 0;
 }
 
-template <int NT, int STAGES, int LK, int EK>
+template <int NT, int STAGES, int LK, int EK, int PW = 8, int MINB = 2>
 static int launch_tc(const SebGemm* s, const GemmArgs& g, cudaStream_t st) {
   static bool attr_done = false;
   constexpr int SMEM = tc_smem_bytes<NT, STAGES>();
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<NT, STAGES, LK, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<NT, STAGES, LK, EK, PW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) { set_error("gemm tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     attr_done = true;
   }
@@ -42,7 +42,7 @@ static int launch_tc(const SebGemm* s, const GemmArgs& g, cudaStream_t st) {
               "gemm tc: weight image has n-tile %d x %d, kernel wants %d covering N=%d", s->tc_ntile, s->tc_ntiles, NT, s->N);
   SEB_REQUIRE(aligned16(s->w_tc), SEB_EALIGN, "gemm tc: weight image not 16-byte aligned");
   dim3 grid((g.M + BM - 1) / BM, s->tc_ntiles);
-  gemm_tc_kernel<NT, STAGES, LK, EK><<<grid, TC_THREADS, SMEM, st>>>(g, reinterpret_cast<const uint8_t*>(s->w_tc));
+  gemm_tc_kernel<NT, STAGES, LK, EK, PW, MINB><<<grid, (PW + 2) * 32, SMEM, st>>>(g, reinterpret_cast<const uint8_t*>(s->w_tc));
   SEB_CHECK_LAUNCH("gemm_tc_kernel");
   return 0;
 }
@@ -116,13 +116,17 @@ extern "C" int seb200_gemm(const SebGemm* s, int engine, void* stream) {
       case SEB_LOAD_CONV_SPLIT * 16 + SEB_EPI_SUBPIXEL: if (nt == 128) return launch_conv_split<128, 1, SEB_EPI_SUBPIXEL>(s, g, st); break;
       case SEB_LOAD_HANKEL * 16 + SEB_EPI_COMPRESS: if (nt == 208) return launch_tc<208, 1, SEB_LOAD_HANKEL, SEB_EPI_COMPRESS>(s, g, st); break;
       case SEB_LOAD_ROWS * 16 + SEB_EPI_BIAS:       if (nt == 208) return launch_tc<208, 1, SEB_LOAD_ROWS, SEB_EPI_BIAS>(s, g, st); break;
-      case SEB_LOAD_ROWS * 16 + SEB_EPI_RESID:      if (nt == 64)  return launch_tc<64, 2, SEB_LOAD_ROWS, SEB_EPI_RESID>(s, g, st); break;
+      case SEB_LOAD_ROWS * 16 + SEB_EPI_RESID:      if (nt == 64)  return (s->K <= 128) ? launch_tc<64, 1, SEB_LOAD_ROWS, SEB_EPI_RESID, 4, 4>(s, g, st)
+                                                                                      : launch_tc<64, 2, SEB_LOAD_ROWS, SEB_EPI_RESID>(s, g, st); break;
       case SEB_LOAD_CONV * 16 + SEB_EPI_BIAS:       if (nt == 64)  return launch_tc<64, 2, SEB_LOAD_CONV, SEB_EPI_BIAS>(s, g, st); break;
       case SEB_LOAD_CONV * 16 + SEB_EPI_SUBPIXEL:   if (nt == 128) return launch_tc<128, 1, SEB_LOAD_CONV, SEB_EPI_SUBPIXEL>(s, g, st); break;
       case SEB_LOAD_ROWS_LN * 16 + SEB_EPI_SWISH:   if (nt == 256) return launch_tc<256, 1, SEB_LOAD_ROWS_LN, SEB_EPI_SWISH>(s, g, st); break;
-      case SEB_LOAD_ROWS_LN * 16 + SEB_EPI_GLU:     if (nt == 256) return launch_tc<256, 1, SEB_LOAD_ROWS_LN, SEB_EPI_GLU>(s, g, st); break;
-      case SEB_LOAD_ROWS_LN * 16 + SEB_EPI_BIAS:    if (nt == 192) return launch_tc<192, 1, SEB_LOAD_ROWS_LN, SEB_EPI_BIAS>(s, g, st); break;
-      case SEB_LOAD_ROWS_LN * 16 + SEB_EPI_QKV_F16: if (nt == 192) return launch_tc<192, 1, SEB_LOAD_ROWS_LN, SEB_EPI_QKV_F16>(s, g, st); break;
+      case SEB_LOAD_ROWS_LN * 16 + SEB_EPI_GLU:     if (nt == 256) return launch_tc<256, 1, SEB_LOAD_ROWS_LN, SEB_EPI_GLU>(s, g, st);
+                                                    if (nt == 64)  return launch_tc<64, 1, SEB_LOAD_ROWS_LN, SEB_EPI_GLU, 4, 4>(s, g, st); break;
+      case SEB_LOAD_ROWS_LN * 16 + SEB_EPI_BIAS:    if (nt == 192) return launch_tc<192, 1, SEB_LOAD_ROWS_LN, SEB_EPI_BIAS>(s, g, st);
+                                                    if (nt == 64)  return launch_tc<64, 1, SEB_LOAD_ROWS_LN, SEB_EPI_BIAS, 4, 4>(s, g, st); break;
+      case SEB_LOAD_ROWS_LN * 16 + SEB_EPI_QKV_F16: if (nt == 192) return launch_tc<192, 1, SEB_LOAD_ROWS_LN, SEB_EPI_QKV_F16>(s, g, st);
+                                                    if (nt == 64)  return launch_tc<64, 1, SEB_LOAD_ROWS_LN, SEB_EPI_QKV_F16, 4, 4>(s, g, st); break;
       default: break;
     }
   }

@@ -370,16 +370,20 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 }
 }  // namespace ptx
 
-constexpr int TC_THREADS = 320;        // 8 producer/epilogue warps + MMA warp + weight-copy warp
+constexpr int TC_THREADS = 320;        // default shape: 8 producer/epilogue warps + MMA warp + weight-copy warp
 constexpr int TC_A_BYTES = BM * 128;   // one bf16 plane of the A tile
 
 template <int NT> constexpr int tc_stage_bytes() { return 2 * TC_A_BYTES + 2 * NT * 128; }
 template <int NT, int STAGES> constexpr int tc_smem_bytes() { return STAGES * tc_stage_bytes<NT>() + 1024; }
 template <int NT> constexpr uint32_t tc_tmem_cols() { return NT <= 32 ? 32 : NT <= 64 ? 64 : NT <= 128 ? 128 : 256; }
 
-template <int NT, int STAGES, int LK, int EK>
-__global__ void __launch_bounds__(TC_THREADS, 2)
+// PW = producer/epilogue warps (8 or 4), MINB = CTAs per SM the register budget is sized for.  The K = 64 / 128 token
+// GEMMs are bandwidth/latency bound: they run as PW = 4, one stage, n-tile 64 -> 49 KB smem, 64 TMEM columns and
+// 192 threads per CTA, i.e. 4 resident CTAs per SM keep four tiles' loads in flight.
+template <int NT, int STAGES, int LK, int EK, int PW = 8, int MINB = 2>
+__global__ void __launch_bounds__((PW + 2) * 32, MINB)
 gemm_tc_kernel(const GemmArgs g, const uint8_t* __restrict__ w_tc) {
+  static_assert(PW == 4 || PW == 8, "producer warps must cover the four TMEM lane quarters once or twice");
   static_assert(NT % 16 == 0 && NT >= 16 && NT <= 256, "UMMA M=128 needs N % 16 == 0, N <= 256");
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
@@ -396,22 +400,23 @@ gemm_tc_kernel(const GemmArgs g, const uint8_t* __restrict__ w_tc) {
   const int nkc = g.K / BK;
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 256 + 1); ptx::mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], PW * 32 + 1); ptx::mbar_init(&empty_bar[s], 1); }
     ptx::mbar_init(&accum_bar, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 8) ptx::tmem_alloc(&tmem_base_s, TMEM_COLS);
+  if (warp == PW) ptx::tmem_alloc(&tmem_base_s, TMEM_COLS);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  if (warp < 8) {
+  if (warp < PW) {
     // ---------------- producers: fp32 global -> bf16 hi/lo swizzled shared ----------------
     const int sub = tid & 7, rloc = tid >> 3;
-    typename Loader<LK>::Row rows[4];
+    constexpr int RPP = PW * 4, NPASS = BM / RPP;      // rows per pass, passes per tile
+    typename Loader<LK>::Row rows[NPASS];
 #pragma unroll
-    for (int p = 0; p < 4; ++p) Loader<LK>::init_row(g, m0 + p * 32 + rloc, rows[p]);
+    for (int p = 0; p < NPASS; ++p) Loader<LK>::init_row(g, m0 + p * RPP + rloc, rows[p]);
     for (int kc = 0; kc < nkc; ++kc) {
       const int s = kc % STAGES;
       const uint32_t ph = (uint32_t)(kc / STAGES) & 1u;
@@ -419,7 +424,7 @@ gemm_tc_kernel(const GemmArgs g, const uint8_t* __restrict__ w_tc) {
       uint8_t* a_hi = smem + s * STAGE;
       uint8_t* a_lo = a_hi + TC_A_BYTES;
 #pragma unroll
-      for (int p = 0; p < 4; ++p) {
+      for (int p = 0; p < NPASS; ++p) {
         float v[8];
         Loader<LK>::load(g, rows[p], kc, sub, v);
         uint4 hi, lo;
@@ -427,7 +432,7 @@ gemm_tc_kernel(const GemmArgs g, const uint8_t* __restrict__ w_tc) {
         split_bf16x2(v[2], v[3], hi.y, lo.y);
         split_bf16x2(v[4], v[5], hi.z, lo.z);
         split_bf16x2(v[6], v[7], hi.w, lo.w);
-        const int r = p * 32 + rloc;
+        const int r = p * RPP + rloc;
         const int off = r * 128 + ((sub ^ (r & 7)) << 4);
         *reinterpret_cast<uint4*>(a_hi + off) = hi;
         *reinterpret_cast<uint4*>(a_lo + off) = lo;
@@ -443,7 +448,7 @@ gemm_tc_kernel(const GemmArgs g, const uint8_t* __restrict__ w_tc) {
     ptx::mbar_wait(&accum_bar, 0);
     ptx::tc_fence_after();
     const int wq = warp & 3, half = warp >> 2;
-    constexpr int HALF_COLS = NT / 2;            // multiple of 8
+    constexpr int HALF_COLS = NT / (PW / 4);     // columns per epilogue warp; multiple of 8
     const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(half * HALF_COLS);
     float4* stg = reinterpret_cast<float4*>(smem + warp * 4096);    // [32 rows][8 x float4]
 #pragma unroll 1
@@ -471,7 +476,7 @@ gemm_tc_kernel(const GemmArgs g, const uint8_t* __restrict__ w_tc) {
       __syncwarp();
     }
     ptx::tc_fence_before();
-  } else if (warp == 8) {
+  } else if (warp == PW) {
     // ---------------- MMA issuer (one thread) ----------------
     if (lane == 0) {
       constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -510,7 +515,7 @@ gemm_tc_kernel(const GemmArgs g, const uint8_t* __restrict__ w_tc) {
     }
   }
   __syncthreads();
-  if (warp == 8) {
+  if (warp == PW) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, TMEM_COLS);
   }

@@ -55,20 +55,25 @@ def test_gemm_layernorm_loader_epilogues(engine):
     assert rel_max(out, h * torch.sigmoid(h)) < TOL[engine]
     # pointwise conv 64 -> 256 + GLU (interleaved packing)
     wi, bi = packing.glu_interleave(w.cpu(), b.cpu())
-    out = torch.empty(M, 128, device=DEV)
-    ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_GLU, M=M, w=packing.pack_weight(wi, 256, bi).to(DEV), a=[x], lda=64, ln=(g, be), out=out, ldo=128, engine=engine)
-    assert rel_max(out, h[:, :128] * torch.sigmoid(h[:, 128:])) < TOL[engine]
+    for ntile in (256, 64):           # 64: the 4-CTA-per-SM shape the model uses
+        out = torch.empty(M, 128, device=DEV)
+        ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_GLU, M=M, w=packing.pack_weight(wi, ntile, bi).to(DEV), a=[x], lda=64, ln=(g, be), out=out, ldo=128, engine=engine)
+        assert rel_max(out, h[:, :128] * torch.sigmoid(h[:, 128:])) < TOL[engine]
     # q | k | v projection, no bias
     wq = rnd(192, 64, seed=10, scale=0.17)
     out = torch.empty(M, 192, device=DEV)
     ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_BIAS, M=M, w=packing.pack_weight(wq.cpu(), 192, None).to(DEV), a=[x], lda=64, ln=(g, be), out=out, ldo=192, engine=engine)
     assert rel_max(out, xn @ wq.double().t()) < TOL[engine]
     # the same projection in the fp16 layout the tensor-core attention reads (q pre-scaled)
-    outh = torch.empty(M, 192, device=DEV, dtype=torch.float16)
-    ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_QKV_F16, M=M, w=packing.pack_weight(wq.cpu(), 192, None).to(DEV), a=[x], lda=64, ln=(g, be), out=outh, ldo=192, engine=engine)
     refh = xn @ wq.double().t()
     refh[:, :64] *= 0.25 * 1.4426950408889634
-    assert rel_max(outh.double(), refh) < 1e-3
+    for ntile in (192, 64):
+        outh = torch.empty(M, 192, device=DEV, dtype=torch.float16)
+        ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_QKV_F16, M=M, w=packing.pack_weight(wq.cpu(), ntile, None).to(DEV), a=[x], lda=64, ln=(g, be), out=outh, ldo=192, engine=engine)
+        assert rel_max(outh.double(), refh) < 1e-3
+    out = torch.empty(M, 192, device=DEV)
+    ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_BIAS, M=M, w=packing.pack_weight(wq.cpu(), 64, None).to(DEV), a=[x], lda=64, ln=(g, be), out=out, ldo=192, engine=engine)
+    assert rel_max(out, xn @ wq.double().t()) < TOL[engine]
 
 
 @pytest.mark.parametrize("M", [128, 777, 40000])
