@@ -65,9 +65,10 @@ typedef struct SebGemm {
   int B, T, Fin, Fout;      /* CONV geometry: M = B*T*Fout output pixels; HANKEL: M = B*T, hop 100 */
   int taps_t, dil, stride_f, nslots; /* CONV: kernel (taps_t, 3), dilation (dil, 1), stride (1, stride_f), pad (dil*(taps_t-1) top, 1 left/right) */
   /* W operand (see seb200 packing.py / DESIGN.md for the image layouts) */
-  const void* w_tc;         /* tcgen05 image: per (n-tile, k-chunk) bf16 hi|lo, 128B-swizzled K-major */
+  const void* w_tc;         /* tcgen05 image: per (n-tile, k-chunk) bf16 planes hi|lo (or hi|mid|lo), 128B-swizzled K-major */
   int tc_ntile;             /* rows per n-tile in w_tc (16..256, multiple of 16) */
   int tc_ntiles;
+  int tc_planes;            /* 2: hi+lo, 3 products (network GEMMs); 3: hi+mid+lo, 6 products (DFT / iDFT: fp32-grade) */
   const float* w_simt;      /* fp32 [K][simt_npad] (K-major rows)               */
   int simt_npad;            /* multiple of 64                                   */
   const float* bias;        /* [N] or NULL */

@@ -29,7 +29,7 @@ class SebGemm(C.Structure):
         ("ln_gamma", _fp), ("ln_beta", _fp),
         ("B", C.c_int), ("T", C.c_int), ("Fin", C.c_int), ("Fout", C.c_int),
         ("taps_t", C.c_int), ("dil", C.c_int), ("stride_f", C.c_int), ("nslots", C.c_int),
-        ("w_tc", _fp), ("tc_ntile", C.c_int), ("tc_ntiles", C.c_int),
+        ("w_tc", _fp), ("tc_ntile", C.c_int), ("tc_ntiles", C.c_int), ("tc_planes", C.c_int),
         ("w_simt", _fp), ("simt_npad", C.c_int),
         ("bias", _fp),
         ("out", _fp), ("ldo", C.c_longlong),

@@ -61,4 +61,17 @@ __device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, u
   lo = *reinterpret_cast<uint32_t*>(&l);
 }
 
+// fp32 -> (hi, mid, lo) bf16 triple: hi + mid + lo == x to ~2^-24 relative
+__device__ __forceinline__ void split3_bf16x2(float x0, float x1, uint32_t& hi, uint32_t& mid, uint32_t& lo) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+  float2 hf = __bfloat1622float2(h);
+  const float r0 = x0 - hf.x, r1 = x1 - hf.y;
+  __nv_bfloat162 m = __floats2bfloat162_rn(r0, r1);
+  float2 mf = __bfloat1622float2(m);
+  __nv_bfloat162 l = __floats2bfloat162_rn(r0 - mf.x, r1 - mf.y);
+  hi = *reinterpret_cast<uint32_t*>(&h);
+  mid = *reinterpret_cast<uint32_t*>(&m);
+  lo = *reinterpret_cast<uint32_t*>(&l);
+}
+
 }  // namespace seb

@@ -29,12 +29,13 @@ static int launch_simt(const SebGemm* s, const GemmArgs& g, cudaStream_t st) {
   return 0;
 }
 
-template <int NT, int STAGES, int LK, int EK, int PW = 8, int MINB = 2>
+template <int NT, int STAGES, int LK, int EK, int PW = 8, int MINB = 2, int NPL = 2>
 static int launch_tc(const SebGemm* s, const GemmArgs& g, cudaStream_t st) {
   static bool attr_done = false;
-  constexpr int SMEM = tc_smem_bytes<NT, STAGES>();
+  constexpr int SMEM = tc_smem_bytes<NT, STAGES, NPL>();
+  SEB_REQUIRE(s->tc_planes == NPL, SEB_EINVAL, "gemm tc: weight image has %d planes, kernel wants %d", s->tc_planes, NPL);
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<NT, STAGES, LK, EK, PW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<NT, STAGES, LK, EK, PW, MINB, NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) { set_error("gemm tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     attr_done = true;
   }
@@ -42,7 +43,7 @@ static int launch_tc(const SebGemm* s, const GemmArgs& g, cudaStream_t st) {
               "gemm tc: weight image has n-tile %d x %d, kernel wants %d covering N=%d", s->tc_ntile, s->tc_ntiles, NT, s->N);
   SEB_REQUIRE(aligned16(s->w_tc), SEB_EALIGN, "gemm tc: weight image not 16-byte aligned");
   dim3 grid((g.M + BM - 1) / BM, s->tc_ntiles);
-  gemm_tc_kernel<NT, STAGES, LK, EK, PW, MINB><<<grid, (PW + 2) * 32, SMEM, st>>>(g, reinterpret_cast<const uint8_t*>(s->w_tc));
+  gemm_tc_kernel<NT, STAGES, LK, EK, PW, MINB, NPL><<<grid, (PW + 2) * 32, SMEM, st>>>(g, reinterpret_cast<const uint8_t*>(s->w_tc));
   SEB_CHECK_LAUNCH("gemm_tc_kernel");
   return 0;
 }
@@ -59,6 +60,7 @@ static int launch_conv_split(const SebGemm* s, const GemmArgs& g, cudaStream_t s
   SEB_REQUIRE(s->w_tc && s->tc_ntile == NT && s->tc_ntiles >= 1 && s->tc_ntile * s->tc_ntiles >= s->N && aligned16(s->w_tc), SEB_EINVAL,
               "conv split: weight image has n-tile %d x %d, kernel wants %d covering N=%d", s->tc_ntile, s->tc_ntiles, NT, s->N);
   SEB_REQUIRE(s->T < 32768 && s->Fout < 65536, SEB_EINVAL, "conv split: T/F too large for the packed row index");
+  SEB_REQUIRE(s->tc_planes == 2, SEB_EINVAL, "conv split: weight image must have 2 planes");
   dim3 grid((g.M + BM - 1) / BM, s->tc_ntiles);
   conv_split_tc_kernel<NT, STAGES, EK><<<grid, TC_THREADS, SMEM, st>>>(g, reinterpret_cast<const uint8_t*>(s->w_tc));
   SEB_CHECK_LAUNCH("conv_split_tc_kernel");
@@ -114,8 +116,10 @@ extern "C" int seb200_gemm(const SebGemm* s, int engine, void* stream) {
     switch (key) {
       case SEB_LOAD_CONV_SPLIT * 16 + SEB_EPI_BIAS:     if (nt == 64)  return launch_conv_split<64, 2, SEB_EPI_BIAS>(s, g, st); break;
       case SEB_LOAD_CONV_SPLIT * 16 + SEB_EPI_SUBPIXEL: if (nt == 128) return launch_conv_split<128, 1, SEB_EPI_SUBPIXEL>(s, g, st); break;
-      case SEB_LOAD_HANKEL * 16 + SEB_EPI_COMPRESS: if (nt == 208) return launch_tc<208, 1, SEB_LOAD_HANKEL, SEB_EPI_COMPRESS>(s, g, st); break;
-      case SEB_LOAD_ROWS * 16 + SEB_EPI_BIAS:       if (nt == 208) return launch_tc<208, 1, SEB_LOAD_ROWS, SEB_EPI_BIAS>(s, g, st); break;
+      case SEB_LOAD_HANKEL * 16 + SEB_EPI_COMPRESS: if (nt == 208) return (s->tc_planes == 3) ? launch_tc<208, 1, SEB_LOAD_HANKEL, SEB_EPI_COMPRESS, 8, 1, 3>(s, g, st)
+                                                                                             : launch_tc<208, 1, SEB_LOAD_HANKEL, SEB_EPI_COMPRESS>(s, g, st); break;
+      case SEB_LOAD_ROWS * 16 + SEB_EPI_BIAS:       if (nt == 208) return (s->tc_planes == 3) ? launch_tc<208, 1, SEB_LOAD_ROWS, SEB_EPI_BIAS, 8, 1, 3>(s, g, st)
+                                                                                             : launch_tc<208, 1, SEB_LOAD_ROWS, SEB_EPI_BIAS>(s, g, st); break;
       case SEB_LOAD_ROWS * 16 + SEB_EPI_RESID:      if (nt == 64)  return (s->K <= 128) ? launch_tc<64, 1, SEB_LOAD_ROWS, SEB_EPI_RESID, 4, 4>(s, g, st)
                                                                                       : launch_tc<64, 2, SEB_LOAD_ROWS, SEB_EPI_RESID>(s, g, st); break;
       case SEB_LOAD_CONV * 16 + SEB_EPI_BIAS:       if (nt == 64)  return launch_tc<64, 2, SEB_LOAD_CONV, SEB_EPI_BIAS>(s, g, st); break;

@@ -373,24 +373,28 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 constexpr int TC_THREADS = 320;        // default shape: 8 producer/epilogue warps + MMA warp + weight-copy warp
 constexpr int TC_A_BYTES = BM * 128;   // one bf16 plane of the A tile
 
-template <int NT> constexpr int tc_stage_bytes() { return 2 * TC_A_BYTES + 2 * NT * 128; }
-template <int NT, int STAGES> constexpr int tc_smem_bytes() { return STAGES * tc_stage_bytes<NT>() + 1024; }
+template <int NT, int NPL = 2> constexpr int tc_stage_bytes() { return NPL * TC_A_BYTES + NPL * NT * 128; }
+template <int NT, int STAGES, int NPL = 2> constexpr int tc_smem_bytes() { return STAGES * tc_stage_bytes<NT, NPL>() + 1024; }
 template <int NT> constexpr uint32_t tc_tmem_cols() { return NT <= 32 ? 32 : NT <= 64 ? 64 : NT <= 128 ? 128 : 256; }
 
 // PW = producer/epilogue warps (8 or 4), MINB = CTAs per SM the register budget is sized for.  The K = 64 / 128 token
 // GEMMs are bandwidth/latency bound: they run as PW = 4, one stage, n-tile 64 -> 49 KB smem, 64 TMEM columns and
 // 192 threads per CTA, i.e. 4 resident CTAs per SM keep four tiles' loads in flight.
-template <int NT, int STAGES, int LK, int EK, int PW = 8, int MINB = 2>
+// NPL = operand planes.  2: x = hi + lo, products hi*hi + hi*lo + lo*hi (network GEMMs, ~2^-17 operand error).
+// 3: x = hi + mid + lo, six products (all terms down to 2^-24): fp32-grade accuracy on the tensor pipe, used for the
+// DFT / iDFT, where |X|^0.3 amplifies operand rounding on near-zero bins.
+template <int NT, int STAGES, int LK, int EK, int PW = 8, int MINB = 2, int NPL = 2>
 __global__ void __launch_bounds__((PW + 2) * 32, MINB)
 gemm_tc_kernel(const GemmArgs g, const uint8_t* __restrict__ w_tc) {
   static_assert(PW == 4 || PW == 8, "producer warps must cover the four TMEM lane quarters once or twice");
+  static_assert(NPL == 2 || NPL == 3, "two or three bf16 planes per operand");
   static_assert(NT % 16 == 0 && NT >= 16 && NT <= 256, "UMMA M=128 needs N % 16 == 0, N <= 256");
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
   __shared__ uint32_t tmem_base_s;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t smem_base = ptx::smem_u32(smem);
-  constexpr int STAGE = tc_stage_bytes<NT>();
+  constexpr int STAGE = tc_stage_bytes<NT, NPL>();
   constexpr uint32_t W_BYTES = NT * 128;
   constexpr uint32_t TMEM_COLS = tc_tmem_cols<NT>();
 
@@ -422,18 +426,27 @@ gemm_tc_kernel(const GemmArgs g, const uint8_t* __restrict__ w_tc) {
       const uint32_t ph = (uint32_t)(kc / STAGES) & 1u;
       ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
       uint8_t* a_hi = smem + s * STAGE;
-      uint8_t* a_lo = a_hi + TC_A_BYTES;
+      uint8_t* a_lo = a_hi + (NPL - 1) * TC_A_BYTES;      // planes: hi | (mid |) lo
 #pragma unroll
       for (int p = 0; p < NPASS; ++p) {
         float v[8];
         Loader<LK>::load(g, rows[p], kc, sub, v);
-        uint4 hi, lo;
-        split_bf16x2(v[0], v[1], hi.x, lo.x);
-        split_bf16x2(v[2], v[3], hi.y, lo.y);
-        split_bf16x2(v[4], v[5], hi.z, lo.z);
-        split_bf16x2(v[6], v[7], hi.w, lo.w);
         const int r = p * RPP + rloc;
         const int off = r * 128 + ((sub ^ (r & 7)) << 4);
+        uint4 hi, lo;
+        if (NPL == 2) {
+          split_bf16x2(v[0], v[1], hi.x, lo.x);
+          split_bf16x2(v[2], v[3], hi.y, lo.y);
+          split_bf16x2(v[4], v[5], hi.z, lo.z);
+          split_bf16x2(v[6], v[7], hi.w, lo.w);
+        } else {
+          uint4 mid;
+          split3_bf16x2(v[0], v[1], hi.x, mid.x, lo.x);
+          split3_bf16x2(v[2], v[3], hi.y, mid.y, lo.y);
+          split3_bf16x2(v[4], v[5], hi.z, mid.z, lo.z);
+          split3_bf16x2(v[6], v[7], hi.w, mid.w, lo.w);
+          *reinterpret_cast<uint4*>(a_hi + TC_A_BYTES + off) = mid;
+        }
         *reinterpret_cast<uint4*>(a_hi + off) = hi;
         *reinterpret_cast<uint4*>(a_lo + off) = lo;
       }
@@ -487,14 +500,21 @@ gemm_tc_kernel(const GemmArgs g, const uint8_t* __restrict__ w_tc) {
         ptx::tc_fence_after();
         const uint32_t base = smem_base + s * STAGE;
         const uint64_t a_hi = ptx::umma_desc_sw128(base);
-        const uint64_t a_lo = ptx::umma_desc_sw128(base + TC_A_BYTES);
-        const uint64_t w_hi = ptx::umma_desc_sw128(base + 2 * TC_A_BYTES);
-        const uint64_t w_lo = ptx::umma_desc_sw128(base + 2 * TC_A_BYTES + W_BYTES);
+        const uint64_t a_lo = ptx::umma_desc_sw128(base + (NPL - 1) * TC_A_BYTES);
+        const uint64_t w_hi = ptx::umma_desc_sw128(base + NPL * TC_A_BYTES);
+        const uint64_t w_lo = ptx::umma_desc_sw128(base + NPL * TC_A_BYTES + (NPL - 1) * W_BYTES);
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
           const uint64_t ko = (uint64_t)((k * 32) >> 4);   // 16 bf16 = 32 bytes along K inside the swizzle row
-          ptx::mma_bf16(tmem_base, a_lo + ko, w_hi + ko, IDESC, (kc | k) ? 1u : 0u);
+          ptx::mma_bf16(tmem_base, a_lo + ko, w_hi + ko, IDESC, (kc | k) ? 1u : 0u);      // smallest terms first
           ptx::mma_bf16(tmem_base, a_hi + ko, w_lo + ko, IDESC, 1u);
+          if (NPL == 3) {
+            const uint64_t a_mid = ptx::umma_desc_sw128(base + TC_A_BYTES);
+            const uint64_t w_mid = ptx::umma_desc_sw128(base + NPL * TC_A_BYTES + W_BYTES);
+            ptx::mma_bf16(tmem_base, a_mid + ko, w_mid + ko, IDESC, 1u);
+            ptx::mma_bf16(tmem_base, a_mid + ko, w_hi + ko, IDESC, 1u);
+            ptx::mma_bf16(tmem_base, a_hi + ko, w_mid + ko, IDESC, 1u);
+          }
           ptx::mma_bf16(tmem_base, a_hi + ko, w_hi + ko, IDESC, 1u);
         }
         ptx::tc_commit(&empty_bar[s]);
@@ -504,13 +524,13 @@ gemm_tc_kernel(const GemmArgs g, const uint8_t* __restrict__ w_tc) {
   } else {
     // ---------------- weight stager: one bulk copy (hi|lo image) per stage ----------------
     if (lane == 0) {
-      const uint8_t* src = w_tc + (size_t)ntile * nkc * (2 * W_BYTES);
+      const uint8_t* src = w_tc + (size_t)ntile * nkc * (NPL * W_BYTES);
       for (int kc = 0; kc < nkc; ++kc) {
         const int s = kc % STAGES;
         const uint32_t ph = (uint32_t)(kc / STAGES) & 1u;
         ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
-        ptx::mbar_arrive_expect_tx(&full_bar[s], 2 * W_BYTES);
-        ptx::bulk_g2s(smem_base + s * STAGE + 2 * TC_A_BYTES, src + (size_t)kc * (2 * W_BYTES), 2 * W_BYTES, &full_bar[s]);
+        ptx::mbar_arrive_expect_tx(&full_bar[s], NPL * W_BYTES);
+        ptx::bulk_g2s(smem_base + s * STAGE + NPL * TC_A_BYTES, src + (size_t)kc * (NPL * W_BYTES), NPL * W_BYTES, &full_bar[s]);
       }
     }
   }

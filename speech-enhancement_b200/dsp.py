@@ -19,7 +19,7 @@ from ._lib import EPI_BIAS, EPI_COMPRESS, LOAD_HANKEL, LOAD_ROWS, require_cuda
 from .packing import dft_basis, hamming_periodic, idft_basis, inv_envelope, pack_weight
 
 N_FFT, HOP, N_BINS, LDZ = 400, 100, 201, 448
-DFT_ENGINE = "simt"      # fp32 main loop for the DFTs (see enhancer.py); "tcgen05" selects the split-bf16 tensor path
+DFT_ENGINE = "tcgen05"   # DFT / iDFT on tcgen05 with three bf16 planes per operand (six products, fp32-grade); "simt" = fp32 FFMA loop
 
 _cache: Dict[tuple, object] = {}
 
@@ -27,7 +27,7 @@ _cache: Dict[tuple, object] = {}
 def _bases(device):
     key = ("bases", str(device))
     if key not in _cache:
-        _cache[key] = (pack_weight(dft_basis(N_FFT), 208).to(device), pack_weight(idft_basis(N_FFT), 208).to(device))
+        _cache[key] = (pack_weight(dft_basis(N_FFT), 208, planes=3).to(device), pack_weight(idft_basis(N_FFT), 208, planes=3).to(device))
     return _cache[key]
 
 

@@ -124,7 +124,7 @@ def gemm(*, loader: int, epilogue: int, M: int, w: PackedWeight, a: Sequence[tor
     if conv is not None:
         g.B, g.T, g.Fin, g.Fout = conv["B"], conv["T"], conv["Fin"], conv["Fout"]
         g.taps_t, g.dil, g.stride_f, g.nslots = conv.get("taps_t", 1), conv.get("dil", 1), conv.get("stride_f", 1), conv.get("nslots", 1)
-    g.w_tc, g.tc_ntile, g.tc_ntiles = ptr(w.w_tc), w.tc_ntile, w.tc_ntiles
+    g.w_tc, g.tc_ntile, g.tc_ntiles, g.tc_planes = ptr(w.w_tc), w.tc_ntile, w.tc_ntiles, w.planes
     g.w_simt, g.simt_npad = ptr(w.w_simt), w.simt_npad
     g.bias = ptr(w.bias)
     g.out, g.ldo = ptr(out), ldo

@@ -35,11 +35,12 @@ class PackedWeight:
     w_tc: torch.Tensor     # uint8
     w_simt: torch.Tensor   # float32 [K][simt_npad]
     bias: Optional[torch.Tensor]
+    planes: int = 2        # bf16 planes per operand in w_tc: 2 (hi|lo) or 3 (hi|mid|lo)
 
     def to(self, device):
         return PackedWeight(self.N, self.K, self.tc_ntile, self.tc_ntiles, self.simt_npad,
                             self.w_tc.to(device), self.w_simt.to(device),
-                            None if self.bias is None else self.bias.to(device))
+                            None if self.bias is None else self.bias.to(device), self.planes)
 
 
 def split_bf16(w: torch.Tensor):
@@ -58,8 +59,16 @@ def swizzle128(block: torch.Tensor) -> torch.Tensor:
     return torch.gather(b, 1, src.view(rows, 8, 1).expand(rows, 8, 8)).reshape(rows, 64)
 
 
-def pack_weight(w: torch.Tensor, tc_ntile: int, bias: Optional[torch.Tensor] = None) -> PackedWeight:
-    """w: [N, K] fp32 (CPU)."""
+def split_bf16_3(w: torch.Tensor):
+    hi = w.to(torch.bfloat16)
+    r = w - hi.to(torch.float32)
+    mid = r.to(torch.bfloat16)
+    lo = (r - mid.to(torch.float32)).to(torch.bfloat16)
+    return hi, mid, lo
+
+
+def pack_weight(w: torch.Tensor, tc_ntile: int, bias: Optional[torch.Tensor] = None, planes: int = 2) -> PackedWeight:
+    """w: [N, K] fp32 (CPU).  planes = 3 packs hi|mid|lo (six-product mode of the engine, used by the DFT bases)."""
     w = w.detach().to(torch.float32).cpu().contiguous()
     N, K = w.shape
     kp = int(math.ceil(K / BK)) * BK
@@ -67,20 +76,20 @@ def pack_weight(w: torch.Tensor, tc_ntile: int, bias: Optional[torch.Tensor] = N
     npad_tc = ntiles * tc_ntile
     wp = torch.zeros(npad_tc, kp, dtype=torch.float32)
     wp[:N, :K] = w
-    hi, lo = split_bf16(wp)
+    parts = split_bf16(wp) if planes == 2 else split_bf16_3(wp)
     nkc = kp // BK
-    img = torch.empty(ntiles, nkc, 2, tc_ntile, BK, dtype=torch.bfloat16)
+    img = torch.empty(ntiles, nkc, planes, tc_ntile, BK, dtype=torch.bfloat16)
     for j in range(ntiles):
         for kc in range(nkc):
             sl = (slice(j * tc_ntile, (j + 1) * tc_ntile), slice(kc * BK, (kc + 1) * BK))
-            img[j, kc, 0] = swizzle128(hi[sl])
-            img[j, kc, 1] = swizzle128(lo[sl])
+            for pi, part in enumerate(parts):
+                img[j, kc, pi] = swizzle128(part[sl])
     w_tc = img.contiguous().view(torch.uint8).reshape(-1)
     npad = int(math.ceil(N / 64)) * 64
     w_simt = torch.zeros(kp, npad, dtype=torch.float32)
     w_simt[:K, :N] = w.t()
     b = None if bias is None else bias.detach().to(torch.float32).cpu().contiguous()
-    return PackedWeight(N, kp, tc_ntile, ntiles, npad, w_tc, w_simt.contiguous(), b)
+    return PackedWeight(N, kp, tc_ntile, ntiles, npad, w_tc, w_simt.contiguous(), b, planes)
 
 
 def conv_weight_matrix(w: torch.Tensor) -> torch.Tensor:

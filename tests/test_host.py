@@ -86,6 +86,21 @@ def test_split_bf16_three_product_error_model():
     assert rel_max(f(ah, bh), exact) > 1e-3             # single-pass bf16 is not enough
 
 
+def test_three_plane_split_is_fp32_grade():
+    """six products of (hi, mid, lo) planes: the DFT mode of the tensor path reproduces an fp32 GEMM"""
+    g = torch.Generator().manual_seed(5)
+    a, b = torch.randn(128, 448, generator=g), torch.randn(96, 448, generator=g)
+    ah, am, al = packing.split_bf16_3(a)
+    bh, bm, bl = packing.split_bf16_3(b)
+    assert rel_max(ah.float() + am.float() + al.float(), a) < 2.0 ** -22
+    f = lambda x, y: x.float() @ y.float().t()
+    approx = f(al, bh) + f(ah, bl) + f(am, bm) + f(am, bh) + f(ah, bm) + f(ah, bh)
+    exact = (a.double() @ b.double().t()).float()
+    assert rel_max(approx, exact) < 2e-6
+    pw = packing.pack_weight(b, 48, planes=3)
+    assert pw.planes == 3 and pw.w_tc.numel() == 2 * 7 * 3 * 48 * 64 * 2
+
+
 def test_dft_bases_match_torch_fft():
     x = torch.randn(3, 400, generator=torch.Generator().manual_seed(2))
     w = O.hamming_periodic()
