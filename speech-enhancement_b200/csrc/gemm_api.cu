@@ -1,7 +1,13 @@
 // gemm_api.cu -- seb200_gemm: argument checking and dispatch onto the instantiated engine kernels.
 #include "gemm_engine.cuh"
+#include <stdlib.h>
 
 namespace seb {
+
+int launch_conv_tap(const SebGemm* s, const GemmArgs& g, cudaStream_t st);       // conv_tap.cu (experimental)
+bool conv_tap_enabled();
+int launch_conv_persist(const SebGemm* s, const GemmArgs& g, cudaStream_t st);   // conv_persist.cu
+int conv_persist_max_chunks();
 
 static GemmArgs to_args(const SebGemm* s) {
   GemmArgs g;
@@ -59,12 +65,19 @@ static int launch_conv_split(const SebGemm* s, const GemmArgs& g, cudaStream_t s
   }
   SEB_REQUIRE(s->w_tc && s->tc_ntile == NT && s->tc_ntiles >= 1 && s->tc_ntile * s->tc_ntiles >= s->N && aligned16(s->w_tc), SEB_EINVAL,
               "conv split: weight image has n-tile %d x %d, kernel wants %d covering N=%d", s->tc_ntile, s->tc_ntiles, NT, s->N);
-  SEB_REQUIRE(s->T < 32768 && s->Fout < 65536, SEB_EINVAL, "conv split: T/F too large for the packed row index");
+  SEB_REQUIRE(s->T < 32768 && s->Fout < 65536 && (long long)s->B * s->T * s->Fin < 2147483647LL, SEB_EINVAL, "conv split: T/F/pixel count too large for the packed row index");
   SEB_REQUIRE(s->tc_planes == 2, SEB_EINVAL, "conv split: weight image must have 2 planes");
   dim3 grid((g.M + BM - 1) / BM, s->tc_ntiles);
   conv_split_tc_kernel<NT, STAGES, EK><<<grid, TC_THREADS, SMEM, st>>>(g, reinterpret_cast<const uint8_t*>(s->w_tc));
   SEB_CHECK_LAUNCH("conv_split_tc_kernel");
   return 0;
+}
+
+// K-chunk count up to which the persistent kernel is used (SEB200_CONV_PERSIST_MAXK overrides; tuning knob)
+int conv_persist_max_chunks() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SEB200_CONV_PERSIST_MAXK"); v = e ? atoi(e) : 12; }   // measured: persistent wins for <= 12 chunks (layers 1-2, conv_2), the 2-CTA ring for longer K
+  return v;
 }
 
 }  // namespace seb
@@ -114,7 +127,13 @@ extern "C" int seb200_gemm(const SebGemm* s, int engine, void* stream) {
   } else if (engine == SEB_ENGINE_TCGEN05) {
     const int nt = s->tc_ntile;
     switch (key) {
-      case SEB_LOAD_CONV_SPLIT * 16 + SEB_EPI_BIAS:     if (nt == 64)  return launch_conv_split<64, 2, SEB_EPI_BIAS>(s, g, st); break;
+      case SEB_LOAD_CONV_SPLIT * 16 + SEB_EPI_BIAS:
+        if (nt == 64 && s->tc_ntiles == 1 && s->N == 64 && s->stride_f == 1 && s->Fin == s->Fout && s->ldo % 4 == 0 && s->tc_planes == 2 && conv_tap_enabled())
+          return launch_conv_tap(s, g, st);              // experimental: shared A tile for the three frequency taps
+        if (nt == 64 && s->tc_ntiles == 1 && s->N == 64 && s->ldo % 4 == 0 && s->tc_planes == 2 && s->Fout >= 64 && s->K / BK <= conv_persist_max_chunks())
+          return launch_conv_persist(s, g, st);          // persistent 4-slot ring
+        if (nt == 64) return launch_conv_split<64, 2, SEB_EPI_BIAS>(s, g, st);
+        break;
       case SEB_LOAD_CONV_SPLIT * 16 + SEB_EPI_SUBPIXEL: if (nt == 128) return launch_conv_split<128, 1, SEB_EPI_SUBPIXEL>(s, g, st); break;
       case SEB_LOAD_HANKEL * 16 + SEB_EPI_COMPRESS: if (nt == 208) return (s->tc_planes == 3) ? launch_tc<208, 1, SEB_LOAD_HANKEL, SEB_EPI_COMPRESS, 8, 1, 3>(s, g, st)
                                                                                              : launch_tc<208, 1, SEB_LOAD_HANKEL, SEB_EPI_COMPRESS>(s, g, st); break;

@@ -314,16 +314,33 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must surface as a launch error, never as a hung GPU.  The bookkeeping between polls
-// doubles as back-off: measured on B200, a bare try_wait spin (or a suspend-time hint) slows the conv pipeline by
-// 25% -- the polls compete with the producers' shared-memory stores on the MIO path / add wake-up latency.
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a launch error, never as a hung GPU.
+#ifndef SEB_MBAR_TESTWAIT
+#define SEB_MBAR_TESTWAIT 1
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#if SEB_MBAR_TESTWAIT
+  // non-blocking poll: test_wait returns immediately, so the waiter reacts within a few cycles of the arrival
+  for (uint32_t it = 0; it < (1u << 30); ++it)
+    if (mbar_test_wait(bar, parity)) return;
+  __trap();
+#else
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if ((++spins & 1023u) == 0 && clock64() - t0 > 4000000000LL) __trap();
   }
+#endif
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -575,7 +592,7 @@ conv_split_tc_kernel(const GemmArgs g, const uint8_t* __restrict__ w_tc) {
   const int nkc = g.K / BK;
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 8 + 1); ptx::mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 8 / STAGES + 1); ptx::mbar_init(&empty_bar[s], 1); }
     ptx::mbar_init(&accum_bar, 1);
     ptx::fence_barrier_init();
   }
@@ -587,56 +604,53 @@ conv_split_tc_kernel(const GemmArgs g, const uint8_t* __restrict__ w_tc) {
 
   if (warp < 8) {
     // ---------------- producers: cp.async of pre-split bf16 planes ----------------
+    // The 8 producer warps form STAGES independent groups; group gidx owns ring slot gidx and loads every STAGES-th
+    // K-chunk into it: wait for the slot, copy, wait for the copy, publish.  Publishing chunk c therefore depends only
+    // on MMA(c - STAGES) and on its own copy -- never on another chunk's slot.  (With one group that published chunk
+    // c - 1 after queueing chunk c, the publish sat behind the wait for MMA(c - 1): a fully serialised pipeline,
+    // measured 1.2 k cycles per 384-cycle chunk even with the copies disabled.)
     // lane -> (16-byte chunk c = lane & 7, plane = (lane >> 3) & 1, row-in-pair = lane >> 4): one warp instruction
-    // copies 2 pixels x 256 contiguous bytes; pass p covers rows p*16 + warp*2 + (lane >> 4).
-    const int c = lane & 7, plane = (lane >> 3) & 1, r0 = warp * 2 + (lane >> 4);
-    long long pix[8];        // flat input pixel index of the centre tap (or -1 for rows beyond M)
-    int tf[8];               // (t << 16) | f
+    // copies 2 pixels x 256 contiguous bytes.
+    constexpr int GW = 8 / STAGES;                       // warps per group
+    constexpr int RPP = GW * 2, NPASS = BM / RPP;        // rows per pass, passes per chunk
+    const int gidx = warp / GW, gw = warp % GW;
+    const int c = lane & 7, plane = (lane >> 3) & 1, r0 = gw * 2 + (lane >> 4);
+    const uint32_t dst0 = (uint32_t)(plane * TC_A_BYTES + r0 * 128 + ((c ^ (r0 & 7)) << 4));   // + p * RPP * 128 per pass (RPP % 8 == 0)
+    const int src_lane_off = plane * 128 + c * 16;                                             // bytes inside a pixel
+    int pix[NPASS];           // flat input pixel index of the centre tap of this thread's row in pass p (-1: row beyond M)
+    int tf[NPASS];            // (t << 16) | f
 #pragma unroll
-    for (int p = 0; p < 8; ++p) {
-      const int m = m0 + p * 16 + r0;
+    for (int p = 0; p < NPASS; ++p) {
+      const int m = m0 + p * RPP + r0;
       if (m < g.M) {
         const int bt = m / g.Fout, f = m - bt * g.Fout, b = bt / g.T, t = bt - b * g.T;
-        pix[p] = ((long long)b * g.T + t) * g.Fin + (long long)f * g.stride_f;
+        pix[p] = (b * g.T + t) * g.Fin + f * g.stride_f;
         tf[p] = (t << 16) | f;
       } else { pix[p] = -1; tf[p] = 0; }
     }
-    const uint32_t dst0 = (uint32_t)(plane * TC_A_BYTES + r0 * 128 + ((c ^ (r0 & 7)) << 4));   // + p * 2048 per pass
-    const int src_lane_off = plane * 128 + c * 16;                                             // bytes inside a pixel
-    for (int kc = 0; kc < nkc; ++kc) {
-      const int s = kc % STAGES;
+    for (int kc = gidx; kc < nkc; kc += STAGES) {
+      const int s = gidx;
       const uint32_t ph = (uint32_t)(kc / STAGES) & 1u;
-      ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
       const int tap = kc / g.nslots, slot = kc - tap * g.nslots;
       const int kt = (g.taps_t == 2) ? tap / 3 : 0, kf = tap - kt * 3;
       const int dt = (g.taps_t - 1 - kt) * g.dil, df = kf - 1;
       const uint8_t* src_base = reinterpret_cast<const uint8_t*>(g.a[slot]) + src_lane_off;
-      const long long dpix = (long long)df - (long long)dt * g.Fin;
+      const int dpix = df - dt * g.Fin;
       const uint32_t dst = smem_base + s * STAGE + dst0;
+      ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
 #pragma unroll
-      for (int p = 0; p < 8; ++p) {
+      for (int p = 0; p < NPASS; ++p) {
         const int t = tf[p] >> 16, f = tf[p] & 0xffff;
         const int ff = f * g.stride_f + df;
         const bool ok = pix[p] >= 0 && t >= dt && ff >= 0 && ff < g.Fin;
-        const long long q = ok ? pix[p] + dpix : 0;
-        cp_async16_zfill(dst + p * 2048, src_base + q * 256, ok ? 16u : 0u);
+        const long long q = ok ? (long long)(pix[p] + dpix) : 0;
+        cp_async16_zfill(dst + p * (RPP * 128), src_base + q * 256, ok ? 16u : 0u);
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
-      // keep LAG = STAGES - 1 copy groups in flight: chunk kc - LAG has landed -> publish it to the MMA issuer
-      constexpr int LAG = STAGES - 1;
-      if (kc >= LAG) {
-        if (LAG == 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
-        else asm volatile("cp.async.wait_group 1;" ::: "memory");
-        ptx::fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&full_bar[(kc - LAG) % STAGES]);
-      }
-    }
-    if (STAGES > 1) {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       ptx::fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&full_bar[(nkc - 1) % STAGES]);
+      if (lane == 0) ptx::mbar_arrive(&full_bar[s]);
     }
 
     // ---------------- epilogue (identical to gemm_tc_kernel) ----------------
