@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(CTP_THREADS, 1) conv_tap_tc_kernel(const GemmA
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[CTP_STAGES], empty_bar[CTP_STAGES], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (STS/LDS, not generic ST/LD)
   const uint32_t smem_base = ptx::smem_u32(smem);
   uint8_t* stg_base = smem + CTP_STAGES * CT_STAGE;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;

@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(Y3_THREADS, 1) conv_y3_kernel(const GemmArgs g
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[Y3_SLOTS], empty_bar[Y3_SLOTS], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (STS/LDS, not generic ST/LD)
   const uint32_t smem_base = ptx::smem_u32(smem);
   float4* stg = reinterpret_cast<float4*>(smem + Y3_SLOTS * Y3_STAGE);    // [128 rows][16 x float4], chunk XOR (row & 7)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;

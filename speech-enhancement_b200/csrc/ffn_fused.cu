@@ -26,8 +26,8 @@ struct FfnArgs {
 };
 
 // ---- persistent, warp-specialised version ----------------------------------------------------------------------
-// One CTA per SM loops over 128-token tiles.  Both weight images (W1 and W2, hi|lo, 128 KB) are loaded ONCE and stay
-// resident in shared memory; 4 loader warps run ahead (LayerNorm + split of the next tile into a double-buffered
+// One CTA per SM loops over 128-token tiles.  W1 (hi|lo, 64 KB) is loaded ONCE and stays resident in shared memory, W2
+// blocks stream through a 2-slot ring; the A operand and the hidden chunk H are double buffered; 4 loader warps run ahead (LayerNorm + split of the next tile into a double-buffered
 // A operand); 8 epilogue warps do the Swish mid-epilogues and the final store; 1 thread issues every tcgen05.mma.
 // acc1 and acc2 are double buffered in TMEM, so MMA1 of tile i+1 overlaps the final epilogue of tile i.
 constexpr int FF_LOAD_WARPS = 4, FF_EPI_WARPS = 16;
@@ -37,29 +37,32 @@ constexpr int FF_CPT = 64 / FF_CG;                 // columns per thread per qua
 constexpr int FF_THREADS = (FF_LOAD_WARPS + FF_EPI_WARPS + 2) * 32;     // + MMA warp + weight warp = 704
 constexpr int FF_PLANE = BM * 128;                 // 16 KB: one bf16 plane of a 128 x 64 operand tile
 constexpr int FF_WBLK = 2 * 64 * 128;              // 16 KB: hi|lo image of a 64-row x 64-k weight block
-constexpr int FF_SMEM = 1024 + 2 * (2 * FF_PLANE) /*A x2*/ + 4 * FF_WBLK /*W1*/ + 4 * FF_WBLK /*W2*/ + 2 * FF_PLANE /*H*/;
+constexpr int FF_SMEM = 1024 + 2 * (2 * FF_PLANE) /*A x2*/ + 4 * FF_WBLK /*W1 resident*/ + 2 * FF_WBLK /*W2 ring*/ + 2 * (2 * FF_PLANE) /*H x2*/;
 
 __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t a_full[2], a_empty[2], w_full, acc1_full[2], acc1_empty[2], h_full, h_empty, acc2_full[2], acc2_empty[2];
+  __shared__ uint64_t a_full[2], a_empty[2], w_full, w2_full[2], w2_empty[2], acc1_full[2], acc1_empty[2], h_full[2], h_empty[2], acc2_full[2], acc2_empty[2];
   __shared__ uint32_t tmem_base_s;
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (STS/LDS, not generic ST/LD)
   uint8_t* sA = smem;                           // [2][hi | lo]            64 KB
-  uint8_t* sW1 = sA + 4 * FF_PLANE;             // 4 blocks x (hi | lo)    64 KB
-  uint8_t* sW2 = sW1 + 4 * FF_WBLK;             // 4 blocks x (hi | lo)    64 KB
-  uint8_t* sH = sW2 + 4 * FF_WBLK;              // hi | lo                 32 KB  (also the fp32 staging tile of the final store)
+  uint8_t* sW1 = sA + 4 * FF_PLANE;             // 4 blocks x (hi | lo)    64 KB  resident
+  uint8_t* sW2 = sW1 + 4 * FF_WBLK;             // 2-slot ring of (hi | lo) blocks   32 KB  (streamed: 64 KB per tile from L2)
+  uint8_t* sH = sW2 + 2 * FF_WBLK;              // [2][hi | lo]            64 KB  (H[0] doubles as the fp32 staging tile of the final store)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ntiles = (a.M + BM - 1) / BM;
   const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(&a_full[i], FF_LOAD_WARPS * 32); ptx::mbar_init(&a_empty[i], 1);
       ptx::mbar_init(&acc1_full[i], 1); ptx::mbar_init(&acc1_empty[i], FF_EPI_WARPS * 32);
       ptx::mbar_init(&acc2_full[i], 1); ptx::mbar_init(&acc2_empty[i], FF_EPI_WARPS * 32);
+      ptx::mbar_init(&h_full[i], FF_EPI_WARPS * 32); ptx::mbar_init(&h_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&a_full[i], FF_LOAD_WARPS * 32); ptx::mbar_init(&a_empty[i], 1);
+      ptx::mbar_init(&w2_full[i], 1); ptx::mbar_init(&w2_empty[i], 1);
     }
     ptx::mbar_init(&w_full, 1);
-    ptx::mbar_init(&h_full, FF_EPI_WARPS * 32); ptx::mbar_init(&h_empty, 1);
     ptx::fence_barrier_init();
   }
   if (warp == FF_LOAD_WARPS + FF_EPI_WARPS) ptx::tmem_alloc(&tmem_base_s, 256);
@@ -75,7 +78,6 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnArgs 
     const int sub = tid & 7, rloc = tid >> 3;          // 16 rows per pass, 8 passes
     for (int it = 0; it < my_tiles; ++it) {
       const int m0 = ((int)blockIdx.x + it * (int)gridDim.x) * BM;
-      const int s = it & 1;
       // pull the NEXT tile's rows (and its residual rows) into L2 now: 128 loader threads x 2 (x 2) 128-byte lines,
       // so the demand loads below find their data on chip and DRAM always has a full tile in flight per SM
       if (it + 1 < my_tiles) {
@@ -90,6 +92,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnArgs 
           }
         }
       }
+      const int s = it & 1;
       ptx::mbar_wait(&a_empty[s], ((uint32_t)(it >> 1) & 1u) ^ 1u);
       uint8_t* dA = sA + s * 2 * FF_PLANE;
 #pragma unroll 4
@@ -126,7 +129,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnArgs 
 #pragma unroll 1
       for (int q = 0; q < 4; ++q) {
         const int b = q & 1;
-        const uint32_t u1 = (uint32_t)(2 * it + (q >> 1)), uh = (uint32_t)(4 * it + q);
+        const uint32_t u1 = (uint32_t)(2 * it + (q >> 1));
         const float* bias = a.b1 + q * 64 + cg * FF_CPT;
         float4 bb[FF_CPT / 4];
 #pragma unroll
@@ -148,7 +151,8 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnArgs 
         for (int j = 0; j < FF_CPT / 4; ++j) { v[4 * j] += bb[j].x; v[4 * j + 1] += bb[j].y; v[4 * j + 2] += bb[j].z; v[4 * j + 3] += bb[j].w; }
 #pragma unroll
         for (int j = 0; j < FF_CPT; ++j) v[j] *= sigmoidf_acc(v[j]);
-        ptx::mbar_wait(&h_empty, (uh & 1u) ^ 1u);
+        uint8_t* dH = sH + (q & 1) * 2 * FF_PLANE;            // H buffer q & 1; its use count is 2 * it + (q >> 1) == u1
+        ptx::mbar_wait(&h_empty[q & 1], (u1 & 1u) ^ 1u);
 #pragma unroll
         for (int c8 = 0; c8 < FF_CPT / 8; ++c8) {
           uint4 hi, lo;
@@ -156,11 +160,11 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnArgs 
           split_bf16x2(v[c8 * 8 + 4], v[c8 * 8 + 5], hi.z, lo.z); split_bf16x2(v[c8 * 8 + 6], v[c8 * 8 + 7], hi.w, lo.w);
           const int c = cg * (FF_CPT / 8) + c8;
           const int off = row * 128 + ((c ^ (row & 7)) << 4);
-          *reinterpret_cast<uint4*>(sH + off) = hi;
-          *reinterpret_cast<uint4*>(sH + FF_PLANE + off) = lo;
+          *reinterpret_cast<uint4*>(dH + off) = hi;
+          *reinterpret_cast<uint4*>(dH + FF_PLANE + off) = lo;
         }
         ptx::fence_proxy_async_smem();
-        ptx::mbar_arrive(&h_full);
+        ptx::mbar_arrive(&h_full[q & 1]);
       }
       // ---- final epilogue: acc2 -> staging (H buffer: every MMA2 of this tile has completed) -> coalesced store
       // issue the residual loads first: they do not depend on the accumulator
@@ -242,11 +246,13 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnArgs 
           if (q == 3) ptx::tc_commit(&a_empty[s]);
         };
         auto mma2 = [&](int q) {
-          const uint32_t uh = (uint32_t)(4 * it + q);
-          ptx::mbar_wait(&h_full, uh & 1u);
+          const uint32_t u1 = (uint32_t)(2 * it + (q >> 1));      // use count of H[q & 1] and of W2 ring slot q & 1
+          ptx::mbar_wait(&h_full[q & 1], u1 & 1u);
+          ptx::mbar_wait(&w2_full[q & 1], u1 & 1u);
           ptx::tc_fence_after();
-          gemm64(tmem_base + 128u + (uint32_t)(ab * 64), uH, uW2 + q * FF_WBLK, q == 0);
-          ptx::tc_commit(&h_empty);
+          gemm64(tmem_base + 128u + (uint32_t)(ab * 64), uH + (q & 1) * 2 * FF_PLANE, uW2 + (q & 1) * FF_WBLK, q == 0);
+          ptx::tc_commit(&h_empty[q & 1]);
+          ptx::tc_commit(&w2_empty[q & 1]);
           if (q == 3) ptx::tc_commit(&acc2_full[ab]);
         };
         ptx::mbar_wait(&a_full[s], (uint32_t)(it >> 1) & 1u);
@@ -262,10 +268,15 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnArgs 
   } else {
     // ================= weights: loaded once, resident for the whole kernel =================
     if (lane == 0 && my_tiles > 0) {
-      ptx::mbar_arrive_expect_tx(&w_full, 8 * FF_WBLK);
-      for (int q = 0; q < 4; ++q) {
-        ptx::bulk_g2s(ptx::smem_u32(sW1) + q * FF_WBLK, a.w1 + (size_t)q * FF_WBLK, FF_WBLK, &w_full);
-        ptx::bulk_g2s(ptx::smem_u32(sW2) + q * FF_WBLK, a.w2 + (size_t)q * FF_WBLK, FF_WBLK, &w_full);
+      ptx::mbar_arrive_expect_tx(&w_full, 4 * FF_WBLK);           // W1: loaded once, resident
+      for (int q = 0; q < 4; ++q) ptx::bulk_g2s(ptx::smem_u32(sW1) + q * FF_WBLK, a.w1 + (size_t)q * FF_WBLK, FF_WBLK, &w_full);
+      for (int it = 0; it < my_tiles; ++it) {                     // W2: block q of every tile through the 2-slot ring
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t u = (uint32_t)(2 * it + (q >> 1));
+          ptx::mbar_wait(&w2_empty[q & 1], (u & 1u) ^ 1u);
+          ptx::mbar_arrive_expect_tx(&w2_full[q & 1], FF_WBLK);
+          ptx::bulk_g2s(ptx::smem_u32(sW2) + (q & 1) * FF_WBLK, a.w2 + (size_t)q * FF_WBLK, FF_WBLK, &w2_full[q & 1]);
+        }
       }
     }
   }

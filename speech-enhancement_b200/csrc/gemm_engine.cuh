@@ -325,7 +325,7 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug must surface as a launch error, never as a hung GPU.
 #ifndef SEB_MBAR_TESTWAIT
-#define SEB_MBAR_TESTWAIT 1
+#define SEB_MBAR_TESTWAIT 0
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #if SEB_MBAR_TESTWAIT
@@ -409,7 +409,7 @@ gemm_tc_kernel(const GemmArgs g, const uint8_t* __restrict__ w_tc) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
   __shared__ uint32_t tmem_base_s;
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (STS/LDS, not generic ST/LD)
   const uint32_t smem_base = ptx::smem_u32(smem);
   constexpr int STAGE = tc_stage_bytes<NT, NPL>();
   constexpr uint32_t W_BYTES = NT * 128;
@@ -580,7 +580,7 @@ conv_split_tc_kernel(const GemmArgs g, const uint8_t* __restrict__ w_tc) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
   __shared__ uint32_t tmem_base_s;
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (STS/LDS, not generic ST/LD)
   const uint32_t smem_base = ptx::smem_u32(smem);
   constexpr int STAGE = tc_stage_bytes<NT>();
   constexpr uint32_t W_BYTES = NT * 128;
