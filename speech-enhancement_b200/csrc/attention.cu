@@ -138,6 +138,10 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_b
                ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(src_bytes) : "memory");
 }
 
+// BAND = true (long sequences, n > ~1100): key tiles whose offsets i - j all lie beyond +-512 see ONE embedding row
+// (conformer.py:108 clamps the distance), so their rel-pos logit is a per-query constant q_i . E[0] or q_i . E[1024]:
+// the score accumulators start from that constant and the R GEMM + skew are skipped (78 % of the tiles at T = 4801).
+template <bool BAND>
 __global__ void __launch_bounds__(128, 3) attention_f16_kernel(const __half* __restrict__ qkvh, const __half* __restrict__ Eh,
                                                               const SebSeq sq, int nqb, float* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smraw[];
@@ -201,6 +205,20 @@ __global__ void __launch_bounds__(128, 3) attention_f16_kernel(const __half* __r
       for (int e = 0; e < 4; ++e) o[mt][x][e] = 0.f;
   }
   const uint32_t ones = (g == 0) ? 0x3C003C00u : 0u;
+  float c_far[2][2][2];        // [far side: 0 = offsets <= -512 (E[0]), 1 = offsets >= +512 (E[1024])][mt][row g / g+8]
+  if (BAND) {
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+      const uint32_t* er = reinterpret_cast<const uint32_t*>(Eh + side * (2 * AT_MAXPOS) * AT_D) + t;
+      const uint32_t e0 = __ldg(er), e1 = __ldg(er + 4);            // every B column is the same embedding row
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        float r4[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_f16(r4, qa[mt], e0, e1);
+        c_far[side][mt][0] = r4[0]; c_far[side][mt][1] = r4[2];
+      }
+    }
+  }
   // ldmatrix lane addressing (in halfs, relative to a tile): matrix i = lane >> 3, row = lane & 7
   const int lm_i = lane >> 3, lm_r = lane & 7;
   const int k_off = ((lm_i >> 1) * 8 + lm_r) * A2_LD + (lm_i & 1) * 8;        // K: (n-tile pair, d half)
@@ -218,7 +236,9 @@ __global__ void __launch_bounds__(128, 3) attention_f16_kernel(const __half* __r
     const __half* Vs = Ks + A2_TILE_H;
     if (warp_live) {
 
-    // ---- content scores: S[mt] = Q[mt] K^T  (16 x 64 each)
+    // ---- content scores: S[mt] = Q[mt] K^T  (16 x 64 each), started from the far-field rel-pos constant when BAND applies
+    const int dlo = iw - j0 - 64;                 // offsets i - j of this warp tile span [dlo + 1, dlo + 95]
+    const int far = !BAND ? -1 : (dlo + 1 >= AT_MAXPOS ? 1 : (dlo + 95 <= -AT_MAXPOS ? 0 : -1));
     float s[2][8][4];
 #pragma unroll
     for (int np = 0; np < 4; ++np) {
@@ -227,13 +247,16 @@ __global__ void __launch_bounds__(128, 3) attention_f16_kernel(const __half* __r
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) { s[mt][2 * np][e] = 0.f; s[mt][2 * np + 1][e] = 0.f; }
+        for (int e = 0; e < 4; ++e) {
+          const float c0 = !BAND ? 0.f : (far == 1 ? c_far[1][mt][e >> 1] : (far == 0 ? c_far[0][mt][e >> 1] : 0.f));
+          s[mt][2 * np][e] = c0; s[mt][2 * np + 1][e] = c0;
+        }
         mma_f16(s[mt][2 * np], qa[mt], kb[0], kb[1]);
         mma_f16(s[mt][2 * np + 1], qa[mt], kb[2], kb[3]);
       }
     }
+    if (!BAND || far < 0) {
     // ---- relative-position scores: R[r, dd] = q_r . E[clamp(dlo + dd)], dd in [0, 96)
-    const int dlo = iw - j0 - 64;
 #pragma unroll
     for (int nt = 0; nt < 12; ++nt) {
       int d = dlo + nt * 8 + g;
@@ -266,6 +289,7 @@ __global__ void __launch_bounds__(128, 3) attention_f16_kernel(const __half* __r
           s[mt][nt][e] += Rs[r * A2_RLD + 64 + r - c];
         }
     __syncwarp();
+    }   // in-band tile
     if (j0 + A2_BK > n) {   // mask keys beyond the sequence (last tile only)
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
@@ -354,14 +378,18 @@ extern "C" int seb200_attention(const void* qkv, const float* rel_pos_emb, const
   SEB_REQUIRE(rel_pos_emb_h && aligned16(rel_pos_emb_h), SEB_EINVAL, "attention: the tensor-core variant needs the fp16 copy of rel_pos_emb");
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(attention_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attention_f16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_f16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM);
     if (e != cudaSuccess) { set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     attr_done = true;
   }
   const int nqb = ((n + A2_WROWS - 1) / A2_WROWS + 3) / 4;
   const long long nblocks = (long long)seq->nseq * AT_H * nqb;
   SEB_REQUIRE(nblocks < 2147483647LL, SEB_EINVAL, "attention: grid too large");
-  attention_f16_kernel<<<(unsigned)nblocks, 128, A2_SMEM, st>>>(reinterpret_cast<const __half*>(qkv), reinterpret_cast<const __half*>(rel_pos_emb_h), *seq, nqb, out);
+  if (n > 2 * AT_MAXPOS + 128)     // far-field shortcut pays once a sizeable share of the (query, key) tiles lies beyond the clamp
+    attention_f16_kernel<true><<<(unsigned)nblocks, 128, A2_SMEM, st>>>(reinterpret_cast<const __half*>(qkv), reinterpret_cast<const __half*>(rel_pos_emb_h), *seq, nqb, out);
+  else
+    attention_f16_kernel<false><<<(unsigned)nblocks, 128, A2_SMEM, st>>>(reinterpret_cast<const __half*>(qkv), reinterpret_cast<const __half*>(rel_pos_emb_h), *seq, nqb, out);
   SEB_CHECK_LAUNCH("attention_f16_kernel");
   return 0;
 }
