@@ -10,6 +10,7 @@ int launch_conv_persist(const SebGemm* s, const GemmArgs& g, cudaStream_t st);  
 int conv_persist_max_chunks();
 int launch_conv_y3(const SebGemm* s, const GemmArgs& g, cudaStream_t st);        // conv_y3.cu
 int conv_y3_enabled();
+int launch_tok_gemm(const SebGemm* s, const GemmArgs& g, cudaStream_t st);       // tok_gemm.cu (-100: not a persistent token GEMM)
 
 static GemmArgs to_args(const SebGemm* s) {
   GemmArgs g;
@@ -134,6 +135,10 @@ extern "C" int seb200_gemm(const SebGemm* s, int engine, void* stream) {
     }
   } else if (engine == SEB_ENGINE_TCGEN05) {
     const int nt = s->tc_ntile;
+    {
+      const int r = launch_tok_gemm(s, g, st);       // persistent kernels for the conformer's token-wise projections
+      if (r != -100) return r;
+    }
     switch (key) {
       case SEB_LOAD_CONV_SPLIT * 16 + SEB_EPI_BIAS:
         if (nt == 64 && s->tc_ntiles == 1 && s->N == 64 && s->stride_f == 1 && s->Fin == s->Fout && s->ldo % 4 == 0 && s->tc_planes == 2 && conv_tap_enabled())
