@@ -21,8 +21,13 @@ from .generator import TSCNet
 
 
 class EnhancerB200(nn.Module):
-    def __init__(self, model: TSCNet, n_fft: int = 400, hop: int = 100):
+    def __init__(self, model: TSCNet, n_fft: int = 400, hop: int = 100, use_cuda_graph: bool = False):
+        """``use_cuda_graph``: capture the ~135 launches of one forward per (B, L) shape and replay them -- removes the
+        host launch overhead that dominates small batches (1 x 2 s: 2.6 ms eager).  The result is returned as a copy."""
         super().__init__()
+        self.use_cuda_graph = use_cuda_graph
+        self._graphs = {}
+        self.graph_kernel_nodes = 0
         if n_fft != dsp.N_FFT or hop != dsp.HOP:
             raise ValueError("only the reference configuration N_FFT=400, HOP_SAMPLES=100 is implemented")
         self.model = model
@@ -37,6 +42,33 @@ class EnhancerB200(nn.Module):
         x = noisy.to(torch.float32).contiguous()
         if x.dim() == 1:
             x = x.unsqueeze(0)
+        if self.use_cuda_graph and stages is None:
+            return self._forward_graphed(x)
+        return self._forward_eager(x, stages)
+
+    def _forward_graphed(self, x: torch.Tensor) -> torch.Tensor:
+        key = (str(x.device), tuple(x.shape), self.model._version_key(), self.model.engine, self.dft_engine)
+        entry = self._graphs.get(key)
+        if entry is None:
+            for _ in range(2):                       # warm-up: packs weights, sizes workspaces, sets kernel attributes
+                self._forward_eager(x, None)
+            torch.cuda.synchronize(x.device)
+            static_in = x.clone()
+            graph = torch.cuda.CUDAGraph()
+            from . import _lib
+            n0 = _lib.launch_count()
+            with torch.cuda.graph(graph):
+                static_out = self._forward_eager(static_in, None)
+            self.graph_kernel_nodes = _lib.launch_count() - n0      # kernels replayed per call (the C-ABI counter only sees the capture)
+            if len(self._graphs) > 8:
+                self._graphs.clear()
+            entry = self._graphs[key] = (graph, static_in, static_out)
+        graph, static_in, static_out = entry
+        static_in.copy_(x)
+        graph.replay()
+        return static_out.clone()
+
+    def _forward_eager(self, x: torch.Tensor, stages=None) -> torch.Tensor:
         B, L = x.shape
         Lp = int(math.ceil(L / dsp.HOP)) * dsp.HOP
         T = Lp // dsp.HOP + 1

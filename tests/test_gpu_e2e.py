@@ -97,6 +97,17 @@ def test_fp32_path_is_fp32_exact():
     assert rel_max(y_g, y_o) < 2e-5
 
 
+def test_cuda_graph_replay_matches_eager():
+    """the captured forward (launch-overhead-free path for small batches) reproduces the eager result bit for bit"""
+    model = _model(0, "tcgen05")
+    eager = se_b200.EnhancerB200(model)
+    graphed = se_b200.EnhancerB200(model, use_cuda_graph=True)
+    for seed in (31, 32):
+        noisy, _ = weights.synth_wave(1, 8000, seed=seed, kind="speech")
+        noisy = noisy.to(DEV)
+        assert torch.equal(graphed(noisy), eager(noisy))
+
+
 def test_batch_rows_are_independent():
     """pure batch sharding: a row enhanced alone equals the same row inside a batch, bit for bit"""
     model = _model(0, "tcgen05")
