@@ -27,27 +27,33 @@ struct FfnArgs {
 
 // ---- persistent, warp-specialised version ----------------------------------------------------------------------
 // One CTA per SM loops over 128-token tiles.  W1 (hi|lo, 64 KB) is loaded ONCE and stays resident in shared memory, W2
-// blocks stream through a 2-slot ring; the A operand and the hidden chunk H are double buffered; 4 loader warps run ahead (LayerNorm + split of the next tile into a double-buffered
-// A operand); 8 epilogue warps do the Swish mid-epilogues and the final store; 1 thread issues every tcgen05.mma.
+// blocks stream through a 2-slot ring.  The raw fp32 rows of the NEXT tile (128 x 256 B, contiguous in HBM) are staged
+// into shared memory by one cp.async.bulk issued by a dedicated warp, so the 4 loader warps (LayerNorm + bf16 hi/lo
+// split into the double-buffered A operand) never wait on a global load: round 1 profiling showed the loaders, with
+// eight serialised ~740-cycle LDG waits per tile, pacing the whole kernel.  The hidden chunk H is single buffered
+// (its writer only needs it after its MUFU phase, by which time MMA2 of the previous chunk has long retired);
+// 16 epilogue warps do the Swish mid-epilogues and the final store; 1 thread issues every tcgen05.mma.
 // acc1 and acc2 are double buffered in TMEM, so MMA1 of tile i+1 overlaps the final epilogue of tile i.
 constexpr int FF_LOAD_WARPS = 4, FF_EPI_WARPS = 16;
 constexpr int FF_EPI_THREADS = FF_EPI_WARPS * 32;
 constexpr int FF_CG = FF_EPI_WARPS / 4;            // column groups: each epilogue thread owns one row x (64 / FF_CG) columns
 constexpr int FF_CPT = 64 / FF_CG;                 // columns per thread per quarter (16)
-constexpr int FF_THREADS = (FF_LOAD_WARPS + FF_EPI_WARPS + 2) * 32;     // + MMA warp + weight warp = 704
+constexpr int FF_THREADS = (FF_LOAD_WARPS + FF_EPI_WARPS + 3) * 32;     // + MMA warp + weight warp + x-staging warp = 736
 constexpr int FF_PLANE = BM * 128;                 // 16 KB: one bf16 plane of a 128 x 64 operand tile
 constexpr int FF_WBLK = 2 * 64 * 128;              // 16 KB: hi|lo image of a 64-row x 64-k weight block
-constexpr int FF_SMEM = 1024 + 2 * (2 * FF_PLANE) /*A x2*/ + 4 * FF_WBLK /*W1 resident*/ + 2 * FF_WBLK /*W2 ring*/ + 2 * (2 * FF_PLANE) /*H x2*/;
+constexpr int FF_XBYTES = BM * 64 * 4;             // 32 KB: raw fp32 rows of one tile
+constexpr int FF_SMEM = 1024 + 2 * (2 * FF_PLANE) /*A x2*/ + 4 * FF_WBLK /*W1 resident*/ + 2 * FF_WBLK /*W2 ring*/ + 2 * FF_PLANE /*H*/ + FF_XBYTES /*x staging*/;
 
 __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t a_full[2], a_empty[2], w_full, w2_full[2], w2_empty[2], acc1_full[2], acc1_empty[2], h_full[2], h_empty[2], acc2_full[2], acc2_empty[2];
+  __shared__ uint64_t a_full[2], a_empty[2], w_full, w2_full[2], w2_empty[2], acc1_full[2], acc1_empty[2], h_full, h_empty, x_full, x_empty, acc2_full[2], acc2_empty[2];
   __shared__ uint32_t tmem_base_s;
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (STS/LDS, not generic ST/LD)
   uint8_t* sA = smem;                           // [2][hi | lo]            64 KB
   uint8_t* sW1 = sA + 4 * FF_PLANE;             // 4 blocks x (hi | lo)    64 KB  resident
   uint8_t* sW2 = sW1 + 4 * FF_WBLK;             // 2-slot ring of (hi | lo) blocks   32 KB  (streamed: 64 KB per tile from L2)
-  uint8_t* sH = sW2 + 2 * FF_WBLK;              // [2][hi | lo]            64 KB  (H[0] doubles as the fp32 staging tile of the final store)
+  uint8_t* sH = sW2 + 2 * FF_WBLK;              // [hi | lo]               32 KB  (doubles as the fp32 staging tile of the final store)
+  uint8_t* sX = sH + 2 * FF_PLANE;              // raw fp32 rows of the tile the loaders work on   32 KB
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ntiles = (a.M + BM - 1) / BM;
   const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -56,8 +62,9 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnArgs 
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&acc1_full[i], 1); ptx::mbar_init(&acc1_empty[i], FF_EPI_WARPS * 32);
       ptx::mbar_init(&acc2_full[i], 1); ptx::mbar_init(&acc2_empty[i], FF_EPI_WARPS * 32);
-      ptx::mbar_init(&h_full[i], FF_EPI_WARPS * 32); ptx::mbar_init(&h_empty[i], 1);
     }
+    ptx::mbar_init(&h_full, FF_EPI_WARPS * 32); ptx::mbar_init(&h_empty, 1);
+    ptx::mbar_init(&x_full, 1); ptx::mbar_init(&x_empty, FF_LOAD_WARPS * 32);
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&a_full[i], FF_LOAD_WARPS * 32); ptx::mbar_init(&a_empty[i], 1);
       ptx::mbar_init(&w2_full[i], 1); ptx::mbar_init(&w2_empty[i], 1);
@@ -72,36 +79,53 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnArgs 
   const uint32_t tmem_base = tmem_base_s;     // acc1[b] at column 64 b, acc2[b] at column 128 + 64 b
 
   if (warp < FF_LOAD_WARPS) {
-    // ================= loaders: x -> LayerNorm -> bf16 hi/lo -> swizzled A[s] =================
-    GemmArgs g;
-    g.a[0] = a.x; g.lda = 64; g.M = a.M; g.ln_g = a.ln_g; g.ln_b = a.ln_b;
-    const int sub = tid & 7, rloc = tid >> 3;          // 16 rows per pass, 8 passes
+    // ================= loaders: staged x rows -> LayerNorm -> bf16 hi/lo -> swizzled A[s] =================
+    const int sub = tid & 7, rloc = tid >> 3;          // 16 rows per pass, 8 passes; 8 adjacent lanes own one row
+    const float4 g0 = ldg4(a.ln_g + sub * 8), g1 = ldg4(a.ln_g + sub * 8 + 4);
+    const float4 b0 = ldg4(a.ln_b + sub * 8), b1 = ldg4(a.ln_b + sub * 8 + 4);
     for (int it = 0; it < my_tiles; ++it) {
       const int m0 = ((int)blockIdx.x + it * (int)gridDim.x) * BM;
-      // pull the NEXT tile's rows (and its residual rows) into L2 now: 128 loader threads x 2 (x 2) 128-byte lines,
-      // so the demand loads below find their data on chip and DRAM always has a full tile in flight per SM
-      if (it + 1 < my_tiles) {
-        const long long nrow = (long long)(m0 + (int)gridDim.x * BM) * 64;
-        const long long off = nrow + (long long)tid * 64;            // floats: 2 lines of 32 floats per thread
-        if ((nrow >> 6) + (tid >> 0) * 1 < (long long)a.M) {
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.x + off));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.x + off + 32));
-          if (a.resid2 && a.resid2 != a.x) {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.resid2 + off));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.resid2 + off + 32));
-          }
+      // pull the residual rows of the NEXT tile (read by the final epilogue) into L2 while this tile is processed
+      if (it + 1 < my_tiles && a.resid2 && a.resid2 != a.x) {
+        const long long nrow = (long long)m0 + (long long)gridDim.x * BM + tid;
+        if (nrow < (long long)a.M) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.resid2 + nrow * 64));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.resid2 + nrow * 64 + 32));
         }
       }
       const int s = it & 1;
+      ptx::mbar_wait(&x_full, (uint32_t)it & 1u);
       ptx::mbar_wait(&a_empty[s], ((uint32_t)(it >> 1) & 1u) ^ 1u);
       uint8_t* dA = sA + s * 2 * FF_PLANE;
-#pragma unroll 4
+#pragma unroll
       for (int p = 0; p < 8; ++p) {
         const int r = p * 16 + rloc;
-        Loader<SEB_LOAD_ROWS_LN>::Row row;
-        Loader<SEB_LOAD_ROWS_LN>::init_row(g, m0 + r, row);
         float v[8];
-        Loader<SEB_LOAD_ROWS_LN>::load(g, row, 0, sub, v);
+        {
+          const float4 x0 = *reinterpret_cast<const float4*>(sX + r * 256 + sub * 32);
+          const float4 x1 = *reinterpret_cast<const float4*>(sX + r * 256 + sub * 32 + 16);
+          v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+        }
+        if (m0 + r >= a.M) {        // rows past the end of the tensor were not staged: keep the operand finite
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        }
+        float sm = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+        sm += __shfl_xor_sync(0xffffffffu, sm, 1);
+        sm += __shfl_xor_sync(0xffffffffu, sm, 2);
+        sm += __shfl_xor_sync(0xffffffffu, sm, 4);
+        const float mean = sm * (1.0f / 64.0f);
+        float qv = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { v[i] -= mean; qv = fmaf(v[i], v[i], qv); }
+        qv += __shfl_xor_sync(0xffffffffu, qv, 1);
+        qv += __shfl_xor_sync(0xffffffffu, qv, 2);
+        qv += __shfl_xor_sync(0xffffffffu, qv, 4);
+        const float rstd = 1.0f / sqrtf(qv * (1.0f / 64.0f) + 1e-5f);
+        v[0] = v[0] * rstd * g0.x + b0.x; v[1] = v[1] * rstd * g0.y + b0.y;
+        v[2] = v[2] * rstd * g0.z + b0.z; v[3] = v[3] * rstd * g0.w + b0.w;
+        v[4] = v[4] * rstd * g1.x + b1.x; v[5] = v[5] * rstd * g1.y + b1.y;
+        v[6] = v[6] * rstd * g1.z + b1.z; v[7] = v[7] * rstd * g1.w + b1.w;
         uint4 hi, lo;
         split_bf16x2(v[0], v[1], hi.x, lo.x); split_bf16x2(v[2], v[3], hi.y, lo.y);
         split_bf16x2(v[4], v[5], hi.z, lo.z); split_bf16x2(v[6], v[7], hi.w, lo.w);
@@ -109,6 +133,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnArgs 
         *reinterpret_cast<uint4*>(dA + off) = hi;
         *reinterpret_cast<uint4*>(dA + FF_PLANE + off) = lo;
       }
+      ptx::mbar_arrive(&x_empty);               // staged rows consumed: the next tile may land
       ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(&a_full[s]);
     }
@@ -151,8 +176,9 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnArgs 
         for (int j = 0; j < FF_CPT / 4; ++j) { v[4 * j] += bb[j].x; v[4 * j + 1] += bb[j].y; v[4 * j + 2] += bb[j].z; v[4 * j + 3] += bb[j].w; }
 #pragma unroll
         for (int j = 0; j < FF_CPT; ++j) v[j] *= sigmoidf_acc(v[j]);
-        uint8_t* dH = sH + (q & 1) * 2 * FF_PLANE;            // H buffer q & 1; its use count is 2 * it + (q >> 1) == u1
-        ptx::mbar_wait(&h_empty[q & 1], (u1 & 1u) ^ 1u);
+        uint8_t* dH = sH;                                     // single H buffer; its use count is 4 * it + q
+        const uint32_t uh = (uint32_t)(4 * it + q);
+        ptx::mbar_wait(&h_empty, (uh & 1u) ^ 1u);
 #pragma unroll
         for (int c8 = 0; c8 < FF_CPT / 8; ++c8) {
           uint4 hi, lo;
@@ -164,7 +190,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnArgs 
           *reinterpret_cast<uint4*>(dH + FF_PLANE + off) = lo;
         }
         ptx::fence_proxy_async_smem();
-        ptx::mbar_arrive(&h_full[q & 1]);
+        ptx::mbar_arrive(&h_full);
       }
       // ---- final epilogue: acc2 -> staging (H buffer: every MMA2 of this tile has completed) -> coalesced store
       // issue the residual loads first: they do not depend on the accumulator
@@ -246,12 +272,12 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnArgs 
           if (q == 3) ptx::tc_commit(&a_empty[s]);
         };
         auto mma2 = [&](int q) {
-          const uint32_t u1 = (uint32_t)(2 * it + (q >> 1));      // use count of H[q & 1] and of W2 ring slot q & 1
-          ptx::mbar_wait(&h_full[q & 1], u1 & 1u);
+          const uint32_t u1 = (uint32_t)(2 * it + (q >> 1));      // use count of W2 ring slot q & 1
+          ptx::mbar_wait(&h_full, (uint32_t)(4 * it + q) & 1u);
           ptx::mbar_wait(&w2_full[q & 1], u1 & 1u);
           ptx::tc_fence_after();
-          gemm64(tmem_base + 128u + (uint32_t)(ab * 64), uH + (q & 1) * 2 * FF_PLANE, uW2 + (q & 1) * FF_WBLK, q == 0);
-          ptx::tc_commit(&h_empty[q & 1]);
+          gemm64(tmem_base + 128u + (uint32_t)(ab * 64), uH, uW2 + (q & 1) * FF_WBLK, q == 0);
+          ptx::tc_commit(&h_empty);
           ptx::tc_commit(&w2_empty[q & 1]);
           if (q == 3) ptx::tc_commit(&acc2_full[ab]);
         };
@@ -263,6 +289,17 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnArgs 
           if (q < 3) mma1(q + 1);
           mma2(q);
         }
+      }
+    }
+  } else if (warp == FF_LOAD_WARPS + FF_EPI_WARPS + 2) {
+    // ================= x staging: one bulk copy per tile (rows are contiguous in HBM) =================
+    if (lane == 0) {
+      for (int it = 0; it < my_tiles; ++it) {
+        const int m0 = ((int)blockIdx.x + it * (int)gridDim.x) * BM;
+        const int rows = (a.M - m0 < BM) ? a.M - m0 : BM;
+        ptx::mbar_wait(&x_empty, ((uint32_t)it & 1u) ^ 1u);
+        ptx::mbar_arrive_expect_tx(&x_full, (uint32_t)rows * 256u);
+        ptx::bulk_g2s(ptx::smem_u32(sX), a.x + (long long)m0 * 64, (uint32_t)rows * 256u, &x_full);
       }
     }
   } else {
