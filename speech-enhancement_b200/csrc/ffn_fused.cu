@@ -5,13 +5,23 @@
 //     y   = x + alpha * ( W2 . swish( W1 . LayerNorm(x) + b1 ) + b2 )
 //     out = post ? LayerNorm_post(y) + resid2 : y
 //
-// The 128 x 256 hidden activation never leaves the SM.  Per 128-token CTA tile:
-//   producers (8 warps)  : x -> LayerNorm -> bf16 hi/lo -> swizzled smem A operand
-//   for q in 0..3        : MMA1(q): acc1[q&1] (TMEM, 64 cols) = A . W1[64q:64q+64]^T          (tcgen05, 3-product split)
-//                          epilogue warps: tcgen05.ld acc1 -> +b1 -> swish -> bf16 hi/lo -> smem H (K-chunk q of GEMM 2)
-//                          MMA2(q): acc2 (TMEM, 64 cols) += H . W2[:, 64q:64q+64]^T
-//   final                : tcgen05.ld acc2 -> smem transpose -> coalesced: *alpha + b2 + x (-> LayerNorm + resid2) -> store
-// acc1 is double buffered, so MMA1(q+1) overlaps the Swish epilogue of chunk q.
+// v3.  ncu of v2 showed the kernel bound by SHARED-MEMORY bandwidth and by all 16 epilogue warps marching in lock step
+// (MUFU pipe 32 % busy): with the 3-product bf16 split every tcgen05.mma re-read its 128 x 16 A slice from shared
+// memory (N = 64 is too narrow to amortise it), the hidden tile H made a round trip through shared memory, and the
+// loaders waited on eight serialised global loads per tile.  v3 keeps BOTH A operands in tensor memory (the
+// `[a_tmem]` form of tcgen05.mma), so shared memory only serves the resident weights:
+//
+//   copy warp      : cp.async 16 B of the next tile's raw fp32 rows into a 2-slot swizzled staging tile; loads W1|W2 once
+//   4 LN warps     : thread = row.  staged row -> LayerNorm -> bf16 hi|lo -> tcgen05.st into XA[s]            (TMEM)
+//   MMA1 issuer    : ACC1[g] = XA[s] . W1[64q : 64q+64]^T      (A from TMEM, W1 resident in smem; 3 products)
+//   16 mid warps   : two groups of 8 that alternate hidden chunks (g = q & 1), so one group's MUFU phase overlaps the
+//                    other's TMEM traffic:  tcgen05.ld ACC1[g] -> +b1 -> swish -> bf16 hi|lo -> tcgen05.st H[g]  (TMEM)
+//   MMA2 issuer    : ACC2[ab] += H[g] . W2[:, 64q : 64q+64]^T  (A from TMEM, W2 resident in smem)
+//   4 final warps  : thread = row.  tcgen05.ld ACC2 -> *alpha + b2 + x (staged row) -> row statistics -> staged in place ->
+//                    coalesced copy-out (normalise + resid2 when post-norm is requested)
+//
+// TMEM map (512 columns): XA[2] | ACC1[2] | H[2] | ACC2[2], 64 columns each.  All hand-offs are mbarriers; the two MMA
+// issuers are separate threads so that GEMM 1 of chunk q + 2 never queues behind GEMM 2 of chunk q.
 #include "gemm_engine.cuh"
 
 namespace seb {
@@ -25,302 +35,349 @@ struct FfnArgs {
   const float* pn_g; const float* pn_b; const float* resid2;
 };
 
-// ---- persistent, warp-specialised version ----------------------------------------------------------------------
-// One CTA per SM loops over 128-token tiles.  W1 (hi|lo, 64 KB) is loaded ONCE and stays resident in shared memory, W2
-// blocks stream through a 2-slot ring.  The raw fp32 rows of the NEXT tile (128 x 256 B, contiguous in HBM) are staged
-// into shared memory by one cp.async.bulk issued by a dedicated warp, so the 4 loader warps (LayerNorm + bf16 hi/lo
-// split into the double-buffered A operand) never wait on a global load: round 1 profiling showed the loaders, with
-// eight serialised ~740-cycle LDG waits per tile, pacing the whole kernel.  The hidden chunk H is single buffered
-// (its writer only needs it after its MUFU phase, by which time MMA2 of the previous chunk has long retired);
-// 16 epilogue warps do the Swish mid-epilogues and the final store; 1 thread issues every tcgen05.mma.
-// acc1 and acc2 are double buffered in TMEM, so MMA1 of tile i+1 overlaps the final epilogue of tile i.
-constexpr int FF_LOAD_WARPS = 4, FF_EPI_WARPS = 16;
-constexpr int FF_EPI_THREADS = FF_EPI_WARPS * 32;
-constexpr int FF_CG = FF_EPI_WARPS / 4;            // column groups: each epilogue thread owns one row x (64 / FF_CG) columns
-constexpr int FF_CPT = 64 / FF_CG;                 // columns per thread per quarter (16)
-constexpr int FF_THREADS = (FF_LOAD_WARPS + FF_EPI_WARPS + 3) * 32;     // + MMA warp + weight warp + x-staging warp = 736
-constexpr int FF_PLANE = BM * 128;                 // 16 KB: one bf16 plane of a 128 x 64 operand tile
-constexpr int FF_WBLK = 2 * 64 * 128;              // 16 KB: hi|lo image of a 64-row x 64-k weight block
-constexpr int FF_XBYTES = BM * 64 * 4;             // 32 KB: raw fp32 rows of one tile
-constexpr int FF_SMEM = 1024 + 2 * (2 * FF_PLANE) /*A x2*/ + 4 * FF_WBLK /*W1 resident*/ + 2 * FF_WBLK /*W2 ring*/ + 2 * FF_PLANE /*H*/ + FF_XBYTES /*x staging*/;
+constexpr int F3_LN_WARPS = 4, F3_MID_WARPS = 16, F3_FIN_WARPS = 4;
+constexpr int F3_W_MID0 = F3_LN_WARPS;                       // first mid warp (multiple of 4: warp % 4 = TMEM lane quarter)
+constexpr int F3_W_FIN0 = F3_W_MID0 + F3_MID_WARPS;          // 20
+constexpr int F3_W_MMA1 = F3_W_FIN0 + F3_FIN_WARPS;          // 24
+constexpr int F3_W_MMA2 = F3_W_MMA1 + 1;                     // 25
+constexpr int F3_W_COPY = F3_W_MMA2 + 1;                     // 26
+constexpr int F3_THREADS = (F3_W_COPY + 1) * 32;             // 864
+constexpr int F3_WBLK = 2 * 64 * 128;                        // 16 KB: hi|lo image of a 64-row x 64-k weight block
+constexpr int F3_XSLOT = BM * 256;                           // 32 KB: raw fp32 rows of one tile (16-byte chunks XOR-swizzled by row & 7)
+constexpr int F3_TAB_FLOATS = 256 + 5 * 64 + 2 * BM;         // b1 | b2 | ln_g | ln_b | pn_g | pn_b | (mean, rstd) per row
+constexpr int F3_SMEM = 1024 + 8 * F3_WBLK + 2 * F3_XSLOT + F3_TAB_FLOATS * 4;
+// TMEM columns
+constexpr uint32_t F3_XA = 0, F3_ACC1 = 128, F3_H = 256, F3_ACC2 = 384;
 
-__global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_kernel(const FfnArgs a) {
+namespace ptx {
+__device__ __forceinline__ void mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+}  // namespace ptx
+
+__device__ __forceinline__ float4 lds4(const uint8_t* p) { return *reinterpret_cast<const float4*>(p); }
+
+// swish of 16 accumulator columns (+ bias) -> 8 packed bf16 hi columns + 8 packed lo columns
+__device__ __forceinline__ void swish_split16(const uint32_t (&r)[16], const float* bias, uint32_t* hi, uint32_t* lo) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 b = *reinterpret_cast<const float4*>(bias + 4 * j);
+    float v0 = __uint_as_float(r[4 * j]) + b.x, v1 = __uint_as_float(r[4 * j + 1]) + b.y;
+    float v2 = __uint_as_float(r[4 * j + 2]) + b.z, v3 = __uint_as_float(r[4 * j + 3]) + b.w;
+    v0 *= sigmoidf_acc(v0); v1 *= sigmoidf_acc(v1); v2 *= sigmoidf_acc(v2); v3 *= sigmoidf_acc(v3);
+    split_bf16x2(v0, v1, hi[2 * j], lo[2 * j]);
+    split_bf16x2(v2, v3, hi[2 * j + 1], lo[2 * j + 1]);
+  }
+}
+
+__global__ void __launch_bounds__(F3_THREADS, 1) ffn_fused_kernel(const FfnArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t a_full[2], a_empty[2], w_full, w2_full[2], w2_empty[2], acc1_full[2], acc1_empty[2], h_full, h_empty, x_full, x_empty, acc2_full[2], acc2_empty[2];
+  __shared__ uint64_t w_full, x_full[2], x_empty[2], xa_full[2], xa_empty[2], acc1_full[2], acc1_empty[2], h_full[2], h_empty[2],
+      acc2_full[2], acc2_empty[2];
   __shared__ uint32_t tmem_base_s;
-  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (STS/LDS, not generic ST/LD)
-  uint8_t* sA = smem;                           // [2][hi | lo]            64 KB
-  uint8_t* sW1 = sA + 4 * FF_PLANE;             // 4 blocks x (hi | lo)    64 KB  resident
-  uint8_t* sW2 = sW1 + 4 * FF_WBLK;             // 2-slot ring of (hi | lo) blocks   32 KB  (streamed: 64 KB per tile from L2)
-  uint8_t* sH = sW2 + 2 * FF_WBLK;              // [hi | lo]               32 KB  (doubles as the fp32 staging tile of the final store)
-  uint8_t* sX = sH + 2 * FF_PLANE;              // raw fp32 rows of the tile the loaders work on   32 KB
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space
+  uint8_t* sW1 = smem;                          // 4 blocks x (hi | lo)   64 KB  resident
+  uint8_t* sW2 = sW1 + 4 * F3_WBLK;             // 4 blocks x (hi | lo)   64 KB  resident
+  uint8_t* sX = sW2 + 4 * F3_WBLK;              // [2] raw fp32 tiles     64 KB
+  float* sTab = reinterpret_cast<float*>(sX + 2 * F3_XSLOT);
+  float* sB1 = sTab; float* sB2 = sTab + 256; float* sG = sTab + 320; float* sBt = sTab + 384; float* sPG = sTab + 448; float* sPB = sTab + 512;
+  float2* sStat = reinterpret_cast<float2*>(sTab + 576);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ntiles = (a.M + BM - 1) / BM;
   const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const bool post = a.pn_g != nullptr;
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(&acc1_full[i], 1); ptx::mbar_init(&acc1_empty[i], FF_EPI_WARPS * 32);
-      ptx::mbar_init(&acc2_full[i], 1); ptx::mbar_init(&acc2_empty[i], FF_EPI_WARPS * 32);
-    }
-    ptx::mbar_init(&h_full, FF_EPI_WARPS * 32); ptx::mbar_init(&h_empty, 1);
-    ptx::mbar_init(&x_full, 1); ptx::mbar_init(&x_empty, FF_LOAD_WARPS * 32);
-    for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(&a_full[i], FF_LOAD_WARPS * 32); ptx::mbar_init(&a_empty[i], 1);
-      ptx::mbar_init(&w2_full[i], 1); ptx::mbar_init(&w2_empty[i], 1);
-    }
     ptx::mbar_init(&w_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&x_full[i], 32);                         ptx::mbar_init(&x_empty[i], F3_FIN_WARPS * 32);
+      ptx::mbar_init(&xa_full[i], F3_LN_WARPS * 32);          ptx::mbar_init(&xa_empty[i], 1);
+      ptx::mbar_init(&acc1_full[i], 1);                       ptx::mbar_init(&acc1_empty[i], (F3_MID_WARPS / 2) * 32);
+      ptx::mbar_init(&h_full[i], (F3_MID_WARPS / 2) * 32);    ptx::mbar_init(&h_empty[i], 1);
+      ptx::mbar_init(&acc2_full[i], 1);                       ptx::mbar_init(&acc2_empty[i], F3_FIN_WARPS * 32);
+    }
     ptx::fence_barrier_init();
   }
-  if (warp == FF_LOAD_WARPS + FF_EPI_WARPS) ptx::tmem_alloc(&tmem_base_s, 256);
+  for (int i = tid; i < 576; i += F3_THREADS) {
+    float v;
+    if (i < 256) v = a.b1[i];
+    else if (i < 320) v = a.b2[i - 256];
+    else if (i < 384) v = a.ln_g[i - 320];
+    else if (i < 448) v = a.ln_b[i - 384];
+    else if (i < 512) v = post ? a.pn_g[i - 448] : 1.f;
+    else v = post ? a.pn_b[i - 512] : 0.f;
+    sTab[i] = v;
+  }
+  if (warp == F3_W_MMA1) ptx::tmem_alloc(&tmem_base_s, 512);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = tmem_base_s;     // acc1[b] at column 64 b, acc2[b] at column 128 + 64 b
+  const uint32_t tmem_base = tmem_base_s;
 
-  if (warp < FF_LOAD_WARPS) {
-    // ================= loaders: staged x rows -> LayerNorm -> bf16 hi/lo -> swizzled A[s] =================
-    const int sub = tid & 7, rloc = tid >> 3;          // 16 rows per pass, 8 passes; 8 adjacent lanes own one row
-    const float4 g0 = ldg4(a.ln_g + sub * 8), g1 = ldg4(a.ln_g + sub * 8 + 4);
-    const float4 b0 = ldg4(a.ln_b + sub * 8), b1 = ldg4(a.ln_b + sub * 8 + 4);
+  if (warp < F3_LN_WARPS) {
+    // ================= LayerNorm warps: thread = row; staged x row -> LN -> bf16 hi|lo -> XA[s] in TMEM =================
+    const int row = tid, sw = row & 7;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
     for (int it = 0; it < my_tiles; ++it) {
-      const int m0 = ((int)blockIdx.x + it * (int)gridDim.x) * BM;
-      // pull the residual rows of the NEXT tile (read by the final epilogue) into L2 while this tile is processed
-      if (it + 1 < my_tiles && a.resid2 && a.resid2 != a.x) {
-        const long long nrow = (long long)m0 + (long long)gridDim.x * BM + tid;
-        if (nrow < (long long)a.M) {
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.resid2 + nrow * 64));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.resid2 + nrow * 64 + 32));
-        }
-      }
       const int s = it & 1;
-      ptx::mbar_wait(&x_full, (uint32_t)it & 1u);
-      ptx::mbar_wait(&a_empty[s], ((uint32_t)(it >> 1) & 1u) ^ 1u);
-      uint8_t* dA = sA + s * 2 * FF_PLANE;
+      const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+      const uint8_t* xr = sX + s * F3_XSLOT + row * 256;
+      ptx::mbar_wait(&x_full[s], ph);
+      // pass A: shifted one-pass statistics (shift = first element of the row; exact for constant rows)
+      float sum = 0.f, sq = 0.f;
+      const float x0 = lds4(xr + ((0 ^ sw) << 4)).x;
 #pragma unroll
-      for (int p = 0; p < 8; ++p) {
-        const int r = p * 16 + rloc;
-        float v[8];
-        {
-          const float4 x0 = *reinterpret_cast<const float4*>(sX + r * 256 + sub * 32);
-          const float4 x1 = *reinterpret_cast<const float4*>(sX + r * 256 + sub * 32 + 16);
-          v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
-        }
-        if (m0 + r >= a.M) {        // rows past the end of the tensor were not staged: keep the operand finite
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = 0.f;
-        }
-        float sm = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
-        sm += __shfl_xor_sync(0xffffffffu, sm, 1);
-        sm += __shfl_xor_sync(0xffffffffu, sm, 2);
-        sm += __shfl_xor_sync(0xffffffffu, sm, 4);
-        const float mean = sm * (1.0f / 64.0f);
-        float qv = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { v[i] -= mean; qv = fmaf(v[i], v[i], qv); }
-        qv += __shfl_xor_sync(0xffffffffu, qv, 1);
-        qv += __shfl_xor_sync(0xffffffffu, qv, 2);
-        qv += __shfl_xor_sync(0xffffffffu, qv, 4);
-        const float rstd = 1.0f / sqrtf(qv * (1.0f / 64.0f) + 1e-5f);
-        v[0] = v[0] * rstd * g0.x + b0.x; v[1] = v[1] * rstd * g0.y + b0.y;
-        v[2] = v[2] * rstd * g0.z + b0.z; v[3] = v[3] * rstd * g0.w + b0.w;
-        v[4] = v[4] * rstd * g1.x + b1.x; v[5] = v[5] * rstd * g1.y + b1.y;
-        v[6] = v[6] * rstd * g1.z + b1.z; v[7] = v[7] * rstd * g1.w + b1.w;
-        uint4 hi, lo;
-        split_bf16x2(v[0], v[1], hi.x, lo.x); split_bf16x2(v[2], v[3], hi.y, lo.y);
-        split_bf16x2(v[4], v[5], hi.z, lo.z); split_bf16x2(v[6], v[7], hi.w, lo.w);
-        const int off = r * 128 + ((sub ^ (r & 7)) << 4);
-        *reinterpret_cast<uint4*>(dA + off) = hi;
-        *reinterpret_cast<uint4*>(dA + FF_PLANE + off) = lo;
+      for (int c = 0; c < 16; ++c) {
+        const float4 v = lds4(xr + ((c ^ sw) << 4));
+        const float d0 = v.x - x0, d1 = v.y - x0, d2 = v.z - x0, d3 = v.w - x0;
+        sum += (d0 + d1) + (d2 + d3);
+        sq = fmaf(d0, d0, sq); sq = fmaf(d1, d1, sq); sq = fmaf(d2, d2, sq); sq = fmaf(d3, d3, sq);
       }
-      ptx::mbar_arrive(&x_empty);               // staged rows consumed: the next tile may land
-      ptx::fence_proxy_async_smem();
-      ptx::mbar_arrive(&a_full[s]);
+      const float md = sum * (1.0f / 64.0f);
+      const float var = fmaxf(sq * (1.0f / 64.0f) - md * md, 0.f);
+      const float rstd = 1.0f / sqrtf(var + 1e-5f);
+      const float mean = x0 + md;
+      ptx::mbar_wait(&xa_empty[s], ph ^ 1u);
+      ptx::tc_fence_after();
+      const uint32_t xa = lane_base + F3_XA + (uint32_t)(s * 64);
+#pragma unroll
+      for (int c16 = 0; c16 < 4; ++c16) {          // 16 k-values -> 8 hi + 8 lo packed columns
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = c16 * 4 + j;
+          const float4 v = lds4(xr + ((c ^ sw) << 4));
+          const float4 gg = *reinterpret_cast<const float4*>(sG + c * 4);
+          const float4 bb = *reinterpret_cast<const float4*>(sBt + c * 4);
+          const float y0 = fmaf((v.x - mean) * rstd, gg.x, bb.x), y1 = fmaf((v.y - mean) * rstd, gg.y, bb.y);
+          const float y2 = fmaf((v.z - mean) * rstd, gg.z, bb.z), y3 = fmaf((v.w - mean) * rstd, gg.w, bb.w);
+          split_bf16x2(y0, y1, hi[2 * j], lo[2 * j]);
+          split_bf16x2(y2, y3, hi[2 * j + 1], lo[2 * j + 1]);
+        }
+        ptx::tmem_st8(xa + (uint32_t)(c16 * 8), hi);
+        ptx::tmem_st8(xa + 32u + (uint32_t)(c16 * 8), lo);
+      }
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&xa_full[s]);
     }
-  } else if (warp < FF_LOAD_WARPS + FF_EPI_WARPS) {
-    // ================= epilogue warps =================
-    const int ew = warp - FF_LOAD_WARPS;                // 0..15
-    const int wq = warp & 3, cg = ew >> 2;              // TMEM lane quarter (hardware: warp % 4), column group
-    const int row = wq * 32 + lane;
-    const int cq = lane & 15;
-    const float4 b2 = ldg4(a.b2 + cq * 4);
-    float4 pg = make_float4(0, 0, 0, 0), pb = pg;
-    if (a.pn_g) { pg = ldg4(a.pn_g + cq * 4); pb = ldg4(a.pn_b + cq * 4); }
-    float4* stg = reinterpret_cast<float4*>(sH);        // [128 rows][16 x float4], chunk index XOR (row & 7)
+  } else if (warp < F3_W_FIN0) {
+    // ================= mid-epilogue warps: ACC1[g] -> +b1 -> swish -> bf16 hi|lo -> H[g] (TMEM) =================
+    const int e = warp - F3_W_MID0;
+    const int wq = e & 3, g = (e >> 2) & 1, hf = e >> 3;          // lane quarter, chunk parity handled, column half
+    const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16);
+    const uint32_t t_acc = lane_base + F3_ACC1 + (uint32_t)(g * 64 + hf * 32);
+    const uint32_t t_h = lane_base + F3_H + (uint32_t)(g * 64 + hf * 16);
+    for (int it = 0; it < my_tiles; ++it) {
+#pragma unroll 1
+      for (int qq = 0; qq < 2; ++qq) {
+        const int q = 2 * qq + g;
+        const uint32_t u = (uint32_t)(2 * it + qq);               // use count of ACC1[g] / H[g]
+        const float* bias = sB1 + q * 64 + hf * 32;
+        ptx::mbar_wait(&acc1_full[g], u & 1u);
+        ptx::tc_fence_after();
+        uint32_t r0[16], r1[16];
+        ptx::tmem_ld16_nowait(t_acc, r0);
+        ptx::tmem_ld16_nowait(t_acc + 16u, r1);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&acc1_empty[g]);
+        uint32_t hi[16], lo[16];
+        swish_split16(r0, bias, hi, lo);
+        swish_split16(r1, bias + 16, hi + 8, lo + 8);
+        ptx::mbar_wait(&h_empty[g], (u & 1u) ^ 1u);
+        ptx::tc_fence_after();
+        ptx::tmem_st8(t_h, hi);
+        ptx::tmem_st8(t_h + 8u, hi + 8);
+        ptx::tmem_st8(t_h + 32u, lo);
+        ptx::tmem_st8(t_h + 40u, lo + 8);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&h_full[g]);
+      }
+    }
+  } else if (warp < F3_W_MMA1) {
+    // ================= final warps: thread = row; ACC2 -> *alpha + b2 + x -> (post-norm statistics) -> coalesced store =================
+    const int fw = warp - F3_W_FIN0;
+    const int row = fw * 32 + lane, sw = row & 7;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(fw * 32) << 16);
+    const int cc = lane & 15;                                     // 16-byte chunk handled in the copy-out
+    const float4 pg = *reinterpret_cast<const float4*>(sPG + cc * 4), pb = *reinterpret_cast<const float4*>(sPB + cc * 4);
     for (int it = 0; it < my_tiles; ++it) {
       const int m0 = ((int)blockIdx.x + it * (int)gridDim.x) * BM;
-      const int ab = it & 1;
-      // ---- mid epilogues: acc1 -> +b1 -> swish -> H operand (K-chunk q of GEMM 2)
-#pragma unroll 1
-      for (int q = 0; q < 4; ++q) {
-        const int b = q & 1;
-        const uint32_t u1 = (uint32_t)(2 * it + (q >> 1));
-        const float* bias = a.b1 + q * 64 + cg * FF_CPT;
-        float4 bb[FF_CPT / 4];
-#pragma unroll
-        for (int j = 0; j < FF_CPT / 4; ++j) bb[j] = ldg4(bias + 4 * j);
-        ptx::mbar_wait(&acc1_full[b], u1 & 1u);
-        ptx::tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(b * 64 + cg * FF_CPT);
-        float v[FF_CPT];
-#pragma unroll
-        for (int j = 0; j < FF_CPT; j += 8) {
-          float t8[8];
-          ptx::tmem_ld8(taddr + j, t8);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[j + i] = t8[i];
+      const int s = it & 1, ab = it & 1;
+      const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+      uint8_t* xs = sX + s * F3_XSLOT;
+      uint8_t* xr = xs + row * 256;
+      // the residual rows of this tile are consumed by the copy-out below: start pulling them into L2 now
+      if (post && a.resid2 != a.x) {
+        const long long mrow = (long long)m0 + row;
+        if (mrow < (long long)a.M) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.resid2 + mrow * 64));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.resid2 + mrow * 64 + 32));
         }
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(&acc1_empty[b]);
-#pragma unroll
-        for (int j = 0; j < FF_CPT / 4; ++j) { v[4 * j] += bb[j].x; v[4 * j + 1] += bb[j].y; v[4 * j + 2] += bb[j].z; v[4 * j + 3] += bb[j].w; }
-#pragma unroll
-        for (int j = 0; j < FF_CPT; ++j) v[j] *= sigmoidf_acc(v[j]);
-        uint8_t* dH = sH;                                     // single H buffer; its use count is 4 * it + q
-        const uint32_t uh = (uint32_t)(4 * it + q);
-        ptx::mbar_wait(&h_empty, (uh & 1u) ^ 1u);
-#pragma unroll
-        for (int c8 = 0; c8 < FF_CPT / 8; ++c8) {
-          uint4 hi, lo;
-          split_bf16x2(v[c8 * 8 + 0], v[c8 * 8 + 1], hi.x, lo.x); split_bf16x2(v[c8 * 8 + 2], v[c8 * 8 + 3], hi.y, lo.y);
-          split_bf16x2(v[c8 * 8 + 4], v[c8 * 8 + 5], hi.z, lo.z); split_bf16x2(v[c8 * 8 + 6], v[c8 * 8 + 7], hi.w, lo.w);
-          const int c = cg * (FF_CPT / 8) + c8;
-          const int off = row * 128 + ((c ^ (row & 7)) << 4);
-          *reinterpret_cast<uint4*>(dH + off) = hi;
-          *reinterpret_cast<uint4*>(dH + FF_PLANE + off) = lo;
-        }
-        ptx::fence_proxy_async_smem();
-        ptx::mbar_arrive(&h_full);
       }
-      // ---- final epilogue: acc2 -> staging (H buffer: every MMA2 of this tile has completed) -> coalesced store
-      // issue the residual loads first: they do not depend on the accumulator
-      float4 xv[128 / (FF_EPI_WARPS * 2)], r2v[128 / (FF_EPI_WARPS * 2)];
-#pragma unroll
-      for (int i8 = 0; i8 < 128 / (FF_EPI_WARPS * 2); ++i8) {
-        const int m = m0 + i8 * (FF_EPI_WARPS * 2) + ew * 2 + (lane >> 4);
-        const bool ok = m < a.M;
-        xv[i8] = ok ? *reinterpret_cast<const float4*>(a.x + (long long)m * 64 + cq * 4) : make_float4(0, 0, 0, 0);
-        r2v[i8] = (ok && a.pn_g) ? *reinterpret_cast<const float4*>(a.resid2 + (long long)m * 64 + cq * 4) : make_float4(0, 0, 0, 0);
-      }
-      ptx::mbar_wait(&acc2_full[ab], (uint32_t)(it >> 1) & 1u);
+      ptx::mbar_wait(&acc2_full[ab], ph);
       ptx::tc_fence_after();
-      {
-        const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(128 + ab * 64 + cg * FF_CPT);
+      const uint32_t t_acc = lane_base + F3_ACC2 + (uint32_t)(ab * 64);
+      float y0s = 0.f, sum = 0.f, sq = 0.f;
 #pragma unroll
-        for (int j = 0; j < FF_CPT; j += 8) {
-          float t8[8];
-          ptx::tmem_ld8(taddr + j, t8);
-          const int c0 = cg * (FF_CPT / 4) + (j >> 2);
-          stg[row * 16 + ((c0 + 0) ^ (row & 7))] = make_float4(t8[0], t8[1], t8[2], t8[3]);
-          stg[row * 16 + ((c0 + 1) ^ (row & 7))] = make_float4(t8[4], t8[5], t8[6], t8[7]);
+      for (int c16 = 0; c16 < 4; ++c16) {
+        uint32_t r[16];
+        ptx::tmem_ld16_nowait(t_acc + (uint32_t)(c16 * 16), r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = c16 * 4 + j;
+          uint8_t* p = xr + ((c ^ sw) << 4);
+          const float4 xv = lds4(p);
+          const float4 b2 = *reinterpret_cast<const float4*>(sB2 + c * 4);
+          float4 y;
+          y.x = fmaf(a.alpha, __uint_as_float(r[4 * j]) + b2.x, xv.x);
+          y.y = fmaf(a.alpha, __uint_as_float(r[4 * j + 1]) + b2.y, xv.y);
+          y.z = fmaf(a.alpha, __uint_as_float(r[4 * j + 2]) + b2.z, xv.z);
+          y.w = fmaf(a.alpha, __uint_as_float(r[4 * j + 3]) + b2.w, xv.w);
+          if (c == 0) y0s = y.x;
+          const float d0 = y.x - y0s, d1 = y.y - y0s, d2 = y.z - y0s, d3 = y.w - y0s;
+          sum += (d0 + d1) + (d2 + d3);
+          sq = fmaf(d0, d0, sq); sq = fmaf(d1, d1, sq); sq = fmaf(d2, d2, sq); sq = fmaf(d3, d3, sq);
+          *reinterpret_cast<float4*>(p) = y;
         }
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&acc2_empty[ab]);
-      asm volatile("bar.sync 1, %0;" ::"n"(FF_EPI_THREADS) : "memory");
-#pragma unroll
-      for (int i8 = 0; i8 < 128 / (FF_EPI_WARPS * 2); ++i8) {
-        const int R = i8 * (FF_EPI_WARPS * 2) + ew * 2 + (lane >> 4);
-        const int m = m0 + R;
-        const bool ok = m < a.M;
-        const float4 acc = stg[R * 16 + (cq ^ (R & 7))];
-        float4 y;
-        y.x = fmaf(a.alpha, acc.x + b2.x, xv[i8].x); y.y = fmaf(a.alpha, acc.y + b2.y, xv[i8].y);
-        y.z = fmaf(a.alpha, acc.z + b2.z, xv[i8].z); y.w = fmaf(a.alpha, acc.w + b2.w, xv[i8].w);
-        if (a.pn_g) {       // post_norm + outer residual (uniform branch)
-          float sm = y.x + y.y + y.z + y.w;
-#pragma unroll
-          for (int o = 1; o < 16; o <<= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
-          const float mean = sm * (1.0f / 64.0f);
-          y.x -= mean; y.y -= mean; y.z -= mean; y.w -= mean;
-          float qv = y.x * y.x + y.y * y.y + y.z * y.z + y.w * y.w;
-#pragma unroll
-          for (int o = 1; o < 16; o <<= 1) qv += __shfl_xor_sync(0xffffffffu, qv, o);
-          const float rstd = 1.0f / sqrtf(qv * (1.0f / 64.0f) + 1e-5f);
-          y.x = y.x * rstd * pg.x + pb.x + r2v[i8].x; y.y = y.y * rstd * pg.y + pb.y + r2v[i8].y;
-          y.z = y.z * rstd * pg.z + pb.z + r2v[i8].z; y.w = y.w * rstd * pg.w + pb.w + r2v[i8].w;
-        }
-        if (ok) st4(a.out + (long long)m * 64 + cq * 4, y);
+      {
+        const float md = sum * (1.0f / 64.0f);
+        const float var = fmaxf(sq * (1.0f / 64.0f) - md * md, 0.f);
+        sStat[row] = make_float2(y0s + md, 1.0f / sqrtf(var + 1e-5f));
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(FF_EPI_THREADS) : "memory");     // staging tile is overwritten by the next tile's H chunk
-    }
-  } else if (warp == FF_LOAD_WARPS + FF_EPI_WARPS) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      const uint32_t uA = ptx::smem_u32(sA), uW1 = ptx::smem_u32(sW1), uH = ptx::smem_u32(sH), uW2 = ptx::smem_u32(sW2);
-      auto gemm64 = [&](uint32_t d_tmem, uint32_t a_base, uint32_t w_base, bool fresh) {
-        const uint64_t a_hi = ptx::umma_desc_sw128(a_base), a_lo = ptx::umma_desc_sw128(a_base + FF_PLANE);
-        const uint64_t w_hi = ptx::umma_desc_sw128(w_base), w_lo = ptx::umma_desc_sw128(w_base + 64 * 128);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t ko = (uint64_t)((k * 32) >> 4);
-          ptx::mma_bf16(d_tmem, a_lo + ko, w_hi + ko, IDESC, (fresh && k == 0) ? 0u : 1u);
-          ptx::mma_bf16(d_tmem, a_hi + ko, w_lo + ko, IDESC, 1u);
-          ptx::mma_bf16(d_tmem, a_hi + ko, w_hi + ko, IDESC, 1u);
+      __syncwarp();
+      // coalesced copy-out of this warp's 32 rows: half a warp per row, one 16-byte chunk per lane
+#pragma unroll 4
+      for (int i = 0; i < 16; ++i) {
+        const int rr = fw * 32 + 2 * i + (lane >> 4);
+        const int m = m0 + rr;
+        float4 y = lds4(xs + rr * 256 + ((cc ^ (rr & 7)) << 4));
+        if (post) {
+          const float2 st = sStat[rr];
+          float4 r2 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (m < a.M) r2 = *reinterpret_cast<const float4*>(a.resid2 + (long long)m * 64 + cc * 4);
+          y.x = fmaf((y.x - st.x) * st.y, pg.x, pb.x) + r2.x; y.y = fmaf((y.y - st.x) * st.y, pg.y, pb.y) + r2.y;
+          y.z = fmaf((y.z - st.x) * st.y, pg.z, pb.z) + r2.z; y.w = fmaf((y.w - st.x) * st.y, pg.w, pb.w) + r2.w;
         }
-      };
+        if (m < a.M) st4(a.out + (long long)m * 64 + cc * 4, y);
+      }
+      __syncwarp();
+      ptx::mbar_arrive(&x_empty[s]);            // this thread's reads of the staging slot are done
+    }
+  } else if (warp == F3_W_MMA1) {
+    // ================= GEMM 1 issuer: ACC1[g] = XA[s] . W1[q]^T =================
+    if (lane == 0 && my_tiles > 0) {
+      constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t uW1 = ptx::smem_u32(sW1);
       ptx::mbar_wait(&w_full, 0);
       for (int it = 0; it < my_tiles; ++it) {
-        const int s = it & 1, ab = it & 1;
-        auto mma1 = [&](int q) {
-          const uint32_t u1 = (uint32_t)(2 * it + (q >> 1));
-          ptx::mbar_wait(&acc1_empty[q & 1], (u1 & 1u) ^ 1u);
-          ptx::tc_fence_after();
-          gemm64(tmem_base + (uint32_t)((q & 1) * 64), uA + s * 2 * FF_PLANE, uW1 + q * FF_WBLK, true);
-          ptx::tc_commit(&acc1_full[q & 1]);
-          if (q == 3) ptx::tc_commit(&a_empty[s]);
-        };
-        auto mma2 = [&](int q) {
-          const uint32_t u1 = (uint32_t)(2 * it + (q >> 1));      // use count of W2 ring slot q & 1
-          ptx::mbar_wait(&h_full, (uint32_t)(4 * it + q) & 1u);
-          ptx::mbar_wait(&w2_full[q & 1], u1 & 1u);
-          ptx::tc_fence_after();
-          gemm64(tmem_base + 128u + (uint32_t)(ab * 64), uH, uW2 + (q & 1) * FF_WBLK, q == 0);
-          ptx::tc_commit(&h_empty);
-          ptx::tc_commit(&w2_empty[q & 1]);
-          if (q == 3) ptx::tc_commit(&acc2_full[ab]);
-        };
-        ptx::mbar_wait(&a_full[s], (uint32_t)(it >> 1) & 1u);
-        ptx::mbar_wait(&acc2_empty[ab], ((uint32_t)(it >> 1) & 1u) ^ 1u);
-        ptx::tc_fence_after();
-        mma1(0);
+        const int s = it & 1;
+        ptx::mbar_wait(&xa_full[s], (uint32_t)(it >> 1) & 1u);
         for (int q = 0; q < 4; ++q) {
-          if (q < 3) mma1(q + 1);
-          mma2(q);
+          const int g = q & 1;
+          const uint32_t u = (uint32_t)(2 * it + (q >> 1));
+          ptx::mbar_wait(&acc1_empty[g], (u & 1u) ^ 1u);
+          ptx::tc_fence_after();
+          const uint32_t d = tmem_base + F3_ACC1 + (uint32_t)(g * 64);
+          const uint32_t a_hi = tmem_base + F3_XA + (uint32_t)(s * 64), a_lo = a_hi + 32u;
+          const uint64_t w_hi = ptx::umma_desc_sw128(uW1 + q * F3_WBLK), w_lo = ptx::umma_desc_sw128(uW1 + q * F3_WBLK + 64 * 128);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ko = (uint64_t)((k * 32) >> 4);
+            ptx::mma_bf16_ts(d, a_lo + (uint32_t)(k * 8), w_hi + ko, IDESC, k == 0 ? 0u : 1u);
+            ptx::mma_bf16_ts(d, a_hi + (uint32_t)(k * 8), w_lo + ko, IDESC, 1u);
+            ptx::mma_bf16_ts(d, a_hi + (uint32_t)(k * 8), w_hi + ko, IDESC, 1u);
+          }
+          ptx::tc_commit(&acc1_full[g]);
+          if (q == 3) ptx::tc_commit(&xa_empty[s]);
         }
       }
     }
-  } else if (warp == FF_LOAD_WARPS + FF_EPI_WARPS + 2) {
-    // ================= x staging: one bulk copy per tile (rows are contiguous in HBM) =================
-    if (lane == 0) {
+  } else if (warp == F3_W_MMA2) {
+    // ================= GEMM 2 issuer: ACC2[ab] += H[g] . W2[:, q]^T =================
+    if (lane == 0 && my_tiles > 0) {
+      constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t uW2 = ptx::smem_u32(sW2);
+      ptx::mbar_wait(&w_full, 0);
       for (int it = 0; it < my_tiles; ++it) {
-        const int m0 = ((int)blockIdx.x + it * (int)gridDim.x) * BM;
-        const int rows = (a.M - m0 < BM) ? a.M - m0 : BM;
-        ptx::mbar_wait(&x_empty, ((uint32_t)it & 1u) ^ 1u);
-        ptx::mbar_arrive_expect_tx(&x_full, (uint32_t)rows * 256u);
-        ptx::bulk_g2s(ptx::smem_u32(sX), a.x + (long long)m0 * 64, (uint32_t)rows * 256u, &x_full);
+        const int ab = it & 1;
+        for (int q = 0; q < 4; ++q) {
+          const int g = q & 1;
+          const uint32_t u = (uint32_t)(2 * it + (q >> 1));
+          if (q == 0) ptx::mbar_wait(&acc2_empty[ab], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+          ptx::mbar_wait(&h_full[g], u & 1u);
+          ptx::tc_fence_after();
+          const uint32_t d = tmem_base + F3_ACC2 + (uint32_t)(ab * 64);
+          const uint32_t a_hi = tmem_base + F3_H + (uint32_t)(g * 64), a_lo = a_hi + 32u;
+          const uint64_t w_hi = ptx::umma_desc_sw128(uW2 + q * F3_WBLK), w_lo = ptx::umma_desc_sw128(uW2 + q * F3_WBLK + 64 * 128);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ko = (uint64_t)((k * 32) >> 4);
+            ptx::mma_bf16_ts(d, a_lo + (uint32_t)(k * 8), w_hi + ko, IDESC, (q == 0 && k == 0) ? 0u : 1u);
+            ptx::mma_bf16_ts(d, a_hi + (uint32_t)(k * 8), w_lo + ko, IDESC, 1u);
+            ptx::mma_bf16_ts(d, a_hi + (uint32_t)(k * 8), w_hi + ko, IDESC, 1u);
+          }
+          ptx::tc_commit(&h_empty[g]);
+          if (q == 3) ptx::tc_commit(&acc2_full[ab]);
+        }
       }
     }
   } else {
-    // ================= weights: loaded once, resident for the whole kernel =================
-    if (lane == 0 && my_tiles > 0) {
-      ptx::mbar_arrive_expect_tx(&w_full, 4 * FF_WBLK);           // W1: loaded once, resident
-      for (int q = 0; q < 4; ++q) ptx::bulk_g2s(ptx::smem_u32(sW1) + q * FF_WBLK, a.w1 + (size_t)q * FF_WBLK, FF_WBLK, &w_full);
-      for (int it = 0; it < my_tiles; ++it) {                     // W2: block q of every tile through the 2-slot ring
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t u = (uint32_t)(2 * it + (q >> 1));
-          ptx::mbar_wait(&w2_empty[q & 1], (u & 1u) ^ 1u);
-          ptx::mbar_arrive_expect_tx(&w2_full[q & 1], FF_WBLK);
-          ptx::bulk_g2s(ptx::smem_u32(sW2) + (q & 1) * FF_WBLK, a.w2 + (size_t)q * FF_WBLK, FF_WBLK, &w2_full[q & 1]);
+    // ================= copy warp: resident weights once, then the raw rows of every tile (swizzled 16-byte chunks) =================
+    if (my_tiles > 0) {
+      if (lane == 0) {
+        ptx::mbar_arrive_expect_tx(&w_full, 8 * F3_WBLK);
+        for (int q = 0; q < 4; ++q) ptx::bulk_g2s(ptx::smem_u32(sW1) + q * F3_WBLK, a.w1 + (size_t)q * F3_WBLK, F3_WBLK, &w_full);
+        for (int q = 0; q < 4; ++q) ptx::bulk_g2s(ptx::smem_u32(sW2) + q * F3_WBLK, a.w2 + (size_t)q * F3_WBLK, F3_WBLK, &w_full);
+      }
+      for (int it = 0; it < my_tiles; ++it) {
+        const int m0 = ((int)blockIdx.x + it * (int)gridDim.x) * BM;
+        const int s = it & 1;
+        ptx::mbar_wait(&x_empty[s], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+        const uint32_t dst0 = ptx::smem_u32(sX) + s * F3_XSLOT;
+#pragma unroll 8
+        for (int k = 0; k < 64; ++k) {
+          const int i = k * 32 + lane, r = i >> 4, c = i & 15;
+          const int m = m0 + r;
+          const int mc = m < a.M ? m : a.M - 1;
+          ptx::cp_async16_zfill(dst0 + r * 256 + ((c ^ (r & 7)) << 4), a.x + (long long)mc * 64 + c * 4, m < a.M ? 16u : 0u);
         }
+        ptx::cp_async_mbar_arrive(&x_full[s]);
       }
     }
   }
   __syncthreads();
-  if (warp == FF_LOAD_WARPS + FF_EPI_WARPS) {
+  if (warp == F3_W_MMA1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 256);
+    ptx::tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -335,7 +392,7 @@ extern "C" int seb200_ffn_fused(const SebFfn* f, void* stream) {
   if (f->post_gamma) SEB_REQUIRE(f->post_beta && f->resid2 && aligned16(f->resid2), SEB_EINVAL, "ffn_fused: post-norm needs beta and resid2");
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(ffn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(ffn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F3_SMEM);
     if (e != cudaSuccess) { set_error("ffn_fused: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     attr_done = true;
   }
@@ -352,7 +409,7 @@ extern "C" int seb200_ffn_fused(const SebFfn* f, void* stream) {
   }
   const long long ntiles = (f->tokens + BM - 1) / BM;
   const unsigned grid = (unsigned)(ntiles < num_sms ? ntiles : num_sms);      // persistent: one CTA per SM
-  ffn_fused_kernel<<<grid, FF_THREADS, FF_SMEM, (cudaStream_t)stream>>>(a);
+  ffn_fused_kernel<<<grid, F3_THREADS, F3_SMEM, (cudaStream_t)stream>>>(a);
   SEB_CHECK_LAUNCH("ffn_fused_kernel");
   return 0;
 }
