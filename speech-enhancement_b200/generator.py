@@ -192,7 +192,7 @@ class TSCNet(nn.Module):
                 P[f"{p}.attn.qkv"] = pack_weight(wqkv, 192, None).to(device)     # one wide n-tile: splitting N re-reads + re-normalises x (measured 2x slower)
                 P[f"{p}.attn.out"] = pack_weight(sd[f"{p}.attn.fn.to_out.weight"], 64, sd[f"{p}.attn.fn.to_out.bias"]).to(device)
                 P[f"{p}.attn.emb"] = dev(sd[f"{p}.attn.fn.rel_pos_emb.weight"])
-                P[f"{p}.attn.emb_h"] = dev(sd[f"{p}.attn.fn.rel_pos_emb.weight"].to(torch.float16))
+                P[f"{p}.attn.emb_h"] = dev(ops.pack_rel_pos(sd[f"{p}.attn.fn.rel_pos_emb.weight"]))
                 P[f"{p}.attn.ln"] = (dev(sd[f"{p}.attn.norm.weight"]), dev(sd[f"{p}.attn.norm.bias"]))
                 P[f"{p}.conv.ln"] = (dev(sd[f"{p}.conv.net.0.weight"]), dev(sd[f"{p}.conv.net.0.bias"]))
                 w1, b1 = glu_interleave(sd[f"{p}.conv.net.2.weight"].squeeze(-1), sd[f"{p}.conv.net.2.bias"])

@@ -308,20 +308,30 @@ def make_seq(nseq: int, n: int, inner: int, outer_stride: int, pos_stride: int) 
     return s
 
 
+_FRAG_ORDER = [0, 1, 8, 9, 2, 3, 10, 11, 4, 5, 12, 13, 6, 7, 14, 15]
+
+
+def pack_rel_pos(rel_pos_emb: torch.Tensor) -> torch.Tensor:
+    """rel_pos_emb [1025, 16] -> float16 table in MMA-fragment order (what attention variant 0 reads): the four halfs a
+    lane contributes to a B fragment (k = 2t, 2t+1, 2t+8, 2t+9) are adjacent, so it fetches them with one 8-byte load."""
+    return rel_pos_emb.to(torch.float16)[:, _FRAG_ORDER].contiguous()
+
+
 def attention(qkv, rel_pos_emb, seq: SebSeq, out, variant: int = 0, rel_pos_emb_h=None):
-    """variant 0: qkv float16 [tokens, 192] with q pre-scaled (EPI_QKV_F16); variant 1: qkv float32, unscaled."""
+    """variant 0 / 2: qkv float16 [tokens, 192] with q pre-scaled (EPI_QKV_F16) -- 0 is the production kernel, 2 the
+    round-1 kernel kept for A/B measurements; variant 1: qkv float32, unscaled (fp32 SIMT cross-check)."""
     _f32c(rel_pos_emb, out)
     require_cuda(qkv)
-    if variant == 0:
+    if variant in (0, 2):
         if qkv.dtype != torch.float16 or not qkv.is_contiguous():
             raise RuntimeError("tensor-core attention reads the float16 q|k|v projection")
-        if rel_pos_emb_h is None:
-            rel_pos_emb_h = rel_pos_emb.to(torch.float16)
+        if rel_pos_emb_h is None:       # variant 0 reads the fragment-ordered table, variant 2 the plain fp16 copy
+            rel_pos_emb_h = pack_rel_pos(rel_pos_emb) if variant == 0 else rel_pos_emb.to(torch.float16)
         if rel_pos_emb_h.dtype != torch.float16 or not rel_pos_emb_h.is_contiguous():
             raise RuntimeError("rel_pos_emb_h must be a contiguous float16 copy of the embedding table")
     else:
         _f32c(qkv)
-    tok = _pb("attention", 96.0 * 4 * seq.nseq * seq.n * seq.n, (2.0 if variant == 0 else 4.0) * qkv.numel() + 4.0 * out.numel()) if _PROF is not None else None
+    tok = _pb("attention", 96.0 * 4 * seq.nseq * seq.n * seq.n, (4.0 if variant == 1 else 2.0) * qkv.numel() + 4.0 * out.numel()) if _PROF is not None else None
     check(_lib.load().seb200_attention(ptr(qkv), ptr(rel_pos_emb), ptr(rel_pos_emb_h), C.byref(seq), ptr(out), variant, stream_ptr()), "seb200_attention")
     _pe(tok)
     return out

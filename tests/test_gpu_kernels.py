@@ -320,16 +320,16 @@ def _attention_core_ref(qkv_seq, emb):
     return (dots.softmax(-1) @ v).permute(0, 2, 1, 3).reshape(S, n, 64)
 
 
-@pytest.mark.parametrize("variant", [1, 0])
+@pytest.mark.parametrize("variant", [1, 0, 2])
 @pytest.mark.parametrize("axis,B,T,Fh", [("freq", 2, 5, 101), ("time", 1, 150, 3), ("time", 1, 700, 2), ("freq", 1, 3, 64),
-                                          ("time", 1, 1400, 1)])     # 1400 > 2*512 + 128: far-field (clamped) tiles take the constant shortcut
+                                          ("time", 1, 641, 2), ("time", 2, 97, 1), ("time", 1, 1400, 1)])     # 641 = 10 x 64 + 1: the 16-key tail body, 3-warp CTAs; 1400 > 2*512 + 128: far-field (clamped) tiles take the constant shortcut
 def test_attention(variant, axis, B, T, Fh):
     qkv = rnd(B, T, Fh, 192, seed=80, scale=1.5)
     emb = rnd(1025, 16, seed=81)
     seq, to_seq, from_seq = _seq_layouts(B, T, Fh)[axis]
     out = torch.zeros(B * T * Fh, 64, device=DEV)
     inp = qkv.view(-1, 192)
-    if variant == 0:      # what SEB_EPI_QKV_F16 writes: fp16, q pre-scaled by dim_head^-0.5 * log2(e)
+    if variant != 1:      # what SEB_EPI_QKV_F16 writes: fp16, q pre-scaled by dim_head^-0.5 * log2(e)
         inp = torch.cat([inp[:, :64] * (0.25 * 1.4426950408889634), inp[:, 64:]], 1).to(torch.float16).contiguous()
     ops.attention(inp, emb, seq, out, variant)
     ref = from_seq(_attention_core_ref(to_seq(qkv.cpu()), emb.cpu()))
