@@ -117,6 +117,12 @@ __device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], u
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// D = A . B + C with C in its own registers (an accumulator that starts from a per-row constant needs no copies)
+__device__ __forceinline__ void mma_f16_c(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, float c0, float c1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%11,%11};"
+               : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(c0), "f"(c1));
+}
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -487,67 +493,75 @@ __global__ void __launch_bounds__(128, 3) attention_v4_kernel(const __half* __re
     const int b0 = iw - j0 - 63;                            // offset of column dd = 0 for tile 0 (tile 1: + 1)
     const int far = !BAND ? -1 : (b0 >= AT_MAXPOS ? 1 : (b0 + 96 <= -AT_MAXPOS ? 0 : -1));
     float s[2][NT][4];
+    constexpr int NT_LO = (NT == 8) ? 0 : 6;
+    const bool rel = !BAND || far < 0;                       // this tile needs the R GEMM + skew (else: far-field constant)
+    const bool inband = (b0 >= -AT_MAXPOS) && (b0 + 96 <= AT_MAXPOS);
+    // E fragments of tile mt: issued early so that the loads fly under the MMAs in front of their use
+    uint2 ef[12];
+    auto load_e = [&](int mt) {
+      if (inband) {                   // all offsets inside +-512: one base pointer, immediates
+        const uint2* ebase = reinterpret_cast<const uint2*>(Eh + (long long)(b0 + mt + g + AT_MAXPOS) * AT_D) + t;
+#pragma unroll
+        for (int nt = NT_LO; nt < 12; ++nt) ef[nt] = __ldg(ebase + nt * 8 * (AT_D / 4));
+      } else {                        // tile straddles the clamp (conformer.py:108)
+#pragma unroll
+        for (int nt = NT_LO; nt < 12; ++nt) {
+          int d = b0 + mt + nt * 8 + g;
+          d = d < -AT_MAXPOS ? -AT_MAXPOS : (d > AT_MAXPOS ? AT_MAXPOS : d);
+          ef[nt] = __ldg(reinterpret_cast<const uint2*>(Eh + (d + AT_MAXPOS) * AT_D) + t);
+        }
+      }
+    };
+    // R[rho, dd] = q . E[clamp(b0 + mt + dd)], dd in [0, 96) -> fp16, transposed, descending (rows < 8 use n-tiles <= 9, rows >= 8 n-tiles >= 2)
+    auto r_gemm = [&](int mt) {
+#pragma unroll
+      for (int nt = NT_LO; nt < 12; ++nt) {
+        float r4[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_f16(r4, qa[mt], ef[nt].x, ef[nt].y);
+        if (nt < 10) rw_lo[mt * 16 - 4 * nt * A4_PW] = pack_h2(r4[1], r4[0]);
+        if (nt >= 2) rw_lo[mt * 16 + 8 - 4 * nt * A4_PW] = pack_h2(r4[3], r4[2]);
+      }
+    };
+    // skew-add on the tensor pipe: S[:, 16 kb : 16 kb + 16] += A_skew . [I | 0], [0 | I]
+    auto skew_add = [&](int mt) {
+#pragma unroll
+      for (int kb = 0; kb < NKB; ++kb) {
+        const uint32_t* p = rr + mt * 16 + 8 * kb * A4_PW;
+        const uint32_t a[4] = {p[0], p[8 - 8 * A4_PW], p[4 * A4_PW], p[8 - 4 * A4_PW]};
+        mma_f16(s[mt][2 * kb], a, idf, 0u);
+        mma_f16(s[mt][2 * kb + 1], a, 0u, idf);
+      }
+    };
+    if (rel) load_e(0);
     // ---- content scores start from -m (lazy reference maximum) plus the far-field rel-pos constant
+    float cinit[2][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int rh = 0; rh < 2; ++rh) {
+        float c0 = -mrow[mt][rh];
+        if (BAND) c0 += (far == 1 ? c_far[1][mt][rh] : (far == 0 ? c_far[0][mt][rh] : 0.f));
+        cinit[mt][rh] = c0;
+      }
 #pragma unroll
     for (int np = 0; np < NKB; ++np) {
       uint32_t kb[4];
       ldsm_x4(kb, Ks + np * 16 * A2_LD + k_off);
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float c0 = -mrow[mt][e >> 1];
-          if (BAND) c0 += (far == 1 ? c_far[1][mt][e >> 1] : (far == 0 ? c_far[0][mt][e >> 1] : 0.f));
-          s[mt][2 * np][e] = c0; s[mt][2 * np + 1][e] = c0;
-        }
-        mma_f16(s[mt][2 * np], qa[mt], kb[0], kb[1]);
-        mma_f16(s[mt][2 * np + 1], qa[mt], kb[2], kb[3]);
+        mma_f16_c(s[mt][2 * np], qa[mt], kb[0], kb[1], cinit[mt][0], cinit[mt][1]);
+        mma_f16_c(s[mt][2 * np + 1], qa[mt], kb[2], kb[3], cinit[mt][0], cinit[mt][1]);
       }
     }
-    if (!BAND || far < 0) {
-      // ---- R[rho, dd] = q . E[clamp(b0 + mt + dd)], dd in [0, 96): tile 0 / rows < 8 use n-tiles <= 9, rows >= 8 use n-tiles >= 2
-      constexpr int NT_LO = (NT == 8) ? 0 : 6;
-      if ((b0 >= -AT_MAXPOS) && (b0 + 96 <= AT_MAXPOS)) {       // in-band tile: E rows addressed with immediates
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          const uint2* ebase = reinterpret_cast<const uint2*>(Eh + (long long)(b0 + mt + g + AT_MAXPOS) * AT_D) + t;
-          if (mt == 1) asm volatile("" ::: "memory");      // keep tile 1's fragment loads behind tile 0's MMAs (register pressure)
-#pragma unroll
-          for (int nt = NT_LO; nt < 12; ++nt) {
-            const uint2 ef = __ldg(ebase + nt * 8 * (AT_D / 4));
-            float r4[4] = {0.f, 0.f, 0.f, 0.f};
-            mma_f16(r4, qa[mt], ef.x, ef.y);
-            if (nt < 10) rw_lo[mt * 16 - 4 * nt * A4_PW] = pack_h2(r4[1], r4[0]);
-            if (nt >= 2) rw_lo[mt * 16 + 8 - 4 * nt * A4_PW] = pack_h2(r4[3], r4[2]);
-          }
-        }
-      } else {                                                   // tile straddles the +-512 clamp (conformer.py:108): compact loop
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-#pragma unroll 1
-          for (int nt = NT_LO; nt < 12; ++nt) {
-            int d = b0 + mt + nt * 8 + g;
-            d = d < -AT_MAXPOS ? -AT_MAXPOS : (d > AT_MAXPOS ? AT_MAXPOS : d);
-            const uint2 ef = __ldg(reinterpret_cast<const uint2*>(Eh + (d + AT_MAXPOS) * AT_D) + t);
-            float r4[4] = {0.f, 0.f, 0.f, 0.f};
-            mma_f16(r4, qa[mt], ef.x, ef.y);
-            uint32_t* w = rw_lo + mt * 16 - 4 * nt * A4_PW;
-            if (nt < 10) w[0] = pack_h2(r4[1], r4[0]);
-            if (nt >= 2) w[8] = pack_h2(r4[3], r4[2]);
-          }
-        }
-      }
+    if (rel) {
+      r_gemm(0);
+      asm volatile("" ::: "memory");
+      load_e(1);                      // in flight under tile 0's skew-add
       __syncwarp();
-      // ---- skew-add on the tensor pipe: S[:, 16 kb : 16 kb + 16] += A_skew . [I | 0], [0 | I]
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int kb = 0; kb < NKB; ++kb) {
-          const uint32_t* p = rr + mt * 16 + 8 * kb * A4_PW;
-          const uint32_t a[4] = {p[0], p[8 - 8 * A4_PW], p[4 * A4_PW], p[8 - 4 * A4_PW]};
-          mma_f16(s[mt][2 * kb], a, idf, 0u);
-          mma_f16(s[mt][2 * kb + 1], a, 0u, idf);
-        }
+      skew_add(0);
+      r_gemm(1);
+      __syncwarp();
+      skew_add(1);
       __syncwarp();
     }
     if (j0 + NT * 8 > n) {   // mask keys beyond the sequence (last tile only)
