@@ -1,101 +1,155 @@
 // tok_gemm.cu -- persistent tcgen05 GEMM for the token-wise projections of the conformer (K = 64 or 128):
-//   q|k|v projection      LayerNorm -> 64 -> 192, fp16 epilogue            (conformer.py:100-101)
-//   pointwise conv + GLU  LayerNorm -> 64 -> 256 -> a * sigmoid(b)         (conformer.py:162-166)
-// These are HBM-bound (2.7 - 4.2 GB per launch for ~0.1 TFLOP).  The one-tile-per-CTA engine kernel re-fetches the
-// weight image for every 128-token tile and pays launch / barrier-init / TMEM-alloc / first-load latency per tile; here
-// one CTA per SM keeps the whole weight image resident in shared memory, 8 loader warps run ahead through a 3-slot A
-// ring (LayerNorm + bf16 hi/lo split fused, next tile prefetched into L2), one thread issues the MMAs into a double-
-// buffered TMEM accumulator and 16 epilogue warps apply the engine's epilogue functors with coalesced stores.
+//   q|k|v projection        LayerNorm -> 64 -> 192, fp16 epilogue            (conformer.py:100-101)
+//   pointwise conv + GLU    LayerNorm -> 64 -> 256 -> a * sigmoid(b)         (conformer.py:162-166)
+//   attention out-proj      64 -> 64 + bias + residual                       (conformer.py:122-124, 203)
+//   pointwise conv 2        128 -> 64 + bias + residual                      (conformer.py:169, 204)
+// These are HBM-bound (2.7 - 4.2 GB per launch for ~0.1 TFLOP); round-1 profiles had them at 34 - 50 % of the HBM peak
+// because at most one tile's loads were in flight per SM (register-staged loaders) and the A operand made a shared-memory
+// round trip.  v3 follows the fused feed-forward kernel:
+//   copy warp     : cp.async 16-byte chunks of the next tiles' raw fp32 rows into a swizzled staging ring (2 - 3 tiles =
+//                   64 - 128 KB in flight per SM, no registers involved); loads the whole weight image once (resident)
+//   4 row warps   : thread = row.  staged row -> [LayerNorm] -> bf16 hi|lo -> tcgen05.st into XA[s] (tensor memory)
+//   MMA issuer    : ACC[ab] = XA[s] . W^T, A operand from TMEM (`[a_tmem]` form), 3-product split
+//   16 epilogue warps : tcgen05.ld -> warp-private smem transpose -> the engine's epilogue functors, coalesced stores
 #include "gemm_engine.cuh"
 #include <stdlib.h>
 
 namespace seb {
 
-constexpr int TG_LOAD_WARPS = 8, TG_EPI_WARPS = 16, TG_SLOTS = 3;
-constexpr int TG_THREADS = (TG_LOAD_WARPS + TG_EPI_WARPS + 2) * 32;          // 832
-constexpr int TG_ASLOT = 2 * TC_A_BYTES;                                      // 32 KB: hi | lo planes of a 128 x 64 chunk
+constexpr int TG_ROW_WARPS = 4, TG_EPI_WARPS = 16;
+constexpr int TG_W_EPI0 = TG_ROW_WARPS;                                       // multiple of 4: warp % 4 = TMEM lane quarter
+constexpr int TG_W_MMA = TG_W_EPI0 + TG_EPI_WARPS;                            // 20
+constexpr int TG_W_COPY = TG_W_MMA + 1;                                       // 21
+constexpr int TG_THREADS = (TG_W_COPY + 1) * 32;                              // 704
+template <int KCH> constexpr int tg_slots() { return KCH == 1 ? 3 : 2; }
+template <int KCH> constexpr int tg_xslot() { return BM * 64 * KCH * 4; }     // raw fp32 rows of one tile: 32 / 64 KB
 template <int NT, int KCH> constexpr int tg_smem_bytes() {
-  return 1024 + TG_SLOTS * TG_ASLOT + KCH * 2 * NT * 128 + TG_EPI_WARPS * 4096;
+  return 1024 + tg_slots<KCH>() * tg_xslot<KCH>() + KCH * 2 * NT * 128 + TG_EPI_WARPS * 4096 + 2 * 64 * 4;
 }
+
+namespace ptx {
+__device__ __forceinline__ void tg_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tg_tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+}  // namespace ptx
 
 template <int NT, int KCH, int LK, int EK>
 __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs g, const uint8_t* __restrict__ w_tc) {
   static_assert(NT % 64 == 0 && NT <= 256 && (KCH == 1 || KCH == 2), "unsupported token GEMM shape");
+  static_assert(LK == SEB_LOAD_ROWS || (LK == SEB_LOAD_ROWS_LN && KCH == 1), "loader: plain rows, or LayerNorm over 64 features");
+  constexpr int K = 64 * KCH, NSLOT = tg_slots<KCH>(), XSLOT = tg_xslot<KCH>(), PITCH = K * 4, NCH = K / 4;   // 16-byte chunks per row
+  constexpr bool ACC2 = (2 * K + 2 * NT <= 512);                 // double-buffered accumulator when tensor memory has room
+  constexpr uint32_t T_ACC = 2 * K;                              // TMEM: XA[2] (K columns each: hi | lo) | ACC[1 or 2] (NT columns each)
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t a_full[TG_SLOTS], a_empty[TG_SLOTS], w_full, acc_full[2], acc_empty[2];
+  __shared__ uint64_t x_full[NSLOT], x_empty[NSLOT], xa_full[2], xa_empty[2], w_full, acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sA = smem;                                   // ring of A chunks
-  uint8_t* sW = sA + TG_SLOTS * TG_ASLOT;               // [kc][hi | lo][NT rows x 128 B], resident
-  uint8_t* sStg = sW + KCH * 2 * NT * 128;              // 4 KB per epilogue warp
-  constexpr uint32_t TCOLS = (2 * NT <= 128) ? 128 : (2 * NT <= 256 ? 256 : 512);
+  uint8_t* sW = smem;                                   // [kc][hi | lo][NT rows x 128 B], resident
+  uint8_t* sX = sW + KCH * 2 * NT * 128;                // ring of raw fp32 tiles, 16-byte chunk c of row r at r * PITCH + ((c ^ (r & 7)) << 4)
+  uint8_t* sStg = sX + NSLOT * XSLOT;                   // 4 KB per epilogue warp
+  float* sG = reinterpret_cast<float*>(sStg + TG_EPI_WARPS * 4096);
+  float* sBt = sG + 64;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ntiles = (g.M + BM - 1) / BM;
   const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (tid == 0) {
-    for (int i = 0; i < TG_SLOTS; ++i) { ptx::mbar_init(&a_full[i], TG_LOAD_WARPS * 32); ptx::mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], TG_EPI_WARPS * 32); }
+    for (int i = 0; i < NSLOT; ++i) { ptx::mbar_init(&x_full[i], 32); ptx::mbar_init(&x_empty[i], TG_ROW_WARPS * 32); }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&xa_full[i], TG_ROW_WARPS * 32); ptx::mbar_init(&xa_empty[i], 1);
+      ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], TG_EPI_WARPS * 32);
+    }
     ptx::mbar_init(&w_full, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == TG_LOAD_WARPS + TG_EPI_WARPS) ptx::tmem_alloc(&tmem_base_s, TCOLS);
+  if (LK == SEB_LOAD_ROWS_LN && tid < 128) { if (tid < 64) sG[tid] = g.ln_g[tid]; else sBt[tid - 64] = g.ln_b[tid - 64]; }
+  if (warp == TG_W_MMA) ptx::tmem_alloc(&tmem_base_s, 512);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = tmem_base_s;               // accumulator ab at column NT * ab
+  const uint32_t tmem_base = tmem_base_s;
 
-  if (warp < TG_LOAD_WARPS) {
-    // ================= loaders =================
-    const int sub = tid & 7, rloc = tid >> 3;           // 32 rows per pass, 4 passes
-    const long long total = (long long)my_tiles * KCH;
-    for (long long gc = 0; gc < total; ++gc) {
-      const int it = (int)(gc / KCH), kc = (int)(gc - (long long)it * KCH);
-      const int m0 = ((int)blockIdx.x + it * (int)gridDim.x) * BM;
-      const int s = (int)(gc % TG_SLOTS);
-      if (kc == 0 && it + 1 < my_tiles) {               // pull the next tile's rows into L2 (one 128-byte line per thread and chunk)
-        const long long nrow = (long long)(m0 + (int)gridDim.x * BM) + (tid >> 1);
-        if (nrow < g.M) {
-          const float* p = g.a[0] + nrow * g.lda + (tid & 1) * 32;
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-          if (KCH == 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 64));
-          if (EK == SEB_EPI_RESID && g.resid != g.a[0]) asm volatile("prefetch.global.L2 [%0];" ::"l"(g.resid + nrow * g.ldr + (tid & 1) * 32));
-        }
-      }
-      ptx::mbar_wait(&a_empty[s], ((uint32_t)(gc / TG_SLOTS) & 1u) ^ 1u);
-      uint8_t* dA = sA + s * TG_ASLOT;
+  if (warp < TG_ROW_WARPS) {
+    // ================= row warps: thread = row; staged row -> [LayerNorm] -> bf16 hi|lo -> XA[s] (TMEM) =================
+    const int row = tid, sw = row & 7;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int it = 0; it < my_tiles; ++it) {
+      const int slot = it % NSLOT, s2 = it & 1;
+      const uint8_t* xr = sX + slot * XSLOT + row * PITCH;
+      ptx::mbar_wait(&x_full[slot], (uint32_t)(it / NSLOT) & 1u);
+      float mean = 0.f, rstd = 1.f;
+      if (LK == SEB_LOAD_ROWS_LN) {     // shifted one-pass statistics, four partial sums (short dependency chains)
+        float ps[4] = {0.f, 0.f, 0.f, 0.f}, pq[4] = {0.f, 0.f, 0.f, 0.f};
+        const float x0 = reinterpret_cast<const float4*>(xr + ((0 ^ sw) << 4))->x;
 #pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        const int r = p * 32 + rloc;
-        typename Loader<LK>::Row row;
-        Loader<LK>::init_row(g, m0 + r, row);
-        float v[8];
-        Loader<LK>::load(g, row, kc, sub, v);
-        uint4 hi, lo;
-        split_bf16x2(v[0], v[1], hi.x, lo.x); split_bf16x2(v[2], v[3], hi.y, lo.y);
-        split_bf16x2(v[4], v[5], hi.z, lo.z); split_bf16x2(v[6], v[7], hi.w, lo.w);
-        const int off = r * 128 + ((sub ^ (r & 7)) << 4);
-        *reinterpret_cast<uint4*>(dA + off) = hi;
-        *reinterpret_cast<uint4*>(dA + TC_A_BYTES + off) = lo;
+        for (int c = 0; c < NCH; ++c) {
+          const float4 v = *reinterpret_cast<const float4*>(xr + ((c ^ sw) << 4));
+          const float d0 = v.x - x0, d1 = v.y - x0, d2 = v.z - x0, d3 = v.w - x0;
+          ps[c & 3] += (d0 + d1) + (d2 + d3);
+          pq[c & 3] += fmaf(d0, d0, d1 * d1) + fmaf(d2, d2, d3 * d3);
+        }
+        const float md = ((ps[0] + ps[1]) + (ps[2] + ps[3])) * (1.0f / 64.0f);
+        const float var = fmaxf(((pq[0] + pq[1]) + (pq[2] + pq[3])) * (1.0f / 64.0f) - md * md, 0.f);
+        rstd = 1.0f / sqrtf(var + 1e-5f);
+        mean = x0 + md;
       }
-      ptx::fence_proxy_async_smem();
-      ptx::mbar_arrive(&a_full[s]);
+      ptx::mbar_wait(&xa_empty[s2], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+      ptx::tc_fence_after();
+      const uint32_t xa = lane_base + (uint32_t)(s2 * K);
+#pragma unroll
+      for (int c16 = 0; c16 < K / 16; ++c16) {          // 16 k-values -> 8 hi + 8 lo packed columns
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = c16 * 4 + j;
+          float4 v = *reinterpret_cast<const float4*>(xr + ((c ^ sw) << 4));
+          if (LK == SEB_LOAD_ROWS_LN) {
+            const float4 gg = *reinterpret_cast<const float4*>(sG + c * 4);
+            const float4 bb = *reinterpret_cast<const float4*>(sBt + c * 4);
+            v.x = fmaf((v.x - mean) * rstd, gg.x, bb.x); v.y = fmaf((v.y - mean) * rstd, gg.y, bb.y);
+            v.z = fmaf((v.z - mean) * rstd, gg.z, bb.z); v.w = fmaf((v.w - mean) * rstd, gg.w, bb.w);
+          }
+          split_bf16x2(v.x, v.y, hi[2 * j], lo[2 * j]);
+          split_bf16x2(v.z, v.w, hi[2 * j + 1], lo[2 * j + 1]);
+        }
+        ptx::tg_tmem_st8(xa + (uint32_t)(c16 * 8), hi);
+        ptx::tg_tmem_st8(xa + (uint32_t)(K / 2 + c16 * 8), lo);
+      }
+      ptx::mbar_arrive(&x_empty[slot]);          // the staged row is consumed: the copy warp may refill the slot
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&xa_full[s2]);
     }
-  } else if (warp < TG_LOAD_WARPS + TG_EPI_WARPS) {
+  } else if (warp < TG_W_MMA) {
     // ================= epilogue warps: TMEM -> warp-private smem transpose -> coalesced functor =================
-    const int ew = warp - TG_LOAD_WARPS;
-    const int wq = warp & 3, cgi = ew >> 2;             // TMEM lane quarter (hardware: warp % 4; TG_LOAD_WARPS % 4 == 0), column group
+    const int ew = warp - TG_W_EPI0;
+    const int wq = warp & 3, cgi = ew >> 2;             // TMEM lane quarter (hardware: warp % 4), column group
     constexpr int CPW = NT / (TG_EPI_WARPS / 4);        // columns per warp (64 / 48 / 16)
     float4* stg = reinterpret_cast<float4*>(sStg + ew * 4096);      // [32 rows][8 x float4]
     for (int it = 0; it < my_tiles; ++it) {
       const int m0 = ((int)blockIdx.x + it * (int)gridDim.x) * BM;
-      const int ab = it & 1;
-      ptx::mbar_wait(&acc_full[ab], (uint32_t)(it >> 1) & 1u);
+      const int ab = ACC2 ? (it & 1) : 0;
+      const uint32_t use = ACC2 ? (uint32_t)(it >> 1) : (uint32_t)it;
+      if (EK == SEB_EPI_RESID && g.resid != g.a[0] && lane < 8) {      // this warp's 32 residual rows: pull them towards L2 early
+        const long long mrow = (long long)m0 + wq * 32 + cgi * 8 + lane;
+        if (mrow < g.M) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(g.resid + mrow * g.ldr));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(g.resid + mrow * g.ldr + 32));
+        }
+      }
+      ptx::mbar_wait(&acc_full[ab], use & 1u);
       ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(ab * NT + cgi * CPW);
+      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + T_ACC + (uint32_t)(ab * NT + cgi * CPW);
 #pragma unroll
       for (int c0 = 0; c0 < CPW; c0 += 32) {
-        constexpr int dummy = 0; (void)dummy;
         const int ncols = (CPW - c0 < 32) ? CPW - c0 : 32;
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
@@ -120,50 +174,68 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs 
         __syncwarp();
       }
     }
-  } else if (warp == TG_LOAD_WARPS + TG_EPI_WARPS) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+  } else if (warp == TG_W_MMA) {
+    // ================= MMA issuer: ACC[ab] = XA[s] . W^T (A from tensor memory) =================
+    if (lane == 0 && my_tiles > 0) {
       constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      const uint32_t uA = ptx::smem_u32(sA), uW = ptx::smem_u32(sW);
+      const uint32_t uW = ptx::smem_u32(sW);
       ptx::mbar_wait(&w_full, 0);
-      long long gc = 0;
       for (int it = 0; it < my_tiles; ++it) {
-        const int ab = it & 1;
-        ptx::mbar_wait(&acc_empty[ab], ((uint32_t)(it >> 1) & 1u) ^ 1u);
-        const uint32_t d_tmem = tmem_base + (uint32_t)(ab * NT);
+        const int s2 = it & 1;
+        const int ab = ACC2 ? (it & 1) : 0;
+        const uint32_t use = ACC2 ? (uint32_t)(it >> 1) : (uint32_t)it;
+        ptx::mbar_wait(&xa_full[s2], (uint32_t)(it >> 1) & 1u);
+        ptx::mbar_wait(&acc_empty[ab], (use & 1u) ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + T_ACC + (uint32_t)(ab * NT);
+        const uint32_t a_hi0 = tmem_base + (uint32_t)(s2 * K), a_lo0 = a_hi0 + (uint32_t)(K / 2);
 #pragma unroll
-        for (int kc = 0; kc < KCH; ++kc, ++gc) {
-          const int s = (int)(gc % TG_SLOTS);
-          ptx::mbar_wait(&a_full[s], (uint32_t)(gc / TG_SLOTS) & 1u);
-          ptx::tc_fence_after();
-          const uint32_t base = uA + s * TG_ASLOT;
-          const uint64_t a_hi = ptx::umma_desc_sw128(base), a_lo = ptx::umma_desc_sw128(base + TC_A_BYTES);
+        for (int kc = 0; kc < KCH; ++kc) {
           const uint64_t w_hi = ptx::umma_desc_sw128(uW + kc * 2 * NT * 128), w_lo = ptx::umma_desc_sw128(uW + kc * 2 * NT * 128 + NT * 128);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t ko = (uint64_t)((k * 32) >> 4);
-            ptx::mma_bf16(d_tmem, a_lo + ko, w_hi + ko, IDESC, (kc | k) ? 1u : 0u);
-            ptx::mma_bf16(d_tmem, a_hi + ko, w_lo + ko, IDESC, 1u);
-            ptx::mma_bf16(d_tmem, a_hi + ko, w_hi + ko, IDESC, 1u);
+            const uint32_t ac = (uint32_t)(kc * 32 + k * 8);
+            ptx::tg_mma_ts(d_tmem, a_lo0 + ac, w_hi + ko, IDESC, (kc | k) ? 1u : 0u);
+            ptx::tg_mma_ts(d_tmem, a_hi0 + ac, w_lo + ko, IDESC, 1u);
+            ptx::tg_mma_ts(d_tmem, a_hi0 + ac, w_hi + ko, IDESC, 1u);
           }
-          ptx::tc_commit(&a_empty[s]);
         }
+        ptx::tc_commit(&xa_empty[s2]);
         ptx::tc_commit(&acc_full[ab]);
       }
     }
   } else {
-    // ================= weights: loaded once =================
-    if (lane == 0 && my_tiles > 0) {
-      constexpr uint32_t WB = KCH * 2 * NT * 128;
-      ptx::mbar_arrive_expect_tx(&w_full, WB);
-      constexpr uint32_t PIECE = 16384;                  // bulk copies of 16 KB
-      for (uint32_t o = 0; o < WB; o += PIECE) ptx::bulk_g2s(ptx::smem_u32(sW) + o, w_tc + o, (WB - o < PIECE) ? WB - o : PIECE, &w_full);
+    // ================= copy warp: weights once, then the raw rows of every tile (swizzled 16-byte chunks) =================
+    if (my_tiles > 0) {
+      if (lane == 0) {
+        constexpr uint32_t WB = KCH * 2 * NT * 128;
+        ptx::mbar_arrive_expect_tx(&w_full, WB);
+        constexpr uint32_t PIECE = 16384;                  // bulk copies of 16 KB
+        for (uint32_t o = 0; o < WB; o += PIECE) ptx::bulk_g2s(ptx::smem_u32(sW) + o, w_tc + o, (WB - o < PIECE) ? WB - o : PIECE, &w_full);
+      }
+      const float* src0 = g.a[0];
+      for (int it = 0; it < my_tiles; ++it) {
+        const int m0 = ((int)blockIdx.x + it * (int)gridDim.x) * BM;
+        const int slot = it % NSLOT;
+        ptx::mbar_wait(&x_empty[slot], ((uint32_t)(it / NSLOT) & 1u) ^ 1u);
+        const uint32_t dst0 = ptx::smem_u32(sX) + slot * XSLOT;
+#pragma unroll 8
+        for (int kk = 0; kk < BM * NCH / 32; ++kk) {
+          const int i = kk * 32 + lane, r = i / NCH, c = i % NCH;
+          const int m = m0 + r;
+          const int mc = m < g.M ? m : g.M - 1;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
+                       ::"r"(dst0 + r * PITCH + ((c ^ (r & 7)) << 4)), "l"(src0 + (long long)mc * g.lda + c * 4), "r"(m < g.M ? 16u : 0u) : "memory");
+        }
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(ptx::smem_u32(&x_full[slot])) : "memory");
+      }
     }
   }
   __syncthreads();
-  if (warp == TG_LOAD_WARPS + TG_EPI_WARPS) {
+  if (warp == TG_W_MMA) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, TCOLS);
+    ptx::tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -197,8 +269,10 @@ int launch_tok_gemm(const SebGemm* s, const GemmArgs& g, cudaStream_t st) {
     return launch_tok<192, 1, SEB_LOAD_ROWS_LN, SEB_EPI_QKV_F16>(s, g, st);
   if (s->loader == SEB_LOAD_ROWS_LN && s->epilogue == SEB_EPI_GLU && nt == 256 && s->K == 64)
     return launch_tok<256, 1, SEB_LOAD_ROWS_LN, SEB_EPI_GLU>(s, g, st);
-  // The N = 64 residual GEMMs (attention out-proj, pointwise 128 -> 64) measured faster on the 4-CTA-per-SM engine shape
-  // (6.7 / 8.4 ms per step vs 8.5 / 9.4 ms here), so they are not routed to this kernel.
+  if (s->loader == SEB_LOAD_ROWS && s->epilogue == SEB_EPI_RESID && nt == 64 && s->K == 64 && s->lda == 64)
+    return launch_tok<64, 1, SEB_LOAD_ROWS, SEB_EPI_RESID>(s, g, st);
+  if (s->loader == SEB_LOAD_ROWS && s->epilogue == SEB_EPI_RESID && nt == 64 && s->K == 128 && s->lda == 128)
+    return launch_tok<64, 2, SEB_LOAD_ROWS, SEB_EPI_RESID>(s, g, st);
   return -100;
 }
 
