@@ -15,28 +15,33 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return _
 
 __global__ void __launch_bounds__(128, 3) dwconv_bn_swish_kernel(const float* __restrict__ x, const SebSeq sq,
                                                                 const float* __restrict__ w, const float* __restrict__ bn_scale,
-                                                                const float* __restrict__ bn_shift, float* __restrict__ y) {
+                                                                const float* __restrict__ bn_shift, float* __restrict__ y, int nchunks) {
   __shared__ __align__(16) float tile[DW_TI + DW_K - 1][DW_C];
-  const int seq = blockIdx.x, i0 = blockIdx.y * DW_TI;
+  // position chunks are the fastest grid index: neighbouring chunks of a sequence run together, so the 30 halo rows they
+  // share are served by L2 instead of a second trip to HBM
+  const int seq = blockIdx.x / nchunks, i0 = (blockIdx.x - seq * nchunks) * DW_TI;
   const int cp = threadIdx.x & 63, ph = threadIdx.x >> 6;
   const long long base = (long long)(seq / sq.inner) * sq.outer_stride + (seq % sq.inner);
-  // stage rows i0-15 .. i0+64+15 (zero outside the sequence): 32 lanes x float4 cover one 512-byte row
+  // stage rows i0-15 .. i0+64+15 (zero outside the sequence) with cp.async: 32 lanes x 16 B cover one 512-byte row and the
+  // whole 47 KB tile is in flight at once (register-staged loads serialised four DRAM round trips per CTA)
   {
     constexpr int NV = (DW_TI + DW_K - 1) * (DW_C / 4);
-    float4* t4 = reinterpret_cast<float4*>(&tile[0][0]);
-#pragma unroll 6
+    const uint32_t t0 = (uint32_t)__cvta_generic_to_shared(&tile[0][0]);
+#pragma unroll 4
     for (int idx = threadIdx.x; idx < NV; idx += 128) {
       const int r = idx >> 5, c4 = idx & 31;
       const int i = i0 + r - DW_PAD;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (i >= 0 && i < sq.n) v = ldg4(x + (base + (long long)i * sq.pos_stride) * DW_C + c4 * 4);
-      t4[idx] = v;
+      const bool ok = i >= 0 && i < sq.n;
+      const float* src = x + (base + (long long)(ok ? i : 0) * sq.pos_stride) * DW_C + c4 * 4;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(t0 + idx * 16), "l"(src), "r"(ok ? 16 : 0) : "memory");
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
   float2 wr[DW_K];
 #pragma unroll
   for (int k = 0; k < DW_K; ++k) wr[k] = __ldg(reinterpret_cast<const float2*>(w + k * DW_C) + cp);
   const float2 sc = __ldg(reinterpret_cast<const float2*>(bn_scale) + cp), sh = __ldg(reinterpret_cast<const float2*>(bn_shift) + cp);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   const float2* t2 = reinterpret_cast<const float2*>(&tile[0][0]) + cp;      // row stride DW_C / 2 float2
 #pragma unroll 1
@@ -84,9 +89,10 @@ extern "C" int seb200_dwconv_bn_swish(const float* x, const SebSeq* seq, const f
                                       float* y, void* stream) {
   SEB_REQUIRE(x && seq && w && bn_scale && bn_shift && y, SEB_EINVAL, "dwconv: null argument");
   SEB_REQUIRE(seq->nseq > 0 && seq->n > 0 && seq->inner > 0, SEB_EINVAL, "dwconv: bad sequence descriptor");
-  dim3 grid(seq->nseq, (seq->n + DW_TI - 1) / DW_TI);   // sequences on x (2^31 limit), position chunks on y
-  SEB_REQUIRE(grid.y <= 65535u, SEB_EINVAL, "dwconv: sequence too long");
-  dwconv_bn_swish_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(x, *seq, w, bn_scale, bn_shift, y);
+  const int nchunks = (seq->n + DW_TI - 1) / DW_TI;
+  const long long nblocks = (long long)seq->nseq * nchunks;
+  SEB_REQUIRE(nblocks < 2147483647LL, SEB_EINVAL, "dwconv: grid too large");
+  dwconv_bn_swish_kernel<<<(unsigned)nblocks, 128, 0, (cudaStream_t)stream>>>(x, *seq, w, bn_scale, bn_shift, y, nchunks);
   SEB_CHECK_LAUNCH("dwconv_bn_swish_kernel");
   return 0;
 }
