@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(128, 3) attention_f16_kernel(const __half* __r
 //   * the fp16 embedding table arrives in FRAGMENT ORDER (halfs k = 0,1,8,9, 2,3,10,11, ... of a row; ops.pack_rel_pos),
 //     so one 8-byte load per lane fetches a whole B fragment of an offset tile (half the LSU wavefronts of two 4-byte loads);
 //   * in-band tiles (all offsets inside +-512) address E with immediates; CTAs have 3 or 4 warps, whichever wastes fewer;
-//     a final tile with <= 16 live keys runs a 16-key body.
+//     a final tile with <= 16 (33..48) live keys runs a 16-key (48-key) body.
 // ------------------------------------------------------------------------------------------------
 constexpr int A4_PW = 40;                                   // staged R is TRANSPOSED: word (w, row) at w * 40 + row, w < 48, row < 32 -- with the
                                                             // fragment lane maps both the half2 stores (-40 t + g) and the A-fragment reads (25 g + 8 t mod 32) hit 32 distinct banks
@@ -493,7 +493,7 @@ __global__ void __launch_bounds__(128, 3) attention_v4_kernel(const __half* __re
     const int b0 = iw - j0 - 63;                            // offset of column dd = 0 for tile 0 (tile 1: + 1)
     const int far = !BAND ? -1 : (b0 >= AT_MAXPOS ? 1 : (b0 + 96 <= -AT_MAXPOS ? 0 : -1));
     float s[2][NT][4];
-    constexpr int NT_LO = (NT == 8) ? 0 : 6;
+    constexpr int NT_LO = 8 - NT;                            // dd = 2 rho - c + 63 with c < 8 NT  ->  dd >= 64 - 8 NT
     const bool rel = !BAND || far < 0;                       // this tile needs the R GEMM + skew (else: far-field constant)
     const bool inband = (b0 >= -AT_MAXPOS) && (b0 + 96 <= AT_MAXPOS);
     // E fragments of tile mt: issued early so that the loads fly under the MMAs in front of their use
@@ -635,7 +635,9 @@ __global__ void __launch_bounds__(128, 3) attention_v4_kernel(const __half* __re
     const __half* Ks = KV + stage * 2 * A2_TILE_H;
     const __half* Vs = Ks + A2_TILE_H;
     if (warp_live) {
-      if (n - j0 <= 16) tile_body(std::integral_constant<int, 2>{}, Ks, Vs, j0, tile == 0);
+      const int rem = n - j0;        // live keys of this tile: a short last tile runs a narrower body (16 / 48 keys)
+      if (rem <= 16) tile_body(std::integral_constant<int, 2>{}, Ks, Vs, j0, tile == 0);
+      else if (rem > 32 && rem <= 48) tile_body(std::integral_constant<int, 6>{}, Ks, Vs, j0, tile == 0);
       else tile_body(std::integral_constant<int, 8>{}, Ks, Vs, j0, tile == 0);
     }
     __syncwarp();
