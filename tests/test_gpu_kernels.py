@@ -337,6 +337,25 @@ def test_attention(variant, axis, B, T, Fh):
     assert rel_max(out.view(B, T, Fh, 64).cpu(), ref) < tol
 
 
+@pytest.mark.parametrize("variant", [0, 2])
+def test_attention_peaky_logits(variant):
+    """large, sharply peaked logits: the lazy running maximum of variant 0 has to move its reference (and rescale) often"""
+    B, T, Fh = 1, 300, 2
+    qkv = rnd(B, T, Fh, 192, seed=82, scale=4.0)
+    emb = rnd(1025, 16, seed=83, scale=2.0)
+    seq, to_seq, from_seq = _seq_layouts(B, T, Fh)["time"]
+    out = torch.zeros(B * T * Fh, 64, device=DEV)
+    inp = qkv.view(-1, 192)
+    inp = torch.cat([inp[:, :64] * (0.25 * 1.4426950408889634), inp[:, 64:]], 1).to(torch.float16).contiguous()
+    ops.attention(inp, emb, seq, out, variant)
+    assert torch.isfinite(out).all()
+    # reference on the SAME fp16-rounded operands (the logits are too steep for the operand rounding itself to be negligible)
+    qh = inp.float()
+    qkv_r = torch.cat([qh[:, :64] / (0.25 * 1.4426950408889634), qh[:, 64:]], 1).view(B, T, Fh, 192)
+    ref = from_seq(_attention_core_ref(to_seq(qkv_r.cpu()), emb.to(torch.float16).float().cpu()))
+    assert rel_max(out.view(B, T, Fh, 64).cpu(), ref) < 5e-3
+
+
 @pytest.mark.parametrize("axis,B,T,Fh", [("freq", 2, 5, 101), ("time", 2, 130, 3)])
 def test_dwconv_bn_swish(axis, B, T, Fh):
     sd = weights.synth_state_dict(1)
