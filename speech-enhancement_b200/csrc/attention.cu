@@ -123,6 +123,12 @@ __device__ __forceinline__ void mma_f16_c(float (&d)[4], const uint32_t (&a)[4],
                : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(c0), "f"(c1));
 }
+// fp16-accumulating variant: the two D registers are half2 (row g: cols 2t, 2t+1 | row g + 8: same cols)
+__device__ __forceinline__ void mma_f16_h(uint32_t& d0, uint32_t& d1, const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f16.f16.f16.f16 {%0,%1}, {%2,%3,%4,%5}, {%6,%7}, {%8,%8};"
+               : "=r"(d0), "=r"(d1)
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "r"(0u));
+}
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -482,8 +488,8 @@ __global__ void __launch_bounds__(128, 3) attention_v4_kernel(const __half* __re
   const int lm_i = lane >> 3, lm_r = lane & 7;
   const int k_off = ((lm_i >> 1) * 8 + lm_r) * A2_LD + (lm_i & 1) * 8;
   const int v_off = ((lm_i & 1) * 8 + lm_r) * A2_LD + (lm_i >> 1) * 8;
-  // staged-R addressing (words): write (row, dd pair) -> (47 - 4 nt - t) * PW + row ; read A fragment -> (16 - rho + 8 kb + t (+ 4)) * PW + row
-  uint32_t* rw_lo = Rw + (47 - t) * A4_PW + g;             // + mt * 16, - 4 nt * PW ; rows g + 8: + 8
+  // staged-R addressing (words): write (row, dd pair) -> (44 - 4 nt + t) * PW + row ; read A fragment -> (16 - rho + 8 kb + t (+ 4)) * PW + row
+  uint32_t* rw_lo = Rw + (44 + t) * A4_PW + g;             // + mt * 16, - 4 nt * PW ; rows g + 8: + 8
   const uint32_t* rr = Rw + (16 - g + t) * A4_PW + g;      // + mt * 16 + 8 kb * PW ; rows g + 8: + 8 - 8 * PW
 
   // one key tile of NT n-tiles (8: 64 keys; 2: the 16-key tail body)
@@ -500,26 +506,28 @@ __global__ void __launch_bounds__(128, 3) attention_v4_kernel(const __half* __re
     uint2 ef[12];
     auto load_e = [&](int mt) {
       if (inband) {                   // all offsets inside +-512: one base pointer, immediates
-        const uint2* ebase = reinterpret_cast<const uint2*>(Eh + (long long)(b0 + mt + g + AT_MAXPOS) * AT_D) + t;
+        const uint2* ebase = reinterpret_cast<const uint2*>(Eh + (long long)(b0 + mt + 7 - g + AT_MAXPOS) * AT_D) + t;
 #pragma unroll
         for (int nt = NT_LO; nt < 12; ++nt) ef[nt] = __ldg(ebase + nt * 8 * (AT_D / 4));
       } else {                        // tile straddles the clamp (conformer.py:108)
 #pragma unroll
         for (int nt = NT_LO; nt < 12; ++nt) {
-          int d = b0 + mt + nt * 8 + g;
+          int d = b0 + mt + nt * 8 + 7 - g;
           d = d < -AT_MAXPOS ? -AT_MAXPOS : (d > AT_MAXPOS ? AT_MAXPOS : d);
           ef[nt] = __ldg(reinterpret_cast<const uint2*>(Eh + (d + AT_MAXPOS) * AT_D) + t);
         }
       }
     };
-    // R[rho, dd] = q . E[clamp(b0 + mt + dd)], dd in [0, 96) -> fp16, transposed, descending (rows < 8 use n-tiles <= 9, rows >= 8 n-tiles >= 2)
+    // R[rho, dd] = q . E[clamp(b0 + mt + dd)], dd in [0, 96) -> fp16, transposed, descending (rows < 8 use n-tiles <= 9, rows >= 8
+    // n-tiles >= 2).  Column n of offset tile nt is dd = 8 nt + 7 - n (lane g fetched that row), so the half2 the fp16-accumulating
+    // MMA returns for columns (2t, 2t + 1) already is one word of the descending staging row: no conversion, no packing.
     auto r_gemm = [&](int mt) {
 #pragma unroll
       for (int nt = NT_LO; nt < 12; ++nt) {
-        float r4[4] = {0.f, 0.f, 0.f, 0.f};
-        mma_f16(r4, qa[mt], ef[nt].x, ef[nt].y);
-        if (nt < 10) rw_lo[mt * 16 - 4 * nt * A4_PW] = pack_h2(r4[1], r4[0]);
-        if (nt >= 2) rw_lo[mt * 16 + 8 - 4 * nt * A4_PW] = pack_h2(r4[3], r4[2]);
+        uint32_t d0, d1;
+        mma_f16_h(d0, d1, qa[mt], ef[nt].x, ef[nt].y);
+        if (nt < 10) rw_lo[mt * 16 - 4 * nt * A4_PW] = d0;
+        if (nt >= 2) rw_lo[mt * 16 + 8 - 4 * nt * A4_PW] = d1;
       }
     };
     // skew-add on the tensor pipe: S[:, 16 kb : 16 kb + 16] += A_skew . [I | 0], [0 | I]
