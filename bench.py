@@ -237,6 +237,15 @@ def run_b200(args):
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get(dominant)
         shares = {k: round(v["ms"] / step_ms_prof, 4) for k, v in sorted(table.items(), key=lambda kv: -kv[1]["ms"])}
+        secondary = None
+        if dominant == "attention":
+            # the attention core is additionally capped by the MUFU exp rate (one ex2 per (query, key, head) = flops / 96);
+            # 16 ex2 / clk / SM on sm_100, at the SM clock sampled during the timed region
+            gexp = dom["flops"] / 96.0 / dom["launches"] / (per_launch_ms * 1e-3) / 1e9
+            sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+            n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+            pk_exp = n_sm * 16 * sm_mhz * 1e6 / 1e9
+            secondary = {"bound": "mufu", "achieved": gexp, "peak": pk_exp, "unit": "Gexp/s", "frac": gexp / pk_exp}
         line = {
             "metric": METRIC, "value": audio_s / (dev_ms * 1e-3), "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -252,7 +261,7 @@ def run_b200(args):
             "gpu_launches": int(launches),
             "roofline": {"kernel": dominant, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
                          "traffic": traffic, "peak_source": pk["src"], "launches_timed": dom["launches"], "ms_per_launch": per_launch_ms,
-                         "share_of_step": shares.get(dominant)},
+                         "share_of_step": shares.get(dominant), "secondary": secondary},
             "kernel_shares": shares,
         }
         if world == 1 and not args.no_cpu_baseline:
