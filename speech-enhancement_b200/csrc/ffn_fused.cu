@@ -274,20 +274,31 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn_fused_kernel(const FfnArgs 
         sStat[row] = make_float2(y0s + md, 1.0f / sqrtf(var + 1e-5f));
       }
       __syncwarp();
-      // coalesced copy-out of this warp's 32 rows: half a warp per row, one 16-byte chunk per lane
-#pragma unroll 4
-      for (int i = 0; i < 16; ++i) {
-        const int rr = fw * 32 + 2 * i + (lane >> 4);
-        const int m = m0 + rr;
-        float4 y = lds4(xs + rr * 256 + ((cc ^ (rr & 7)) << 4));
-        if (post) {
-          const float2 st = sStat[rr];
-          float4 r2 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (m < a.M) r2 = *reinterpret_cast<const float4*>(a.resid2 + (long long)m * 64 + cc * 4);
-          y.x = fmaf((y.x - st.x) * st.y, pg.x, pb.x) + r2.x; y.y = fmaf((y.y - st.x) * st.y, pg.y, pb.y) + r2.y;
-          y.z = fmaf((y.z - st.x) * st.y, pg.z, pb.z) + r2.z; y.w = fmaf((y.w - st.x) * st.y, pg.w, pb.w) + r2.w;
+      // coalesced copy-out of this warp's 32 rows: half a warp per row, one 16-byte chunk per lane.  Loads of a group of four
+      // rows are issued before its stores: `out` may alias `resid2`, so the compiler cannot hoist them itself and the
+      // residual reads would otherwise serialise into sixteen DRAM round trips per tile.
+#pragma unroll 1
+      for (int i0 = 0; i0 < 16; i0 += 4) {
+        float4 yv[4], r2[4];
+        float2 st[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int rr = fw * 32 + 2 * (i0 + u) + (lane >> 4);
+          const int m = m0 + rr;
+          yv[u] = lds4(xs + rr * 256 + ((cc ^ (rr & 7)) << 4));
+          st[u] = sStat[rr];
+          r2[u] = (post && m < a.M) ? *reinterpret_cast<const float4*>(a.resid2 + (long long)m * 64 + cc * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        if (m < a.M) st4(a.out + (long long)m * 64 + cc * 4, y);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int m = m0 + fw * 32 + 2 * (i0 + u) + (lane >> 4);
+          float4 y = yv[u];
+          if (post) {
+            y.x = fmaf((y.x - st[u].x) * st[u].y, pg.x, pb.x) + r2[u].x; y.y = fmaf((y.y - st[u].x) * st[u].y, pg.y, pb.y) + r2[u].y;
+            y.z = fmaf((y.z - st[u].x) * st[u].y, pg.z, pb.z) + r2[u].z; y.w = fmaf((y.w - st[u].x) * st[u].y, pg.w, pb.w) + r2[u].w;
+          }
+          if (m < a.M) st4(a.out + (long long)m * 64 + cc * 4, y);
+        }
       }
       __syncwarp();
       ptx::mbar_arrive(&x_empty[s]);            // this thread's reads of the staging slot are done

@@ -138,11 +138,16 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs 
       const int m0 = ((int)blockIdx.x + it * (int)gridDim.x) * BM;
       const int ab = ACC2 ? (it & 1) : 0;
       const uint32_t use = ACC2 ? (uint32_t)(it >> 1) : (uint32_t)it;
-      if (EK == SEB_EPI_RESID && g.resid != g.a[0] && lane < 8) {      // this warp's 32 residual rows: pull them towards L2 early
-        const long long mrow = (long long)m0 + wq * 32 + cgi * 8 + lane;
-        if (mrow < g.M) {
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(g.resid + mrow * g.ldr));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(g.resid + mrow * g.ldr + 32));
+      const int ch = lane & 7;
+      // residual rows of this warp's outputs: issued BEFORE the accumulator wait (out may alias resid, so the compiler
+      // cannot hoist them over the stores of the copy-out loop itself; serialised they cost eight DRAM round trips per tile)
+      float4 res[8];
+      if (EK == SEB_EPI_RESID) {
+        static_assert(EK != SEB_EPI_RESID || CPW <= 32, "residual prefetch covers one 32-column pass");
+#pragma unroll
+        for (int i8 = 0; i8 < 8; ++i8) {
+          const int m = m0 + wq * 32 + i8 * 4 + (lane >> 3), n = cgi * CPW + ch * 4;
+          res[i8] = (ch * 4 < CPW && m < g.M) ? *reinterpret_cast<const float4*>(g.resid + (long long)m * g.ldr + n) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
       ptx::mbar_wait(&acc_full[ab], use & 1u);
@@ -162,13 +167,28 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs 
         }
         if (c0 + 32 >= CPW) { ptx::tc_fence_before(); ptx::mbar_arrive(&acc_empty[ab]); }     // accumulator fully read
         __syncwarp();
-        const int ch = lane & 7;
+        float4 vals[8];
+#pragma unroll
+        for (int i8 = 0; i8 < 8; ++i8) {          // all staging reads first: nothing between them and their use can alias
+          const int R = i8 * 4 + (lane >> 3);
+          vals[i8] = stg[R * 8 + (ch ^ (R & 7))];
+        }
 #pragma unroll
         for (int i8 = 0; i8 < 8; ++i8) {
           const int R = i8 * 4 + (lane >> 3);
           if (ch * 4 < ncols) {
-            const float4 val = stg[R * 8 + (ch ^ (R & 7))];
-            Epi<EK>::apply(g, m0 + wq * 32 + R, cgi * CPW + c0 + ch * 4, val);
+            const int m = m0 + wq * 32 + R, n = cgi * CPW + c0 + ch * 4;
+            if (EK == SEB_EPI_RESID) {
+              if (m < g.M && n < g.N) {
+                float4 v = vals[i8];
+                const float4 bb = g.bias ? ldg4(g.bias + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v.x = fmaf(g.alpha, v.x + bb.x, res[i8].x); v.y = fmaf(g.alpha, v.y + bb.y, res[i8].y);
+                v.z = fmaf(g.alpha, v.z + bb.z, res[i8].z); v.w = fmaf(g.alpha, v.w + bb.w, res[i8].w);
+                st4(g.out + (long long)m * g.ldo + n, v);
+              }
+            } else {
+              Epi<EK>::apply(g, m, n, vals[i8]);
+            }
           }
         }
         __syncwarp();
