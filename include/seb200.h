@@ -160,6 +160,12 @@ int seb200_attention(const void* qkv, const float* rel_pos_emb, const void* rel_
  * x, y [tokens, 128]; w [31][128] (tap-major); bn_scale/bn_shift fold conv bias, running stats and affine */
 int seb200_dwconv_bn_swish(const float* x, const SebSeq* seq, const float* w, const float* bn_scale,
                            const float* bn_shift, float* y, void* stream);
+/* The same depthwise stage fused with the pointwise Conv1d(128 -> 64) that follows it and the block residual
+ * (conformer.py:166-169, 204):  out = resid + W3 . Swish(BN(DWConv31(u))) + b3.   u: [tokens, 128] fp32 (GLU output),
+ * w3_tc: tcgen05 image of W3 [64, 128] packed with n-tile 64 (packing.py), resid / out: [tokens, 64] fp32 (out may alias
+ * resid).  The depthwise result goes straight into the MMA operand tile in shared memory; it is never written to HBM. */
+int seb200_dwconv_pw2(const float* u, const SebSeq* seq, const float* w, const float* bn_scale, const float* bn_shift,
+                      const void* w3_tc, const float* b3, const float* resid, float* out, void* stream);
 /* post_norm + the TSCB outer residual (conformer.py:211, generator.py:70,72): out = LN(x) * g + b + resid */
 int seb200_layernorm_residual(const float* x, long long tokens, const float* gamma, const float* beta,
                               const float* resid, float* out, void* stream);

@@ -143,6 +143,8 @@ class TSCNet(nn.Module):
         self.num_features = num_features
         self.engine = ops.default_engine()     # "tcgen05" | "simt" main loop of the GEMM engine
         self.attention_variant = 0             # 0 tensor-core, 1 SIMT cross-check
+        self.fuse_dwconv_pw2 = False           # opt-in: depthwise conv + pointwise 128 -> 64 in one kernel (seb200_dwconv_pw2); measured
+                                               # 21.5 ms vs 16.2 ms for the two-kernel path at configs[1], so off by default
         self._packed: Optional[Dict[str, object]] = None
         self._packed_key = None
         self._ws: Dict[tuple, Dict[str, torch.Tensor]] = {}
@@ -304,8 +306,11 @@ class TSCNet(nn.Module):
         ops.gemm(loader=LOAD_ROWS, epilogue=EPI_RESID, M=M, w=P[f"{p}.attn.out"], a=[o], lda=64, out=y, ldo=64, resid=y, ldr=64, alpha=1.0, engine=eng, label="attn_out")
         # y += ConvModule(y)
         ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_GLU, M=M, w=P[f"{p}.conv.pw1"], a=[y], lda=64, ln=P[f"{p}.conv.ln"], out=u, ldo=128, engine=eng, label="pw1_glu")
-        ops.dwconv_bn_swish(u, seq, P[f"{p}.conv.dw"], P[f"{p}.conv.bn"][0], P[f"{p}.conv.bn"][1], v)
-        ops.gemm(loader=LOAD_ROWS, epilogue=EPI_RESID, M=M, w=P[f"{p}.conv.pw2"], a=[v], lda=128, out=y, ldo=64, resid=y, ldr=64, alpha=1.0, engine=eng, label="pw2")
+        if fused and self.fuse_dwconv_pw2:      # depthwise + BN + Swish + pointwise 128 -> 64 + residual in one kernel: v never touches HBM
+            ops.dwconv_pw2(u, seq, P[f"{p}.conv.dw"], P[f"{p}.conv.bn"][0], P[f"{p}.conv.bn"][1], P[f"{p}.conv.pw2"], y, y)
+        else:
+            ops.dwconv_bn_swish(u, seq, P[f"{p}.conv.dw"], P[f"{p}.conv.bn"][0], P[f"{p}.conv.bn"][1], v)
+            ops.gemm(loader=LOAD_ROWS, epilogue=EPI_RESID, M=M, w=P[f"{p}.conv.pw2"], a=[v], lda=128, out=y, ldo=64, resid=y, ldr=64, alpha=1.0, engine=eng, label="pw2")
         # x = post_norm(y + 0.5 * FF2(LN(y))) + x
         if fused:
             ops.ffn_fused(y, x, P[f"{p}.ff2.ln"], P[f"{p}.ff2.w1"], P[f"{p}.ff2.w2"], 0.5, post=P[f"{p}.post_norm"], resid2=x)

@@ -337,6 +337,18 @@ def attention(qkv, rel_pos_emb, seq: SebSeq, out, variant: int = 0, rel_pos_emb_
     return out
 
 
+def dwconv_pw2(u, seq: SebSeq, w, bn_scale, bn_shift, w3: PackedWeight, resid, out):
+    """out = resid + W3 . Swish(BN(DWConv31(u))) + b3 in one kernel (conformer.py:166-169, 204); u [tokens, 128], out [tokens, 64]."""
+    _f32c(u, w, bn_scale, bn_shift, resid, out)
+    if w3.tc_ntile != 64 or w3.N != 64 or w3.K != 128 or w3.planes != 2 or w3.bias is None:
+        raise RuntimeError("dwconv_pw2 expects W3 [64, 128] packed with n-tile 64, two planes, and a bias")
+    tok = _pb("dwconv_pw2", 62.0 * u.numel() + 2.0 * 64 * u.numel(), 4.0 * u.numel() + 8.0 * out.numel()) if _PROF is not None else None
+    check(_lib.load().seb200_dwconv_pw2(ptr(u), C.byref(seq), ptr(w), ptr(bn_scale), ptr(bn_shift), ptr(w3.w_tc), ptr(w3.bias),
+                                        ptr(resid), ptr(out), stream_ptr()), "seb200_dwconv_pw2")
+    _pe(tok)
+    return out
+
+
 def dwconv_bn_swish(x, seq: SebSeq, w, bn_scale, bn_shift, y):
     _f32c(x, w, bn_scale, bn_shift, y)
     tok = _pb("dwconv", 62.0 * x.numel(), 8.0 * x.numel()) if _PROF is not None else None
