@@ -24,7 +24,7 @@ constexpr int TG_THREADS = (TG_W_COPY + 1) * 32;                              //
 template <int KCH> constexpr int tg_slots() { return KCH == 1 ? 3 : 2; }
 template <int KCH> constexpr int tg_xslot() { return BM * 64 * KCH * 4; }     // raw fp32 rows of one tile: 32 / 64 KB
 template <int NT, int KCH> constexpr int tg_smem_bytes() {
-  return 1024 + tg_slots<KCH>() * tg_xslot<KCH>() + KCH * 2 * NT * 128 + TG_EPI_WARPS * 4096 + 2 * 64 * 4;
+  return 1024 + tg_slots<KCH>() * tg_xslot<KCH>() + KCH * 2 * NT * 128 + TG_EPI_WARPS * 4096 + 2 * 64 * 4 + NT * 4;
 }
 
 namespace ptx {
@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs 
   uint8_t* sStg = sX + NSLOT * XSLOT;                   // 4 KB per epilogue warp
   float* sG = reinterpret_cast<float*>(sStg + TG_EPI_WARPS * 4096);
   float* sBt = sG + 64;
+  float* sBias = sBt + 64;                               // [NT] output bias (zeros when the GEMM has none)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ntiles = (g.M + BM - 1) / BM;
   const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -71,6 +72,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs 
     ptx::fence_barrier_init();
   }
   if (LK == SEB_LOAD_ROWS_LN && tid < 128) { if (tid < 64) sG[tid] = g.ln_g[tid]; else sBt[tid - 64] = g.ln_b[tid - 64]; }
+  for (int i = tid; i < NT; i += TG_THREADS) sBias[i] = (g.bias && i < g.N) ? g.bias[i] : 0.f;
   if (warp == TG_W_MMA) ptx::tmem_alloc(&tmem_base_s, 512);
   ptx::tc_fence_before();
   __syncthreads();
@@ -163,6 +165,63 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs 
       ptx::mbar_wait(&acc_full[ab], use & 1u);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + T_ACC + (uint32_t)(ab * NT + cgi * CPW);
+      if (EK == SEB_EPI_GLU || EK == SEB_EPI_QKV_F16) {
+        // element-wise part in the accumulator's own thread = row layout (bias, GLU / fp16 scaling), THEN the transpose: the
+        // staged tile and the copy-out carry the packed outputs only (half the words of the fp32 accumulator columns)
+        uint4* stq = reinterpret_cast<uint4*>(stg);                   // [32 rows][4 x 16 B], chunk XOR ((row >> 1) & 3)
+#pragma unroll
+        for (int c0 = 0; c0 < CPW; c0 += 32) {
+          constexpr int dummy = 0; (void)dummy;
+          const int ncols = (CPW - c0 < 32) ? CPW - c0 : 32;
+          const int n0 = cgi * CPW + c0;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (j < ncols) {
+              float t8[8];
+              ptx::tmem_ld8(taddr + c0 + j, t8);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[j + i] = t8[i];
+            }
+          }
+          if (c0 + 32 >= CPW) { ptx::tc_fence_before(); ptx::mbar_arrive(&acc_empty[ab]); }     // accumulator fully read
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {            // output chunk q <- accumulator columns 8q .. 8q + 7
+            if (q * 8 < ncols) {
+              uint4 o;
+              if (EK == SEB_EPI_GLU) {             // packed columns: (value_j, gate_j) adjacent (conformer.py:36-37)
+                const float4 b0 = *reinterpret_cast<const float4*>(sBias + n0 + 8 * q), b1 = *reinterpret_cast<const float4*>(sBias + n0 + 8 * q + 4);
+                o.x = __float_as_uint((v[8 * q + 0] + b0.x) * sigmoidf_acc(v[8 * q + 1] + b0.y));
+                o.y = __float_as_uint((v[8 * q + 2] + b0.z) * sigmoidf_acc(v[8 * q + 3] + b0.w));
+                o.z = __float_as_uint((v[8 * q + 4] + b1.x) * sigmoidf_acc(v[8 * q + 5] + b1.y));
+                o.w = __float_as_uint((v[8 * q + 6] + b1.z) * sigmoidf_acc(v[8 * q + 7] + b1.w));
+              } else {                             // fp16 q | k | v, q pre-scaled by dim_head^-0.5 * log2(e)
+                const float sc = (n0 + 8 * q < 64) ? 0.25f * 1.4426950408889634f : 1.0f;
+                __half2 h0 = __floats2half2_rn(v[8 * q + 0] * sc, v[8 * q + 1] * sc), h1 = __floats2half2_rn(v[8 * q + 2] * sc, v[8 * q + 3] * sc);
+                __half2 h2 = __floats2half2_rn(v[8 * q + 4] * sc, v[8 * q + 5] * sc), h3 = __floats2half2_rn(v[8 * q + 6] * sc, v[8 * q + 7] * sc);
+                o = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1), *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+              }
+              stq[lane * 4 + (q ^ ((lane >> 1) & 3))] = o;
+            }
+          }
+          __syncwarp();
+          const int cc = lane & 3;
+          if (cc * 8 < ncols) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int R = 8 * i + (lane >> 2);
+              const int m = m0 + wq * 32 + R;
+              const uint4 o = stq[R * 4 + (cc ^ ((R >> 1) & 3))];
+              if (m < g.M) {
+                if (EK == SEB_EPI_GLU) *reinterpret_cast<uint4*>(g.out + (long long)m * g.ldo + (n0 >> 1) + cc * 4) = o;
+                else *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(g.out) + (long long)m * g.ldo + n0 + cc * 8) = o;
+              }
+            }
+          }
+          __syncwarp();
+        }
+        continue;
+      }
 #pragma unroll
       for (int c0 = 0; c0 < CPW; c0 += 32) {
         const int ncols = (CPW - c0 < 32) ? CPW - c0 : 32;
