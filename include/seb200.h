@@ -98,6 +98,9 @@ int seb200_ffn_fused(const SebFfn* f, void* stream);
  * c = sqrt(L / sum x^2); xpad[b, 0 : Lp+400] = reflect200(wrap_pad(c * x)); c_out[b] = c. */
 int seb200_rms_pad(const float* wave, int B, int L, int Lp, int normalize,
                    float* xpad, float* c_out, void* stream);
+/* normalize_batch, core/function.py:647-659: the clean utterance takes the NOISY utterance's gain:
+ * xpad[b, 0 : Lp+400] = reflect200(wrap_pad(c_in[b] * x)). */
+int seb200_scale_pad(const float* wave, int B, int L, int Lp, const float* c_in, float* xpad, void* stream);
 /* complex64 (B, F, T) spectrogram (torch.stft layout) -> in3 [B, T, F, 3] = (|x|, re, im); generator.py:146-151 */
 int seb200_spec_to_in3(const float* spec_ri, int B, int F, int T, float* in3, void* stream);
 /* in3 [B, T, F, 3] -> complex64 (B, F, T): the layout compressed_stft returns (core/function.py:693) */

@@ -87,7 +87,7 @@ def load():
         from models.generator import TSCNet
         import models.generator as gen_mod
         import models.conformer as conf_mod
-        from core.function import compressed_stft, uncompressed_istft
+        from core.function import compressed_stft, uncompressed_istft, batch_stft, normalize_batch
         from utils.utils import kaiming_init
         try:
             from inference_gan import predict
@@ -97,6 +97,7 @@ def load():
         sys.path.remove(REF_ROOT)
     ns = types.SimpleNamespace(TSCNet=TSCNet, predict=predict, compressed_stft=compressed_stft,
                                uncompressed_istft=uncompressed_istft, kaiming_init=kaiming_init,
+                               batch_stft=batch_stft, normalize_batch=normalize_batch,
                                generator=gen_mod, conformer=conf_mod,
                                config=types.SimpleNamespace(N_FFT=400, HOP_SAMPLES=100))
     _cache["ns"] = ns

@@ -10,6 +10,7 @@ no einops) of the reference's algorithm for the path named in BASELINE.json:
     ConformerBlock.forward /root/reference/models/conformer.py:206-212
     power_uncompress()     /root/reference/core/function.py:636-645
     uncompressed_istft()   /root/reference/core/function.py:695-703
+    normalize_batch() / batch_stft()  /root/reference/core/function.py:647-683
 
 It is driven purely by a ``state_dict`` with the reference's 359 keys.  Only
 ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
@@ -82,6 +83,18 @@ def compressed_stft(x: torch.Tensor, n_fft: int = N_FFT, hop: int = HOP,
     fr = stft_frames(x, n_fft, hop) * w
     spec = torch.fft.rfft(fr, dim=-1).transpose(1, 2)
     return power_compress(spec)
+
+
+def normalize_batch(clean: torch.Tensor, noisy: torch.Tensor):
+    """core/function.py:647-659: c = sqrt(L / sum noisy^2) per utterance, applied to both signals."""
+    c = torch.sqrt(noisy.size(-1) / torch.sum(noisy ** 2.0, dim=-1, keepdim=True))
+    return clean * c, noisy * c
+
+
+def batch_stft(clean: torch.Tensor, noisy: torch.Tensor):
+    """core/function.py:664-683 (forward DSP of the training caller): normalised waveforms and their compressed STFTs."""
+    clean, noisy = normalize_batch(clean, noisy)
+    return clean, noisy, compressed_stft(clean), compressed_stft(noisy)
 
 
 def uncompressed_istft(spec: torch.Tensor, n_fft: int = N_FFT, hop: int = HOP,

@@ -4,6 +4,7 @@ Public surface (mirrors the reference's interface for this path):
 
 * ``TSCNet(num_channel=64, num_features=201)``            models/generator.py:132-167
 * ``compressed_stft`` / ``uncompressed_istft``             core/function.py:685-703
+* ``normalize_batch`` / ``batch_stft``                       core/function.py:647-683 (training caller, forward DSP)
 * ``EnhancerB200(model)(noisy)`` / ``.predict(numpy)``     inference_gan.py:75-100
 * ``load_model(path)``                                      inference_gan.py:60-72
 * ``shard_slice`` / ``enhance_sharded``                     batch sharding across ranks (inference has no collective)
@@ -11,7 +12,7 @@ Public surface (mirrors the reference's interface for this path):
 The directory is called ``speech-enhancement_b200``; import it as ``se_b200`` (the ``se_b200.py`` shim at the repo root).
 """
 from .generator import TSCNet
-from .dsp import compressed_stft, uncompressed_istft
+from .dsp import batch_stft, compressed_stft, normalize_batch, uncompressed_istft
 from .enhancer import EnhancerB200
 from .sharding import enhance_sharded, shard_slice
 from . import ops, packing, _lib
@@ -29,5 +30,5 @@ def load_model(model_path, device="cuda"):
     return model
 
 
-__all__ = ["TSCNet", "compressed_stft", "uncompressed_istft", "EnhancerB200", "load_model", "shard_slice",
+__all__ = ["TSCNet", "compressed_stft", "uncompressed_istft", "normalize_batch", "batch_stft", "EnhancerB200", "load_model", "shard_slice",
            "enhance_sharded", "ops", "packing"]

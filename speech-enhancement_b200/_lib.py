@@ -52,6 +52,7 @@ _SIGS = {
     "seb200_gemm": [C.POINTER(SebGemm), C.c_int, _fp],
     "seb200_ffn_fused": [C.POINTER(SebFfn), _fp],
     "seb200_rms_pad": [_fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp],
+    "seb200_scale_pad": [_fp, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp],
     "seb200_spec_to_in3": [_fp, C.c_int, C.c_int, C.c_int, _fp, _fp],
     "seb200_in3_to_spec": [_fp, C.c_int, C.c_int, C.c_int, _fp, _fp],
     "seb200_decompress_rows": [_fp, C.c_int, C.c_int, _fp, C.c_int, _fp],

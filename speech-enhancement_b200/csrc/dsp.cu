@@ -4,14 +4,16 @@
 namespace seb {
 
 // predict() glue (inference_gan.py:79-87) + torch.stft's centre reflect padding, one CTA per utterance.
+// With c_in the per-utterance gain is taken from the caller instead (normalize_batch applies the NOISY signal's gain to
+// the clean signal as well, core/function.py:647-659).
 __global__ void __launch_bounds__(512) rms_pad_kernel(const float* __restrict__ wave, int L, int Lp, int normalize,
-                                                     float* __restrict__ xpad, float* __restrict__ c_out) {
+                                                     const float* __restrict__ c_in, float* __restrict__ xpad, float* __restrict__ c_out) {
   const int b = blockIdx.x;
   const float* x = wave + (long long)b * L;
   __shared__ double red[16];
   __shared__ float c_s;
-  float c = 1.0f;
-  if (normalize) {
+  float c = c_in ? c_in[b] : 1.0f;
+  if (normalize && !c_in) {
     double acc = 0.0;
     for (int i = threadIdx.x * 4; i < L; i += blockDim.x * 4) {   // short fp32 runs, fp64 across runs
       float s = 0.f;
@@ -29,7 +31,7 @@ __global__ void __launch_bounds__(512) rms_pad_kernel(const float* __restrict__ 
     __syncthreads();
     c = c_s;
   }
-  if (threadIdx.x == 0) c_out[b] = c;
+  if (threadIdx.x == 0 && c_out) c_out[b] = c;
   const int total = Lp + 400;
   float* o = xpad + (long long)b * total;
   for (int i = threadIdx.x; i < total; i += blockDim.x) {
@@ -142,7 +144,15 @@ using namespace seb;
 extern "C" int seb200_rms_pad(const float* wave, int B, int L, int Lp, int normalize, float* xpad, float* c_out, void* stream) {
   SEB_REQUIRE(wave && xpad && c_out && B > 0 && L > 0 && Lp >= L && Lp % 100 == 0 && Lp - L < 100 && Lp > 200, SEB_EINVAL,
               "rms_pad: bad arguments B=%d L=%d Lp=%d", B, L, Lp);
-  rms_pad_kernel<<<B, 512, 0, (cudaStream_t)stream>>>(wave, L, Lp, normalize, xpad, c_out);
+  rms_pad_kernel<<<B, 512, 0, (cudaStream_t)stream>>>(wave, L, Lp, normalize, nullptr, xpad, c_out);
+  SEB_CHECK_LAUNCH("rms_pad_kernel");
+  return 0;
+}
+
+extern "C" int seb200_scale_pad(const float* wave, int B, int L, int Lp, const float* c_in, float* xpad, void* stream) {
+  SEB_REQUIRE(wave && xpad && c_in && B > 0 && L > 0 && Lp >= L && Lp % 100 == 0 && Lp - L < 100 && Lp > 200, SEB_EINVAL,
+              "scale_pad: bad arguments B=%d L=%d Lp=%d", B, L, Lp);
+  rms_pad_kernel<<<B, 512, 0, (cudaStream_t)stream>>>(wave, L, Lp, 0, c_in, xpad, nullptr);
   SEB_CHECK_LAUNCH("rms_pad_kernel");
   return 0;
 }

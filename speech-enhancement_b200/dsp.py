@@ -97,3 +97,48 @@ def uncompressed_istft(spec: torch.Tensor, n_fft: int = N_FFT, hop_length: int =
     z = torch.empty(B * T, LDZ, device=spec.device, dtype=torch.float32)
     ops.spec_decompress_rows(spec.to(torch.complex64), z)
     return istft_rows(z, B, T, None, engine)
+
+
+# ------------------------------------------------------------------------------- training caller
+def _on_device(t: torch.Tensor, gpu) -> torch.Tensor:
+    if gpu is not None:
+        t = t.cuda(gpu, non_blocking=True)
+    require_cuda(t)
+    return t.to(torch.float32).contiguous()
+
+
+def _normalize_pad(batch, args):
+    clean, noisy = _on_device(batch["audio"], getattr(args, "gpu", None)), _on_device(batch["noisy"], getattr(args, "gpu", None))
+    if clean.shape != noisy.shape or noisy.dim() != 2:
+        raise RuntimeError("batch['audio'] and batch['noisy'] must both be (B, L)")
+    L = noisy.shape[1]
+    if L % HOP != 0:
+        raise RuntimeError("crop length must be a multiple of hop (the reference crops to whole seconds, main_gan.py --crop-len)")
+    npad, c = ops.rms_pad(noisy, L, normalize=True)          # c = sqrt(L / sum noisy^2), applied to both signals
+    cpad = ops.scale_pad(clean, L, c)
+    return cpad, npad, L
+
+
+def normalize_batch(batch, args):
+    """core/function.py:647-659: per-utterance gain from the NOISY signal applied to clean and noisy.  ``batch`` is the
+    data loader's dict ('audio' = clean, 'noisy'), ``args.gpu`` the device index (or None when the tensors are already
+    on the GPU).  Returns (clean, noisy), each (B, L): views of the reflect-padded buffers the STFT reads."""
+    cpad, npad, L = _normalize_pad(batch, args)
+    return cpad[:, N_FFT // 2:N_FFT // 2 + L], npad[:, N_FFT // 2:N_FFT // 2 + L]
+
+
+def batch_stft(batch, args, config):
+    """core/function.py:664-683: normalise, then the compressed STFT of noisy and clean in one pass over each padded
+    buffer.  Returns the reference's 8-tuple (clean, noisy, clean_spec, noisy_spec, clean_real, clean_imag, one_labels,
+    hamming_window)."""
+    _check_cfg(config.N_FFT, config.HOP_SAMPLES, None, "pow")
+    cpad, npad, L = _normalize_pad(batch, args)
+    T = L // HOP + 1
+    noisy_spec = ops.in3_to_spec(stft_in3(npad, T))
+    clean_spec = ops.in3_to_spec(stft_in3(cpad, T))
+    dev = npad.device
+    one_labels = torch.ones(npad.shape[0], device=dev)
+    hamming_window = torch.hamming_window(config.N_FFT, device=dev)
+    half = N_FFT // 2
+    return (cpad[:, half:half + L], npad[:, half:half + L], clean_spec, noisy_spec, clean_spec.real.unsqueeze(1),
+            clean_spec.imag.unsqueeze(1), one_labels, hamming_window)

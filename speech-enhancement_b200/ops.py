@@ -164,6 +164,19 @@ def rms_pad(wave: torch.Tensor, Lp: int, normalize: bool = True):
     return xpad, c
 
 
+def scale_pad(wave: torch.Tensor, Lp: int, c: torch.Tensor):
+    """xpad[b] = reflect200(wrap_pad(c[b] * wave[b])) with the caller's per-utterance gain (normalize_batch's clean branch)."""
+    _f32c(wave); _f32c(c)
+    B, L = wave.shape
+    if c.numel() != B:
+        raise RuntimeError("scale_pad: one gain per utterance expected")
+    xpad = torch.empty(B, Lp + 400, device=wave.device, dtype=torch.float32)
+    tok = _pb("rms_pad", 0.0, 8.0 * wave.numel()) if _PROF is not None else None
+    check(_lib.load().seb200_scale_pad(ptr(wave), B, L, Lp, ptr(c), ptr(xpad), stream_ptr()), "seb200_scale_pad")
+    _pe(tok)
+    return xpad
+
+
 def spec_to_in3(spec: torch.Tensor, out: Optional[torch.Tensor] = None):
     """complex64 (B, F, T) -> in3 [B, T, F, 3]."""
     require_cuda(spec)

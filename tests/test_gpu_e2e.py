@@ -117,3 +117,23 @@ def test_batch_rows_are_independent():
     full = enh(noisy).clone()
     for i in range(3):
         assert torch.equal(enh(noisy[i:i + 1])[0], full[i])
+
+
+def test_batch_stft_matches_oracle():
+    """the training caller's forward DSP (normalize_batch + two compressed STFTs, core/function.py:647-683)
+    through the reference's own signature: batch dict, args.gpu, config.N_FFT / HOP_SAMPLES."""
+    import types
+    noisy, clean = weights.synth_wave(4, 32000, 5, "speech")          # configs[4]: 2 s crops, batch 4 per GPU
+    cfg = types.SimpleNamespace(N_FFT=400, HOP_SAMPLES=100)
+    out = se_b200.batch_stft({"audio": clean, "noisy": noisy}, types.SimpleNamespace(gpu=0), cfg)
+    g_clean, g_noisy, g_cspec, g_nspec, g_creal, g_cimag, ones, win = out
+    o_clean, o_noisy, o_cspec, o_nspec = O.batch_stft(clean, noisy)
+    assert g_clean.shape == (4, 32000) and g_cspec.shape == (4, 201, 321) and g_creal.shape == (4, 1, 201, 321)
+    assert rel_max(g_clean.cpu(), o_clean) < 1e-6 and rel_max(g_noisy.cpu(), o_noisy) < 1e-6
+    for g, o in ((g_cspec, o_cspec), (g_nspec, o_nspec)):
+        assert rel_l2(torch.view_as_real(g.cpu()), torch.view_as_real(o)) < SPEC_TOL
+        assert rel_max(torch.view_as_real(g.cpu()), torch.view_as_real(o)) < 2e-4      # worst bin / peak (SURVEY 7.3 #2)
+    assert torch.equal(g_creal.squeeze(1), g_cspec.real) and torch.equal(g_cimag.squeeze(1), g_cspec.imag)
+    assert torch.equal(ones.cpu(), torch.ones(4)) and torch.allclose(win.cpu(), torch.hamming_window(400))
+    n2c, n2n = se_b200.normalize_batch({"audio": clean.to(DEV), "noisy": noisy.to(DEV)}, types.SimpleNamespace(gpu=None))
+    assert torch.equal(n2c, g_clean) and torch.equal(n2n, g_noisy)

@@ -91,3 +91,20 @@ def test_oracle_against_live_reference():
         a = blk(x)
         b = O.conformer_block(x, sd, "TSCB_1.time_conformer", chunk=2)
     assert rel_max(b, a) < 1e-5
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="/root/reference not mounted")
+def test_batch_stft_against_live_reference():
+    """normalize_batch / batch_stft (core/function.py:647-683) restated vs the reference itself."""
+    import types
+    ref = ref_import.load()
+    noisy, clean = weights.synth_wave(3, 3200, 21, "speech")
+    out = ref.batch_stft({"audio": clean.clone(), "noisy": noisy.clone()}, types.SimpleNamespace(gpu=None), ref.config)
+    r_clean, r_noisy, r_cspec, r_nspec, r_creal, r_cimag, ones, win = out
+    o_clean, o_noisy, o_cspec, o_nspec = O.batch_stft(clean, noisy)
+    assert rel_max(o_clean, r_clean) < 1e-6 and rel_max(o_noisy, r_noisy) < 1e-6
+    assert rel_max(torch.view_as_real(o_cspec), torch.view_as_real(r_cspec)) < 2e-5
+    assert rel_max(torch.view_as_real(o_nspec), torch.view_as_real(r_nspec)) < 2e-5
+    assert r_creal.shape == (3, 1, 201, 33) and ones.shape == (3,) and win.shape == (400,)
+    # the noisy signal ends up with unit RMS; the clean one shares its gain
+    assert torch.allclose(r_noisy.pow(2).mean(-1), torch.ones(3), atol=1e-5)
