@@ -669,6 +669,8 @@ __global__ void __launch_bounds__(128, MINB) attention_v4_kernel(const __half* _
     }
 }
 
+int attention_tc_launch(const __half* qkvh, const __half* Eh, const SebSeq* seq, float* out, cudaStream_t st);   // attention_tc.cu
+
 }  // namespace seb
 
 using namespace seb;
@@ -701,6 +703,8 @@ extern "C" int seb200_attention(const void* qkv, const float* rel_pos_emb, const
     if (e != cudaSuccess) { set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     attr_done = true;
   }
+  if (variant == 3)      // tcgen05 kernel (attention_tc.cu); same inputs as variant 0
+    return attention_tc_launch(reinterpret_cast<const __half*>(qkv), reinterpret_cast<const __half*>(rel_pos_emb_h), seq, out, st);
   const bool band = n > 2 * AT_MAXPOS + 128;     // far-field shortcut pays once a sizeable share of the (query, key) tiles lies beyond the clamp
   if (variant == 0) {
     // 3 or 4 warps (32 query rows each) per CTA, whichever leaves fewer idle warps in the last CTA of a (sequence, head)

@@ -1,0 +1,462 @@
+// attention_tc.cu -- variant 3 of seb200_attention: the Shaw-relative-position attention core (conformer.py:103-122) on
+// tcgen05 tensor cores with every accumulator in tensor memory.
+//
+// One CTA = (sequence, head PAIR, 64-query block); it walks the keys in tiles of 64.  The 128 accumulator lanes are
+// (head-local hl, query parity par, lane l) -> quadrant w = 2 hl + par holds queries i0 + 2 l + par of head 2 hp + hl, so
+// every warp is parity-uniform (what lets the skewed rel-pos read address whole fp16 pairs, see below).
+//
+//   MMA 1a  S[128 x 64]  (fp32) = Aexp[128 x 32] . K[64 x 32]^T     Aexp row = q in its head's 16-wide k slot, zeros in the
+//                                                                  other head's slot; K rows are the natural [token, 2 x 16]
+//                                                                  slice of the q|k|v projection -> per-head q.k
+//   MMA 1b  R[128 x 128] (fp16) = Q[128 x 16] . Ewin[128 x 16]^T    Ewin row c = E[clamp(dtop - c)], dtop = i0 + 63 - j0: all
+//                                                                  127 distinct offsets of a 64 x 64 tile, DESCENDING, so
+//                                                                  the entries a query needs are an ascending run
+//   threads (lane = accumulator row): tcgen05.ld R with pack::16b (half2 words straight from the fp16 accumulator, no
+//           conversion) -> 16 x STS.128 into a thread-private shared-memory row -> 33 x LDS.32 at the row's own offset
+//           (the per-row skew that registers cannot index) -> FHADD (fp32 += one half of a word, a single instruction on
+//           sm_100) onto the content scores from tcgen05.ld S -> lazy running maximum -> ex2 -> fp16 P -> tcgen05.st
+//   MMA 3   O[128 x 32]  (fp32) += P[128 x 64] (A operand in TMEM) . V[64 x 32]   V tile in its natural [key, d] order = an
+//                                                                  MN-major B operand; row sums are kept by the threads
+//
+// TMEM (256 columns, two CTAs per SM): S (64) | R (128) | P (32) | O (32).  A fifth warp streams K, V and the E window of
+// tile t + 3 with zero-filling cp.async into a 4-slot ring (no-swizzle canonical UMMA layouts, 16-byte chunks placed
+// directly) and its lane 0 issues the MMAs.  Four mbarriers: S/R written (tcgen05.commit), S/R read into registers (128
+// threads), P stored (128 threads), O updated (tcgen05.commit).  MMA 1 of tile t + 1 is issued as soon as the threads hold
+// S(t), R(t) in registers, so the next scores are ready when the threads finish the exponentials of tile t: the softmax
+// warps never wait for the tensor pipe in steady state.
+#include "gemm_engine.cuh"   // ptx:: mbarrier / tcgen05 helpers
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+namespace seb {
+
+constexpr int T5_KT = 64, T5_BQ = 64, T5_STAGES = 4, T5_THREADS = 224;
+constexpr int T5_ROWH = 192, T5_MAXPOS = 512, T5_D = 16;
+constexpr int T5_AEXP = 0, T5_QPL = 8192, T5_STAGE0 = 12288;
+constexpr int T5_KS = 0, T5_ES = 4096, T5_VS = 8192, T5_STAGE = 12288;
+constexpr int T5_RSCR = T5_STAGE0 + T5_STAGES * T5_STAGE;
+constexpr int T5_RPITCH = 272;                      // bytes per private R row: 64 words + 4 -> STS.128 and the skewed LDS.32 are both conflict-free
+constexpr int T5_SMEM = T5_RSCR + 128 * T5_RPITCH + 128;
+constexpr uint32_t T5_TS = 0, T5_TR = 64, T5_TP = 192, T5_TO = 224, T5_TCOLS = 256;
+constexpr float T5_LAZY = 8.0f;
+
+namespace ptx {
+// no-swizzle canonical operand: 8-row x 16-byte core matrices; lbo / sbo in bytes (K-major: lbo = next core matrix along K,
+// sbo = next 8-row group; MN-major: sbo = next 8 elements along MN, lbo = next 8 rows along K)
+__device__ __forceinline__ uint64_t umma_desc_ns(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(lbo >> 4) << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+__device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+#define SEB_R32(r, o) "=r"(r[o + 0]), "=r"(r[o + 1]), "=r"(r[o + 2]), "=r"(r[o + 3]), "=r"(r[o + 4]), "=r"(r[o + 5]), "=r"(r[o + 6]), "=r"(r[o + 7]), \
+                      "=r"(r[o + 8]), "=r"(r[o + 9]), "=r"(r[o + 10]), "=r"(r[o + 11]), "=r"(r[o + 12]), "=r"(r[o + 13]), "=r"(r[o + 14]), "=r"(r[o + 15]), \
+                      "=r"(r[o + 16]), "=r"(r[o + 17]), "=r"(r[o + 18]), "=r"(r[o + 19]), "=r"(r[o + 20]), "=r"(r[o + 21]), "=r"(r[o + 22]), "=r"(r[o + 23]), \
+                      "=r"(r[o + 24]), "=r"(r[o + 25]), "=r"(r[o + 26]), "=r"(r[o + 27]), "=r"(r[o + 28]), "=r"(r[o + 29]), "=r"(r[o + 30]), "=r"(r[o + 31])
+#define SEB_L32 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}"
+// 32 fp32 columns of this thread's lane
+template <int O>
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 " SEB_L32 ", [%32];" : SEB_R32(r, O) : "r"(taddr) : "memory");
+}
+// 64 columns holding 16-bit values -> 32 registers (column 2k in the low half of register k)
+template <int O>
+__device__ __forceinline__ void tmem_ld32_pack16(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 " SEB_L32 ", [%32];" : SEB_R32(r, O) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+                 "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]),
+                 "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+                 "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait5() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// Lean bounded wait: try_wait with a suspend-time hint (the warp sleeps in hardware until the phase completes or the hint
+// expires) and a 3-instruction retry loop.  The generic ptx::mbar_wait re-reads the clock every iteration; with two
+// resident CTAs its ~12-instruction spin took issue slots from the other CTA's working warps (43 % of all issued
+// instructions in the first profile).
+#ifndef T5_WAIT_HINT_NS
+#define T5_WAIT_HINT_NS 4000
+#endif
+template <int MODE>
+__device__ __forceinline__ void mbar_wait_lean(uint64_t* bar, uint32_t parity) {
+  if (MODE == 0) { mbar_wait(bar, parity); return; }
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+  for (uint32_t it = 0; it < (1u << 22); ++it) {
+    if (MODE == 2 && it) __nanosleep(40);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (ok) return;
+  }
+  __trap();     // a protocol bug must surface as a launch error, never as a hung GPU
+}
+__device__ __forceinline__ void cp16z(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+// fp32 += one fp16 (a single FHADD on sm_100; the half comes from either half of a 32-bit register)
+__device__ __forceinline__ float fhadd(unsigned short h, float s) {
+  float d;
+  asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(d) : "h"(h), "f"(s));
+  return d;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+}  // namespace ptx
+
+#ifdef T5_TRACE
+__device__ long long t5_trace[2][16][8];     // [role][tile][event] clock64 stamps of one CTA (debug builds only)
+#define T5_STAMP(role, t, ev) do { if (blockIdx.x == T5_TRACE && (t) < 16 && ((role) ? lane == 0 : tid == 0)) t5_trace[role][t][ev] = clock64(); } while (0)
+#else
+#define T5_STAMP(role, t, ev) do { } while (0)
+#endif
+__device__ __forceinline__ long long t5_seq_base(const SebSeq& sq, int seq) {
+  return (long long)(seq / sq.inner) * sq.outer_stride + (seq % sq.inner);
+}
+
+template <int WM, int PK>
+__global__ void __launch_bounds__(T5_THREADS, 2)
+attention_tc_kernel(const __half* __restrict__ qkvh, const __half* __restrict__ Eh, const SebSeq sq, int nqb, float* __restrict__ out) {
+  extern __shared__ uint8_t t5_smraw[];
+  __shared__ uint64_t bar_S, bar_F, bar_P, bar_O, full_bar[T5_STAGES], empty_bar[T5_STAGES];
+  __shared__ uint32_t tmem_base_s;
+  const uint32_t sm0 = (ptx::smem_u32(t5_smraw) + 127u) & ~127u;      // shared-window byte address of the carved buffers
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int qb = blockIdx.x % nqb, sh = blockIdx.x / nqb;
+  const int hp = sh & 1, seq = sh >> 1;
+  const int n = sq.n, i0 = qb * T5_BQ;
+  const long long base = t5_seq_base(sq, seq);
+  const int ntiles = (n + T5_KT - 1) / T5_KT;
+  const __half* seq0 = qkvh + base * T5_ROWH;                           // row 0 of this sequence
+
+  if (tid == 0) {
+    ptx::mbar_init(&bar_S, 1);        // S(t), R(t) written            (tcgen05.commit)
+    ptx::mbar_init(&bar_F, 128);      // S(t), R(t) read into registers (every softmax thread)
+    ptx::mbar_init(&bar_P, 128);      // P(t) stored                    (every softmax thread)
+    ptx::mbar_init(&bar_O, 1);        // O += P(t) V(t) done            (tcgen05.commit)
+    for (int s = 0; s < T5_STAGES; ++s) { ptx::mbar_init(&full_bar[s], 32); ptx::mbar_init(&empty_bar[s], 1); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 4) ptx::tmem_alloc(&tmem_base_s, T5_TCOLS);
+
+  if (warp < 4) {
+    // ---- operand rows of this thread: Aexp (q in its head's slot) and Q (k order permuted like the fragment-ordered E table)
+    const int hl = warp >> 1, par = warp & 1;
+    const int i = i0 + 2 * lane + par;
+    uint4 qlo = make_uint4(0u, 0u, 0u, 0u), qhi = qlo;
+    if (i < n) {
+      const uint4* qp = reinterpret_cast<const uint4*>(seq0 + (long long)i * sq.pos_stride * T5_ROWH + (2 * hp + hl) * T5_D);
+      qlo = __ldg(qp); qhi = __ldg(qp + 1);
+    }
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    const uint32_t arow = sm0 + T5_AEXP + (uint32_t)((tid >> 3) * 512 + (tid & 7) * 16);
+    auto sts128 = [](uint32_t addr, uint4 v) {
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    };
+    sts128(arow + 0 * 128, hl == 0 ? qlo : zero);
+    sts128(arow + 1 * 128, hl == 0 ? qhi : zero);
+    sts128(arow + 2 * 128, hl == 1 ? qlo : zero);
+    sts128(arow + 3 * 128, hl == 1 ? qhi : zero);
+    // E rows are stored as k = 0,1,8,9,2,3,10,11 | 4,5,12,13,6,7,14,15 (ops.pack_rel_pos): the same permutation on q leaves q . E unchanged
+    const uint32_t qrow = sm0 + T5_QPL + (uint32_t)((tid >> 3) * 256 + (tid & 7) * 16);
+    sts128(qrow, make_uint4(qlo.x, qhi.x, qlo.y, qhi.y));
+    sts128(qrow + 128, make_uint4(qlo.z, qhi.z, qlo.w, qhi.w));
+    ptx::fence_proxy_async_smem();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 4) {
+    // ================= loader warp: K, V and the E window of every tile, 8 + 8 + 8 chunks of 16 bytes per lane =================
+    // lane -> (key & 7, chunk) is fixed; a tile is announced on full[slot] two commit groups later (wait_group + proxy fence per lane)
+    const long long key_stride_h = sq.pos_stride * T5_ROWH;              // halfs between consecutive positions
+    const __half* kv_lane = seq0 + (long long)(lane >> 2) * key_stride_h + 64 + hp * 32 + (lane & 3) * 8;
+    const uint32_t k_dst = (uint32_t)(T5_KS + (lane & 3) * 128 + (lane >> 2) * 16);
+    const uint32_t v_dst = (uint32_t)(T5_VS + (lane & 3) * 1024 + (lane >> 2) * 16);
+    const uint32_t e_dst = (uint32_t)(T5_ES + (lane >> 4) * 256 + (lane & 1) * 128 + ((lane >> 1) & 7) * 16);
+    const __half* e_lane = Eh + T5_MAXPOS * T5_D + (lane & 1) * 8;
+    for (int t = 0; t < ntiles + 2; ++t) {
+      if (t < ntiles) {
+        const int slot = t % T5_STAGES;
+        if (t >= T5_STAGES) ptx::mbar_wait_lean<WM>(&empty_bar[slot], (uint32_t)(t / T5_STAGES - 1) & 1u);    // MMA 1 and MMA 3 of tile t - 4 are done
+        const uint32_t st = sm0 + T5_STAGE0 + (uint32_t)(slot * T5_STAGE);
+        const int j0 = t * T5_KT;
+        const int key0 = j0 + (lane >> 2);
+        const __half* src0 = kv_lane + (long long)j0 * key_stride_h;
+        const int d0 = i0 + 63 - j0 - (lane >> 1);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const bool ok = key0 + 8 * k < n;
+          const __half* src = ok ? src0 + (long long)(8 * k) * key_stride_h : seq0;
+          ptx::cp16z(st + k_dst + (uint32_t)(k * 512), src, ok ? 16u : 0u);
+          ptx::cp16z(st + v_dst + (uint32_t)(k * 128), ok ? src + 64 : seq0, ok ? 16u : 0u);
+          int d = d0 - 16 * k;
+          d = d < -T5_MAXPOS ? -T5_MAXPOS : (d > T5_MAXPOS ? T5_MAXPOS : d);
+          ptx::cp16z(st + e_dst + (uint32_t)(k * 512), e_lane + d * T5_D, 16u);
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (t >= 2) {
+        asm volatile("cp.async.wait_group 2;" ::: "memory");     // this lane's chunks of tile t - 2 have landed
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive(&full_bar[(t - 2) % T5_STAGES]);
+      }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  } else if (warp == 5) {
+    // ================= MMA 1 issuer: S(t) = Aexp . K(t)^T,  R(t) = Q . Ewin(t)^T, as soon as S / R of tile t - 1 sit in registers =================
+    if (lane == 0) {
+      constexpr uint32_t IDESC_S = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);                 // f16 x f16 -> f32, N = 64
+      constexpr uint32_t IDESC_R = ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);                            // f16 x f16 -> f16, N = 128
+      const uint32_t tS = tmem_base + T5_TS, tR = tmem_base + T5_TR;
+      const uint64_t a0 = ptx::umma_desc_ns(sm0 + T5_AEXP, 128, 512), a1 = ptx::umma_desc_ns(sm0 + T5_AEXP + 256, 128, 512),
+                     aq = ptx::umma_desc_ns(sm0 + T5_QPL, 128, 256);
+      for (int t = 0; t < ntiles; ++t) {
+        const int slot = t % T5_STAGES;
+        const uint32_t st = sm0 + T5_STAGE0 + (uint32_t)(slot * T5_STAGE);
+        const uint64_t bk = ptx::umma_desc_ns(st + T5_KS, 128, 512), be = ptx::umma_desc_ns(st + T5_ES, 128, 256);
+        ptx::mbar_wait_lean<WM>(&full_bar[slot], (uint32_t)(t / T5_STAGES) & 1u);
+        T5_STAMP(1, t, 0);
+        if (t > 0) ptx::mbar_wait_lean<WM>(&bar_F, (uint32_t)(t - 1) & 1u);
+        T5_STAMP(1, t, 1);
+        ptx::tc_fence_after();
+        ptx::mma_f16_ss(tS, a0, bk, IDESC_S, 0u);
+        ptx::mma_f16_ss(tS, a1, bk + (256 >> 4), IDESC_S, 1u);
+        ptx::mma_f16_ss(tR, aq, be, IDESC_R, 0u);
+        ptx::tc_commit(&bar_S);
+        T5_STAMP(1, t, 2);
+      }
+    }
+  } else if (warp == 6) {
+    // ================= MMA 3 issuer: O += P(t) . V(t); its completion frees P, O (for a rescale) and the ring slot =================
+    if (lane == 0) {
+      constexpr uint32_t IDESC_O = (1u << 4) | (1u << 16) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);    // B MN-major, N = 32
+      const uint32_t tP = tmem_base + T5_TP, tO = tmem_base + T5_TO;
+      for (int t = 0; t < ntiles; ++t) {
+        const int slot = t % T5_STAGES;
+        const uint64_t bv = ptx::umma_desc_ns(sm0 + T5_STAGE0 + (uint32_t)(slot * T5_STAGE) + T5_VS, 128, 1024);
+        ptx::mbar_wait_lean<WM>(&bar_P, (uint32_t)t & 1u);
+        T5_STAMP(1, t, 3);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          ptx::mma_f16_ts(tO, tP + (uint32_t)(ks * 8), bv + (uint64_t)((ks * 256) >> 4), IDESC_O, (t | ks) ? 1u : 0u);
+        ptx::tc_commit(&bar_O);
+        ptx::tc_commit(&empty_bar[slot]);
+        T5_STAMP(1, t, 4);
+      }
+    }
+  } else {
+    // ================= softmax threads: one accumulator row each =================
+    const int hl = warp >> 1, par = warp & 1;
+    const int i = i0 + 2 * lane + par;
+    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+    const uint32_t tS = tmem_base + lane_sel + T5_TS, tR = tmem_base + lane_sel + T5_TR, tP = tmem_base + lane_sel + T5_TP,
+                   tO = tmem_base + lane_sel + T5_TO;
+    const uint32_t myrow = sm0 + T5_RSCR + (uint32_t)(tid * T5_RPITCH);
+    const uint32_t rd = myrow + (uint32_t)((31 - lane) * 4);      // word (cs >> 1) of the row, cs = 63 - par - 2 lane
+    float m = 0.f, l = 0.f;
+    for (int t = 0; t < ntiles; ++t) {
+      T5_STAMP(0, t, 0);
+      ptx::mbar_wait_lean<WM>(&bar_S, (uint32_t)t & 1u);
+      T5_STAMP(0, t, 1);
+      ptx::tc_fence_after();
+      uint32_t w[64];
+      ptx::tmem_ld32_pack16<0>(tR, w);
+      ptx::tmem_ld32_pack16<32>(tR + 64u, w);
+      ptx::tmem_ld_wait();
+      uint32_t sb[64];
+      ptx::tmem_ld32<0>(tS, sb);
+      ptx::tmem_ld32<32>(tS + 32u, sb);
+#pragma unroll
+      for (int q = 0; q < 16; ++q)
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(myrow + q * 16), "r"(w[4 * q]), "r"(w[4 * q + 1]), "r"(w[4 * q + 2]), "r"(w[4 * q + 3]) : "memory");
+      uint32_t x[33];
+#pragma unroll
+      for (int k = 0; k < 33; ++k) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x[k]) : "r"(rd + k * 4) : "memory");
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&bar_F);          // S / R may be overwritten by the next tile's MMA 1
+      T5_STAMP(0, t, 2);
+      float s[64];
+      if (par) {        // cs even: key pair (2p, 2p + 1) = the two halves of word p
+#pragma unroll
+        for (int p = 0; p < 32; ++p) {
+          s[2 * p] = ptx::fhadd((unsigned short)(x[p] & 0xffffu), __uint_as_float(sb[2 * p]));
+          s[2 * p + 1] = ptx::fhadd((unsigned short)(x[p] >> 16), __uint_as_float(sb[2 * p + 1]));
+        }
+      } else {          // cs odd: key 2p = high half of word p, key 2p + 1 = low half of word p + 1
+#pragma unroll
+        for (int p = 0; p < 32; ++p) {
+          s[2 * p] = ptx::fhadd((unsigned short)(x[p] >> 16), __uint_as_float(sb[2 * p]));
+          s[2 * p + 1] = ptx::fhadd((unsigned short)(x[p + 1] & 0xffffu), __uint_as_float(sb[2 * p + 1]));
+        }
+      }
+      const int rem = n - t * T5_KT;
+      if (rem < T5_KT) {                 // last tile: keys beyond the sequence
+#pragma unroll
+        for (int jj = 0; jj < 64; ++jj)
+          if (jj >= rem) s[jj] = -1e30f;
+      }
+      float mx;
+      {
+        float a[22];
+#pragma unroll
+        for (int k = 0; k < 21; ++k) a[k] = ptx::fmax3(s[3 * k], s[3 * k + 1], s[3 * k + 2]);
+        a[21] = s[63];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) a[k] = ptx::fmax3(a[3 * k], a[3 * k + 1], a[3 * k + 2]);
+        a[7] = a[21];
+        a[0] = ptx::fmax3(a[0], a[1], a[2]);
+        a[1] = ptx::fmax3(a[3], a[4], a[5]);
+        mx = fmaxf(ptx::fmax3(a[0], a[1], a[6]), a[7]);
+      }
+      T5_STAMP(0, t, 3);
+      if (t > 0) {                                                    // MMA 3 of tile t - 1 has consumed P and updated O (long since)
+        ptx::mbar_wait_lean<WM>(&bar_O, (uint32_t)(t - 1) & 1u);
+        T5_STAMP(0, t, 4);
+        ptx::tc_fence_after();
+      }
+      if (t == 0) {
+        m = mx;
+      } else {
+        const bool need = mx > m + T5_LAZY;
+        if (__any_sync(0xffffffffu, need)) {       // rare: move the reference maximum, rescale this row of O and its running sum
+          const float mn = need ? mx : m;
+          const float corr = ptx::ex2f(m - mn);
+          m = mn;
+          l *= corr;
+          uint32_t o[32];
+          ptx::tmem_ld32<0>(tO, o);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * corr);
+          ptx::tmem_st32(tO, o);
+        }
+      }
+      uint32_t pw[32];
+      if (!PK) {
+        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#pragma unroll
+        for (int p = 0; p < 32; p += 2) {
+          const float p0 = ptx::ex2f(s[2 * p] - m), p1 = ptx::ex2f(s[2 * p + 1] - m), p2 = ptx::ex2f(s[2 * p + 2] - m), p3 = ptx::ex2f(s[2 * p + 3] - m);
+          l0 += p0; l1 += p1; l2 += p2; l3 += p3;
+          const __half2 h0 = __floats2half2_rn(p0, p1), h1 = __floats2half2_rn(p2, p3);
+          pw[p] = *reinterpret_cast<const uint32_t*>(&h0);
+          pw[p + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+        }
+        l += (l0 + l1) + (l2 + l3);
+      } else {
+      float2 la = make_float2(0.f, 0.f), lb = la;
+      const float2 negm = make_float2(-m, -m);
+#pragma unroll
+      for (int p = 0; p < 32; p += 2) {       // packed fp32x2 (FADD2) for the shift by -m and for the row sums
+        const float2 a = __fadd2_rn(make_float2(s[2 * p], s[2 * p + 1]), negm), b = __fadd2_rn(make_float2(s[2 * p + 2], s[2 * p + 3]), negm);
+        const float2 pa = make_float2(ptx::ex2f(a.x), ptx::ex2f(a.y)), pb = make_float2(ptx::ex2f(b.x), ptx::ex2f(b.y));
+        la = __fadd2_rn(la, pa); lb = __fadd2_rn(lb, pb);
+        const __half2 h0 = __floats2half2_rn(pa.x, pa.y), h1 = __floats2half2_rn(pb.x, pb.y);
+        pw[p] = *reinterpret_cast<const uint32_t*>(&h0);
+        pw[p + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+      }
+      l += (la.x + la.y) + (lb.x + lb.y);
+      }
+      ptx::tmem_st32(tP, pw);
+      T5_STAMP(0, t, 5);
+      ptx::tmem_st_wait5();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&bar_P);
+      T5_STAMP(0, t, 6);
+    }
+    ptx::mbar_wait_lean<WM>(&bar_O, (uint32_t)(ntiles - 1) & 1u);
+    ptx::tc_fence_after();
+    uint32_t o[16];
+    ptx::tmem_ld16(tO + (uint32_t)(hl * 16), o);
+    ptx::tmem_ld_wait();
+    if (i < n) {
+      const float inv = 1.0f / l;
+      float* op = out + (base + (long long)i * sq.pos_stride) * 64 + (2 * hp + hl) * T5_D;
+#pragma unroll
+      for (int c = 0; c < 16; c += 4)
+        *reinterpret_cast<float4*>(op + c) = make_float4(__uint_as_float(o[c]) * inv, __uint_as_float(o[c + 1]) * inv,
+                                                         __uint_as_float(o[c + 2]) * inv, __uint_as_float(o[c + 3]) * inv);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 4) ptx::tmem_dealloc(tmem_base, T5_TCOLS);
+}
+
+#ifdef T5_TRACE
+extern "C" int seb200_t5_trace(long long* host) { return (int)cudaMemcpyFromSymbol(host, t5_trace, sizeof(t5_trace)); }
+#endif
+
+int attention_tc_launch(const __half* qkvh, const __half* Eh, const SebSeq* seq, float* out, cudaStream_t st) {
+  static bool attr_done = false;
+  static int mode = 0;
+  if (!attr_done) {
+    const char* ev = getenv("SEB200_T5_MODE");      // experiment switch: wait mode * 2 + packed
+    mode = ev ? atoi(ev) : 1;
+    cudaError_t e = cudaSuccess;
+#define T5_ATTR(W, P) if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<W, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM);
+    T5_ATTR(0, 0) T5_ATTR(0, 1) T5_ATTR(1, 0) T5_ATTR(1, 1) T5_ATTR(2, 0) T5_ATTR(2, 1)
+    if (e != cudaSuccess) { set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    attr_done = true;
+  }
+  const int nqb = (seq->n + T5_BQ - 1) / T5_BQ;
+  const long long nblocks = (long long)seq->nseq * 2 * nqb;
+  SEB_REQUIRE(nblocks < 2147483647LL, SEB_EINVAL, "attention: grid too large");
+#define T5_GO(W, P) attention_tc_kernel<W, P><<<(unsigned)nblocks, T5_THREADS, T5_SMEM, st>>>(qkvh, Eh, *seq, nqb, out)
+  switch (mode) {
+    case 1: T5_GO(0, 1); break;
+    case 2: T5_GO(1, 0); break;
+    case 3: T5_GO(1, 1); break;
+    case 4: T5_GO(2, 0); break;
+    case 5: T5_GO(2, 1); break;
+    default: T5_GO(0, 0); break;
+  }
+  SEB_CHECK_LAUNCH("attention_tc_kernel");
+  return 0;
+}
+
+}  // namespace seb

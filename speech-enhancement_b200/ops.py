@@ -335,11 +335,11 @@ def attention(qkv, rel_pos_emb, seq: SebSeq, out, variant: int = 0, rel_pos_emb_
     round-1 kernel kept for A/B measurements; variant 1: qkv float32, unscaled (fp32 SIMT cross-check)."""
     _f32c(rel_pos_emb, out)
     require_cuda(qkv)
-    if variant in (0, 2):
+    if variant in (0, 2, 3):
         if qkv.dtype != torch.float16 or not qkv.is_contiguous():
             raise RuntimeError("tensor-core attention reads the float16 q|k|v projection")
         if rel_pos_emb_h is None:       # variant 0 reads the fragment-ordered table, variant 2 the plain fp16 copy
-            rel_pos_emb_h = pack_rel_pos(rel_pos_emb) if variant == 0 else rel_pos_emb.to(torch.float16)
+            rel_pos_emb_h = pack_rel_pos(rel_pos_emb) if variant in (0, 3) else rel_pos_emb.to(torch.float16)
         if rel_pos_emb_h.dtype != torch.float16 or not rel_pos_emb_h.is_contiguous():
             raise RuntimeError("rel_pos_emb_h must be a contiguous float16 copy of the embedding table")
     else:
