@@ -122,6 +122,11 @@ __device__ __forceinline__ void mbar_wait_lean(uint64_t* bar, uint32_t parity) {
   }
   __trap();     // a protocol bug must surface as a launch error, never as a hung GPU
 }
+// L1-allocating variant for the embedding window: beyond the +-512 clamp every row of the window is the SAME table row, and
+// with .cg all CTAs of a long sequence hammer two L2 lines (26 ms instead of ~8 at T = 4801)
+__device__ __forceinline__ void cp16_ca(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp16z(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
 }
@@ -178,6 +183,38 @@ attention_tc_kernel(const __half* __restrict__ qkvh, const __half* __restrict__ 
   }
   if (warp == 4) ptx::tmem_alloc(&tmem_base_s, T5_TCOLS);
 
+  // ---- loader warp state: K, V and the E window of a tile = 8 + 8 + 8 chunks of 16 bytes per lane; lane -> (key & 7, chunk) is fixed
+  const long long key_stride_h = sq.pos_stride * T5_ROWH;              // halfs between consecutive positions
+  const __half* kv_lane = seq0 + (long long)(lane >> 2) * key_stride_h + 64 + hp * 32 + (lane & 3) * 8;
+  const uint32_t k_dst = (uint32_t)(T5_KS + (lane & 3) * 128 + (lane >> 2) * 16);
+  const uint32_t v_dst = (uint32_t)(T5_VS + (lane & 3) * 1024 + (lane >> 2) * 16);
+  const uint32_t e_dst = (uint32_t)(T5_ES + (lane >> 4) * 256 + (lane & 1) * 128 + ((lane >> 1) & 7) * 16);
+  const __half* e_lane = Eh + T5_MAXPOS * T5_D + (lane & 1) * 8;
+  auto issue_tile = [&](int t) {          // one commit group per call (empty past the last tile)
+    if (t < ntiles) {
+      const uint32_t st = sm0 + T5_STAGE0 + (uint32_t)((t % T5_STAGES) * T5_STAGE);
+      const int j0 = t * T5_KT;
+      const int key0 = j0 + (lane >> 2);
+      const __half* src0 = kv_lane + (long long)j0 * key_stride_h;
+      const int d0 = i0 + 63 - j0 - (lane >> 1);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const bool ok = key0 + 8 * k < n;
+        const __half* src = ok ? src0 + (long long)(8 * k) * key_stride_h : seq0;
+        ptx::cp16z(st + k_dst + (uint32_t)(k * 512), src, ok ? 16u : 0u);
+        ptx::cp16z(st + v_dst + (uint32_t)(k * 128), ok ? src + 64 : seq0, ok ? 16u : 0u);
+        int d = d0 - 16 * k;
+        d = d < -T5_MAXPOS ? -T5_MAXPOS : (d > T5_MAXPOS ? T5_MAXPOS : d);
+        ptx::cp16_ca(st + e_dst + (uint32_t)(k * 512), e_lane + d * T5_D);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (warp == 4) {                        // the first two tiles fly under the TMEM allocation, the q loads and the CTA barrier
+    issue_tile(0);
+    issue_tile(1);
+  }
+
   if (warp < 4) {
     // ---- operand rows of this thread: Aexp (q in its head's slot) and Q (k order permuted like the fragment-ordered E table)
     const int hl = warp >> 1, par = warp & 1;
@@ -208,40 +245,16 @@ attention_tc_kernel(const __half* __restrict__ qkvh, const __half* __restrict__ 
   const uint32_t tmem_base = tmem_base_s;
 
   if (warp == 4) {
-    // ================= loader warp: K, V and the E window of every tile, 8 + 8 + 8 chunks of 16 bytes per lane =================
-    // lane -> (key & 7, chunk) is fixed; a tile is announced on full[slot] two commit groups later (wait_group + proxy fence per lane)
-    const long long key_stride_h = sq.pos_stride * T5_ROWH;              // halfs between consecutive positions
-    const __half* kv_lane = seq0 + (long long)(lane >> 2) * key_stride_h + 64 + hp * 32 + (lane & 3) * 8;
-    const uint32_t k_dst = (uint32_t)(T5_KS + (lane & 3) * 128 + (lane >> 2) * 16);
-    const uint32_t v_dst = (uint32_t)(T5_VS + (lane & 3) * 1024 + (lane >> 2) * 16);
-    const uint32_t e_dst = (uint32_t)(T5_ES + (lane >> 4) * 256 + (lane & 1) * 128 + ((lane >> 1) & 7) * 16);
-    const __half* e_lane = Eh + T5_MAXPOS * T5_D + (lane & 1) * 8;
-    for (int t = 0; t < ntiles + 2; ++t) {
-      if (t < ntiles) {
-        const int slot = t % T5_STAGES;
-        if (t >= T5_STAGES) ptx::mbar_wait_lean<WM>(&empty_bar[slot], (uint32_t)(t / T5_STAGES - 1) & 1u);    // MMA 1 and MMA 3 of tile t - 4 are done
-        const uint32_t st = sm0 + T5_STAGE0 + (uint32_t)(slot * T5_STAGE);
-        const int j0 = t * T5_KT;
-        const int key0 = j0 + (lane >> 2);
-        const __half* src0 = kv_lane + (long long)j0 * key_stride_h;
-        const int d0 = i0 + 63 - j0 - (lane >> 1);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const bool ok = key0 + 8 * k < n;
-          const __half* src = ok ? src0 + (long long)(8 * k) * key_stride_h : seq0;
-          ptx::cp16z(st + k_dst + (uint32_t)(k * 512), src, ok ? 16u : 0u);
-          ptx::cp16z(st + v_dst + (uint32_t)(k * 128), ok ? src + 64 : seq0, ok ? 16u : 0u);
-          int d = d0 - 16 * k;
-          d = d < -T5_MAXPOS ? -T5_MAXPOS : (d > T5_MAXPOS ? T5_MAXPOS : d);
-          ptx::cp16z(st + e_dst + (uint32_t)(k * 512), e_lane + d * T5_D, 16u);
-        }
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      if (t >= 2) {
-        asm volatile("cp.async.wait_group 2;" ::: "memory");     // this lane's chunks of tile t - 2 have landed
+    // ================= loader warp (continued): tiles 0 and 1 were issued before the CTA barrier =================
+    for (int t = 2; t < ntiles + 2; ++t) {
+      {                           // announce tile t - 2 first: it never waits behind the slot release below
+        asm volatile("cp.async.wait_group 1;" ::: "memory");     // all groups but the newest (tile t - 1): this lane's chunks of tile t - 2 have landed
         ptx::fence_proxy_async_smem();
         ptx::mbar_arrive(&full_bar[(t - 2) % T5_STAGES]);
       }
+      if (t >= T5_STAGES && t < ntiles)
+        ptx::mbar_wait_lean<WM>(&empty_bar[t % T5_STAGES], (uint32_t)(t / T5_STAGES - 1) & 1u);    // MMA 1 and MMA 3 of tile t - 4 are done
+      issue_tile(t);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else if (warp == 5) {
@@ -306,7 +319,7 @@ attention_tc_kernel(const __half* __restrict__ qkvh, const __half* __restrict__ 
       ptx::tmem_ld32_pack16<0>(tR, w);
       ptx::tmem_ld32_pack16<32>(tR + 64u, w);
       ptx::tmem_ld_wait();
-      uint32_t sb[64];
+      uint32_t sb[64];                   // in flight under the shared-memory round trip (holding w and sb together spills)
       ptx::tmem_ld32<0>(tS, sb);
       ptx::tmem_ld32<32>(tS + 32u, sb);
 #pragma unroll
@@ -317,7 +330,7 @@ attention_tc_kernel(const __half* __restrict__ qkvh, const __half* __restrict__ 
       for (int k = 0; k < 33; ++k) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x[k]) : "r"(rd + k * 4) : "memory");
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
-      ptx::mbar_arrive(&bar_F);          // S / R may be overwritten by the next tile's MMA 1
+      ptx::mbar_arrive(&bar_F);          // S / R sit in registers: the next tile's MMA 1 may overwrite them
       T5_STAMP(0, t, 2);
       float s[64];
       if (par) {        // cs even: key pair (2p, 2p + 1) = the two halves of word p

@@ -142,7 +142,7 @@ class TSCNet(nn.Module):
         self.num_channel = ch
         self.num_features = num_features
         self.engine = ops.default_engine()     # "tcgen05" | "simt" main loop of the GEMM engine
-        self.attention_variant = 0             # 0 tensor-core, 1 SIMT cross-check
+        self.attention_variant = 0             # 0 tensor-core (mma.sync, fastest), 3 tcgen05 / TMEM kernel (attention_tc.cu), 1 SIMT cross-check
         self.fuse_dwconv_pw2 = False           # opt-in: depthwise conv + pointwise 128 -> 64 in one kernel (seb200_dwconv_pw2); measured
                                                # 21.5 ms vs 16.2 ms for the two-kernel path at configs[1], so off by default
         self._packed: Optional[Dict[str, object]] = None
@@ -296,10 +296,10 @@ class TSCNet(nn.Module):
             ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_SWISH, M=M, w=P[f"{p}.ff1.w1"], a=[x], lda=64, ln=P[f"{p}.ff1.ln"], out=h, ldo=256, engine=eng, label="ffn1")
             ops.gemm(loader=LOAD_ROWS, epilogue=EPI_RESID, M=M, w=P[f"{p}.ff1.w2"], a=[h], lda=256, out=y, ldo=64, resid=x, ldr=64, alpha=0.5, engine=eng, label="ffn2")
         # y += Attn(LN(y))
-        if self.attention_variant == 0:      # fp16 projection (q pre-scaled) feeding the tensor-core attention
+        if self.attention_variant in (0, 3):      # fp16 projection (q pre-scaled) feeding the tensor-core attention
             qkv_h = qkv.view(-1).view(torch.float16)[:M * 192].view(M, 192)
             ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_QKV_F16, M=M, w=P[f"{p}.attn.qkv"], a=[y], lda=64, ln=P[f"{p}.attn.ln"], out=qkv_h, ldo=192, engine=eng, label="qkv")
-            ops.attention(qkv_h, P[f"{p}.attn.emb"], seq, o, 0, P[f"{p}.attn.emb_h"])
+            ops.attention(qkv_h, P[f"{p}.attn.emb"], seq, o, self.attention_variant, P[f"{p}.attn.emb_h"])
         else:                                # fp32 projection + fp32 SIMT attention (cross-check path)
             ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_BIAS, M=M, w=P[f"{p}.attn.qkv"], a=[y], lda=64, ln=P[f"{p}.attn.ln"], out=qkv, ldo=192, engine=eng, label="qkv")
             ops.attention(qkv, P[f"{p}.attn.emb"], seq, o, 1)

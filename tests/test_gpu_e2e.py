@@ -83,6 +83,21 @@ def test_stages_against_oracle(engine):
     assert rel_max(y_g, y_o) < WAVE_TOL
 
 
+def test_tcgen05_attention_end_to_end():
+    """the whole path with the tcgen05 / TMEM attention kernel (attention_variant = 3) inside the north_star tolerances,
+    on a clip long enough for the +-512 clamp, and bit-for-bit deterministic"""
+    sd = weights.synth_state_dict(4)
+    model = _model(4, "tcgen05")
+    model.attention_variant = 3
+    noisy, clean = weights.synth_wave(1, 60000, seed=11, kind="speech")
+    with torch.no_grad():
+        y_o = O.predict(noisy, sd, chunk=8)
+    enh = se_b200.EnhancerB200(model)
+    y_g = enh(noisy.to(DEV)).cpu()
+    assert rel_max(y_g, y_o) < WAVE_TOL
+    assert torch.equal(enh(noisy.to(DEV)).cpu(), y_g)
+
+
 def test_fp32_path_is_fp32_exact():
     """SIMT GEMM engine + SIMT attention: every contraction in fp32 -> agreement with the oracle at fp32 noise level"""
     sd = weights.synth_state_dict(4)

@@ -320,7 +320,7 @@ def _attention_core_ref(qkv_seq, emb):
     return (dots.softmax(-1) @ v).permute(0, 2, 1, 3).reshape(S, n, 64)
 
 
-@pytest.mark.parametrize("variant", [1, 0, 2])
+@pytest.mark.parametrize("variant", [1, 0, 2, 3])     # 3 = the tcgen05 / TMEM kernel (attention_tc.cu)
 @pytest.mark.parametrize("axis,B,T,Fh", [("freq", 2, 5, 101), ("time", 1, 150, 3), ("time", 1, 700, 2), ("freq", 1, 3, 64),
                                           ("time", 1, 641, 2), ("time", 2, 97, 1), ("time", 1, 3, 2), ("freq", 1, 2, 9), ("time", 1, 40, 1), ("time", 1, 1400, 1)])     # 641 = 10 x 64 + 1: the 16-key tail body, 3-warp CTAs; 1400 > 2*512 + 128: far-field (clamped) tiles take the constant shortcut
 def test_attention(variant, axis, B, T, Fh):
@@ -337,7 +337,7 @@ def test_attention(variant, axis, B, T, Fh):
     assert rel_max(out.view(B, T, Fh, 64).cpu(), ref) < tol
 
 
-@pytest.mark.parametrize("variant", [0, 2])
+@pytest.mark.parametrize("variant", [0, 2, 3])
 def test_attention_peaky_logits(variant):
     """large, sharply peaked logits: the lazy running maximum of variant 0 has to move its reference (and rescale) often"""
     B, T, Fh = 1, 300, 2
