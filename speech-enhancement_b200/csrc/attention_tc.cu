@@ -27,6 +27,7 @@
 #include "gemm_engine.cuh"   // ptx:: mbarrier / tcgen05 helpers
 #include <cuda_fp16.h>
 #include <stdlib.h>
+#include <type_traits>
 
 namespace seb {
 
@@ -85,6 +86,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_pack16(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.pack::16b.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st8u(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
@@ -292,9 +303,10 @@ attention_tc_kernel(const __half* __restrict__ qkvh, const __half* __restrict__ 
         ptx::mbar_wait_lean<WM>(&bar_P, (uint32_t)t & 1u);
         T5_STAMP(1, t, 3);
         ptx::tc_fence_after();
+        const int nks = (n - t * T5_KT <= 16) ? 1 : 4;       // short last tile: the threads stored P for 16 keys only
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
-          ptx::mma_f16_ts(tO, tP + (uint32_t)(ks * 8), bv + (uint64_t)((ks * 256) >> 4), IDESC_O, (t | ks) ? 1u : 0u);
+          if (ks < nks) ptx::mma_f16_ts(tO, tP + (uint32_t)(ks * 8), bv + (uint64_t)((ks * 256) >> 4), IDESC_O, (t | ks) ? 1u : 0u);
         ptx::tc_commit(&bar_O);
         ptx::tc_commit(&empty_bar[slot]);
         T5_STAMP(1, t, 4);
@@ -310,60 +322,65 @@ attention_tc_kernel(const __half* __restrict__ qkvh, const __half* __restrict__ 
     const uint32_t myrow = sm0 + T5_RSCR + (uint32_t)(tid * T5_RPITCH);
     const uint32_t rd = myrow + (uint32_t)((31 - lane) * 4);      // word (cs >> 1) of the row, cs = 63 - par - 2 lane
     float m = 0.f, l = 0.f;
-    for (int t = 0; t < ntiles; ++t) {
+    // One key tile.  NK = keys this thread processes: 64, or 16 for a short last tile (641 = 10 x 64 + 1: the eleventh tile
+    // holds ONE live key; the MMAs still run at N = 64 on zero-filled keys, but the threads -- the bound -- do a quarter of the work
+    // and MMA 3 contracts over 16 keys only).
+    auto tile_body = [&](auto nk_tag, int t) {
+      constexpr int NK = decltype(nk_tag)::value;
+      constexpr int NWR = NK == 64 ? 64 : 40;          // staged R words: 31 + NK / 2 + 1, rounded up to whole STS.128
       T5_STAMP(0, t, 0);
       ptx::mbar_wait_lean<WM>(&bar_S, (uint32_t)t & 1u);
       T5_STAMP(0, t, 1);
       ptx::tc_fence_after();
-      uint32_t w[64];
-      ptx::tmem_ld32_pack16<0>(tR, w);
-      ptx::tmem_ld32_pack16<32>(tR + 64u, w);
-      ptx::tmem_ld_wait();
-      uint32_t sb[64];                   // in flight under the shared-memory round trip (holding w and sb together spills)
-      ptx::tmem_ld32<0>(tS, sb);
-      ptx::tmem_ld32<32>(tS + 32u, sb);
+      {
+        uint32_t w[64];
+        ptx::tmem_ld32_pack16<0>(tR, w);
+        if (NK == 64) ptx::tmem_ld32_pack16<32>(tR + 64u, w); else ptx::tmem_ld16_pack16(tR + 64u, w + 32);
+        ptx::tmem_ld_wait();
 #pragma unroll
-      for (int q = 0; q < 16; ++q)
-        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(myrow + q * 16), "r"(w[4 * q]), "r"(w[4 * q + 1]), "r"(w[4 * q + 2]), "r"(w[4 * q + 3]) : "memory");
-      uint32_t x[33];
+        for (int q = 0; q < NWR / 4; ++q)
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(myrow + q * 16), "r"(w[4 * q]), "r"(w[4 * q + 1]), "r"(w[4 * q + 2]), "r"(w[4 * q + 3]) : "memory");
+      }
+      uint32_t sb[NK];                   // in flight under the shared-memory round trip
+      if (NK == 64) { ptx::tmem_ld32<0>(tS, sb); ptx::tmem_ld32<32>(tS + 32u, sb); } else ptx::tmem_ld16(tS, sb);
+      uint32_t x[NK / 2 + 1];
 #pragma unroll
-      for (int k = 0; k < 33; ++k) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x[k]) : "r"(rd + k * 4) : "memory");
+      for (int k = 0; k < NK / 2 + 1; ++k) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x[k]) : "r"(rd + k * 4) : "memory");
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       ptx::mbar_arrive(&bar_F);          // S / R sit in registers: the next tile's MMA 1 may overwrite them
       T5_STAMP(0, t, 2);
-      float s[64];
+      float s[NK];
       if (par) {        // cs even: key pair (2p, 2p + 1) = the two halves of word p
 #pragma unroll
-        for (int p = 0; p < 32; ++p) {
+        for (int p = 0; p < NK / 2; ++p) {
           s[2 * p] = ptx::fhadd((unsigned short)(x[p] & 0xffffu), __uint_as_float(sb[2 * p]));
           s[2 * p + 1] = ptx::fhadd((unsigned short)(x[p] >> 16), __uint_as_float(sb[2 * p + 1]));
         }
       } else {          // cs odd: key 2p = high half of word p, key 2p + 1 = low half of word p + 1
 #pragma unroll
-        for (int p = 0; p < 32; ++p) {
+        for (int p = 0; p < NK / 2; ++p) {
           s[2 * p] = ptx::fhadd((unsigned short)(x[p] >> 16), __uint_as_float(sb[2 * p]));
           s[2 * p + 1] = ptx::fhadd((unsigned short)(x[p + 1] & 0xffffu), __uint_as_float(sb[2 * p + 1]));
         }
       }
       const int rem = n - t * T5_KT;
-      if (rem < T5_KT) {                 // last tile: keys beyond the sequence
+      if (rem < NK) {                    // last tile: keys beyond the sequence
 #pragma unroll
-        for (int jj = 0; jj < 64; ++jj)
+        for (int jj = 0; jj < NK; ++jj)
           if (jj >= rem) s[jj] = -1e30f;
       }
       float mx;
       {
-        float a[22];
+        constexpr int N1 = (NK + 2) / 3;
+        float a[N1];
 #pragma unroll
-        for (int k = 0; k < 21; ++k) a[k] = ptx::fmax3(s[3 * k], s[3 * k + 1], s[3 * k + 2]);
-        a[21] = s[63];
+        for (int k = 0; k < NK / 3; ++k) a[k] = ptx::fmax3(s[3 * k], s[3 * k + 1], s[3 * k + 2]);
+        a[N1 - 1] = s[NK - 1];                                       // NK = 64 and 16 both leave exactly one element over
+        mx = a[0];
 #pragma unroll
-        for (int k = 0; k < 7; ++k) a[k] = ptx::fmax3(a[3 * k], a[3 * k + 1], a[3 * k + 2]);
-        a[7] = a[21];
-        a[0] = ptx::fmax3(a[0], a[1], a[2]);
-        a[1] = ptx::fmax3(a[3], a[4], a[5]);
-        mx = fmaxf(ptx::fmax3(a[0], a[1], a[6]), a[7]);
+        for (int k = 1; k + 1 < N1; k += 2) mx = ptx::fmax3(mx, a[k], a[k + 1]);
+        if ((N1 & 1) == 0) mx = fmaxf(mx, a[N1 - 1]);
       }
       T5_STAMP(0, t, 3);
       if (t > 0) {                                                    // MMA 3 of tile t - 1 has consumed P and updated O (long since)
@@ -388,23 +405,11 @@ attention_tc_kernel(const __half* __restrict__ qkvh, const __half* __restrict__ 
           ptx::tmem_st32(tO, o);
         }
       }
-      uint32_t pw[32];
-      if (!PK) {
-        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-#pragma unroll
-        for (int p = 0; p < 32; p += 2) {
-          const float p0 = ptx::ex2f(s[2 * p] - m), p1 = ptx::ex2f(s[2 * p + 1] - m), p2 = ptx::ex2f(s[2 * p + 2] - m), p3 = ptx::ex2f(s[2 * p + 3] - m);
-          l0 += p0; l1 += p1; l2 += p2; l3 += p3;
-          const __half2 h0 = __floats2half2_rn(p0, p1), h1 = __floats2half2_rn(p2, p3);
-          pw[p] = *reinterpret_cast<const uint32_t*>(&h0);
-          pw[p + 1] = *reinterpret_cast<const uint32_t*>(&h1);
-        }
-        l += (l0 + l1) + (l2 + l3);
-      } else {
+      uint32_t pw[NK / 2];
       float2 la = make_float2(0.f, 0.f), lb = la;
       const float2 negm = make_float2(-m, -m);
 #pragma unroll
-      for (int p = 0; p < 32; p += 2) {       // packed fp32x2 (FADD2) for the shift by -m and for the row sums
+      for (int p = 0; p < NK / 2; p += 2) {       // packed fp32x2 (FADD2) for the shift by -m and for the row sums
         const float2 a = __fadd2_rn(make_float2(s[2 * p], s[2 * p + 1]), negm), b = __fadd2_rn(make_float2(s[2 * p + 2], s[2 * p + 3]), negm);
         const float2 pa = make_float2(ptx::ex2f(a.x), ptx::ex2f(a.y)), pb = make_float2(ptx::ex2f(b.x), ptx::ex2f(b.y));
         la = __fadd2_rn(la, pa); lb = __fadd2_rn(lb, pb);
@@ -413,13 +418,25 @@ attention_tc_kernel(const __half* __restrict__ qkvh, const __half* __restrict__ 
         pw[p + 1] = *reinterpret_cast<const uint32_t*>(&h1);
       }
       l += (la.x + la.y) + (lb.x + lb.y);
-      }
-      ptx::tmem_st32(tP, pw);
+      if (NK == 64) ptx::tmem_st32(tP, pw); else ptx::tmem_st8u(tP, pw);
       T5_STAMP(0, t, 5);
       ptx::tmem_st_wait5();
       ptx::tc_fence_before();
       ptx::mbar_arrive(&bar_P);
       T5_STAMP(0, t, 6);
+    };
+    if (i0 + par >= n) {                // every query row of this warp lies past the sequence (last block): keep the protocol, skip the work
+      for (int t = 0; t < ntiles; ++t) {
+        ptx::mbar_wait_lean<WM>(&bar_S, (uint32_t)t & 1u);
+        ptx::mbar_arrive(&bar_F);
+        if (t > 0) ptx::mbar_wait_lean<WM>(&bar_O, (uint32_t)(t - 1) & 1u);
+        ptx::mbar_arrive(&bar_P);         // this warp's P rows stay stale: they only feed its own (never stored) rows of O
+      }
+    } else {
+      for (int t = 0; t < ntiles; ++t) {
+        if (n - t * T5_KT <= 16) tile_body(std::integral_constant<int, 16>{}, t);
+        else tile_body(std::integral_constant<int, 64>{}, t);
+      }
     }
     ptx::mbar_wait_lean<WM>(&bar_O, (uint32_t)(ntiles - 1) & 1u);
     ptx::tc_fence_after();
