@@ -165,6 +165,12 @@ __device__ long long t5_trace[2][16][8];     // [role][tile][event] clock64 stam
 #else
 #define T5_STAMP(role, t, ev) do { } while (0)
 #endif
+// +1 / -1: every (query, key) offset of tile t of the 64-query block at i0 lies at or beyond +512 / -512 (conformer.py:108 clamps
+// the distance, so the rel-pos logit is a per-query constant); 0: the tile needs the R GEMM
+__device__ __forceinline__ int t5_far(int i0, int t) {
+  const int j0 = t * T5_KT;
+  return (i0 - (j0 + T5_KT - 1) >= T5_MAXPOS) ? 1 : ((i0 + T5_BQ - 1 - j0 <= -T5_MAXPOS) ? -1 : 0);
+}
 __device__ __forceinline__ long long t5_seq_base(const SebSeq& sq, int seq) {
   return (long long)(seq / sq.inner) * sq.outer_stride + (seq % sq.inner);
 }
@@ -208,15 +214,18 @@ attention_tc_kernel(const __half* __restrict__ qkvh, const __half* __restrict__ 
       const int key0 = j0 + (lane >> 2);
       const __half* src0 = kv_lane + (long long)j0 * key_stride_h;
       const int d0 = i0 + 63 - j0 - (lane >> 1);
+      const bool need_e = t5_far(i0, t) == 0;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const bool ok = key0 + 8 * k < n;
         const __half* src = ok ? src0 + (long long)(8 * k) * key_stride_h : seq0;
         ptx::cp16z(st + k_dst + (uint32_t)(k * 512), src, ok ? 16u : 0u);
         ptx::cp16z(st + v_dst + (uint32_t)(k * 128), ok ? src + 64 : seq0, ok ? 16u : 0u);
-        int d = d0 - 16 * k;
-        d = d < -T5_MAXPOS ? -T5_MAXPOS : (d > T5_MAXPOS ? T5_MAXPOS : d);
-        ptx::cp16_ca(st + e_dst + (uint32_t)(k * 512), e_lane + d * T5_D);
+        if (need_e) {
+          int d = d0 - 16 * k;
+          d = d < -T5_MAXPOS ? -T5_MAXPOS : (d > T5_MAXPOS ? T5_MAXPOS : d);
+          ptx::cp16_ca(st + e_dst + (uint32_t)(k * 512), e_lane + d * T5_D);
+        }
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -287,7 +296,7 @@ attention_tc_kernel(const __half* __restrict__ qkvh, const __half* __restrict__ 
         ptx::tc_fence_after();
         ptx::mma_f16_ss(tS, a0, bk, IDESC_S, 0u);
         ptx::mma_f16_ss(tS, a1, bk + (256 >> 4), IDESC_S, 1u);
-        ptx::mma_f16_ss(tR, aq, be, IDESC_R, 0u);
+        if (t5_far(i0, t) == 0) ptx::mma_f16_ss(tR, aq, be, IDESC_R, 0u);
         ptx::tc_commit(&bar_S);
         T5_STAMP(1, t, 2);
       }
@@ -322,17 +331,37 @@ attention_tc_kernel(const __half* __restrict__ qkvh, const __half* __restrict__ 
     const uint32_t myrow = sm0 + T5_RSCR + (uint32_t)(tid * T5_RPITCH);
     const uint32_t rd = myrow + (uint32_t)((31 - lane) * 4);      // word (cs >> 1) of the row, cs = 63 - par - 2 lane
     float m = 0.f, l = 0.f;
+    // far-field constants of this row: q . E[1024] (offsets >= +512) and q . E[0] (offsets <= -512), fp32 from the fp16 operands
+    float c_hi = 0.f, c_lo = 0.f;
+    if (n > T5_MAXPOS) {
+      const uint32_t qw = sm0 + T5_QPL + (uint32_t)((tid >> 3) * 256 + (tid & 7) * 16);      // this row of Q (same k permutation as the E table)
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        uint4 qv;
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(qv.x), "=r"(qv.y), "=r"(qv.z), "=r"(qv.w) : "r"(qw + ch * 128) : "memory");
+        const uint4 eh = __ldg(reinterpret_cast<const uint4*>(Eh + 2 * T5_MAXPOS * T5_D) + ch), el = __ldg(reinterpret_cast<const uint4*>(Eh) + ch);
+        const uint32_t qq[4] = {qv.x, qv.y, qv.z, qv.w}, hh[4] = {eh.x, eh.y, eh.z, eh.w}, ll[4] = {el.x, el.y, el.z, el.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 qf = __half22float2(*reinterpret_cast<const __half2*>(&qq[k]));
+          const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hh[k])), lf = __half22float2(*reinterpret_cast<const __half2*>(&ll[k]));
+          c_hi = fmaf(qf.x, hf.x, fmaf(qf.y, hf.y, c_hi));
+          c_lo = fmaf(qf.x, lf.x, fmaf(qf.y, lf.y, c_lo));
+        }
+      }
+    }
     // One key tile.  NK = keys this thread processes: 64, or 16 for a short last tile (641 = 10 x 64 + 1: the eleventh tile
     // holds ONE live key; the MMAs still run at N = 64 on zero-filled keys, but the threads -- the bound -- do a quarter of the work
     // and MMA 3 contracts over 16 keys only).
-    auto tile_body = [&](auto nk_tag, int t) {
+    auto tile_body = [&](auto nk_tag, auto far_tag, int t, float cadd) {
       constexpr int NK = decltype(nk_tag)::value;
+      constexpr bool FAR = decltype(far_tag)::value;     // every offset of the tile lies beyond the +-512 clamp: the rel-pos logit is the per-row constant cadd
       constexpr int NWR = NK == 64 ? 64 : 40;          // staged R words: 31 + NK / 2 + 1, rounded up to whole STS.128
       T5_STAMP(0, t, 0);
       ptx::mbar_wait_lean<WM>(&bar_S, (uint32_t)t & 1u);
       T5_STAMP(0, t, 1);
       ptx::tc_fence_after();
-      {
+      if (!FAR) {
         uint32_t w[64];
         ptx::tmem_ld32_pack16<0>(tR, w);
         if (NK == 64) ptx::tmem_ld32_pack16<32>(tR + 64u, w); else ptx::tmem_ld16_pack16(tR + 64u, w + 32);
@@ -344,14 +373,19 @@ attention_tc_kernel(const __half* __restrict__ qkvh, const __half* __restrict__ 
       uint32_t sb[NK];                   // in flight under the shared-memory round trip
       if (NK == 64) { ptx::tmem_ld32<0>(tS, sb); ptx::tmem_ld32<32>(tS + 32u, sb); } else ptx::tmem_ld16(tS, sb);
       uint32_t x[NK / 2 + 1];
+      if (!FAR) {
 #pragma unroll
-      for (int k = 0; k < NK / 2 + 1; ++k) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x[k]) : "r"(rd + k * 4) : "memory");
+        for (int k = 0; k < NK / 2 + 1; ++k) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x[k]) : "r"(rd + k * 4) : "memory");
+      }
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       ptx::mbar_arrive(&bar_F);          // S / R sit in registers: the next tile's MMA 1 may overwrite them
       T5_STAMP(0, t, 2);
       float s[NK];
-      if (par) {        // cs even: key pair (2p, 2p + 1) = the two halves of word p
+      if (FAR) {
+#pragma unroll
+        for (int jj = 0; jj < NK; ++jj) s[jj] = __uint_as_float(sb[jj]);
+      } else if (par) {        // cs even: key pair (2p, 2p + 1) = the two halves of word p
 #pragma unroll
         for (int p = 0; p < NK / 2; ++p) {
           s[2 * p] = ptx::fhadd((unsigned short)(x[p] & 0xffffu), __uint_as_float(sb[2 * p]));
@@ -381,6 +415,7 @@ attention_tc_kernel(const __half* __restrict__ qkvh, const __half* __restrict__ 
 #pragma unroll
         for (int k = 1; k + 1 < N1; k += 2) mx = ptx::fmax3(mx, a[k], a[k + 1]);
         if ((N1 & 1) == 0) mx = fmaxf(mx, a[N1 - 1]);
+        if (FAR) mx += cadd;
       }
       T5_STAMP(0, t, 3);
       if (t > 0) {                                                    // MMA 3 of tile t - 1 has consumed P and updated O (long since)
@@ -407,7 +442,7 @@ attention_tc_kernel(const __half* __restrict__ qkvh, const __half* __restrict__ 
       }
       uint32_t pw[NK / 2];
       float2 la = make_float2(0.f, 0.f), lb = la;
-      const float2 negm = make_float2(-m, -m);
+      const float2 negm = FAR ? make_float2(cadd - m, cadd - m) : make_float2(-m, -m);
 #pragma unroll
       for (int p = 0; p < NK / 2; p += 2) {       // packed fp32x2 (FADD2) for the shift by -m and for the row sums
         const float2 a = __fadd2_rn(make_float2(s[2 * p], s[2 * p + 1]), negm), b = __fadd2_rn(make_float2(s[2 * p + 2], s[2 * p + 3]), negm);
@@ -434,8 +469,12 @@ attention_tc_kernel(const __half* __restrict__ qkvh, const __half* __restrict__ 
       }
     } else {
       for (int t = 0; t < ntiles; ++t) {
-        if (n - t * T5_KT <= 16) tile_body(std::integral_constant<int, 16>{}, t);
-        else tile_body(std::integral_constant<int, 64>{}, t);
+        const int far = t5_far(i0, t);
+        const bool tail = n - t * T5_KT <= 16;           // the loader and the MMA issuer key on t5_far alone: a short last tile can be far as well
+        if (far && tail) tile_body(std::integral_constant<int, 16>{}, std::true_type{}, t, far > 0 ? c_hi : c_lo);
+        else if (far) tile_body(std::integral_constant<int, 64>{}, std::true_type{}, t, far > 0 ? c_hi : c_lo);
+        else if (tail) tile_body(std::integral_constant<int, 16>{}, std::false_type{}, t, 0.f);
+        else tile_body(std::integral_constant<int, 64>{}, std::false_type{}, t, 0.f);
       }
     }
     ptx::mbar_wait_lean<WM>(&bar_O, (uint32_t)(ntiles - 1) & 1u);

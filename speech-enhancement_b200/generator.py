@@ -142,7 +142,10 @@ class TSCNet(nn.Module):
         self.num_channel = ch
         self.num_features = num_features
         self.engine = ops.default_engine()     # "tcgen05" | "simt" main loop of the GEMM engine
-        self.attention_variant = 0             # 0 tensor-core (mma.sync, fastest), 3 tcgen05 / TMEM kernel (attention_tc.cu), 1 SIMT cross-check
+        self.attention_variant = 0             # 0 tensor-core (mma.sync), 3 tcgen05 / TMEM kernel (attention_tc.cu), 1 SIMT cross-check
+        # sequences at least this long take the tcgen05 kernel when attention_variant == 0 (measured: 4.40 vs 4.91 ms at n = 4801,
+        # 8.3 vs 7.8 ms at n = 641, 3.3 vs 2.3 ms at n = 101 -- tools/attn_tc_check.py)
+        self.attention_tc_min_len = 2048
         self.fuse_dwconv_pw2 = False           # opt-in: depthwise conv + pointwise 128 -> 64 in one kernel (seb200_dwconv_pw2); measured
                                                # 21.5 ms vs 16.2 ms for the two-kernel path at configs[1], so off by default
         self._packed: Optional[Dict[str, object]] = None
@@ -299,7 +302,8 @@ class TSCNet(nn.Module):
         if self.attention_variant in (0, 3):      # fp16 projection (q pre-scaled) feeding the tensor-core attention
             qkv_h = qkv.view(-1).view(torch.float16)[:M * 192].view(M, 192)
             ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_QKV_F16, M=M, w=P[f"{p}.attn.qkv"], a=[y], lda=64, ln=P[f"{p}.attn.ln"], out=qkv_h, ldo=192, engine=eng, label="qkv")
-            ops.attention(qkv_h, P[f"{p}.attn.emb"], seq, o, self.attention_variant, P[f"{p}.attn.emb_h"])
+            variant = 3 if (self.attention_variant == 0 and seq.n >= self.attention_tc_min_len) else self.attention_variant
+            ops.attention(qkv_h, P[f"{p}.attn.emb"], seq, o, variant, P[f"{p}.attn.emb_h"])
         else:                                # fp32 projection + fp32 SIMT attention (cross-check path)
             ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_BIAS, M=M, w=P[f"{p}.attn.qkv"], a=[y], lda=64, ln=P[f"{p}.attn.ln"], out=qkv, ldo=192, engine=eng, label="qkv")
             ops.attention(qkv, P[f"{p}.attn.emb"], seq, o, 1)
