@@ -31,7 +31,7 @@
 
 namespace seb {
 
-constexpr int T5_KT = 64, T5_BQ = 64, T5_STAGES = 4, T5_THREADS = 224;
+constexpr int T5_KT = 64, T5_BQ = 64, T5_STAGES = 4, T5_THREADS = 192;
 constexpr int T5_ROWH = 192, T5_MAXPOS = 512, T5_D = 16;
 constexpr int T5_AEXP = 0, T5_QPL = 8192, T5_STAGE0 = 12288;
 constexpr int T5_KS = 0, T5_ES = 4096, T5_VS = 8192, T5_STAGE = 12288;
@@ -272,20 +272,25 @@ attention_tc_kernel(const __half* __restrict__ qkvh, const __half* __restrict__ 
         ptx::fence_proxy_async_smem();
         ptx::mbar_arrive(&full_bar[(t - 2) % T5_STAGES]);
       }
-      if (t >= T5_STAGES && t < ntiles)
-        ptx::mbar_wait_lean<WM>(&empty_bar[t % T5_STAGES], (uint32_t)(t / T5_STAGES - 1) & 1u);    // MMA 1 and MMA 3 of tile t - 4 are done
+      if (t >= T5_STAGES && t < ntiles) {    // MMA 1 and MMA 3 of tile t - 4 are done; one lane polls, the others sleep at the warp barrier
+        if (lane == 0) ptx::mbar_wait_lean<WM>(&empty_bar[t % T5_STAGES], (uint32_t)(t / T5_STAGES - 1) & 1u);
+        __syncwarp();
+      }
       issue_tile(t);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else if (warp == 5) {
-    // ================= MMA 1 issuer: S(t) = Aexp . K(t)^T,  R(t) = Q . Ewin(t)^T, as soon as S / R of tile t - 1 sit in registers =================
+    // ================= MMA issuer (one thread): MMA 1 of tile t + 1 as soon as S / R of tile t sit in registers, then MMA 3 of tile t
+    // when its P is stored.  F(t) always precedes P(t), so one thread serves both without delaying either; a second issuer warp
+    // only added another spinning waiter next to the softmax warps. =================
     if (lane == 0) {
       constexpr uint32_t IDESC_S = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);                 // f16 x f16 -> f32, N = 64
       constexpr uint32_t IDESC_R = ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);                            // f16 x f16 -> f16, N = 128
-      const uint32_t tS = tmem_base + T5_TS, tR = tmem_base + T5_TR;
+      constexpr uint32_t IDESC_O = (1u << 4) | (1u << 16) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);    // B MN-major, N = 32
+      const uint32_t tS = tmem_base + T5_TS, tR = tmem_base + T5_TR, tP = tmem_base + T5_TP, tO = tmem_base + T5_TO;
       const uint64_t a0 = ptx::umma_desc_ns(sm0 + T5_AEXP, 128, 512), a1 = ptx::umma_desc_ns(sm0 + T5_AEXP + 256, 128, 512),
                      aq = ptx::umma_desc_ns(sm0 + T5_QPL, 128, 256);
-      for (int t = 0; t < ntiles; ++t) {
+      auto mma1 = [&](int t) {          // S(t) = Aexp . K(t)^T,  R(t) = Q . Ewin(t)^T (skipped when every offset is clamped)
         const int slot = t % T5_STAGES;
         const uint32_t st = sm0 + T5_STAGE0 + (uint32_t)(slot * T5_STAGE);
         const uint64_t bk = ptx::umma_desc_ns(st + T5_KS, 128, 512), be = ptx::umma_desc_ns(st + T5_ES, 128, 256);
@@ -299,14 +304,10 @@ attention_tc_kernel(const __half* __restrict__ qkvh, const __half* __restrict__ 
         if (t5_far(i0, t) == 0) ptx::mma_f16_ss(tR, aq, be, IDESC_R, 0u);
         ptx::tc_commit(&bar_S);
         T5_STAMP(1, t, 2);
-      }
-    }
-  } else if (warp == 6) {
-    // ================= MMA 3 issuer: O += P(t) . V(t); its completion frees P, O (for a rescale) and the ring slot =================
-    if (lane == 0) {
-      constexpr uint32_t IDESC_O = (1u << 4) | (1u << 16) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);    // B MN-major, N = 32
-      const uint32_t tP = tmem_base + T5_TP, tO = tmem_base + T5_TO;
+      };
+      mma1(0);
       for (int t = 0; t < ntiles; ++t) {
+        if (t + 1 < ntiles) mma1(t + 1);
         const int slot = t % T5_STAGES;
         const uint64_t bv = ptx::umma_desc_ns(sm0 + T5_STAGE0 + (uint32_t)(slot * T5_STAGE) + T5_VS, 128, 1024);
         ptx::mbar_wait_lean<WM>(&bar_P, (uint32_t)t & 1u);
@@ -316,8 +317,8 @@ attention_tc_kernel(const __half* __restrict__ qkvh, const __half* __restrict__ 
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
           if (ks < nks) ptx::mma_f16_ts(tO, tP + (uint32_t)(ks * 8), bv + (uint64_t)((ks * 256) >> 4), IDESC_O, (t | ks) ? 1u : 0u);
-        ptx::tc_commit(&bar_O);
-        ptx::tc_commit(&empty_bar[slot]);
+        ptx::tc_commit(&bar_O);            // O updated, P free
+        ptx::tc_commit(&empty_bar[slot]);  // ring slot free (MMA 1 of this tile completed earlier)
         T5_STAMP(1, t, 4);
       }
     }
