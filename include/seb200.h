@@ -155,6 +155,9 @@ typedef struct SebSeq { int nseq, n, inner; long long outer_stride, pos_stride; 
  *   variant 0 (tensor cores): qkv is __half, q pre-scaled by 0.25 * log2(e) (SEB_EPI_QKV_F16 writes it);
  *                             rel_pos_emb_h = rel_pos_emb [1025, 16] rounded to IEEE fp16 with the 16 halfs of every row
  *                             in MMA-fragment order k = 0,1,8,9, 2,3,10,11, 4,5,12,13, 6,7,14,15 (packed once by the host)
+ *   variant 3 (tcgen05): same inputs as variant 0.  S = Q K^T (fp32) and R = Q E_window^T (fp16) accumulate in tensor memory,
+ *                        the per-row skew of R goes through thread-private shared-memory rows, P is the TMEM A operand of
+ *                        the P V product; key tiles beyond the +-512 clamp skip the rel-pos GEMM (attention_tc.cu)
  *   variant 2: the round-1 tensor-core kernel (fp32 skew staging), same inputs as variant 0 except that rel_pos_emb_h is in natural k order; kept for A/B measurements;
  *   variant 1 (fp32 SIMT cross-check): qkv is float, unscaled; rel_pos_emb [1025, 16] fp32 */
 int seb200_attention(const void* qkv, const float* rel_pos_emb, const void* rel_pos_emb_h, const SebSeq* seq, float* out,
