@@ -497,6 +497,354 @@ attention_tc_kernel(const __half* __restrict__ qkvh, const __half* __restrict__ 
   if (warp == 4) ptx::tmem_dealloc(tmem_base, T5_TCOLS);
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// Three query groups per CTA (one CTA per SM, all 512 TMEM columns).  The two-CTA kernel above is bound by the latency chain
+// of its softmax warps (wait S -> tcgen05.ld -> STS / LDS -> FHADD -> max -> ex2 -> tcgen05.st -> arrive): two chains per
+// scheduler leave every pipe under 45 %.  TMEM holds no third copy of (S | R | P | O) = 256 columns -- but R is live only from
+// its MMA to the threads' tcgen05.ld (~300 of a tile's ~2500 clocks), so THREE groups of 128 accumulator rows (three consecutive
+// 64-query blocks of one (sequence, head pair): they share every K / V tile and one 256-row E window) take turns on ONE R buffer:
+//   TMEM: group g: S 128g | P 128g + 64 | O 128g + 96;  R 384..511 (shared, handed on through the R-free barrier)
+// The strict (tile, group) order of the R users also staggers the three groups by a third of a tile period, so their LSU-,
+// MUFU- and TMEM-bound phases interleave instead of colliding.
+// ------------------------------------------------------------------------------------------------------------------------
+constexpr int T6_G = 3, T6_BQ = T6_G * T5_BQ;
+constexpr int T6_W_LOAD = 4 * T6_G, T6_W_MMA1 = T6_W_LOAD + 1, T6_W_MMA3 = T6_W_LOAD + 2, T6_THREADS = (T6_W_MMA3 + 1) * 32;     // 480
+constexpr int T6_STAGES = 4;
+constexpr int T6_AEXP = 0, T6_QPL = T6_G * 8192, T6_STAGE0 = T6_QPL + T6_G * 4096;
+constexpr int T6_KS = 0, T6_VS = 4096, T6_ES = 8192, T6_STAGE = 16384;           // E window: 256 rows (64 keys + 192 queries - 1 offsets)
+constexpr int T6_RSCR = T6_STAGE0 + T6_STAGES * T6_STAGE;
+constexpr int T6_SMEM = T6_RSCR + T6_G * 128 * T5_RPITCH + 128;
+constexpr uint32_t T6_TR = 384;
+
+template <int WM>
+__global__ void __launch_bounds__(T6_THREADS, 1)
+attention_tc3_kernel(const __half* __restrict__ qkvh, const __half* __restrict__ Eh, const SebSeq sq, int nqb, float* __restrict__ out) {
+  extern __shared__ uint8_t t5_smraw[];
+  __shared__ uint64_t bar_S[T6_G], bar_F[T6_G], bar_P[T6_G], bar_O[T6_G], bar_RF, full_bar[T6_STAGES], empty_bar[T6_STAGES];
+  __shared__ uint32_t tmem_base_s;
+  const uint32_t sm0 = (ptx::smem_u32(t5_smraw) + 127u) & ~127u;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int qb = blockIdx.x % nqb, sh = blockIdx.x / nqb;
+  const int hp = sh & 1, seq = sh >> 1;
+  const int n = sq.n, i0 = qb * T6_BQ;
+  const long long base = t5_seq_base(sq, seq);
+  const int ntiles = (n + T5_KT - 1) / T5_KT;
+  const int ng = min(T6_G, (n - i0 + T5_BQ - 1) / T5_BQ);              // live groups of this CTA
+  const __half* seq0 = qkvh + base * T5_ROWH;
+
+  if (tid == 0) {
+    for (int g = 0; g < T6_G; ++g) {
+      ptx::mbar_init(&bar_S[g], 1); ptx::mbar_init(&bar_F[g], 128); ptx::mbar_init(&bar_P[g], 128); ptx::mbar_init(&bar_O[g], 1);
+    }
+    ptx::mbar_init(&bar_RF, 128);       // the 128 threads of the group that owns R have it in registers
+    for (int s = 0; s < T6_STAGES; ++s) { ptx::mbar_init(&full_bar[s], 32); ptx::mbar_init(&empty_bar[s], 1); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == T6_W_LOAD) ptx::tmem_alloc(&tmem_base_s, 512);
+
+  // ---- loader state: K, V (8 + 8 chunks of 16 bytes per lane) and the 256-row E window (16 chunks per lane) of a tile
+  const long long key_stride_h = sq.pos_stride * T5_ROWH;
+  const __half* kv_lane = seq0 + (long long)(lane >> 2) * key_stride_h + 64 + hp * 32 + (lane & 3) * 8;
+  const uint32_t k_dst = (uint32_t)(T6_KS + (lane & 3) * 128 + (lane >> 2) * 16);
+  const uint32_t v_dst = (uint32_t)(T6_VS + (lane & 3) * 1024 + (lane >> 2) * 16);
+  const uint32_t e_dst = (uint32_t)(T6_ES + (lane >> 4) * 256 + (lane & 1) * 128 + ((lane >> 1) & 7) * 16);
+  const __half* e_lane = Eh + T5_MAXPOS * T5_D + (lane & 1) * 8;
+  auto any_near = [&](int t) {            // does any live group need the R GEMM for tile t?
+    bool r = false;
+    for (int g = 0; g < ng; ++g) r = r || (t5_far(i0 + g * T5_BQ, t) == 0);
+    return r;
+  };
+  auto issue_tile = [&](int t) {          // one commit group per call (empty past the last tile)
+    if (t < ntiles) {
+      const uint32_t st = sm0 + T6_STAGE0 + (uint32_t)((t % T6_STAGES) * T6_STAGE);
+      const int j0 = t * T5_KT;
+      const int key0 = j0 + (lane >> 2);
+      const __half* src0 = kv_lane + (long long)j0 * key_stride_h;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const bool ok = key0 + 8 * k < n;
+        const __half* src = ok ? src0 + (long long)(8 * k) * key_stride_h : seq0;
+        ptx::cp16z(st + k_dst + (uint32_t)(k * 512), src, ok ? 16u : 0u);
+        ptx::cp16z(st + v_dst + (uint32_t)(k * 128), ok ? src + 64 : seq0, ok ? 16u : 0u);
+      }
+      if (any_near(t)) {                  // row c of the window = E[clamp(i0 + 191 - j0 - c)]; group g reads rows 64 (2 - g) .. + 127
+        const int d0 = i0 + T6_BQ - 1 - j0 - (lane >> 1);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          int d = d0 - 16 * k;
+          d = d < -T5_MAXPOS ? -T5_MAXPOS : (d > T5_MAXPOS ? T5_MAXPOS : d);
+          ptx::cp16_ca(st + e_dst + (uint32_t)(k * 512), e_lane + d * T5_D);
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (warp == T6_W_LOAD) {
+    issue_tile(0);
+    issue_tile(1);
+  }
+
+  const int gi = warp >> 2, q4 = warp & 3;                 // softmax warps: query group, TMEM lane quadrant
+  const int i0g = i0 + gi * T5_BQ;
+  if (warp < T6_W_LOAD && gi < ng) {
+    // ---- operand rows of this thread: Aexp (q in its head's slot) and Q (k order permuted like the fragment-ordered E table)
+    const int hl = q4 >> 1, par = q4 & 1, r = tid & 127;
+    const int i = i0g + 2 * lane + par;
+    uint4 qlo = make_uint4(0u, 0u, 0u, 0u), qhi = qlo;
+    if (i < n) {
+      const uint4* qp = reinterpret_cast<const uint4*>(seq0 + (long long)i * key_stride_h + (2 * hp + hl) * T5_D);
+      qlo = __ldg(qp); qhi = __ldg(qp + 1);
+    }
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    const uint32_t arow = sm0 + T6_AEXP + (uint32_t)(gi * 8192 + (r >> 3) * 512 + (r & 7) * 16);
+    auto sts128 = [](uint32_t addr, uint4 v) {
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    };
+    sts128(arow + 0 * 128, hl == 0 ? qlo : zero);
+    sts128(arow + 1 * 128, hl == 0 ? qhi : zero);
+    sts128(arow + 2 * 128, hl == 1 ? qlo : zero);
+    sts128(arow + 3 * 128, hl == 1 ? qhi : zero);
+    const uint32_t qrow = sm0 + T6_QPL + (uint32_t)(gi * 4096 + (r >> 3) * 256 + (r & 7) * 16);
+    sts128(qrow, make_uint4(qlo.x, qhi.x, qlo.y, qhi.y));
+    sts128(qrow + 128, make_uint4(qlo.z, qhi.z, qlo.w, qhi.w));
+    ptx::fence_proxy_async_smem();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == T6_W_LOAD) {
+    // ================= loader warp (continued) =================
+    for (int t = 2; t < ntiles + 2; ++t) {
+      {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");     // this lane's chunks of tile t - 2 have landed
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive(&full_bar[(t - 2) % T6_STAGES]);
+      }
+      if (t >= T6_STAGES && t < ntiles) {
+        if (lane == 0) ptx::mbar_wait_lean<WM>(&empty_bar[t % T6_STAGES], (uint32_t)(t / T6_STAGES - 1) & 1u);
+        __syncwarp();
+      }
+      issue_tile(t);
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  } else if (warp == T6_W_MMA1) {
+    // ================= MMA 1 issuer: strict (tile, group) order; the R GEMM of a group waits until the previous owner of R has read it =================
+    if (lane == 0) {
+      constexpr uint32_t IDESC_S = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      constexpr uint32_t IDESC_R = ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      int ruse = 0;                        // R GEMMs issued so far = phases of bar_RF
+      for (int t = 0; t < ntiles; ++t) {
+        const int slot = t % T6_STAGES;
+        const uint32_t st = sm0 + T6_STAGE0 + (uint32_t)(slot * T6_STAGE);
+        const uint64_t bk = ptx::umma_desc_ns(st + T6_KS, 128, 512);
+        ptx::mbar_wait_lean<WM>(&full_bar[slot], (uint32_t)(t / T6_STAGES) & 1u);
+        for (int g = 0; g < ng; ++g) {
+          const uint32_t tS = tmem_base + (uint32_t)(128 * g);
+          const uint64_t a0 = ptx::umma_desc_ns(sm0 + T6_AEXP + g * 8192, 128, 512);
+          if (t > 0) ptx::mbar_wait_lean<WM>(&bar_F[g], (uint32_t)(t - 1) & 1u);
+          const bool near = t5_far(i0 + g * T5_BQ, t) == 0;
+          if (near && ruse > 0) ptx::mbar_wait_lean<WM>(&bar_RF, (uint32_t)(ruse - 1) & 1u);
+          ptx::tc_fence_after();
+          ptx::mma_f16_ss(tS, a0, bk, IDESC_S, 0u);
+          ptx::mma_f16_ss(tS, a0 + (256 >> 4), bk + (256 >> 4), IDESC_S, 1u);
+          if (near) {
+            ptx::mma_f16_ss(tmem_base + T6_TR, ptx::umma_desc_ns(sm0 + T6_QPL + g * 4096, 128, 256),
+                            ptx::umma_desc_ns(st + T6_ES + (T6_G - 1 - g) * 2048, 128, 256), IDESC_R, 0u);
+            ++ruse;
+          }
+          ptx::tc_commit(&bar_S[g]);
+        }
+      }
+    }
+  } else if (warp == T6_W_MMA3) {
+    // ================= MMA 3 issuer: O_g += P_g(t) . V(t) in (tile, group) order; the last group's commit frees the ring slot =================
+    if (lane == 0) {
+      constexpr uint32_t IDESC_O = (1u << 4) | (1u << 16) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      for (int t = 0; t < ntiles; ++t) {
+        const int slot = t % T6_STAGES;
+        const uint64_t bv = ptx::umma_desc_ns(sm0 + T6_STAGE0 + (uint32_t)(slot * T6_STAGE) + T6_VS, 128, 1024);
+        const int nks = (n - t * T5_KT <= 16) ? 1 : 4;
+        for (int g = 0; g < ng; ++g) {
+          const uint32_t tP = tmem_base + (uint32_t)(128 * g + 64), tO = tmem_base + (uint32_t)(128 * g + 96);
+          ptx::mbar_wait_lean<WM>(&bar_P[g], (uint32_t)t & 1u);
+          ptx::tc_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            if (ks < nks) ptx::mma_f16_ts(tO, tP + (uint32_t)(ks * 8), bv + (uint64_t)((ks * 256) >> 4), IDESC_O, (t | ks) ? 1u : 0u);
+          ptx::tc_commit(&bar_O[g]);
+        }
+        ptx::tc_commit(&empty_bar[slot]);
+      }
+    }
+  } else if (gi < ng) {
+    // ================= softmax threads: one accumulator row each =================
+    const int hl = q4 >> 1, par = q4 & 1;
+    const int i = i0g + 2 * lane + par;
+    const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
+    const uint32_t tS = tmem_base + lane_sel + (uint32_t)(128 * gi), tP = tS + 64u, tO = tS + 96u, tR = tmem_base + lane_sel + T6_TR;
+    const uint32_t myrow = sm0 + T6_RSCR + (uint32_t)(tid * T5_RPITCH);
+    const uint32_t rd = myrow + (uint32_t)((31 - lane) * 4);
+    uint64_t* const bS = &bar_S[gi]; uint64_t* const bF = &bar_F[gi]; uint64_t* const bP = &bar_P[gi]; uint64_t* const bO = &bar_O[gi];
+    float m = 0.f, l = 0.f;
+    float c_hi = 0.f, c_lo = 0.f;
+    if (n > T5_MAXPOS) {
+      const uint32_t qw = sm0 + T6_QPL + (uint32_t)(gi * 4096 + ((tid & 127) >> 3) * 256 + (tid & 7) * 16);
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        uint4 qv;
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(qv.x), "=r"(qv.y), "=r"(qv.z), "=r"(qv.w) : "r"(qw + ch * 128) : "memory");
+        const uint4 eh = __ldg(reinterpret_cast<const uint4*>(Eh + 2 * T5_MAXPOS * T5_D) + ch), el = __ldg(reinterpret_cast<const uint4*>(Eh) + ch);
+        const uint32_t qq[4] = {qv.x, qv.y, qv.z, qv.w}, hh[4] = {eh.x, eh.y, eh.z, eh.w}, ll[4] = {el.x, el.y, el.z, el.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 qf = __half22float2(*reinterpret_cast<const __half2*>(&qq[k]));
+          const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hh[k])), lf = __half22float2(*reinterpret_cast<const __half2*>(&ll[k]));
+          c_hi = fmaf(qf.x, hf.x, fmaf(qf.y, hf.y, c_hi));
+          c_lo = fmaf(qf.x, lf.x, fmaf(qf.y, lf.y, c_lo));
+        }
+      }
+    }
+    auto tile_body = [&](auto nk_tag, auto far_tag, int t, float cadd) {
+      constexpr int NK = decltype(nk_tag)::value;
+      constexpr bool FAR = decltype(far_tag)::value;
+      constexpr int NWR = NK == 64 ? 64 : 40;
+      ptx::mbar_wait_lean<WM>(bS, (uint32_t)t & 1u);
+      ptx::tc_fence_after();
+      if (!FAR) {
+        uint32_t w[64];
+        ptx::tmem_ld32_pack16<0>(tR, w);
+        if (NK == 64) ptx::tmem_ld32_pack16<32>(tR + 64u, w); else ptx::tmem_ld16_pack16(tR + 64u, w + 32);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&bar_RF);       // R may go to the next group
+#pragma unroll
+        for (int q = 0; q < NWR / 4; ++q)
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(myrow + q * 16), "r"(w[4 * q]), "r"(w[4 * q + 1]), "r"(w[4 * q + 2]), "r"(w[4 * q + 3]) : "memory");
+      }
+      uint32_t sb[NK];
+      if (NK == 64) { ptx::tmem_ld32<0>(tS, sb); ptx::tmem_ld32<32>(tS + 32u, sb); } else ptx::tmem_ld16(tS, sb);
+      uint32_t x[NK / 2 + 1];
+      if (!FAR) {
+#pragma unroll
+        for (int k = 0; k < NK / 2 + 1; ++k) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x[k]) : "r"(rd + k * 4) : "memory");
+      }
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(bF);              // S sits in registers: the next tile's MMA 1 may overwrite it
+      float s[NK];
+      if (FAR) {
+#pragma unroll
+        for (int jj = 0; jj < NK; ++jj) s[jj] = __uint_as_float(sb[jj]);
+      } else if (par) {
+#pragma unroll
+        for (int p = 0; p < NK / 2; ++p) {
+          s[2 * p] = ptx::fhadd((unsigned short)(x[p] & 0xffffu), __uint_as_float(sb[2 * p]));
+          s[2 * p + 1] = ptx::fhadd((unsigned short)(x[p] >> 16), __uint_as_float(sb[2 * p + 1]));
+        }
+      } else {
+#pragma unroll
+        for (int p = 0; p < NK / 2; ++p) {
+          s[2 * p] = ptx::fhadd((unsigned short)(x[p] >> 16), __uint_as_float(sb[2 * p]));
+          s[2 * p + 1] = ptx::fhadd((unsigned short)(x[p + 1] & 0xffffu), __uint_as_float(sb[2 * p + 1]));
+        }
+      }
+      const int rem = n - t * T5_KT;
+      if (rem < NK) {
+#pragma unroll
+        for (int jj = 0; jj < NK; ++jj)
+          if (jj >= rem) s[jj] = -1e30f;
+      }
+      float mx;
+      {
+        constexpr int N1 = (NK + 2) / 3;
+        float a[N1];
+#pragma unroll
+        for (int k = 0; k < NK / 3; ++k) a[k] = ptx::fmax3(s[3 * k], s[3 * k + 1], s[3 * k + 2]);
+        a[N1 - 1] = s[NK - 1];
+        mx = a[0];
+#pragma unroll
+        for (int k = 1; k + 1 < N1; k += 2) mx = ptx::fmax3(mx, a[k], a[k + 1]);
+        if ((N1 & 1) == 0) mx = fmaxf(mx, a[N1 - 1]);
+        if (FAR) mx += cadd;
+      }
+      if (t > 0) {
+        ptx::mbar_wait_lean<WM>(bO, (uint32_t)(t - 1) & 1u);
+        ptx::tc_fence_after();
+      }
+      if (t == 0) {
+        m = mx;
+      } else {
+        const bool need = mx > m + T5_LAZY;
+        if (__any_sync(0xffffffffu, need)) {
+          const float mn = need ? mx : m;
+          const float corr = ptx::ex2f(m - mn);
+          m = mn;
+          l *= corr;
+          uint32_t o[32];
+          ptx::tmem_ld32<0>(tO, o);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * corr);
+          ptx::tmem_st32(tO, o);
+        }
+      }
+      uint32_t pw[NK / 2];
+      float2 la = make_float2(0.f, 0.f), lb = la;
+      const float2 negm = FAR ? make_float2(cadd - m, cadd - m) : make_float2(-m, -m);
+#pragma unroll
+      for (int p = 0; p < NK / 2; p += 2) {
+        const float2 a = __fadd2_rn(make_float2(s[2 * p], s[2 * p + 1]), negm), b = __fadd2_rn(make_float2(s[2 * p + 2], s[2 * p + 3]), negm);
+        const float2 pa = make_float2(ptx::ex2f(a.x), ptx::ex2f(a.y)), pb = make_float2(ptx::ex2f(b.x), ptx::ex2f(b.y));
+        la = __fadd2_rn(la, pa); lb = __fadd2_rn(lb, pb);
+        const __half2 h0 = __floats2half2_rn(pa.x, pa.y), h1 = __floats2half2_rn(pb.x, pb.y);
+        pw[p] = *reinterpret_cast<const uint32_t*>(&h0);
+        pw[p + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+      }
+      l += (la.x + la.y) + (lb.x + lb.y);
+      if (NK == 64) ptx::tmem_st32(tP, pw); else ptx::tmem_st8u(tP, pw);
+      ptx::tmem_st_wait5();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(bP);
+    };
+    if (i0g + par >= n) {                // every query row of this warp lies past the sequence: keep the protocol, skip the work
+      for (int t = 0; t < ntiles; ++t) {
+        ptx::mbar_wait_lean<WM>(bS, (uint32_t)t & 1u);
+        if (t5_far(i0g, t) == 0) ptx::mbar_arrive(&bar_RF);
+        ptx::mbar_arrive(bF);
+        if (t > 0) ptx::mbar_wait_lean<WM>(bO, (uint32_t)(t - 1) & 1u);
+        ptx::mbar_arrive(bP);
+      }
+    } else {
+      for (int t = 0; t < ntiles; ++t) {
+        const int far = t5_far(i0g, t);
+        const bool tail = n - t * T5_KT <= 16;
+        if (far && tail) tile_body(std::integral_constant<int, 16>{}, std::true_type{}, t, far > 0 ? c_hi : c_lo);
+        else if (far) tile_body(std::integral_constant<int, 64>{}, std::true_type{}, t, far > 0 ? c_hi : c_lo);
+        else if (tail) tile_body(std::integral_constant<int, 16>{}, std::false_type{}, t, 0.f);
+        else tile_body(std::integral_constant<int, 64>{}, std::false_type{}, t, 0.f);
+      }
+    }
+    ptx::mbar_wait_lean<WM>(bO, (uint32_t)(ntiles - 1) & 1u);
+    ptx::tc_fence_after();
+    uint32_t o[16];
+    ptx::tmem_ld16(tO + (uint32_t)(hl * 16), o);
+    ptx::tmem_ld_wait();
+    if (i < n) {
+      const float inv = 1.0f / l;
+      float* op = out + (base + (long long)i * sq.pos_stride) * 64 + (2 * hp + hl) * T5_D;
+#pragma unroll
+      for (int c = 0; c < 16; c += 4)
+        *reinterpret_cast<float4*>(op + c) = make_float4(__uint_as_float(o[c]) * inv, __uint_as_float(o[c + 1]) * inv,
+                                                         __uint_as_float(o[c + 2]) * inv, __uint_as_float(o[c + 3]) * inv);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == T6_W_LOAD) ptx::tmem_dealloc(tmem_base, 512);
+}
+
 #ifdef T5_TRACE
 extern "C" int seb200_t5_trace(long long* host) { return (int)cudaMemcpyFromSymbol(host, t5_trace, sizeof(t5_trace)); }
 #endif
@@ -505,11 +853,12 @@ int attention_tc_launch(const __half* qkvh, const __half* Eh, const SebSeq* seq,
   static bool attr_done = false;
   static int mode = 0;
   if (!attr_done) {
-    const char* ev = getenv("SEB200_T5_MODE");      // experiment switch: wait mode * 2 + packed
-    mode = ev ? atoi(ev) : 1;
+    const char* ev = getenv("SEB200_T5_MODE");      // experiment switch: 6 = three query groups per CTA (default), 0..5 = the two-CTA kernel (wait mode * 2 + packed)
+    mode = ev ? atoi(ev) : 6;
     cudaError_t e = cudaSuccess;
 #define T5_ATTR(W, P) if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<W, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM);
     T5_ATTR(0, 0) T5_ATTR(0, 1) T5_ATTR(1, 0) T5_ATTR(1, 1) T5_ATTR(2, 0) T5_ATTR(2, 1)
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, T6_SMEM);
     if (e != cudaSuccess) { set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     attr_done = true;
   }
@@ -517,6 +866,13 @@ int attention_tc_launch(const __half* qkvh, const __half* Eh, const SebSeq* seq,
   const long long nblocks = (long long)seq->nseq * 2 * nqb;
   SEB_REQUIRE(nblocks < 2147483647LL, SEB_EINVAL, "attention: grid too large");
 #define T5_GO(W, P) attention_tc_kernel<W, P><<<(unsigned)nblocks, T5_THREADS, T5_SMEM, st>>>(qkvh, Eh, *seq, nqb, out)
+  if (mode == 6) {
+    const int nqb3 = (seq->n + T6_BQ - 1) / T6_BQ;
+    const long long nb3 = (long long)seq->nseq * 2 * nqb3;
+    attention_tc3_kernel<0><<<(unsigned)nb3, T6_THREADS, T6_SMEM, st>>>(qkvh, Eh, *seq, nqb3, out);
+    SEB_CHECK_LAUNCH("attention_tc3_kernel");
+    return 0;
+  }
   switch (mode) {
     case 1: T5_GO(0, 1); break;
     case 2: T5_GO(1, 0); break;

@@ -143,9 +143,9 @@ class TSCNet(nn.Module):
         self.num_features = num_features
         self.engine = ops.default_engine()     # "tcgen05" | "simt" main loop of the GEMM engine
         self.attention_variant = 0             # 0 tensor-core (mma.sync), 3 tcgen05 / TMEM kernel (attention_tc.cu), 1 SIMT cross-check
-        # sequences at least this long take the tcgen05 kernel when attention_variant == 0 (measured: 4.40 vs 4.91 ms at n = 4801,
-        # 8.3 vs 7.8 ms at n = 641, 3.3 vs 2.3 ms at n = 101 -- tools/attn_tc_check.py)
-        self.attention_tc_min_len = 2048
+        # sequences at least this long take the tcgen05 kernel when attention_variant == 0 (measured, three-group kernel vs mma.sync:
+        # 3.51 vs 4.91 ms at n = 4801, 7.15 vs 7.78 ms at n = 641, 3.6 vs 2.3 ms at n = 101 -- tools/attn_tc_check.py)
+        self.attention_tc_min_len = 512
         self.fuse_dwconv_pw2 = False           # opt-in: depthwise conv + pointwise 128 -> 64 in one kernel (seb200_dwconv_pw2); measured
                                                # 21.5 ms vs 16.2 ms for the two-kernel path at configs[1], so off by default
         self._packed: Optional[Dict[str, object]] = None
