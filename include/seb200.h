@@ -42,7 +42,9 @@ enum {
  * (conformer.py:87-89,137-140,165,169).
  */
 enum { SEB_LOAD_ROWS = 0, SEB_LOAD_ROWS_LN = 1, SEB_LOAD_CONV = 2, SEB_LOAD_HANKEL = 3,
-       SEB_LOAD_CONV_SPLIT = 4 /* CONV on pre-split inputs: every pixel = 64 bf16 hi + 64 bf16 lo (256 bytes); tcgen05 engine only */ };
+       SEB_LOAD_CONV_SPLIT = 4, /* CONV on pre-split inputs: every pixel = 64 bf16 hi + 64 bf16 lo (256 bytes); tcgen05 engine only */
+       SEB_LOAD_ROWS2 = 5       /* K = 128: row m = (a[0][m, 0:64] | a[1][m, 0:64]), both with row stride lda: the two 1x1 convs of
+                                   MergeBlock (models/tsc_diffusion.py:21-22,32-34) as one contraction over [x | conditioner] */ };
 enum {
   SEB_EPI_BIAS = 0,     /* out = acc + bias                                  */
   SEB_EPI_SWISH = 1,    /* v = acc + bias; out = v * sigmoid(v)              */
@@ -50,7 +52,11 @@ enum {
   SEB_EPI_RESID = 3,    /* out = alpha * (acc + bias) + resid                */
   SEB_EPI_SUBPIXEL = 4, /* out[(bt*2Fo + 2w + n/64), n%64] = acc + bias      */
   SEB_EPI_COMPRESS = 5, /* columns interleaved (re, im): out[m, k, 0..2] = (|X|^.3, re|X|^-.7, im|X|^-.7) */
-  SEB_EPI_QKV_F16 = 6   /* out is __half [M, 192] = (q * 0.25 * log2(e) | k | v): input of seb200_attention variant 0 */
+  SEB_EPI_QKV_F16 = 6,  /* out is __half [M, 192] = (q * 0.25 * log2(e) | k | v): input of seb200_attention variant 0 */
+  SEB_EPI_GATE = 7,     /* columns interleaved (gate, filter): out[n/2] = sigmoid(g) * tanh(f) with (g, f) = acc + bias + rowbias;
+                           rowbias = resid[(m / ldr) * N + n] when resid != NULL: one extra bias row per group of ldr consecutive
+                           rows (the diffusion-step projection, constant per utterance; models/tsc_diffusion.py:27-37) */
+  SEB_EPI_RESID_SCALE = 8 /* out = alpha * (acc + bias + resid): (x + output_residual(y)) / sqrt(2), tsc_diffusion.py:39-41 */
 };
 enum { SEB_ENGINE_TCGEN05 = 0, SEB_ENGINE_SIMT = 1 };
 
@@ -175,6 +181,18 @@ int seb200_dwconv_pw2(const float* u, const SebSeq* seq, const float* w, const f
 /* post_norm + the TSCB outer residual (conformer.py:211, generator.py:70,72): out = LN(x) * g + b + resid */
 int seb200_layernorm_residual(const float* x, long long tokens, const float* gamma, const float* beta,
                               const float* resid, float* out, void* stream);
+
+/* ---- diffusion variant (models/tsc_diffusion.py) ------------ */
+/* MergeBlock's diffusion-step branch (tsc_diffusion.py:27-29 + models/DiffuSE.py:46-62) folded into a per-step bias of the
+ * merge GEMM:  e = table[step] (integer step) or lerp(table[floor], table[ceil]) (fractional step);
+ *   h = silu(W1 e + b1); h = silu(W2 h + b2); d = Wp h + bp   (128 -> 512 -> 512 -> 64)
+ *   d_out[s, 0:64] = d;  rowbias[s, n] = sum_k wm[n, k] * d[k]  (n < 128; wm = merge_diffusion weight in the row order the
+ *   merge GEMM uses), so that W_m (x + d) = W_m x + rowbias.  nsteps entries (1 or B), max_steps rows in table [max_steps, 128].
+ * All device pointers; fp32. */
+int seb200_diffusion_embed(const float* steps, int nsteps, const float* table, int max_steps,
+                           const float* w1, const float* b1, const float* w2, const float* b2,
+                           const float* wp, const float* bp, const float* wm,
+                           float* d_out, float* rowbias, void* stream);
 
 /* ---- misc ------------------------------------------------------------------ */
 int seb200_version(void);

@@ -57,6 +57,43 @@ def main():
             final_real=fr.numpy(), final_imag=fi.numpy(),
             weight_seed=np.int64(sseed), wave_seed=np.int64(wseed))
         print(name, "enhanced peak", float(np.abs(enhanced).max()))
+    diffusion_golden(ref, out_dir)
+
+
+# models/tsc_diffusion.py:TSCNet.forward on (estimate, conditioning utterance, step); integer, fractional
+# (DiffuSE.py:57-62 interpolation) and per-utterance steps
+DIFFUSION_CASE = dict(name="diffusion_b2_L3000", batch=2, length=3000, wave_seed=11, weight_seed=3, max_steps=50,
+                      steps=[("int1", [7], "int64"), ("frac1", [3.4], "float32"), ("intB", [2, 40], "int64")])
+
+
+def diffusion_inputs(case=DIFFUSION_CASE):
+    """(estimate wave, conditioning wave): the conditioning utterance is the RMS-normalised noisy clip; the estimate is a
+    partly denoised mixture, as the reverse process holds mid-way (inference_diffuse.py:246-262)."""
+    noisy, clean = weights.synth_wave(case["batch"], case["length"], case["wave_seed"], "speech")
+    c = torch.sqrt(noisy.shape[-1] / torch.sum(noisy ** 2.0, dim=-1, keepdim=True))
+    g = torch.Generator().manual_seed(case["wave_seed"] + 1)
+    est = c * (0.5 * clean + 0.5 * noisy) + 0.05 * torch.randn(noisy.shape, generator=g)
+    return est, c * noisy
+
+
+def diffusion_golden(ref, out_dir):
+    case = DIFFUSION_CASE
+    sd = weights.synth_state_dict(case["weight_seed"], spec=weights.tsc_diffusion_spec())
+    model = ref.DiffusionTSCNet(num_channel=64, num_features=201, noise_schedule=list(range(case["max_steps"])))
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    est, cond = diffusion_inputs(case)
+    out = {}
+    with torch.no_grad():
+        win = torch.hamming_window(400)
+        sx, sn = ref.compressed_stft(est, 400, 100, win), ref.compressed_stft(cond, 400, 100, win)
+        for tag, vals, dt in case["steps"]:
+            fr, fi = model(sx, sn, torch.tensor(vals, dtype=getattr(torch, dt)))
+            out[f"final_real_{tag}"], out[f"final_imag_{tag}"] = fr.numpy(), fi.numpy()
+    np.savez_compressed(os.path.join(out_dir, case["name"] + ".npz"), est=est.numpy(), cond=cond.numpy(),
+                        spec_x_real=sx.real.numpy(), spec_x_imag=sx.imag.numpy(), spec_n_real=sn.real.numpy(), spec_n_imag=sn.imag.numpy(),
+                        weight_seed=np.int64(case["weight_seed"]), wave_seed=np.int64(case["wave_seed"]), max_steps=np.int64(case["max_steps"]), **out)
+    print(case["name"], {k: float(np.abs(v).max()) for k, v in out.items()})
 
 
 if __name__ == "__main__":

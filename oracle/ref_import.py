@@ -90,12 +90,16 @@ def load():
         from core.function import compressed_stft, uncompressed_istft, batch_stft, normalize_batch
         from utils.utils import kaiming_init
         try:
+            from models.tsc_diffusion import TSCNet as DiffusionTSCNet
+        except Exception:  # pragma: no cover
+            DiffusionTSCNet = None
+        try:
             from inference_gan import predict
         except Exception:  # pragma: no cover - depends on what else the script imports
             predict = None
     finally:
         sys.path.remove(REF_ROOT)
-    ns = types.SimpleNamespace(TSCNet=TSCNet, predict=predict, compressed_stft=compressed_stft,
+    ns = types.SimpleNamespace(TSCNet=TSCNet, DiffusionTSCNet=DiffusionTSCNet, predict=predict, compressed_stft=compressed_stft,
                                uncompressed_istft=uncompressed_istft, kaiming_init=kaiming_init,
                                batch_stft=batch_stft, normalize_batch=normalize_batch,
                                generator=gen_mod, conformer=conf_mod,

@@ -11,6 +11,7 @@ no einops) of the reference's algorithm for the path named in BASELINE.json:
     power_uncompress()     /root/reference/core/function.py:636-645
     uncompressed_istft()   /root/reference/core/function.py:695-703
     normalize_batch() / batch_stft()  /root/reference/core/function.py:647-683
+    tsc_diffusion.TSCNet / MergeBlock /root/reference/models/tsc_diffusion.py:16-90 (+ models/DiffuSE.py:39-69), SURVEY 8f row f3
 
 It is driven purely by a ``state_dict`` with the reference's 359 keys.  Only
 ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
@@ -280,6 +281,69 @@ def tscnet_forward(spec: torch.Tensor, sd: SD, chunk: int = 0, stages: Optional[
     if stages is not None:
         stages["mask"] = mask
         stages["complex"] = cplx
+    return fr, fi
+
+
+# ----------------------------------------------------------------------------
+# Diffusion variant: models/tsc_diffusion.py, models/DiffuSE.py:39-69
+# ----------------------------------------------------------------------------
+def diffusion_step_table(max_steps: int) -> torch.Tensor:
+    """DiffusionEmbedding._build_embedding  models/DiffuSE.py:64-69 -> [max_steps, 128]."""
+    steps = torch.arange(max_steps).unsqueeze(1)
+    dims = torch.arange(64).unsqueeze(0)
+    table = steps * 10.0 ** (dims * 4.0 / 63.0)
+    return torch.cat([torch.sin(table), torch.cos(table)], dim=1)
+
+
+def diffusion_embedding(step: torch.Tensor, sd: SD, p: str, max_steps: int) -> torch.Tensor:
+    """DiffusionEmbedding.forward  models/DiffuSE.py:46-62: table row (integer step) or the linear interpolation of the
+    two neighbouring rows (fractional step), then Linear-SiLU-Linear-SiLU."""
+    table = diffusion_step_table(max_steps)
+    if step.dtype in (torch.int32, torch.int64):
+        e = table[step]
+    else:
+        lo, hi = torch.floor(step).long(), torch.ceil(step).long()
+        e = table[lo] + (table[hi] - table[lo]) * (step - lo).unsqueeze(-1)
+    h = _swish(F.linear(e, sd[p + ".projection1.weight"], sd[p + ".projection1.bias"]))
+    return _swish(F.linear(h, sd[p + ".projection2.weight"], sd[p + ".projection2.bias"]))
+
+
+def merge_block(x, cond, step, sd: SD, max_steps: int, p: str = "merge_block"):
+    """MergeBlock.forward  models/tsc_diffusion.py:27-41.  x, cond: (B, 64, T, F'); step: [1] or [B]."""
+    d = diffusion_embedding(step, sd, p + ".diffusion_embedding", max_steps)
+    d = F.linear(d, sd[p + ".diffusion_projection.weight"], sd[p + ".diffusion_projection.bias"])[:, :, None, None]
+    c = F.conv2d(cond, sd[p + ".conditioner_projection.weight"], sd[p + ".conditioner_projection.bias"])
+    y = F.conv2d(x + d, sd[p + ".merge_diffusion.weight"], sd[p + ".merge_diffusion.bias"]) + c
+    gate, filt = torch.chunk(y, 2, dim=1)
+    y = torch.sigmoid(gate) * torch.tanh(filt)
+    r = F.conv2d(y, sd[p + ".output_residual.weight"], sd[p + ".output_residual.bias"])
+    return (x + r) / math.sqrt(2.0)
+
+
+def tsc_diffusion_forward(spec: torch.Tensor, noisy_spec: torch.Tensor, step: torch.Tensor, sd: SD, max_steps: int,
+                          chunk: int = 0, stages: Optional[dict] = None):
+    """tsc_diffusion.TSCNet.forward  models/tsc_diffusion.py:60-90.  spec, noisy_spec: complex64 (B, 201, T); the mask and
+    the phase come from ``spec`` (the current estimate), ``noisy_spec`` only conditions the merge blocks."""
+    def in3(z):
+        return torch.cat([z.abs().unsqueeze(1).permute(0, 1, 3, 2), z.real.unsqueeze(1).permute(0, 1, 3, 2),
+                          z.imag.unsqueeze(1).permute(0, 1, 3, 2)], dim=1)
+    mag = spec.abs().unsqueeze(1).permute(0, 1, 3, 2)
+    ph = spec.angle().unsqueeze(1).permute(0, 1, 3, 2)
+    h = dense_encoder(in3(spec), sd, "dense_encoder")
+    cond = dense_encoder(in3(noisy_spec), sd, "dense_encoder_noisy")
+    if stages is not None:
+        stages["encoder"], stages["encoder_noisy"] = h, cond
+    for i in range(1, 5):
+        h = tscb(merge_block(h, cond, step, sd, max_steps), sd, f"TSCB_{i}", chunk)
+        if stages is not None:
+            stages[f"tscb{i}"] = h
+    mask = mask_decoder(h, sd)
+    cplx = complex_decoder(h, sd)
+    out_mag = mask * mag
+    fr = out_mag * torch.cos(ph) + cplx[:, 0:1]
+    fi = out_mag * torch.sin(ph) + cplx[:, 1:2]
+    if stages is not None:
+        stages["mask"], stages["complex"] = mask, cplx
     return fr, fi
 
 

@@ -79,9 +79,26 @@ def tscnet_spec():
     return k
 
 
-def synth_state_dict(seed: int = 0, perturb: float = 0.1) -> "OrderedDict[str, torch.Tensor]":
+def tsc_diffusion_spec():
+    """[(key, shape, kind)] of models/tsc_diffusion.py:TSCNet in the reference's state_dict order: the generator's entries with
+    ``dense_encoder_noisy`` and ``merge_block`` inserted after ``dense_encoder`` (tsc_diffusion.py:46-57)."""
+    base = tscnet_spec()
+    enc = [e for e in base if e[0].startswith("dense_encoder.")]
+    rest = [e for e in base if not e[0].startswith("dense_encoder.")]
+    noisy = [(k.replace("dense_encoder.", "dense_encoder_noisy.", 1), sh, kind) for k, sh, kind in enc]
+    m = "merge_block"
+    merge = [(f"{m}.diffusion_embedding.projection1.weight", (512, 128), "w"), (f"{m}.diffusion_embedding.projection1.bias", (512,), "b"),
+             (f"{m}.diffusion_embedding.projection2.weight", (512, 512), "w"), (f"{m}.diffusion_embedding.projection2.bias", (512,), "b"),
+             (f"{m}.diffusion_projection.weight", (64, 512), "w"), (f"{m}.diffusion_projection.bias", (64,), "b"),
+             (f"{m}.merge_diffusion.weight", (128, 64, 1, 1), "w"), (f"{m}.merge_diffusion.bias", (128,), "b"),
+             (f"{m}.conditioner_projection.weight", (128, 64, 1, 1), "w"), (f"{m}.conditioner_projection.bias", (128,), "b"),
+             (f"{m}.output_residual.weight", (64, 64, 1, 1), "w"), (f"{m}.output_residual.bias", (64,), "b")]
+    return enc + noisy + merge + rest
+
+
+def synth_state_dict(seed: int = 0, perturb: float = 0.1, spec=None) -> "OrderedDict[str, torch.Tensor]":
     sd = OrderedDict()
-    for idx, (key, shape, kind) in enumerate(tscnet_spec()):
+    for idx, (key, shape, kind) in enumerate(tscnet_spec() if spec is None else spec):
         g = torch.Generator().manual_seed(seed * 100003 + idx)
         rn = lambda: torch.randn(shape, generator=g, dtype=torch.float32)
         if kind == "w":

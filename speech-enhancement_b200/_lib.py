@@ -14,8 +14,8 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libseb200.so")
 
-LOAD_ROWS, LOAD_ROWS_LN, LOAD_CONV, LOAD_HANKEL, LOAD_CONV_SPLIT = 0, 1, 2, 3, 4
-EPI_BIAS, EPI_SWISH, EPI_GLU, EPI_RESID, EPI_SUBPIXEL, EPI_COMPRESS, EPI_QKV_F16 = 0, 1, 2, 3, 4, 5, 6
+LOAD_ROWS, LOAD_ROWS_LN, LOAD_CONV, LOAD_HANKEL, LOAD_CONV_SPLIT, LOAD_ROWS2 = 0, 1, 2, 3, 4, 5
+EPI_BIAS, EPI_SWISH, EPI_GLU, EPI_RESID, EPI_SUBPIXEL, EPI_COMPRESS, EPI_QKV_F16, EPI_GATE, EPI_RESID_SCALE = 0, 1, 2, 3, 4, 5, 6, 7, 8
 ENGINE_TCGEN05, ENGINE_SIMT = 0, 1
 
 _fp = C.c_void_p  # raw device pointers travel as void*
@@ -71,6 +71,7 @@ _SIGS = {
     "seb200_dwconv_bn_swish": [_fp, C.POINTER(SebSeq), _fp, _fp, _fp, _fp, _fp],
     "seb200_dwconv_pw2": [_fp, C.POINTER(SebSeq), _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp],
     "seb200_layernorm_residual": [_fp, C.c_longlong, _fp, _fp, _fp, _fp, _fp],
+    "seb200_diffusion_embed": [_fp, C.c_int, _fp, C.c_int, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp],
 }
 EXPORTS = sorted(list(_SIGS) + ["seb200_inorm_workspace_bytes", "seb200_version", "seb200_last_error_string",
                                 "seb200_launch_count"])

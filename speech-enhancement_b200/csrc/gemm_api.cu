@@ -100,6 +100,9 @@ extern "C" int seb200_gemm(const SebGemm* s, int engine, void* stream) {
   if (s->loader == SEB_LOAD_ROWS || s->loader == SEB_LOAD_ROWS_LN) {
     SEB_REQUIRE(s->lda % 4 == 0 && s->lda >= s->K, SEB_EALIGN, "gemm: lda=%lld must be a multiple of 4 and >= K", s->lda);
   }
+  if (s->loader == SEB_LOAD_ROWS2) {
+    SEB_REQUIRE(s->K == 128 && s->a[1] && aligned16(s->a[1]) && s->lda % 4 == 0 && s->lda >= 64, SEB_EALIGN, "gemm: the two-source loader needs K == 128, a[1] and lda >= 64");
+  }
   if (s->loader == SEB_LOAD_ROWS_LN) {
     SEB_REQUIRE(s->K == 64 && s->ln_gamma && s->ln_beta, SEB_EINVAL, "gemm: LayerNorm loader needs K == 64 and gamma/beta");
   }
@@ -112,7 +115,11 @@ extern "C" int seb200_gemm(const SebGemm* s, int engine, void* stream) {
   if (s->loader == SEB_LOAD_HANKEL) {
     SEB_REQUIRE(s->Fin > 0 && s->Fin % 8 == 0 && s->Fin <= s->K && s->stride_f % 4 == 0 && s->lda % 4 == 0 && s->T > 0, SEB_EALIGN, "gemm: bad framing geometry");
   }
-  if (s->epilogue == SEB_EPI_RESID) SEB_REQUIRE(s->resid && s->ldr % 4 == 0 && aligned16(s->resid), SEB_EALIGN, "gemm: residual null/unaligned");
+  if (s->epilogue == SEB_EPI_GATE) {
+    SEB_REQUIRE(s->N % 8 == 0 && s->ldo % 4 == 0, SEB_EALIGN, "gemm: the gate epilogue needs N % 8 == 0 and ldo % 4 == 0");
+    SEB_REQUIRE(!s->resid || (s->ldr > 0 && s->ldr <= 2147483647LL && aligned16(s->resid)), SEB_EINVAL, "gemm: gate row bias needs ldr = rows per group > 0");
+  }
+  if (s->epilogue == SEB_EPI_RESID || s->epilogue == SEB_EPI_RESID_SCALE) SEB_REQUIRE(s->resid && s->ldr % 4 == 0 && aligned16(s->resid), SEB_EALIGN, "gemm: residual null/unaligned");
   if (s->epilogue == SEB_EPI_GLU) SEB_REQUIRE(s->ldo % 2 == 0, SEB_EALIGN, "gemm: ldo must be even");
   else if (s->epilogue != SEB_EPI_COMPRESS) SEB_REQUIRE(s->ldo % 4 == 0, SEB_EALIGN, "gemm: ldo must be a multiple of 4");
   if (s->epilogue == SEB_EPI_QKV_F16) SEB_REQUIRE(s->N == 192 && s->ldo == 192, SEB_EINVAL, "gemm: the fp16 q|k|v epilogue needs N == ldo == 192");
@@ -125,6 +132,8 @@ extern "C" int seb200_gemm(const SebGemm* s, int engine, void* stream) {
       case SEB_LOAD_HANKEL * 16 + SEB_EPI_COMPRESS: return launch_simt<SEB_LOAD_HANKEL, SEB_EPI_COMPRESS>(s, g, st);
       case SEB_LOAD_ROWS * 16 + SEB_EPI_BIAS:       return launch_simt<SEB_LOAD_ROWS, SEB_EPI_BIAS>(s, g, st);
       case SEB_LOAD_ROWS * 16 + SEB_EPI_RESID:      return launch_simt<SEB_LOAD_ROWS, SEB_EPI_RESID>(s, g, st);
+      case SEB_LOAD_ROWS * 16 + SEB_EPI_RESID_SCALE: return launch_simt<SEB_LOAD_ROWS, SEB_EPI_RESID_SCALE>(s, g, st);
+      case SEB_LOAD_ROWS2 * 16 + SEB_EPI_GATE:      return launch_simt<SEB_LOAD_ROWS2, SEB_EPI_GATE>(s, g, st);
       case SEB_LOAD_CONV * 16 + SEB_EPI_BIAS:       return launch_simt<SEB_LOAD_CONV, SEB_EPI_BIAS>(s, g, st);
       case SEB_LOAD_CONV * 16 + SEB_EPI_SUBPIXEL:   return launch_simt<SEB_LOAD_CONV, SEB_EPI_SUBPIXEL>(s, g, st);
       case SEB_LOAD_ROWS_LN * 16 + SEB_EPI_SWISH:   return launch_simt<SEB_LOAD_ROWS_LN, SEB_EPI_SWISH>(s, g, st);
@@ -156,6 +165,8 @@ extern "C" int seb200_gemm(const SebGemm* s, int engine, void* stream) {
                                                                                              : launch_tc<208, 1, SEB_LOAD_ROWS, SEB_EPI_BIAS>(s, g, st); break;
       case SEB_LOAD_ROWS * 16 + SEB_EPI_RESID:      if (nt == 64)  return (s->K <= 128) ? launch_tc<64, 1, SEB_LOAD_ROWS, SEB_EPI_RESID, 4, 4>(s, g, st)
                                                                                       : launch_tc<64, 2, SEB_LOAD_ROWS, SEB_EPI_RESID>(s, g, st); break;
+      case SEB_LOAD_ROWS * 16 + SEB_EPI_RESID_SCALE: if (nt == 64) return launch_tc<64, 1, SEB_LOAD_ROWS, SEB_EPI_RESID_SCALE, 4, 4>(s, g, st); break;
+      case SEB_LOAD_ROWS2 * 16 + SEB_EPI_GATE:      if (nt == 128) return launch_tc<128, 1, SEB_LOAD_ROWS2, SEB_EPI_GATE>(s, g, st); break;
       case SEB_LOAD_CONV * 16 + SEB_EPI_BIAS:       if (nt == 64)  return launch_tc<64, 2, SEB_LOAD_CONV, SEB_EPI_BIAS>(s, g, st); break;
       case SEB_LOAD_CONV * 16 + SEB_EPI_SUBPIXEL:   if (nt == 128) return launch_tc<128, 1, SEB_LOAD_CONV, SEB_EPI_SUBPIXEL>(s, g, st); break;
       case SEB_LOAD_ROWS_LN * 16 + SEB_EPI_SWISH:   if (nt == 256) return launch_tc<256, 1, SEB_LOAD_ROWS_LN, SEB_EPI_SWISH>(s, g, st); break;

@@ -58,6 +58,23 @@ template <> struct Loader<SEB_LOAD_ROWS> {
   }
 };
 
+// Two 64-wide row sources side by side (K = 128): K chunk 0 reads a[0], chunk 1 reads a[1] (MergeBlock: [x | conditioner],
+// models/tsc_diffusion.py:32-34 -- merge_diffusion and conditioner_projection are one contraction over the pair)
+template <> struct Loader<SEB_LOAD_ROWS2> {
+  struct Row { long long off; };   // off < 0: row beyond M
+  __device__ static void init_row(const GemmArgs& g, int m, Row& r) { r.off = (m < g.M) ? (long long)m * g.lda : -1; }
+  __device__ static void load(const GemmArgs& g, const Row& r, int kc, int sub, float (&v)[8]) {
+    if (r.off >= 0) {
+      const float* p = g.a[kc & 1] + r.off + sub * 8;
+      float4 x = ldg4(p), y = ldg4(p + 4);
+      v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    }
+  }
+};
+
 // LayerNorm(64, eps 1e-5) fused into the load (PreNorm, conformer.py:63-71 and net[0] of the conv module)
 template <> struct Loader<SEB_LOAD_ROWS_LN> {
   using Row = Loader<SEB_LOAD_ROWS>::Row;
@@ -186,6 +203,31 @@ template <> struct Epi<SEB_EPI_RESID> {
     v = add_bias(g, n, v);
     float4 r = *reinterpret_cast<const float4*>(g.resid + (long long)m * g.ldr + n);
     v.x = g.alpha * v.x + r.x; v.y = g.alpha * v.y + r.y; v.z = g.alpha * v.z + r.z; v.w = g.alpha * v.w + r.w;
+    st4(g.out + (long long)m * g.ldo + n, v);
+  }
+};
+
+// MergeBlock gate (models/tsc_diffusion.py:36-37): packed columns (gate_j, filter_j); the diffusion-step projection enters as one
+// extra bias row per group of g.ldr consecutive rows (g.resid [groups, N]; null: none)
+template <> struct Epi<SEB_EPI_GATE> {
+  __device__ static void apply(const GemmArgs& g, int m, int n, float4 v) {
+    if (m >= g.M || n >= g.N) return;
+    v = add_bias(g, n, v);
+    if (g.resid) {
+      const float4 r = ldg4(g.resid + (long long)(m / (int)g.ldr) * g.N + n);
+      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    }
+    float2 o = make_float2(sigmoidf_acc(v.x) * tanhf_acc(v.y), sigmoidf_acc(v.z) * tanhf_acc(v.w));
+    *reinterpret_cast<float2*>(g.out + (long long)m * g.ldo + (n >> 1)) = o;
+  }
+};
+
+template <> struct Epi<SEB_EPI_RESID_SCALE> {   // (x + output_residual(y)) / sqrt(2): tsc_diffusion.py:39-41
+  __device__ static void apply(const GemmArgs& g, int m, int n, float4 v) {
+    if (m >= g.M || n >= g.N) return;
+    v = add_bias(g, n, v);
+    float4 r = *reinterpret_cast<const float4*>(g.resid + (long long)m * g.ldr + n);
+    v.x = g.alpha * (v.x + r.x); v.y = g.alpha * (v.y + r.y); v.z = g.alpha * (v.z + r.z); v.w = g.alpha * (v.w + r.w);
     st4(g.out + (long long)m * g.ldo + n, v);
   }
 };

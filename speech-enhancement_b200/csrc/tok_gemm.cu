@@ -23,8 +23,11 @@ constexpr int TG_W_COPY = TG_W_MMA + 1;                                       //
 constexpr int TG_THREADS = (TG_W_COPY + 1) * 32;                              // 704
 template <int KCH> constexpr int tg_slots() { return KCH == 1 ? 3 : 2; }
 template <int KCH> constexpr int tg_xslot() { return BM * 64 * KCH * 4; }     // raw fp32 rows of one tile: 32 / 64 KB
-template <int NT, int KCH> constexpr int tg_smem_bytes() {
-  return 1024 + tg_slots<KCH>() * tg_xslot<KCH>() + KCH * 2 * NT * 128 + TG_EPI_WARPS * 4096 + 2 * 64 * 4 + NT * 4;
+// epilogue staging per warp: the packed epilogues (GLU / fp16 q|k|v / gate) transpose 32 x 64 B, the others 32 x 128 B
+template <int EK> constexpr bool tg_packed() { return EK == SEB_EPI_GLU || EK == SEB_EPI_QKV_F16 || EK == SEB_EPI_GATE; }
+template <int EK> constexpr int tg_stg() { return tg_packed<EK>() ? 2048 : 4096; }
+template <int NT, int KCH, int EK> constexpr int tg_smem_bytes() {
+  return 1024 + tg_slots<KCH>() * tg_xslot<KCH>() + KCH * 2 * NT * 128 + TG_EPI_WARPS * tg_stg<EK>() + 2 * 64 * 4 + NT * 4;
 }
 
 namespace ptx {
@@ -44,7 +47,9 @@ __device__ __forceinline__ void tg_tmem_st8(uint32_t taddr, const uint32_t* r) {
 template <int NT, int KCH, int LK, int EK>
 __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs g, const uint8_t* __restrict__ w_tc) {
   static_assert(NT % 64 == 0 && NT <= 256 && (KCH == 1 || KCH == 2), "unsupported token GEMM shape");
-  static_assert(LK == SEB_LOAD_ROWS || (LK == SEB_LOAD_ROWS_LN && KCH == 1), "loader: plain rows, or LayerNorm over 64 features");
+  static_assert(LK == SEB_LOAD_ROWS || (LK == SEB_LOAD_ROWS_LN && KCH == 1) || (LK == SEB_LOAD_ROWS2 && KCH == 2),
+                "loader: plain rows, LayerNorm over 64 features, or two 64-wide sources side by side");
+  constexpr int STG = tg_stg<EK>();
   constexpr int K = 64 * KCH, NSLOT = tg_slots<KCH>(), XSLOT = tg_xslot<KCH>(), PITCH = K * 4, NCH = K / 4;   // 16-byte chunks per row
   constexpr bool ACC2 = (2 * K + 2 * NT <= 512);                 // double-buffered accumulator when tensor memory has room
   constexpr uint32_t T_ACC = 2 * K;                              // TMEM: XA[2] (K columns each: hi | lo) | ACC[1 or 2] (NT columns each)
@@ -55,7 +60,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs 
   uint8_t* sW = smem;                                   // [kc][hi | lo][NT rows x 128 B], resident
   uint8_t* sX = sW + KCH * 2 * NT * 128;                // ring of raw fp32 tiles, 16-byte chunk c of row r at r * PITCH + ((c ^ (r & 7)) << 4)
   uint8_t* sStg = sX + NSLOT * XSLOT;                   // 4 KB per epilogue warp
-  float* sG = reinterpret_cast<float*>(sStg + TG_EPI_WARPS * 4096);
+  float* sG = reinterpret_cast<float*>(sStg + TG_EPI_WARPS * STG);
   float* sBt = sG + 64;
   float* sBias = sBt + 64;                               // [NT] output bias (zeros when the GEMM has none)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -135,7 +140,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs 
     const int ew = warp - TG_W_EPI0;
     const int wq = warp & 3, cgi = ew >> 2;             // TMEM lane quarter (hardware: warp % 4), column group
     constexpr int CPW = NT / (TG_EPI_WARPS / 4);        // columns per warp (64 / 48 / 16)
-    float4* stg = reinterpret_cast<float4*>(sStg + ew * 4096);      // [32 rows][8 x float4]
+    float4* stg = reinterpret_cast<float4*>(sStg + ew * STG);       // [32 rows][8 x float4] (packed epilogues: [32 rows][4 x 16 B])
     // the bias of this lane's columns is loop invariant: keep it in registers and hand the functors a bias-free descriptor
     // (inside Epi<>::apply the load sat in front of every use: ~20 % of the epilogue's stall samples)
     GemmArgs gnb = g;
@@ -154,8 +159,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs 
       // residual rows of this warp's outputs: issued BEFORE the accumulator wait (out may alias resid, so the compiler
       // cannot hoist them over the stores of the copy-out loop itself; serialised they cost eight DRAM round trips per tile)
       float4 res[8];
-      if (EK == SEB_EPI_RESID) {
-        static_assert(EK != SEB_EPI_RESID || CPW <= 32, "residual prefetch covers one 32-column pass");
+      if (EK == SEB_EPI_RESID || EK == SEB_EPI_RESID_SCALE) {
+        static_assert((EK != SEB_EPI_RESID && EK != SEB_EPI_RESID_SCALE) || CPW <= 32, "residual prefetch covers one 32-column pass");
 #pragma unroll
         for (int i8 = 0; i8 < 8; ++i8) {
           const int m = m0 + wq * 32 + i8 * 4 + (lane >> 3), n = cgi * CPW + ch * 4;
@@ -165,7 +170,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs 
       ptx::mbar_wait(&acc_full[ab], use & 1u);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + T_ACC + (uint32_t)(ab * NT + cgi * CPW);
-      if (EK == SEB_EPI_GLU || EK == SEB_EPI_QKV_F16) {
+      if (tg_packed<EK>()) {
         // element-wise part in the accumulator's own thread = row layout (bias, GLU / fp16 scaling), THEN the transpose: the
         // staged tile and the copy-out carry the packed outputs only (half the words of the fp32 accumulator columns)
         uint4* stq = reinterpret_cast<uint4*>(stg);                   // [32 rows][4 x 16 B], chunk XOR ((row >> 1) & 3)
@@ -185,6 +190,11 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs 
             }
           }
           if (c0 + 32 >= CPW) { ptx::tc_fence_before(); ptx::mbar_arrive(&acc_empty[ab]); }     // accumulator fully read
+          const float* rb = nullptr;               // gate: this row's group bias (diffusion-step projection), L1-resident
+          if (EK == SEB_EPI_GATE && g.resid) {
+            const int mr = m0 + wq * 32 + lane;
+            rb = g.resid + (long long)((mr < g.M ? mr : g.M - 1) / (int)g.ldr) * g.N + n0;
+          }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {            // output chunk q <- accumulator columns 8q .. 8q + 7
             if (q * 8 < ncols) {
@@ -195,6 +205,16 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs 
                 o.y = __float_as_uint((v[8 * q + 2] + b0.z) * sigmoidf_acc(v[8 * q + 3] + b0.w));
                 o.z = __float_as_uint((v[8 * q + 4] + b1.x) * sigmoidf_acc(v[8 * q + 5] + b1.y));
                 o.w = __float_as_uint((v[8 * q + 6] + b1.z) * sigmoidf_acc(v[8 * q + 7] + b1.w));
+              } else if (EK == SEB_EPI_GATE) {     // packed columns: (gate_j, filter_j) adjacent (tsc_diffusion.py:36-37)
+                float4 b0 = *reinterpret_cast<const float4*>(sBias + n0 + 8 * q), b1 = *reinterpret_cast<const float4*>(sBias + n0 + 8 * q + 4);
+                if (rb) {
+                  const float4 r0 = ldg4(rb + 8 * q), r1 = ldg4(rb + 8 * q + 4);
+                  b0.x += r0.x; b0.y += r0.y; b0.z += r0.z; b0.w += r0.w; b1.x += r1.x; b1.y += r1.y; b1.z += r1.z; b1.w += r1.w;
+                }
+                o.x = __float_as_uint(sigmoidf_acc(v[8 * q + 0] + b0.x) * tanhf_acc(v[8 * q + 1] + b0.y));
+                o.y = __float_as_uint(sigmoidf_acc(v[8 * q + 2] + b0.z) * tanhf_acc(v[8 * q + 3] + b0.w));
+                o.z = __float_as_uint(sigmoidf_acc(v[8 * q + 4] + b1.x) * tanhf_acc(v[8 * q + 5] + b1.y));
+                o.w = __float_as_uint(sigmoidf_acc(v[8 * q + 6] + b1.z) * tanhf_acc(v[8 * q + 7] + b1.w));
               } else {                             // fp16 q | k | v, q pre-scaled by dim_head^-0.5 * log2(e)
                 const float sc = (n0 + 8 * q < 64) ? 0.25f * 1.4426950408889634f : 1.0f;
                 __half2 h0 = __floats2half2_rn(v[8 * q + 0] * sc, v[8 * q + 1] * sc), h1 = __floats2half2_rn(v[8 * q + 2] * sc, v[8 * q + 3] * sc);
@@ -213,7 +233,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs 
               const int m = m0 + wq * 32 + R;
               const uint4 o = stq[R * 4 + (cc ^ ((R >> 1) & 3))];
               if (m < g.M) {
-                if (EK == SEB_EPI_GLU) *reinterpret_cast<uint4*>(g.out + (long long)m * g.ldo + (n0 >> 1) + cc * 4) = o;
+                if (EK == SEB_EPI_GLU || EK == SEB_EPI_GATE) *reinterpret_cast<uint4*>(g.out + (long long)m * g.ldo + (n0 >> 1) + cc * 4) = o;
                 else *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(g.out) + (long long)m * g.ldo + n0 + cc * 8) = o;
               }
             }
@@ -253,6 +273,14 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs 
                 const float4 bb = bias4[c0 / 32];
                 v.x = fmaf(g.alpha, v.x + bb.x, res[i8].x); v.y = fmaf(g.alpha, v.y + bb.y, res[i8].y);
                 v.z = fmaf(g.alpha, v.z + bb.z, res[i8].z); v.w = fmaf(g.alpha, v.w + bb.w, res[i8].w);
+                st4(g.out + (long long)m * g.ldo + n, v);
+              }
+            } else if (EK == SEB_EPI_RESID_SCALE) {
+              if (m < g.M && n < g.N) {
+                float4 v = vals[i8];
+                const float4 bb = bias4[c0 / 32];
+                v.x = g.alpha * (v.x + bb.x + res[i8].x); v.y = g.alpha * (v.y + bb.y + res[i8].y);
+                v.z = g.alpha * (v.z + bb.z + res[i8].z); v.w = g.alpha * (v.w + bb.w + res[i8].w);
                 st4(g.out + (long long)m * g.ldo + n, v);
               }
             } else {
@@ -307,6 +335,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs 
         for (uint32_t o = 0; o < WB; o += PIECE) ptx::bulk_g2s(ptx::smem_u32(sW) + o, w_tc + o, (WB - o < PIECE) ? WB - o : PIECE, &w_full);
       }
       const float* src0 = g.a[0];
+      const float* src1 = (LK == SEB_LOAD_ROWS2) ? g.a[1] : nullptr;
       for (int it = 0; it < my_tiles; ++it) {
         const int m0 = ((int)blockIdx.x + it * (int)gridDim.x) * BM;
         const int slot = it % NSLOT;
@@ -317,8 +346,10 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs 
           const int i = kk * 32 + lane, r = i / NCH, c = i % NCH;
           const int m = m0 + r;
           const int mc = m < g.M ? m : g.M - 1;
+          const float* src = (LK == SEB_LOAD_ROWS2) ? ((c < 16 ? src0 : src1) + (long long)mc * g.lda + (c & 15) * 4)
+                                                    : (src0 + (long long)mc * g.lda + c * 4);
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
-                       ::"r"(dst0 + r * PITCH + ((c ^ (r & 7)) << 4)), "l"(src0 + (long long)mc * g.lda + c * 4), "r"(m < g.M ? 16u : 0u) : "memory");
+                       ::"r"(dst0 + r * PITCH + ((c ^ (r & 7)) << 4)), "l"(src), "r"(m < g.M ? 16u : 0u) : "memory");
         }
         asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(ptx::smem_u32(&x_full[slot])) : "memory");
       }
@@ -335,7 +366,8 @@ template <int NT, int KCH, int LK, int EK>
 static int launch_tok(const SebGemm* s, const GemmArgs& g, cudaStream_t st) {
   static bool attr_done = false;
   static int num_sms = 0;
-  constexpr int SMEM = tg_smem_bytes<NT, KCH>();
+  constexpr int SMEM = tg_smem_bytes<NT, KCH, EK>();
+  static_assert(SMEM + 256 <= 232448, "token GEMM: shared memory over the 227 KB per-CTA limit");
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(tok_gemm_kernel<NT, KCH, LK, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) { set_error("tok gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
@@ -365,6 +397,10 @@ int launch_tok_gemm(const SebGemm* s, const GemmArgs& g, cudaStream_t st) {
     return launch_tok<64, 1, SEB_LOAD_ROWS, SEB_EPI_RESID>(s, g, st);
   if (s->loader == SEB_LOAD_ROWS && s->epilogue == SEB_EPI_RESID && nt == 64 && s->K == 128 && s->lda == 128)
     return launch_tok<64, 2, SEB_LOAD_ROWS, SEB_EPI_RESID>(s, g, st);
+  if (s->loader == SEB_LOAD_ROWS2 && s->epilogue == SEB_EPI_GATE && nt == 128 && s->K == 128 && s->N == 128)
+    return launch_tok<128, 2, SEB_LOAD_ROWS2, SEB_EPI_GATE>(s, g, st);
+  if (s->loader == SEB_LOAD_ROWS && s->epilogue == SEB_EPI_RESID_SCALE && nt == 64 && s->K == 64 && s->lda == 64)
+    return launch_tok<64, 1, SEB_LOAD_ROWS, SEB_EPI_RESID_SCALE>(s, g, st);
   return -100;
 }
 

@@ -106,17 +106,22 @@ def _sub_pixel(ch: int) -> _Bag:
     return sp
 
 
+def _dense_encoder(ch: int) -> _Bag:
+    """DenseEncoder(in_channel=3, channels=ch) parameters (generator.py:35-48)."""
+    enc = _Bag()
+    enc.conv_1 = nn.Sequential(nn.Conv2d(3, ch, (1, 1), (1, 1)), nn.InstanceNorm2d(ch, affine=True), nn.PReLU(ch))
+    enc.dilated_dense = _dense_block(ch)
+    enc.conv_2 = nn.Sequential(nn.Conv2d(ch, ch, (1, 3), (1, 2), padding=(0, 1)), nn.InstanceNorm2d(ch, affine=True), nn.PReLU(ch))
+    return enc
+
+
 class TSCNet(nn.Module):
     def __init__(self, num_channel: int = 64, num_features: int = 201):
         super().__init__()
         if num_channel != 64:
             raise ValueError("the sm_100a kernels are specialised for num_channel=64 (main_gan.py:145, inference_gan.py:61)")
         ch = num_channel
-        enc = _Bag()
-        enc.conv_1 = nn.Sequential(nn.Conv2d(3, ch, (1, 1), (1, 1)), nn.InstanceNorm2d(ch, affine=True), nn.PReLU(ch))
-        enc.dilated_dense = _dense_block(ch)
-        enc.conv_2 = nn.Sequential(nn.Conv2d(ch, ch, (1, 3), (1, 2), padding=(0, 1)), nn.InstanceNorm2d(ch, affine=True), nn.PReLU(ch))
-        self.dense_encoder = enc
+        self.dense_encoder = _dense_encoder(ch)
         for i in range(1, 5):
             blk = _Bag()
             blk.time_conformer = _conformer(ch)
@@ -178,13 +183,13 @@ class TSCNet(nn.Module):
                     P[f"{prefix}.{nm}{i}.weight"] = dev(sd[f"{prefix}.{nm}{i}.weight"])
                 P[f"{prefix}.norm{i}.bias"] = dev(sd[f"{prefix}.norm{i}.bias"])
 
-        e = "dense_encoder"
-        P[f"{e}.conv_1.w"] = dev(sd[f"{e}.conv_1.0.weight"].reshape(64, 3))
-        P[f"{e}.conv_1.b"] = dev(sd[f"{e}.conv_1.0.bias"])
-        for k in ("conv_1.1.weight", "conv_1.1.bias", "conv_1.2.weight", "conv_2.1.weight", "conv_2.1.bias", "conv_2.2.weight"):
-            P[f"{e}.{k}"] = dev(sd[f"{e}.{k}"])
-        dense(f"{e}.dilated_dense")
-        P[f"{e}.conv_2"] = pack_weight(conv_weight_matrix(sd[f"{e}.conv_2.0.weight"]), 64, sd[f"{e}.conv_2.0.bias"]).to(device)
+        for e in self._encoder_names():
+            P[f"{e}.conv_1.w"] = dev(sd[f"{e}.conv_1.0.weight"].reshape(64, 3))
+            P[f"{e}.conv_1.b"] = dev(sd[f"{e}.conv_1.0.bias"])
+            for k in ("conv_1.1.weight", "conv_1.1.bias", "conv_1.2.weight", "conv_2.1.weight", "conv_2.1.bias", "conv_2.2.weight"):
+                P[f"{e}.{k}"] = dev(sd[f"{e}.{k}"])
+            dense(f"{e}.dilated_dense")
+            P[f"{e}.conv_2"] = pack_weight(conv_weight_matrix(sd[f"{e}.conv_2.0.weight"]), 64, sd[f"{e}.conv_2.0.bias"]).to(device)
 
         for i in range(1, 5):
             for ax in ("time", "freq"):
@@ -223,7 +228,14 @@ class TSCNet(nn.Module):
         for k in ("prelu.weight", "norm.weight", "norm.bias", "conv.bias"):
             P[f"{c}.{k}"] = dev(sd[f"{c}.{k}"])
         P[f"{c}.conv.w"] = dev(sd[f"{c}.conv.weight"][:, :, 0, :].permute(0, 2, 1))                   # [2 out][2 taps][64]
+        self._pack_extra(sd, P, dev, device)
         return P
+
+    def _encoder_names(self):
+        return ("dense_encoder",)
+
+    def _pack_extra(self, sd, P, dev, device):
+        """hook for variants with more parameters (tsc_diffusion.TSCNet: second encoder + MergeBlock)"""
 
     # -----------------------------------------------------------------------------------------
     # workspaces: one set of activation buffers per (device, B, T), reused across calls
@@ -338,10 +350,17 @@ class TSCNet(nn.Module):
         dev = in3.device
         P = self.packed()
         ws = self.workspace(B, T, dev)
-        eng = self.engine
-        e = "dense_encoder"
+        x = self._encode(P, "dense_encoder", ws, in3, ws["x"])
+        if stages is not None:
+            stages["encoder"] = x.view(B, T, Fh, 64).clone()
+        self._tscbs(P, ws, x, B, T, Fh, stages)
+        return self._decode(P, ws, x, in3, stages)
 
-        # ---- DenseEncoder (generator.py:50-54)
+    def _encode(self, P, e, ws, in3, x):
+        """DenseEncoder.forward (generator.py:50-54): in3 [B, T, F, 3] -> x [B*T*F', 64] (written in place, returned)."""
+        B, T, F, _ = in3.shape
+        Fh = (F - 1) // 2 + 1
+        eng = self.engine
         tc = eng == "tcgen05"
         conv_loader = LOAD_CONV_SPLIT if tc else LOAD_CONV
         enc, raw = [self._conv_in(t) for t in ws["enc"]], ws["enc_raw"]
@@ -351,20 +370,34 @@ class TSCNet(nn.Module):
         rawh = ws["dec_raw"]
         ops.gemm(loader=conv_loader, epilogue=EPI_BIAS, M=B * T * Fh, w=P[f"{e}.conv_2"], a=[d4], out=rawh, ldo=64, engine=eng, label="conv2",
                  conv=dict(B=B, T=T, Fin=F, Fout=Fh, taps_t=1, dil=1, stride_f=2, nslots=1))
-        x = ws["x"]
         self._inorm_prelu(ws, rawh, B, T * Fh, P[f"{e}.conv_2.1.weight"], P[f"{e}.conv_2.1.bias"], P[f"{e}.conv_2.2.weight"], x)
-        if stages is not None:
-            stages["encoder"] = x.view(B, T, Fh, 64).clone()
+        return x
 
-        # ---- 4 x TSCB (generator.py:67-74)
+    def _before_tscb(self, P, ws, x, i):
+        """hook: tsc_diffusion.TSCNet runs its MergeBlock on x before every TSCB"""
+
+    def _tscbs(self, P, ws, x, B, T, Fh, stages=None):
+        """4 x TSCB (generator.py:67-74); x [B*T*F', 64] updated in place."""
         M = B * T * Fh
         seq_t = ops.make_seq(B * Fh, T, Fh, T * Fh, Fh)
         seq_f = ops.make_seq(B * T, Fh, 1, Fh, 1)
         for i in range(1, 5):
+            self._before_tscb(P, ws, x, i)
             self._conformer(P, f"TSCB_{i}.time_conformer", ws, x, seq_t, M)
             self._conformer(P, f"TSCB_{i}.freq_conformer", ws, x, seq_f, M)
             if stages is not None:
                 stages[f"tscb{i}"] = x.view(B, T, Fh, 64).clone()
+
+    def _decode(self, P, ws, x, in3, stages=None):
+        """Mask / Complex decoders + recombination with the spectrogram in3 (generator.py:106-129,158-165) -> est [B*T, F, 2]."""
+        B, T, F, _ = in3.shape
+        Fh = (F - 1) // 2 + 1
+        M = B * T * Fh
+        dev = in3.device
+        eng = self.engine
+        tc = eng == "tcgen05"
+        conv_loader = LOAD_CONV_SPLIT if tc else LOAD_CONV
+        rawh = ws["dec_raw"]
 
         # ---- MaskDecoder (generator.py:106-112)
         m = "mask_decoder"

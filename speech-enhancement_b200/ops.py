@@ -135,6 +135,20 @@ def gemm(*, loader: int, epilogue: int, M: int, w: PackedWeight, a: Sequence[tor
     return out
 
 
+def diffusion_embed(steps: torch.Tensor, table, w1, b1, w2, b2, wp, bp, wm, d_out: torch.Tensor, rowbias: torch.Tensor):
+    """MergeBlock's diffusion-step branch (tsc_diffusion.py:27-29, DiffuSE.py:46-62): steps float32 [n] -> d_out [n, 64] and
+    rowbias [n, 128] = wm . d (the per-utterance bias row of the merge GEMM)."""
+    _f32c(steps, table, w1, b1, w2, b2, wp, bp, wm, d_out, rowbias)
+    n = steps.numel()
+    if table.shape[1] != 128 or tuple(d_out.shape) != (n, 64) or tuple(rowbias.shape) != (n, 128):
+        raise RuntimeError("diffusion_embed: bad shapes")
+    tok = _pb("diffusion_embed")
+    check(_lib.load().seb200_diffusion_embed(ptr(steps), n, ptr(table), table.shape[0], ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(wp), ptr(bp),
+                                             ptr(wm), ptr(d_out), ptr(rowbias), stream_ptr()), "seb200_diffusion_embed")
+    _pe(tok)
+    return d_out, rowbias
+
+
 def ffn_fused(x, out, ln, w1: PackedWeight, w2: PackedWeight, alpha: float = 0.5, post=None, resid2=None):
     """y = x + alpha * FF(LN(x)); with ``post=(gamma, beta)``: out = LN_post(y) + resid2.  One tcgen05 kernel."""
     _f32c(x, out, resid2)

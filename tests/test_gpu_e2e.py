@@ -65,6 +65,40 @@ def test_module_forward_matches_reference_golden(golden, engine):
 
 
 @pytest.mark.parametrize("engine", ["simt", "tcgen05"])
+def test_diffusion_module_matches_reference_golden(golden, engine):
+    """tsc_diffusion.TSCNet.forward(x, noisy_spec, diffusion_step) against the reference's own outputs
+    (integer, fractional and per-utterance steps), and stage by stage against the oracle."""
+    from se_b200 import tsc_diffusion
+    g = golden("diffusion_b2_L3000")
+    sd = weights.synth_state_dict(int(g["weight_seed"]), spec=weights.tsc_diffusion_spec())
+    model = tsc_diffusion.TSCNet(num_channel=64, num_features=201, noise_schedule=[0.0] * int(g["max_steps"]))
+    model.load_state_dict(sd, strict=True)
+    model = model.to(DEV).eval()
+    model.engine = engine
+    sx = torch.complex(torch.from_numpy(g["spec_x_real"]), torch.from_numpy(g["spec_x_imag"]))
+    sn = torch.complex(torch.from_numpy(g["spec_n_real"]), torch.from_numpy(g["spec_n_imag"]))
+    for tag, vals, dt in [("int1", [7], torch.int64), ("frac1", [3.4], torch.float32), ("intB", [2, 40], torch.int64)]:
+        fr, fi = model(sx.to(DEV), sn.to(DEV), torch.tensor(vals, dtype=dt, device=DEV))
+        assert fr.shape == (2, 1, 31, 201) and fi.shape == fr.shape and fr.dtype == torch.float32
+        peak = max(np.abs(g[f"final_real_{tag}"]).max(), np.abs(g[f"final_imag_{tag}"]).max())
+        assert (fr.cpu() - torch.from_numpy(g[f"final_real_{tag}"])).abs().max() / peak < WAVE_TOL, tag
+        assert (fi.cpu() - torch.from_numpy(g[f"final_imag_{tag}"])).abs().max() / peak < WAVE_TOL, tag
+    # stage by stage (per-utterance steps), through the in3 entry the fused front end uses
+    st_o, st_g = {}, {}
+    step = torch.tensor([2, 40])
+    with torch.no_grad():
+        O.tsc_diffusion_forward(sx, sn, step, sd, int(g["max_steps"]), stages=st_o)
+        model.forward_in3(se_b200.ops.spec_to_in3(sx.to(DEV)), se_b200.ops.spec_to_in3(sn.to(DEV)), step.to(DEV), stages=st_g)
+    cl = lambda t: t.permute(0, 2, 3, 1)
+    for k in ("encoder", "encoder_noisy", "tscb1", "tscb4"):
+        assert rel_max(st_g[k].cpu(), cl(st_o[k])) < 1e-3, k
+    # a python int / list step works like the reference's tensor (torch.as_tensor on the host side)
+    fr2, _ = model(sx.to(DEV), sn.to(DEV), torch.tensor([7], device=DEV))
+    fr3, _ = model(sx.to(DEV), sn.to(DEV), [7])
+    assert torch.equal(fr2, fr3)
+
+
+@pytest.mark.parametrize("engine", ["simt", "tcgen05"])
 def test_stages_against_oracle(engine):
     """per-stage parity on a clip long enough for the +-512 relative-position clamp (T = 601 frames)"""
     sd = weights.synth_state_dict(4)

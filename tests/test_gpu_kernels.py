@@ -12,8 +12,8 @@ from oracle import tscnet_oracle as O, weights
 
 import se_b200
 from se_b200 import ops, packing
-from se_b200._lib import (EPI_BIAS, EPI_COMPRESS, EPI_GLU, EPI_QKV_F16, EPI_RESID, EPI_SUBPIXEL, EPI_SWISH, LOAD_CONV, LOAD_CONV_SPLIT,
-                          LOAD_HANKEL, LOAD_ROWS, LOAD_ROWS_LN)
+from se_b200._lib import (EPI_BIAS, EPI_COMPRESS, EPI_GATE, EPI_GLU, EPI_QKV_F16, EPI_RESID, EPI_RESID_SCALE, EPI_SUBPIXEL, EPI_SWISH, LOAD_CONV,
+                          LOAD_CONV_SPLIT, LOAD_HANKEL, LOAD_ROWS, LOAD_ROWS2, LOAD_ROWS_LN)
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -39,6 +39,60 @@ def test_gemm_rows_resid(engine, K, M):
     r2 = r.clone()
     ops.gemm(loader=LOAD_ROWS, epilogue=EPI_RESID, M=M, w=pw, a=[a], lda=K, out=r2, ldo=64, resid=r2, ldr=64, alpha=0.5, engine=engine)
     assert torch.equal(r2, out)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("M,groups", [(300, 1), (128 * 5, 5), (40007, 7)])
+def test_gemm_merge_block(engine, M, groups):
+    """MergeBlock's two contractions (models/tsc_diffusion.py:32-41): [x | cond] -> sigmoid * tanh gate with a per-group bias
+    row (groups of rows_per_group consecutive rows; the last group may be ragged), then (x + W_o g + b_o) / sqrt(2)."""
+    x, c = rnd(M, 64, seed=1), rnd(M, 64, seed=2)
+    wm, wc, bm, bc = rnd(128, 64, seed=3, scale=0.125), rnd(128, 64, seed=4, scale=0.125), rnd(128, seed=5, scale=0.1), rnd(128, seed=6, scale=0.1)
+    rpg = -(-M // groups)
+    d = rnd(groups, 64, seed=7)
+    wcat, bcat = packing.glu_interleave(torch.cat([wm, wc], 1).cpu(), (bm + bc).cpu())
+    pw = packing.pack_weight(wcat, 128, bcat).to(DEV)
+    rowbias = (d.double() @ wcat[:, :64].to(DEV).double().t()).float().contiguous()
+    g = torch.empty(M, 64, device=DEV)
+    ops.gemm(loader=LOAD_ROWS2, epilogue=EPI_GATE, M=M, w=pw, a=[x, c], lda=64, out=g, ldo=64, resid=rowbias, ldr=rpg, engine=engine)
+    grp = torch.arange(M, device=DEV) // rpg
+    y = (x.double() + d.double()[grp]) @ wm.double().t() + bm.double() + c.double() @ wc.double().t() + bc.double()
+    ref = torch.sigmoid(y[:, :64]) * torch.tanh(y[:, 64:])
+    assert rel_max(g, ref) < TOL[engine]
+    # no row bias at all
+    ops.gemm(loader=LOAD_ROWS2, epilogue=EPI_GATE, M=M, w=pw, a=[x, c], lda=64, out=g, ldo=64, engine=engine)
+    y0 = x.double() @ wm.double().t() + bm.double() + c.double() @ wc.double().t() + bc.double()
+    assert rel_max(g, torch.sigmoid(y0[:, :64]) * torch.tanh(y0[:, 64:])) < TOL[engine]
+    # output residual, in place on x
+    wo, bo = rnd(64, 64, seed=8, scale=0.125), rnd(64, seed=9, scale=0.1)
+    po = packing.pack_weight(wo.cpu(), 64, bo.cpu()).to(DEV)
+    gg = ref.float().contiguous()
+    x2 = x.clone()
+    ops.gemm(loader=LOAD_ROWS, epilogue=EPI_RESID_SCALE, M=M, w=po, a=[gg], lda=64, out=x2, ldo=64, resid=x2, ldr=64, alpha=2 ** -0.5, engine=engine)
+    ref2 = (x.double() + gg.double() @ wo.double().t() + bo.double()) / math.sqrt(2.0)
+    assert rel_max(x2, ref2) < TOL[engine]
+
+
+def test_diffusion_embed_matches_oracle():
+    sd = weights.synth_state_dict(2, spec=weights.tsc_diffusion_spec())
+    m = "merge_block"
+    steps = torch.tensor([0.0, 7.0, 3.4, 48.75, 49.0])
+    with torch.no_grad():
+        e = O.diffusion_embedding(steps, sd, f"{m}.diffusion_embedding", 50)
+        d_ref = F.linear(e, sd[f"{m}.diffusion_projection.weight"], sd[f"{m}.diffusion_projection.bias"])
+        e_int = O.diffusion_embedding(torch.tensor([0, 7, 49]), sd, f"{m}.diffusion_embedding", 50)
+        d_int = F.linear(e_int, sd[f"{m}.diffusion_projection.weight"], sd[f"{m}.diffusion_projection.bias"])
+    wm = rnd(128, 64, seed=4, scale=0.125)
+    dv = lambda k: sd[k].to(DEV).contiguous()
+    d = torch.empty(5, 64, device=DEV)
+    rb = torch.empty(5, 128, device=DEV)
+    ops.diffusion_embed(steps.to(DEV), O.diffusion_step_table(50).to(DEV), dv(f"{m}.diffusion_embedding.projection1.weight"),
+                        dv(f"{m}.diffusion_embedding.projection1.bias"), dv(f"{m}.diffusion_embedding.projection2.weight"),
+                        dv(f"{m}.diffusion_embedding.projection2.bias"), dv(f"{m}.diffusion_projection.weight"), dv(f"{m}.diffusion_projection.bias"),
+                        wm, d, rb)
+    assert rel_max(d.cpu(), d_ref) < 1e-5
+    assert rel_max(d.cpu()[[0, 1, 4]], d_int) < 1e-5
+    assert rel_max(rb, d.double() @ wm.double().t()) < 1e-5
 
 
 @pytest.mark.parametrize("engine", ENGINES)

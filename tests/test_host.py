@@ -29,6 +29,27 @@ def test_state_dict_is_the_reference_contract():
     assert sum(isinstance(x, torch.nn.SyncBatchNorm) for x in conv.modules()) == 8
 
 
+def test_diffusion_state_dict_is_the_reference_contract():
+    """tsc_diffusion.TSCNet(num_channel, num_features, noise_schedule) -- same keys, order, shapes"""
+    from se_b200 import tsc_diffusion
+    m = tsc_diffusion.TSCNet(num_channel=64, num_features=201, noise_schedule=[0.1] * 50)
+    sd = weights.synth_state_dict(0, spec=weights.tsc_diffusion_spec())
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    for k, v in m.state_dict().items():
+        assert v.shape == sd[k].shape and v.dtype == sd[k].dtype, k
+    m.load_state_dict(sd, strict=True)
+    tab = m.merge_block.diffusion_embedding.embedding          # non-persistent buffer, as models/DiffuSE.py:42
+    assert tab.shape == (50, 128) and torch.equal(tab, O.diffusion_step_table(50))
+    with pytest.raises(TypeError):
+        tsc_diffusion.TSCNet(64, 201)
+    m.eval()
+    z = torch.zeros(1, 201, 5, dtype=torch.complex64)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(z, z, torch.tensor([3]))
+    with pytest.raises(TypeError):
+        m(z)
+
+
 def test_no_cpu_path():
     m = se_b200.TSCNet().eval()
     with pytest.raises(RuntimeError, match="no CPU path"):

@@ -28,6 +28,53 @@ def test_oracle_matches_golden(golden, name):
     assert y.shape == noisy.shape
 
 
+DIFF_STEPS = [("int1", [7], torch.int64), ("frac1", [3.4], torch.float32), ("intB", [2, 40], torch.int64)]
+
+
+def test_diffusion_oracle_matches_golden(golden):
+    """the tsc_diffusion.TSCNet restatement against outputs of the reference's own module."""
+    g = golden("diffusion_b2_L3000")
+    sd = weights.synth_state_dict(int(g["weight_seed"]), spec=weights.tsc_diffusion_spec())
+    sx = torch.complex(torch.from_numpy(g["spec_x_real"]), torch.from_numpy(g["spec_x_imag"]))
+    sn = torch.complex(torch.from_numpy(g["spec_n_real"]), torch.from_numpy(g["spec_n_imag"]))
+    for tag, vals, dt in DIFF_STEPS:
+        with torch.no_grad():
+            fr, fi = O.tsc_diffusion_forward(sx, sn, torch.tensor(vals, dtype=dt), sd, int(g["max_steps"]))
+        assert rel_max(fr, torch.from_numpy(g[f"final_real_{tag}"])) < 1e-5, tag
+        assert rel_max(fi, torch.from_numpy(g[f"final_imag_{tag}"])) < 1e-5, tag
+    # the step matters (different steps give different outputs) and an integral float step equals the integer one
+    assert rel_max(torch.from_numpy(g["final_real_int1"]), torch.from_numpy(g["final_real_frac1"])) > 1e-3
+    with torch.no_grad():
+        a = O.diffusion_embedding(torch.tensor([7]), sd, "merge_block.diffusion_embedding", 50)
+        b = O.diffusion_embedding(torch.tensor([7.0]), sd, "merge_block.diffusion_embedding", 50)
+    assert torch.equal(a, b)
+
+
+def test_diffusion_spec_state_dict_contract():
+    spec = weights.tsc_diffusion_spec()
+    assert len(spec) == 401 and len({k for k, _, _ in spec}) == 401
+    assert sum(k.startswith("dense_encoder_noisy.") for k, _, _ in spec) == 30
+    assert sum(k.startswith("merge_block.") for k, _, _ in spec) == 12
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="/root/reference not mounted")
+def test_diffusion_oracle_against_live_reference():
+    ref = ref_import.load()
+    spec = weights.tsc_diffusion_spec()
+    model = ref.DiffusionTSCNet(num_channel=64, num_features=201, noise_schedule=list(range(30)))
+    assert list(model.state_dict().keys()) == [k for k, _, _ in spec]
+    sd = weights.synth_state_dict(5, spec=spec)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    est, cond = weights.synth_wave(1, 2400, 3, "speech")
+    with torch.no_grad():
+        sx, sn = O.compressed_stft(est), O.compressed_stft(cond)
+        for step in (torch.tensor([29]), torch.tensor([0.25])):
+            fr, fi = model(sx, sn, step)
+            ofr, ofi = O.tsc_diffusion_forward(sx, sn, step, sd, 30)
+            assert rel_max(ofr, fr) < 1e-5 and rel_max(ofi, fi) < 1e-5
+
+
 def test_golden_inputs_are_reproducible(golden):
     """the committed inputs are exactly what oracle.weights regenerates from the stored seeds"""
     g = golden("speech_b2_L8000")
