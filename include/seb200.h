@@ -194,6 +194,13 @@ int seb200_diffusion_embed(const float* steps, int nsteps, const float* table, i
                            const float* wp, const float* bp, const float* wm,
                            float* d_out, float* rowbias, void* stream);
 
+/* One waveform update of the reverse process, predict_tsc in inference_diffuse.py:255-264:
+ *   out[b, i] = (ca * audio[b, i] + cb * noisy[b, i] + cc * pred[b, i] + cs * noise[b, i]) * (c_div ? 1 / c_div[b] : 1)
+ * audio / pred / noise / out: [B, L] contiguous (noise may be NULL); noisy: rows of stride ld_noisy (a view of the padded
+ * conditioning buffer); c_div: the per-utterance RMS gain removed after the last step (:265), or NULL. */
+int seb200_diffusion_update(const float* audio, const float* noisy, long long ld_noisy, const float* pred, const float* noise,
+                            int B, long long L, float ca, float cb, float cc, float cs, const float* c_div, float* out, void* stream);
+
 /* ---- misc ------------------------------------------------------------------ */
 int seb200_version(void);
 const char* seb200_last_error_string(void);

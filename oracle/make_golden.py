@@ -90,10 +90,34 @@ def diffusion_golden(ref, out_dir):
         for tag, vals, dt in case["steps"]:
             fr, fi = model(sx, sn, torch.tensor(vals, dtype=getattr(torch, dt)))
             out[f"final_real_{tag}"], out[f"final_imag_{tag}"] = fr.numpy(), fi.numpy()
-    np.savez_compressed(os.path.join(out_dir, case["name"] + ".npz"), est=est.numpy(), cond=cond.numpy(),
+    np.savez_compressed(os.path.join(out_dir, case["name"] + ".npz"),
                         spec_x_real=sx.real.numpy(), spec_x_imag=sx.imag.numpy(), spec_n_real=sn.real.numpy(), spec_n_imag=sn.imag.numpy(),
                         weight_seed=np.int64(case["weight_seed"]), wave_seed=np.int64(case["wave_seed"]), max_steps=np.int64(case["max_steps"]), **out)
     print(case["name"], {k: float(np.abs(v).max()) for k, v in out.items()})
+    reverse_golden(ref, out_dir, sd, model)
+
+
+REVERSE_CASE = dict(name="diffusion_reverse_L2950", length=2950, wave_seed=31, noise_seed=123)     # 2950: predict_tsc's wrap-pad branch
+
+
+def reverse_golden(ref, out_dir, sd, model):
+    """the reference's own predict_tsc (inference_diffuse.py:231-267) with its fast-sampling schedule (inference_schedule on
+    config/default.py:27-28,119: 50 training steps, 6 inference steps); torch.manual_seed pins its randn_like draws."""
+    import types
+    case = REVERSE_CASE
+    cfg = types.SimpleNamespace(N_FFT=400, HOP_SAMPLES=100, NOISE_SCHEDULE=np.linspace(1e-4, 0.035, DIFFUSION_CASE["max_steps"]).tolist(),
+                                INFERENCE_NOISE_SCHEDULE=[0.0001, 0.001, 0.01, 0.05, 0.2, 0.35])
+    alpha, beta, alpha_cum, sigmas, T, c1, c2, c3, delta, delta_bar = ref.inference_schedule(cfg, fast_sampling=True)
+    noisy, _ = weights.synth_wave(1, case["length"], case["wave_seed"], "speech")
+    torch.manual_seed(case["noise_seed"])
+    y = ref.predict_tsc(model, types.SimpleNamespace(comp_type="pow"), cfg, noisy[0].numpy(), alpha, beta, alpha_cum, sigmas, T, c1, c2, c3,
+                        delta, delta_bar, device=torch.device("cpu"))
+    f64 = lambda a: np.asarray(a, dtype=np.float64)
+    np.savez_compressed(os.path.join(out_dir, case["name"] + ".npz"), noisy=noisy.numpy(), enhanced=y.astype(np.float32)[None],
+                        T=np.asarray(T, dtype=np.float32), c1=f64(c1), c2=f64(c2), c3=f64(c3), delta_bar=f64(delta_bar), alpha=f64(alpha),
+                        weight_seed=np.int64(DIFFUSION_CASE["weight_seed"]), max_steps=np.int64(DIFFUSION_CASE["max_steps"]),
+                        noise_seed=np.int64(case["noise_seed"]), wave_seed=np.int64(case["wave_seed"]))
+    print(case["name"], "T", T, "enhanced peak", float(np.abs(y).max()))
 
 
 if __name__ == "__main__":

@@ -94,12 +94,17 @@ def load():
         except Exception:  # pragma: no cover
             DiffusionTSCNet = None
         try:
+            from inference_diffuse import predict_tsc, inference_schedule
+        except Exception:  # pragma: no cover
+            predict_tsc = inference_schedule = None
+        try:
             from inference_gan import predict
         except Exception:  # pragma: no cover - depends on what else the script imports
             predict = None
     finally:
         sys.path.remove(REF_ROOT)
-    ns = types.SimpleNamespace(TSCNet=TSCNet, DiffusionTSCNet=DiffusionTSCNet, predict=predict, compressed_stft=compressed_stft,
+    ns = types.SimpleNamespace(TSCNet=TSCNet, DiffusionTSCNet=DiffusionTSCNet, predict_tsc=predict_tsc,
+                               inference_schedule=inference_schedule, predict=predict, compressed_stft=compressed_stft,
                                uncompressed_istft=uncompressed_istft, kaiming_init=kaiming_init,
                                batch_stft=batch_stft, normalize_batch=normalize_batch,
                                generator=gen_mod, conformer=conf_mod,

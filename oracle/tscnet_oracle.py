@@ -347,6 +347,33 @@ def tsc_diffusion_forward(spec: torch.Tensor, noisy_spec: torch.Tensor, step: to
     return fr, fi
 
 
+def predict_tsc(wave: torch.Tensor, sd: SD, max_steps: int, T, c1, c2, c3, delta_bar, noises, chunk: int = 0,
+                trace: Optional[list] = None) -> torch.Tensor:
+    """predict_tsc  inference_diffuse.py:231-267, batched: (B, L) noisy -> (B, L) enhanced.  ``noises[n]`` is the (B, Lp)
+    Gaussian draw the reference takes with torch.randn_like at step n > 0 (passed in so the run is reproducible)."""
+    x = wave.to(torch.float32)
+    B, L = x.shape
+    c = torch.sqrt(L / torch.sum(x ** 2.0, dim=-1, keepdim=True))
+    x = x * c
+    pad = int(math.ceil(L / 100)) * 100 - L
+    noisy_audio = torch.cat([x, x[:, :pad]], dim=-1)
+    audio = noisy_audio
+    orig = compressed_stft(noisy_audio)
+    for n in range(len(c1) - 1, -1, -1):
+        spec = compressed_stft(audio)
+        fr, fi = tsc_diffusion_forward(spec, orig, torch.tensor([T[n]]), sd, max_steps, chunk)
+        pred = uncompressed_istft(torch.complex(fr.permute(0, 1, 3, 2), fi.permute(0, 1, 3, 2)).squeeze(1))
+        if n > 0:
+            audio = c1[n] * audio + c2[n] * noisy_audio - c3[n] * pred
+            audio = audio + delta_bar[n] ** 0.5 * noises[n]
+        else:
+            audio = c1[n] * audio - c3[n] * pred
+            audio = (1 - 0.2) * audio + 0.2 * noisy_audio
+        if trace is not None:
+            trace.append(audio if n > 0 else audio / c)
+    return (audio / c)[:, :L]
+
+
 # ----------------------------------------------------------------------------
 # wave -> wave  (inference_gan.py:75-100, batched)
 # ----------------------------------------------------------------------------

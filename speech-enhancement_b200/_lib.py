@@ -71,6 +71,7 @@ _SIGS = {
     "seb200_dwconv_bn_swish": [_fp, C.POINTER(SebSeq), _fp, _fp, _fp, _fp, _fp],
     "seb200_dwconv_pw2": [_fp, C.POINTER(SebSeq), _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp],
     "seb200_layernorm_residual": [_fp, C.c_longlong, _fp, _fp, _fp, _fp, _fp],
+    "seb200_diffusion_update": [_fp, _fp, C.c_longlong, _fp, _fp, C.c_int, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float, _fp, _fp, _fp],
     "seb200_diffusion_embed": [_fp, C.c_int, _fp, C.c_int, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp],
 }
 EXPORTS = sorted(list(_SIGS) + ["seb200_inorm_workspace_bytes", "seb200_version", "seb200_last_error_string",

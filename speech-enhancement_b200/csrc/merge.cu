@@ -55,9 +55,34 @@ __global__ void __launch_bounds__(512) diffusion_embed_kernel(const float* __res
   dense_rows<false>(wm, nullptr, d, rowbias + s * 128, 128, 64, warp, lane, 16);
 }
 
+// one reverse-diffusion update of the waveform (inference_diffuse.py:255-264):
+//   out[b, i] = (ca * audio[b, i] + cb * noisy[b, i] + cc * pred[b, i] + cs * noise[b, i]) * (c_div ? 1 / c_div[b] : 1)
+__global__ void __launch_bounds__(256) diffusion_update_kernel(const float* __restrict__ audio, const float* __restrict__ noisy, long long ldn,
+                                                               const float* __restrict__ pred, const float* __restrict__ noise, long long L,
+                                                               float ca, float cb, float cc, float cs, const float* __restrict__ c_div,
+                                                               float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const float sc = c_div ? 1.0f / c_div[b] : 1.0f;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < L; i += (long long)gridDim.x * 256) {
+    const long long o = (long long)b * L + i;
+    float v = ca * audio[o] + cb * noisy[(long long)b * ldn + i] + cc * pred[o];
+    if (noise) v = fmaf(cs, noise[o], v);
+    out[o] = v * sc;
+  }
+}
+
 }  // namespace seb
 
 using namespace seb;
+
+extern "C" int seb200_diffusion_update(const float* audio, const float* noisy, long long ld_noisy, const float* pred, const float* noise,
+                                       int B, long long L, float ca, float cb, float cc, float cs, const float* c_div, float* out, void* stream) {
+  SEB_REQUIRE(audio && noisy && pred && out && B > 0 && B < 65536 && L > 0 && ld_noisy >= L, SEB_EINVAL, "diffusion_update: bad arguments");
+  dim3 grid((unsigned)((L + 255) / 256 < 1024 ? (L + 255) / 256 : 1024), B);
+  diffusion_update_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(audio, noisy, ld_noisy, pred, noise, L, ca, cb, cc, cs, c_div, out);
+  SEB_CHECK_LAUNCH("diffusion_update_kernel");
+  return 0;
+}
 
 extern "C" int seb200_diffusion_embed(const float* steps, int nsteps, const float* table, int max_steps,
                                       const float* w1, const float* b1, const float* w2, const float* b2,

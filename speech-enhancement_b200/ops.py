@@ -149,6 +149,22 @@ def diffusion_embed(steps: torch.Tensor, table, w1, b1, w2, b2, wp, bp, wm, d_ou
     return d_out, rowbias
 
 
+def diffusion_update(audio, noisy, pred, noise, ca: float, cb: float, cc: float, cs: float, c_div=None, out=None):
+    """out = (ca * audio + cb * noisy + cc * pred + cs * noise) [/ c_div per utterance]; noisy may be a row-strided view."""
+    _f32c(audio, pred, noise, c_div)
+    require_cuda(noisy)
+    B, L = audio.shape
+    if noisy.dtype != torch.float32 or noisy.shape != audio.shape or noisy.stride(1) != 1 or pred.shape != audio.shape:
+        raise RuntimeError("diffusion_update: noisy / pred must be float32 (B, L) like audio (noisy may have a row stride)")
+    if out is None:
+        out = torch.empty_like(audio)
+    tok = _pb("diffusion_update", 0.0, 20.0 * audio.numel()) if _PROF is not None else None
+    check(_lib.load().seb200_diffusion_update(ptr(audio), ptr(noisy), noisy.stride(0), ptr(pred), ptr(noise), B, L, ca, cb, cc, cs, ptr(c_div),
+                                              ptr(out), stream_ptr()), "seb200_diffusion_update")
+    _pe(tok)
+    return out
+
+
 def ffn_fused(x, out, ln, w1: PackedWeight, w2: PackedWeight, alpha: float = 0.5, post=None, resid2=None):
     """y = x + alpha * FF(LN(x)); with ``post=(gamma, beta)``: out = LN_post(y) + resid2.  One tcgen05 kernel."""
     _f32c(x, out, resid2)

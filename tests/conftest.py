@@ -30,6 +30,16 @@ def load_golden(name):
     return {k: z[k] for k in z.files}
 
 
+def reverse_noises(g):
+    """the Gaussian draws the reference's predict_tsc took for tests/golden/diffusion_reverse_*.npz: torch.manual_seed(noise_seed),
+    then one randn_like(audio) of shape (1, Lp) per step n = N-1 .. 1 (inference_diffuse.py:259)."""
+    L = g["noisy"].shape[-1]
+    Lp = -(-L // 100) * 100
+    gen = torch.Generator().manual_seed(int(g["noise_seed"]))
+    n_steps = len(g["c1"])
+    return {n: torch.randn(1, Lp, generator=gen) for n in range(n_steps - 1, 0, -1)}
+
+
 @pytest.fixture(scope="session")
 def golden():
     return load_golden

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import rel_max, rel_l2
+from conftest import rel_max, rel_l2, reverse_noises
 from oracle import tscnet_oracle as O, weights
 
 import se_b200
@@ -96,6 +96,68 @@ def test_diffusion_module_matches_reference_golden(golden, engine):
     fr2, _ = model(sx.to(DEV), sn.to(DEV), torch.tensor([7], device=DEV))
     fr3, _ = model(sx.to(DEV), sn.to(DEV), [7])
     assert torch.equal(fr2, fr3)
+
+
+def _diffusion_model(g, engine):
+    from se_b200 import tsc_diffusion
+    sd = weights.synth_state_dict(int(g["weight_seed"]), spec=weights.tsc_diffusion_spec())
+    model = tsc_diffusion.TSCNet(64, 201, noise_schedule=[0.0] * int(g["max_steps"]))
+    model.load_state_dict(sd, strict=True)
+    model = model.to(DEV).eval()
+    model.engine = engine
+    return model, sd
+
+
+def test_predict_tsc_matches_reference_golden(golden):
+    """the reverse process through the drop-in predict_tsc (reference argument list) against the reference's own output: six
+    network evaluations chained through iSTFT -> update -> STFT with the reference's Gaussian draws injected.  With random
+    weights the chain amplifies a per-evaluation perturbation ~100x (measured with the oracle: 3e-4 of peak injected per step
+    -> 3e-2 at the end), so the end-to-end comparison runs on the fp32 configuration of the kernels (fp32 GEMM loop, fp32
+    attention, fp32 DFT: ~6e-6 per evaluation); the default tensor-core configuration is checked step by step below."""
+    import types
+    from se_b200 import diffusion, dsp
+    g = golden("diffusion_reverse_L2950")
+    model, _ = _diffusion_model(g, "simt")
+    model.attention_variant = 1
+    noises = reverse_noises(g)
+    cfg = types.SimpleNamespace(N_FFT=400, HOP_SAMPLES=100)
+    saved = dsp.DFT_ENGINE
+    dsp.DFT_ENGINE = "simt"
+    try:
+        y = diffusion.predict_tsc(model, types.SimpleNamespace(comp_type="pow"), cfg, g["noisy"][0], g["alpha"], None, None, None, g["T"], g["c1"],
+                                  g["c2"], g["c3"], None, g["delta_bar"], device=torch.device(DEV), noise_fn=lambda n, shape: noises[n].to(DEV))
+    finally:
+        dsp.DFT_ENGINE = saved
+    ref = g["enhanced"][0]
+    assert y.shape == ref.shape and y.dtype == np.float32
+    err = np.abs(y - ref).max() / np.abs(ref).max()
+    assert err < WAVE_TOL, f"waveform max-abs/peak {err:.3e}"
+
+
+@pytest.mark.parametrize("engine", ["simt", "tcgen05"])
+def test_reverse_steps_against_oracle(golden, engine):
+    """every reverse step on its own (teacher-forced with the oracle's waveform before the step): STFT -> diffusion TSCNet ->
+    iSTFT -> update within the path tolerance of 1e-3 of peak; then the batched chain with torch's own noise runs and is finite"""
+    from se_b200 import diffusion
+    g = golden("diffusion_reverse_L2950")
+    model, sd = _diffusion_model(g, engine)
+    noises = reverse_noises(g)
+    trace = []
+    with torch.no_grad():
+        O.predict_tsc(torch.from_numpy(g["noisy"]), sd, int(g["max_steps"]), g["T"], g["c1"], g["c2"], g["c3"], g["delta_bar"], noises, trace=trace)
+    enh = diffusion.DiffusionEnhancerB200(model)
+    noisy_audio, cond_in3, c = enh.prepare(torch.from_numpy(g["noisy"]).to(DEV))
+    nsteps = len(g["c1"])
+    audio = noisy_audio.contiguous()
+    for i, n in enumerate(range(nsteps - 1, -1, -1)):
+        nxt = enh.step(audio, noisy_audio, cond_in3, n, g["T"], g["c1"], g["c2"], g["c3"], g["delta_bar"],
+                       noises[n].to(DEV) if n > 0 else None, c)
+        err = rel_max(nxt.cpu(), trace[i])
+        assert err < WAVE_TOL, f"step {n}: {err:.3e}"
+        audio = trace[i].to(DEV)                      # teacher forcing: the next step starts from the oracle's state
+    wav = torch.from_numpy(np.concatenate([g["noisy"], g["noisy"][:, ::-1].copy()])).to(DEV)
+    yb = enh.reverse(wav, g["T"], g["c1"], g["c2"], g["c3"], g["delta_bar"])
+    assert yb.shape == wav.shape and bool(torch.isfinite(yb).all())
 
 
 @pytest.mark.parametrize("engine", ["simt", "tcgen05"])

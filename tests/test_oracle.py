@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import rel_max
+from conftest import rel_max, reverse_noises
 from oracle import ref_import, tscnet_oracle as O, weights
 
 CASES = ["speech_b2_L8000", "noise_b1_L4050_wrap"]
@@ -48,6 +48,17 @@ def test_diffusion_oracle_matches_golden(golden):
         a = O.diffusion_embedding(torch.tensor([7]), sd, "merge_block.diffusion_embedding", 50)
         b = O.diffusion_embedding(torch.tensor([7.0]), sd, "merge_block.diffusion_embedding", 50)
     assert torch.equal(a, b)
+
+
+def test_predict_tsc_oracle_matches_golden(golden):
+    """the reverse process (inference_diffuse.predict_tsc, 6-step fast schedule, wrap-pad branch) restated vs the reference's output"""
+    g = golden("diffusion_reverse_L2950")
+    sd = weights.synth_state_dict(int(g["weight_seed"]), spec=weights.tsc_diffusion_spec())
+    with torch.no_grad():
+        y = O.predict_tsc(torch.from_numpy(g["noisy"]), sd, int(g["max_steps"]), g["T"], g["c1"], g["c2"], g["c3"], g["delta_bar"],
+                          reverse_noises(g))
+    assert y.shape == g["noisy"].shape
+    assert rel_max(y, torch.from_numpy(g["enhanced"])) < 5e-5
 
 
 def test_diffusion_spec_state_dict_contract():
