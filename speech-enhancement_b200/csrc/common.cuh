@@ -60,13 +60,30 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// fp32 -> (hi, lo) bf16 pair with hi + lo ~= x to ~2^-17 relative (round-to-nearest both)
+// fp32 -> (hi, lo) bf16 pair with hi + lo ~= x to ~2^-17 relative (round-to-nearest both).  The residual x - hi is exact in
+// fp32 either way; it is formed with one packed FFMA2 (hi * -1 + x) for the two values instead of two FADDs.
 __device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
   __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
-  float2 hf = __bfloat1622float2(h);
-  __nv_bfloat162 l = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
   hi = *reinterpret_cast<uint32_t*>(&h);
+  const float2 hf = make_float2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u));
+  const float2 r = __ffma2_rn(hf, make_float2(-1.0f, -1.0f), make_float2(x0, x1));
+  __nv_bfloat162 l = __floats2bfloat162_rn(r.x, r.y);
   lo = *reinterpret_cast<uint32_t*>(&l);
+}
+
+// LayerNorm of four values on packed fp32x2: ((v - mean) * rstd) * gamma + beta in the reference's operation order
+__device__ __forceinline__ void ln_apply4(const float4 v, float mean, float rstd, const float4 g, const float4 b, float2& y01, float2& y23) {
+  const float2 nm = make_float2(-mean, -mean), rs = make_float2(rstd, rstd);
+  y01 = __ffma2_rn(__fmul2_rn(__fadd2_rn(make_float2(v.x, v.y), nm), rs), make_float2(g.x, g.y), make_float2(b.x, b.y));
+  y23 = __ffma2_rn(__fmul2_rn(__fadd2_rn(make_float2(v.z, v.w), nm), rs), make_float2(g.z, g.w), make_float2(b.z, b.w));
+}
+
+// shifted one-pass statistics of four more values: s += (v - x0), q += (v - x0)^2, both as float2 partial sums
+__device__ __forceinline__ void stats_acc4(const float4 v, float2 nx0, float2& s, float2& q) {
+  const float2 d0 = __fadd2_rn(make_float2(v.x, v.y), nx0), d1 = __fadd2_rn(make_float2(v.z, v.w), nx0);
+  s = __fadd2_rn(s, __fadd2_rn(d0, d1));
+  q = __ffma2_rn(d0, d0, q);
+  q = __ffma2_rn(d1, d1, q);
 }
 
 // fp32 -> (hi, mid, lo) bf16 triple: hi + mid + lo == x to ~2^-24 relative

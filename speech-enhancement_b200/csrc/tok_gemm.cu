@@ -94,17 +94,13 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs 
       ptx::mbar_wait(&x_full[slot], (uint32_t)(it / NSLOT) & 1u);
       float mean = 0.f, rstd = 1.f;
       if (LK == SEB_LOAD_ROWS_LN) {     // shifted one-pass statistics, four partial sums (short dependency chains)
-        float ps[4] = {0.f, 0.f, 0.f, 0.f}, pq[4] = {0.f, 0.f, 0.f, 0.f};
+        float2 ps[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, pq[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
         const float x0 = reinterpret_cast<const float4*>(xr + ((0 ^ sw) << 4))->x;
+        const float2 nx0 = make_float2(-x0, -x0);
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          const float4 v = *reinterpret_cast<const float4*>(xr + ((c ^ sw) << 4));
-          const float d0 = v.x - x0, d1 = v.y - x0, d2 = v.z - x0, d3 = v.w - x0;
-          ps[c & 3] += (d0 + d1) + (d2 + d3);
-          pq[c & 3] += fmaf(d0, d0, d1 * d1) + fmaf(d2, d2, d3 * d3);
-        }
-        const float md = ((ps[0] + ps[1]) + (ps[2] + ps[3])) * (1.0f / 64.0f);
-        const float var = fmaxf(((pq[0] + pq[1]) + (pq[2] + pq[3])) * (1.0f / 64.0f) - md * md, 0.f);
+        for (int c = 0; c < NCH; ++c) stats_acc4(*reinterpret_cast<const float4*>(xr + ((c ^ sw) << 4)), nx0, ps[c & 1], pq[c & 1]);
+        const float md = ((ps[0].x + ps[0].y) + (ps[1].x + ps[1].y)) * (1.0f / 64.0f);
+        const float var = fmaxf(((pq[0].x + pq[0].y) + (pq[1].x + pq[1].y)) * (1.0f / 64.0f) - md * md, 0.f);
         rstd = 1.0f / sqrtf(var + 1e-5f);
         mean = x0 + md;
       }
@@ -117,15 +113,12 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs 
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int c = c16 * 4 + j;
-          float4 v = *reinterpret_cast<const float4*>(xr + ((c ^ sw) << 4));
-          if (LK == SEB_LOAD_ROWS_LN) {
-            const float4 gg = *reinterpret_cast<const float4*>(sG + c * 4);
-            const float4 bb = *reinterpret_cast<const float4*>(sBt + c * 4);
-            v.x = fmaf((v.x - mean) * rstd, gg.x, bb.x); v.y = fmaf((v.y - mean) * rstd, gg.y, bb.y);
-            v.z = fmaf((v.z - mean) * rstd, gg.z, bb.z); v.w = fmaf((v.w - mean) * rstd, gg.w, bb.w);
-          }
-          split_bf16x2(v.x, v.y, hi[2 * j], lo[2 * j]);
-          split_bf16x2(v.z, v.w, hi[2 * j + 1], lo[2 * j + 1]);
+          const float4 v = *reinterpret_cast<const float4*>(xr + ((c ^ sw) << 4));
+          float2 y01 = make_float2(v.x, v.y), y23 = make_float2(v.z, v.w);
+          if (LK == SEB_LOAD_ROWS_LN)
+            ln_apply4(v, mean, rstd, *reinterpret_cast<const float4*>(sG + c * 4), *reinterpret_cast<const float4*>(sBt + c * 4), y01, y23);
+          split_bf16x2(y01.x, y01.y, hi[2 * j], lo[2 * j]);
+          split_bf16x2(y23.x, y23.y, hi[2 * j + 1], lo[2 * j + 1]);
         }
         ptx::tg_tmem_st8(xa + (uint32_t)(c16 * 8), hi);
         ptx::tg_tmem_st8(xa + (uint32_t)(K / 2 + c16 * 8), lo);
