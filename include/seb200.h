@@ -201,6 +201,19 @@ int seb200_diffusion_embed(const float* steps, int nsteps, const float* table, i
 int seb200_diffusion_update(const float* audio, const float* noisy, long long ld_noisy, const float* pred, const float* noise,
                             int B, long long L, float ca, float cb, float cc, float cs, const float* c_div, float* out, void* stream);
 
+/* ---- host-side helpers (no launches) ------------------------------------------ */
+/* Sizes of the two weight images of one logical W [N, K] (see SebGemm.w_tc / w_simt): bytes of the tcgen05 image, floats of the
+ * fp32 image, the padded K, the number of n-tiles and the padded N of the fp32 image.  Any output pointer may be NULL. */
+int seb200_packed_weight_sizes(int N, int K, int tc_ntile, int planes, long long* tc_bytes, long long* simt_floats,
+                               int* k_padded, int* tc_ntiles, int* simt_npad);
+/* Pack W [N, K] fp32 (HOST memory, row-major: nn.Linear / reshaped conv weight) into the tcgen05 image (bf16 hi | lo [| mid] planes,
+ * 128-byte-swizzled K-major blocks per (n-tile, 64-wide k-chunk)) and / or the K-major fp32 image; both in HOST memory, sized by
+ * seb200_packed_weight_sizes; the caller copies them to the device.  planes: 2 = network GEMMs, 3 = DFT / iDFT bases. */
+int seb200_pack_weights(const float* w, int N, int K, int tc_ntile, int planes, void* w_tc, float* w_simt);
+/* Bytes of activation workspace one forward over B utterances x T frames x F bins needs, as the shipped host allocates it
+ * (kind 0: generator, models/generator.py; kind 1: diffusion variant, models/tsc_diffusion.py); -1 on bad arguments. */
+long long seb200_workspace_bytes(int kind, int B, int T, int F);
+
 /* ---- misc ------------------------------------------------------------------ */
 int seb200_version(void);
 const char* seb200_last_error_string(void);

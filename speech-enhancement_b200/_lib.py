@@ -71,10 +71,13 @@ _SIGS = {
     "seb200_dwconv_bn_swish": [_fp, C.POINTER(SebSeq), _fp, _fp, _fp, _fp, _fp],
     "seb200_dwconv_pw2": [_fp, C.POINTER(SebSeq), _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp],
     "seb200_layernorm_residual": [_fp, C.c_longlong, _fp, _fp, _fp, _fp, _fp],
+    "seb200_packed_weight_sizes": [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_int),
+                                   C.POINTER(C.c_int), C.POINTER(C.c_int)],
+    "seb200_pack_weights": [_fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp],
     "seb200_diffusion_update": [_fp, _fp, C.c_longlong, _fp, _fp, C.c_int, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float, _fp, _fp, _fp],
     "seb200_diffusion_embed": [_fp, C.c_int, _fp, C.c_int, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp],
 }
-EXPORTS = sorted(list(_SIGS) + ["seb200_inorm_workspace_bytes", "seb200_version", "seb200_last_error_string",
+EXPORTS = sorted(list(_SIGS) + ["seb200_inorm_workspace_bytes", "seb200_workspace_bytes", "seb200_version", "seb200_last_error_string",
                                 "seb200_launch_count"])
 
 _lock = threading.Lock()
@@ -103,6 +106,8 @@ def load(build_if_missing: bool = True):
             fn.restype = C.c_int
         lib.seb200_inorm_workspace_bytes.argtypes = [C.c_int, C.c_longlong, C.c_int]
         lib.seb200_inorm_workspace_bytes.restype = C.c_longlong
+        lib.seb200_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
+        lib.seb200_workspace_bytes.restype = C.c_longlong
         lib.seb200_version.restype = C.c_int
         lib.seb200_last_error_string.restype = C.c_char_p
         lib.seb200_launch_count.restype = C.c_longlong

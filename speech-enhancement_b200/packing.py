@@ -68,7 +68,26 @@ def split_bf16_3(w: torch.Tensor):
 
 
 def pack_weight(w: torch.Tensor, tc_ntile: int, bias: Optional[torch.Tensor] = None, planes: int = 2) -> PackedWeight:
-    """w: [N, K] fp32 (CPU).  planes = 3 packs hi|mid|lo (six-product mode of the engine, used by the DFT bases)."""
+    """w: [N, K] fp32 (CPU).  planes = 3 packs hi|mid|lo (six-product mode of the engine, used by the DFT bases).
+    The images come from the library's own host-side packer (``seb200_pack_weights``, csrc/pack.cu) -- the same entry point a
+    non-Python caller of the C ABI uses; ``pack_weight_torch`` is the independent restatement the tests compare it with."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    w = w.detach().to(torch.float32).cpu().contiguous()
+    N, K = w.shape
+    tcb, sf, kp, ntiles, npad = C.c_longlong(), C.c_longlong(), C.c_int(), C.c_int(), C.c_int()
+    _lib.check(lib.seb200_packed_weight_sizes(N, K, tc_ntile, planes, C.byref(tcb), C.byref(sf), C.byref(kp), C.byref(ntiles), C.byref(npad)),
+               "seb200_packed_weight_sizes")
+    w_tc = torch.empty(tcb.value, dtype=torch.uint8)
+    w_simt = torch.empty(kp.value, npad.value, dtype=torch.float32)
+    _lib.check(lib.seb200_pack_weights(w.data_ptr(), N, K, tc_ntile, planes, w_tc.data_ptr(), w_simt.data_ptr()), "seb200_pack_weights")
+    b = None if bias is None else bias.detach().to(torch.float32).cpu().contiguous()
+    return PackedWeight(N, kp.value, tc_ntile, ntiles.value, npad.value, w_tc, w_simt, b, planes)
+
+
+def pack_weight_torch(w: torch.Tensor, tc_ntile: int, bias: Optional[torch.Tensor] = None, planes: int = 2) -> PackedWeight:
+    """the same images built with torch ops (layout restated independently of csrc/pack.cu; used by tests/test_host.py)"""
     w = w.detach().to(torch.float32).cpu().contiguous()
     N, K = w.shape
     kp = int(math.ceil(K / BK)) * BK

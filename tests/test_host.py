@@ -150,6 +150,34 @@ def test_abi_exports_every_declared_symbol():
     assert lib.seb200_version() == 1
 
 
+@pytest.mark.parametrize("N,K,ntile,planes", [(64, 64, 64, 2), (192, 64, 192, 2), (64, 1536, 64, 2), (402, 400, 208, 3), (128, 128, 128, 2), (70, 100, 64, 2)])
+def test_c_abi_weight_packer_matches_torch_restatement(N, K, ntile, planes):
+    """seb200_pack_weights (host-side C, what a non-Python caller uses) == the torch restatement of the layout, bit for bit"""
+    w = torch.randn(N, K, generator=torch.Generator().manual_seed(N + K)) * (K ** -0.5)
+    w[0, 0], w[-1, -1] = 1e-30, 3.0e38                 # a denormal-range value and a near-max value go through the rounding too
+    a, b = packing.pack_weight(w, ntile, None, planes), packing.pack_weight_torch(w, ntile, None, planes)
+    assert (a.N, a.K, a.tc_ntile, a.tc_ntiles, a.simt_npad, a.planes) == (b.N, b.K, b.tc_ntile, b.tc_ntiles, b.simt_npad, b.planes)
+    assert torch.equal(a.w_tc, b.w_tc) and torch.equal(a.w_simt, b.w_simt)
+
+
+def test_workspace_bytes_matches_the_host_allocation():
+    """seb200_workspace_bytes(kind, B, T, F) == what TSCNet.workspace really allocates"""
+    from se_b200 import tsc_diffusion
+    lib = se_b200._lib.load()
+    B, T, F = 2, 7, 201
+
+    def total(ws):
+        n = 0
+        for v in ws.values():
+            for t in (v if isinstance(v, list) else [v]):
+                n += t.numel() * t.element_size()
+        return n
+    assert lib.seb200_workspace_bytes(0, B, T, F) == total(se_b200.TSCNet().workspace(B, T, "cpu"))
+    assert lib.seb200_workspace_bytes(1, B, T, F) == total(tsc_diffusion.TSCNet(64, 201, [0.1] * 4).workspace(B, T, "cpu"))
+    assert lib.seb200_workspace_bytes(0, 64, 641, 201) < 45e9            # configs[1]: ~ 37 GB of the 180 GB
+    assert lib.seb200_workspace_bytes(0, 1, 5, 200) == -1 and b"workspace_bytes" in lib.seb200_last_error_string()
+
+
 def test_abi_rejects_bad_arguments_without_a_gpu():
     lib = se_b200._lib.load()
     assert lib.seb200_gemm(None, 0, None) == -1
