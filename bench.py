@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--engine", default=None, help="tcgen05 (default) | simt")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graphs", action="store_true", help="replay a captured CUDA graph per step (small-batch latency mode)")
-    ap.add_argument("--cpu-sample-clips", type=int, default=2)
+    ap.add_argument("--cpu-sample-clips", type=int, default=6, help="clips of the batch the CPU oracle leg times (6 x 4 s ~ 11 s of CPU work on 16 cores)")
     ap.add_argument("--total-clips", type=int, default=0,
                     help="BASELINE configs[3]: enhance this many clips in total (4096), sharded across the ranks in micro-batches of "
                          "--batch, host buffers in and out; strong scaling.  One step = the whole job.")

@@ -83,6 +83,9 @@ __device__ __forceinline__ float4 lds4(const uint8_t* p) { return *reinterpret_c
 // Packed fp32x2 arithmetic (FADD2 / FMUL2 / FFMA2, sm_100): the bias add, the exponent scaling, 1 + e, v * sigmoid and the
 // hi/lo residual each cost one instruction per PAIR of hidden elements -- 6.5 instead of ~9.5 instructions per element in the
 // loop that bounds the kernel (issue slots); the two MUFU ops per element stay scalar.
+#ifndef SEB_FFN_EXP
+#define SEB_FFN_EXP 0
+#endif
 #ifndef SEB_FFN_PACKED
 #define SEB_FFN_PACKED 1
 #endif
@@ -95,7 +98,11 @@ __device__ __forceinline__ void swish_split_pair(float a0, float a1, float2 b, u
   const float2 d = __fadd2_rn(make_float2(e0, e1), make_float2(1.0f, 1.0f));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d.x));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d.y));
+#if SEB_FFN_EXP == 1          // timing experiment only: no MUFU work in the mid epilogue
+  const float2 s = v;
+#else
   const float2 s = __fmul2_rn(v, make_float2(r0, r1));
+#endif
   __nv_bfloat162 h = __floats2bfloat162_rn(s.x, s.y);
   hi = *reinterpret_cast<uint32_t*>(&h);
   const float2 hf = make_float2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u));
@@ -274,7 +281,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn_fused_kernel(const FfnArgs 
       const uint32_t t_acc = lane_base + F3_ACC2 + (uint32_t)(ab * 64);
       float y0s = 0.f, sum = 0.f, sq = 0.f;
 #pragma unroll
-      for (int c16 = 0; c16 < 4; ++c16) {
+      for (int c16 = 0; c16 < (SEB_FFN_EXP == 4 ? 0 : 4); ++c16) {
         uint32_t r[16];
         ptx::tmem_ld16_nowait(t_acc + (uint32_t)(c16 * 16), r);
         ptx::tmem_ld_wait();
@@ -308,7 +315,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn_fused_kernel(const FfnArgs 
       // rows are issued before its stores: `out` may alias `resid2`, so the compiler cannot hoist them itself and the
       // residual reads would otherwise serialise into sixteen DRAM round trips per tile.
 #pragma unroll 1
-      for (int i0 = 0; i0 < 16; i0 += 4) {
+      for (int i0 = 0; i0 < (SEB_FFN_EXP == 2 ? 0 : 16); i0 += 4) {
         float4 yv[4], r2[4];
         float2 st[4];
 #pragma unroll

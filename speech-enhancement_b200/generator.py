@@ -153,6 +153,7 @@ class TSCNet(nn.Module):
         self.attention_tc_min_len = 512
         self.fuse_dwconv_pw2 = False           # opt-in: depthwise conv + pointwise 128 -> 64 in one kernel (seb200_dwconv_pw2); measured
                                                # 21.5 ms vs 16.2 ms for the two-kernel path at configs[1], so off by default
+        self.overlap_decoders = False          # opt-in: complex decoder on a side stream next to the mask decoder (second buffer set; measured in DESIGN.md)
         self._packed: Optional[Dict[str, object]] = None
         self._packed_key = None
         self._ws: Dict[tuple, Dict[str, torch.Tensor]] = {}
@@ -272,6 +273,24 @@ class TSCNet(nn.Module):
     # -----------------------------------------------------------------------------------------
     # building blocks
     # -----------------------------------------------------------------------------------------
+    def _second_decoder_buffers(self, ws, B, T, device):
+        if "dec2" not in ws:
+            Fh = (self.num_features - 1) // 2 + 1
+            Ph = B * T * Fh
+            f32 = dict(device=device, dtype=torch.float32)
+            ws["dec2"] = {"dec": [torch.empty(Ph, 64, **f32) for _ in range(4)], "dec_raw": torch.empty(Ph, 64, **f32),
+                          "sp": torch.empty(B * T * 2 * Fh, 64, **f32), "stats": torch.empty(B, 64, 2, **f32),
+                          "in_ws": ops.inorm_workspace(B, T * 2 * Fh, 64, device)}
+        return ws["dec2"]
+
+    def _side_stream(self, device):
+        key = str(device)
+        if not hasattr(self, "_side_streams"):
+            self._side_streams = {}
+        if key not in self._side_streams:
+            self._side_streams[key] = torch.cuda.Stream(device=device)
+        return self._side_streams[key]
+
     def _inorm_prelu(self, ws, raw, B, pix_per_b, gamma, beta, slope, out):
         ops.inorm_stats(raw, B, pix_per_b, 64, ws["stats"], ws["in_ws"])
         ops.inorm_prelu(raw, B, pix_per_b, ws["stats"], gamma, beta, slope, out)
@@ -397,27 +416,42 @@ class TSCNet(nn.Module):
         eng = self.engine
         tc = eng == "tcgen05"
         conv_loader = LOAD_CONV_SPLIT if tc else LOAD_CONV
-        rawh = ws["dec_raw"]
 
-        # ---- MaskDecoder (generator.py:106-112)
-        m = "mask_decoder"
-        dec, sp = [self._conv_in(t) for t in ws["dec"]], ws["sp"]
+        m, c = "mask_decoder", "complex_decoder"
         x0 = ops.split_planes(x, self._as_split(ws["xs"])) if tc else x      # both decoders read the TSCB output as a conv input
-        d4 = self._dense(P, f"{m}.dense_block", ws, x0, dec, rawh, B, T, Fh)
-        ops.gemm(loader=conv_loader, epilogue=EPI_SUBPIXEL, M=M, w=P[f"{m}.sub_pixel"], a=[d4], out=sp, ldo=64, engine=eng, label="subpixel",
-                 conv=dict(B=B, T=T, Fin=Fh, Fout=Fh, taps_t=1, dil=1, stride_f=1, nslots=1))
         b1, g_in, b_in, s1, wf, bf = P[f"{m}.scalars"]
-        ops.mask_conv(sp, B * T, 2 * Fh, P[f"{m}.conv_1.w"], b1, ws["mask_raw"])
-        ops.inorm_stats(ws["mask_raw"], B, T * F, 1, ws["stats1"], ws["in_ws"])
 
-        # ---- ComplexDecoder (generator.py:124-129)
-        c = "complex_decoder"
-        d4 = self._dense(P, f"{c}.dense_block", ws, x0, dec, rawh, B, T, Fh)
-        ops.gemm(loader=conv_loader, epilogue=EPI_SUBPIXEL, M=M, w=P[f"{c}.sub_pixel"], a=[d4], out=sp, ldo=64, engine=eng, label="subpixel",
-                 conv=dict(B=B, T=T, Fin=Fh, Fout=Fh, taps_t=1, dil=1, stride_f=1, nslots=1))
-        ops.inorm_stats(sp, B, T * 2 * Fh, 64, ws["stats"], ws["in_ws"])
-        ops.complex_conv(sp, B, T, 2 * Fh, ws["stats"], P[f"{c}.norm.weight"], P[f"{c}.norm.bias"], P[f"{c}.prelu.weight"],
-                         P[f"{c}.conv.w"], P[f"{c}.conv.bias"], ws["cplx"])
+        def mask_branch(w):        # MaskDecoder up to the InstanceNorm statistics (generator.py:106-109)
+            dec, sp = [self._conv_in(t) for t in w["dec"]], w["sp"]
+            d4 = self._dense(P, f"{m}.dense_block", w, x0, dec, w["dec_raw"], B, T, Fh)
+            ops.gemm(loader=conv_loader, epilogue=EPI_SUBPIXEL, M=M, w=P[f"{m}.sub_pixel"], a=[d4], out=sp, ldo=64, engine=eng, label="subpixel",
+                     conv=dict(B=B, T=T, Fin=Fh, Fout=Fh, taps_t=1, dil=1, stride_f=1, nslots=1))
+            ops.mask_conv(sp, B * T, 2 * Fh, P[f"{m}.conv_1.w"], b1, ws["mask_raw"])
+            ops.inorm_stats(ws["mask_raw"], B, T * F, 1, ws["stats1"], w["in_ws"])
+
+        def complex_branch(w):     # ComplexDecoder (generator.py:124-129)
+            dec, sp = [self._conv_in(t) for t in w["dec"]], w["sp"]
+            d4 = self._dense(P, f"{c}.dense_block", w, x0, dec, w["dec_raw"], B, T, Fh)
+            ops.gemm(loader=conv_loader, epilogue=EPI_SUBPIXEL, M=M, w=P[f"{c}.sub_pixel"], a=[d4], out=sp, ldo=64, engine=eng, label="subpixel",
+                     conv=dict(B=B, T=T, Fin=Fh, Fout=Fh, taps_t=1, dil=1, stride_f=1, nslots=1))
+            ops.inorm_stats(sp, B, T * 2 * Fh, 64, w["stats"], w["in_ws"])
+            ops.complex_conv(sp, B, T, 2 * Fh, w["stats"], P[f"{c}.norm.weight"], P[f"{c}.norm.bias"], P[f"{c}.prelu.weight"],
+                             P[f"{c}.conv.w"], P[f"{c}.conv.bias"], ws["cplx"])
+
+        if self.overlap_decoders:
+            # the two decoders are independent until the recombination: the complex decoder runs on a side stream with its own
+            # buffers, so its bandwidth-bound norm kernels can fill the gaps of the other branch's tensor-bound convolutions
+            w2 = self._second_decoder_buffers(ws, B, T, dev)
+            main = torch.cuda.current_stream(dev)
+            side = self._side_stream(dev)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                complex_branch(w2)
+            mask_branch(ws)
+            main.wait_stream(side)
+        else:
+            mask_branch(ws)
+            complex_branch(ws)
 
         # ---- mask tail + recombination (generator.py:110-112,158-165)
         mask_out = None

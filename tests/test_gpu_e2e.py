@@ -219,6 +219,18 @@ def test_cuda_graph_replay_matches_eager():
         assert torch.equal(graphed(noisy), eager(noisy))
 
 
+def test_decoders_on_two_streams_match_bitwise():
+    """opt-in TSCNet.overlap_decoders (complex decoder on a side stream with its own buffers): same result bit for bit, eager and captured"""
+    model = _model(0, "tcgen05")
+    enh = se_b200.EnhancerB200(model)
+    noisy, _ = weights.synth_wave(2, 8000, seed=41, kind="speech")
+    noisy = noisy.to(DEV)
+    ref = enh(noisy).clone()
+    model.overlap_decoders = True
+    assert torch.equal(enh(noisy), ref)
+    assert torch.equal(se_b200.EnhancerB200(model, use_cuda_graph=True)(noisy), ref)
+
+
 def test_batch_rows_are_independent():
     """pure batch sharding: a row enhanced alone equals the same row inside a batch, bit for bit"""
     model = _model(0, "tcgen05")
