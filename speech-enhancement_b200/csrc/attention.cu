@@ -693,15 +693,15 @@ extern "C" int seb200_attention(const void* qkv, const float* rel_pos_emb, const
     return 0;
   }
   SEB_REQUIRE(rel_pos_emb_h && aligned16(rel_pos_emb_h), SEB_EINVAL, "attention: the tensor-core variant needs the fp16 copy of rel_pos_emb");
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_done;
+  if (!attr_done.done()) {
     cudaError_t e = cudaFuncSetAttribute(attention_f16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_f16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_v4_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, a4_smem(4));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_v4_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, a4_smem(4));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_v4_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, a4_smem(4));
     if (e != cudaSuccess) { set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-    attr_done = true;
+    attr_done.set();
   }
   if (variant == 3)      // tcgen05 kernel (attention_tc.cu); same inputs as variant 0
     return attention_tc_launch(reinterpret_cast<const __half*>(qkv), reinterpret_cast<const __half*>(rel_pos_emb_h), seq, out, st);

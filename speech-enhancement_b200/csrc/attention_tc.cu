@@ -850,9 +850,9 @@ extern "C" int seb200_t5_trace(long long* host) { return (int)cudaMemcpyFromSymb
 #endif
 
 int attention_tc_launch(const __half* qkvh, const __half* Eh, const SebSeq* seq, float* out, cudaStream_t st) {
-  static bool attr_done = false;
+  static PerDeviceOnce attr_done;
   static int mode = 0;
-  if (!attr_done) {
+  if (!attr_done.done()) {
     const char* ev = getenv("SEB200_T5_MODE");      // experiment switch: 6 = three query groups per CTA (default), 0..5 = the two-CTA kernel (wait mode * 2 + packed)
     mode = ev ? atoi(ev) : 6;
     cudaError_t e = cudaSuccess;
@@ -860,7 +860,7 @@ int attention_tc_launch(const __half* qkvh, const __half* Eh, const SebSeq* seq,
     T5_ATTR(0, 0) T5_ATTR(0, 1) T5_ATTR(1, 0) T5_ATTR(1, 1) T5_ATTR(2, 0) T5_ATTR(2, 1)
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, T6_SMEM);
     if (e != cudaSuccess) { set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-    attr_done = true;
+    attr_done.set();
   }
   const int nqb = (seq->n + T5_BQ - 1) / T5_BQ;
   const long long nblocks = (long long)seq->nseq * 2 * nqb;

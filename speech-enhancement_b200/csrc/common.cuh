@@ -5,6 +5,7 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 
 #include "../../include/seb200.h"
 
@@ -31,6 +32,21 @@ void count_launch(int n = 1);
     }                                                                           \
     seb::count_launch();                                                        \
   } while (0)
+
+// Once-per-(call site, device) guard.  Kernel attributes (opt-in dynamic shared memory) are per device and one process may drive
+// several devices (nn.DataParallel around the module, main_gan.py:168-188), so a plain `static bool` would leave every device but
+// the first without its attribute.  Racing threads at worst set the same attribute twice.
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> mask{0};
+  bool done() const {
+    int d = 0;
+    return cudaGetDevice(&d) == cudaSuccess && d < 64 && ((mask.load(std::memory_order_acquire) >> d) & 1ull);
+  }
+  void set() {
+    int d = 0;
+    if (cudaGetDevice(&d) == cudaSuccess && d < 64) mask.fetch_or(1ull << d, std::memory_order_release);
+  }
+};
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

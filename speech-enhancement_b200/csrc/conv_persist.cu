@@ -178,15 +178,15 @@ __global__ void __launch_bounds__(CP_THREADS, 1) conv_persist_kernel(const GemmA
 }
 
 int launch_conv_persist(const SebGemm* s, const GemmArgs& g, cudaStream_t st) {
-  static bool attr_done = false;
+  static PerDeviceOnce attr_done;
   static int num_sms = 0;
-  if (!attr_done) {
+  if (!attr_done.done()) {
     cudaError_t e = cudaFuncSetAttribute(conv_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CP_SMEM);
     if (e != cudaSuccess) { set_error("conv persist: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     int dev = 0;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
-    attr_done = true;
+    attr_done.set();
   }
   SEB_REQUIRE(s->T < 32768 && s->Fout < 65536 && s->Fout >= 64 && (long long)s->B * s->T * s->Fin < 2147483647LL, SEB_EINVAL,
               "conv persist: geometry outside the packed row-table range (needs 64 <= Fout < 65536, T < 32768)");

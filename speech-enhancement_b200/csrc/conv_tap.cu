@@ -219,15 +219,15 @@ __global__ void __launch_bounds__(CTP_THREADS, 1) conv_tap_tc_kernel(const GemmA
 }
 
 int launch_conv_tap(const SebGemm* s, const GemmArgs& g, cudaStream_t st) {
-  static bool attr_done = false;
+  static PerDeviceOnce attr_done;
   static int num_sms = 0;
-  if (!attr_done) {
+  if (!attr_done.done()) {
     cudaError_t e = cudaFuncSetAttribute(conv_tap_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CTP_SMEM);
     if (e != cudaSuccess) { set_error("conv tap: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     int dev = 0;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
-    attr_done = true;
+    attr_done.set();
   }
   const long long Mp = (long long)s->B * s->T * (s->Fin + 1);
   SEB_REQUIRE(Mp < 2147483647LL - 256, SEB_EINVAL, "conv tap: padded pixel count overflows int");

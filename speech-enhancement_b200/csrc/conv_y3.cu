@@ -212,15 +212,15 @@ __global__ void __launch_bounds__(Y3_THREADS, 1) conv_y3_kernel(const GemmArgs g
 }
 
 int launch_conv_y3(const SebGemm* s, const GemmArgs& g, cudaStream_t st) {
-  static bool attr_done = false;
+  static PerDeviceOnce attr_done;
   static int num_sms = 0;
-  if (!attr_done) {
+  if (!attr_done.done()) {
     cudaError_t e = cudaFuncSetAttribute(conv_y3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Y3_SMEM);
     if (e != cudaSuccess) { set_error("conv y3: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     int dev = 0;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
-    attr_done = true;
+    attr_done.set();
   }
   SEB_REQUIRE(s->Fin >= 16 && (long long)s->M + s->Fin < 2147483647LL, SEB_EINVAL, "conv y3: geometry out of range");
   const long long ntiles = ((long long)s->M + Y3_OUT - 1) / Y3_OUT;

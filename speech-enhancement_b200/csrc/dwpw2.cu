@@ -272,15 +272,15 @@ extern "C" int seb200_dwconv_pw2(const float* u, const SebSeq* seq, const float*
   SEB_REQUIRE(u && seq && w && bn_scale && bn_shift && w3_tc && b3 && resid && out, SEB_EINVAL, "dwconv_pw2: null argument");
   SEB_REQUIRE(aligned16(u) && aligned16(w3_tc) && aligned16(b3) && aligned16(resid) && aligned16(out), SEB_EALIGN, "dwconv_pw2: unaligned pointer");
   SEB_REQUIRE(seq->nseq > 0 && seq->n > 0 && seq->inner > 0, SEB_EINVAL, "dwconv_pw2: bad sequence descriptor");
-  static bool attr_done = false;
+  static PerDeviceOnce attr_done;
   static int num_sms = 0;
-  if (!attr_done) {
+  if (!attr_done.done()) {
     cudaError_t e = cudaFuncSetAttribute(dwpw2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DP_SMEM);
     if (e != cudaSuccess) { set_error("dwconv_pw2: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     int dev = 0;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
-    attr_done = true;
+    attr_done.set();
   }
   DwPw2Args a;
   a.u = u; a.sq = *seq; a.w = w; a.bn_scale = bn_scale; a.bn_shift = bn_shift;

@@ -438,11 +438,11 @@ extern "C" int seb200_ffn_fused(const SebFfn* f, void* stream) {
   SEB_REQUIRE(f->ln_gamma && f->ln_beta && f->w1_tc && f->b1 && f->w2_tc && f->b2, SEB_EINVAL, "ffn_fused: null parameter");
   SEB_REQUIRE(aligned16(f->x) && aligned16(f->out) && aligned16(f->w1_tc) && aligned16(f->w2_tc) && aligned16(f->b1) && aligned16(f->b2), SEB_EALIGN, "ffn_fused: unaligned pointer");
   if (f->post_gamma) SEB_REQUIRE(f->post_beta && f->resid2 && aligned16(f->resid2), SEB_EINVAL, "ffn_fused: post-norm needs beta and resid2");
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_done;
+  if (!attr_done.done()) {
     cudaError_t e = cudaFuncSetAttribute(ffn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F3_SMEM);
     if (e != cudaSuccess) { set_error("ffn_fused: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-    attr_done = true;
+    attr_done.set();
   }
   FfnArgs a;
   a.x = f->x; a.out = f->out; a.M = (int)f->tokens; a.ln_g = f->ln_gamma; a.ln_b = f->ln_beta;

@@ -25,11 +25,11 @@ static GemmArgs to_args(const SebGemm* s) {
 
 template <int LK, int EK>
 static int launch_simt(const SebGemm* s, const GemmArgs& g, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_done;
+  if (!attr_done.done()) {
     cudaError_t e = cudaFuncSetAttribute(gemm_simt_kernel<LK, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SIMT_SMEM);
     if (e != cudaSuccess) { set_error("gemm simt: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-    attr_done = true;
+    attr_done.set();
   }
   SEB_REQUIRE(s->w_simt && s->simt_npad % 64 == 0 && s->simt_npad >= s->N, SEB_EINVAL, "gemm simt: bad weight image");
   dim3 grid((g.M + BM - 1) / BM, s->simt_npad / 64);
@@ -40,13 +40,13 @@ static int launch_simt(const SebGemm* s, const GemmArgs& g, cudaStream_t st) {
 
 template <int NT, int STAGES, int LK, int EK, int PW = 8, int MINB = 2, int NPL = 2>
 static int launch_tc(const SebGemm* s, const GemmArgs& g, cudaStream_t st) {
-  static bool attr_done = false;
+  static PerDeviceOnce attr_done;
   constexpr int SMEM = tc_smem_bytes<NT, STAGES, NPL>();
   SEB_REQUIRE(s->tc_planes == NPL, SEB_EINVAL, "gemm tc: weight image has %d planes, kernel wants %d", s->tc_planes, NPL);
-  if (!attr_done) {
+  if (!attr_done.done()) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<NT, STAGES, LK, EK, PW, MINB, NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) { set_error("gemm tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-    attr_done = true;
+    attr_done.set();
   }
   SEB_REQUIRE(s->w_tc && s->tc_ntile == NT && s->tc_ntiles >= 1 && s->tc_ntile * s->tc_ntiles >= s->N, SEB_EINVAL,
               "gemm tc: weight image has n-tile %d x %d, kernel wants %d covering N=%d", s->tc_ntile, s->tc_ntiles, NT, s->N);
@@ -59,12 +59,12 @@ static int launch_tc(const SebGemm* s, const GemmArgs& g, cudaStream_t st) {
 
 template <int NT, int STAGES, int EK>
 static int launch_conv_split(const SebGemm* s, const GemmArgs& g, cudaStream_t st) {
-  static bool attr_done = false;
+  static PerDeviceOnce attr_done;
   constexpr int SMEM = tc_smem_bytes<NT, STAGES>();
-  if (!attr_done) {
+  if (!attr_done.done()) {
     cudaError_t e = cudaFuncSetAttribute(conv_split_tc_kernel<NT, STAGES, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) { set_error("conv split: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-    attr_done = true;
+    attr_done.set();
   }
   SEB_REQUIRE(s->w_tc && s->tc_ntile == NT && s->tc_ntiles >= 1 && s->tc_ntile * s->tc_ntiles >= s->N && aligned16(s->w_tc), SEB_EINVAL,
               "conv split: weight image has n-tile %d x %d, kernel wants %d covering N=%d", s->tc_ntile, s->tc_ntiles, NT, s->N);

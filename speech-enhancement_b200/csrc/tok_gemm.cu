@@ -357,17 +357,17 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs 
 
 template <int NT, int KCH, int LK, int EK>
 static int launch_tok(const SebGemm* s, const GemmArgs& g, cudaStream_t st) {
-  static bool attr_done = false;
+  static PerDeviceOnce attr_done;
   static int num_sms = 0;
   constexpr int SMEM = tg_smem_bytes<NT, KCH, EK>();
   static_assert(SMEM + 256 <= 232448, "token GEMM: shared memory over the 227 KB per-CTA limit");
-  if (!attr_done) {
+  if (!attr_done.done()) {
     cudaError_t e = cudaFuncSetAttribute(tok_gemm_kernel<NT, KCH, LK, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) { set_error("tok gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     int dev = 0;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
-    attr_done = true;
+    attr_done.set();
   }
   const long long ntiles = ((long long)s->M + BM - 1) / BM;
   dim3 grid((unsigned)(ntiles < num_sms ? ntiles : num_sms));

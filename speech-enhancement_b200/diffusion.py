@@ -47,15 +47,16 @@ class DiffusionEnhancerB200:
         nsteps = len(c1)
         if not (len(T) == len(c2) == len(c3) == len(delta_bar) == nsteps) or nsteps < 1:
             raise RuntimeError("schedule arrays T, c1, c2, c3, delta_bar must have one entry per inference step")
-        noisy_audio, cond_in3, c = self.prepare(x)
-        audio = noisy_audio.contiguous()
-        for n in range(nsteps - 1, -1, -1):
-            noise = None
-            if n > 0:
-                noise = noise_fn(n, tuple(audio.shape)) if noise_fn is not None else torch.randn(audio.shape, device=x.device)
-            audio = self.step(audio, noisy_audio, cond_in3, n, T, c1, c2, c3, delta_bar, noise, c)
-            if trace is not None:
-                trace.append(audio.clone())
+        with torch.cuda.device(x.device):                 # launches follow the input's device
+            noisy_audio, cond_in3, c = self.prepare(x)
+            audio = noisy_audio.contiguous()
+            for n in range(nsteps - 1, -1, -1):
+                noise = None
+                if n > 0:
+                    noise = noise_fn(n, tuple(audio.shape)) if noise_fn is not None else torch.randn(audio.shape, device=x.device)
+                audio = self.step(audio, noisy_audio, cond_in3, n, T, c1, c2, c3, delta_bar, noise, c)
+                if trace is not None:
+                    trace.append(audio.clone())
         return audio[:, :L]
 
 

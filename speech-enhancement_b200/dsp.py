@@ -81,9 +81,10 @@ def compressed_stft(signal: torch.Tensor, n_fft: int = N_FFT, hop_length: int = 
     B, L = x.shape
     if L % HOP != 0:
         raise RuntimeError("signal length must be a multiple of hop (predict() pads it, inference_gan.py:83-87)")
-    xpad, _ = ops.rms_pad(x, L, normalize=False)
-    in3 = stft_in3(xpad, L // HOP + 1, engine)
-    return ops.in3_to_spec(in3)
+    with torch.cuda.device(x.device):
+        xpad, _ = ops.rms_pad(x, L, normalize=False)
+        in3 = stft_in3(xpad, L // HOP + 1, engine)
+        return ops.in3_to_spec(in3)
 
 
 def uncompressed_istft(spec: torch.Tensor, n_fft: int = N_FFT, hop_length: int = HOP, window: Optional[torch.Tensor] = None,
@@ -94,9 +95,10 @@ def uncompressed_istft(spec: torch.Tensor, n_fft: int = N_FFT, hop_length: int =
     B, F, T = spec.shape
     if F != N_BINS:
         raise RuntimeError(f"expected {N_BINS} bins")
-    z = torch.empty(B * T, LDZ, device=spec.device, dtype=torch.float32)
-    ops.spec_decompress_rows(spec.to(torch.complex64), z)
-    return istft_rows(z, B, T, None, engine)
+    with torch.cuda.device(spec.device):
+        z = torch.empty(B * T, LDZ, device=spec.device, dtype=torch.float32)
+        ops.spec_decompress_rows(spec.to(torch.complex64), z)
+        return istft_rows(z, B, T, None, engine)
 
 
 # ------------------------------------------------------------------------------- training caller

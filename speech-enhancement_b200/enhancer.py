@@ -42,9 +42,10 @@ class EnhancerB200(nn.Module):
         x = noisy.to(torch.float32).contiguous()
         if x.dim() == 1:
             x = x.unsqueeze(0)
-        if self.use_cuda_graph and stages is None:
-            return self._forward_graphed(x)
-        return self._forward_eager(x, stages)
+        with torch.cuda.device(x.device):                 # launches follow the input's device
+            if self.use_cuda_graph and stages is None:
+                return self._forward_graphed(x)
+            return self._forward_eager(x, stages)
 
     def _forward_graphed(self, x: torch.Tensor) -> torch.Tensor:
         key = (str(x.device), tuple(x.shape), self.model._version_key(), self.model.engine, self.dft_engine)

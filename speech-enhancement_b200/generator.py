@@ -470,7 +470,7 @@ class TSCNet(nn.Module):
             raise RuntimeError("se_b200.TSCNet has no CPU path: input must be a CUDA tensor on an sm_100a device")
         if not x.is_complex():
             raise RuntimeError("TSCNet.forward expects the complex compressed spectrogram (B, F, T)")
-        with torch.no_grad():
+        with torch.no_grad(), torch.cuda.device(x.device):      # launches follow the input's device (DataParallel replicas, cuda:k inputs)
             B, F, T = x.shape
             in3 = ops.spec_to_in3(x.to(torch.complex64))
             est = self.forward_in3(in3)

@@ -155,7 +155,7 @@ class TSCNet(_GanTSCNet):
             raise RuntimeError("se_b200.tsc_diffusion.TSCNet has no CPU path: inputs must be CUDA tensors on an sm_100a device")
         if not (x.is_complex() and noisy_spec.is_complex()):
             raise RuntimeError("TSCNet.forward expects complex compressed spectrograms (B, F, T)")
-        with torch.no_grad():
+        with torch.no_grad(), torch.cuda.device(x.device):
             B, F, T = x.shape
             in3 = ops.spec_to_in3(x.to(torch.complex64))
             nin3 = ops.spec_to_in3(noisy_spec.to(torch.complex64))

@@ -231,6 +231,24 @@ def test_decoders_on_two_streams_match_bitwise():
     assert torch.equal(se_b200.EnhancerB200(model, use_cuda_graph=True)(noisy), ref)
 
 
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_second_device_in_the_same_process():
+    """one process driving two devices (nn.DataParallel-style, main_gan.py:168-188): kernel attributes, packed weights, DFT bases
+    and workspaces are per device, launches follow the input's device; results are bit-identical across devices"""
+    sd = weights.synth_state_dict(0)
+    noisy, _ = weights.synth_wave(2, 8000, seed=41, kind="speech")
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        m = se_b200.TSCNet()
+        m.load_state_dict(sd)
+        m = m.to(dev).eval()
+        outs.append(se_b200.EnhancerB200(m)(noisy.to(dev)).cpu())            # current device stays cuda:0 throughout
+        spec = se_b200.compressed_stft(noisy.to(dev))
+        fr, fi = m(spec)
+        assert fr.device == torch.device(dev) and spec.device == torch.device(dev)
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_batch_rows_are_independent():
     """pure batch sharding: a row enhanced alone equals the same row inside a batch, bit for bit"""
     model = _model(0, "tcgen05")
