@@ -120,6 +120,19 @@ int seb200_spec_decompress_rows(const float* spec_ri, int B, int F, int T, float
 int seb200_overlap_add(const float* frames, int B, int T, int ldf, const float* inv_env,
                        const float* c, float* out, int Lout, int ld_out, void* stream);
 
+/* ---- backward of the DSP bracket (consistency-loss chain, core/function.py:231-254) -------------------
+ * Gradients of complex tensors follow PyTorch: (dL/dRe, dL/dIm) interleaved.  The DFT contractions of the backward pass are
+ * seb200_gemm calls with the transposed bases (ROWS loader for the STFT, HANKEL loader + BIAS epilogue for the iSTFT). */
+/* compressed_stft backward, step 1: Y, gY complex64 (B, F, T) -> rows [B*T, ldz] = gX (re, im) per bin, zero padded */
+int seb200_compress_backward_rows(const float* spec_ri, const float* gspec_ri, int B, int F, int T, float* rows, int ldz, void* stream);
+/* compressed_stft backward, step 3: gframes [B*T, ldf] (after the basis^T GEMM) -> gx [B, L], L = 100*(T-1): the adjoint of
+ * torch.stft's reflect padding + framing as a gather */
+int seb200_stft_fold(const float* gframes, int B, int T, int ldf, int L, float* gx, void* stream);
+/* uncompressed_istft backward, step 1: wpad [B, Lout+400] = zero-pad200(gy * inv_env); its Hankel frames are the frame gradients */
+int seb200_istft_grad_pad(const float* gy, const float* inv_env, int B, int Lout, float* wpad, void* stream);
+/* uncompressed_istft backward, step 3: gZ rows [B*T, ldz] (after the basis^T GEMM) + Y complex64 (B, F, T) -> gY (B, F, T) */
+int seb200_decompress_backward_spec(const float* spec_ri, const float* rows, int B, int F, int T, int ldz, float* gspec_ri, void* stream);
+
 /* ---- encoder / decoder bandwidth kernels ---------------------------------- */
 /* DenseEncoder.conv_1[0]: 1x1 conv 3 -> 64 (generator.py:39) on in3 */
 int seb200_conv1x1_in3(const float* in3, long long pixels, const float* w /*[64,3]*/,

@@ -74,6 +74,10 @@ _SIGS = {
     "seb200_packed_weight_sizes": [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_int),
                                    C.POINTER(C.c_int), C.POINTER(C.c_int)],
     "seb200_pack_weights": [_fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp],
+    "seb200_compress_backward_rows": [_fp, _fp, C.c_int, C.c_int, C.c_int, _fp, C.c_int, _fp],
+    "seb200_stft_fold": [_fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp],
+    "seb200_istft_grad_pad": [_fp, _fp, C.c_int, C.c_int, _fp, _fp],
+    "seb200_decompress_backward_spec": [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp],
     "seb200_diffusion_update": [_fp, _fp, C.c_longlong, _fp, _fp, C.c_int, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float, _fp, _fp, _fp],
     "seb200_diffusion_embed": [_fp, C.c_int, _fp, C.c_int, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp],
 }

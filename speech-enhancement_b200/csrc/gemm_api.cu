@@ -131,6 +131,7 @@ extern "C" int seb200_gemm(const SebGemm* s, int engine, void* stream) {
     switch (key) {
       case SEB_LOAD_HANKEL * 16 + SEB_EPI_COMPRESS: return launch_simt<SEB_LOAD_HANKEL, SEB_EPI_COMPRESS>(s, g, st);
       case SEB_LOAD_ROWS * 16 + SEB_EPI_BIAS:       return launch_simt<SEB_LOAD_ROWS, SEB_EPI_BIAS>(s, g, st);
+      case SEB_LOAD_HANKEL * 16 + SEB_EPI_BIAS:     return launch_simt<SEB_LOAD_HANKEL, SEB_EPI_BIAS>(s, g, st);
       case SEB_LOAD_ROWS * 16 + SEB_EPI_RESID:      return launch_simt<SEB_LOAD_ROWS, SEB_EPI_RESID>(s, g, st);
       case SEB_LOAD_ROWS * 16 + SEB_EPI_RESID_SCALE: return launch_simt<SEB_LOAD_ROWS, SEB_EPI_RESID_SCALE>(s, g, st);
       case SEB_LOAD_ROWS2 * 16 + SEB_EPI_GATE:      return launch_simt<SEB_LOAD_ROWS2, SEB_EPI_GATE>(s, g, st);
@@ -161,6 +162,7 @@ extern "C" int seb200_gemm(const SebGemm* s, int engine, void* stream) {
       case SEB_LOAD_CONV_SPLIT * 16 + SEB_EPI_SUBPIXEL: if (nt == 128) return launch_conv_split<128, 1, SEB_EPI_SUBPIXEL>(s, g, st); break;
       case SEB_LOAD_HANKEL * 16 + SEB_EPI_COMPRESS: if (nt == 208) return (s->tc_planes == 3) ? launch_tc<208, 1, SEB_LOAD_HANKEL, SEB_EPI_COMPRESS, 8, 1, 3>(s, g, st)
                                                                                              : launch_tc<208, 1, SEB_LOAD_HANKEL, SEB_EPI_COMPRESS>(s, g, st); break;
+      case SEB_LOAD_HANKEL * 16 + SEB_EPI_BIAS:     if (nt == 208 && s->tc_planes == 3) return launch_tc<208, 1, SEB_LOAD_HANKEL, SEB_EPI_BIAS, 8, 1, 3>(s, g, st); break;
       case SEB_LOAD_ROWS * 16 + SEB_EPI_BIAS:       if (nt == 208) return (s->tc_planes == 3) ? launch_tc<208, 1, SEB_LOAD_ROWS, SEB_EPI_BIAS, 8, 1, 3>(s, g, st)
                                                                                              : launch_tc<208, 1, SEB_LOAD_ROWS, SEB_EPI_BIAS>(s, g, st); break;
       case SEB_LOAD_ROWS * 16 + SEB_EPI_RESID:      if (nt == 64)  return (s->K <= 128) ? launch_tc<64, 1, SEB_LOAD_ROWS, SEB_EPI_RESID, 4, 4>(s, g, st)

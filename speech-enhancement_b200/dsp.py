@@ -31,6 +31,15 @@ def _bases(device):
     return _cache[key]
 
 
+def _bases_bwd(device):
+    """transposed bases for the backward pass: the adjoint of a dense contraction is the contraction with the transposed matrix"""
+    key = ("bases_bwd", str(device))
+    if key not in _cache:
+        _cache[key] = (pack_weight(dft_basis(N_FFT).t().contiguous(), 208, planes=3).to(device),      # [400, 402]: gX rows -> gFrames
+                       pack_weight(idft_basis(N_FFT).t().contiguous(), 208, planes=3).to(device))     # [402, 400]: gFrames -> gZ rows
+    return _cache[key]
+
+
 def _inv_env(T: int, device):
     key = ("env", str(device), T)
     if key not in _cache:
@@ -70,6 +79,64 @@ def istft_rows(z: torch.Tensor, B: int, T: int, c: Optional[torch.Tensor], engin
     return out
 
 
+class _CompressedStft(torch.autograd.Function):
+    """compressed_stft with its hand-written backward: the consistency-loss chain of train_gan
+    (core/function.py:231-254) differentiates est_audio -> compressed_stft.  x: (B, L) fp32 CUDA, L a multiple of 100."""
+
+    @staticmethod
+    def forward(ctx, x, engine):
+        with torch.cuda.device(x.device):
+            xpad, _ = ops.rms_pad(x, x.shape[1], normalize=False)
+            spec = ops.in3_to_spec(stft_in3(xpad, x.shape[1] // HOP + 1, engine))
+        ctx.save_for_backward(spec)
+        ctx.engine = engine
+        return spec
+
+    @staticmethod
+    def backward(ctx, gspec):
+        (spec,) = ctx.saved_tensors
+        B, F, T = spec.shape
+        eng = ctx.engine or DFT_ENGINE
+        with torch.cuda.device(spec.device):
+            rows = torch.empty(B * T, LDZ, device=spec.device, dtype=torch.float32)
+            ops.compress_backward_rows(spec, gspec.to(torch.complex64).contiguous(), rows)
+            fwd_t, _ = _bases_bwd(spec.device)
+            gframes = torch.empty(B * T, N_FFT, device=spec.device, dtype=torch.float32)
+            ops.gemm(loader=LOAD_ROWS, epilogue=EPI_BIAS, M=B * T, N=N_FFT, w=fwd_t, a=[rows], lda=LDZ, out=gframes, ldo=N_FFT, engine=eng,
+                     label="stft_bwd", k_logical=2 * N_BINS)
+            gx = ops.stft_fold(gframes, B, T, HOP * (T - 1))
+        return gx, None
+
+
+class _UncompressedIstft(torch.autograd.Function):
+    """uncompressed_istft with its hand-written backward (core/function.py:227-228 feeds the generator's output through it)."""
+
+    @staticmethod
+    def forward(ctx, spec, engine):
+        B, F, T = spec.shape
+        with torch.cuda.device(spec.device):
+            z = torch.empty(B * T, LDZ, device=spec.device, dtype=torch.float32)
+            ops.spec_decompress_rows(spec, z)
+            y = istft_rows(z, B, T, None, engine)
+        ctx.save_for_backward(spec)
+        ctx.engine = engine
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (spec,) = ctx.saved_tensors
+        B, F, T = spec.shape
+        eng = ctx.engine or DFT_ENGINE
+        with torch.cuda.device(spec.device):
+            wpad = ops.istft_grad_pad(gy.to(torch.float32).contiguous(), _inv_env(T, spec.device))
+            _, inv_t = _bases_bwd(spec.device)
+            rows = torch.empty(B * T, LDZ, device=spec.device, dtype=torch.float32)
+            ops.gemm(loader=LOAD_HANKEL, epilogue=EPI_BIAS, M=B * T, N=2 * N_BINS, w=inv_t, a=[wpad], lda=wpad.shape[1], out=rows, ldo=LDZ,
+                     engine=eng, label="istft_bwd", k_logical=N_FFT, conv=dict(B=B, T=T, Fin=N_FFT, Fout=0, stride_f=HOP))
+            gspec = ops.decompress_backward_spec(spec, rows)
+        return gspec, None
+
+
 def compressed_stft(signal: torch.Tensor, n_fft: int = N_FFT, hop_length: int = HOP, window: Optional[torch.Tensor] = None,
                     comp_type: str = "pow", engine: Optional[str] = None) -> torch.Tensor:
     """(B, L) fp32 CUDA -> complex64 (B, 201, L/100 + 1); core/function.py:685-693.  L must be a multiple of 100."""
@@ -81,6 +148,8 @@ def compressed_stft(signal: torch.Tensor, n_fft: int = N_FFT, hop_length: int = 
     B, L = x.shape
     if L % HOP != 0:
         raise RuntimeError("signal length must be a multiple of hop (predict() pads it, inference_gan.py:83-87)")
+    if torch.is_grad_enabled() and x.requires_grad:       # training caller: est_audio carries the generator's graph
+        return _CompressedStft.apply(x, engine)
     with torch.cuda.device(x.device):
         xpad, _ = ops.rms_pad(x, L, normalize=False)
         in3 = stft_in3(xpad, L // HOP + 1, engine)
@@ -95,6 +164,8 @@ def uncompressed_istft(spec: torch.Tensor, n_fft: int = N_FFT, hop_length: int =
     B, F, T = spec.shape
     if F != N_BINS:
         raise RuntimeError(f"expected {N_BINS} bins")
+    if torch.is_grad_enabled() and spec.requires_grad:
+        return _UncompressedIstft.apply(spec.to(torch.complex64).contiguous(), engine)
     with torch.cuda.device(spec.device):
         z = torch.empty(B * T, LDZ, device=spec.device, dtype=torch.float32)
         ops.spec_decompress_rows(spec.to(torch.complex64), z)

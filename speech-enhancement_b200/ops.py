@@ -149,6 +149,55 @@ def diffusion_embed(steps: torch.Tensor, table, w1, b1, w2, b2, wp, bp, wm, d_ou
     return d_out, rowbias
 
 
+# ---- backward of the DSP bracket ----------------------------------------------------------------
+def compress_backward_rows(spec: torch.Tensor, gspec: torch.Tensor, rows: torch.Tensor):
+    """Y, gY complex64 (B, F, T) -> rows [B*T, ldz] = gX (re, im), zero padded."""
+    require_cuda(spec, gspec)
+    _f32c(rows)
+    if spec.dtype != torch.complex64 or gspec.dtype != torch.complex64 or spec.shape != gspec.shape:
+        raise RuntimeError("compress_backward_rows: spec / gspec must be complex64 of the same shape")
+    B, F, T = spec.shape
+    tok = _pb("compress_bwd", 0.0, 24.0 * B * F * T) if _PROF is not None else None
+    check(_lib.load().seb200_compress_backward_rows(ptr(torch.view_as_real(spec.contiguous())), ptr(torch.view_as_real(gspec.contiguous())), B, F, T,
+                                                    ptr(rows), rows.shape[1], stream_ptr()), "seb200_compress_backward_rows")
+    _pe(tok)
+    return rows
+
+
+def stft_fold(gframes: torch.Tensor, B: int, T: int, L: int):
+    _f32c(gframes)
+    gx = torch.empty(B, L, device=gframes.device, dtype=torch.float32)
+    tok = _pb("stft_fold", 0.0, 4.0 * gframes.numel()) if _PROF is not None else None
+    check(_lib.load().seb200_stft_fold(ptr(gframes), B, T, gframes.shape[1], L, ptr(gx), stream_ptr()), "seb200_stft_fold")
+    _pe(tok)
+    return gx
+
+
+def istft_grad_pad(gy: torch.Tensor, inv_env: torch.Tensor):
+    _f32c(gy, inv_env)
+    B, Lout = gy.shape
+    wpad = torch.empty(B, Lout + 400, device=gy.device, dtype=torch.float32)
+    tok = _pb("istft_grad_pad", 0.0, 8.0 * gy.numel()) if _PROF is not None else None
+    check(_lib.load().seb200_istft_grad_pad(ptr(gy), ptr(inv_env), B, Lout, ptr(wpad), stream_ptr()), "seb200_istft_grad_pad")
+    _pe(tok)
+    return wpad
+
+
+def decompress_backward_spec(spec: torch.Tensor, rows: torch.Tensor):
+    """Y complex64 (B, F, T) + gZ rows [B*T, ldz] -> gY complex64 (B, F, T)."""
+    require_cuda(spec)
+    _f32c(rows)
+    if spec.dtype != torch.complex64:
+        raise RuntimeError("decompress_backward_spec: spec must be complex64")
+    B, F, T = spec.shape
+    g = torch.empty(B, F, T, device=spec.device, dtype=torch.complex64)
+    tok = _pb("decompress_bwd", 0.0, 24.0 * B * F * T) if _PROF is not None else None
+    check(_lib.load().seb200_decompress_backward_spec(ptr(torch.view_as_real(spec.contiguous())), ptr(rows), B, F, T, rows.shape[1],
+                                                      ptr(torch.view_as_real(g)), stream_ptr()), "seb200_decompress_backward_spec")
+    _pe(tok)
+    return g
+
+
 def diffusion_update(audio, noisy, pred, noise, ca: float, cb: float, cc: float, cs: float, c_div=None, out=None):
     """out = (ca * audio + cb * noisy + cc * pred + cs * noise) [/ c_div per utterance]; noisy may be a row-strided view."""
     _f32c(audio, pred, noise, c_div)
