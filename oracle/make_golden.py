@@ -57,7 +57,22 @@ def main():
             final_real=fr.numpy(), final_imag=fi.numpy(),
             weight_seed=np.int64(sseed), wave_seed=np.int64(wseed))
         print(name, "enhanced peak", float(np.abs(enhanced).max()))
+    default_init_golden(ref, out_dir)
     diffusion_golden(ref, out_dir)
+
+
+def default_init_golden(ref, out_dir):
+    """second weight set: PyTorch-default initialisation (oracle.weights.torch_default_state_dict)"""
+    name, b, L, wseed, sseed = "default_init_b1_L6000", 1, 6000, 55, 2
+    sd = weights.torch_default_state_dict(sseed)
+    model = ref.TSCNet(num_channel=64, num_features=201)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    noisy, clean = weights.synth_wave(b, L, wseed, "speech")
+    enhanced = np.stack([ref.predict(model, ref.config, noisy[i].numpy(), device=torch.device("cpu")) for i in range(b)])
+    np.savez_compressed(os.path.join(out_dir, name + ".npz"), noisy=noisy.numpy(), clean=clean.numpy(), enhanced=enhanced.astype(np.float32),
+                        weight_seed=np.int64(sseed), wave_seed=np.int64(wseed))
+    print(name, "enhanced peak", float(np.abs(enhanced).max()))
 
 
 # SURVEY 8f row f3: models/tsc_diffusion.py:TSCNet.forward on (estimate, conditioning utterance, step); integer, fractional

@@ -96,6 +96,41 @@ def tsc_diffusion_spec():
     return enc + noisy + merge + rest
 
 
+def torch_default_state_dict(seed: int = 0, spec=None) -> "OrderedDict[str, torch.Tensor]":
+    """The second weight set of SURVEY 8d: PyTorch's DEFAULT initialisation of every layer (what ``TSCNet(...)`` holds before
+    ``model.apply(kaiming_init)``): Linear / ConvNd weights kaiming_uniform(a = sqrt 5), i.e. U(-1/sqrt(fan_in), 1/sqrt(fan_in)), biases
+    U(-1/sqrt(fan_in), 1/sqrt(fan_in)) with the fan-in of their layer, Embedding N(0, 1), norms 1 / 0, BatchNorm running statistics 0 / 1,
+    PReLU 0.25 (``prelu_out`` -0.25, generator.py:104).  Drawn from per-entry generators so any box rebuilds the same tensors."""
+    sd = OrderedDict()
+    fan_in = 1
+    for idx, (key, shape, kind) in enumerate(tscnet_spec() if spec is None else spec):
+        g = torch.Generator().manual_seed(7919 + seed * 100003 + idx)
+        uni = lambda bound: (torch.rand(shape, generator=g, dtype=torch.float32) * 2.0 - 1.0) * bound
+        if kind in ("w", "w1"):
+            fan_in = 1
+            for d in shape[1:]:
+                fan_in *= d
+            t = uni(1.0 / math.sqrt(fan_in))
+        elif kind == "b":
+            t = uni(1.0 / math.sqrt(fan_in))          # the bias entry follows its layer's weight in the spec
+        elif kind in ("g", "rv"):
+            t = torch.ones(shape)
+        elif kind in ("beta", "rm"):
+            t = torch.zeros(shape)
+        elif kind == "slope":
+            t = torch.full(shape, 0.25)
+        elif kind == "slope_neg":
+            t = torch.full(shape, -0.25)
+        elif kind == "emb":
+            t = torch.randn(shape, generator=g, dtype=torch.float32)
+        elif kind == "count":
+            t = torch.zeros((), dtype=torch.int64)
+        else:
+            raise KeyError(kind)
+        sd[key] = t
+    return sd
+
+
 def synth_state_dict(seed: int = 0, perturb: float = 0.1, spec=None) -> "OrderedDict[str, torch.Tensor]":
     sd = OrderedDict()
     for idx, (key, shape, kind) in enumerate(tscnet_spec() if spec is None else spec):

@@ -52,6 +52,21 @@ def test_predict_matches_reference_golden(golden, name, engine):
 
 
 @pytest.mark.parametrize("engine", ["simt", "tcgen05"])
+def test_predict_matches_reference_golden_default_init(golden, engine):
+    """second weight set: PyTorch-default initialisation (small uniform weights, identity norms)"""
+    g = golden("default_init_b1_L6000")
+    m = se_b200.TSCNet(num_channel=64, num_features=201)
+    m.load_state_dict(weights.torch_default_state_dict(int(g["weight_seed"])))
+    m = m.to(DEV).eval()
+    m.engine = engine
+    y = se_b200.EnhancerB200(m)(torch.from_numpy(g["noisy"]).to(DEV)).cpu()
+    ref, clean = torch.from_numpy(g["enhanced"]), torch.from_numpy(g["clean"])
+    err = rel_max(y, ref)
+    assert err < WAVE_TOL, f"waveform max-abs/peak {err:.3e}"
+    assert (O.si_sdr(y, clean) - O.si_sdr(ref, clean)).abs().max().item() < SISDR_TOL_DB
+
+
+@pytest.mark.parametrize("engine", ["simt", "tcgen05"])
 def test_module_forward_matches_reference_golden(golden, engine):
     """TSCNet.forward(complex spectrogram) -> (real, imag), the reference's nn.Module contract."""
     g = golden("speech_b2_L8000")

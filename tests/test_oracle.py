@@ -86,6 +86,16 @@ def test_diffusion_oracle_against_live_reference():
             assert rel_max(ofr, fr) < 1e-5 and rel_max(ofi, fi) < 1e-5
 
 
+def test_oracle_matches_golden_default_init(golden):
+    """second weight set: PyTorch-default initialisation, output of the reference's predict()"""
+    g = golden("default_init_b1_L6000")
+    sd = weights.torch_default_state_dict(int(g["weight_seed"]))
+    assert list(sd.keys()) == [k for k, _, _ in weights.tscnet_spec()]
+    with torch.no_grad():
+        y = O.predict(torch.from_numpy(g["noisy"]), sd)
+    assert rel_max(y, torch.from_numpy(g["enhanced"])) < 2e-5
+
+
 def test_golden_inputs_are_reproducible(golden):
     """the committed inputs are exactly what oracle.weights regenerates from the stored seeds"""
     g = golden("speech_b2_L8000")
