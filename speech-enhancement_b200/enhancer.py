@@ -42,6 +42,11 @@ class EnhancerB200(nn.Module):
         x = noisy.to(torch.float32).contiguous()
         if x.dim() == 1:
             x = x.unsqueeze(0)
+        if x.shape[0] == 0:                               # an empty shard (more ranks than utterances): nothing to launch
+            return x.new_zeros(x.shape)
+        if x.shape[1] <= dsp.N_FFT // 2:
+            raise RuntimeError(f"utterance of {x.shape[1]} samples: torch.stft's reflect padding (n_fft/2 = 200) needs more than 200 "
+                               "samples, as in the reference (core/function.py:690)")
         with torch.cuda.device(x.device):                 # launches follow the input's device
             if self.use_cuda_graph and stages is None:
                 return self._forward_graphed(x)

@@ -264,6 +264,25 @@ def test_second_device_in_the_same_process():
     assert torch.equal(outs[0], outs[1])
 
 
+@pytest.mark.parametrize("L", [201, 300, 1000])
+def test_shortest_utterances(L):
+    """edge sizes: 201 samples is the shortest clip torch.stft's reflect padding accepts (T = 4 frames after the wrap-pad to 300:
+    every dilated-conv layer reads mostly padding, time-axis sequences of 4 positions); shorter clips raise as in the reference"""
+    sd = weights.synth_state_dict(2)
+    model = _model(2, "tcgen05")
+    enh = se_b200.EnhancerB200(model)
+    noisy, _ = weights.synth_wave(2, L, seed=61, kind="speech")
+    with torch.no_grad():
+        y_o = O.predict(noisy, sd)
+    y_g = enh(noisy.to(DEV)).cpu()
+    assert y_g.shape == (2, L)
+    assert rel_max(y_g, y_o) < WAVE_TOL
+    with pytest.raises(RuntimeError, match="reflect padding"):
+        enh(noisy[:, :200].to(DEV))
+    empty = enh(noisy[:0].to(DEV))
+    assert empty.shape == (0, L)
+
+
 def test_batch_rows_are_independent():
     """pure batch sharding: a row enhanced alone equals the same row inside a batch, bit for bit"""
     model = _model(0, "tcgen05")
