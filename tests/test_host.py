@@ -188,6 +188,38 @@ def test_abi_rejects_bad_arguments_without_a_gpu():
     assert lib.seb200_rms_pad(None, 1, 100, 100, 1, None, None, None) == -1
 
 
+def test_abi_validates_merge_block_descriptors_without_a_gpu():
+    """argument checks of the two-source loader / gate epilogue happen before any launch"""
+    lib = se_b200._lib.load()
+    buf = (ctypes.c_float * 64)()
+    addr = ctypes.addressof(buf) & ~15
+    g = se_b200._lib.SebGemm()
+    g.loader, g.epilogue = se_b200._lib.LOAD_ROWS2, se_b200._lib.EPI_GATE
+    g.M, g.N, g.K, g.lda, g.ldo = 128, 128, 64, 64, 64          # K must be 128
+    g.a[0], g.a[1], g.out = addr, addr, addr
+    assert lib.seb200_gemm(ctypes.byref(g), 0, None) == -2 and b"two-source" in lib.seb200_last_error_string()
+    g.K, g.a[1] = 128, 0                                          # second source missing
+    assert lib.seb200_gemm(ctypes.byref(g), 0, None) == -2
+    g.a[1], g.resid, g.ldr = addr, addr, 0                        # row bias without rows-per-group
+    assert lib.seb200_gemm(ctypes.byref(g), 0, None) == -1 and b"rows per group" in lib.seb200_last_error_string()
+    assert lib.seb200_diffusion_embed(None, 1, None, 50, None, None, None, None, None, None, None, None, None, None) == -1
+    assert lib.seb200_stft_fold(None, 1, 5, 400, 400, None, None) == -1
+    assert lib.seb200_pack_weights(None, 64, 64, 64, 2, None, None) == -1
+
+
+def test_c_abi_weight_packer_random_shapes():
+    """hypothesis: any (N, K, n-tile, planes) the engine accepts packs identically in C and in the torch restatement"""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=25, deadline=None)
+    @given(st.integers(1, 300), st.integers(1, 300), st.sampled_from([16, 64, 128, 192, 208, 256]), st.sampled_from([2, 3]), st.integers(0, 1000))
+    def check(N, K, ntile, planes, seed):
+        w = torch.randn(N, K, generator=torch.Generator().manual_seed(seed))
+        a, b = packing.pack_weight(w, ntile, None, planes), packing.pack_weight_torch(w, ntile, None, planes)
+        assert torch.equal(a.w_tc, b.w_tc) and torch.equal(a.w_simt, b.w_simt) and (a.K, a.tc_ntiles, a.simt_npad) == (b.K, b.tc_ntiles, b.simt_npad)
+    check()
+
+
 def test_shard_slice_partitions():
     for n, g in [(4096, 8), (10, 4), (3, 8), (64, 1)]:
         idx = []
