@@ -44,8 +44,11 @@ constexpr int F3_W_COPY = F3_W_MMA2 + 1;                     // 26
 constexpr int F3_THREADS = (F3_W_COPY + 1) * 32;             // 864
 constexpr int F3_WBLK = 2 * 64 * 128;                        // 16 KB: hi|lo image of a 64-row x 64-k weight block
 constexpr int F3_XSLOT = BM * 256;                           // 32 KB: raw fp32 rows of one tile (16-byte chunks XOR-swizzled by row & 7)
-constexpr int F3_TAB_FLOATS = 256 + 5 * 64 + 2 * BM;         // b1 | b2 | ln_g | ln_b | pn_g | pn_b | (mean, rstd) per row
-constexpr int F3_SMEM = 1024 + 8 * F3_WBLK + 2 * F3_XSLOT + F3_TAB_FLOATS * 4;
+constexpr int F3_NSLOT = 3;                                  // staging slots: a slot lives from the copy to the end of its tile, so the slot
+                                                             // count caps the tiles in flight (two slots left the DRAM latency in the chain)
+constexpr int F3_TAB_FLOATS = 256 + 64;                      // b1 | b2  (LayerNorm parameters come through L1, row statistics by warp shuffle)
+constexpr int F3_SMEM = 1024 + 8 * F3_WBLK + F3_NSLOT * F3_XSLOT + F3_TAB_FLOATS * 4;
+static_assert(F3_SMEM + 256 <= 232448, "ffn_fused: shared memory over the 227 KB per-CTA limit (dynamic + the static mbarriers)");
 // TMEM columns
 constexpr uint32_t F3_XA = 0, F3_ACC1 = 128, F3_H = 256, F3_ACC2 = 384;
 
@@ -130,16 +133,15 @@ __device__ __forceinline__ void swish_split16(const uint32_t (&r)[16], const flo
 
 __global__ void __launch_bounds__(F3_THREADS, 1) ffn_fused_kernel(const FfnArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t w_full, x_full[2], x_empty[2], xa_full[2], xa_empty[2], acc1_full[2], acc1_empty[2], h_full[2], h_empty[2],
+  __shared__ uint64_t w_full, x_full[F3_NSLOT], x_empty[F3_NSLOT], xa_full[2], xa_empty[2], acc1_full[2], acc1_empty[2], h_full[2], h_empty[2],
       acc2_full[2], acc2_empty[2];
   __shared__ uint32_t tmem_base_s;
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space
   uint8_t* sW1 = smem;                          // 4 blocks x (hi | lo)   64 KB  resident
   uint8_t* sW2 = sW1 + 4 * F3_WBLK;             // 4 blocks x (hi | lo)   64 KB  resident
   uint8_t* sX = sW2 + 4 * F3_WBLK;              // [2] raw fp32 tiles     64 KB
-  float* sTab = reinterpret_cast<float*>(sX + 2 * F3_XSLOT);
-  float* sB1 = sTab; float* sB2 = sTab + 256; float* sG = sTab + 320; float* sBt = sTab + 384; float* sPG = sTab + 448; float* sPB = sTab + 512;
-  float2* sStat = reinterpret_cast<float2*>(sTab + 576);
+  float* sTab = reinterpret_cast<float*>(sX + F3_NSLOT * F3_XSLOT);
+  float* sB1 = sTab; float* sB2 = sTab + 256;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ntiles = (a.M + BM - 1) / BM;
   const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -147,8 +149,8 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn_fused_kernel(const FfnArgs 
 
   if (tid == 0) {
     ptx::mbar_init(&w_full, 1);
+    for (int i = 0; i < F3_NSLOT; ++i) { ptx::mbar_init(&x_full[i], 32); ptx::mbar_init(&x_empty[i], F3_FIN_WARPS * 32); }
     for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(&x_full[i], 32);                         ptx::mbar_init(&x_empty[i], F3_FIN_WARPS * 32);
       ptx::mbar_init(&xa_full[i], F3_LN_WARPS * 32);          ptx::mbar_init(&xa_empty[i], 1);
       ptx::mbar_init(&acc1_full[i], 1);                       ptx::mbar_init(&acc1_empty[i], (F3_MID_WARPS / 2) * 32);
       ptx::mbar_init(&h_full[i], (F3_MID_WARPS / 2) * 32);    ptx::mbar_init(&h_empty[i], 1);
@@ -156,16 +158,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn_fused_kernel(const FfnArgs 
     }
     ptx::fence_barrier_init();
   }
-  for (int i = tid; i < 576; i += F3_THREADS) {
-    float v;
-    if (i < 256) v = a.b1[i];
-    else if (i < 320) v = a.b2[i - 256];
-    else if (i < 384) v = a.ln_g[i - 320];
-    else if (i < 448) v = a.ln_b[i - 384];
-    else if (i < 512) v = post ? a.pn_g[i - 448] : 1.f;
-    else v = post ? a.pn_b[i - 512] : 0.f;
-    sTab[i] = v;
-  }
+  for (int i = tid; i < F3_TAB_FLOATS; i += F3_THREADS) sTab[i] = (i < 256) ? a.b1[i] : a.b2[i - 256];
   if (warp == F3_W_MMA1) ptx::tmem_alloc(&tmem_base_s, 512);
   ptx::tc_fence_before();
   __syncthreads();
@@ -177,10 +170,10 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn_fused_kernel(const FfnArgs 
     const int row = tid, sw = row & 7;
     const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
     for (int it = 0; it < my_tiles; ++it) {
-      const int s = it & 1;
+      const int s = it & 1, xsl = it % F3_NSLOT;
       const uint32_t ph = (uint32_t)(it >> 1) & 1u;
-      const uint8_t* xr = sX + s * F3_XSLOT + row * 256;
-      ptx::mbar_wait(&x_full[s], ph);
+      const uint8_t* xr = sX + xsl * F3_XSLOT + row * 256;
+      ptx::mbar_wait(&x_full[xsl], (uint32_t)(it / F3_NSLOT) & 1u);
       // pass A: shifted one-pass statistics (shift = first element of the row; exact for constant rows)
       float sum = 0.f, sq = 0.f;
       const float x0 = lds4(xr + ((0 ^ sw) << 4)).x;
@@ -206,8 +199,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn_fused_kernel(const FfnArgs 
         for (int j = 0; j < 4; ++j) {
           const int c = c16 * 4 + j;
           const float4 v = lds4(xr + ((c ^ sw) << 4));
-          const float4 gg = *reinterpret_cast<const float4*>(sG + c * 4);
-          const float4 bb = *reinterpret_cast<const float4*>(sBt + c * 4);
+          const float4 gg = ldg4(a.ln_g + c * 4), bb = ldg4(a.ln_b + c * 4);      // warp-uniform, L1-resident (no room left in shared memory)
           float2 y01, y23;
           ln_apply4(v, mean, rstd, gg, bb, y01, y23);
           split_bf16x2(y01.x, y01.y, hi[2 * j], lo[2 * j]);
@@ -261,12 +253,12 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn_fused_kernel(const FfnArgs 
     const int row = fw * 32 + lane, sw = row & 7;
     const uint32_t lane_base = tmem_base + ((uint32_t)(fw * 32) << 16);
     const int cc = lane & 15;                                     // 16-byte chunk handled in the copy-out
-    const float4 pg = *reinterpret_cast<const float4*>(sPG + cc * 4), pb = *reinterpret_cast<const float4*>(sPB + cc * 4);
+    const float4 pg = post ? ldg4(a.pn_g + cc * 4) : make_float4(1.f, 1.f, 1.f, 1.f), pb = post ? ldg4(a.pn_b + cc * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     for (int it = 0; it < my_tiles; ++it) {
       const int m0 = ((int)blockIdx.x + it * (int)gridDim.x) * BM;
-      const int s = it & 1, ab = it & 1;
+      const int xsl = it % F3_NSLOT, ab = it & 1;
       const uint32_t ph = (uint32_t)(it >> 1) & 1u;
-      uint8_t* xs = sX + s * F3_XSLOT;
+      uint8_t* xs = sX + xsl * F3_XSLOT;
       uint8_t* xr = xs + row * 256;
       // the residual rows of this tile are consumed by the copy-out below: start pulling them into L2 now
       if (post && a.resid2 != a.x) {
@@ -305,10 +297,12 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn_fused_kernel(const FfnArgs 
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&acc2_empty[ab]);
+      float my_mean, my_rstd;                  // this thread's row; the copy-out fetches a row's pair from its owner lane by shuffle
       {
         const float md = sum * (1.0f / 64.0f);
         const float var = fmaxf(sq * (1.0f / 64.0f) - md * md, 0.f);
-        sStat[row] = make_float2(y0s + md, 1.0f / sqrtf(var + 1e-5f));
+        my_mean = y0s + md;
+        my_rstd = 1.0f / sqrtf(var + 1e-5f);
       }
       __syncwarp();
       // coalesced copy-out of this warp's 32 rows: half a warp per row, one 16-byte chunk per lane.  Loads of a group of four
@@ -323,7 +317,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn_fused_kernel(const FfnArgs 
           const int rr = fw * 32 + 2 * (i0 + u) + (lane >> 4);
           const int m = m0 + rr;
           yv[u] = lds4(xs + rr * 256 + ((cc ^ (rr & 7)) << 4));
-          st[u] = sStat[rr];
+          st[u] = make_float2(__shfl_sync(0xffffffffu, my_mean, rr & 31), __shfl_sync(0xffffffffu, my_rstd, rr & 31));
           r2[u] = (post && m < a.M) ? *reinterpret_cast<const float4*>(a.resid2 + (long long)m * 64 + cc * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
@@ -338,7 +332,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn_fused_kernel(const FfnArgs 
         }
       }
       __syncwarp();
-      ptx::mbar_arrive(&x_empty[s]);            // this thread's reads of the staging slot are done
+      ptx::mbar_arrive(&x_empty[xsl]);          // this thread's reads of the staging slot are done
     }
   } else if (warp == F3_W_MMA1) {
     // ================= GEMM 1 issuer: ACC1[g] = XA[s] . W1[q]^T =================
@@ -408,8 +402,8 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn_fused_kernel(const FfnArgs 
       }
       for (int it = 0; it < my_tiles; ++it) {
         const int m0 = ((int)blockIdx.x + it * (int)gridDim.x) * BM;
-        const int s = it & 1;
-        ptx::mbar_wait(&x_empty[s], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+        const int s = it % F3_NSLOT;
+        ptx::mbar_wait(&x_empty[s], ((uint32_t)(it / F3_NSLOT) & 1u) ^ 1u);
         const uint32_t dst0 = ptx::smem_u32(sX) + s * F3_XSLOT;
 #pragma unroll 8
         for (int k = 0; k < 64; ++k) {
@@ -437,7 +431,9 @@ extern "C" int seb200_ffn_fused(const SebFfn* f, void* stream) {
   SEB_REQUIRE(f && f->x && f->out && f->tokens > 0 && f->tokens < 2147483647LL - 128, SEB_EINVAL, "ffn_fused: bad arguments");
   SEB_REQUIRE(f->ln_gamma && f->ln_beta && f->w1_tc && f->b1 && f->w2_tc && f->b2, SEB_EINVAL, "ffn_fused: null parameter");
   SEB_REQUIRE(aligned16(f->x) && aligned16(f->out) && aligned16(f->w1_tc) && aligned16(f->w2_tc) && aligned16(f->b1) && aligned16(f->b2), SEB_EALIGN, "ffn_fused: unaligned pointer");
-  if (f->post_gamma) SEB_REQUIRE(f->post_beta && f->resid2 && aligned16(f->resid2), SEB_EINVAL, "ffn_fused: post-norm needs beta and resid2");
+  SEB_REQUIRE(aligned16(f->ln_gamma) && aligned16(f->ln_beta), SEB_EALIGN, "ffn_fused: unaligned LayerNorm parameters");
+  if (f->post_gamma) SEB_REQUIRE(f->post_beta && f->resid2 && aligned16(f->resid2) && aligned16(f->post_gamma) && aligned16(f->post_beta), SEB_EINVAL,
+                                 "ffn_fused: post-norm needs 16-byte aligned gamma / beta and resid2");
   static PerDeviceOnce attr_done;
   if (!attr_done.done()) {
     cudaError_t e = cudaFuncSetAttribute(ffn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F3_SMEM);
