@@ -78,3 +78,26 @@ def test_configs2_16x30s_properties():
     alt = enh(base[:1].to(DEV))
     err = rel_max(alt, small)
     assert err < WAVE_TOL, f"30 s clip, mma.sync vs tcgen05 attention: {err:.3e}"
+
+
+def test_diffusion_per_utterance_steps_at_4s():
+    """diffusion variant, 8 x 4 s with one step per utterance (integer and fractional): row i equals the same utterance evaluated alone
+    with its own step, bit for bit -- the per-utterance bias rows of the merge GEMM change inside 128-row tiles (64 741 tokens per clip)"""
+    from se_b200 import tsc_diffusion
+    m = tsc_diffusion.TSCNet(64, 201, noise_schedule=[0.0] * 50)
+    m.load_state_dict(weights.synth_state_dict(3, spec=weights.tsc_diffusion_spec()))
+    m = m.to(DEV).eval()
+    est, _ = weights.synth_wave(8, 64000, seed=5, kind="speech")
+    cond, _ = weights.synth_wave(8, 64000, seed=6, kind="speech")
+    sx, sn = se_b200.compressed_stft(est.to(DEV)), se_b200.compressed_stft(cond.to(DEV))
+    steps = torch.tensor([0.0, 3.0, 7.25, 12.5, 20.0, 33.75, 48.0, 49.0], device=DEV)
+    fr, fi = m(sx, sn, steps)
+    fr, fi = fr.clone(), fi.clone()
+    assert fr.shape == (8, 1, 641, 201) and bool(torch.isfinite(fr).all())
+    for i in (0, 2, 7):
+        fr1, fi1 = m(sx[i:i + 1], sn[i:i + 1], steps[i:i + 1])
+        assert torch.equal(fr1[0], fr[i]) and torch.equal(fi1[0], fi[i]), f"utterance {i}"
+    # a shared step equals that step repeated per utterance
+    fa, _ = m(sx, sn, torch.tensor([7.25], device=DEV))
+    fb, _ = m(sx, sn, torch.full((8,), 7.25, device=DEV))
+    assert torch.equal(fa, fb)
