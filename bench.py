@@ -249,6 +249,18 @@ def run_b200(args):
             n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
             pk_exp = n_sm * 16 * sm_mhz * 1e6 / 1e9
             secondary = {"bound": "mufu", "achieved": gexp, "peak": pk_exp, "unit": "Gexp/s", "frac": gexp / pk_exp}
+        # per-kernel roofline fractions (north_star) from the fully event-bracketed pass: ALGORITHMIC flops / bytes per label as the
+        # wrappers in ops.py attach them, over the label's device time; `bound` is the roofline DESIGN.md section 4 assigns to the kernel
+        hbm_bound = {"qkv", "attn_out", "pw1_glu", "pw2", "merge_gate", "merge_out"}
+        kernel_rooflines = {}
+        for k, v in sorted(table.items(), key=lambda kv: -kv[1]["ms"]):
+            if v["ms"] <= 0:
+                continue
+            tf, gb = v["flops"] / (v["ms"] * 1e-3) / 1e12, v["bytes"] / (v["ms"] * 1e-3) / 1e9
+            tensor = (k in TENSOR_LABELS or k == "ffn_fused") and k not in hbm_bound
+            kernel_rooflines[k] = {"bound": "tensor" if tensor else "hbm", "ms": round(v["ms"], 3), "launches": v["launches"],
+                                   "achieved": round(tf if tensor else gb, 1), "unit": "TFLOP/s" if tensor else "GB/s",
+                                   "frac": round((tf / pk["tflops"]) if tensor else (gb / pk["hbm_gbs"]), 4)}
         line = {
             "metric": METRIC, "value": audio_s / (dev_ms * 1e-3), "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -266,6 +278,7 @@ def run_b200(args):
                          "traffic": traffic, "peak_source": pk["src"], "launches_timed": dom["launches"], "ms_per_launch": per_launch_ms,
                          "share_of_step": shares.get(dominant), "secondary": secondary},
             "kernel_shares": shares,
+            "kernel_rooflines": kernel_rooflines,
         }
         if world == 1 and not args.no_cpu_baseline:
             val, tsec, cores = cpu_oracle_throughput(args.cpu_sample_clips, args.clip_seconds, 0, 1)

@@ -129,7 +129,15 @@ def gemm(*, loader: int, epilogue: int, M: int, w: PackedWeight, a: Sequence[tor
     g.bias = ptr(w.bias)
     g.out, g.ldo = ptr(out), ldo
     g.resid, g.ldr, g.alpha = ptr(resid), ldr, alpha
-    tok = _pb(label, 2.0 * M * g.N * (k_logical or w.K), 4.0 * M * (g.N + (k_logical or w.K))) if _PROF is not None else None
+    if _PROF is not None:
+        # algorithmic bytes: the A rows once, the output once (fp16 q|k|v: 2 B, GLU / gate: half the columns), the residual once
+        n_out = g.N // 2 if epilogue in (EPI_GLU, _lib.EPI_GATE) else g.N
+        nbytes = 4.0 * M * (k_logical or w.K) + (2.0 if epilogue == EPI_QKV_F16 else 4.0) * M * n_out
+        if epilogue in (EPI_RESID, _lib.EPI_RESID_SCALE):
+            nbytes += 4.0 * M * g.N
+        tok = _pb(label, 2.0 * M * g.N * (k_logical or w.K), nbytes)
+    else:
+        tok = None
     check(lib.seb200_gemm(C.byref(g), ENGINES[engine], stream_ptr()), "seb200_gemm")
     _pe(tok)
     return out
