@@ -107,7 +107,8 @@ TENSOR_LABELS = {"dconv", "conv2", "subpixel", "ffn1", "ffn2", "qkv", "attn_out"
 # ------------------------------------------------------------------------------------------- CPU arm
 def cpu_oracle_throughput(clips: int, clip_s: float, warmup: int, steps: int):
     """Times the oracle port of the reference path (oracle/tscnet_oracle.predict) on the host cores."""
-    from oracle import tscnet_oracle as O, weights
+    from oracle import tscnet_oracle as O
+    import synth as weights
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd = weights.synth_state_dict(0)
@@ -155,7 +156,7 @@ def run_b200(args):
 
     import se_b200
     from se_b200 import ops
-    from oracle import weights
+    import synth as weights
 
     model = se_b200.TSCNet(num_channel=64, num_features=201)
     model.load_state_dict(weights.synth_state_dict(0))
@@ -302,7 +303,7 @@ def run_job(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     import se_b200
-    from oracle import weights
+    import synth as weights
     model = se_b200.TSCNet(num_channel=64, num_features=201)
     model.load_state_dict(weights.synth_state_dict(0))
     model = model.to(dev).eval()

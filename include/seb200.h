@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SEB200_ABI_VERSION 1
+#define SEB200_ABI_VERSION 2
 
 enum {
   SEB_OK = 0,
@@ -177,7 +177,6 @@ typedef struct SebSeq { int nseq, n, inner; long long outer_stride, pos_stride; 
  *   variant 3 (tcgen05): same inputs as variant 0.  S = Q K^T (fp32) and R = Q E_window^T (fp16) accumulate in tensor memory,
  *                        the per-row skew of R goes through thread-private shared-memory rows, P is the TMEM A operand of
  *                        the P V product; key tiles beyond the +-512 clamp skip the rel-pos GEMM (attention_tc.cu)
- *   variant 2: the round-1 tensor-core kernel (fp32 skew staging), same inputs as variant 0 except that rel_pos_emb_h is in natural k order; kept for A/B measurements;
  *   variant 1 (fp32 SIMT cross-check): qkv is float, unscaled; rel_pos_emb [1025, 16] fp32 */
 int seb200_attention(const void* qkv, const float* rel_pos_emb, const void* rel_pos_emb_h, const SebSeq* seq, float* out,
                      int variant, void* stream);
@@ -185,12 +184,6 @@ int seb200_attention(const void* qkv, const float* rel_pos_emb, const void* rel_
  * x, y [tokens, 128]; w [31][128] (tap-major); bn_scale/bn_shift fold conv bias, running stats and affine */
 int seb200_dwconv_bn_swish(const float* x, const SebSeq* seq, const float* w, const float* bn_scale,
                            const float* bn_shift, float* y, void* stream);
-/* The same depthwise stage fused with the pointwise Conv1d(128 -> 64) that follows it and the block residual
- * (conformer.py:166-169, 204):  out = resid + W3 . Swish(BN(DWConv31(u))) + b3.   u: [tokens, 128] fp32 (GLU output),
- * w3_tc: tcgen05 image of W3 [64, 128] packed with n-tile 64 (packing.py), resid / out: [tokens, 64] fp32 (out may alias
- * resid).  The depthwise result goes straight into the MMA operand tile in shared memory; it is never written to HBM. */
-int seb200_dwconv_pw2(const float* u, const SebSeq* seq, const float* w, const float* bn_scale, const float* bn_shift,
-                      const void* w3_tc, const float* b3, const float* resid, float* out, void* stream);
 /* post_norm + the TSCB outer residual (conformer.py:211, generator.py:70,72): out = LN(x) * g + b + resid */
 int seb200_layernorm_residual(const float* x, long long tokens, const float* gamma, const float* beta,
                               const float* resid, float* out, void* stream);

@@ -59,6 +59,7 @@ def main():
         print(name, "enhanced peak", float(np.abs(enhanced).max()))
     default_init_golden(ref, out_dir)
     diffusion_golden(ref, out_dir)
+    train_golden(ref, out_dir)
 
 
 def default_init_golden(ref, out_dir):
@@ -135,5 +136,121 @@ def reverse_golden(ref, out_dir, sd, model):
     print(case["name"], "T", T, "enhanced peak", float(np.abs(y).max()))
 
 
+# ---- long clips (BASELINE configs[2]: 30 s, T = 4801; and 10 s, T = 1001, both clamp sides active inside one sequence) --------
+LONG_CASES = [
+    # name, length, wave seed, weight seed
+    ("long_b1_L100000", 100000, 21, 0),
+    ("long_b1_L480000", 480000, 99, 1),
+]
+
+
+def _chunked_tscb_forward(self, x_in, chunk=8):
+    """TSCB.forward (generator.py:67-74) with the reference's OWN time / frequency ConformerBlock modules driven over chunks of
+    <= `chunk` sequences: in eval mode every (b, f) / (b, t) sequence is independent through a ConformerBlock (BatchNorm uses
+    running statistics; tests/test_oracle.py checks this), and the un-chunked call would materialise 3 x (101, 4, 4801, 4801)
+    score tensors (110 GB) at 30 s."""
+    b, c, t, f = x_in.size()
+    x_t = x_in.permute(0, 3, 2, 1).contiguous().view(b * f, t, c)
+    x_t = torch.cat([self.time_conformer(x_t[i:i + chunk]) for i in range(0, b * f, chunk)], dim=0) + x_t
+    x_f = x_t.view(b, f, t, c).permute(0, 2, 1, 3).contiguous().view(b * t, f, c)
+    x_f = torch.cat([self.freq_conformer(x_f[i:i + 256]) for i in range(0, b * t, 256)], dim=0) + x_f
+    return x_f.view(b, t, f, c).permute(0, 3, 1, 2)
+
+
+def long_golden(ref, out_dir, only=None):
+    """the reference's predict() on one long clip; only the enhanced waveform is stored (the input is re-made from the seeds)"""
+    import time
+    import types
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    for name, L, wseed, sseed in LONG_CASES:
+        if only and name not in only:
+            continue
+        t0 = time.time()
+        model = ref.TSCNet(num_channel=64, num_features=201)
+        model.load_state_dict(weights.synth_state_dict(sseed), strict=True)
+        model.eval()
+        for k in range(1, 5):
+            blk = getattr(model, f"TSCB_{k}")
+            blk.forward = types.MethodType(_chunked_tscb_forward, blk)
+        noisy, _ = weights.synth_wave(1, L, wseed, "speech")
+        enhanced = ref.predict(model, ref.config, noisy[0].numpy(), device=torch.device("cpu"))
+        np.savez_compressed(os.path.join(out_dir, name + ".npz"), enhanced=enhanced.astype(np.float32)[None],
+                            weight_seed=np.int64(sseed), wave_seed=np.int64(wseed), length=np.int64(L))
+        print(name, "enhanced peak", float(np.abs(enhanced).max()), f"{time.time() - t0:.0f} s", flush=True)
+
+
+# ---- train mode (SURVEY 8f row f1): the reference's TSCNet under .train() with its nn.Dropout modules patched to fixed masks ----------
+TRAIN_CASE = dict(name="train_b2_L10000", batch=2, length=10000, wave_seed=41, weight_seed=4, mask_seed=7, cot_seed=1)
+
+
+def _patch_dropouts(model, masks_ref, p=0.2):
+    """replace the forward of every active nn.Dropout of the reference model by x * mask / (1 - p) with the injected mask"""
+    name_of = {}
+    for i in range(1, 5):
+        for ax in ("time", "freq"):
+            q = f"TSCB_{i}.{ax}_conformer"
+            name_of[f"{q}.ff1.fn.fn.net.2"] = f"{q}.ff1.drop1"; name_of[f"{q}.ff1.fn.fn.net.4"] = f"{q}.ff1.drop2"
+            name_of[f"{q}.ff2.fn.fn.net.2"] = f"{q}.ff2.drop1"; name_of[f"{q}.ff2.fn.fn.net.4"] = f"{q}.ff2.drop2"
+            name_of[f"{q}.attn.fn.dropout"] = f"{q}.attn.drop"
+    seen = 0
+    for name, mod in model.named_modules():
+        if isinstance(mod, torch.nn.Dropout) and mod.p > 0:
+            site = name_of[name]
+            mod.forward = (lambda m: (lambda x: x * m.to(x.dtype) * (1.0 / (1.0 - p))))(masks_ref[site])
+            seen += 1
+    assert seen == len(name_of) == 40, seen
+
+
+def train_golden(ref, out_dir):
+    """The unmodified reference TSCNet under .train() with injected dropout masks, twice: in float32 (what main_gan.py runs) and in
+    float64 (`model.double()`, the same modules: the truth the float32 run is an approximation of).  Stored: the compressed spectrogram
+    fed to the model (every implementation under test starts from these bits), the train-mode outputs and the BatchNorm buffers after
+    the step (float32 run), the gradient of sum(final_real * g_r + final_imag * g_i) for all 335 parameters from the FLOAT64 run
+    (rounded to float32), and per parameter the rel-L2 distance of the reference's own float32 gradient from it (`ref32_err:`).
+    Why both: this random-weight network amplifies perturbations ~100x from input to gradient (a 1e-5 change of the spectrogram moves
+    gradients by 1e-3), so two correct float32 implementations differ by a few 1e-3; the float64 run is the common yardstick."""
+    c = TRAIN_CASE
+    sd = weights.synth_state_dict(c["weight_seed"])
+    noisy, _ = weights.synth_wave(c["batch"], c["length"], c["wave_seed"], "speech")
+    cfac = torch.sqrt(noisy.shape[-1] / torch.sum(noisy ** 2.0, dim=-1, keepdim=True))
+    spec = ref.compressed_stft(noisy * cfac, 400, 100, torch.hamming_window(400))
+    B, _, T = spec.shape
+    masks = weights.masks_reference_layout(weights.dropout_masks(c["mask_seed"], B, T, 101))
+    gr, gi = weights.cotangents(c["cot_seed"], B, T)
+
+    def run(dt):
+        model = ref.TSCNet(num_channel=64, num_features=201)
+        model.load_state_dict(sd, strict=True)
+        model.train()
+        model = model.to(dt)
+        _patch_dropouts(model, masks)
+        fr, fi = model(spec.to(torch.complex128 if dt == torch.float64 else torch.complex64))
+        ((fr * gr.to(dt)).sum() + (fi * gi.to(dt)).sum()).backward()
+        return model, fr.detach(), fi.detach()
+
+    m32, fr, fi = run(torch.float32)
+    m64, fr64, _ = run(torch.float64)
+    out = {"spec_real": spec.real.numpy(), "spec_imag": spec.imag.numpy(), "final_real": fr.numpy(), "final_imag": fi.numpy()}
+    for k, v in m32.state_dict().items():
+        if "running_" in k or "num_batches" in k:
+            out["buf:" + k] = v.numpy()
+    p32 = dict(m32.named_parameters())
+    worst = 0.0
+    for k, prm in m64.named_parameters():
+        t = prm.grad
+        out["grad:" + k] = t.to(torch.float32).numpy()
+        e = float((p32[k].grad.double() - t).norm() / t.norm().clamp_min(1e-300))
+        out["ref32_err:" + k] = np.float32(e)
+        if not weights.has_zero_gradient(k):
+            worst = max(worst, e)
+    np.savez_compressed(os.path.join(out_dir, c["name"] + ".npz"), **out, **{k: np.int64(v) for k, v in c.items() if k != "name"})
+    print(c["name"], "335 gradients; reference float32 vs float64: worst rel-L2", worst, "forward", float((fr.double() - fr64).abs().max() / fr64.abs().max()))
+
+
 if __name__ == "__main__":
-    main()
+    if "--train" in sys.argv:
+        train_golden(ref_import.load(), os.path.join(ROOT, "tests", "golden"))
+    elif "--long" in sys.argv:
+        long_golden(ref_import.load(), os.path.join(ROOT, "tests", "golden"), only=[a for a in sys.argv[1:] if not a.startswith("--")])
+    else:
+        main()

@@ -80,7 +80,7 @@ def power_uncompress(spec: torch.Tensor) -> torch.Tensor:
 def compressed_stft(x: torch.Tensor, n_fft: int = N_FFT, hop: int = HOP,
                     window: Optional[torch.Tensor] = None) -> torch.Tensor:
     """(B, L) fp32 -> complex64 (B, n_fft/2+1, T).  core/function.py:685-693."""
-    w = hamming_periodic(n_fft) if window is None else window
+    w = hamming_periodic(n_fft).to(x.device) if window is None else window
     fr = stft_frames(x, n_fft, hop) * w
     spec = torch.fft.rfft(fr, dim=-1).transpose(1, 2)
     return power_compress(spec)
@@ -103,17 +103,21 @@ def uncompressed_istft(spec: torch.Tensor, n_fft: int = N_FFT, hop: int = HOP,
     """complex64 (B, F, T) -> (B, hop*(T-1)).  core/function.py:695-703:
     decompress, irfft, synthesis window, overlap-add, divide by the squared
     window envelope, trim n_fft/2 at both ends (torch.istft, center=True)."""
-    w = hamming_periodic(n_fft) if window is None else window
+    w = hamming_periodic(n_fft).to(spec.device) if window is None else window
     z = power_uncompress(spec)
     B, _, T = z.shape
     fr = torch.fft.irfft(z.transpose(1, 2), n=n_fft, dim=-1) * w      # (B, T, n_fft)
     full = n_fft + hop * (T - 1)
-    y = torch.zeros(B, full, dtype=fr.dtype)
-    env = torch.zeros(full, dtype=fr.dtype)
+    y = torch.zeros(B, full, dtype=fr.dtype, device=fr.device)
+    env = torch.zeros(full, dtype=fr.dtype, device=fr.device)
     w2 = w * w
-    for t in range(T):
-        y[:, t * hop:t * hop + n_fft] += fr[:, t]
-        env[t * hop:t * hop + n_fft] += w2
+    if fr.is_cuda:       # what torch.istft does: one col2im (bench.py's informational GPU-eager leg; a T-iteration loop would be launch-bound)
+        y = F.fold(fr.transpose(1, 2), (1, full), (1, n_fft), stride=(1, hop)).reshape(B, full)
+        env = F.fold(w2.expand(1, T, n_fft).transpose(1, 2), (1, full), (1, n_fft), stride=(1, hop)).reshape(full)
+    else:
+        for t in range(T):
+            y[:, t * hop:t * hop + n_fft] += fr[:, t]
+            env[t * hop:t * hop + n_fft] += w2
     half = n_fft // 2
     return y[:, half:full - half] / env[half:full - half]
 
@@ -161,19 +165,41 @@ def _swish(x):
     return x * torch.sigmoid(x)
 
 
-def feed_forward(x, sd: SD, p: str):
-    """Scale(0.5, PreNorm(FeedForward))  models/conformer.py:53-71,128-145 (eval: dropout off)."""
+class TrainCtx:
+    """Train-mode semantics of the generator (core/function.py:218-229 runs model(noisy_spec) under model.train()):
+    * ``masks[site]``: the keep-mask (bool / 0-1, the shape of the dropped tensor) of every nn.Dropout(p=0.2) on the path --
+      ``<conformer>.ff{1,2}.drop1`` after the Swish (conformer.py:139), ``.drop2`` after the second Linear (:141), ``<conformer>.attn.drop``
+      on the projected attention output (:125); kept values are scaled by 1 / (1 - p) as nn.Dropout does.  The masks are INJECTED
+      so that the reference, this restatement and the CUDA path see the same draw.
+    * BatchNorm1d (conformer.py:167) uses batch statistics (biased variance) and updates ``running[<conv>.net.5.running_mean / _var]``
+      with momentum 0.1 and the UNBIASED variance, ``num_batches_tracked`` += 1 -- collected in ``running`` instead of mutating sd."""
+
+    def __init__(self, masks, p: float = 0.2):
+        self.masks, self.p, self.running = masks, p, {}
+
+    def drop(self, x, site):
+        return x * self.masks[site].to(x.dtype) * (1.0 / (1.0 - self.p))
+
+
+def feed_forward(x, sd: SD, p: str, tr: Optional[TrainCtx] = None):
+    """Scale(0.5, PreNorm(FeedForward))  models/conformer.py:53-71,128-145 (eval: dropout off; train: two dropouts)."""
     h = _ln(x, sd, p + ".fn.norm")
     h = F.linear(h, sd[p + ".fn.fn.net.0.weight"], sd[p + ".fn.fn.net.0.bias"])
     h = _swish(h)
+    if tr is not None:
+        h = tr.drop(h, p + ".drop1")
     h = F.linear(h, sd[p + ".fn.fn.net.3.weight"], sd[p + ".fn.fn.net.3.bias"])
+    if tr is not None:
+        h = tr.drop(h, p + ".drop2")
     return 0.5 * h
 
 
-def attention(x, sd: SD, p: str, chunk: int = 0):
+def attention(x, sd: SD, p: str, chunk: int = 0, tr: Optional[TrainCtx] = None):
     """PreNorm(Attention) with Shaw relative positions  models/conformer.py:96-125.
     x: (S, n, 64).  ``chunk`` > 0 evaluates the S sequences in groups (the
     sequences are independent) to bound the (S, h, n, n) memory."""
+    if tr is not None:
+        return tr.drop(attention(x, sd, p, chunk), p + ".drop")       # conformer.py:125: dropout on the projected output only
     if chunk and x.shape[0] > chunk:
         return torch.cat([attention(x[i:i + chunk], sd, p) for i in range(0, x.shape[0], chunk)], 0)
     S, n, _ = x.shape
@@ -185,7 +211,7 @@ def attention(x, sd: SD, p: str, chunk: int = 0):
     q, k, v = split(q), split(k), split(v)
     scale = DIM_HEAD ** -0.5
     dots = torch.matmul(q, k.transpose(-1, -2)) * scale
-    pos = torch.arange(n)
+    pos = torch.arange(n, device=x.device)
     dist = (pos[:, None] - pos[None, :]).clamp(-MAX_POS, MAX_POS) + MAX_POS
     rel = sd[p + ".fn.rel_pos_emb.weight"][dist]                          # (n, n, d)
     dots = dots + torch.einsum("bhnd,nrd->bhnr", q, rel) * scale
@@ -194,8 +220,8 @@ def attention(x, sd: SD, p: str, chunk: int = 0):
     return F.linear(o, sd[p + ".fn.to_out.weight"], sd[p + ".fn.to_out.bias"])
 
 
-def conv_module(x, sd: SD, p: str):
-    """ConformerConvModule (eval)  models/conformer.py:161-172."""
+def conv_module(x, sd: SD, p: str, tr: Optional[TrainCtx] = None):
+    """ConformerConvModule  models/conformer.py:161-172 (eval: running statistics; train: batch statistics + running update)."""
     h = _ln(x, sd, p + ".net.0").transpose(1, 2)                           # b c n
     h = F.conv1d(h, sd[p + ".net.2.weight"], sd[p + ".net.2.bias"])
     a, g = h.chunk(2, dim=1)
@@ -203,29 +229,35 @@ def conv_module(x, sd: SD, p: str):
     ks = sd[p + ".net.4.conv.weight"].shape[-1]
     h = F.pad(h, (ks // 2, ks // 2 - (ks + 1) % 2))
     h = F.conv1d(h, sd[p + ".net.4.conv.weight"], sd[p + ".net.4.conv.bias"], groups=h.shape[1])
-    h = F.batch_norm(h, sd[p + ".net.5.running_mean"], sd[p + ".net.5.running_var"],
-                     sd[p + ".net.5.weight"], sd[p + ".net.5.bias"], False, 0.0, 1e-5)
+    if tr is None:
+        h = F.batch_norm(h, sd[p + ".net.5.running_mean"], sd[p + ".net.5.running_var"],
+                         sd[p + ".net.5.weight"], sd[p + ".net.5.bias"], False, 0.0, 1e-5)
+    else:
+        rm, rv = sd[p + ".net.5.running_mean"].detach().clone(), sd[p + ".net.5.running_var"].detach().clone()
+        h = F.batch_norm(h, rm, rv, sd[p + ".net.5.weight"], sd[p + ".net.5.bias"], True, 0.1, 1e-5)
+        tr.running[p + ".net.5.running_mean"], tr.running[p + ".net.5.running_var"] = rm, rv
+        tr.running[p + ".net.5.num_batches_tracked"] = sd[p + ".net.5.num_batches_tracked"] + 1
     h = _swish(h)
     h = F.conv1d(h, sd[p + ".net.7.weight"], sd[p + ".net.7.bias"])
     return h.transpose(1, 2)
 
 
-def conformer_block(x, sd: SD, p: str, chunk: int = 0):
+def conformer_block(x, sd: SD, p: str, chunk: int = 0, tr: Optional[TrainCtx] = None):
     """ConformerBlock.forward  models/conformer.py:206-212."""
-    x = feed_forward(x, sd, p + ".ff1") + x
-    x = attention(x, sd, p + ".attn", chunk) + x
-    x = conv_module(x, sd, p + ".conv") + x
-    x = feed_forward(x, sd, p + ".ff2") + x
+    x = feed_forward(x, sd, p + ".ff1", tr) + x
+    x = attention(x, sd, p + ".attn", chunk, tr) + x
+    x = conv_module(x, sd, p + ".conv", tr) + x
+    x = feed_forward(x, sd, p + ".ff2", tr) + x
     return _ln(x, sd, p + ".post_norm")
 
 
-def tscb(x, sd: SD, p: str, chunk: int = 0):
+def tscb(x, sd: SD, p: str, chunk: int = 0, tr: Optional[TrainCtx] = None):
     """TSCB.forward  models/generator.py:67-74.  x: (B, C, T, F)."""
     b, c, t, f = x.shape
     xt = x.permute(0, 3, 2, 1).reshape(b * f, t, c)
-    xt = conformer_block(xt, sd, p + ".time_conformer", chunk) + xt
+    xt = conformer_block(xt, sd, p + ".time_conformer", chunk, tr) + xt
     xf = xt.reshape(b, f, t, c).permute(0, 2, 1, 3).reshape(b * t, f, c)
-    xf = conformer_block(xf, sd, p + ".freq_conformer", chunk) + xf
+    xf = conformer_block(xf, sd, p + ".freq_conformer", chunk, tr) + xf
     return xf.reshape(b, t, f, c).permute(0, 3, 1, 2)
 
 
@@ -257,10 +289,11 @@ def complex_decoder(x, sd: SD, p: str = "complex_decoder"):
     return F.conv2d(h, sd[p + ".conv.weight"], sd[p + ".conv.bias"])
 
 
-def tscnet_forward(spec: torch.Tensor, sd: SD, chunk: int = 0, stages: Optional[dict] = None):
+def tscnet_forward(spec: torch.Tensor, sd: SD, chunk: int = 0, stages: Optional[dict] = None, tr: Optional[TrainCtx] = None):
     """TSCNet.forward  models/generator.py:145-167.
     spec: complex64 (B, 201, T) -> (final_real, final_imag), each (B, 1, T, 201).
-    If ``stages`` is a dict, per-stage tensors are stored in it (reference layout)."""
+    If ``stages`` is a dict, per-stage tensors are stored in it (reference layout).  ``tr``: train-mode semantics (TrainCtx);
+    InstanceNorm2d keeps no running statistics, so only the conformers differ between train and eval."""
     mag = spec.abs().unsqueeze(1).permute(0, 1, 3, 2)
     ph = spec.angle().unsqueeze(1).permute(0, 1, 3, 2)
     x_in = torch.cat([mag, spec.real.unsqueeze(1).permute(0, 1, 3, 2),
@@ -270,7 +303,7 @@ def tscnet_forward(spec: torch.Tensor, sd: SD, chunk: int = 0, stages: Optional[
         stages["x_in"] = x_in
         stages["encoder"] = h
     for i in range(1, 5):
-        h = tscb(h, sd, f"TSCB_{i}", chunk)
+        h = tscb(h, sd, f"TSCB_{i}", chunk, tr)
         if stages is not None:
             stages[f"tscb{i}"] = h
     mask = mask_decoder(h, sd)

@@ -17,6 +17,7 @@ _LIB_PATH = os.path.join(_HERE, "libseb200.so")
 LOAD_ROWS, LOAD_ROWS_LN, LOAD_CONV, LOAD_HANKEL, LOAD_CONV_SPLIT, LOAD_ROWS2 = 0, 1, 2, 3, 4, 5
 EPI_BIAS, EPI_SWISH, EPI_GLU, EPI_RESID, EPI_SUBPIXEL, EPI_COMPRESS, EPI_QKV_F16, EPI_GATE, EPI_RESID_SCALE = 0, 1, 2, 3, 4, 5, 6, 7, 8
 ENGINE_TCGEN05, ENGINE_SIMT = 0, 1
+ABI_VERSION = 2          # SEB200_ABI_VERSION in include/seb200.h
 
 _fp = C.c_void_p  # raw device pointers travel as void*
 
@@ -69,7 +70,6 @@ _SIGS = {
     "seb200_split_ri": [_fp, C.c_longlong, _fp, _fp, _fp],
     "seb200_attention": [_fp, _fp, _fp, C.POINTER(SebSeq), _fp, C.c_int, _fp],
     "seb200_dwconv_bn_swish": [_fp, C.POINTER(SebSeq), _fp, _fp, _fp, _fp, _fp],
-    "seb200_dwconv_pw2": [_fp, C.POINTER(SebSeq), _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp],
     "seb200_layernorm_residual": [_fp, C.c_longlong, _fp, _fp, _fp, _fp, _fp],
     "seb200_packed_weight_sizes": [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_int),
                                    C.POINTER(C.c_int), C.POINTER(C.c_int)],
@@ -98,12 +98,16 @@ def load(build_if_missing: bool = True):
     with _lock:
         if _lib is not None:
             return _lib
+        from . import build as _build
+        if build_if_missing and _build.have_nvcc():
+            _build.build()          # no-op when the source digest matches the stamp; rebuilds a stale library after any csrc / header edit
         if not os.path.exists(_LIB_PATH):
-            if not build_if_missing:
-                raise RuntimeError(f"{_LIB_PATH} is missing: run `python speech-enhancement_b200/build.py`")
-            from . import build as _build
-            _build.build()
+            raise RuntimeError(f"{_LIB_PATH} is missing and cannot be built here: run `python speech-enhancement_b200/build.py`")
         lib = C.CDLL(_LIB_PATH)
+        lib.seb200_version.restype = C.c_int
+        if lib.seb200_version() != ABI_VERSION:
+            raise RuntimeError(f"{_LIB_PATH} reports ABI version {lib.seb200_version()}, this binding expects {ABI_VERSION}: rebuild "
+                               "(`python speech-enhancement_b200/build.py --force`)")
         for name, args in _SIGS.items():
             fn = getattr(lib, name)
             fn.argtypes = args

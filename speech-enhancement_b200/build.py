@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libseb200.so")
 OBJ_DIR = os.path.join(CSRC, "build")
-SOURCES = ["core.cu", "gemm_api.cu", "tok_gemm.cu", "conv_y3.cu", "conv_persist.cu", "conv_tap.cu", "ffn_fused.cu", "dsp.cu", "norm_act.cu", "attention.cu", "attention_tc.cu", "dwconv.cu", "dwpw2.cu", "merge.cu", "pack.cu", "dsp_bwd.cu"]
+SOURCES = ["core.cu", "gemm_api.cu", "tok_gemm.cu", "conv_y3.cu", "conv_persist.cu", "ffn_fused.cu", "dsp.cu", "norm_act.cu", "attention.cu", "attention_tc.cu", "dwconv.cu", "merge.cu", "pack.cu", "dsp_bwd.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 NVCC_FLAGS += os.environ.get("SEB200_NVCC_EXTRA", "").split()      # experiment switches (-DSEB_...=n); part of the build digest
@@ -29,6 +29,12 @@ def _nvcc() -> str:
         if c and (os.path.isabs(c) and os.path.exists(c) or not os.path.isabs(c)):
             return c
     return "nvcc"
+
+
+def have_nvcc() -> bool:
+    import shutil
+    c = _nvcc()
+    return os.path.exists(c) if os.path.isabs(c) else shutil.which(c) is not None
 
 
 def _digest() -> str:

@@ -154,222 +154,9 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_b
 // BAND = true (long sequences, n > ~1100): key tiles whose offsets i - j all lie beyond +-512 see ONE embedding row
 // (conformer.py:108 clamps the distance), so their rel-pos logit is a per-query constant q_i . E[0] or q_i . E[1024]:
 // the score accumulators start from that constant and the R GEMM + skew are skipped (78 % of the tiles at T = 4801).
-template <bool BAND>
-__global__ void __launch_bounds__(128, 3) attention_f16_kernel(const __half* __restrict__ qkvh, const __half* __restrict__ Eh,
-                                                              const SebSeq sq, int nqb, float* __restrict__ out) {
-  extern __shared__ __align__(16) unsigned char smraw[];
-  __shared__ uint64_t full_bar[A2_STAGES], empty_bar[A2_STAGES];
-  __half* KV = reinterpret_cast<__half*>(smraw);                       // [stage][K | V][64][24]
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  float* Rs = reinterpret_cast<float*>(KV + A2_STAGES * 2 * A2_TILE_H) + warp * A2_WROWS * A2_RLD;   // [32][104] per warp
-  const int sh = blockIdx.x / nqb, qb = blockIdx.x - sh * nqb;
-  const int seq = sh >> 2, h = sh & 3;
-  const int n = sq.n;
-  const long long base = seq_base(sq, seq);
-  const __half* hbase = qkvh + h * AT_D;
-  const int iw = (qb * 4 + warp) * A2_WROWS;          // first query row of this warp
-  const bool warp_live = iw < n;
-
-  // K/V tile loader: 64 keys x (2 + 2) 16-byte chunks, 2 cp.async per thread; keys past the sequence are zero-filled
-  // The ring is mbarrier-driven (no CTA-wide barrier per tile): every thread's cp.asyncs arrive on full[stage] when they
-  // land, every warp arrives on empty[stage] when it has finished reading, so warps may drift apart by up to a tile.
-  if (tid == 0) {
-    for (int i = 0; i < A2_STAGES; ++i) { ptx::mbar_init(&full_bar[i], 128); ptx::mbar_init(&empty_bar[i], 4); }
-    ptx::fence_barrier_init();
-  }
-  __syncthreads();
-  auto issue_tile = [&](int tile) {
-    const int stage = tile % A2_STAGES;
-    __half* dstb = KV + stage * 2 * A2_TILE_H;
-#pragma unroll
-    for (int rep = 0; rep < 2; ++rep) {
-      const int idx = tid + rep * 128, key = idx >> 2, c = idx & 3;
-      const int j = tile * A2_BK + key;
-      const int jj = j < n ? j : n - 1;
-      const __half* src = hbase + (base + (long long)jj * sq.pos_stride) * AT_ROWH + 64 + (c >> 1) * 64 + (c & 1) * 8;
-      cp_async16(dstb + (c >> 1) * A2_TILE_H + key * A2_LD + (c & 1) * 8, src, j < n ? 16 : 0);
-    }
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(ptx::smem_u32(&full_bar[stage])) : "memory");
-  };
-  const int ntiles = (n + A2_BK - 1) / A2_BK;
-  issue_tile(0);
-  if (ntiles > 1) issue_tile(1);
-
-  // Q fragments (already scaled by dim_head^-0.5 * log2(e) and rounded to fp16 by the projection epilogue)
-  uint32_t qa[2][4];
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt) {
-    int r0 = iw + mt * 16 + g, r1 = r0 + 8;
-    r0 = r0 < n ? r0 : n - 1;
-    r1 = r1 < n ? r1 : n - 1;
-    const uint32_t* q0 = reinterpret_cast<const uint32_t*>(hbase + (base + (long long)r0 * sq.pos_stride) * AT_ROWH) + t;
-    const uint32_t* q1 = reinterpret_cast<const uint32_t*>(hbase + (base + (long long)r1 * sq.pos_stride) * AT_ROWH) + t;
-    qa[mt][0] = __ldg(q0); qa[mt][1] = __ldg(q1); qa[mt][2] = __ldg(q0 + 4); qa[mt][3] = __ldg(q1 + 4);
-  }
-  // o[mt][0..1]: output columns 0-7 / 8-15; o[mt][2]: a ones column appended to V, so column 0 carries sum_j p_ij
-  float o[2][3][4];
-  float mrow[2][2];
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt) {
-    mrow[mt][0] = mrow[mt][1] = -1e30f;
-#pragma unroll
-    for (int x = 0; x < 3; ++x)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) o[mt][x][e] = 0.f;
-  }
-  const uint32_t ones = (g == 0) ? 0x3C003C00u : 0u;
-  float c_far[2][2][2];        // [far side: 0 = offsets <= -512 (E[0]), 1 = offsets >= +512 (E[1024])][mt][row g / g+8]
-  if (BAND) {
-#pragma unroll
-    for (int side = 0; side < 2; ++side) {
-      const uint32_t* er = reinterpret_cast<const uint32_t*>(Eh + side * (2 * AT_MAXPOS) * AT_D) + t;
-      const uint32_t e0 = __ldg(er), e1 = __ldg(er + 4);            // every B column is the same embedding row
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        float r4[4] = {0.f, 0.f, 0.f, 0.f};
-        mma_f16(r4, qa[mt], e0, e1);
-        c_far[side][mt][0] = r4[0]; c_far[side][mt][1] = r4[2];
-      }
-    }
-  }
-  // ldmatrix lane addressing (in halfs, relative to a tile): matrix i = lane >> 3, row = lane & 7
-  const int lm_i = lane >> 3, lm_r = lane & 7;
-  const int k_off = ((lm_i >> 1) * 8 + lm_r) * A2_LD + (lm_i & 1) * 8;        // K: (n-tile pair, d half)
-  const int v_off = ((lm_i & 1) * 8 + lm_r) * A2_LD + (lm_i >> 1) * 8;        // V (transposed load): (key half, d half)
-
-  for (int tile = 0; tile < ntiles; ++tile) {
-    const int stage = tile % A2_STAGES;
-    if (tile + 2 < ntiles) {        // refill the stage that tile - 1 used, once all four warps have released it
-      if (tile >= 1) ptx::mbar_wait(&empty_bar[(tile + 2) % A2_STAGES], (uint32_t)((tile - 1) / A2_STAGES) & 1u);
-      issue_tile(tile + 2);
-    }
-    ptx::mbar_wait(&full_bar[stage], (uint32_t)(tile / A2_STAGES) & 1u);
-    const int j0 = tile * A2_BK;
-    const __half* Ks = KV + stage * 2 * A2_TILE_H;
-    const __half* Vs = Ks + A2_TILE_H;
-    if (warp_live) {
-
-    // ---- content scores: S[mt] = Q[mt] K^T  (16 x 64 each), started from the far-field rel-pos constant when BAND applies
-    const int dlo = iw - j0 - 64;                 // offsets i - j of this warp tile span [dlo + 1, dlo + 95]
-    const int far = !BAND ? -1 : (dlo + 1 >= AT_MAXPOS ? 1 : (dlo + 95 <= -AT_MAXPOS ? 0 : -1));
-    float s[2][8][4];
-#pragma unroll
-    for (int np = 0; np < 4; ++np) {
-      uint32_t kb[4];
-      ldsm_x4(kb, Ks + np * 16 * A2_LD + k_off);
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float c0 = !BAND ? 0.f : (far == 1 ? c_far[1][mt][e >> 1] : (far == 0 ? c_far[0][mt][e >> 1] : 0.f));
-          s[mt][2 * np][e] = c0; s[mt][2 * np + 1][e] = c0;
-        }
-        mma_f16(s[mt][2 * np], qa[mt], kb[0], kb[1]);
-        mma_f16(s[mt][2 * np + 1], qa[mt], kb[2], kb[3]);
-      }
-    }
-    if (!BAND || far < 0) {
-    // ---- relative-position scores: R[r, dd] = q_r . E[clamp(dlo + dd)], dd in [0, 96)
-#pragma unroll
-    for (int nt = 0; nt < 12; ++nt) {
-      int d = dlo + nt * 8 + g;
-      d = d < -AT_MAXPOS ? -AT_MAXPOS : (d > AT_MAXPOS ? AT_MAXPOS : d);
-      const uint32_t* er = reinterpret_cast<const uint32_t*>(Eh + (d + AT_MAXPOS) * AT_D) + t;
-      const uint32_t e0 = __ldg(er), e1 = __ldg(er + 4);
-      if (nt < 10) {        // rows 0..15 use offsets 1..79
-        float r4[4] = {0.f, 0.f, 0.f, 0.f};
-        mma_f16(r4, qa[0], e0, e1);
-        *reinterpret_cast<float2*>(Rs + g * A2_RLD + nt * 8 + 2 * t) = make_float2(r4[0], r4[1]);
-        *reinterpret_cast<float2*>(Rs + (g + 8) * A2_RLD + nt * 8 + 2 * t) = make_float2(r4[2], r4[3]);
-      }
-      if (nt >= 2) {        // rows 16..31 use offsets 17..95
-        float r4[4] = {0.f, 0.f, 0.f, 0.f};
-        mma_f16(r4, qa[1], e0, e1);
-        *reinterpret_cast<float2*>(Rs + (16 + g) * A2_RLD + nt * 8 + 2 * t) = make_float2(r4[0], r4[1]);
-        *reinterpret_cast<float2*>(Rs + (24 + g) * A2_RLD + nt * 8 + 2 * t) = make_float2(r4[2], r4[3]);
-      }
-    }
-    __syncwarp();
-    // ---- skew: S[r, c] += R[r, 64 + r - c]  (initialising the accumulators from R instead was measured slower: it
-    //      puts the shared-memory round trip in front of the content MMAs)
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int r = mt * 16 + g + ((e >> 1) << 3), c = nt * 8 + 2 * t + (e & 1);
-          s[mt][nt][e] += Rs[r * A2_RLD + 64 + r - c];
-        }
-    __syncwarp();
-    }   // in-band tile
-    if (j0 + A2_BK > n) {   // mask keys beyond the sequence (last tile only)
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (j0 + nt * 8 + 2 * t + (e & 1) >= n) s[mt][nt][e] = -1e30f;
-    }
-    // ---- online softmax (base-2); the row sums come out of the P V product (ones column)
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-      for (int rh = 0; rh < 2; ++rh) {
-        float mx = -1e30f;
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) mx = fmaxf(mx, fmaxf(s[mt][nt][2 * rh], s[mt][nt][2 * rh + 1]));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-        const float mn = fmaxf(mrow[mt][rh], mx);
-        const float corr = ex2_approx(mrow[mt][rh] - mn);
-        mrow[mt][rh] = mn;
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-          s[mt][nt][2 * rh] = ex2_approx(s[mt][nt][2 * rh] - mn);
-          s[mt][nt][2 * rh + 1] = ex2_approx(s[mt][nt][2 * rh + 1] - mn);
-        }
-#pragma unroll
-        for (int x = 0; x < 3; ++x) { o[mt][x][2 * rh] *= corr; o[mt][x][2 * rh + 1] *= corr; }
-      }
-    // ---- O += P [V | 1]  (k = 16 keys per step; C fragments of two adjacent S n-tiles form one A fragment)
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      uint32_t vb[4];
-      ldsm_x4_trans(vb, Vs + ks * 16 * A2_LD + v_off);
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        const uint32_t pa[4] = {pack_h2(s[mt][2 * ks][0], s[mt][2 * ks][1]), pack_h2(s[mt][2 * ks][2], s[mt][2 * ks][3]),
-                                pack_h2(s[mt][2 * ks + 1][0], s[mt][2 * ks + 1][1]), pack_h2(s[mt][2 * ks + 1][2], s[mt][2 * ks + 1][3])};
-        mma_f16(o[mt][0], pa, vb[0], vb[1]);
-        mma_f16(o[mt][1], pa, vb[2], vb[3]);
-        mma_f16(o[mt][2], pa, ones, ones);
-      }
-    }
-    }   // warp_live
-    __syncwarp();
-    if (lane == 0) ptx::mbar_arrive(&empty_bar[stage]);
-  }
-  if (!warp_live) return;
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int rh = 0; rh < 2; ++rh) {
-      const float l = __shfl_sync(0xffffffffu, o[mt][2][2 * rh], lane & ~3);   // column 0 lives on lane t == 0
-      const int i = iw + mt * 16 + g + 8 * rh;
-      if (i < n) {
-        const float inv = 1.0f / l;
-        float* op = out + (base + (long long)i * sq.pos_stride) * 64 + h * AT_D + 2 * t;
-        *reinterpret_cast<float2*>(op) = make_float2(o[mt][0][2 * rh] * inv, o[mt][0][2 * rh + 1] * inv);
-        *reinterpret_cast<float2*>(op + 8) = make_float2(o[mt][1][2 * rh] * inv, o[mt][1][2 * rh + 1] * inv);
-      }
-    }
-}
-
 
 // ------------------------------------------------------------------------------------------------
-// variant 0 (v4): same mathematics as the kernel above, reorganised around what ncu showed binds it -- the LSU / shared
+// variant 0 (v4): the tensor-core kernel, organised around what ncu showed binds it -- the LSU / shared
 // memory pipe (72 % busy with the fp32 skew round trip, 27 % of it bank conflicts), dead warps (641 rows = 20 full
 // 32-row blocks + 1 row -> a quarter of the last CTA idles), a 64-key tile spent on ONE live key, and ~11 instructions
 // per score.
@@ -695,9 +482,7 @@ extern "C" int seb200_attention(const void* qkv, const float* rel_pos_emb, const
   SEB_REQUIRE(rel_pos_emb_h && aligned16(rel_pos_emb_h), SEB_EINVAL, "attention: the tensor-core variant needs the fp16 copy of rel_pos_emb");
   static PerDeviceOnce attr_done;
   if (!attr_done.done()) {
-    cudaError_t e = cudaFuncSetAttribute(attention_f16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_f16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_v4_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, a4_smem(4));
+    cudaError_t e = cudaFuncSetAttribute(attention_v4_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, a4_smem(4));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_v4_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, a4_smem(4));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_v4_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, a4_smem(4));
     if (e != cudaSuccess) { set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
@@ -723,14 +508,6 @@ extern "C" int seb200_attention(const void* qkv, const float* rel_pos_emb, const
     SEB_CHECK_LAUNCH("attention_v4_kernel");
     return 0;
   }
-  // variant 2: the round-1 kernel (fp32 skew staging), kept for A/B measurements
-  const int nqb = ((n + A2_WROWS - 1) / A2_WROWS + 3) / 4;
-  const long long nblocks = (long long)seq->nseq * AT_H * nqb;
-  SEB_REQUIRE(nblocks < 2147483647LL, SEB_EINVAL, "attention: grid too large");
-  if (band)
-    attention_f16_kernel<true><<<(unsigned)nblocks, 128, A2_SMEM, st>>>(reinterpret_cast<const __half*>(qkv), reinterpret_cast<const __half*>(rel_pos_emb_h), *seq, nqb, out);
-  else
-    attention_f16_kernel<false><<<(unsigned)nblocks, 128, A2_SMEM, st>>>(reinterpret_cast<const __half*>(qkv), reinterpret_cast<const __half*>(rel_pos_emb_h), *seq, nqb, out);
-  SEB_CHECK_LAUNCH("attention_f16_kernel");
-  return 0;
+  set_error("attention: variant %d is not implemented (0: mma.sync, 1: fp32 SIMT cross-check, 3: tcgen05)", variant);
+  return SEB_EUNSUPPORTED;
 }

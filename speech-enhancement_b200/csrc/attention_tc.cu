@@ -175,328 +175,6 @@ __device__ __forceinline__ long long t5_seq_base(const SebSeq& sq, int seq) {
   return (long long)(seq / sq.inner) * sq.outer_stride + (seq % sq.inner);
 }
 
-template <int WM, int PK>
-__global__ void __launch_bounds__(T5_THREADS, 2)
-attention_tc_kernel(const __half* __restrict__ qkvh, const __half* __restrict__ Eh, const SebSeq sq, int nqb, float* __restrict__ out) {
-  extern __shared__ uint8_t t5_smraw[];
-  __shared__ uint64_t bar_S, bar_F, bar_P, bar_O, full_bar[T5_STAGES], empty_bar[T5_STAGES];
-  __shared__ uint32_t tmem_base_s;
-  const uint32_t sm0 = (ptx::smem_u32(t5_smraw) + 127u) & ~127u;      // shared-window byte address of the carved buffers
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int qb = blockIdx.x % nqb, sh = blockIdx.x / nqb;
-  const int hp = sh & 1, seq = sh >> 1;
-  const int n = sq.n, i0 = qb * T5_BQ;
-  const long long base = t5_seq_base(sq, seq);
-  const int ntiles = (n + T5_KT - 1) / T5_KT;
-  const __half* seq0 = qkvh + base * T5_ROWH;                           // row 0 of this sequence
-
-  if (tid == 0) {
-    ptx::mbar_init(&bar_S, 1);        // S(t), R(t) written            (tcgen05.commit)
-    ptx::mbar_init(&bar_F, 128);      // S(t), R(t) read into registers (every softmax thread)
-    ptx::mbar_init(&bar_P, 128);      // P(t) stored                    (every softmax thread)
-    ptx::mbar_init(&bar_O, 1);        // O += P(t) V(t) done            (tcgen05.commit)
-    for (int s = 0; s < T5_STAGES; ++s) { ptx::mbar_init(&full_bar[s], 32); ptx::mbar_init(&empty_bar[s], 1); }
-    ptx::fence_barrier_init();
-  }
-  if (warp == 4) ptx::tmem_alloc(&tmem_base_s, T5_TCOLS);
-
-  // ---- loader warp state: K, V and the E window of a tile = 8 + 8 + 8 chunks of 16 bytes per lane; lane -> (key & 7, chunk) is fixed
-  const long long key_stride_h = sq.pos_stride * T5_ROWH;              // halfs between consecutive positions
-  const __half* kv_lane = seq0 + (long long)(lane >> 2) * key_stride_h + 64 + hp * 32 + (lane & 3) * 8;
-  const uint32_t k_dst = (uint32_t)(T5_KS + (lane & 3) * 128 + (lane >> 2) * 16);
-  const uint32_t v_dst = (uint32_t)(T5_VS + (lane & 3) * 1024 + (lane >> 2) * 16);
-  const uint32_t e_dst = (uint32_t)(T5_ES + (lane >> 4) * 256 + (lane & 1) * 128 + ((lane >> 1) & 7) * 16);
-  const __half* e_lane = Eh + T5_MAXPOS * T5_D + (lane & 1) * 8;
-  auto issue_tile = [&](int t) {          // one commit group per call (empty past the last tile)
-    if (t < ntiles) {
-      const uint32_t st = sm0 + T5_STAGE0 + (uint32_t)((t % T5_STAGES) * T5_STAGE);
-      const int j0 = t * T5_KT;
-      const int key0 = j0 + (lane >> 2);
-      const __half* src0 = kv_lane + (long long)j0 * key_stride_h;
-      const int d0 = i0 + 63 - j0 - (lane >> 1);
-      const bool need_e = t5_far(i0, t) == 0;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const bool ok = key0 + 8 * k < n;
-        const __half* src = ok ? src0 + (long long)(8 * k) * key_stride_h : seq0;
-        ptx::cp16z(st + k_dst + (uint32_t)(k * 512), src, ok ? 16u : 0u);
-        ptx::cp16z(st + v_dst + (uint32_t)(k * 128), ok ? src + 64 : seq0, ok ? 16u : 0u);
-        if (need_e) {
-          int d = d0 - 16 * k;
-          d = d < -T5_MAXPOS ? -T5_MAXPOS : (d > T5_MAXPOS ? T5_MAXPOS : d);
-          ptx::cp16_ca(st + e_dst + (uint32_t)(k * 512), e_lane + d * T5_D);
-        }
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  if (warp == 4) {                        // the first two tiles fly under the TMEM allocation, the q loads and the CTA barrier
-    issue_tile(0);
-    issue_tile(1);
-  }
-
-  if (warp < 4) {
-    // ---- operand rows of this thread: Aexp (q in its head's slot) and Q (k order permuted like the fragment-ordered E table)
-    const int hl = warp >> 1, par = warp & 1;
-    const int i = i0 + 2 * lane + par;
-    uint4 qlo = make_uint4(0u, 0u, 0u, 0u), qhi = qlo;
-    if (i < n) {
-      const uint4* qp = reinterpret_cast<const uint4*>(seq0 + (long long)i * sq.pos_stride * T5_ROWH + (2 * hp + hl) * T5_D);
-      qlo = __ldg(qp); qhi = __ldg(qp + 1);
-    }
-    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-    const uint32_t arow = sm0 + T5_AEXP + (uint32_t)((tid >> 3) * 512 + (tid & 7) * 16);
-    auto sts128 = [](uint32_t addr, uint4 v) {
-      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-    };
-    sts128(arow + 0 * 128, hl == 0 ? qlo : zero);
-    sts128(arow + 1 * 128, hl == 0 ? qhi : zero);
-    sts128(arow + 2 * 128, hl == 1 ? qlo : zero);
-    sts128(arow + 3 * 128, hl == 1 ? qhi : zero);
-    // E rows are stored as k = 0,1,8,9,2,3,10,11 | 4,5,12,13,6,7,14,15 (ops.pack_rel_pos): the same permutation on q leaves q . E unchanged
-    const uint32_t qrow = sm0 + T5_QPL + (uint32_t)((tid >> 3) * 256 + (tid & 7) * 16);
-    sts128(qrow, make_uint4(qlo.x, qhi.x, qlo.y, qhi.y));
-    sts128(qrow + 128, make_uint4(qlo.z, qhi.z, qlo.w, qhi.w));
-    ptx::fence_proxy_async_smem();
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = tmem_base_s;
-
-  if (warp == 4) {
-    // ================= loader warp (continued): tiles 0 and 1 were issued before the CTA barrier =================
-    for (int t = 2; t < ntiles + 2; ++t) {
-      {                           // announce tile t - 2 first: it never waits behind the slot release below
-        asm volatile("cp.async.wait_group 1;" ::: "memory");     // all groups but the newest (tile t - 1): this lane's chunks of tile t - 2 have landed
-        ptx::fence_proxy_async_smem();
-        ptx::mbar_arrive(&full_bar[(t - 2) % T5_STAGES]);
-      }
-      if (t >= T5_STAGES && t < ntiles) {    // MMA 1 and MMA 3 of tile t - 4 are done; one lane polls, the others sleep at the warp barrier
-        if (lane == 0) ptx::mbar_wait_lean<WM>(&empty_bar[t % T5_STAGES], (uint32_t)(t / T5_STAGES - 1) & 1u);
-        __syncwarp();
-      }
-      issue_tile(t);
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-  } else if (warp == 5) {
-    // ================= MMA issuer (one thread): MMA 1 of tile t + 1 as soon as S / R of tile t sit in registers, then MMA 3 of tile t
-    // when its P is stored.  F(t) always precedes P(t), so one thread serves both without delaying either; a second issuer warp
-    // only added another spinning waiter next to the softmax warps. =================
-    if (lane == 0) {
-      constexpr uint32_t IDESC_S = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);                 // f16 x f16 -> f32, N = 64
-      constexpr uint32_t IDESC_R = ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);                            // f16 x f16 -> f16, N = 128
-      constexpr uint32_t IDESC_O = (1u << 4) | (1u << 16) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);    // B MN-major, N = 32
-      const uint32_t tS = tmem_base + T5_TS, tR = tmem_base + T5_TR, tP = tmem_base + T5_TP, tO = tmem_base + T5_TO;
-      const uint64_t a0 = ptx::umma_desc_ns(sm0 + T5_AEXP, 128, 512), a1 = ptx::umma_desc_ns(sm0 + T5_AEXP + 256, 128, 512),
-                     aq = ptx::umma_desc_ns(sm0 + T5_QPL, 128, 256);
-      auto mma1 = [&](int t) {          // S(t) = Aexp . K(t)^T,  R(t) = Q . Ewin(t)^T (skipped when every offset is clamped)
-        const int slot = t % T5_STAGES;
-        const uint32_t st = sm0 + T5_STAGE0 + (uint32_t)(slot * T5_STAGE);
-        const uint64_t bk = ptx::umma_desc_ns(st + T5_KS, 128, 512), be = ptx::umma_desc_ns(st + T5_ES, 128, 256);
-        ptx::mbar_wait_lean<WM>(&full_bar[slot], (uint32_t)(t / T5_STAGES) & 1u);
-        T5_STAMP(1, t, 0);
-        if (t > 0) ptx::mbar_wait_lean<WM>(&bar_F, (uint32_t)(t - 1) & 1u);
-        T5_STAMP(1, t, 1);
-        ptx::tc_fence_after();
-        ptx::mma_f16_ss(tS, a0, bk, IDESC_S, 0u);
-        ptx::mma_f16_ss(tS, a1, bk + (256 >> 4), IDESC_S, 1u);
-        if (t5_far(i0, t) == 0) ptx::mma_f16_ss(tR, aq, be, IDESC_R, 0u);
-        ptx::tc_commit(&bar_S);
-        T5_STAMP(1, t, 2);
-      };
-      mma1(0);
-      for (int t = 0; t < ntiles; ++t) {
-        if (t + 1 < ntiles) mma1(t + 1);
-        const int slot = t % T5_STAGES;
-        const uint64_t bv = ptx::umma_desc_ns(sm0 + T5_STAGE0 + (uint32_t)(slot * T5_STAGE) + T5_VS, 128, 1024);
-        ptx::mbar_wait_lean<WM>(&bar_P, (uint32_t)t & 1u);
-        T5_STAMP(1, t, 3);
-        ptx::tc_fence_after();
-        const int nks = (n - t * T5_KT <= 16) ? 1 : 4;       // short last tile: the threads stored P for 16 keys only
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          if (ks < nks) ptx::mma_f16_ts(tO, tP + (uint32_t)(ks * 8), bv + (uint64_t)((ks * 256) >> 4), IDESC_O, (t | ks) ? 1u : 0u);
-        ptx::tc_commit(&bar_O);            // O updated, P free
-        ptx::tc_commit(&empty_bar[slot]);  // ring slot free (MMA 1 of this tile completed earlier)
-        T5_STAMP(1, t, 4);
-      }
-    }
-  } else {
-    // ================= softmax threads: one accumulator row each =================
-    const int hl = warp >> 1, par = warp & 1;
-    const int i = i0 + 2 * lane + par;
-    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
-    const uint32_t tS = tmem_base + lane_sel + T5_TS, tR = tmem_base + lane_sel + T5_TR, tP = tmem_base + lane_sel + T5_TP,
-                   tO = tmem_base + lane_sel + T5_TO;
-    const uint32_t myrow = sm0 + T5_RSCR + (uint32_t)(tid * T5_RPITCH);
-    const uint32_t rd = myrow + (uint32_t)((31 - lane) * 4);      // word (cs >> 1) of the row, cs = 63 - par - 2 lane
-    float m = 0.f, l = 0.f;
-    // far-field constants of this row: q . E[1024] (offsets >= +512) and q . E[0] (offsets <= -512), fp32 from the fp16 operands
-    float c_hi = 0.f, c_lo = 0.f;
-    if (n > T5_MAXPOS) {
-      const uint32_t qw = sm0 + T5_QPL + (uint32_t)((tid >> 3) * 256 + (tid & 7) * 16);      // this row of Q (same k permutation as the E table)
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        uint4 qv;
-        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(qv.x), "=r"(qv.y), "=r"(qv.z), "=r"(qv.w) : "r"(qw + ch * 128) : "memory");
-        const uint4 eh = __ldg(reinterpret_cast<const uint4*>(Eh + 2 * T5_MAXPOS * T5_D) + ch), el = __ldg(reinterpret_cast<const uint4*>(Eh) + ch);
-        const uint32_t qq[4] = {qv.x, qv.y, qv.z, qv.w}, hh[4] = {eh.x, eh.y, eh.z, eh.w}, ll[4] = {el.x, el.y, el.z, el.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float2 qf = __half22float2(*reinterpret_cast<const __half2*>(&qq[k]));
-          const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hh[k])), lf = __half22float2(*reinterpret_cast<const __half2*>(&ll[k]));
-          c_hi = fmaf(qf.x, hf.x, fmaf(qf.y, hf.y, c_hi));
-          c_lo = fmaf(qf.x, lf.x, fmaf(qf.y, lf.y, c_lo));
-        }
-      }
-    }
-    // One key tile.  NK = keys this thread processes: 64, or 16 for a short last tile (641 = 10 x 64 + 1: the eleventh tile
-    // holds ONE live key; the MMAs still run at N = 64 on zero-filled keys, but the threads -- the bound -- do a quarter of the work
-    // and MMA 3 contracts over 16 keys only).
-    auto tile_body = [&](auto nk_tag, auto far_tag, int t, float cadd) {
-      constexpr int NK = decltype(nk_tag)::value;
-      constexpr bool FAR = decltype(far_tag)::value;     // every offset of the tile lies beyond the +-512 clamp: the rel-pos logit is the per-row constant cadd
-      constexpr int NWR = NK == 64 ? 64 : 40;          // staged R words: 31 + NK / 2 + 1, rounded up to whole STS.128
-      T5_STAMP(0, t, 0);
-      ptx::mbar_wait_lean<WM>(&bar_S, (uint32_t)t & 1u);
-      T5_STAMP(0, t, 1);
-      ptx::tc_fence_after();
-      if (!FAR) {
-        uint32_t w[64];
-        ptx::tmem_ld32_pack16<0>(tR, w);
-        if (NK == 64) ptx::tmem_ld32_pack16<32>(tR + 64u, w); else ptx::tmem_ld16_pack16(tR + 64u, w + 32);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int q = 0; q < NWR / 4; ++q)
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(myrow + q * 16), "r"(w[4 * q]), "r"(w[4 * q + 1]), "r"(w[4 * q + 2]), "r"(w[4 * q + 3]) : "memory");
-      }
-      uint32_t sb[NK];                   // in flight under the shared-memory round trip
-      if (NK == 64) { ptx::tmem_ld32<0>(tS, sb); ptx::tmem_ld32<32>(tS + 32u, sb); } else ptx::tmem_ld16(tS, sb);
-      uint32_t x[NK / 2 + 1];
-      if (!FAR) {
-#pragma unroll
-        for (int k = 0; k < NK / 2 + 1; ++k) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x[k]) : "r"(rd + k * 4) : "memory");
-      }
-      ptx::tmem_ld_wait();
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&bar_F);          // S / R sit in registers: the next tile's MMA 1 may overwrite them
-      T5_STAMP(0, t, 2);
-      float s[NK];
-      if (FAR) {
-#pragma unroll
-        for (int jj = 0; jj < NK; ++jj) s[jj] = __uint_as_float(sb[jj]);
-      } else if (par) {        // cs even: key pair (2p, 2p + 1) = the two halves of word p
-#pragma unroll
-        for (int p = 0; p < NK / 2; ++p) {
-          s[2 * p] = ptx::fhadd((unsigned short)(x[p] & 0xffffu), __uint_as_float(sb[2 * p]));
-          s[2 * p + 1] = ptx::fhadd((unsigned short)(x[p] >> 16), __uint_as_float(sb[2 * p + 1]));
-        }
-      } else {          // cs odd: key 2p = high half of word p, key 2p + 1 = low half of word p + 1
-#pragma unroll
-        for (int p = 0; p < NK / 2; ++p) {
-          s[2 * p] = ptx::fhadd((unsigned short)(x[p] >> 16), __uint_as_float(sb[2 * p]));
-          s[2 * p + 1] = ptx::fhadd((unsigned short)(x[p + 1] & 0xffffu), __uint_as_float(sb[2 * p + 1]));
-        }
-      }
-      const int rem = n - t * T5_KT;
-      if (rem < NK) {                    // last tile: keys beyond the sequence
-#pragma unroll
-        for (int jj = 0; jj < NK; ++jj)
-          if (jj >= rem) s[jj] = -1e30f;
-      }
-      float mx;
-      {
-        constexpr int N1 = (NK + 2) / 3;
-        float a[N1];
-#pragma unroll
-        for (int k = 0; k < NK / 3; ++k) a[k] = ptx::fmax3(s[3 * k], s[3 * k + 1], s[3 * k + 2]);
-        a[N1 - 1] = s[NK - 1];                                       // NK = 64 and 16 both leave exactly one element over
-        mx = a[0];
-#pragma unroll
-        for (int k = 1; k + 1 < N1; k += 2) mx = ptx::fmax3(mx, a[k], a[k + 1]);
-        if ((N1 & 1) == 0) mx = fmaxf(mx, a[N1 - 1]);
-        if (FAR) mx += cadd;
-      }
-      T5_STAMP(0, t, 3);
-      if (t > 0) {                                                    // MMA 3 of tile t - 1 has consumed P and updated O (long since)
-        ptx::mbar_wait_lean<WM>(&bar_O, (uint32_t)(t - 1) & 1u);
-        T5_STAMP(0, t, 4);
-        ptx::tc_fence_after();
-      }
-      if (t == 0) {
-        m = mx;
-      } else {
-        const bool need = mx > m + T5_LAZY;
-        if (__any_sync(0xffffffffu, need)) {       // rare: move the reference maximum, rescale this row of O and its running sum
-          const float mn = need ? mx : m;
-          const float corr = ptx::ex2f(m - mn);
-          m = mn;
-          l *= corr;
-          uint32_t o[32];
-          ptx::tmem_ld32<0>(tO, o);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * corr);
-          ptx::tmem_st32(tO, o);
-        }
-      }
-      uint32_t pw[NK / 2];
-      float2 la = make_float2(0.f, 0.f), lb = la;
-      const float2 negm = FAR ? make_float2(cadd - m, cadd - m) : make_float2(-m, -m);
-#pragma unroll
-      for (int p = 0; p < NK / 2; p += 2) {       // packed fp32x2 (FADD2) for the shift by -m and for the row sums
-        const float2 a = __fadd2_rn(make_float2(s[2 * p], s[2 * p + 1]), negm), b = __fadd2_rn(make_float2(s[2 * p + 2], s[2 * p + 3]), negm);
-        const float2 pa = make_float2(ptx::ex2f(a.x), ptx::ex2f(a.y)), pb = make_float2(ptx::ex2f(b.x), ptx::ex2f(b.y));
-        la = __fadd2_rn(la, pa); lb = __fadd2_rn(lb, pb);
-        const __half2 h0 = __floats2half2_rn(pa.x, pa.y), h1 = __floats2half2_rn(pb.x, pb.y);
-        pw[p] = *reinterpret_cast<const uint32_t*>(&h0);
-        pw[p + 1] = *reinterpret_cast<const uint32_t*>(&h1);
-      }
-      l += (la.x + la.y) + (lb.x + lb.y);
-      if (NK == 64) ptx::tmem_st32(tP, pw); else ptx::tmem_st8u(tP, pw);
-      T5_STAMP(0, t, 5);
-      ptx::tmem_st_wait5();
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&bar_P);
-      T5_STAMP(0, t, 6);
-    };
-    if (i0 + par >= n) {                // every query row of this warp lies past the sequence (last block): keep the protocol, skip the work
-      for (int t = 0; t < ntiles; ++t) {
-        ptx::mbar_wait_lean<WM>(&bar_S, (uint32_t)t & 1u);
-        ptx::mbar_arrive(&bar_F);
-        if (t > 0) ptx::mbar_wait_lean<WM>(&bar_O, (uint32_t)(t - 1) & 1u);
-        ptx::mbar_arrive(&bar_P);         // this warp's P rows stay stale: they only feed its own (never stored) rows of O
-      }
-    } else {
-      for (int t = 0; t < ntiles; ++t) {
-        const int far = t5_far(i0, t);
-        const bool tail = n - t * T5_KT <= 16;           // the loader and the MMA issuer key on t5_far alone: a short last tile can be far as well
-        if (far && tail) tile_body(std::integral_constant<int, 16>{}, std::true_type{}, t, far > 0 ? c_hi : c_lo);
-        else if (far) tile_body(std::integral_constant<int, 64>{}, std::true_type{}, t, far > 0 ? c_hi : c_lo);
-        else if (tail) tile_body(std::integral_constant<int, 16>{}, std::false_type{}, t, 0.f);
-        else tile_body(std::integral_constant<int, 64>{}, std::false_type{}, t, 0.f);
-      }
-    }
-    ptx::mbar_wait_lean<WM>(&bar_O, (uint32_t)(ntiles - 1) & 1u);
-    ptx::tc_fence_after();
-    uint32_t o[16];
-    ptx::tmem_ld16(tO + (uint32_t)(hl * 16), o);
-    ptx::tmem_ld_wait();
-    if (i < n) {
-      const float inv = 1.0f / l;
-      float* op = out + (base + (long long)i * sq.pos_stride) * 64 + (2 * hp + hl) * T5_D;
-#pragma unroll
-      for (int c = 0; c < 16; c += 4)
-        *reinterpret_cast<float4*>(op + c) = make_float4(__uint_as_float(o[c]) * inv, __uint_as_float(o[c + 1]) * inv,
-                                                         __uint_as_float(o[c + 2]) * inv, __uint_as_float(o[c + 3]) * inv);
-    }
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 4) ptx::tmem_dealloc(tmem_base, T5_TCOLS);
-}
-
 // ------------------------------------------------------------------------------------------------------------------------
 // Three query groups per CTA (one CTA per SM, all 512 TMEM columns).  The two-CTA kernel above is bound by the latency chain
 // of its softmax warps (wait S -> tcgen05.ld -> STS / LDS -> FHADD -> max -> ex2 -> tcgen05.st -> arrive): two chains per
@@ -851,37 +529,16 @@ extern "C" int seb200_t5_trace(long long* host) { return (int)cudaMemcpyFromSymb
 
 int attention_tc_launch(const __half* qkvh, const __half* Eh, const SebSeq* seq, float* out, cudaStream_t st) {
   static PerDeviceOnce attr_done;
-  static int mode = 0;
   if (!attr_done.done()) {
-    const char* ev = getenv("SEB200_T5_MODE");      // experiment switch: 6 = three query groups per CTA (default), 0..5 = the two-CTA kernel (wait mode * 2 + packed)
-    mode = ev ? atoi(ev) : 6;
-    cudaError_t e = cudaSuccess;
-#define T5_ATTR(W, P) if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<W, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM);
-    T5_ATTR(0, 0) T5_ATTR(0, 1) T5_ATTR(1, 0) T5_ATTR(1, 1) T5_ATTR(2, 0) T5_ATTR(2, 1)
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, T6_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attention_tc3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, T6_SMEM);
     if (e != cudaSuccess) { set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     attr_done.set();
   }
-  const int nqb = (seq->n + T5_BQ - 1) / T5_BQ;
-  const long long nblocks = (long long)seq->nseq * 2 * nqb;
-  SEB_REQUIRE(nblocks < 2147483647LL, SEB_EINVAL, "attention: grid too large");
-#define T5_GO(W, P) attention_tc_kernel<W, P><<<(unsigned)nblocks, T5_THREADS, T5_SMEM, st>>>(qkvh, Eh, *seq, nqb, out)
-  if (mode == 6) {
-    const int nqb3 = (seq->n + T6_BQ - 1) / T6_BQ;
-    const long long nb3 = (long long)seq->nseq * 2 * nqb3;
-    attention_tc3_kernel<0><<<(unsigned)nb3, T6_THREADS, T6_SMEM, st>>>(qkvh, Eh, *seq, nqb3, out);
-    SEB_CHECK_LAUNCH("attention_tc3_kernel");
-    return 0;
-  }
-  switch (mode) {
-    case 1: T5_GO(0, 1); break;
-    case 2: T5_GO(1, 0); break;
-    case 3: T5_GO(1, 1); break;
-    case 4: T5_GO(2, 0); break;
-    case 5: T5_GO(2, 1); break;
-    default: T5_GO(0, 0); break;
-  }
-  SEB_CHECK_LAUNCH("attention_tc_kernel");
+  const int nqb3 = (seq->n + T6_BQ - 1) / T6_BQ;
+  const long long nb3 = (long long)seq->nseq * 2 * nqb3;
+  SEB_REQUIRE(nb3 < 2147483647LL, SEB_EINVAL, "attention: grid too large");
+  attention_tc3_kernel<0><<<(unsigned)nb3, T6_THREADS, T6_SMEM, st>>>(qkvh, Eh, *seq, nqb3, out);
+  SEB_CHECK_LAUNCH("attention_tc3_kernel");
   return 0;
 }
 

@@ -34,7 +34,7 @@ void count_launch(int n = 1);
   } while (0)
 
 // Once-per-(call site, device) guard.  Kernel attributes (opt-in dynamic shared memory) are per device and one process may drive
-// several devices (nn.DataParallel around the module, main_gan.py:168-188), so a plain `static bool` would leave every device but
+// several devices (one module instance per cuda:k), so a plain `static bool` would leave every device but
 // the first without its attribute.  Racing threads at worst set the same attribute twice.
 struct PerDeviceOnce {
   std::atomic<unsigned long long> mask{0};

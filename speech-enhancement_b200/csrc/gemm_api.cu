@@ -4,8 +4,6 @@
 
 namespace seb {
 
-int launch_conv_tap(const SebGemm* s, const GemmArgs& g, cudaStream_t st);       // conv_tap.cu (experimental)
-bool conv_tap_enabled();
 int launch_conv_persist(const SebGemm* s, const GemmArgs& g, cudaStream_t st);   // conv_persist.cu
 int conv_persist_max_chunks();
 int launch_conv_y3(const SebGemm* s, const GemmArgs& g, cudaStream_t st);        // conv_y3.cu
@@ -151,8 +149,6 @@ extern "C" int seb200_gemm(const SebGemm* s, int engine, void* stream) {
     }
     switch (key) {
       case SEB_LOAD_CONV_SPLIT * 16 + SEB_EPI_BIAS:
-        if (nt == 64 && s->tc_ntiles == 1 && s->N == 64 && s->stride_f == 1 && s->Fin == s->Fout && s->ldo % 4 == 0 && s->tc_planes == 2 && conv_tap_enabled())
-          return launch_conv_tap(s, g, st);              // experimental: shared A tile for the three frequency taps
         if (nt == 64 && s->tc_ntiles == 1 && s->N == 64 && s->stride_f == 1 && s->Fin == s->Fout && s->taps_t == 2 && s->Fin >= 16 && s->ldo % 4 == 0 && s->tc_planes == 2 && conv_y3_enabled())
           return launch_conv_y3(s, g, st);               // three frequency taps folded into N = 192
         if (nt == 64 && s->tc_ntiles == 1 && s->N == 64 && s->ldo % 4 == 0 && s->tc_planes == 2 && s->Fout >= 64 && s->K / BK <= conv_persist_max_chunks())

@@ -10,6 +10,7 @@ n_fft=400, hop=100, periodic Hamming window, comp_type='pow' (config/default.py:
 """
 from __future__ import annotations
 
+from collections import OrderedDict
 from typing import Dict, Optional
 
 import torch
@@ -26,7 +27,10 @@ DFT_ENGINE = "tcgen05"   # DFT / iDFT on tcgen05 with three bf16 planes per oper
 # autograd (2.2e-3) vs 2.9e-2 (tensor path).  The DFTs are 0.25 % of a step, so the training path gives up nothing measurable.
 GRAD_DFT_ENGINE = "simt"
 
-_cache: Dict[tuple, object] = {}
+_cache: Dict[tuple, object] = {}          # DFT bases per device (a handful of entries, never evicted)
+_env_cache: "OrderedDict[tuple, torch.Tensor]" = OrderedDict()      # 1 / window envelope per (device, frame count): LRU, bounded
+_ENV_CACHE_MAX = 32
+_window_ok: Dict[tuple, bool] = {}         # validated caller windows, keyed by (data_ptr, version, device): no D2H sync per call
 
 
 def _bases(device):
@@ -46,18 +50,29 @@ def _bases_bwd(device):
 
 
 def _inv_env(T: int, device):
-    key = ("env", str(device), T)
-    if key not in _cache:
-        _cache[key] = inv_envelope(T, N_FFT, HOP).to(device)
-    return _cache[key]
+    key = (str(device), T)
+    env = _env_cache.get(key)
+    if env is None:
+        env = _env_cache[key] = inv_envelope(T, N_FFT, HOP).to(device)
+        while len(_env_cache) > _ENV_CACHE_MAX:       # dataset inference sees many utterance lengths: keep the most recent ones only
+            _env_cache.popitem(last=False)
+    else:
+        _env_cache.move_to_end(key)
+    return env
 
 
 def _check_cfg(n_fft, hop, window, comp_type):
     if n_fft != N_FFT or hop != HOP or comp_type != "pow":
         raise RuntimeError("se_b200 DSP kernels are specialised for n_fft=400, hop=100, comp_type='pow'")
     if window is not None:
-        ref = hamming_periodic(N_FFT).to(torch.float32)
-        if window.numel() != N_FFT or not torch.allclose(window.detach().float().cpu(), ref, atol=1e-6):
+        key = (window.data_ptr(), int(window._version), str(window.device), window.numel())
+        if key not in _window_ok:            # one device-to-host read per distinct window tensor, not per call
+            ref = hamming_periodic(N_FFT).to(torch.float32)
+            ok = window.numel() == N_FFT and bool(torch.allclose(window.detach().float().cpu(), ref, atol=1e-6))
+            if len(_window_ok) > 64:
+                _window_ok.clear()
+            _window_ok[key] = ok
+        if not _window_ok[key]:
             raise RuntimeError("se_b200 DSP kernels fold the periodic Hamming window into the DFT basis; got a different window")
 
 

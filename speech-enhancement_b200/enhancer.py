@@ -68,8 +68,14 @@ class EnhancerB200(nn.Module):
             self.graph_kernel_nodes = _lib.launch_count() - n0      # kernels replayed per call (the C-ABI counter only sees the capture)
             if len(self._graphs) > 8:
                 self._graphs.clear()
-            entry = self._graphs[key] = (graph, static_in, static_out)
-        graph, static_in, static_out = entry
+            # the captured kernels hold raw pointers into the model's workspace tensors and packed weights (allocated by the eager
+            # warm-up, outside the graph's private pool): the cache entry keeps both alive for as long as the graph can be replayed,
+            # whatever TSCNet.workspace() / packed() evict in the meantime
+            B, L = x.shape
+            T = int(math.ceil(L / dsp.HOP)) + 1
+            keep = (self.model.workspace(B, T, x.device), self.model.packed())
+            entry = self._graphs[key] = (graph, static_in, static_out, keep)
+        graph, static_in, static_out, _keep = entry
         static_in.copy_(x)
         graph.replay()
         return static_out.clone()

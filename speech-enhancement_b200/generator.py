@@ -151,8 +151,6 @@ class TSCNet(nn.Module):
         # sequences at least this long take the tcgen05 kernel when attention_variant == 0 (measured, three-group kernel vs mma.sync:
         # 3.51 vs 4.91 ms at n = 4801, 7.15 vs 7.78 ms at n = 641, 3.6 vs 2.3 ms at n = 101 -- tools/attn_tc_check.py)
         self.attention_tc_min_len = 512
-        self.fuse_dwconv_pw2 = False           # opt-in: depthwise conv + pointwise 128 -> 64 in one kernel (seb200_dwconv_pw2); measured
-                                               # 21.5 ms vs 16.2 ms for the two-kernel path at configs[1], so off by default
         self.overlap_decoders = False          # opt-in: complex decoder on a side stream next to the mask decoder (second buffer set; measured in DESIGN.md)
         self._packed: Optional[Dict[str, object]] = None
         self._packed_key = None
@@ -341,11 +339,8 @@ class TSCNet(nn.Module):
         ops.gemm(loader=LOAD_ROWS, epilogue=EPI_RESID, M=M, w=P[f"{p}.attn.out"], a=[o], lda=64, out=y, ldo=64, resid=y, ldr=64, alpha=1.0, engine=eng, label="attn_out")
         # y += ConvModule(y)
         ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_GLU, M=M, w=P[f"{p}.conv.pw1"], a=[y], lda=64, ln=P[f"{p}.conv.ln"], out=u, ldo=128, engine=eng, label="pw1_glu")
-        if fused and self.fuse_dwconv_pw2:      # depthwise + BN + Swish + pointwise 128 -> 64 + residual in one kernel: v never touches HBM
-            ops.dwconv_pw2(u, seq, P[f"{p}.conv.dw"], P[f"{p}.conv.bn"][0], P[f"{p}.conv.bn"][1], P[f"{p}.conv.pw2"], y, y)
-        else:
-            ops.dwconv_bn_swish(u, seq, P[f"{p}.conv.dw"], P[f"{p}.conv.bn"][0], P[f"{p}.conv.bn"][1], v)
-            ops.gemm(loader=LOAD_ROWS, epilogue=EPI_RESID, M=M, w=P[f"{p}.conv.pw2"], a=[v], lda=128, out=y, ldo=64, resid=y, ldr=64, alpha=1.0, engine=eng, label="pw2")
+        ops.dwconv_bn_swish(u, seq, P[f"{p}.conv.dw"], P[f"{p}.conv.bn"][0], P[f"{p}.conv.bn"][1], v)
+        ops.gemm(loader=LOAD_ROWS, epilogue=EPI_RESID, M=M, w=P[f"{p}.conv.pw2"], a=[v], lda=128, out=y, ldo=64, resid=y, ldr=64, alpha=1.0, engine=eng, label="pw2")
         # x = post_norm(y + 0.5 * FF2(LN(y))) + x
         if fused:
             ops.ffn_fused(y, x, P[f"{p}.ff2.ln"], P[f"{p}.ff2.w1"], P[f"{p}.ff2.w2"], 0.5, post=P[f"{p}.post_norm"], resid2=x)
@@ -360,8 +355,8 @@ class TSCNet(nn.Module):
     # -----------------------------------------------------------------------------------------
     def forward_in3(self, in3: torch.Tensor, stages: Optional[dict] = None) -> torch.Tensor:
         """in3: [B, T, F, 3] = (|Y|, Re Y, Im Y) of the compressed spectrogram -> est [B*T, F, 2] (workspace tensor)."""
-        if self.training and torch.is_grad_enabled():
-            raise RuntimeError("the B200 TSCNet implements the inference forward (eval / no_grad); the training step is a later row (SURVEY 8f)")
+        if self.training:
+            raise RuntimeError("se_b200.TSCNet.forward_in3 is the inference forward: call .eval() (train mode goes through forward())")
         B, T, F, _ = in3.shape
         if F != self.num_features or F % 2 == 0:
             raise RuntimeError(f"expected {self.num_features} frequency bins, got {F}")
@@ -464,13 +459,19 @@ class TSCNet(nn.Module):
             stages["mask"] = mask_out
         return ws["est"]
 
+    def _forward_train(self, x: torch.Tensor):
+        """train-mode forward (core/function.py:221: dropout active, BatchNorm batch statistics, autograd graph): SURVEY 8f row f1"""
+        raise RuntimeError("se_b200.TSCNet is in train() mode: call .eval() for inference (the training step lives in se_b200.training)")
+
     def forward(self, x: torch.Tensor, diffusion_step=None):
         """x: complex64 (B, num_features, T) compressed spectrogram -> (final_real, final_imag), each fp32 (B, 1, T, F)."""
         if not x.is_cuda:
             raise RuntimeError("se_b200.TSCNet has no CPU path: input must be a CUDA tensor on an sm_100a device")
         if not x.is_complex():
             raise RuntimeError("TSCNet.forward expects the complex compressed spectrogram (B, F, T)")
-        with torch.no_grad(), torch.cuda.device(x.device):      # launches follow the input's device (DataParallel replicas, cuda:k inputs)
+        if self.training:
+            return self._forward_train(x)
+        with torch.no_grad(), torch.cuda.device(x.device):      # launches follow the input's device (cuda:k inputs)
             B, F, T = x.shape
             in3 = ops.spec_to_in3(x.to(torch.complex64))
             est = self.forward_in3(in3)

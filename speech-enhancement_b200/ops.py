@@ -418,33 +418,21 @@ def pack_rel_pos(rel_pos_emb: torch.Tensor) -> torch.Tensor:
 
 
 def attention(qkv, rel_pos_emb, seq: SebSeq, out, variant: int = 0, rel_pos_emb_h=None):
-    """variant 0 / 2: qkv float16 [tokens, 192] with q pre-scaled (EPI_QKV_F16) -- 0 is the production kernel, 2 the
-    round-1 kernel kept for A/B measurements; variant 1: qkv float32, unscaled (fp32 SIMT cross-check)."""
+    """variant 0 (mma.sync) / 3 (tcgen05): qkv float16 [tokens, 192] with q pre-scaled (EPI_QKV_F16); variant 1: qkv float32,
+    unscaled (fp32 SIMT cross-check)."""
     _f32c(rel_pos_emb, out)
     require_cuda(qkv)
-    if variant in (0, 2, 3):
+    if variant in (0, 3):
         if qkv.dtype != torch.float16 or not qkv.is_contiguous():
             raise RuntimeError("tensor-core attention reads the float16 q|k|v projection")
-        if rel_pos_emb_h is None:       # variant 0 reads the fragment-ordered table, variant 2 the plain fp16 copy
-            rel_pos_emb_h = pack_rel_pos(rel_pos_emb) if variant in (0, 3) else rel_pos_emb.to(torch.float16)
+        if rel_pos_emb_h is None:
+            rel_pos_emb_h = pack_rel_pos(rel_pos_emb)
         if rel_pos_emb_h.dtype != torch.float16 or not rel_pos_emb_h.is_contiguous():
             raise RuntimeError("rel_pos_emb_h must be a contiguous float16 copy of the embedding table")
     else:
         _f32c(qkv)
     tok = _pb("attention", 96.0 * 4 * seq.nseq * seq.n * seq.n, (4.0 if variant == 1 else 2.0) * qkv.numel() + 4.0 * out.numel()) if _PROF is not None else None
     check(_lib.load().seb200_attention(ptr(qkv), ptr(rel_pos_emb), ptr(rel_pos_emb_h), C.byref(seq), ptr(out), variant, stream_ptr()), "seb200_attention")
-    _pe(tok)
-    return out
-
-
-def dwconv_pw2(u, seq: SebSeq, w, bn_scale, bn_shift, w3: PackedWeight, resid, out):
-    """out = resid + W3 . Swish(BN(DWConv31(u))) + b3 in one kernel (conformer.py:166-169, 204); u [tokens, 128], out [tokens, 64]."""
-    _f32c(u, w, bn_scale, bn_shift, resid, out)
-    if w3.tc_ntile != 64 or w3.N != 64 or w3.K != 128 or w3.planes != 2 or w3.bias is None:
-        raise RuntimeError("dwconv_pw2 expects W3 [64, 128] packed with n-tile 64, two planes, and a bias")
-    tok = _pb("dwconv_pw2", 62.0 * u.numel() + 2.0 * 64 * u.numel(), 4.0 * u.numel() + 8.0 * out.numel()) if _PROF is not None else None
-    check(_lib.load().seb200_dwconv_pw2(ptr(u), C.byref(seq), ptr(w), ptr(bn_scale), ptr(bn_shift), ptr(w3.w_tc), ptr(w3.bias),
-                                        ptr(resid), ptr(out), stream_ptr()), "seb200_dwconv_pw2")
     _pe(tok)
     return out
 

@@ -163,7 +163,7 @@ def inv_envelope(T: int, n_fft: int = 400, hop: int = 100) -> torch.Tensor:
     w2 = hamming_periodic(n_fft) ** 2
     full = n_fft + hop * (T - 1)
     env = torch.zeros(full, dtype=torch.float64)
-    for t in range(T):
-        env[t * hop:t * hop + n_fft] += w2
+    idx = (torch.arange(T) * hop)[:, None] + torch.arange(n_fft)[None, :]
+    env.index_add_(0, idx.reshape(-1), w2.to(torch.float64).repeat(T))        # one scatter instead of a Python loop over T frames
     half = n_fft // 2
     return (1.0 / env[half:full - half]).to(torch.float32)

@@ -122,8 +122,8 @@ class TSCNet(_GanTSCNet):
 
     def forward_in3(self, in3: torch.Tensor, noisy_in3: torch.Tensor = None, diffusion_step=None, stages: Optional[dict] = None) -> torch.Tensor:
         """in3 / noisy_in3: [B, T, F, 3] = (|Y|, Re Y, Im Y) of the two compressed spectrograms -> est [B*T, F, 2] (workspace tensor)."""
-        if self.training and torch.is_grad_enabled():
-            raise RuntimeError("the B200 TSCNet implements the inference forward (eval / no_grad); the training step is a later row (SURVEY 8f)")
+        if self.training:
+            raise RuntimeError("se_b200.tsc_diffusion.TSCNet is in train() mode: only the inference forward is implemented; call .eval()")
         if noisy_in3 is None or noisy_in3.shape != in3.shape:
             raise RuntimeError("tsc_diffusion.TSCNet needs the conditioning spectrogram with the shape of x")
         B, T, F, _ = in3.shape
@@ -155,6 +155,8 @@ class TSCNet(_GanTSCNet):
             raise RuntimeError("se_b200.tsc_diffusion.TSCNet has no CPU path: inputs must be CUDA tensors on an sm_100a device")
         if not (x.is_complex() and noisy_spec.is_complex()):
             raise RuntimeError("TSCNet.forward expects complex compressed spectrograms (B, F, T)")
+        if self.training:
+            raise RuntimeError("se_b200.tsc_diffusion.TSCNet is in train() mode: only the inference forward is implemented; call .eval()")
         with torch.no_grad(), torch.cuda.device(x.device):
             B, F, T = x.shape
             in3 = ops.spec_to_in3(x.to(torch.complex64))

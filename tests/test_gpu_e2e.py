@@ -312,3 +312,57 @@ def test_batch_stft_matches_oracle():
     assert torch.equal(ones.cpu(), torch.ones(4)) and torch.allclose(win.cpu(), torch.hamming_window(400))
     n2c, n2n = se_b200.normalize_batch({"audio": clean.to(DEV), "noisy": noisy.to(DEV)}, types.SimpleNamespace(gpu=None))
     assert torch.equal(n2c, g_clean) and torch.equal(n2n, g_noisy)
+
+
+# ---- long clips against the reference's own output (oracle/make_golden.py --long: the unmodified reference modules driven over
+# ---- chunks of <= 8 sequences): BASELINE configs[2]'s utterance length (30 s, T = 4801: > 80 % of the key tiles of the time axis
+# ---- take the far-field constant shortcut, 16-key tail body) and 10 s (T = 1001: both clamp sides active inside one sequence)
+@pytest.mark.parametrize("name", ["long_b1_L100000", "long_b1_L480000"])
+def test_long_clip_matches_reference_golden(golden, name):
+    g = golden(name)
+    L = int(g["length"])
+    noisy, clean = weights.synth_wave(1, L, int(g["wave_seed"]), "speech")
+    model = _model(int(g["weight_seed"]), "tcgen05")             # the shipped default: tcgen05 engine, tcgen05 attention from n = 512
+    y = se_b200.EnhancerB200(model)(noisy.to(DEV)).cpu()
+    ref = torch.from_numpy(g["enhanced"])
+    assert y.shape == ref.shape == (1, L)
+    err = rel_max(y, ref)
+    assert err < WAVE_TOL, f"{name}: waveform max-abs/peak {err:.3e}"
+    d = (O.si_sdr(y, clean) - O.si_sdr(ref, clean)).abs().max().item()
+    assert d < SISDR_TOL_DB, f"{name}: SI-SDR delta {d:.4f} dB"
+    if L <= 100000:                                               # and the mma.sync attention kernel on the same clip
+        model.attention_tc_min_len = 1 << 30
+        err0 = rel_max(se_b200.EnhancerB200(model)(noisy.to(DEV)).cpu(), ref)
+        assert err0 < WAVE_TOL, f"{name} (mma.sync attention): {err0:.3e}"
+
+
+def test_load_model_reads_reference_checkpoint(golden, tmp_path):
+    """inference_gan.load_model (:60-72): a training checkpoint holds {'gen_state_dict': {'module.' + key: tensor}} (DataParallel / DDP
+    prefix, main_gan.py:291-310); se_b200.load_model strips the prefix, loads the 359 entries, returns the model in eval mode."""
+    g = golden("speech_b2_L8000")
+    sd = weights.synth_state_dict(int(g["weight_seed"]))
+    path = tmp_path / "ckpt.pth.tar"
+    torch.save({"epoch": 3, "arch": "scp", "gen_state_dict": {"module." + k: v for k, v in sd.items()},
+                "disc_state_dict": {}, "best_loss": 0.1}, path)
+    model = se_b200.load_model(str(path), device=DEV)
+    assert isinstance(model, se_b200.TSCNet) and not model.training
+    assert next(model.parameters()).is_cuda
+    for k, v in model.state_dict().items():
+        assert torch.equal(v.cpu(), sd[k]), k
+    y = se_b200.EnhancerB200(model)(torch.from_numpy(g["noisy"]).to(DEV)).cpu()
+    err = rel_max(y, torch.from_numpy(g["enhanced"]))
+    assert err < WAVE_TOL, f"waveform max-abs/peak {err:.3e}"
+
+
+def test_train_mode_forward_never_silently_runs_inference():
+    """a model left in train() mode must not return eval-mode outputs without an autograd graph: it either runs the
+    training forward (requires_grad outputs) or raises"""
+    m = _model(0, "tcgen05")
+    m.train()
+    noisy, _ = weights.synth_wave(1, 4000, 3, "speech")
+    spec = se_b200.compressed_stft(noisy.to(DEV))
+    try:
+        fr, fi = m(spec)
+    except RuntimeError:
+        return
+    assert fr.requires_grad and fi.requires_grad

@@ -374,7 +374,7 @@ def _attention_core_ref(qkv_seq, emb):
     return (dots.softmax(-1) @ v).permute(0, 2, 1, 3).reshape(S, n, 64)
 
 
-@pytest.mark.parametrize("variant", [1, 0, 2, 3])     # 3 = the tcgen05 / TMEM kernel (attention_tc.cu)
+@pytest.mark.parametrize("variant", [1, 0, 3])     # 3 = the tcgen05 / TMEM kernel (attention_tc.cu)
 @pytest.mark.parametrize("axis,B,T,Fh", [("freq", 2, 5, 101), ("time", 1, 150, 3), ("time", 1, 700, 2), ("freq", 1, 3, 64),
                                           ("time", 1, 641, 2), ("time", 2, 97, 1), ("time", 1, 3, 2), ("freq", 1, 2, 9), ("time", 1, 40, 1), ("time", 1, 1400, 1)])     # 641 = 10 x 64 + 1: the 16-key tail body, 3-warp CTAs; 1400 > 2*512 + 128: far-field (clamped) tiles take the constant shortcut
 def test_attention(variant, axis, B, T, Fh):
@@ -391,7 +391,7 @@ def test_attention(variant, axis, B, T, Fh):
     assert rel_max(out.view(B, T, Fh, 64).cpu(), ref) < tol
 
 
-@pytest.mark.parametrize("variant", [0, 2, 3])
+@pytest.mark.parametrize("variant", [0, 3])
 def test_attention_peaky_logits(variant):
     """large, sharply peaked logits: the lazy running maximum of variant 0 has to move its reference (and rescale) often"""
     B, T, Fh = 1, 300, 2
@@ -427,24 +427,3 @@ def test_dwconv_bn_swish(axis, B, T, Fh):
     assert rel_max(y.cpu(), ref) < 1e-5
 
 
-@pytest.mark.parametrize("axis,B,T,Fh", [("freq", 2, 5, 101), ("time", 2, 130, 3), ("time", 1, 641, 2), ("time", 1, 64, 5), ("freq", 3, 2, 200)])
-def test_dwconv_pw2_fused(axis, B, T, Fh):
-    """depthwise + BN + Swish + pointwise 128 -> 64 + residual in one kernel == the two-kernel path == torch"""
-    sd = weights.synth_state_dict(1)
-    p = "TSCB_1.time_conformer.conv.net"
-    u = rnd(B, T, Fh, 128, seed=190)
-    resid = rnd(B, T, Fh, 64, seed=191)
-    seq, to_seq, from_seq = _seq_layouts(B, T, Fh)[axis]
-    scale = sd[f"{p}.5.weight"] / torch.sqrt(sd[f"{p}.5.running_var"] + 1e-5)
-    shift = sd[f"{p}.5.bias"] + (sd[f"{p}.4.conv.bias"] - sd[f"{p}.5.running_mean"]) * scale
-    w3, b3 = sd[f"{p}.7.weight"].squeeze(-1), sd[f"{p}.7.bias"]
-    pw = packing.pack_weight(w3, 64, b3).to(DEV)
-    dw = sd[f"{p}.4.conv.weight"].squeeze(1).t().contiguous().to(DEV)
-    out = resid.clone().view(-1, 64)
-    ops.dwconv_pw2(u.view(-1, 128), seq, dw, scale.to(DEV), shift.to(DEV), pw, out, out)          # in place, as the conformer calls it
-    h = to_seq(u.cpu()).transpose(1, 2)
-    h = F.conv1d(F.pad(h, (15, 15)), sd[f"{p}.4.conv.weight"], sd[f"{p}.4.conv.bias"], groups=128)
-    h = F.batch_norm(h, sd[f"{p}.5.running_mean"], sd[f"{p}.5.running_var"], sd[f"{p}.5.weight"], sd[f"{p}.5.bias"], False, 0.0, 1e-5)
-    h = (h * torch.sigmoid(h)).double()
-    ref = from_seq((torch.einsum("snc,oc->sno", h.transpose(1, 2), w3.double()) + b3.double()).float()) + resid.cpu()
-    assert rel_max(out.view(B, T, Fh, 64).cpu(), ref) < TOL["tcgen05"]

@@ -176,3 +176,62 @@ def test_batch_stft_against_live_reference():
     assert r_creal.shape == (3, 1, 201, 33) and ones.shape == (3,) and win.shape == (400,)
     # the noisy signal ends up with unit RMS; the clean one shares its gain
     assert torch.allclose(r_noisy.pow(2).mean(-1), torch.ones(3), atol=1e-5)
+
+
+# ---- train mode: the restatement with injected dropout masks / BatchNorm batch statistics, and its autograd
+# ---- gradients, against the unmodified reference under .train() (tests/golden/train_b2_L10000.npz, oracle/make_golden.py --train).
+# ---- The golden's gradients come from the reference run in float64; `ref32_err` is the reference's own float32 distance from them.
+def train_oracle_run(g, dtype=torch.float32, device="cpu"):
+    """(final_real, final_imag, running-stat dict, {param: grad}) of the oracle for the training golden's inputs"""
+    import synth
+    sd = {k: (v.to(device=device, dtype=dtype) if v.is_floating_point() else v.to(device)) for k, v in synth.synth_state_dict(int(g["weight_seed"])).items()}
+    params = [k for k, v in sd.items() if v.is_floating_point() and "running_" not in k]
+    for k in params:
+        sd[k].requires_grad_(True)
+    spec = torch.complex(torch.from_numpy(g["spec_real"]), torch.from_numpy(g["spec_imag"])).to(device)
+    if dtype == torch.float64:
+        spec = spec.to(torch.complex128)
+    B, _, T = spec.shape
+    masks = {k: v.to(device) for k, v in synth.masks_reference_layout(synth.dropout_masks(int(g["mask_seed"]), B, T, 101)).items()}
+    tr = O.TrainCtx(masks)
+    fr, fi = O.tscnet_forward(spec, sd, tr=tr)
+    gr, gi = synth.cotangents(int(g["cot_seed"]), B, T)
+    ((fr * gr.to(fr)).sum() + (fi * gi.to(fi)).sum()).backward()
+    return fr.detach(), fi.detach(), tr.running, {k: sd[k].grad for k in params}
+
+
+def grad_errors(grads, g):
+    """per-parameter rel-L2 of `grads` against the golden's float64 gradients; zero-gradient biases are bounded in magnitude instead"""
+    import synth
+    gmax = max(float(np.abs(g["grad:" + k]).max()) for k in grads)
+    errs = {}
+    for k, gv in grads.items():
+        ref = torch.from_numpy(g["grad:" + k]).double()
+        if synth.has_zero_gradient(k):
+            assert float(gv.abs().max()) < 1e-3 * gmax, k
+            continue
+        errs[k] = float((gv.detach().double().cpu() - ref).norm() / ref.norm().clamp_min(1e-30))
+    return errs
+
+
+def test_oracle_train_mode_matches_reference_golden(golden):
+    g = golden("train_b2_L10000")
+    peak = np.abs(g["final_real"]).max()
+    # float32 restatement: forward and BatchNorm buffers against the reference's float32 run
+    fr, fi, running, grads32 = train_oracle_run(g, torch.float32)
+    assert (fr - torch.from_numpy(g["final_real"])).abs().max() / peak < 2e-5
+    assert (fi - torch.from_numpy(g["final_imag"])).abs().max() / peak < 2e-5
+    assert len(running) == 24
+    for k, v in running.items():
+        ref = torch.from_numpy(np.asarray(g["buf:" + k]))
+        assert torch.allclose(v.to(ref.dtype), ref, rtol=1e-5, atol=1e-6), k
+    # float64 restatement: the same function as the reference in float64 -> gradients agree to float32 storage rounding
+    _, _, _, grads64 = train_oracle_run(g, torch.float64)
+    assert len(grads64) == 335
+    e64 = grad_errors(grads64, g)
+    worst = max(e64, key=e64.get)
+    assert e64[worst] < 1e-6, (worst, e64[worst])
+    # float32 restatement: no further from the float64 truth than the reference's own float32 run (x3 slack, floor 1e-4)
+    e32 = grad_errors(grads32, g)
+    for k, e in e32.items():
+        assert e < max(1e-4, 3.0 * float(g["ref32_err:" + k])), (k, e, float(g["ref32_err:" + k]))

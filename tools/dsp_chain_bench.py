@@ -8,7 +8,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import se_b200  # noqa: E402
-from oracle import weights  # noqa: E402
+import synth as weights  # noqa: E402
 
 mse = torch.nn.functional.mse_loss
 

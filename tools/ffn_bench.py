@@ -8,7 +8,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import se_b200  # noqa: E402
 from se_b200 import ops  # noqa: E402
-from oracle import weights  # noqa: E402
+import synth as weights  # noqa: E402
 
 M = 64 * 641 * 101
 m = se_b200.TSCNet()

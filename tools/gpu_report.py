@@ -11,7 +11,8 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import tscnet_oracle as O, weights  # noqa: E402
+from oracle import tscnet_oracle as O  # noqa: E402
+import synth as weights  # noqa: E402  # noqa: E402
 import se_b200  # noqa: E402
 
 

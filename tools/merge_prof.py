@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import se_b200  # noqa: E402
 from se_b200 import ops, tsc_diffusion  # noqa: E402
 from se_b200._lib import EPI_GATE, EPI_RESID_SCALE, LOAD_ROWS, LOAD_ROWS2  # noqa: E402
-from oracle import weights  # noqa: E402
+import synth as weights  # noqa: E402
 
 M = 64 * 641 * 101
 m = tsc_diffusion.TSCNet(64, 201, noise_schedule=[0.0] * 50)

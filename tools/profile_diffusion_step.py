@@ -7,7 +7,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import se_b200  # noqa: E402
 from se_b200 import tsc_diffusion  # noqa: E402
-from oracle import weights  # noqa: E402
+import synth as weights  # noqa: E402
 
 m = tsc_diffusion.TSCNet(64, 201, noise_schedule=[0.0] * 50)
 m.load_state_dict(weights.synth_state_dict(0, spec=weights.tsc_diffusion_spec()))

@@ -6,7 +6,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import se_b200  # noqa: E402
-from oracle import weights  # noqa: E402
+import synth as weights  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 L = int(sys.argv[2]) if len(sys.argv) > 2 else 64000
