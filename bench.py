@@ -38,16 +38,40 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="utterances per GPU per step (configs[1]: 64)")
-    ap.add_argument("--clip-seconds", type=float, default=4.0)
+    ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3, 4],
+                    help="BASELINE.json configs[i]: 1 = 64 x 4 s per GPU (default, the metric's configuration), 2 = 16 x 30 s per GPU, "
+                         "3 = 4096 x 4 s clips in total sharded across the ranks (job mode), 4 = GAN training step, 4 x 2 s per GPU (--train)")
+    ap.add_argument("--batch", type=int, default=None, help="utterances per GPU per step (default: what --config names)")
+    ap.add_argument("--clip-seconds", type=float, default=None)
     ap.add_argument("--engine", default=None, help="tcgen05 (default) | simt")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--train", action="store_true", help="BASELINE configs[4]: generator + metric discriminator training step (same as --config 4)")
     ap.add_argument("--graphs", action="store_true", help="replay a captured CUDA graph per step (small-batch latency mode)")
-    ap.add_argument("--cpu-sample-clips", type=int, default=6, help="clips of the batch the CPU oracle leg times (6 x 4 s ~ 11 s of CPU work on 16 cores)")
+    ap.add_argument("--cpu-sample-clips", type=int, default=4, help="clips of the batch the CPU legs time per step (4 x 4 s ~ 8 s of CPU work on 16 cores); "
+                                                                     "the cpu_baseline leg and --impl reference use the same sample")
+    ap.add_argument("--no-gpu-eager-baseline", action="store_true", help="skip the informational PyTorch-eager leg on the same GPU")
     ap.add_argument("--total-clips", type=int, default=0,
                     help="BASELINE configs[3]: enhance this many clips in total (4096), sharded across the ranks in micro-batches of "
                          "--batch, host buffers in and out; strong scaling.  One step = the whole job.")
-    return ap.parse_args()
+    args = ap.parse_args()
+    preset = {1: (64, 4.0, 0), 2: (16, 30.0, 0), 3: (64, 4.0, 4096), 4: (4, 2.0, 0)}[args.config]
+    if args.batch is None:
+        args.batch = preset[0]
+    if args.clip_seconds is None:
+        args.clip_seconds = preset[1]
+    if args.total_clips == 0:
+        args.total_clips = preset[2]
+    return args
+
+
+def workload_config(args, world: int):
+    """the `config` object of the JSON line: a function of the command line only, so the product arm and the reference arm print the same dict"""
+    B, sec = args.batch, args.clip_seconds
+    named = {(64, 4.0): "BASELINE configs[1]", (16, 30.0): "BASELINE configs[2]"}.get((B, sec), "not a BASELINE configuration")
+    return {"workload": f"generator hot path (RMS-norm, compressed STFT, TSCNet, iSTFT) on {B} x {sec:g} s 16 kHz utterances per GPU ({named})",
+            "batch_per_gpu": B, "clip_seconds": sec, "frames": int(sec * SR) // 100 + 1, "parallelism": f"batch-shard x{world}",
+            "gemm_engine": args.engine or "tcgen05", "dft_engine": "tcgen05", "cuda_graph": bool(args.graphs),
+            "l2": "per-step working set (tens of GB of activations) >> 126 MB L2; no flush needed"}
 
 
 # ------------------------------------------------------------------------------------------- clocks
@@ -124,21 +148,53 @@ def cpu_oracle_throughput(clips: int, clip_s: float, warmup: int, steps: int):
     return clips * clip_s / t, t, cores
 
 
+def cpu_sample_clips(args):
+    """clips per CPU step: bounded so that one step is ~10 s of host work whatever the clip length (30 s clips: one clip)"""
+    return max(1, min(args.cpu_sample_clips, int(16.0 / args.clip_seconds) or 1))
+
+
 def run_reference(args):
+    """the reference path on the host cores (oracle port, all threads) on the SAME bounded sample the product arm's cpu_baseline leg times"""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    clips = 1
-    val, t, cores = cpu_oracle_throughput(clips, args.clip_seconds, args.warmup, args.steps)
-    sample = f"{clips} x {args.clip_seconds:g} s clip per step (of the {args.batch}-clip batch), fp32, torch CPU, all host threads"
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    clips = cpu_sample_clips(args)
+    val, t, cores = cpu_oracle_throughput(clips, args.clip_seconds, min(args.warmup, 1), max(1, min(args.steps, 8)))
+    sample = (f"{clips} x {args.clip_seconds:g} s clips per step (of the {args.batch}-clip batch), fp32, torch CPU, all host threads; "
+              f"{min(args.warmup, 1)} warm-up + {max(1, min(args.steps, 8))} timed passes (bounded: the requested {args.steps} steps of ~{t:.0f} s each would not end within minutes)")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"generator hot path on {args.batch} x {args.clip_seconds:g} s 16 kHz utterances per GPU (BASELINE configs[1])",
-                       "batch_per_gpu": args.batch, "clip_seconds": args.clip_seconds},
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
             "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def gpu_eager_throughput(dev, clip_s: float, clips: int = 2, reps: int = 3):
+    """Informational (SURVEY section 0 calls it the real bar): the reference's algorithm in PyTorch EAGER on the same B200 -- the oracle port's
+    functions under torch.cuda (stock ATen / cuDNN / cuBLAS / cuFFT kernels, TF32 off), at a batch whose materialised (S, 4, n, n)
+    score tensors fit.  The unmodified reference cannot travel to the GPU box; the port issues the same stock ops."""
+    from oracle import tscnet_oracle as O
+    import synth as weights
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    sd = {k: v.to(dev) for k, v in weights.synth_state_dict(0).items()}
+    noisy, _ = weights.synth_wave(clips, int(clip_s * SR), seed=1234, kind="speech")
+    noisy = noisy.to(dev)
+    chunk = 64 if clip_s <= 4.0 else 4
+    with torch.no_grad():
+        O.predict(noisy, sd, chunk=chunk)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            O.predict(noisy, sd, chunk=chunk)
+        e1.record()
+        torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / reps
+    return {"value": clips * clip_s / (ms * 1e-3), "unit": "audio-s/s", "ms_per_step": ms, "kind": "port under torch.cuda (PyTorch eager, fp32, TF32 off)",
+            "sample": f"{clips} x {clip_s:g} s clips per step, attention in chunks of {chunk} sequences"}
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
@@ -266,11 +322,8 @@ def run_b200(args):
             "metric": METRIC, "value": audio_s / (dev_ms * 1e-3), "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"generator hot path (RMS-norm, compressed STFT, TSCNet, iSTFT) on {B} x {args.clip_seconds:g} s 16 kHz utterances per GPU (BASELINE configs[1])",
-                       "batch_per_gpu": B, "clip_seconds": args.clip_seconds, "frames": L // 100 + 1, "parallelism": f"batch-shard x{world}",
-                       "gemm_engine": model.engine, "dft_engine": enh.dft_engine, "cuda_graph": bool(args.graphs),
-                       "l2": "per-step working set (~40 GB of activations) >> 126 MB L2; no flush needed",
-                       "generator_fwd_ms_per_clip": dev_ms / args.steps / B},
+            "config": workload_config(args, world),
+            "generator_fwd_ms_per_clip": dev_ms / args.steps / B,
             "clocks": clocks,
             "e2e": {"value": audio_s / (e2e_ms * 1e-3), "unit": "audio-s/s", "h2d_bytes_per_step": noisy_host.numel() * 4,
                     "d2h_bytes_per_step": out_host.numel() * 4},
@@ -281,10 +334,19 @@ def run_b200(args):
             "kernel_shares": shares,
             "kernel_rooflines": kernel_rooflines,
         }
+        if world == 1 and not args.no_gpu_eager_baseline:
+            try:
+                del noisy
+                model._ws.clear()
+                torch.cuda.empty_cache()
+                line["gpu_eager_baseline"] = gpu_eager_throughput(dev, args.clip_seconds)
+            except Exception as exc:  # noqa: BLE001 -- informational leg: never fail the bench line
+                line["gpu_eager_baseline"] = {"unavailable": repr(exc)[:200]}
         if world == 1 and not args.no_cpu_baseline:
-            val, tsec, cores = cpu_oracle_throughput(args.cpu_sample_clips, args.clip_seconds, 0, 1)
+            clips = cpu_sample_clips(args)
+            val, tsec, cores = cpu_oracle_throughput(clips, args.clip_seconds, 0, 1)
             line["cpu_baseline"] = {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port",
-                                    "sample": f"{args.cpu_sample_clips} x {args.clip_seconds:g} s clips of the batch, one pass, oracle port (torch CPU fp32), {tsec:.1f} s"}
+                                    "sample": f"{clips} x {args.clip_seconds:g} s clips of the batch, one pass, oracle port (torch CPU fp32), {tsec:.1f} s"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -381,10 +443,16 @@ def run_job(args):
         dist.destroy_process_group()
 
 
+def run_train(args):
+    raise SystemExit("bench.py --train: the training step bench is not wired yet")
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == 4 or args.train:
+        run_train(args)
     elif args.total_clips > 0:
         run_job(args)
     else:

@@ -43,8 +43,11 @@ enum {
  */
 enum { SEB_LOAD_ROWS = 0, SEB_LOAD_ROWS_LN = 1, SEB_LOAD_CONV = 2, SEB_LOAD_HANKEL = 3,
        SEB_LOAD_CONV_SPLIT = 4, /* CONV on pre-split inputs: every pixel = 64 bf16 hi + 64 bf16 lo (256 bytes); tcgen05 engine only */
-       SEB_LOAD_ROWS2 = 5       /* K = 128: row m = (a[0][m, 0:64] | a[1][m, 0:64]), both with row stride lda: the two 1x1 convs of
-                                   MergeBlock (models/tsc_diffusion.py:21-22,32-34) as one contraction over [x | conditioner] */ };
+       SEB_LOAD_ROWS2 = 5,      /* K = 128: row m = (a[0][m, 0:64] | a[1][m, 0:64]), both with row stride lda: the two 1x1 convs of
+                                   MergeBlock (models/tsc_diffusion.py:21-22,32-34) as one contraction over [x | conditioner] */
+       SEB_LOAD_CONV_ADJ = 6    /* adjoint of CONV (training, dgrad): rows = pixels of the forward conv's input (M = B*T*Fout), a[0] = gradient
+                                   image of the forward conv's output [B, T, Fin, lda] (lda = 64 or 128 channels), nslots = lda / 64,
+                                   K = taps * lda in (tap, 64-channel part) order; taps_t / dil / stride_f as in the forward conv */ };
 enum {
   SEB_EPI_BIAS = 0,     /* out = acc + bias                                  */
   SEB_EPI_SWISH = 1,    /* v = acc + bias; out = v * sigmoid(v)              */
@@ -58,7 +61,10 @@ enum {
                            rows (the diffusion-step projection, constant per utterance; models/tsc_diffusion.py:27-37) */
   SEB_EPI_RESID_SCALE = 8 /* out = alpha * (acc + bias + resid): (x + output_residual(y)) / sqrt(2), tsc_diffusion.py:39-41 */
 };
-enum { SEB_ENGINE_TCGEN05 = 0, SEB_ENGINE_SIMT = 1 };
+enum { SEB_ENGINE_TCGEN05 = 0, SEB_ENGINE_SIMT = 1,
+       SEB_ENGINE_TCGEN05_F32 = 2 /* tcgen05 with THREE bf16 planes per operand (six products, fp32-grade; w_tc packed with planes = 3), fp32
+                                     inputs split on the fly: the training step's GEMMs (gradients of this network amplify forward
+                                     perturbations ~100x, so the two-plane split of the inference path is not enough there) */ };
 
 typedef struct SebGemm {
   int loader, epilogue;

@@ -9,6 +9,7 @@ int conv_persist_max_chunks();
 int launch_conv_y3(const SebGemm* s, const GemmArgs& g, cudaStream_t st);        // conv_y3.cu
 int conv_y3_enabled();
 int launch_tok_gemm(const SebGemm* s, const GemmArgs& g, cudaStream_t st);       // tok_gemm.cu (-100: not a persistent token GEMM)
+int launch_train_tc(const SebGemm* s, const GemmArgs& g, cudaStream_t st);       // gemm_train.cu: three-plane tcgen05 instantiations of the training step
 
 static GemmArgs to_args(const SebGemm* s) {
   GemmArgs g;
@@ -104,6 +105,12 @@ extern "C" int seb200_gemm(const SebGemm* s, int engine, void* stream) {
   if (s->loader == SEB_LOAD_ROWS_LN) {
     SEB_REQUIRE(s->K == 64 && s->ln_gamma && s->ln_beta, SEB_EINVAL, "gemm: LayerNorm loader needs K == 64 and gamma/beta");
   }
+  if (s->loader == SEB_LOAD_CONV_ADJ) {
+    SEB_REQUIRE((s->lda == 64 || s->lda == 128) && s->nslots == (int)(s->lda / 64) && (s->taps_t == 1 || s->taps_t == 2) && s->stride_f >= 1 && s->dil >= 1,
+                SEB_EINVAL, "gemm: bad adjoint-conv geometry");
+    SEB_REQUIRE(s->K == s->taps_t * 3 * (int)s->lda, SEB_EINVAL, "gemm: adjoint conv K=%d != taps*lda", s->K);
+    SEB_REQUIRE((long long)s->B * s->T * s->Fout == s->M, SEB_EINVAL, "gemm: adjoint conv M != B*T*Fout");
+  }
   if (s->loader == SEB_LOAD_CONV || s->loader == SEB_LOAD_CONV_SPLIT) {
     SEB_REQUIRE(s->nslots >= 1 && s->nslots <= 4 && (s->taps_t == 1 || s->taps_t == 2) && s->stride_f >= 1 && s->dil >= 1, SEB_EINVAL, "gemm: bad conv geometry");
     SEB_REQUIRE(s->K == s->taps_t * 3 * s->nslots * 64, SEB_EINVAL, "gemm: conv K=%d != taps*slots*64", s->K);
@@ -139,8 +146,14 @@ extern "C" int seb200_gemm(const SebGemm* s, int engine, void* stream) {
       case SEB_LOAD_ROWS_LN * 16 + SEB_EPI_GLU:     return launch_simt<SEB_LOAD_ROWS_LN, SEB_EPI_GLU>(s, g, st);
       case SEB_LOAD_ROWS_LN * 16 + SEB_EPI_BIAS:    return launch_simt<SEB_LOAD_ROWS_LN, SEB_EPI_BIAS>(s, g, st);
       case SEB_LOAD_ROWS_LN * 16 + SEB_EPI_QKV_F16: return launch_simt<SEB_LOAD_ROWS_LN, SEB_EPI_QKV_F16>(s, g, st);
+      case SEB_LOAD_CONV_ADJ * 16 + SEB_EPI_BIAS:   return launch_simt<SEB_LOAD_CONV_ADJ, SEB_EPI_BIAS>(s, g, st);
+      case SEB_LOAD_CONV_ADJ * 16 + SEB_EPI_RESID:  return launch_simt<SEB_LOAD_CONV_ADJ, SEB_EPI_RESID>(s, g, st);
+      case SEB_LOAD_CONV * 16 + SEB_EPI_RESID:      return launch_simt<SEB_LOAD_CONV, SEB_EPI_RESID>(s, g, st);
       default: break;
     }
+  } else if (engine == SEB_ENGINE_TCGEN05_F32) {
+    const int r = launch_train_tc(s, g, st);
+    if (r != -100) return r;
   } else if (engine == SEB_ENGINE_TCGEN05) {
     const int nt = s->tc_ntile;
     {

@@ -135,6 +135,33 @@ template <> struct Loader<SEB_LOAD_CONV> {
   }
 };
 
+// Adjoint of the implicit-GEMM convolution (training: dgrad of DilatedDenseNet / conv_2 / SPConvTranspose2d).
+// Rows are the pixels (b, t', f') of the forward conv's INPUT (M = B * T * g.Fout, g.Fout = forward input width); the A operand is the
+// gradient image of the forward conv's OUTPUT: [B, T, g.Fin, g.lda channels] (g.Fin = forward output width, g.lda = 64 or 128).
+// K order = (tap = kt * 3 + kf, 64-channel sub-chunk): chunk kc reads dY[b, t' + (taps_t - 1 - kt) * dil, (f' + 1 - kf) / stride_f, sub * 64 ..]
+// when that pixel exists (the forward conv read X[t - (taps_t - 1 - kt) * dil, fo * stride_f + kf - 1], so X[t', f'] fed exactly those outputs).
+template <> struct Loader<SEB_LOAD_CONV_ADJ> {
+  using Row = Loader<SEB_LOAD_CONV>::Row;
+  __device__ static void init_row(const GemmArgs& g, int m, Row& r) { Loader<SEB_LOAD_CONV>::init_row(g, m, r); }
+  __device__ static void load(const GemmArgs& g, const Row& r, int kc, int sub, float (&v)[8]) {
+    const int tap = kc / g.nslots;
+    const int part = kc - tap * g.nslots;
+    const int kt = (g.taps_t == 2) ? tap / 3 : 0;
+    const int kf = tap - kt * 3;
+    const int tt = r.t + (g.taps_t - 1 - kt) * g.dil;
+    const int num = r.f + 1 - kf;
+    const int ff = num / g.stride_f;
+    if (r.b >= 0 && tt < g.T && num >= 0 && ff * g.stride_f == num && ff < g.Fin) {
+      const float* p = g.a[0] + (((long long)r.b * g.T + tt) * g.Fin + ff) * g.lda + part * 64 + sub * 8;
+      float4 x = ldg4(p), y = ldg4(p + 4);
+      v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    }
+  }
+};
+
 // STFT framing: row (b, t) is the overlapping window xpad[b, t*hop : t*hop + n_fft] (no copy).
 // g.Fin = n_fft (400), g.stride_f = hop (100), g.T = frames per utterance, g.lda = samples per row of xpad.
 template <> struct Loader<SEB_LOAD_HANKEL> {
@@ -519,6 +546,10 @@ gemm_tc_kernel(const GemmArgs g, const uint8_t* __restrict__ w_tc) {
     // contiguous bytes of one row and the epilogue functors see a coalesced (row, column) mapping.
     ptx::mbar_wait(&accum_bar, 0);
     ptx::tc_fence_after();
+    // every producer's operand stores into the ring precede its last full_bar arrival, and accum_bar completes only after the MMAs that read
+    // them: the ring is free for the staging tile.  The named barrier restates that order in a form compute-sanitizer's racecheck models
+    // (it tracks bar.sync, not mbarrier chains); a few cycles per CTA.
+    asm volatile("bar.sync 1, %0;" ::"n"(PW * 32) : "memory");
     const int wq = warp & 3, half = warp >> 2;
     constexpr int HALF_COLS = NT / (PW / 4);     // columns per epilogue warp; multiple of 8
     const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(half * HALF_COLS);
@@ -698,6 +729,7 @@ conv_split_tc_kernel(const GemmArgs g, const uint8_t* __restrict__ w_tc) {
     // ---------------- epilogue (identical to gemm_tc_kernel) ----------------
     ptx::mbar_wait(&accum_bar, 0);
     ptx::tc_fence_after();
+    asm volatile("bar.sync 1, 256;" ::: "memory");     // see gemm_tc_kernel: orders the ring's cp.async writes before the staging stores for racecheck
     const int wq = warp & 3, half = warp >> 2;
     constexpr int HALF_COLS = NT / 2;
     const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(half * HALF_COLS);
