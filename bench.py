@@ -54,6 +54,8 @@ def parse():
                     help="BASELINE configs[3]: enhance this many clips in total (4096), sharded across the ranks in micro-batches of "
                          "--batch, host buffers in and out; strong scaling.  One step = the whole job.")
     args = ap.parse_args()
+    if args.train:
+        args.config = 4
     preset = {1: (64, 4.0, 0), 2: (16, 30.0, 0), 3: (64, 4.0, 4096), 4: (4, 2.0, 0)}[args.config]
     if args.batch is None:
         args.batch = preset[0]
@@ -443,8 +445,197 @@ def run_job(args):
         dist.destroy_process_group()
 
 
+TRAIN_METRIC = "audio_seconds_trained_per_second"
+LOSS_WEIGHTS = (0.3, 0.7, 0.2, 0.05)          # config/scp.yaml:7
+
+
+def train_config(args, world):
+    return {"workload": f"GAN training step (generator + metric discriminator fwd/bwd, arch scp: consistency-preserving losses), {args.batch} x {args.clip_seconds:g} s "
+                        f"clips per GPU, gradient all-reduce over {world} GPU(s) (BASELINE configs[4])",
+            "batch_per_gpu": args.batch, "clip_seconds": args.clip_seconds, "frames": int(args.clip_seconds * SR) // 100 + 1,
+            "parallelism": f"data-parallel x{world} (SyncBatchNorm statistics + one flat 7.34 MB gradient all-reduce; discriminator under DistributedDataParallel)",
+            "generator_engine": args.engine or "tcgen05_f32", "optimizer": "AdamW (fused)", "pesq_labels": "fixed tensor (pesq is not installed, SURVEY 8d cfg 5)",
+            "l2": "per-step working set ~10 GB of saved activations >> 126 MB L2; no flush needed"}
+
+
+def _gan_step(se_b200, model, disc, opt_g, opt_d, batch, cfg, args_ns, world, mse, timers=None):
+    """one iteration of train_gan (core/function.py:206-317, arch scp) on the CUDA generator; `timers`: dict of (start, end) event lists"""
+    import torch.nn.functional as F
+
+    def tick(name):
+        if timers is None:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        timers.setdefault(name, []).append(e)
+        return e
+
+    tick("start")
+    opt_g.zero_grad(set_to_none=True)
+    clean, noisy, clean_spec, noisy_spec, clean_real, clean_imag, one_labels, win = se_b200.batch_stft(batch, args_ns, cfg)
+    tick("stft")
+    est_real, est_imag = model(noisy_spec)
+    tick("gen_fwd")
+    est_real, est_imag = est_real.permute(0, 1, 3, 2), est_imag.permute(0, 1, 3, 2)
+    est_complex = torch.complex(est_real, est_imag).squeeze(1)
+    est_mag = est_complex.abs().unsqueeze(1)
+    clean_mag = clean_spec.abs().unsqueeze(1)
+    est_audio = se_b200.uncompressed_istft(est_complex, 400, 100, win)
+    est_prime = se_b200.compressed_stft(est_audio, 400, 100, win)                       # consistency branch (:231-254)
+    with torch.no_grad():
+        clean_prime_audio = se_b200.uncompressed_istft(clean_spec, 400, 100, win)
+        clean_prime = se_b200.compressed_stft(clean_prime_audio, 400, 100, win)
+    loss_mag = mse(est_prime.abs(), clean_prime.abs())
+    time_loss = torch.mean(torch.abs(est_audio - clean_prime_audio))
+    loss_ri = mse(est_prime.real, clean_prime.real) + mse(est_prime.imag, clean_prime.imag)
+    gan = mse(disc(clean_mag, est_mag).flatten(), one_labels.float())
+    loss = LOSS_WEIGHTS[0] * loss_ri + LOSS_WEIGHTS[1] * loss_mag + LOSS_WEIGHTS[2] * time_loss + LOSS_WEIGHTS[3] * gan
+    tick("losses_fwd")
+    loss.backward()
+    tick("gen_bwd")
+    se_b200.allreduce_gradients(model)
+    tick("allreduce")
+    opt_g.step()
+    tick("opt_g")
+    # ---- discriminator step (:279-313); PESQ labels are a fixed tensor
+    opt_d.zero_grad(set_to_none=True)
+    q = torch.full_like(one_labels, 0.6)
+    d_loss = mse(disc(clean_mag, est_mag.detach()).flatten(), q) + mse(disc(clean_mag, clean_mag).flatten(), one_labels) + \
+        mse(disc(clean_mag, noisy_spec.abs().unsqueeze(1)).flatten(), torch.full_like(one_labels, 0.3))
+    d_loss.backward()
+    opt_d.step()
+    tick("disc")
+    return loss.detach(), d_loss.detach()
+
+
 def run_train(args):
-    raise SystemExit("bench.py --train: the training step bench is not wired yet")
+    """BASELINE configs[4]: one GAN training step per bench step, B clips of clip_seconds per GPU, weak scaling."""
+    import types
+    import torch.distributed as dist
+    import torch.nn as nn
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --train: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import se_b200
+    from se_b200.discriminator import Discriminator
+    import synth as weights
+    torch.manual_seed(1234)
+    model = se_b200.TSCNet(num_channel=64, num_features=201)
+    model.load_state_dict(weights.synth_state_dict(0))
+    disc = Discriminator(16)
+    if world > 1:                                   # main_gan.py:154-171
+        model = nn.SyncBatchNorm.convert_sync_batchnorm(model)
+    model, disc = model.to(dev).train(), disc.to(dev).train()
+    st = se_b200.training._state(model)
+    if args.engine:
+        st.engine = args.engine
+    disc_run = nn.parallel.DistributedDataParallel(disc, device_ids=[local]) if world > 1 else disc
+    opt_g = torch.optim.AdamW(model.parameters(), lr=5e-4, fused=True)
+    opt_d = torch.optim.AdamW(disc.parameters(), lr=1e-3, fused=True)
+    mse = nn.MSELoss()
+    B, L = args.batch, int(args.clip_seconds * SR)
+    noisy, clean = weights.synth_wave(B, L, seed=1234 + rank, kind="speech")
+    host = {"audio": clean.pin_memory(), "noisy": noisy.pin_memory()}
+    cfg = types.SimpleNamespace(N_FFT=400, HOP_SAMPLES=100)
+    args_ns = types.SimpleNamespace(gpu=local)
+
+    def step(timers=None):
+        return _gan_step(se_b200, model, disc_run, opt_g, opt_d, host, cfg, args_ns, world, mse, timers)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    timers = {}
+    step(timers)                                    # one instrumented step: phase breakdown
+    torch.cuda.synchronize()
+    order = ["start", "stft", "gen_fwd", "losses_fwd", "gen_bwd", "allreduce", "opt_g", "disc"]
+    phases = {order[i + 1]: timers[order[i]][0].elapsed_time(timers[order[i + 1]][0]) for i in range(len(order) - 1)}
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = se_b200._lib.launch_count()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        g_loss, d_loss = step()
+    e1.record()
+    barrier()
+    launches = se_b200._lib.launch_count() - launches0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        ms = float(ms[0])
+        audio_s = world * B * args.clip_seconds * args.steps
+        val = audio_s / (ms * 1e-3)
+        # roofline of the step's dominant phase: generator backward, algorithmic FLOPs = 2 x forward (dgrad + wgrad of every contraction)
+        T = L // 100 + 1
+        fwd_flops = B * (643200.0 * T + 101.36e6 * T + 109.4e6 * T + 404.0 * T * (480640.0 + 384.0 * T))
+        pk = peaks()
+        bwd_tf = 2.0 * fwd_flops / (phases["gen_bwd"] * 1e-3) / 1e12
+        line = {"metric": TRAIN_METRIC, "value": val, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": train_config(args, world), "clocks": clocks,
+                "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 2 * B * L * 4, "d2h_bytes_per_step": 0,
+                        "note": "every step starts from pinned host waveforms (batch_stft copies them to the device), as the reference's loader does"},
+                "gpu_launches": int(launches),
+                "phases_ms": {k: round(v, 3) for k, v in phases.items()},
+                "collective": {"gradient_allreduce_bytes": 1834833 * 4, "allreduce_ms": round(phases["allreduce"], 3),
+                               "syncbn_allreduces_per_step": 16 if world > 1 else 0, "limiting": "latency (7.34 MB + 16 x 2 KB): NCCL launch + NVLS one-shot"},
+                "roofline": {"kernel": "generator backward (all kernels)", "bound": "tensor", "achieved": bwd_tf, "peak": pk["tflops"], "unit": "TFLOP/s",
+                             "frac": bwd_tf / pk["tflops"], "traffic": None, "peak_source": pk["src"], "ms": phases["gen_bwd"]},
+                "losses": {"generator": float(g_loss), "discriminator": float(d_loss)}}
+        if world == 1 and not args.no_gpu_eager_baseline:
+            try:
+                line["gpu_eager_baseline"] = gpu_eager_train(dev, B, L)
+            except Exception as exc:  # noqa: BLE001
+                line["gpu_eager_baseline"] = {"unavailable": repr(exc)[:200]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def gpu_eager_train(dev, B, L, reps=3):
+    """Informational: generator forward + backward of the reference's algorithm in PyTorch eager on the same GPU (oracle port with autograd,
+    train mode, its own dropout draw), fp32, TF32 off -- the part of the step the CUDA generator replaces."""
+    from oracle import tscnet_oracle as O
+    import synth as weights
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    sd = {k: (v.to(dev).requires_grad_(v.is_floating_point() and "running_" not in k)) for k, v in weights.synth_state_dict(0).items()}
+    noisy, _ = weights.synth_wave(B, L, seed=1234, kind="speech")
+    c = torch.sqrt(L / torch.sum(noisy ** 2.0, dim=-1, keepdim=True))
+    spec = O.compressed_stft((noisy * c).to(dev))
+    T = spec.shape[-1]
+    masks = {k: v.to(dev) for k, v in weights.masks_reference_layout(weights.dropout_masks(0, B, T, 101)).items()}
+
+    def once():
+        tr = O.TrainCtx(masks)
+        fr, fi = O.tscnet_forward(spec, sd, tr=tr)
+        (fr.square().mean() + fi.square().mean()).backward()
+        for v in sd.values():
+            v.grad = None
+    once()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        once()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / reps
+    return {"generator_fwd_bwd_ms": ms, "kind": "port under torch.cuda with autograd (PyTorch eager, fp32, TF32 off)", "sample": f"{B} x {L / SR:g} s clips"}
 
 
 def main():

@@ -194,6 +194,97 @@ int seb200_dwconv_bn_swish(const float* x, const SebSeq* seq, const float* w, co
 int seb200_layernorm_residual(const float* x, long long tokens, const float* gamma, const float* beta,
                               const float* resid, float* out, void* stream);
 
+/* ---- training step (SURVEY 8f row f1 / 8e training): train-mode forward pieces and the backward of every op of the generator ----------
+ * Reference: model(noisy_spec) under model.train() (core/function.py:221), loss.backward() (:274), SyncBatchNorm (main_gan.py:154-155),
+ * DDP gradient all-reduce (main_gan.py:168-171).  Dense contractions go through seb200_gemm (forward: the layer's own descriptor; dgrad:
+ * the same contraction with the transposed weight image, or SEB_LOAD_CONV_ADJ) with engine SEB_ENGINE_TCGEN05_F32 or SEB_ENGINE_SIMT;
+ * weight gradients through seb200_wgrad.  Weight images are rebuilt on the device from the live parameters every step
+ * (seb200_pack_weights_device).  Reductions are two-stage and deterministic (no atomics on global memory); `workspace` buffers are scratch
+ * of at least seb200_train_workspace_floats() floats (or doubles where the parameter is double*), unless a size query is named. */
+long long seb200_train_workspace_floats(void);
+
+/* W[n, k] = w[n * sn + (k / n1) * s0 + (k % n1) * s1] (k < K) packed into the tcgen05 image (planes 2 or 3) and / or the K-major fp32
+ * image, all in DEVICE memory; same bytes as seb200_pack_weights.  The index map covers Linear weights and their transposes (dgrad) and
+ * Conv2d weights [Cout, Cin, kt, kf] in the engine's K order (tap, cin) and their per-slot adjoints (csrc/pack_dev.cu). */
+int seb200_pack_weights_device(const float* w, int N, int K, int n1, long long sn, long long s0, long long s1, int tc_ntile, int planes,
+                               void* w_tc, float* w_simt, void* stream);
+
+/* dW[n, k] = sum_m g_out[m, n] * A[m, k], db[n] = sum_m g_out[m, n]: `a` is the FORWARD GEMM's descriptor (loader ROWS / ROWS_LN / CONV, a[],
+ * lda, ln_*, conv geometry, M, K; weight / output fields ignored), g_out [M, N] with row stride ldg, N a multiple of 64 (<= 256).
+ * dW lands at dw[n * sn + (k / n1) * s0 + (k % n1) * s1] for k < k_logical (the parameter's own layout); db [N] or NULL. */
+int seb200_wgrad_splits(int M, int N, int K);
+long long seb200_wgrad_workspace_floats(int M, int N, int K);
+int seb200_wgrad(const SebGemm* a, const float* g_out, long long ldg, int N, int k_logical, int n1, long long sn, long long s0, long long s1,
+                 float* dw, float* db, float* workspace, long long workspace_floats, void* stream);
+
+/* nn.Dropout keep-mask (conformer.py:125,139,141), Philox4x32-10: mask[i] = (u_i >= p), u_i from counter offset + i / 4, key seed.  Every
+ * consumer below takes the mask as an explicit pointer (uint8, 1 = keep; NULL = no dropout), so a caller may inject its own draw. */
+int seb200_dropout_mask(unsigned char* mask, long long n, float p, unsigned long long seed, unsigned long long offset, void* stream);
+/* h = swish(a) * keep * scale (conformer.py:138-139); backward da = dh * keep * scale * swish'(a).  n % 4 == 0. */
+int seb200_swish_dropout(const float* a, const unsigned char* mask, float scale, float* h, long long n, void* stream);
+int seb200_swish_dropout_bwd(const float* a, const unsigned char* mask, float scale, const float* dh, float* da, long long n, void* stream);
+/* y = resid + scale * keep * t (dropout, Scale(0.5) and the block residual, conformer.py:60,141,207-210; resid may alias y);
+ * backward of the branch: dt = scale * keep * dy */
+int seb200_dropout_residual(const float* t, const unsigned char* mask, float scale, const float* resid, float* y, long long n, void* stream);
+int seb200_scale_mask(const float* dy, const unsigned char* mask, float scale, float* dt, long long n, void* stream);
+/* GLU in the natural channel order (conformer.py:30-38): a [M, 2C] = (value | gate) -> u [M, C] = value * sigmoid(gate); backward da [M, 2C] */
+int seb200_glu(const float* a, long long M, int C, float* u, void* stream);
+int seb200_glu_bwd(const float* a, const float* du, long long M, int C, float* da, void* stream);
+/* LayerNorm(64) backward (conformer.py:67,162,204): dx = (add ? add : 0) + dLN(x; dy) (add may alias dx), dgamma / dbeta [64] */
+int seb200_layernorm_bwd(const float* x, const float* gamma, const float* dy, const float* add, float* dx, long long tokens,
+                         float* dgamma, float* dbeta, float* workspace, void* stream);
+/* BatchNorm1d(128) in train mode (conformer.py:167) on c [M, 128].  seb200_bn_sums: LOCAL sums[0:128] = sum c, [128:256] = sum c^2 (fp64).
+ * Under SyncBatchNorm (main_gan.py:154) the caller all-reduces `sums` and the token count across ranks, then seb200_bn_finalize turns
+ * them into batch mean | rstd (mean_rstd [256]), the folded scale | shift (scale_shift [256]) and updates running_mean / running_var
+ * (momentum, unbiased variance) and num_batches_tracked (any of the three may be NULL).  seb200_bn_swish: v = swish(scale * c + shift). */
+int seb200_bn_sums(const float* c, long long M, double* sums, double* workspace, void* stream);
+int seb200_bn_finalize(const double* sums, double count, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                       long long* num_batches_tracked, float momentum, float eps, float* scale_shift, float* mean_rstd, void* stream);
+int seb200_bn_swish(const float* c, long long M, const float* scale_shift, float* v, void* stream);
+/* backward of v = swish(BN(c)): LOCAL sums[0:128] = sum dz, [128:256] = sum dz * chat (all-reduced under SyncBatchNorm), then
+ * dc = gamma * rstd * (dz - S1 / count - chat * S2 / count) with the global sums; dgamma = S2, dbeta = S1 of `sums_local` (this rank's own
+ * sums as SyncBatchNorm returns them -- the data-parallel gradient all-reduce adds the ranks; NULL = sums) */
+int seb200_bn_swish_bwd_sums(const float* c, const float* dv, long long M, const float* scale_shift, const float* mean_rstd, double* sums,
+                             double* workspace, void* stream);
+int seb200_bn_swish_bwd_apply(const float* c, const float* dv, long long M, const float* scale_shift, const float* mean_rstd, const double* sums,
+                              const double* sums_local, double count, float* dc, float* dgamma, float* dbeta, void* stream);
+/* y = scale * DWConv31(x; w) + shift per channel, no activation (w [31][128] tap-major): the train-mode forward of DepthWiseConv1d
+ * (conformer.py:40-48) with scale = 1, shift = bias, and its data gradient with reversed taps, scale = 1, shift = 0 */
+int seb200_dwconv(const float* x, const SebSeq* seq, const float* w, const float* scale, const float* shift, float* y, void* stream);
+/* depthwise weight gradient in the parameter layout (128, 1, 31) and bias gradient [128] from the input u and the output gradient dc */
+int seb200_dwconv_wgrad(const float* u, const float* dc, const SebSeq* seq, float* dw, float* db, float* workspace, void* stream);
+/* InstanceNorm2d(affine) + PReLU backward (generator.py:21-22,40-41,46-47,101-102,120-121), C = 64 or 1: x the normalisation's input,
+ * stats from seb200_inorm_stats, dy the gradient of the PReLU output -> dx, dgamma / dbeta / dslope [C] */
+long long seb200_inorm_bwd_workspace_doubles(int B, long long pix_per_b, int C);
+int seb200_inorm_prelu_bwd(const float* x, const float* dy, int B, long long pix_per_b, int C, const float* stats, const float* gamma,
+                           const float* beta, const float* slope, float* dx, float* dgamma, float* dbeta, float* dslope,
+                           double* workspace, long long workspace_doubles, void* stream);
+/* decoder heads Conv2d(64 -> NO, (1, 2)), NO = 1 (MaskDecoder.conv_1) or 2 (ComplexDecoder.conv), generator.py:100,122, with the weight
+ * in the PARAMETER layout (NO, 64, 1, 2) and the bias by pointer: x [rows, Fin, 64] -> out [rows, Fin - 1, NO]; backward dx, dw, db */
+int seb200_head_conv(const float* x, long long rows, int Fin, const float* w, const float* bias, int NO, float* out, void* stream);
+int seb200_head_conv_bwd(const float* x, const float* dout, long long rows, int Fin, const float* w, int NO, float* dx, float* dw, float* db,
+                         float* workspace, void* stream);
+/* seb200_mask_recombine with the five scalars read through device pointers (norm.weight, norm.bias, prelu.weight, final_conv.weight,
+ * final_conv.bias: they change every optimizer step), and the backward of  est = PReLU_f(wf * p1 + bf) * (re, im) + cplx  w.r.t.
+ * p1 = PReLU(IN(mask_raw)): dp1 [B*T, F], dslope_f [F], dwf, dbf (the gradient w.r.t. cplx is d_est itself) */
+int seb200_mask_recombine_dev(const float* mask_raw, const float* mask_stats, int B, long long rows_per_b, int F, const float* const* scalars5,
+                              const float* slope_f, const float* in3, const float* cplx, float* est, void* stream);
+int seb200_mask_tail_bwd(const float* mask_raw, const float* mask_stats, int B, long long rows_per_b, int F, const float* const* scalars5,
+                         const float* slope_f, const float* in3, const float* dest, float* dp1, float* dslope_f, float* dwf, float* dbf,
+                         float* workspace, void* stream);
+/* DenseEncoder.conv_1[0] weight gradient: dw [64][3], db [64] from in3 [pixels, 3] and the output gradient g [pixels, 64] */
+int seb200_conv1x1_in3_wgrad(const float* in3, const float* g, long long pixels, float* dw, float* db, float* workspace, void* stream);
+/* (d final_real, d final_imag) (B, 1, T, F) -> d_est [B*T, F, 2]: the inverse of seb200_split_ri */
+int seb200_merge_ri(const float* re, const float* im, long long n, float* est, void* stream);
+/* fp32 q|k|v [M, 192] -> the fp16 copy (q scaled by 0.25 * log2 e) seb200_attention variants 0 / 3 read */
+int seb200_qkv_to_f16(const float* qkv, long long M, void* out, void* stream);
+/* fp32-grade attention core for training (3xTF32 mma.sync): qkv fp32 [tokens, 192] unscaled -> out [tokens, 64] and lse [tokens, 4];
+ * backward from (qkv, out, lse, dout) to dqkv [tokens, 192] and the gradient of rel_pos_emb [1025, 16] under the +-512 clamp */
+int seb200_attention_train_fwd(const float* qkv, const float* rel_pos_emb, const SebSeq* seq, float* out, float* lse, void* stream);
+long long seb200_attention_bwd_workspace_floats(long long tokens);
+int seb200_attention_bwd(const float* qkv, const float* rel_pos_emb, const SebSeq* seq, long long tokens, const float* out, const float* lse,
+                         const float* dout, float* dqkv, float* drel, float* workspace, long long workspace_floats, void* stream);
+
 /* ---- diffusion variant (models/tsc_diffusion.py) ------------ */
 /* MergeBlock's diffusion-step branch (tsc_diffusion.py:27-29 + models/DiffuSE.py:46-62) folded into a per-step bias of the
  * merge GEMM:  e = table[step] (integer step) or lerp(table[floor], table[ceil]) (fractional step);

@@ -14,9 +14,9 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libseb200.so")
 
-LOAD_ROWS, LOAD_ROWS_LN, LOAD_CONV, LOAD_HANKEL, LOAD_CONV_SPLIT, LOAD_ROWS2 = 0, 1, 2, 3, 4, 5
+LOAD_ROWS, LOAD_ROWS_LN, LOAD_CONV, LOAD_HANKEL, LOAD_CONV_SPLIT, LOAD_ROWS2, LOAD_CONV_ADJ = 0, 1, 2, 3, 4, 5, 6
 EPI_BIAS, EPI_SWISH, EPI_GLU, EPI_RESID, EPI_SUBPIXEL, EPI_COMPRESS, EPI_QKV_F16, EPI_GATE, EPI_RESID_SCALE = 0, 1, 2, 3, 4, 5, 6, 7, 8
-ENGINE_TCGEN05, ENGINE_SIMT = 0, 1
+ENGINE_TCGEN05, ENGINE_SIMT, ENGINE_TCGEN05_F32 = 0, 1, 2
 ABI_VERSION = 2          # SEB200_ABI_VERSION in include/seb200.h
 
 _fp = C.c_void_p  # raw device pointers travel as void*
@@ -79,10 +79,47 @@ _SIGS = {
     "seb200_istft_grad_pad": [_fp, _fp, C.c_int, C.c_int, _fp, _fp],
     "seb200_decompress_backward_spec": [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp],
     "seb200_diffusion_update": [_fp, _fp, C.c_longlong, _fp, _fp, C.c_int, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float, _fp, _fp, _fp],
+    # ---- training step
+    "seb200_pack_weights_device": [_fp, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int, C.c_int, _fp, _fp, _fp],
+    "seb200_wgrad": [C.POINTER(SebGemm), _fp, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_longlong, C.c_longlong, _fp, _fp, _fp, C.c_longlong, _fp],
+    "seb200_dropout_mask": [_fp, C.c_longlong, C.c_float, C.c_ulonglong, C.c_ulonglong, _fp],
+    "seb200_swish_dropout": [_fp, _fp, C.c_float, _fp, C.c_longlong, _fp],
+    "seb200_swish_dropout_bwd": [_fp, _fp, C.c_float, _fp, _fp, C.c_longlong, _fp],
+    "seb200_dropout_residual": [_fp, _fp, C.c_float, _fp, _fp, C.c_longlong, _fp],
+    "seb200_scale_mask": [_fp, _fp, C.c_float, _fp, C.c_longlong, _fp],
+    "seb200_glu": [_fp, C.c_longlong, C.c_int, _fp, _fp],
+    "seb200_glu_bwd": [_fp, _fp, C.c_longlong, C.c_int, _fp, _fp],
+    "seb200_layernorm_bwd": [_fp, _fp, _fp, _fp, _fp, C.c_longlong, _fp, _fp, _fp, _fp],
+    "seb200_bn_sums": [_fp, C.c_longlong, _fp, _fp, _fp],
+    "seb200_bn_finalize": [_fp, C.c_double, _fp, _fp, _fp, _fp, _fp, C.c_float, C.c_float, _fp, _fp, _fp],
+    "seb200_bn_swish": [_fp, C.c_longlong, _fp, _fp, _fp],
+    "seb200_bn_swish_bwd_sums": [_fp, _fp, C.c_longlong, _fp, _fp, _fp, _fp, _fp],
+    "seb200_bn_swish_bwd_apply": [_fp, _fp, C.c_longlong, _fp, _fp, _fp, _fp, C.c_double, _fp, _fp, _fp, _fp],
+    "seb200_dwconv": [_fp, C.POINTER(SebSeq), _fp, _fp, _fp, _fp, _fp],
+    "seb200_dwconv_wgrad": [_fp, _fp, C.POINTER(SebSeq), _fp, _fp, _fp, _fp],
+    "seb200_inorm_prelu_bwd": [_fp, _fp, C.c_int, C.c_longlong, C.c_int, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_longlong, _fp],
+    "seb200_head_conv": [_fp, C.c_longlong, C.c_int, _fp, _fp, C.c_int, _fp, _fp],
+    "seb200_head_conv_bwd": [_fp, _fp, C.c_longlong, C.c_int, _fp, C.c_int, _fp, _fp, _fp, _fp, _fp],
+    "seb200_mask_recombine_dev": [_fp, _fp, C.c_int, C.c_longlong, C.c_int, C.POINTER(_fp), _fp, _fp, _fp, _fp, _fp],
+    "seb200_mask_tail_bwd": [_fp, _fp, C.c_int, C.c_longlong, C.c_int, C.POINTER(_fp), _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp],
+    "seb200_conv1x1_in3_wgrad": [_fp, _fp, C.c_longlong, _fp, _fp, _fp, _fp],
+    "seb200_merge_ri": [_fp, _fp, C.c_longlong, _fp, _fp],
+    "seb200_qkv_to_f16": [_fp, C.c_longlong, _fp, _fp],
+    "seb200_attention_train_fwd": [_fp, _fp, C.POINTER(SebSeq), _fp, _fp, _fp],
+    "seb200_attention_bwd": [_fp, _fp, C.POINTER(SebSeq), C.c_longlong, _fp, _fp, _fp, _fp, _fp, _fp, C.c_longlong, _fp],
     "seb200_diffusion_embed": [_fp, C.c_int, _fp, C.c_int, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp],
 }
-EXPORTS = sorted(list(_SIGS) + ["seb200_inorm_workspace_bytes", "seb200_workspace_bytes", "seb200_version", "seb200_last_error_string",
-                                "seb200_launch_count"])
+_LL_FUNCS = {      # size queries returning long long (or int): name -> argtypes
+    "seb200_inorm_workspace_bytes": [C.c_int, C.c_longlong, C.c_int],
+    "seb200_workspace_bytes": [C.c_int, C.c_int, C.c_int, C.c_int],
+    "seb200_train_workspace_floats": [],
+    "seb200_wgrad_workspace_floats": [C.c_int, C.c_int, C.c_int],
+    "seb200_wgrad_splits": [C.c_int, C.c_int, C.c_int],
+    "seb200_inorm_bwd_workspace_doubles": [C.c_int, C.c_longlong, C.c_int],
+    "seb200_attention_bwd_workspace_floats": [C.c_longlong],
+    "seb200_launch_count": [],
+}
+EXPORTS = sorted(list(_SIGS) + list(_LL_FUNCS) + ["seb200_version", "seb200_last_error_string"])
 
 _lock = threading.Lock()
 _lib = None
@@ -112,13 +149,12 @@ def load(build_if_missing: bool = True):
             fn = getattr(lib, name)
             fn.argtypes = args
             fn.restype = C.c_int
-        lib.seb200_inorm_workspace_bytes.argtypes = [C.c_int, C.c_longlong, C.c_int]
-        lib.seb200_inorm_workspace_bytes.restype = C.c_longlong
-        lib.seb200_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
-        lib.seb200_workspace_bytes.restype = C.c_longlong
+        for name, args in _LL_FUNCS.items():
+            fn = getattr(lib, name)
+            fn.argtypes = args
+            fn.restype = C.c_int if name == "seb200_wgrad_splits" else C.c_longlong
         lib.seb200_version.restype = C.c_int
         lib.seb200_last_error_string.restype = C.c_char_p
-        lib.seb200_launch_count.restype = C.c_longlong
         _lib = lib
         return lib
 

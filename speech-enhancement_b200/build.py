@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libseb200.so")
 OBJ_DIR = os.path.join(CSRC, "build")
-SOURCES = ["core.cu", "gemm_api.cu", "gemm_train.cu", "tok_gemm.cu", "conv_y3.cu", "conv_persist.cu", "ffn_fused.cu", "dsp.cu", "norm_act.cu", "attention.cu", "attention_tc.cu", "dwconv.cu", "merge.cu", "pack.cu", "dsp_bwd.cu"]
+SOURCES = ["core.cu", "gemm_api.cu", "gemm_train.cu", "tok_gemm.cu", "conv_y3.cu", "conv_persist.cu", "ffn_fused.cu", "dsp.cu", "norm_act.cu", "attention.cu", "attention_tc.cu", "dwconv.cu", "merge.cu", "pack.cu", "dsp_bwd.cu", "pack_dev.cu", "wgrad.cu", "train_elem.cu", "attention_train.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 NVCC_FLAGS += os.environ.get("SEB200_NVCC_EXTRA", "").split()      # experiment switches (-DSEB_...=n); part of the build digest

@@ -13,6 +13,7 @@ constexpr int DW_TI = 64, DW_K = 31, DW_PAD = 15, DW_C = 128;
 // of it are live next to the 31 float2 taps.
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 
+template <bool SWISH>
 __global__ void __launch_bounds__(128, 3) dwconv_bn_swish_kernel(const float* __restrict__ x, const SebSeq sq,
                                                                 const float* __restrict__ w, const float* __restrict__ bn_scale,
                                                                 const float* __restrict__ bn_shift, float* __restrict__ y, int nchunks) {
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(128, 3) dwconv_bn_swish_kernel(const float* __
       const int i = i0 + gpos + o;
       if (i < sq.n) {
         float2 v = ffma2(acc[o], sc, sh);
-        v.x *= sigmoidf_acc(v.x); v.y *= sigmoidf_acc(v.y);
+        if (SWISH) { v.x *= sigmoidf_acc(v.x); v.y *= sigmoidf_acc(v.y); }
         *reinterpret_cast<float2*>(y + (base + (long long)i * sq.pos_stride) * DW_C + cp * 2) = v;
       }
     }
@@ -92,7 +93,21 @@ extern "C" int seb200_dwconv_bn_swish(const float* x, const SebSeq* seq, const f
   const int nchunks = (seq->n + DW_TI - 1) / DW_TI;
   const long long nblocks = (long long)seq->nseq * nchunks;
   SEB_REQUIRE(nblocks < 2147483647LL, SEB_EINVAL, "dwconv: grid too large");
-  dwconv_bn_swish_kernel<<<(unsigned)nblocks, 128, 0, (cudaStream_t)stream>>>(x, *seq, w, bn_scale, bn_shift, y, nchunks);
+  dwconv_bn_swish_kernel<true><<<(unsigned)nblocks, 128, 0, (cudaStream_t)stream>>>(x, *seq, w, bn_scale, bn_shift, y, nchunks);
   SEB_CHECK_LAUNCH("dwconv_bn_swish_kernel");
+  return 0;
+}
+
+// The depthwise convolution alone, y = scale * DWConv31(x; w) + shift per channel (training step): with scale = 1,
+// shift = conv bias it is the train-mode forward (BatchNorm1d then needs the batch statistics of y, conformer.py:166-167); with the taps
+// reversed, scale = 1, shift = 0 it is the convolution's data gradient.  w [31][128] tap-major.
+extern "C" int seb200_dwconv(const float* x, const SebSeq* seq, const float* w, const float* scale, const float* shift, float* y, void* stream) {
+  SEB_REQUIRE(x && seq && w && scale && shift && y, SEB_EINVAL, "dwconv: null argument");
+  SEB_REQUIRE(seq->nseq > 0 && seq->n > 0 && seq->inner > 0, SEB_EINVAL, "dwconv: bad sequence descriptor");
+  const int nchunks = (seq->n + DW_TI - 1) / DW_TI;
+  const long long nblocks = (long long)seq->nseq * nchunks;
+  SEB_REQUIRE(nblocks < 2147483647LL, SEB_EINVAL, "dwconv: grid too large");
+  dwconv_bn_swish_kernel<false><<<(unsigned)nblocks, 128, 0, (cudaStream_t)stream>>>(x, *seq, w, scale, shift, y, nchunks);
+  SEB_CHECK_LAUNCH("dwconv_kernel");
   return 0;
 }

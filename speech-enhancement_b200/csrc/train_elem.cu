@@ -255,11 +255,12 @@ __global__ void __launch_bounds__(256) bn_swish_kernel(const float* __restrict__
   }
 }
 
-// dc = gamma * rstd * (dz - S1 / N - chat * S2 / N);  block 0 also writes dgamma = S2, dbeta = S1
+// dc = gamma * rstd * (dz - S1 / N - chat * S2 / N) with the GLOBAL sums;  block 0 also writes dgamma = S2, dbeta = S1 from the LOCAL sums
+// (SyncBatchNorm returns this rank's parameter gradients; the data-parallel all-reduce of the gradients adds the ranks)
 __global__ void __launch_bounds__(256) bn_swish_bwd_apply_kernel(const float* __restrict__ c, const float* __restrict__ dv, long long M,
                                                                 const float* __restrict__ scale_shift, const float* __restrict__ mean_rstd,
-                                                                const double* __restrict__ sums, double count, float* __restrict__ dc,
-                                                                float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                                                const double* __restrict__ sums, const double* __restrict__ sums_local, double count,
+                                                                float* __restrict__ dc, float* __restrict__ dgamma, float* __restrict__ dbeta) {
   constexpr int C = 128;
   const int cq = threadIdx.x & 31;
   float sc[4], sh[4], mu[4], rs[4], a1[4], a2[4];
@@ -270,8 +271,8 @@ __global__ void __launch_bounds__(256) bn_swish_bwd_apply_kernel(const float* __
     a1[j] = (float)(sums[ch] / count); a2[j] = (float)(sums[C + ch] / count);
   }
   if (blockIdx.x == 0 && threadIdx.x < C) {
-    if (dgamma) dgamma[threadIdx.x] = (float)sums[C + threadIdx.x];
-    if (dbeta) dbeta[threadIdx.x] = (float)sums[threadIdx.x];
+    if (dgamma) dgamma[threadIdx.x] = (float)sums_local[C + threadIdx.x];
+    if (dbeta) dbeta[threadIdx.x] = (float)sums_local[threadIdx.x];
   }
   for (long long t = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); t < M; t += (long long)gridDim.x * 8) {
     const float4 x = ldg4(c + t * C + cq * 4), d = ldg4(dv + t * C + cq * 4);
@@ -288,7 +289,7 @@ __global__ void __launch_bounds__(256) bn_swish_bwd_apply_kernel(const float* __
 }
 
 // ---- depthwise conv weight gradient: dw[ch][k] = sum dc[pos] * u[pos + k - 15], db[ch] = sum dc (conformer.py:40-48) -----------------
-constexpr int DWG_TI = 64, DWG_K = 31, DWG_PAD = 15, DWG_C = 128;
+constexpr int DWG_TI = 32, DWG_K = 31, DWG_PAD = 15, DWG_C = 128;
 __global__ void __launch_bounds__(128) dwconv_wgrad_kernel(const float* __restrict__ u, const float* __restrict__ dc, const SebSeq sq, int nchunks,
                                                           long long nitems, float* __restrict__ partial) {
   __shared__ __align__(16) float ut[DWG_TI + DWG_K - 1][DWG_C];
@@ -802,12 +803,12 @@ extern "C" int seb200_bn_swish_bwd_sums(const float* c, const float* dv, long lo
   SEB_CHECK_LAUNCH("finish_f64_kernel");
   return 0;
 }
-// backward step 2 (after the optional all-reduce): dc; dgamma = S2, dbeta = S1 (the global sums: identical on every rank)
+// backward step 2 (after the optional all-reduce): dc from the global sums; dgamma = S2, dbeta = S1 of `sums_local` (this rank's own sums; NULL = sums)
 extern "C" int seb200_bn_swish_bwd_apply(const float* c, const float* dv, long long M, const float* scale_shift, const float* mean_rstd, const double* sums,
-                                         double count, float* dc, float* dgamma, float* dbeta, void* stream) {
+                                         const double* sums_local, double count, float* dc, float* dgamma, float* dbeta, void* stream) {
   SEB_REQUIRE(c && dv && scale_shift && mean_rstd && sums && dc && M > 0 && count >= 1.0 && aligned16(c) && aligned16(dv) && aligned16(dc), SEB_EINVAL,
               "bn_swish_bwd_apply: bad arguments");
-  bn_swish_bwd_apply_kernel<<<tgrid(M, 8 * 8), 256, 0, ST(stream)>>>(c, dv, M, scale_shift, mean_rstd, sums, count, dc, dgamma, dbeta);
+  bn_swish_bwd_apply_kernel<<<tgrid(M, 8 * 8), 256, 0, ST(stream)>>>(c, dv, M, scale_shift, mean_rstd, sums, sums_local ? sums_local : sums, count, dc, dgamma, dbeta);
   SEB_CHECK_LAUNCH("bn_swish_bwd_apply_kernel");
   return 0;
 }
@@ -819,7 +820,6 @@ extern "C" int seb200_dwconv_wgrad(const float* u, const float* dc, const SebSeq
   const int nchunks = (seq->n + DWG_TI - 1) / DWG_TI;
   const long long nitems = (long long)seq->nseq * nchunks;
   const int nb = (int)(nitems < 148 ? nitems : 148);
-  static PerDeviceOnce attr_done;
   dwconv_wgrad_kernel<<<nb, 128, 0, ST(stream)>>>(u, dc, *seq, nchunks, nitems, workspace);
   SEB_CHECK_LAUNCH("dwconv_wgrad_kernel");
   finish_f32_kernel<<<(DWG_C * 32 + 255) / 256, 256, 0, ST(stream)>>>(workspace, nb, DWG_C * 32, dw, DWG_C * DWG_K, db);

@@ -8,78 +8,132 @@
 // block's slot list), so a forward layer and its weight gradient share one description of the operand (SebGemm).
 //
 // The contraction runs over the M pixels / tokens (10^5 .. 10^7), the output is tiny (N x K <= 256 x 1536): split-M.  CTA (s, kc, nt)
-// reduces rows [s * rows_per_split, ...) of the 64 x 64 tile (n-tile nt, K chunk kc) in fp32 registers (16 x 16 threads, 4 x 4 outputs
-// each; operands staged 32 rows at a time in shared memory) and writes partial[s][n][k]; seb200_wgrad_finish sums the S partials in a
+// reduces rows [s * rows_per_split, ...) of the 64 x 64 tile (n-tile nt, K chunk kc) on the tensor cores (3xTF32 mma.sync, fp32-grade;
+// operands staged 32 rows at a time in shared memory) and writes partial[s][n][k]; seb200_wgrad_finish sums the S partials in a
 // fixed order (deterministic, no atomics) and scatters them through a two-level index map into the parameter's own layout (conv weights
 // are [Cout, Cin, kt, kf] while K runs (tap, slot, channel)) -- typically straight into the flat gradient buffer the all-reduce sends.
 #include "gemm_engine.cuh"
+#include "mma_tf32.cuh"
 
 namespace seb {
 
 constexpr int WG_ROWS = 32;          // rows staged per step
-constexpr int WG_LD = 68;            // padded row length (floats): conflict-free float4 reads for both operands
+constexpr int WG_LD = 72;            // padded row length (words): the fragment reads (4 rows x 8 columns per instruction) hit 32 distinct banks
 
+// The 64 x 64 output tile is owned by 8 warps in a 2 (n) x 4 (k) grid, 32 x 16 outputs each, on mma.sync m16n8k8 TF32 with the 3xTF32 split
+// (mma_tf32.cuh): A = G^T (rows n, contraction over the staged rows m), B = the layer input (rows m, columns k).  Both operands are split
+// into (hi, lo) TF32 planes ONCE when they are staged (every element is read by two or four warps), so the main loop is pure LDS + MMA.
+// Every 32-row step accumulates in a fresh tensor-core accumulator that is then added to the running sum with IEEE fp32 adds: the long
+// reduction over 10^4 .. 10^5 rows never sits inside the tensor pipe's accumulator.
 template <int LK>
 __global__ void __launch_bounds__(256) wgrad_kernel(const GemmArgs g, const float* __restrict__ G, long long ldg, int N, int rows_per_split,
                                                     float* __restrict__ partial, float* __restrict__ partial_b) {
-  __shared__ __align__(16) float Gs[WG_ROWS][WG_LD];
-  __shared__ __align__(16) float As[WG_ROWS][WG_LD];
+  __shared__ __align__(16) uint32_t Gh[WG_ROWS][WG_LD], Gl[WG_ROWS][WG_LD], Ah[WG_ROWS][WG_LD], Al[WG_ROWS][WG_LD];
   const int tid = threadIdx.x, sub = tid & 7, rloc = tid >> 3;      // staging: 8 lanes per row, 8 floats each
-  const int tn = tid >> 4, tk = tid & 15;                            // compute: outputs (n0 + 4 tn .. + 3, k0 + 4 tk .. + 3)
+  const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+  const int wn = (warp >> 2) * 32, wk = (warp & 3) * 16;            // this warp's 32 x 16 block of the tile
   const int split = blockIdx.x, kc = blockIdx.y, n0 = blockIdx.z * 64;
   const int m_lo = split * rows_per_split;
   const int m_hi = min(g.M, m_lo + rows_per_split);
-  float acc[4][4];
+  float acc[2][2][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  float bsum[4] = {0.f, 0.f, 0.f, 0.f};
-  const bool want_bias = partial_b != nullptr && kc == 0 && tk == 0;
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
+  float bsum = 0.f;
+  const bool want_bias = partial_b != nullptr && kc == 0;
 
-  for (int m0 = m_lo; m0 < m_hi; m0 += WG_ROWS) {
+  // software pipeline: the global loads of step i + 1 are issued before the MMAs of step i, so their latency hides behind the tensor work
+  float v[8], gv[8];
+  auto fetch = [&](int m0) {
     const int m = m0 + rloc;
-    float v[8];
     typename Loader<LK>::Row row;
-    Loader<LK>::init_row(g, m < m_hi ? m : g.M, row);              // rows past the split read as zeros
+    Loader<LK>::init_row(g, (m0 < m_hi && m < m_hi) ? m : g.M, row);       // rows past the split read as zeros
     Loader<LK>::load(g, row, kc, sub, v);
-    float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
-    if (m < m_hi && n0 + sub * 8 < N) {
-      const float* gp = G + (long long)m * ldg + n0 + sub * 8;
-      g0 = ldg4(gp); g1 = ldg4(gp + 4);
-    }
-    __syncthreads();                                                 // previous step's reads are done
-    *reinterpret_cast<float4*>(&As[rloc][sub * 8]) = make_float4(v[0], v[1], v[2], v[3]);
-    *reinterpret_cast<float4*>(&As[rloc][sub * 8 + 4]) = make_float4(v[4], v[5], v[6], v[7]);
-    *reinterpret_cast<float4*>(&Gs[rloc][sub * 8]) = g0;
-    *reinterpret_cast<float4*>(&Gs[rloc][sub * 8 + 4]) = g1;
-    __syncthreads();
-#pragma unroll 8
-    for (int r = 0; r < WG_ROWS; ++r) {
-      const float4 a = *reinterpret_cast<const float4*>(&Gs[r][tn * 4]);
-      const float4 b = *reinterpret_cast<const float4*>(&As[r][tk * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        acc[i][0] = fmaf(av[i], b.x, acc[i][0]);
-        acc[i][1] = fmaf(av[i], b.y, acc[i][1]);
-        acc[i][2] = fmaf(av[i], b.z, acc[i][2]);
-        acc[i][3] = fmaf(av[i], b.w, acc[i][3]);
+    for (int i = 0; i < 8; ++i) gv[i] = 0.f;
+    if (m0 < m_hi && m < m_hi && n0 + sub * 8 < N) {
+      const float* gp = G + (long long)m * ldg + n0 + sub * 8;
+      const float4 g0 = ldg4(gp), g1 = ldg4(gp + 4);
+      gv[0] = g0.x; gv[1] = g0.y; gv[2] = g0.z; gv[3] = g0.w; gv[4] = g1.x; gv[5] = g1.y; gv[6] = g1.z; gv[7] = g1.w;
+    }
+  };
+  fetch(m_lo);
+  for (int m0 = m_lo; m0 < m_hi; m0 += WG_ROWS) {
+    __syncthreads();                                                 // previous step's reads are done
+    {
+      uint32_t h[8], l[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) tf32::split(v[i], h[i], l[i]);
+      *reinterpret_cast<uint4*>(&Ah[rloc][sub * 8]) = make_uint4(h[0], h[1], h[2], h[3]);       // 16-byte stores: conflict-free per quarter warp
+      *reinterpret_cast<uint4*>(&Ah[rloc][sub * 8 + 4]) = make_uint4(h[4], h[5], h[6], h[7]);
+      *reinterpret_cast<uint4*>(&Al[rloc][sub * 8]) = make_uint4(l[0], l[1], l[2], l[3]);
+      *reinterpret_cast<uint4*>(&Al[rloc][sub * 8 + 4]) = make_uint4(l[4], l[5], l[6], l[7]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) tf32::split(gv[i], h[i], l[i]);
+      *reinterpret_cast<uint4*>(&Gh[rloc][sub * 8]) = make_uint4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<uint4*>(&Gh[rloc][sub * 8 + 4]) = make_uint4(h[4], h[5], h[6], h[7]);
+      *reinterpret_cast<uint4*>(&Gl[rloc][sub * 8]) = make_uint4(l[0], l[1], l[2], l[3]);
+      *reinterpret_cast<uint4*>(&Gl[rloc][sub * 8 + 4]) = make_uint4(l[4], l[5], l[6], l[7]);
+    }
+    __syncthreads();
+    fetch(m0 + WG_ROWS);                                             // next step's operands (all lanes call it: the LayerNorm loader shuffles)
+    float c[2][2][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) c[i][j][e] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < WG_ROWS / 8; ++ks) {
+      const int r0 = ks * 8 + tq, r1 = r0 + 4;
+      uint32_t ah[2][4], al[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int c0 = wn + mt * 16 + gq;
+        ah[mt][0] = Gh[r0][c0]; ah[mt][1] = Gh[r0][c0 + 8]; ah[mt][2] = Gh[r1][c0]; ah[mt][3] = Gh[r1][c0 + 8];
+        al[mt][0] = Gl[r0][c0]; al[mt][1] = Gl[r0][c0 + 8]; al[mt][2] = Gl[r1][c0]; al[mt][3] = Gl[r1][c0 + 8];
       }
-      if (want_bias) { bsum[0] += a.x; bsum[1] += a.y; bsum[2] += a.z; bsum[3] += a.w; }
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const int c0 = wk + nt * 8 + gq;
+        const uint32_t bh[2] = {Ah[r0][c0], Ah[r1][c0]}, bl[2] = {Al[r0][c0], Al[r1][c0]};
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          tf32::mma(c[mt][nt], al[mt], bh);
+          tf32::mma(c[mt][nt], ah[mt], bl);
+          tf32::mma(c[mt][nt], ah[mt], bh);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[i][j][e] += c[i][j][e];
+    if (want_bias && tid < 64) {
+      float b = 0.f;
+#pragma unroll 8
+      for (int r = 0; r < WG_ROWS; ++r) b += __uint_as_float(Gh[r][tid]) + __uint_as_float(Gl[r][tid]);
+      bsum += b;
     }
   }
   const int K = g.K;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int n = n0 + tn * 4 + i;
-    if (n < N) st4(partial + ((long long)split * N + n) * K + kc * 64 + tk * 4, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
-  }
-  if (want_bias) {
+  for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      if (n0 + tn * 4 + i < N) partial_b[(long long)split * N + n0 + tn * 4 + i] = bsum[i];
-  }
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; e += 2) {
+        const int n = n0 + wn + mt * 16 + gq + ((e >> 1) << 3);
+        const int k = kc * 64 + wk + nt * 8 + tq * 2;
+        if (n < N) *reinterpret_cast<float2*>(partial + ((long long)split * N + n) * K + k) = make_float2(acc[mt][nt][e], acc[mt][nt][e + 1]);
+      }
+  if (want_bias && tid < 64 && n0 + tid < N) partial_b[(long long)split * N + n0 + tid] = bsum;
 }
 
 // dW[n, k] = sum_s partial[s][n][k] -> dw[n * sn + (k / n1) * s0 + (k % n1) * s1] for k < k_logical;  db[n] = sum_s partial_b[s][n]

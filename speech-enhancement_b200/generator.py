@@ -460,8 +460,10 @@ class TSCNet(nn.Module):
         return ws["est"]
 
     def _forward_train(self, x: torch.Tensor):
-        """train-mode forward (core/function.py:221: dropout active, BatchNorm batch statistics, autograd graph): SURVEY 8f row f1"""
-        raise RuntimeError("se_b200.TSCNet is in train() mode: call .eval() for inference (the training step lives in se_b200.training)")
+        """train-mode forward (core/function.py:221: dropout active, BatchNorm batch statistics + running update, autograd graph over the
+        parameters): SURVEY 8f row f1, implemented in training.py (one autograd.Function around the generator, hand-written backward)"""
+        from . import training
+        return training.forward_train(self, x)
 
     def forward(self, x: torch.Tensor, diffusion_step=None):
         """x: complex64 (B, num_features, T) compressed spectrogram -> (final_real, final_imag), each fp32 (B, 1, T, F)."""

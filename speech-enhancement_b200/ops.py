@@ -13,11 +13,11 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import (ENGINE_SIMT, ENGINE_TCGEN05, EPI_BIAS, EPI_COMPRESS, EPI_GLU, EPI_QKV_F16, EPI_RESID, EPI_SUBPIXEL, EPI_SWISH,
+from ._lib import (ENGINE_SIMT, ENGINE_TCGEN05, ENGINE_TCGEN05_F32, EPI_BIAS, EPI_COMPRESS, EPI_GLU, EPI_QKV_F16, EPI_RESID, EPI_SUBPIXEL, EPI_SWISH,
                    LOAD_CONV, LOAD_CONV_SPLIT, LOAD_HANKEL, LOAD_ROWS, LOAD_ROWS_LN, SebFfn, SebGemm, SebSeq, check, ptr, require_cuda, stream_ptr)
 from .packing import PackedWeight
 
-ENGINES = {"tcgen05": ENGINE_TCGEN05, "simt": ENGINE_SIMT}
+ENGINES = {"tcgen05": ENGINE_TCGEN05, "simt": ENGINE_SIMT, "tcgen05_f32": ENGINE_TCGEN05_F32}
 
 
 class Profiler:

@@ -1,0 +1,533 @@
+"""GPU: the training step -- every backward kernel against torch autograd of the same op in float64, then the whole
+generator in train mode against the reference's own run (tests/golden/train_b2_L10000.npz: float32 outputs / BatchNorm buffers, float64
+gradients) with the reference's dropout masks injected."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_max, rel_l2
+import synth
+
+import se_b200
+from se_b200 import ops, packing, train_ops as T
+from se_b200._lib import EPI_BIAS, EPI_RESID, LOAD_CONV, LOAD_CONV_ADJ, LOAD_ROWS, LOAD_ROWS_LN
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+ENGINES = ["simt", "tcgen05_f32"]
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+def dev_pack(w, N, K, ntile, engine, n1=None, sn=None, s0=0, s1=1, w_offset=0):
+    pw = T.alloc_packed(N, K, ntile, 3, DEV, engine != "simt", engine == "simt")
+    T.pack_device(pw, w, N, K, n1 or K, sn if sn is not None else K, s0, s1, w_offset)
+    return pw
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,K,ntile,planes", [(64, 64, 64, 2), (192, 64, 192, 3), (64, 1536, 64, 3), (70, 100, 64, 2), (128, 192, 128, 3)])
+def test_device_packer_matches_host_packer_bit_for_bit(N, K, ntile, planes):
+    w = rnd(N, K, seed=N + K)
+    ref = packing.pack_weight(w.cpu(), ntile, planes=planes)
+    pw = T.alloc_packed(N, K, ntile, planes, DEV, True, True)
+    T.pack_device(pw, w, N, K, K, K, 0, 1)
+    assert torch.equal(pw.w_tc.cpu(), ref.w_tc) and torch.equal(pw.w_simt.cpu(), ref.w_simt)
+    # transposed source through the index map
+    wt = w.t().contiguous()
+    T.pack_device(pw, wt, N, K, K, 1, 0, N)
+    assert torch.equal(pw.w_tc.cpu(), ref.w_tc) and torch.equal(pw.w_simt.cpu(), ref.w_simt)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("N,K,M", [(64, 64, 300), (256, 64, 1000), (64, 256, 777), (128, 64, 129), (64, 192, 400)])
+def test_train_gemm_rows_fp32_grade(engine, N, K, M):
+    """the three-plane tcgen05 engine and the fp32 loop on plain rows: forward and dgrad shapes of the conformer's Linear layers"""
+    a, w, b = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=K ** -0.5), rnd(N, seed=3)
+    pw = dev_pack(w, N, K, N if N <= 256 else 64, engine)
+    pw.bias = b
+    out = torch.empty(M, N, device=DEV)
+    ops.gemm(loader=LOAD_ROWS, epilogue=EPI_BIAS, M=M, w=pw, a=[a], lda=K, out=out, ldo=N, engine=engine)
+    ref = a.double() @ w.double().t() + b.double()
+    assert rel_max(out, ref) < 2e-6
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_train_gemm_layernorm_loader(engine):
+    M = 555
+    x, w, g, b = rnd(M, 64, seed=4), rnd(192, 64, seed=5, scale=0.125), 1 + 0.1 * rnd(64, seed=6), 0.1 * rnd(64, seed=7)
+    pw = dev_pack(w, 192, 64, 192, engine)
+    out = torch.empty(M, 192, device=DEV)
+    ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_BIAS, M=M, w=pw, a=[x], lda=64, ln=(g, b), out=out, ldo=192, engine=engine)
+    ref = F.layer_norm(x.double(), (64,), g.double(), b.double(), 1e-5) @ w.double().t()
+    assert rel_max(out, ref) < 3e-6
+
+
+def _wgrad_ref(G, A):
+    return G.double().t() @ A.double(), G.double().sum(0)
+
+
+@pytest.mark.parametrize("N,K,M", [(64, 256, 1000), (256, 64, 5000), (192, 64, 333), (64, 128, 129)])
+def test_wgrad_rows(N, K, M):
+    G, A = rnd(M, N, seed=8), rnd(M, K, seed=9)
+    dw, db = torch.zeros(N, K, device=DEV), torch.zeros(N, device=DEV)
+    T.wgrad(loader=LOAD_ROWS, M=M, K=K, a=[A], lda=K, g_out=G, ldg=N, N=N, dw=dw, db=db, index_map=(K, K, 0, 1))
+    rw, rb = _wgrad_ref(G, A)
+    assert rel_max(dw, rw) < 1e-5 and rel_max(db, rb) < 1e-5
+
+
+def test_wgrad_rows_layernorm():
+    M = 2000
+    G, x, g, b = rnd(M, 256, seed=10), rnd(M, 64, seed=11), 1 + 0.1 * rnd(64, seed=12), 0.1 * rnd(64, seed=13)
+    dw = torch.zeros(256, 64, device=DEV)
+    T.wgrad(loader=LOAD_ROWS_LN, M=M, K=64, a=[x], lda=64, ln=(g, b), g_out=G, ldg=256, N=256, dw=dw, db=None, index_map=(64, 64, 0, 1))
+    rw, _ = _wgrad_ref(G, F.layer_norm(x.double(), (64,), g.double(), b.double(), 1e-5))
+    assert rel_max(dw, rw) < 1e-5
+
+
+def _conv_ref(slots, w, b, dil, taps_t, stride_f):
+    """slots: list of [B, T, F, 64] (newest first) -> torch conv in the reference layout, float64"""
+    x = torch.cat([s.permute(0, 3, 1, 2) for s in slots], 1).double()
+    x = F.pad(x, (1, 1, dil * (taps_t - 1), 0))
+    return F.conv2d(x, w.double(), b.double(), dilation=(dil, 1), stride=(1, stride_f))
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("B,Tn,Fw,nslots,dil,taps_t,stride_f", [(2, 9, 13, 1, 1, 2, 1), (1, 20, 21, 3, 4, 2, 1), (2, 6, 201, 1, 1, 1, 2), (1, 11, 101, 4, 8, 2, 1)])
+def test_conv_forward_dgrad_wgrad(engine, B, Tn, Fw, nslots, dil, taps_t, stride_f):
+    """train-mode conv (fp32 inputs), its data gradient through the adjoint-conv loader and its weight gradient, against torch autograd"""
+    cin, taps = 64 * nslots, taps_t * 3
+    Fo = (Fw - 1) // stride_f + 1 if stride_f > 1 else Fw
+    slots = [rnd(B, Tn, Fw, 64, seed=20 + j) for j in range(nslots)]
+    w = rnd(64, cin, taps_t, 3, seed=30, scale=(cin * taps) ** -0.5)
+    b = rnd(64, seed=31)
+    xs = [s.clone().double().requires_grad_(True) for s in slots]
+    wd, bd = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    y = _conv_ref(xs, wd, bd, dil, taps_t, stride_f)                  # [B, 64, T, Fo]
+    gy = rnd(B, Tn, Fo, 64, seed=32)
+    (y * gy.permute(0, 3, 1, 2).double()).sum().backward()
+    M = B * Tn * Fo
+    conv = dict(B=B, T=Tn, Fin=Fw, Fout=Fo, taps_t=taps_t, dil=dil, stride_f=stride_f, nslots=nslots)
+    pw = dev_pack(w, 64, taps * cin, 64, engine, n1=cin, sn=cin * taps, s0=1, s1=taps)
+    pw.bias = b
+    out = torch.empty(M, 64, device=DEV)
+    flat = [s.view(-1, 64) for s in slots]
+    ops.gemm(loader=LOAD_CONV, epilogue=EPI_BIAS, M=M, w=pw, a=flat, out=out, ldo=64, engine=engine, conv=conv)
+    assert rel_max(out.view(B, Tn, Fo, 64), y.detach().permute(0, 2, 3, 1)) < 1e-5
+    # weight gradient into the parameter layout
+    dw, db = torch.zeros_like(w), torch.zeros(64, device=DEV)
+    T.wgrad(loader=LOAD_CONV, M=M, K=taps * cin, a=flat, g_out=gy.view(-1, 64), ldg=64, N=64, dw=dw, db=db, index_map=(cin, cin * taps, 1, taps), conv=conv)
+    assert rel_max(dw, wd.grad) < 1e-5 and rel_max(db, bd.grad) < 1e-5
+    # data gradient of every slot
+    for j in range(nslots):
+        adj = dev_pack(w, 64, taps * 64, 64, engine, n1=64, sn=taps, s0=1, s1=cin * taps, w_offset=64 * j * taps)
+        gx = torch.empty(B * Tn * Fw, 64, device=DEV)
+        ops.gemm(loader=LOAD_CONV_ADJ, epilogue=EPI_BIAS, M=B * Tn * Fw, w=adj, a=[gy.view(-1, 64)], lda=64, out=gx, ldo=64, engine=engine,
+                 conv=dict(B=B, T=Tn, Fin=Fo, Fout=Fw, taps_t=taps_t, dil=dil, stride_f=stride_f, nslots=1))
+        assert rel_max(gx.view(B, Tn, Fw, 64), xs[j].grad) < 1e-5, f"slot {j}"
+        # accumulate form
+        ops.gemm(loader=LOAD_CONV_ADJ, epilogue=EPI_RESID, M=B * Tn * Fw, w=adj, a=[gy.view(-1, 64)], lda=64, out=gx, ldo=64, resid=gx, ldr=64, alpha=1.0,
+                 engine=engine, conv=dict(B=B, T=Tn, Fin=Fo, Fout=Fw, taps_t=taps_t, dil=dil, stride_f=stride_f, nslots=1))
+        assert rel_max(gx.view(B, Tn, Fw, 64), 2 * xs[j].grad) < 1e-5
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_subpixel_conv_backward(engine):
+    """SPConvTranspose2d (generator.py:85-92): the interleaved output is the [pixels, 128] matrix of the conv, so dgrad reads 128-channel pixels"""
+    B, Tn, Fw = 2, 5, 101
+    x = rnd(B, Tn, Fw, 64, seed=40)
+    w, b = rnd(128, 64, 1, 3, seed=41, scale=192 ** -0.5), rnd(128, seed=42)
+    xd, wd, bd = x.double().requires_grad_(True), w.double().requires_grad_(True), b.double().requires_grad_(True)
+    y = F.conv2d(F.pad(xd.permute(0, 3, 1, 2), (1, 1, 0, 0)), wd, bd)                                  # [B, 128, T, F]
+    y = y.reshape(B, 2, 64, Tn, Fw).permute(0, 2, 3, 4, 1).reshape(B, 64, Tn, 2 * Fw)
+    gsp = rnd(B, Tn, 2 * Fw, 64, seed=43)
+    (y * gsp.permute(0, 3, 1, 2).double()).sum().backward()
+    M = B * Tn * Fw
+    g128 = gsp.view(M, 128)
+    dw, db = torch.zeros_like(w), torch.zeros(128, device=DEV)
+    T.wgrad(loader=LOAD_CONV, M=M, K=192, a=[x.view(-1, 64)], g_out=g128, ldg=128, N=128, dw=dw, db=db, index_map=(64, 192, 1, 3),
+            conv=dict(B=B, T=Tn, Fin=Fw, Fout=Fw, taps_t=1, dil=1, stride_f=1, nslots=1))
+    assert rel_max(dw, wd.grad) < 1e-5 and rel_max(db, bd.grad) < 1e-5
+    adj = dev_pack(w, 64, 384, 64, engine, n1=128, sn=3, s0=1, s1=192)
+    gx = torch.empty(M, 64, device=DEV)
+    ops.gemm(loader=LOAD_CONV_ADJ, epilogue=EPI_BIAS, M=M, w=adj, a=[g128], lda=128, out=gx, ldo=64, engine=engine,
+             conv=dict(B=B, T=Tn, Fin=Fw, Fout=Fw, taps_t=1, dil=1, stride_f=1, nslots=2))
+    assert rel_max(gx.view(B, Tn, Fw, 64), xd.grad) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------------
+def test_elementwise_forward_backward():
+    M = 1000
+    a, dh = rnd(M, 256, seed=50), rnd(M, 256, seed=51)
+    mask = (torch.rand(M, 256, generator=torch.Generator().manual_seed(52)) >= 0.2).to(DEV)
+    ad = a.double().requires_grad_(True)
+    h_ref = ad * torch.sigmoid(ad) * mask.double() * 1.25
+    (h_ref * dh.double()).sum().backward()
+    h, da = torch.empty_like(a), torch.empty_like(a)
+    T.swish_dropout(a, mask, 1.25, h)
+    T.swish_dropout_bwd(a, mask, 1.25, dh, da)
+    assert rel_max(h, h_ref.detach()) < 1e-6 and rel_max(da, ad.grad) < 2e-6
+    # no mask
+    T.swish_dropout(a, None, 1.0, h)
+    assert rel_max(h, (a.double() * torch.sigmoid(a.double()))) < 1e-6
+    # dropout + scale + residual, and the branch gradient
+    t, r = rnd(M, 64, seed=53), rnd(M, 64, seed=54)
+    m2 = (torch.rand(M, 64, generator=torch.Generator().manual_seed(55)) >= 0.2).to(DEV)
+    y, dt = torch.empty_like(t), torch.empty_like(t)
+    T.dropout_residual(t, m2, 0.625, r, y)
+    assert rel_max(y, r.double() + 0.625 * m2.double() * t.double()) < 1e-6
+    T.scale_mask(t, m2, 0.625, dt)
+    assert rel_max(dt, 0.625 * m2.double() * t.double()) < 1e-6
+    # GLU in the natural order
+    a3, du = rnd(M, 256, seed=56), rnd(M, 128, seed=57)
+    a3d = a3.double().requires_grad_(True)
+    u_ref = a3d[:, :128] * torch.sigmoid(a3d[:, 128:])
+    (u_ref * du.double()).sum().backward()
+    u, da3 = torch.empty(M, 128, device=DEV), torch.empty_like(a3)
+    T.glu(a3, u)
+    T.glu_bwd(a3, du, da3)
+    assert rel_max(u, u_ref.detach()) < 1e-6 and rel_max(da3, a3d.grad) < 2e-6
+
+
+def test_dropout_mask_philox():
+    n = 1 << 20
+    m = torch.empty(n + 3, device=DEV, dtype=torch.uint8)
+    T.dropout_mask(m, 0.2, 1234, 0)
+    keep = m.float().mean().item()
+    assert abs(keep - 0.8) < 2e-3
+    m2 = torch.empty_like(m)
+    T.dropout_mask(m2, 0.2, 1234, 0)
+    assert torch.equal(m, m2)                      # reproducible
+    T.dropout_mask(m2, 0.2, 1235, 0)
+    assert (m != m2).float().mean().item() > 0.2   # a different seed is a different draw
+    T.dropout_mask(m2, 0.2, 1234, 1 << 32)
+    assert (m != m2).float().mean().item() > 0.2   # and so is a different offset (step)
+
+
+def test_layernorm_backward():
+    M = 3001
+    x, dy, add = rnd(M, 64, seed=60), rnd(M, 64, seed=61), rnd(M, 64, seed=62)
+    g, b = 1 + 0.1 * rnd(64, seed=63), 0.1 * rnd(64, seed=64)
+    xd, gd, bd = x.double().requires_grad_(True), g.double().requires_grad_(True), b.double().requires_grad_(True)
+    (F.layer_norm(xd, (64,), gd, bd, 1e-5) * dy.double()).sum().backward()
+    dx, dg, db = torch.empty_like(x), torch.empty(64, device=DEV), torch.empty(64, device=DEV)
+    T.layernorm_bwd(x, g, dy, None, dx, dg, db)
+    assert rel_max(dx, xd.grad) < 2e-6 and rel_max(dg, gd.grad) < 1e-5 and rel_max(db, bd.grad) < 1e-5
+    buf = add.clone()
+    T.layernorm_bwd(x, g, dy, buf, buf, dg, db)      # add aliasing dx
+    assert rel_max(buf, xd.grad + add.double()) < 2e-6
+
+
+def test_batchnorm_train_forward_backward():
+    M = 4097
+    c, dv = rnd(M, 128, seed=70, scale=2.0) + 0.5, rnd(M, 128, seed=71)
+    g, b = 1 + 0.1 * rnd(128, seed=72), 0.1 * rnd(128, seed=73)
+    rm, rv = 0.1 * rnd(128, seed=74), 1 + 0.1 * rnd(128, seed=75).abs()
+    nbt = torch.zeros((), device=DEV, dtype=torch.int64)
+    cd, gd, bd = c.double().requires_grad_(True), g.double().requires_grad_(True), b.double().requires_grad_(True)
+    rm_ref, rv_ref = rm.double().clone(), rv.double().clone()
+    z = F.batch_norm(cd, rm_ref, rv_ref, gd, bd, True, 0.1, 1e-5)
+    v_ref = z * torch.sigmoid(z)
+    (v_ref * dv.double()).sum().backward()
+    sums = torch.empty(256, device=DEV, dtype=torch.float64)
+    ss, mr, v = torch.empty(256, device=DEV), torch.empty(256, device=DEV), torch.empty_like(c)
+    T.bn_sums(c, sums)
+    T.bn_finalize(sums, M, g, b, rm, rv, nbt, 0.1, 1e-5, ss, mr)
+    T.bn_swish(c, ss, v)
+    assert rel_max(v, v_ref.detach()) < 2e-6
+    assert torch.allclose(rm.double(), rm_ref, rtol=1e-6, atol=1e-7) and torch.allclose(rv.double(), rv_ref, rtol=1e-6, atol=1e-7) and int(nbt) == 1
+    s2 = torch.empty(256, device=DEV, dtype=torch.float64)
+    dc, dg, db = torch.empty_like(c), torch.empty(128, device=DEV), torch.empty(128, device=DEV)
+    T.bn_swish_bwd_sums(c, dv, ss, mr, s2)
+    T.bn_swish_bwd_apply(c, dv, ss, mr, s2, M, dc, dg, db)          # single rank: local sums == global sums
+    assert rel_max(dc, cd.grad) < 5e-6 and rel_max(dg, gd.grad) < 1e-5 and rel_max(db, bd.grad) < 1e-5
+    # SyncBatchNorm semantics: two "ranks" = halves of the tokens, sums added before finalize == statistics of the whole batch
+    sa, sb = torch.empty_like(sums), torch.empty_like(sums)
+    h = M // 2
+    T.bn_sums(c[:h].contiguous(), sa)
+    T.bn_sums(c[h:].contiguous(), sb)
+    ss2, mr2 = torch.empty_like(ss), torch.empty_like(mr)
+    T.bn_finalize(sa + sb, M, g, b, None, None, None, 0.1, 1e-5, ss2, mr2)
+    assert torch.allclose(ss2, ss, rtol=1e-6, atol=1e-7) and torch.allclose(mr2, mr, rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("axis,B,Tn,Fh", [("freq", 2, 5, 101), ("time", 2, 130, 3), ("time", 1, 33, 2)])
+def test_depthwise_conv_train(axis, B, Tn, Fh):
+    from test_gpu_kernels import _seq_layouts
+    seq, to_seq, from_seq = _seq_layouts(B, Tn, Fh)[axis]
+    u, dcg = rnd(B, Tn, Fh, 128, seed=80), rnd(B, Tn, Fh, 128, seed=81)
+    w, b = rnd(128, 1, 31, seed=82, scale=0.2), rnd(128, seed=83)
+    ud, wd, bd = to_seq(u.cpu()).double().requires_grad_(True), w.cpu().double().requires_grad_(True), b.cpu().double().requires_grad_(True)
+    cref = F.conv1d(F.pad(ud.transpose(1, 2), (15, 15)), wd, bd, groups=128).transpose(1, 2)
+    (cref * to_seq(dcg.cpu()).double()).sum().backward()
+    ones, zeros = torch.ones(128, device=DEV), torch.zeros(128, device=DEV)
+    cc = torch.empty_like(u)
+    T.dwconv(u.view(-1, 128), seq, w.squeeze(1).t().contiguous(), ones, b, cc.view(-1, 128))
+    assert rel_max(cc.cpu(), from_seq(cref.detach())) < 2e-6
+    du = torch.empty_like(u)
+    T.dwconv(dcg.view(-1, 128), seq, w.squeeze(1).flip(-1).t().contiguous(), ones, zeros, du.view(-1, 128))
+    assert rel_max(du.cpu(), from_seq(ud.grad)) < 2e-6
+    dw, db = torch.zeros_like(w), torch.zeros(128, device=DEV)
+    T.dwconv_wgrad(u.view(-1, 128), dcg.view(-1, 128), seq, dw, db)
+    assert rel_max(dw.cpu(), wd.grad) < 1e-5 and rel_max(db.cpu(), bd.grad) < 1e-5
+
+
+@pytest.mark.parametrize("C,B,pix", [(64, 2, 3000), (64, 3, 1025), (1, 2, 70000), (1, 3, 500)])
+def test_instancenorm_prelu_backward(C, B, pix):
+    x, dy = rnd(B, pix, C, seed=90, scale=1.5) + 0.3, rnd(B, pix, C, seed=91)
+    g, b, s = 1 + 0.1 * rnd(C, seed=92), 0.1 * rnd(C, seed=93), 0.25 + 0.05 * rnd(C, seed=94)
+    xd = x.double().requires_grad_(True)
+    gd, bd, sd = g.double().requires_grad_(True), b.double().requires_grad_(True), s.double().requires_grad_(True)
+    y = F.prelu(F.instance_norm(xd.permute(0, 2, 1).unsqueeze(-1), weight=gd, bias=bd, eps=1e-5), sd)
+    (y * dy.permute(0, 2, 1).unsqueeze(-1).double()).sum().backward()
+    stats = torch.empty(B, C, 2, device=DEV)
+    ops.inorm_stats(x.view(-1, C) if C == 64 else x.view(B * pix), B, pix, C, stats, ops.inorm_workspace(B, pix, C, DEV))
+    dx, dg, db, ds = torch.empty_like(x), torch.empty(C, device=DEV), torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+    T.inorm_prelu_bwd(x, dy, B, pix, C, stats, g, b, s, dx, dg, db, ds)
+    assert rel_max(dx, xd.grad) < 1e-5
+    assert rel_max(dg, gd.grad) < 1e-5 and rel_max(db, bd.grad) < 1e-5 and rel_max(ds, sd.grad) < 1e-5
+
+
+@pytest.mark.parametrize("NO", [1, 2])
+def test_head_conv_forward_backward(NO):
+    rows, Fin = 37, 202
+    x, dout = rnd(rows, Fin, 64, seed=100), rnd(rows, Fin - 1, NO, seed=101)
+    w, b = rnd(NO, 64, 1, 2, seed=102, scale=0.1), rnd(NO, seed=103)
+    xd, wd, bd = x.double().requires_grad_(True), w.double().requires_grad_(True), b.double().requires_grad_(True)
+    y = F.conv2d(xd.permute(2, 0, 1).unsqueeze(0), wd, bd)                   # [1, NO, rows, Fin - 1]
+    (y * dout.permute(2, 0, 1).unsqueeze(0).double()).sum().backward()
+    out = torch.empty(rows, Fin - 1, NO, device=DEV)
+    T.head_conv(x, rows, Fin, w, b, NO, out)
+    assert rel_max(out, y.detach()[0].permute(1, 2, 0)) < 2e-6
+    dx, dw, db = torch.empty_like(x), torch.zeros_like(w), torch.zeros(NO, device=DEV)
+    T.head_conv_bwd(x, dout, rows, Fin, w, NO, dx, dw, db)
+    assert rel_max(dx, xd.grad) < 2e-6 and rel_max(dw, wd.grad) < 1e-5 and rel_max(db, bd.grad) < 1e-5
+
+
+def test_mask_tail_forward_backward():
+    B, Tn, Fw = 2, 23, 201
+    raw, in3, cplx, dest = rnd(B * Tn, Fw, seed=110), rnd(B, Tn, Fw, 3, seed=111), rnd(B * Tn, Fw, 2, seed=112), rnd(B * Tn, Fw, 2, seed=113)
+    names = ["norm.weight", "norm.bias", "prelu.weight", "final_conv.weight", "final_conv.bias"]
+    vals = [1.1, 0.05, 0.2, 0.9, 0.1]
+    scal = [torch.tensor([v], device=DEV) for v in vals]
+    slope_f = -0.25 + 0.05 * rnd(Fw, seed=114)
+    sd_ = [s.double().requires_grad_(True) for s in scal]
+    sf = slope_f.double().requires_grad_(True)
+    rd = raw.double().requires_grad_(True)
+    x = F.instance_norm(rd.view(B, 1, Tn, Fw), weight=sd_[0], bias=sd_[1], eps=1e-5)
+    p1 = F.prelu(x, sd_[2])
+    m2 = p1 * sd_[3] + sd_[4]
+    mask = F.prelu(m2.permute(0, 3, 2, 1).squeeze(-1), sf).permute(0, 2, 1)                  # (B, T, F), slope per frequency bin
+    est_ref = torch.stack([mask * in3[..., 1].double() + cplx.view(B, Tn, Fw, 2)[..., 0].double(),
+                           mask * in3[..., 2].double() + cplx.view(B, Tn, Fw, 2)[..., 1].double()], -1)
+    (est_ref * dest.view(B, Tn, Fw, 2).double()).sum().backward()
+    stats1 = torch.empty(B, 1, 2, device=DEV)
+    ops.inorm_stats(raw, B, Tn * Fw, 1, stats1, ops.inorm_workspace(B, Tn * Fw, 1, DEV))
+    est = torch.empty(B * Tn, Fw, 2, device=DEV)
+    T.mask_recombine_dev(raw, stats1, B, Tn, Fw, scal, slope_f, in3, cplx, est)
+    assert rel_max(est.view(B, Tn, Fw, 2), est_ref.detach()) < 2e-6
+    dp1, dsf, dwf, dbf = torch.empty(B * Tn, Fw, device=DEV), torch.empty(Fw, device=DEV), torch.empty(1, device=DEV), torch.empty(1, device=DEV)
+    T.mask_tail_bwd(raw, stats1, B, Tn, Fw, scal, slope_f, in3, dest, dp1, dsf, dwf, dbf)
+    assert rel_max(dsf, sf.grad) < 1e-5 and rel_max(dwf, sd_[3].grad) < 1e-5 and rel_max(dbf, sd_[4].grad) < 1e-5
+    draw, dg, db, ds = torch.empty_like(raw), torch.empty(1, device=DEV), torch.empty(1, device=DEV), torch.empty(1, device=DEV)
+    T.inorm_prelu_bwd(raw, dp1, B, Tn * Fw, 1, stats1, scal[0], scal[1], scal[2], draw, dg, db, ds)
+    assert rel_max(draw, rd.grad) < 1e-5 and rel_max(dg, sd_[0].grad) < 1e-5 and rel_max(db, sd_[1].grad) < 1e-5 and rel_max(ds, sd_[2].grad) < 1e-5
+
+
+def test_conv1x1_in3_wgrad_and_merge_ri():
+    P = 5000
+    in3, g = rnd(P, 3, seed=120), rnd(P, 64, seed=121)
+    dw, db = torch.empty(64, 3, device=DEV), torch.empty(64, device=DEV)
+    T.conv1x1_in3_wgrad(in3, g, dw, db)
+    assert rel_max(dw, g.double().t() @ in3.double()) < 1e-5 and rel_max(db, g.double().sum(0)) < 1e-5
+    re, im = rnd(2, 1, 7, 201, seed=122), rnd(2, 1, 7, 201, seed=123)
+    est = torch.empty(14, 201, 2, device=DEV)
+    T.merge_ri(re, im, est)
+    assert torch.equal(est.view(2, 7, 201, 2)[..., 0], re[:, 0]) and torch.equal(est.view(2, 7, 201, 2)[..., 1], im[:, 0])
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------------
+def _attention_ref(qkv_seq, emb):
+    """(S, n, 192), (1025, 16) float64 with autograd -> (S, n, 64)"""
+    S, n, _ = qkv_seq.shape
+    q, k, v = (qkv_seq[..., i * 64:(i + 1) * 64].reshape(S, n, 4, 16).permute(0, 2, 1, 3) for i in range(3))
+    pos = torch.arange(n)
+    dist = (pos[:, None] - pos[None, :]).clamp(-512, 512) + 512
+    dots = (q @ k.transpose(-1, -2) + torch.einsum("bhnd,nrd->bhnr", q, emb[dist])) * 0.25
+    return (dots.softmax(-1) @ v).permute(0, 2, 1, 3).reshape(S, n, 64)
+
+
+@pytest.mark.parametrize("axis,B,Tn,Fh", [("freq", 2, 3, 101), ("time", 1, 150, 2), ("time", 1, 321, 1), ("time", 1, 3, 2), ("freq", 1, 2, 64), ("time", 1, 700, 1)])
+def test_attention_train_forward_backward(axis, B, Tn, Fh):
+    """3xTF32 attention with the log-sum-exp output, and its backward incl. the gradient of the relative-position table
+    (n = 700: both clamp sides of the +-512 window receive gradient from many (i, j) pairs)"""
+    from test_gpu_kernels import _seq_layouts
+    seq, to_seq, from_seq = _seq_layouts(B, Tn, Fh)[axis]
+    qkv, emb, dout = rnd(B, Tn, Fh, 192, seed=130, scale=1.2), rnd(1025, 16, seed=131), rnd(B, Tn, Fh, 64, seed=132)
+    qd, ed = to_seq(qkv.cpu()).double().requires_grad_(True), emb.cpu().double().requires_grad_(True)
+    ref = _attention_ref(qd, ed)
+    (ref * to_seq(dout.cpu()).double()).sum().backward()
+    M = B * Tn * Fh
+    out, lse = torch.zeros(M, 64, device=DEV), torch.zeros(M, 4, device=DEV)
+    T.attention_train_fwd(qkv.view(M, 192), emb, seq, out, lse)
+    assert rel_max(out.view(B, Tn, Fh, 64).cpu(), from_seq(ref.detach())) < 1e-5
+    dqkv, demb = torch.full((M, 192), float("nan"), device=DEV), torch.full((1025, 16), float("nan"), device=DEV)
+    T.attention_bwd(qkv.view(M, 192), emb, seq, out, lse, dout.view(M, 64), dqkv, demb)
+    assert rel_max(dqkv.view(B, Tn, Fh, 192).cpu(), from_seq(qd.grad)) < 3e-5          # 3xTF32: ~2^-21 per operand, n = 700 keys per row
+    assert rel_max(demb.cpu(), ed.grad) < 3e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------------
+def _train_model(g, engine):
+    m = se_b200.TSCNet(num_channel=64, num_features=201)
+    m.load_state_dict(synth.synth_state_dict(int(g["weight_seed"])))
+    m = m.to(DEV).train()
+    st = se_b200.training._state(m)
+    st.engine = engine
+    return m, st
+
+
+def grad_errors(named_grads, g):
+    gmax = max(float(np.abs(g["grad:" + k]).max()) for k, _ in named_grads)
+    errs = {}
+    for k, gv in named_grads:
+        ref = torch.from_numpy(g["grad:" + k]).double()
+        if synth.has_zero_gradient(k):
+            assert float(gv.abs().max()) < 1e-3 * gmax, k
+            continue
+        errs[k] = float((gv.detach().double().cpu() - ref).norm() / ref.norm().clamp_min(1e-30))
+    return errs
+
+
+# Gradient yardstick.  The golden holds the reference graph's gradients in float64 and, per parameter, how far the reference's OWN float32
+# autograd is from them (`ref32_err`: median 2.0e-3, worst 3.3e-3 -- this random-weight network amplifies rounding ~100x on the way to the
+# gradients).  Rounding noise of that kind is random per entry, so the bar is on the distribution: median and worst rel-L2 over the 335
+# parameters within a factor of the reference's own float32 figures.  fp32 FFMA loop ("simt"): the same arithmetic class as the reference
+# -> factors 1.5 / 2.  Three-plane tcgen05 ("tcgen05_f32", tensor-core fp32 accumulation, 6 of 9 cross products): forward 1.8e-5 instead of
+# 3e-6, gradients ~2x the reference's float32 noise, worst entries are the ill-conditioned sums (a bias in front of a PReLU whose summands
+# cancel to 1e-3 of their magnitude) -> factors 2.5 / 10.
+GRAD_FACTORS = {"simt": (1.5, 2.0), "tcgen05_f32": (2.5, 10.0)}
+GRAD_ABS = {"simt": (7.5e-4, 4e-3), "tcgen05_f32": (5e-3, 2e-2)}      # 4 x 2 s shape (no float32 CPU reference there): median / worst rel-L2 vs float64
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_generator_training_step_matches_reference(golden, engine):
+    """train-mode forward (dropout masks injected, BatchNorm batch statistics + running update) and the gradient of every one of the 335
+    parameters against the unmodified reference (float32 outputs / buffers, float64 gradients)"""
+    g = golden("train_b2_L10000")
+    m, st = _train_model(g, engine)
+    spec = torch.complex(torch.from_numpy(g["spec_real"]), torch.from_numpy(g["spec_imag"])).to(DEV)
+    B, _, Tn = spec.shape
+    st.injected_masks = synth.dropout_masks(int(g["mask_seed"]), B, Tn, 101)
+    fr, fi = m(spec)
+    assert fr.requires_grad and fr.shape == (B, 1, Tn, 201)
+    peak = np.abs(g["final_real"]).max()
+    e_out = max(float((fr.detach().cpu() - torch.from_numpy(g["final_real"])).abs().max() / peak),
+                float((fi.detach().cpu() - torch.from_numpy(g["final_imag"])).abs().max() / peak))
+    assert e_out < 1e-3, f"train-mode outputs: {e_out:.3e}"
+    for k, v in m.state_dict().items():
+        if "running_" in k:
+            assert torch.allclose(v.cpu(), torch.from_numpy(g["buf:" + k]), rtol=1e-5, atol=1e-5), k
+        if "num_batches_tracked" in k:
+            assert int(v) == int(g["buf:" + k])
+    gr, gi = synth.cotangents(int(g["cot_seed"]), B, Tn)
+    ((fr * gr.to(DEV)).sum() + (fi * gi.to(DEV)).sum()).backward()
+    grads = [(k, p.grad) for k, p in m.named_parameters()]
+    assert all(gv is not None for _, gv in grads) and len(grads) == 335
+    assert st.grad_buffer() is not None                      # every .grad aliases the one flat buffer
+    errs = grad_errors(grads, g)
+    worst = max(errs, key=errs.get)
+    med = float(np.median(list(errs.values())))
+    ref = [float(g["ref32_err:" + k]) for k in errs]
+    ref_med, ref_worst = float(np.median(ref)), float(np.max(ref))
+    print(f"[{engine}] outputs {e_out:.2e}; gradients vs float64 reference: median {med:.2e}, worst {errs[worst]:.2e} ({worst}); "
+          f"reference float32 itself: median {ref_med:.2e}, worst {ref_worst:.2e}")
+    fm, fw = GRAD_FACTORS[engine]
+    assert med < fm * ref_med, (med, ref_med)
+    assert errs[worst] < fw * ref_worst, (worst, errs[worst], ref_worst)
+    # a second backward without zero_grad accumulates (autograd semantics), through the second flat buffer
+    fr2, fi2 = m(spec)
+    ((fr2 * gr.to(DEV)).sum() + (fi2 * gi.to(DEV)).sum()).backward()
+    k0, p0 = next(iter(m.named_parameters()))
+    assert rel_l2(p0.grad.cpu(), 2 * torch.from_numpy(g["grad:" + k0])) < 1e-2
+
+
+def _oracle_train_gradients(spec, sd, masks_ref, gr, gi, dtype):
+    """the oracle port's autograd on the GPU box (torch.cuda): train-mode forward + gradients of every parameter, in `dtype`"""
+    from oracle import tscnet_oracle as O
+    cdt = torch.complex128 if dtype == torch.float64 else torch.complex64
+    sdd = {k: (v.to(device=DEV, dtype=dtype) if v.is_floating_point() else v.to(DEV)) for k, v in sd.items()}
+    params = [k for k, v in sdd.items() if v.is_floating_point() and "running_" not in k]
+    for k in params:
+        sdd[k].requires_grad_(True)
+    tr = O.TrainCtx({k: v.to(DEV) for k, v in masks_ref.items()})
+    fr, fi = O.tscnet_forward(spec.to(cdt), sdd, tr=tr, chunk=0)
+    ((fr * gr.to(fr)).sum() + (fi * gi.to(fi)).sum()).backward()
+    return fr.detach(), {k: sdd[k].grad for k in params}
+
+
+def test_generator_training_step_configs4_shape_vs_oracle():
+    """BASELINE configs[4]'s per-GPU shape, 4 x 2 s (T = 321): all 335 gradients against the oracle port's float64 autograd (run on this GPU
+    by torch), next to the port's float32 autograd as the yardstick (what the reference's stock kernels deliver on the same inputs)"""
+    B, L, seed = 4, 32000, 0
+    sd = synth.synth_state_dict(seed)
+    noisy, _ = synth.synth_wave(B, L, 1234, "speech")
+    spec = se_b200.compressed_stft((noisy * torch.sqrt(L / noisy.pow(2).sum(-1, keepdim=True))).to(DEV))
+    Tn = spec.shape[-1]
+    masks = synth.dropout_masks(3, B, Tn, 101)
+    gr, gi = synth.cotangents(2, B, Tn)
+    gr, gi = gr.to(DEV), gi.to(DEV)
+    _, g64 = _oracle_train_gradients(spec, sd, synth.masks_reference_layout(masks), gr, gi, torch.float64)
+    _, g32 = _oracle_train_gradients(spec, sd, synth.masks_reference_layout(masks), gr, gi, torch.float32)
+    keys = [k for k in g64 if not synth.has_zero_gradient(k)]
+    rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+    ref = {k: rel(g32[k], g64[k]) for k in keys}
+    ref_med, ref_worst = float(np.median(list(ref.values()))), max(ref.values())
+    for engine in ENGINES:
+        m = se_b200.TSCNet(64, 201)
+        m.load_state_dict(sd)
+        m = m.to(DEV).train()
+        st = se_b200.training._state(m)
+        st.engine, st.injected_masks = engine, masks
+        fr, fi = m(spec)
+        ((fr * gr).sum() + (fi * gi).sum()).backward()
+        ours = dict(m.named_parameters())
+        errs = {k: rel(ours[k].grad, g64[k]) for k in keys}
+        worst = max(errs, key=errs.get)
+        med = float(np.median(list(errs.values())))
+        print(f"[4 x 2 s, {engine}] gradients vs float64: median {med:.2e}, worst {errs[worst]:.2e} ({worst}); eager float32: median {ref_med:.2e}, worst {ref_worst:.2e}")
+        am, aw = GRAD_ABS[engine]
+        assert med < am and errs[worst] < aw, (engine, med, errs[worst], worst)
+        del m, st
+
+
+def test_train_forward_philox_masks_and_eval_switch(golden):
+    """without injected masks the forward draws its own (Philox, a new draw every step); eval() goes back to the inference path"""
+    g = golden("train_b2_L10000")
+    m, st = _train_model(g, "tcgen05_f32")
+    spec = torch.complex(torch.from_numpy(g["spec_real"]), torch.from_numpy(g["spec_imag"])).to(DEV)
+    a, _ = m(spec)
+    b, _ = m(spec)
+    assert torch.isfinite(a).all() and not torch.equal(a, b)
+    keep = st._bufs[next(iter(st._bufs))]["conf"]["TSCB_1.time_conformer"]["masks"]["ff1.drop1"].float().mean().item()
+    assert abs(keep - 0.8) < 5e-3
+    m.eval()
+    with torch.no_grad():
+        c, _ = m(spec)
+    assert not c.requires_grad
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("engine", ["simt"])
+def test_two_gpu_syncbn_and_flat_allreduce_equal_single_process(engine):
+    """data-parallel training (main_gan.py:154-171): SyncBatchNorm sums + one flat NCCL all-reduce reproduce the full-batch gradients"""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29533",
+           os.path.join(root, "tools", "train_ddp_check.py"), engine]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -257,3 +257,66 @@ def test_sharding_world_size_2_gloo(tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=180)
         assert p.returncode == 0, out.decode()
+
+
+# ---- training: the data-parallel exchange (SURVEY 8e training; main_gan.py:168-171): one flat all-reduce of the gradient buffer ---------
+_GLOO_TRAIN_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+import se_b200
+from se_b200 import training
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+torch.manual_seed(0)
+m = se_b200.TSCNet(64, 201)
+st = training._state(m)
+flat, views = st.flat(0, torch.device("cpu"))
+names, params = st.params()
+assert flat.numel() == 1834833 and len(names) == 335
+# what GeneratorFunction.backward hands to autograd: views of the flat buffer become the .grad tensors
+flat.copy_(torch.arange(flat.numel(), dtype=torch.float32) * (rank + 1))
+for n, p in zip(names, params):
+    p.grad = views[n].view(views[n].shape)
+assert st.grad_buffer() is flat
+# the next backward must not write the buffer the live .grad tensors alias (it would double-count under accumulation)
+other, _ = st.pick_flat(torch.device("cpu"))
+assert other is not flat and other.data_ptr() != flat.data_ptr()
+out = se_b200.allreduce_gradients(m)
+assert out is flat
+expect = torch.arange(flat.numel(), dtype=torch.float32) * (1 + 2) / 2.0           # mean over the two ranks
+assert torch.allclose(flat, expect)
+assert torch.equal(params[5].grad.reshape(-1), flat[sum(p.numel() for p in params[:5]):sum(p.numel() for p in params[:6])])
+# gradients that do not alias the flat buffer (e.g. set by another code path) still get averaged (coalesced fallback)
+for p in params:
+    p.grad = torch.full_like(p, float(rank))
+assert st.grad_buffer() is None
+se_b200.allreduce_gradients(m)
+assert all(torch.allclose(p.grad, torch.full_like(p, 0.5)) for p in params)
+# SyncBatchNorm conversion (main_gan.py:154) keeps the parameter tree: eight SyncBatchNorm children where the BatchNorm1d were
+ms = torch.nn.SyncBatchNorm.convert_sync_batchnorm(m)
+assert sum(isinstance(x, torch.nn.SyncBatchNorm) for x in ms.modules()) == 8
+assert list(ms.state_dict().keys()) == list(se_b200.TSCNet(64, 201).state_dict().keys())
+grp, w = training._sync_group(ms, training._state(ms))
+assert grp is not None and w == 2
+assert training._sync_group(se_b200.TSCNet(64, 201), st) == (None, 1)               # plain BatchNorm1d: local statistics
+dist.barrier(); dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_gradient_allreduce_world_size_2_gloo(tmp_path):
+    script = tmp_path / "t.py"
+    script.write_text(_GLOO_TRAIN_WORKER)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29617")
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
+    for p in procs:
+        out, _ = p.communicate(timeout=300)
+        assert p.returncode == 0, out.decode()
+
+
+def test_training_dropout_sites_match_the_test_generator():
+    import synth
+    from se_b200 import training
+    assert training.dropout_sites() == synth.dropout_sites() and len(training.dropout_sites()) == 40
