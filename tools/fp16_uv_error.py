@@ -1,6 +1,8 @@
 """VERDICT r1 item 3 experiment (CPU, oracle): the conformer conv module with the GLU output u and the depthwise output v stored in fp16
-(what the CUDA path writes between pw1 -> depthwise -> pw2), whole-path waveform error against the reference goldens."""
-import sys; sys.path.insert(0,'' + ROOT + ''); sys.path.insert(0,'' + ROOT + '/tests')
+(what the CUDA path writes between pw1 -> depthwise -> pw2): whole-path waveform error against the reference goldens."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import torch, numpy as np, synth
 from oracle import tscnet_oracle as O
 import torch.nn.functional as F
