@@ -45,6 +45,8 @@ enum { SEB_LOAD_ROWS = 0, SEB_LOAD_ROWS_LN = 1, SEB_LOAD_CONV = 2, SEB_LOAD_HANK
        SEB_LOAD_CONV_SPLIT = 4, /* CONV on pre-split inputs: every pixel = 64 bf16 hi + 64 bf16 lo (256 bytes); tcgen05 engine only */
        SEB_LOAD_ROWS2 = 5,      /* K = 128: row m = (a[0][m, 0:64] | a[1][m, 0:64]), both with row stride lda: the two 1x1 convs of
                                    MergeBlock (models/tsc_diffusion.py:21-22,32-34) as one contraction over [x | conditioner] */
+       SEB_LOAD_ROWS_F16 = 7,   /* ROWS whose A operand is __half [M, K] (a[0] points at halfs, lda in halfs): the depthwise output v feeding the
+                                   pointwise Conv1d(128 -> 64) of the conformer's conv module (conformer.py:169) */
        SEB_LOAD_CONV_ADJ = 6    /* adjoint of CONV (training, dgrad): rows = pixels of the forward conv's input (M = B*T*Fout), a[0] = gradient
                                    image of the forward conv's output [B, T, Fin, lda] (lda = 64 or 128 channels), nslots = lda / 64,
                                    K = taps * lda in (tap, 64-channel part) order; taps_t / dil / stride_f as in the forward conv */ };
@@ -59,7 +61,9 @@ enum {
   SEB_EPI_GATE = 7,     /* columns interleaved (gate, filter): out[n/2] = sigmoid(g) * tanh(f) with (g, f) = acc + bias + rowbias;
                            rowbias = resid[(m / ldr) * N + n] when resid != NULL: one extra bias row per group of ldr consecutive
                            rows (the diffusion-step projection, constant per utterance; models/tsc_diffusion.py:27-37) */
-  SEB_EPI_RESID_SCALE = 8 /* out = alpha * (acc + bias + resid): (x + output_residual(y)) / sqrt(2), tsc_diffusion.py:39-41 */
+  SEB_EPI_RESID_SCALE = 8, /* out = alpha * (acc + bias + resid): (x + output_residual(y)) / sqrt(2), tsc_diffusion.py:39-41 */
+  SEB_EPI_GLU_F16 = 9     /* SEB_EPI_GLU with a __half output [M, N / 2] (ldo in halfs, % 8 == 0): the GLU output u is stored in 16 bits between
+                             pw1 -> depthwise (conformer.py:165-166); measured whole-path cost 1.3-2.1e-4 of peak (profiles/r2/fp16_uv_error.txt) */
 };
 enum { SEB_ENGINE_TCGEN05 = 0, SEB_ENGINE_SIMT = 1,
        SEB_ENGINE_TCGEN05_F32 = 2 /* tcgen05 with THREE bf16 planes per operand (six products, fp32-grade; w_tc packed with planes = 3), fp32
@@ -190,6 +194,9 @@ int seb200_attention(const void* qkv, const float* rel_pos_emb, const void* rel_
  * x, y [tokens, 128]; w [31][128] (tap-major); bn_scale/bn_shift fold conv bias, running stats and affine */
 int seb200_dwconv_bn_swish(const float* x, const SebSeq* seq, const float* w, const float* bn_scale,
                            const float* bn_shift, float* y, void* stream);
+/* the same stage with y stored as __half [tokens, 128] (fp32 arithmetic inside); x is float, or __half when x_is_half != 0 */
+int seb200_dwconv_bn_swish_f16(const void* x, int x_is_half, const SebSeq* seq, const float* w, const float* bn_scale,
+                               const float* bn_shift, void* y, void* stream);
 /* post_norm + the TSCB outer residual (conformer.py:211, generator.py:70,72): out = LN(x) * g + b + resid */
 int seb200_layernorm_residual(const float* x, long long tokens, const float* gamma, const float* beta,
                               const float* resid, float* out, void* stream);

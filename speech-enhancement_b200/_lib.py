@@ -14,8 +14,8 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libseb200.so")
 
-LOAD_ROWS, LOAD_ROWS_LN, LOAD_CONV, LOAD_HANKEL, LOAD_CONV_SPLIT, LOAD_ROWS2, LOAD_CONV_ADJ = 0, 1, 2, 3, 4, 5, 6
-EPI_BIAS, EPI_SWISH, EPI_GLU, EPI_RESID, EPI_SUBPIXEL, EPI_COMPRESS, EPI_QKV_F16, EPI_GATE, EPI_RESID_SCALE = 0, 1, 2, 3, 4, 5, 6, 7, 8
+LOAD_ROWS, LOAD_ROWS_LN, LOAD_CONV, LOAD_HANKEL, LOAD_CONV_SPLIT, LOAD_ROWS2, LOAD_CONV_ADJ, LOAD_ROWS_F16 = 0, 1, 2, 3, 4, 5, 6, 7
+EPI_BIAS, EPI_SWISH, EPI_GLU, EPI_RESID, EPI_SUBPIXEL, EPI_COMPRESS, EPI_QKV_F16, EPI_GATE, EPI_RESID_SCALE, EPI_GLU_F16 = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
 ENGINE_TCGEN05, ENGINE_SIMT, ENGINE_TCGEN05_F32 = 0, 1, 2
 ABI_VERSION = 2          # SEB200_ABI_VERSION in include/seb200.h
 
@@ -70,6 +70,7 @@ _SIGS = {
     "seb200_split_ri": [_fp, C.c_longlong, _fp, _fp, _fp],
     "seb200_attention": [_fp, _fp, _fp, C.POINTER(SebSeq), _fp, C.c_int, _fp],
     "seb200_dwconv_bn_swish": [_fp, C.POINTER(SebSeq), _fp, _fp, _fp, _fp, _fp],
+    "seb200_dwconv_bn_swish_f16": [_fp, C.c_int, C.POINTER(SebSeq), _fp, _fp, _fp, _fp, _fp],
     "seb200_layernorm_residual": [_fp, C.c_longlong, _fp, _fp, _fp, _fp, _fp],
     "seb200_packed_weight_sizes": [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_int),
                                    C.POINTER(C.c_int), C.POINTER(C.c_int)],

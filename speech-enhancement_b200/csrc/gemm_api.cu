@@ -96,6 +96,7 @@ extern "C" int seb200_gemm(const SebGemm* s, int engine, void* stream) {
   SEB_REQUIRE(s != nullptr, SEB_EINVAL, "gemm: null descriptor");
   SEB_REQUIRE(s->M > 0 && s->N > 0 && s->K > 0 && s->K % BK == 0, SEB_EINVAL, "gemm: bad sizes M=%d N=%d K=%d", s->M, s->N, s->K);
   SEB_REQUIRE(s->a[0] && s->out && aligned16(s->a[0]) && aligned16(s->out), SEB_EALIGN, "gemm: a/out null or unaligned");
+  if (s->loader == SEB_LOAD_ROWS_F16) SEB_REQUIRE(s->lda % 8 == 0 && s->lda >= s->K, SEB_EALIGN, "gemm: fp16 rows need lda %% 8 == 0 and >= K");
   if (s->loader == SEB_LOAD_ROWS || s->loader == SEB_LOAD_ROWS_LN) {
     SEB_REQUIRE(s->lda % 4 == 0 && s->lda >= s->K, SEB_EALIGN, "gemm: lda=%lld must be a multiple of 4 and >= K", s->lda);
   }
@@ -126,6 +127,7 @@ extern "C" int seb200_gemm(const SebGemm* s, int engine, void* stream) {
   }
   if (s->epilogue == SEB_EPI_RESID || s->epilogue == SEB_EPI_RESID_SCALE) SEB_REQUIRE(s->resid && s->ldr % 4 == 0 && aligned16(s->resid), SEB_EALIGN, "gemm: residual null/unaligned");
   if (s->epilogue == SEB_EPI_GLU) SEB_REQUIRE(s->ldo % 2 == 0, SEB_EALIGN, "gemm: ldo must be even");
+  else if (s->epilogue == SEB_EPI_GLU_F16) SEB_REQUIRE(s->ldo % 8 == 0 && s->N % 8 == 0, SEB_EALIGN, "gemm: the fp16 GLU epilogue needs ldo %% 8 == 0 and N %% 8 == 0");
   else if (s->epilogue != SEB_EPI_COMPRESS) SEB_REQUIRE(s->ldo % 4 == 0, SEB_EALIGN, "gemm: ldo must be a multiple of 4");
   if (s->epilogue == SEB_EPI_QKV_F16) SEB_REQUIRE(s->N == 192 && s->ldo == 192, SEB_EINVAL, "gemm: the fp16 q|k|v epilogue needs N == ldo == 192");
 
@@ -144,6 +146,8 @@ extern "C" int seb200_gemm(const SebGemm* s, int engine, void* stream) {
       case SEB_LOAD_CONV * 16 + SEB_EPI_SUBPIXEL:   return launch_simt<SEB_LOAD_CONV, SEB_EPI_SUBPIXEL>(s, g, st);
       case SEB_LOAD_ROWS_LN * 16 + SEB_EPI_SWISH:   return launch_simt<SEB_LOAD_ROWS_LN, SEB_EPI_SWISH>(s, g, st);
       case SEB_LOAD_ROWS_LN * 16 + SEB_EPI_GLU:     return launch_simt<SEB_LOAD_ROWS_LN, SEB_EPI_GLU>(s, g, st);
+      case SEB_LOAD_ROWS_LN * 16 + SEB_EPI_GLU_F16: return launch_simt<SEB_LOAD_ROWS_LN, SEB_EPI_GLU_F16>(s, g, st);
+      case SEB_LOAD_ROWS_F16 * 16 + SEB_EPI_RESID:  return launch_simt<SEB_LOAD_ROWS_F16, SEB_EPI_RESID>(s, g, st);
       case SEB_LOAD_ROWS_LN * 16 + SEB_EPI_BIAS:    return launch_simt<SEB_LOAD_ROWS_LN, SEB_EPI_BIAS>(s, g, st);
       case SEB_LOAD_ROWS_LN * 16 + SEB_EPI_QKV_F16: return launch_simt<SEB_LOAD_ROWS_LN, SEB_EPI_QKV_F16>(s, g, st);
       case SEB_LOAD_CONV_ADJ * 16 + SEB_EPI_BIAS:   return launch_simt<SEB_LOAD_CONV_ADJ, SEB_EPI_BIAS>(s, g, st);
@@ -183,6 +187,8 @@ extern "C" int seb200_gemm(const SebGemm* s, int engine, void* stream) {
       case SEB_LOAD_ROWS_LN * 16 + SEB_EPI_SWISH:   if (nt == 256) return launch_tc<256, 1, SEB_LOAD_ROWS_LN, SEB_EPI_SWISH>(s, g, st); break;
       case SEB_LOAD_ROWS_LN * 16 + SEB_EPI_GLU:     if (nt == 256) return launch_tc<256, 1, SEB_LOAD_ROWS_LN, SEB_EPI_GLU>(s, g, st);
                                                     if (nt == 64)  return launch_tc<64, 1, SEB_LOAD_ROWS_LN, SEB_EPI_GLU, 4, 4>(s, g, st); break;
+      case SEB_LOAD_ROWS_LN * 16 + SEB_EPI_GLU_F16: if (nt == 256) return launch_tc<256, 1, SEB_LOAD_ROWS_LN, SEB_EPI_GLU_F16>(s, g, st); break;
+      case SEB_LOAD_ROWS_F16 * 16 + SEB_EPI_RESID:  if (nt == 64)  return launch_tc<64, 2, SEB_LOAD_ROWS_F16, SEB_EPI_RESID>(s, g, st); break;
       case SEB_LOAD_ROWS_LN * 16 + SEB_EPI_BIAS:    if (nt == 192) return launch_tc<192, 1, SEB_LOAD_ROWS_LN, SEB_EPI_BIAS>(s, g, st);
                                                     if (nt == 64)  return launch_tc<64, 1, SEB_LOAD_ROWS_LN, SEB_EPI_BIAS, 4, 4>(s, g, st); break;
       case SEB_LOAD_ROWS_LN * 16 + SEB_EPI_QKV_F16: if (nt == 192) return launch_tc<192, 1, SEB_LOAD_ROWS_LN, SEB_EPI_QKV_F16>(s, g, st);

@@ -58,6 +58,28 @@ template <> struct Loader<SEB_LOAD_ROWS> {
   }
 };
 
+// plain rows stored as __half (g.a[0] points at halfs, g.lda in halfs): exact in the bf16 hi | lo split (11-bit mantissa)
+template <> struct Loader<SEB_LOAD_ROWS_F16> {
+  struct Row { const __half* p; };
+  __device__ static void init_row(const GemmArgs& g, int m, Row& r) {
+    r.p = (m < g.M) ? reinterpret_cast<const __half*>(g.a[0]) + (long long)m * g.lda : nullptr;
+  }
+  __device__ static void load(const GemmArgs& g, const Row& r, int kc, int sub, float (&v)[8]) {
+    if (r.p) {
+      const uint4 h = __ldg(reinterpret_cast<const uint4*>(r.p + kc * BK + sub * 8));
+      const uint32_t w[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+        v[2 * i] = f.x; v[2 * i + 1] = f.y;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    }
+  }
+};
+
 // Two 64-wide row sources side by side (K = 128): K chunk 0 reads a[0], chunk 1 reads a[1] (MergeBlock: [x | conditioner],
 // models/tsc_diffusion.py:32-34 -- merge_diffusion and conditioner_projection are one contraction over the pair)
 template <> struct Loader<SEB_LOAD_ROWS2> {
@@ -221,6 +243,15 @@ template <> struct Epi<SEB_EPI_GLU> {   // packed columns: (value_j, gate_j) adj
     v = add_bias(g, n, v);
     float2 o = make_float2(v.x * sigmoidf_acc(v.y), v.z * sigmoidf_acc(v.w));
     *reinterpret_cast<float2*>(g.out + (long long)m * g.ldo + (n >> 1)) = o;
+  }
+};
+
+template <> struct Epi<SEB_EPI_GLU_F16> {   // GLU with a __half output [M, N / 2]
+  __device__ static void apply(const GemmArgs& g, int m, int n, float4 v) {
+    if (m >= g.M || n >= g.N) return;
+    v = add_bias(g, n, v);
+    const __half2 o = __floats2half2_rn(v.x * sigmoidf_acc(v.y), v.z * sigmoidf_acc(v.w));
+    *reinterpret_cast<__half2*>(reinterpret_cast<__half*>(g.out) + (long long)m * g.ldo + (n >> 1)) = o;
   }
 };
 

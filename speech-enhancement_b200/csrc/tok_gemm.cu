@@ -21,13 +21,14 @@ constexpr int TG_W_EPI0 = TG_ROW_WARPS;                                       //
 constexpr int TG_W_MMA = TG_W_EPI0 + TG_EPI_WARPS;                            // 20
 constexpr int TG_W_COPY = TG_W_MMA + 1;                                       // 21
 constexpr int TG_THREADS = (TG_W_COPY + 1) * 32;                              // 704
-template <int KCH> constexpr int tg_slots() { return KCH == 1 ? 3 : 2; }
-template <int KCH> constexpr int tg_xslot() { return BM * 64 * KCH * 4; }     // raw fp32 rows of one tile: 32 / 64 KB
+// AH: the A rows are stored as __half (SEB_LOAD_ROWS_F16): half the bytes per staged tile
+template <int KCH, bool AH = false> constexpr int tg_slots() { return (KCH == 1 || AH) ? 3 : 2; }
+template <int KCH, bool AH = false> constexpr int tg_xslot() { return BM * 64 * KCH * (AH ? 2 : 4); }     // raw rows of one tile: 32 / 64 KB (fp16: 16 / 32 KB)
 // epilogue staging per warp: the packed epilogues (GLU / fp16 q|k|v / gate) transpose 32 x 64 B, the others 32 x 128 B
-template <int EK> constexpr bool tg_packed() { return EK == SEB_EPI_GLU || EK == SEB_EPI_QKV_F16 || EK == SEB_EPI_GATE; }
+template <int EK> constexpr bool tg_packed() { return EK == SEB_EPI_GLU || EK == SEB_EPI_GLU_F16 || EK == SEB_EPI_QKV_F16 || EK == SEB_EPI_GATE; }
 template <int EK> constexpr int tg_stg() { return tg_packed<EK>() ? 2048 : 4096; }
-template <int NT, int KCH, int EK> constexpr int tg_smem_bytes() {
-  return 1024 + tg_slots<KCH>() * tg_xslot<KCH>() + KCH * 2 * NT * 128 + TG_EPI_WARPS * tg_stg<EK>() + 2 * 64 * 4 + NT * 4;
+template <int NT, int KCH, int EK, bool AH = false> constexpr int tg_smem_bytes() {
+  return 1024 + tg_slots<KCH, AH>() * tg_xslot<KCH, AH>() + KCH * 2 * NT * 128 + TG_EPI_WARPS * tg_stg<EK>() + 2 * 64 * 4 + NT * 4;
 }
 
 namespace ptx {
@@ -47,10 +48,11 @@ __device__ __forceinline__ void tg_tmem_st8(uint32_t taddr, const uint32_t* r) {
 template <int NT, int KCH, int LK, int EK>
 __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs g, const uint8_t* __restrict__ w_tc) {
   static_assert(NT % 64 == 0 && NT <= 256 && (KCH == 1 || KCH == 2), "unsupported token GEMM shape");
-  static_assert(LK == SEB_LOAD_ROWS || (LK == SEB_LOAD_ROWS_LN && KCH == 1) || (LK == SEB_LOAD_ROWS2 && KCH == 2),
-                "loader: plain rows, LayerNorm over 64 features, or two 64-wide sources side by side");
+  static_assert(LK == SEB_LOAD_ROWS || LK == SEB_LOAD_ROWS_F16 || (LK == SEB_LOAD_ROWS_LN && KCH == 1) || (LK == SEB_LOAD_ROWS2 && KCH == 2),
+                "loader: plain rows (fp32 or fp16), LayerNorm over 64 features, or two 64-wide sources side by side");
+  constexpr bool AH = LK == SEB_LOAD_ROWS_F16;
   constexpr int STG = tg_stg<EK>();
-  constexpr int K = 64 * KCH, NSLOT = tg_slots<KCH>(), XSLOT = tg_xslot<KCH>(), PITCH = K * 4, NCH = K / 4;   // 16-byte chunks per row
+  constexpr int K = 64 * KCH, NSLOT = tg_slots<KCH, AH>(), XSLOT = tg_xslot<KCH, AH>(), PITCH = K * (AH ? 2 : 4), NCH = PITCH / 16;   // 16-byte chunks per row
   constexpr bool ACC2 = (2 * K + 2 * NT <= 512);                 // double-buffered accumulator when tensor memory has room
   constexpr uint32_t T_ACC = 2 * K;                              // TMEM: XA[2] (K columns each: hi | lo) | ACC[1 or 2] (NT columns each)
   extern __shared__ uint8_t smem_raw[];
@@ -110,15 +112,29 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs 
 #pragma unroll
       for (int c16 = 0; c16 < K / 16; ++c16) {          // 16 k-values -> 8 hi + 8 lo packed columns
         uint32_t hi[8], lo[8];
+        if (AH) {                                       // 16 halfs = two 16-byte chunks
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int c = c16 * 4 + j;
-          const float4 v = *reinterpret_cast<const float4*>(xr + ((c ^ sw) << 4));
-          float2 y01 = make_float2(v.x, v.y), y23 = make_float2(v.z, v.w);
-          if (LK == SEB_LOAD_ROWS_LN)
-            ln_apply4(v, mean, rstd, *reinterpret_cast<const float4*>(sG + c * 4), *reinterpret_cast<const float4*>(sBt + c * 4), y01, y23);
-          split_bf16x2(y01.x, y01.y, hi[2 * j], lo[2 * j]);
-          split_bf16x2(y23.x, y23.y, hi[2 * j + 1], lo[2 * j + 1]);
+          for (int j = 0; j < 2; ++j) {
+            const int c = c16 * 2 + j;
+            const uint4 h = *reinterpret_cast<const uint4*>(xr + ((c ^ sw) << 4));
+            const uint32_t w4[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w4[i]));
+              split_bf16x2(f.x, f.y, hi[4 * j + i], lo[4 * j + i]);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c = c16 * 4 + j;
+            const float4 v = *reinterpret_cast<const float4*>(xr + ((c ^ sw) << 4));
+            float2 y01 = make_float2(v.x, v.y), y23 = make_float2(v.z, v.w);
+            if (LK == SEB_LOAD_ROWS_LN)
+              ln_apply4(v, mean, rstd, *reinterpret_cast<const float4*>(sG + c * 4), *reinterpret_cast<const float4*>(sBt + c * 4), y01, y23);
+            split_bf16x2(y01.x, y01.y, hi[2 * j], lo[2 * j]);
+            split_bf16x2(y23.x, y23.y, hi[2 * j + 1], lo[2 * j + 1]);
+          }
         }
         ptx::tg_tmem_st8(xa + (uint32_t)(c16 * 8), hi);
         ptx::tg_tmem_st8(xa + (uint32_t)(K / 2 + c16 * 8), lo);
@@ -187,6 +203,35 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs 
           if (EK == SEB_EPI_GATE && g.resid) {
             const int mr = m0 + wq * 32 + lane;
             rb = g.resid + (long long)((mr < g.M ? mr : g.M - 1) / (int)g.ldr) * g.N + n0;
+          }
+          if (EK == SEB_EPI_GLU_F16) {             // 32 accumulator columns -> 16 halfs = two 16-byte chunks
+#pragma unroll
+            for (int qq = 0; qq < 2; ++qq) {
+              if (qq * 16 < ncols) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int c = 16 * qq + 4 * i;
+                  const float4 b = *reinterpret_cast<const float4*>(sBias + n0 + c);
+                  const __half2 h = __floats2half2_rn((v[c + 0] + b.x) * sigmoidf_acc(v[c + 1] + b.y), (v[c + 2] + b.z) * sigmoidf_acc(v[c + 3] + b.w));
+                  pk[i] = *reinterpret_cast<const uint32_t*>(&h);
+                }
+                stq[lane * 4 + (qq ^ ((lane >> 1) & 3))] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              }
+            }
+            __syncwarp();
+            const int cc = lane & 3;
+            if (cc * 16 < ncols) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int R = 8 * i + (lane >> 2);
+                const int m = m0 + wq * 32 + R;
+                const uint4 o = stq[R * 4 + (cc ^ ((R >> 1) & 3))];
+                if (m < g.M) *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(g.out) + (long long)m * g.ldo + (n0 >> 1) + cc * 8) = o;
+              }
+            }
+            __syncwarp();
+            continue;
           }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {            // output chunk q <- accumulator columns 8q .. 8q + 7
@@ -339,8 +384,9 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs 
           const int i = kk * 32 + lane, r = i / NCH, c = i % NCH;
           const int m = m0 + r;
           const int mc = m < g.M ? m : g.M - 1;
-          const float* src = (LK == SEB_LOAD_ROWS2) ? ((c < 16 ? src0 : src1) + (long long)mc * g.lda + (c & 15) * 4)
-                                                    : (src0 + (long long)mc * g.lda + c * 4);
+          const void* src = (LK == SEB_LOAD_ROWS2) ? (const void*)((c < 16 ? src0 : src1) + (long long)mc * g.lda + (c & 15) * 4)
+                            : AH ? (const void*)(reinterpret_cast<const __half*>(src0) + (long long)mc * g.lda + c * 8)
+                                 : (const void*)(src0 + (long long)mc * g.lda + c * 4);
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
                        ::"r"(dst0 + r * PITCH + ((c ^ (r & 7)) << 4)), "l"(src), "r"(m < g.M ? 16u : 0u) : "memory");
         }
@@ -359,7 +405,7 @@ template <int NT, int KCH, int LK, int EK>
 static int launch_tok(const SebGemm* s, const GemmArgs& g, cudaStream_t st) {
   static PerDeviceOnce attr_done;
   static int num_sms = 0;
-  constexpr int SMEM = tg_smem_bytes<NT, KCH, EK>();
+  constexpr int SMEM = tg_smem_bytes<NT, KCH, EK, LK == SEB_LOAD_ROWS_F16>();
   static_assert(SMEM + 256 <= 232448, "token GEMM: shared memory over the 227 KB per-CTA limit");
   if (!attr_done.done()) {
     cudaError_t e = cudaFuncSetAttribute(tok_gemm_kernel<NT, KCH, LK, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -386,6 +432,10 @@ int launch_tok_gemm(const SebGemm* s, const GemmArgs& g, cudaStream_t st) {
     return launch_tok<192, 1, SEB_LOAD_ROWS_LN, SEB_EPI_QKV_F16>(s, g, st);
   if (s->loader == SEB_LOAD_ROWS_LN && s->epilogue == SEB_EPI_GLU && nt == 256 && s->K == 64)
     return launch_tok<256, 1, SEB_LOAD_ROWS_LN, SEB_EPI_GLU>(s, g, st);
+  if (s->loader == SEB_LOAD_ROWS_LN && s->epilogue == SEB_EPI_GLU_F16 && nt == 256 && s->K == 64)
+    return launch_tok<256, 1, SEB_LOAD_ROWS_LN, SEB_EPI_GLU_F16>(s, g, st);
+  if (s->loader == SEB_LOAD_ROWS_F16 && s->epilogue == SEB_EPI_RESID && nt == 64 && s->K == 128 && s->lda == 128)
+    return launch_tok<64, 2, SEB_LOAD_ROWS_F16, SEB_EPI_RESID>(s, g, st);
   if (s->loader == SEB_LOAD_ROWS && s->epilogue == SEB_EPI_RESID && nt == 64 && s->K == 64 && s->lda == 64)
     return launch_tok<64, 1, SEB_LOAD_ROWS, SEB_EPI_RESID>(s, g, st);
   if (s->loader == SEB_LOAD_ROWS && s->epilogue == SEB_EPI_RESID && nt == 64 && s->K == 128 && s->lda == 128)

@@ -25,8 +25,8 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from ._lib import (EPI_BIAS, EPI_GLU, EPI_QKV_F16, EPI_RESID, EPI_SUBPIXEL, EPI_SWISH, LOAD_CONV, LOAD_CONV_SPLIT, LOAD_ROWS,
-                   LOAD_ROWS_LN)
+from ._lib import (EPI_BIAS, EPI_GLU, EPI_GLU_F16, EPI_QKV_F16, EPI_RESID, EPI_SUBPIXEL, EPI_SWISH, LOAD_CONV, LOAD_CONV_SPLIT, LOAD_ROWS,
+                   LOAD_ROWS_F16, LOAD_ROWS_LN)
 from .packing import PackedWeight, conv_weight_matrix, glu_interleave, pack_weight
 
 
@@ -151,6 +151,10 @@ class TSCNet(nn.Module):
         # sequences at least this long take the tcgen05 kernel when attention_variant == 0 (measured, three-group kernel vs mma.sync:
         # 3.51 vs 4.91 ms at n = 4801, 7.15 vs 7.78 ms at n = 641, 3.6 vs 2.3 ms at n = 101 -- tools/attn_tc_check.py)
         self.attention_tc_min_len = 512
+        self.half_v = True                     # tcgen05 engine: the depthwise output v is stored in fp16 between depthwise -> pw2 (-17 GB of HBM traffic per
+                                               # 64 x 4 s step, pw2 7.3 -> 4.8 ms; whole-path cost 1.3-1.6e-4 of peak, profiles/r2/fp16_uv_error.txt)
+        self.half_u = False                    # opt-in: the GLU output u in fp16 too -- measured a net loss (the depthwise kernel is FFMA-issue bound and
+                                               # pays a half2 -> float2 conversion per window load: 13.0 vs 10.0 ms per step), so off by default
         self.overlap_decoders = False          # opt-in: complex decoder on a side stream next to the mask decoder (second buffer set; measured in DESIGN.md)
         self._packed: Optional[Dict[str, object]] = None
         self._packed_key = None
@@ -338,9 +342,14 @@ class TSCNet(nn.Module):
             ops.attention(qkv, P[f"{p}.attn.emb"], seq, o, 1)
         ops.gemm(loader=LOAD_ROWS, epilogue=EPI_RESID, M=M, w=P[f"{p}.attn.out"], a=[o], lda=64, out=y, ldo=64, resid=y, ldr=64, alpha=1.0, engine=eng, label="attn_out")
         # y += ConvModule(y)
-        ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_GLU, M=M, w=P[f"{p}.conv.pw1"], a=[y], lda=64, ln=P[f"{p}.conv.ln"], out=u, ldo=128, engine=eng, label="pw1_glu")
-        ops.dwconv_bn_swish(u, seq, P[f"{p}.conv.dw"], P[f"{p}.conv.bn"][0], P[f"{p}.conv.bn"][1], v)
-        ops.gemm(loader=LOAD_ROWS, epilogue=EPI_RESID, M=M, w=P[f"{p}.conv.pw2"], a=[v], lda=128, out=y, ldo=64, resid=y, ldr=64, alpha=1.0, engine=eng, label="pw2")
+        hu, hv = fused and self.half_u, fused and self.half_v
+        half = lambda t: t.view(-1).view(torch.float16)[:M * 128].view(M, 128)
+        uu, vv = (half(u) if hu else u), (half(v) if hv else v)
+        ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_GLU_F16 if hu else EPI_GLU, M=M, w=P[f"{p}.conv.pw1"], a=[y], lda=64, ln=P[f"{p}.conv.ln"], out=uu, ldo=128,
+                 engine=eng, label="pw1_glu")
+        ops.dwconv_bn_swish(uu, seq, P[f"{p}.conv.dw"], P[f"{p}.conv.bn"][0], P[f"{p}.conv.bn"][1], vv)
+        ops.gemm(loader=LOAD_ROWS_F16 if hv else LOAD_ROWS, epilogue=EPI_RESID, M=M, w=P[f"{p}.conv.pw2"], a=[vv], lda=128, out=y, ldo=64, resid=y, ldr=64, alpha=1.0,
+                 engine=eng, label="pw2")
         # x = post_norm(y + 0.5 * FF2(LN(y))) + x
         if fused:
             ops.ffn_fused(y, x, P[f"{p}.ff2.ln"], P[f"{p}.ff2.w1"], P[f"{p}.ff2.w2"], 0.5, post=P[f"{p}.post_norm"], resid2=x)

@@ -102,10 +102,14 @@ def gemm(*, loader: int, epilogue: int, M: int, w: PackedWeight, a: Sequence[tor
          label: str = "gemm", k_logical: Optional[int] = None):
     """One launch of the GEMM engine (see include/seb200.h: SebGemm)."""
     lib = _lib.load()
-    if epilogue == EPI_QKV_F16:
+    if epilogue in (EPI_QKV_F16, _lib.EPI_GLU_F16):
         if out.dtype != torch.float16 or not out.is_contiguous():
-            raise RuntimeError("the fp16 q|k|v epilogue writes a contiguous float16 [M, 192] tensor")
+            raise RuntimeError("the fp16 epilogues (q|k|v, GLU) write a contiguous float16 tensor")
         _f32c(resid, *a)
+    elif loader == _lib.LOAD_ROWS_F16:
+        if a[0].dtype != torch.float16 or not a[0].is_contiguous() or not a[0].is_cuda:
+            raise RuntimeError("LOAD_ROWS_F16 reads a contiguous CUDA float16 [M, K] tensor")
+        _f32c(out, resid)
     elif loader == LOAD_CONV_SPLIT:
         for t in a:
             if t.dtype != torch.bfloat16 or not t.is_contiguous() or not t.is_cuda:
@@ -131,8 +135,8 @@ def gemm(*, loader: int, epilogue: int, M: int, w: PackedWeight, a: Sequence[tor
     g.resid, g.ldr, g.alpha = ptr(resid), ldr, alpha
     if _PROF is not None:
         # algorithmic bytes: the A rows once, the output once (fp16 q|k|v: 2 B, GLU / gate: half the columns), the residual once
-        n_out = g.N // 2 if epilogue in (EPI_GLU, _lib.EPI_GATE) else g.N
-        nbytes = 4.0 * M * (k_logical or w.K) + (2.0 if epilogue == EPI_QKV_F16 else 4.0) * M * n_out
+        n_out = g.N // 2 if epilogue in (EPI_GLU, _lib.EPI_GATE, _lib.EPI_GLU_F16) else g.N
+        nbytes = (2.0 if loader == _lib.LOAD_ROWS_F16 else 4.0) * M * (k_logical or w.K) + (2.0 if epilogue in (EPI_QKV_F16, _lib.EPI_GLU_F16) else 4.0) * M * n_out
         if epilogue in (EPI_RESID, _lib.EPI_RESID_SCALE):
             nbytes += 4.0 * M * g.N
         tok = _pb(label, 2.0 * M * g.N * (k_logical or w.K), nbytes)
@@ -438,7 +442,18 @@ def attention(qkv, rel_pos_emb, seq: SebSeq, out, variant: int = 0, rel_pos_emb_
 
 
 def dwconv_bn_swish(x, seq: SebSeq, w, bn_scale, bn_shift, y):
-    _f32c(x, w, bn_scale, bn_shift, y)
+    """x, y [tokens, 128]: float32 -> float32, float32 -> float16 (the model's default: half the write) or float16 -> float16; fp32 arithmetic inside"""
+    _f32c(w, bn_scale, bn_shift)
+    if y.dtype == torch.float16:
+        if x.dtype not in (torch.float16, torch.float32) or not (x.is_contiguous() and y.is_contiguous() and x.is_cuda and y.is_cuda):
+            raise RuntimeError("dwconv_bn_swish: contiguous CUDA tensors expected (x float32 or float16, y float16)")
+        xh = x.dtype == torch.float16
+        tok = _pb("dwconv", 62.0 * x.numel(), (4.0 if xh else 6.0) * x.numel()) if _PROF is not None else None
+        check(_lib.load().seb200_dwconv_bn_swish_f16(ptr(x), int(xh), C.byref(seq), ptr(w), ptr(bn_scale), ptr(bn_shift), ptr(y), stream_ptr()),
+              "seb200_dwconv_bn_swish_f16")
+        _pe(tok)
+        return y
+    _f32c(x, y)
     tok = _pb("dwconv", 62.0 * x.numel(), 8.0 * x.numel()) if _PROF is not None else None
     check(_lib.load().seb200_dwconv_bn_swish(ptr(x), C.byref(seq), ptr(w), ptr(bn_scale), ptr(bn_shift), ptr(y), stream_ptr()),
           "seb200_dwconv_bn_swish")

@@ -427,3 +427,46 @@ def test_dwconv_bn_swish(axis, B, T, Fh):
     assert rel_max(y.cpu(), ref) < 1e-5
 
 
+
+
+# ---- fp16 storage of the conv module's intermediates (GLU output u, depthwise output v): half the HBM traffic of pw1 -> depthwise -> pw2
+@pytest.mark.parametrize("engine", ["simt", "tcgen05"])
+@pytest.mark.parametrize("M", [129, 777, 20000])
+def test_glu_fp16_output_and_fp16_rows_gemm(engine, M):
+    from se_b200._lib import EPI_GLU_F16, LOAD_ROWS_F16
+    x = rnd(M, 64, seed=205, scale=3.0) + 0.7
+    g, be = rnd(64, seed=206, scale=0.2) + 1.0, rnd(64, seed=207, scale=0.2)
+    xn = F.layer_norm(x.double(), (64,), g.double(), be.double(), 1e-5)
+    w, b = rnd(256, 64, seed=208, scale=0.17), rnd(256, seed=209, scale=0.1)
+    h = xn @ w.double().t() + b.double()
+    wi, bi = packing.glu_interleave(w.cpu(), b.cpu())
+    u = torch.empty(M, 128, device=DEV, dtype=torch.float16)
+    ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_GLU_F16, M=M, w=packing.pack_weight(wi, 256, bi).to(DEV), a=[x], lda=64, ln=(g, be), out=u, ldo=128, engine=engine)
+    ref_u = h[:, :128] * torch.sigmoid(h[:, 128:])
+    assert rel_max(u.double(), ref_u) < 1e-3                     # fp16 rounding of the output: 2^-11 relative
+    # pointwise 128 -> 64 + bias + residual reading fp16 rows (exact in the bf16 hi | lo split)
+    v = (rnd(M, 128, seed=210, scale=1.5)).to(torch.float16)
+    w3, b3, res = rnd(64, 128, seed=211, scale=0.12), rnd(64, seed=212, scale=0.1), rnd(M, 64, seed=213)
+    out = res.clone()
+    ops.gemm(loader=LOAD_ROWS_F16, epilogue=EPI_RESID, M=M, w=packing.pack_weight(w3.cpu(), 64, b3.cpu()).to(DEV), a=[v], lda=128, out=out, ldo=64, resid=out, ldr=64,
+             alpha=1.0, engine=engine)
+    ref = v.double() @ w3.double().t() + b3.double() + res.double()
+    assert rel_max(out, ref) < TOL[engine]
+
+
+@pytest.mark.parametrize("in_dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("axis,B,T,Fh", [("freq", 2, 5, 101), ("time", 2, 130, 3), ("time", 1, 641, 2)])
+def test_dwconv_bn_swish_fp16_io(axis, B, T, Fh, in_dtype):
+    sd = weights.synth_state_dict(1)
+    p = "TSCB_1.time_conformer.conv.net"
+    u = rnd(B, T, Fh, 128, seed=290).to(in_dtype)
+    seq, to_seq, from_seq = _seq_layouts(B, T, Fh)[axis]
+    scale = sd[f"{p}.5.weight"] / torch.sqrt(sd[f"{p}.5.running_var"] + 1e-5)
+    shift = sd[f"{p}.5.bias"] + (sd[f"{p}.4.conv.bias"] - sd[f"{p}.5.running_mean"]) * scale
+    y = torch.empty(u.shape, device=DEV, dtype=torch.float16)
+    ops.dwconv_bn_swish(u.view(-1, 128), seq, sd[f"{p}.4.conv.weight"].squeeze(1).t().contiguous().to(DEV), scale.to(DEV), shift.to(DEV), y.view(-1, 128))
+    h = to_seq(u.float().cpu()).transpose(1, 2)
+    h = F.conv1d(F.pad(h, (15, 15)), sd[f"{p}.4.conv.weight"], sd[f"{p}.4.conv.bias"], groups=128)
+    h = F.batch_norm(h, sd[f"{p}.5.running_mean"], sd[f"{p}.5.running_var"], sd[f"{p}.5.weight"], sd[f"{p}.5.bias"], False, 0.0, 1e-5)
+    ref = from_seq((h * torch.sigmoid(h)).transpose(1, 2))
+    assert rel_max(y.float().cpu(), ref) < 1e-3
