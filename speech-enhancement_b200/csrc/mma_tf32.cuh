@@ -1,5 +1,5 @@
 // mma_tf32.cuh -- warp-level fp32-grade matrix products on mma.sync m16n8k8 TF32 ("3xTF32": every fp32 operand is split into
-// hi = tf32(x), lo = tf32(x - hi) and the product is accumulated as lo*hi + hi*lo + hi*hi in fp32, ~2^-21 relative operand error).
+// hi = tf32(x), lo = tf32(x - hi) and the product is accumulated as lo*hi + hi*lo + hi*hi in fp32, ~2^-20 relative operand error).
 // Used by the training step's attention kernels and weight-gradient contractions, where gradients of the
 // random-weight network amplify perturbations ~100x and a 10-bit operand mantissa is not enough.  Operands are fetched from shared
 // memory through element accessors, so any layout / transposition is a one-line lambda at the call site.
@@ -14,10 +14,14 @@
 namespace seb {
 namespace tf32 {
 
+// hi = x rounded to the 10-bit TF32 mantissa, lo = x - hi (exact in fp32) rounded the same way: |x - hi - lo| <= 2^-22 |x|, unbiased.
+// The rounding is the integer form (add half an ulp of the 13 dropped bits, mask; a carry into the exponent is the correct result):
+// cvt.rna.tf32.f32 is a multi-instruction sequence on sm_100 (FSETP / SEL / LOP3 / IMAD were 60 % of the first kernels' instruction
+// stream, profiles/r2/ncu_full_attention_train_fwd.txt), and plain truncation of lo biases every product by 2^-21, which this network's
+// ~100x gradient amplification turns into a measurable error (median gradient rel-L2 1.2e-3 instead of < 7.5e-4 at 4 x 2 s).
 __device__ __forceinline__ void split(float x, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-  const float r = x - __uint_as_float(hi);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  lo = (__float_as_uint(x - __uint_as_float(hi)) + 0x1000u) & 0xffffe000u;
 }
 
 __device__ __forceinline__ void mma(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {

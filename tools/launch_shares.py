@@ -22,7 +22,7 @@ def main(path):
         d[1] += 1
     tot = sum(v[0] for v in agg.values())
     n = sum(v[1] for v in agg.values())
-    print(f"# ncu launch list, one forward pass of the hot path at BASELINE configs[1] (64 x 4 s)")
+    print(f"# ncu launch list: {sys.argv[2] if len(sys.argv) > 2 else 'one forward pass of the hot path at BASELINE configs[1] (64 x 4 s)'}")
     print(f"# total {tot:.2f} ms over {n} launches (cold-cache, serialised: compare SHARES)")
     for name, (ms, k) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
         print(f"{ms:9.3f} ms  {ms / tot * 100:5.1f}%  x{k:<3d} {name}")

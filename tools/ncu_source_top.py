@@ -5,6 +5,20 @@ import sys
 
 def main(path, topn=25):
     rows = list(csv.reader(open(path)))
+    # one section per profiled launch: a "Kernel Name" row, a header row, then the SASS lines; summarise the first launch of each kernel
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+    seen = set()
+    for si, st in enumerate(starts):
+        name = rows[st][1].split("(")[0]
+        if name in seen:
+            continue
+        seen.add(name)
+        end = starts[si + 1] if si + 1 < len(starts) else len(rows)
+        print(f"===== {name}")
+        section(rows[st:end], topn)
+
+
+def section(rows, topn):
     hdr = rows[1]
     ci = {h: i for i, h in enumerate(hdr)}
     data = [r for r in rows[2:] if len(r) == len(hdr)]
