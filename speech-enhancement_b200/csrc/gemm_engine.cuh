@@ -513,7 +513,13 @@ gemm_tc_kernel(const GemmArgs g, const uint8_t* __restrict__ w_tc) {
   const uint32_t smem_base = ptx::smem_u32(smem);
   constexpr int STAGE = tc_stage_bytes<NT, NPL>();
   constexpr uint32_t W_BYTES = NT * 128;
-  constexpr uint32_t TMEM_COLS = tc_tmem_cols<NT>();
+  // NPL == 3 keeps TWO accumulators: the hi x hi products go to the first, the five cross terms (2^-8 .. 2^-16 of it) to the second, and the
+  // epilogue adds them.  The tensor pipe's fp32 accumulation truncates, so every MMA that lands in an accumulator costs ~half an ulp OF THAT
+  // ACCUMULATOR, biased toward zero: with all six products in one accumulator a K = 1536 conv took 576 such steps (1.8e-5 of peak after the
+  // whole generator); split this way the large accumulator sees K / 16 steps and the small one's ulp is 2^-8 of it.
+  constexpr uint32_t ACC_COLS = tc_tmem_cols<NT>();
+  constexpr uint32_t TMEM_COLS = (NPL == 3 ? 2 : 1) * ACC_COLS;
+  static_assert(TMEM_COLS <= 512, "two accumulators exceed tensor memory");
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * BM;
@@ -593,6 +599,12 @@ gemm_tc_kernel(const GemmArgs g, const uint8_t* __restrict__ w_tc) {
         if (j < ncols) {
           float v[8];
           ptx::tmem_ld8(taddr + c0 + j, v);
+          if (NPL == 3) {
+            float v2[8];
+            ptx::tmem_ld8(taddr + ACC_COLS + c0 + j, v2);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += v2[i];
+          }
           stg[lane * 8 + (((j >> 2) + 0) ^ (lane & 7))] = make_float4(v[0], v[1], v[2], v[3]);
           stg[lane * 8 + (((j >> 2) + 1) ^ (lane & 7))] = make_float4(v[4], v[5], v[6], v[7]);
         }
@@ -627,16 +639,22 @@ gemm_tc_kernel(const GemmArgs g, const uint8_t* __restrict__ w_tc) {
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
           const uint64_t ko = (uint64_t)((k * 32) >> 4);   // 16 bf16 = 32 bytes along K inside the swizzle row
-          ptx::mma_bf16(tmem_base, a_lo + ko, w_hi + ko, IDESC, (kc | k) ? 1u : 0u);      // smallest terms first
-          ptx::mma_bf16(tmem_base, a_hi + ko, w_lo + ko, IDESC, 1u);
           if (NPL == 3) {
+            const uint32_t first = (kc | k) ? 1u : 0u;
+            const uint32_t acc2 = tmem_base + ACC_COLS;                                    // cross terms: their own accumulator (see above)
             const uint64_t a_mid = ptx::umma_desc_sw128(base + TC_A_BYTES);
             const uint64_t w_mid = ptx::umma_desc_sw128(base + NPL * TC_A_BYTES + W_BYTES);
-            ptx::mma_bf16(tmem_base, a_mid + ko, w_mid + ko, IDESC, 1u);
-            ptx::mma_bf16(tmem_base, a_mid + ko, w_hi + ko, IDESC, 1u);
-            ptx::mma_bf16(tmem_base, a_hi + ko, w_mid + ko, IDESC, 1u);
+            ptx::mma_bf16(acc2, a_lo + ko, w_hi + ko, IDESC, first);                       // smallest terms first
+            ptx::mma_bf16(acc2, a_hi + ko, w_lo + ko, IDESC, 1u);
+            ptx::mma_bf16(acc2, a_mid + ko, w_mid + ko, IDESC, 1u);
+            ptx::mma_bf16(acc2, a_mid + ko, w_hi + ko, IDESC, 1u);
+            ptx::mma_bf16(acc2, a_hi + ko, w_mid + ko, IDESC, 1u);
+            ptx::mma_bf16(tmem_base, a_hi + ko, w_hi + ko, IDESC, first);
+          } else {
+            ptx::mma_bf16(tmem_base, a_lo + ko, w_hi + ko, IDESC, (kc | k) ? 1u : 0u);      // smallest terms first
+            ptx::mma_bf16(tmem_base, a_hi + ko, w_lo + ko, IDESC, 1u);
+            ptx::mma_bf16(tmem_base, a_hi + ko, w_hi + ko, IDESC, 1u);
           }
-          ptx::mma_bf16(tmem_base, a_hi + ko, w_hi + ko, IDESC, 1u);
         }
         ptx::tc_commit(&empty_bar[s]);
       }

@@ -405,13 +405,12 @@ def grad_errors(named_grads, g):
 
 # Gradient yardstick.  The golden holds the reference graph's gradients in float64 and, per parameter, how far the reference's OWN float32
 # autograd is from them (`ref32_err`: median 2.0e-3, worst 3.3e-3 -- this random-weight network amplifies rounding ~100x on the way to the
-# gradients).  Rounding noise of that kind is random per entry, so the bar is on the distribution: median and worst rel-L2 over the 335
-# parameters within a factor of the reference's own float32 figures.  fp32 FFMA loop ("simt"): the same arithmetic class as the reference
-# -> factors 1.5 / 2.  Three-plane tcgen05 ("tcgen05_f32", tensor-core fp32 accumulation, 6 of 9 cross products): forward 1.8e-5 instead of
-# 3e-6, gradients ~2x the reference's float32 noise, worst entries are the ill-conditioned sums (a bias in front of a PReLU whose summands
-# cancel to 1e-3 of their magnitude) -> factors 2.5 / 10.
-GRAD_FACTORS = {"simt": (1.5, 2.0), "tcgen05_f32": (2.5, 10.0)}
-GRAD_ABS = {"simt": (7.5e-4, 4e-3), "tcgen05_f32": (5e-3, 2e-2)}      # 4 x 2 s shape (no float32 CPU reference there): median / worst rel-L2 vs float64
+# gradients, and the figure moves with the input: 4e-4 .. 1e-3 median for the eager float32 port at 4 x 2 s).  Rounding noise of that kind is
+# random per entry, so the bar is on the distribution: median and worst rel-L2 over the 335 parameters within a factor of the float32
+# reference's own figures on the same inputs -- 1.5 x the median and 2 x the worst.  Both engines meet it: the fp32 FFMA loop ("simt"), and the
+# three-plane tcgen05 engine ("tcgen05_f32") since its cross terms accumulate apart from the hi x hi products (with all six products in one
+# tensor-memory accumulator the pipe's truncating fp32 accumulation cost 1.8e-5 of peak in the forward and 3e-3 median / 2e-2 worst here).
+GRAD_FACTORS = {"simt": (1.5, 2.0), "tcgen05_f32": (1.5, 2.0)}
 
 
 @pytest.mark.parametrize("engine", ENGINES)
@@ -444,7 +443,7 @@ def test_generator_training_step_matches_reference(golden, engine):
     med = float(np.median(list(errs.values())))
     ref = [float(g["ref32_err:" + k]) for k in errs]
     ref_med, ref_worst = float(np.median(ref)), float(np.max(ref))
-    print(f"[{engine}] outputs {e_out:.2e}; gradients vs float64 reference: median {med:.2e}, worst {errs[worst]:.2e} ({worst}); "
+    print(f"\n[{engine}] outputs {e_out:.2e}; gradients vs float64 reference: median {med:.2e}, worst {errs[worst]:.2e} ({worst}); "
           f"reference float32 itself: median {ref_med:.2e}, worst {ref_worst:.2e}")
     fm, fw = GRAD_FACTORS[engine]
     assert med < fm * ref_med, (med, ref_med)
@@ -487,6 +486,7 @@ def test_generator_training_step_configs4_shape_vs_oracle():
     rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
     ref = {k: rel(g32[k], g64[k]) for k in keys}
     ref_med, ref_worst = float(np.median(list(ref.values()))), max(ref.values())
+    results = {}
     for engine in ENGINES:
         m = se_b200.TSCNet(64, 201)
         m.load_state_dict(sd)
@@ -499,10 +499,12 @@ def test_generator_training_step_configs4_shape_vs_oracle():
         errs = {k: rel(ours[k].grad, g64[k]) for k in keys}
         worst = max(errs, key=errs.get)
         med = float(np.median(list(errs.values())))
-        print(f"[4 x 2 s, {engine}] gradients vs float64: median {med:.2e}, worst {errs[worst]:.2e} ({worst}); eager float32: median {ref_med:.2e}, worst {ref_worst:.2e}")
-        am, aw = GRAD_ABS[engine]
-        assert med < am and errs[worst] < aw, (engine, med, errs[worst], worst)
+        print(f"\n[4 x 2 s, {engine}] gradients vs float64: median {med:.2e}, worst {errs[worst]:.2e} ({worst}); eager float32: median {ref_med:.2e}, worst {ref_worst:.2e}")
+        results[engine] = (med, errs[worst], worst)
         del m, st
+    for engine, (med, w, wk) in results.items():
+        fm, fw = GRAD_FACTORS[engine]
+        assert med < fm * max(ref_med, 5e-4) and w < fw * max(ref_worst, 2e-3), (engine, med, w, wk, "eager fp32:", ref_med, ref_worst)
 
 
 def test_train_forward_philox_masks_and_eval_switch(golden):
