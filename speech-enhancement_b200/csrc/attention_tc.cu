@@ -159,11 +159,11 @@ __device__ __forceinline__ float ex2f(float x) {
 }
 }  // namespace ptx
 
-#ifdef T5_TRACE
-__device__ long long t5_trace[2][16][8];     // [role][tile][event] clock64 stamps of one CTA (debug builds only)
-#define T5_STAMP(role, t, ev) do { if (blockIdx.x == T5_TRACE && (t) < 16 && ((role) ? lane == 0 : tid == 0)) t5_trace[role][t][ev] = clock64(); } while (0)
+#ifdef T6_TRACE
+__device__ long long t6_trace[6][16][8];     // [role][tile][event] clock64 stamps of one CTA (debug builds only, tools/build_trace_lib.sh): roles 0..2 = softmax warp 0 of group g, 3 = MMA 1 issuer, 4 = MMA 3 issuer
+#define T6_STAMP(role, t, ev) do { if (blockIdx.x == T6_TRACE && (t) < 16 && lane == 0) t6_trace[role][t][ev] = clock64(); } while (0)
 #else
-#define T5_STAMP(role, t, ev) do { } while (0)
+#define T6_STAMP(role, t, ev) do { } while (0)
 #endif
 // +1 / -1: every (query, key) offset of tile t of the 64-query block at i0 lies at or beyond +512 / -512 (conformer.py:108 clamps
 // the distance, so the rel-pos logit is a per-query constant); 0: the tile needs the R GEMM
@@ -318,6 +318,7 @@ attention_tc3_kernel(const __half* __restrict__ qkvh, const __half* __restrict__
         const uint32_t st = sm0 + T6_STAGE0 + (uint32_t)(slot * T6_STAGE);
         const uint64_t bk = ptx::umma_desc_ns(st + T6_KS, 128, 512);
         ptx::mbar_wait_lean<WM>(&full_bar[slot], (uint32_t)(t / T6_STAGES) & 1u);
+        T6_STAMP(3, t, 6);
         for (int g = 0; g < ng; ++g) {
           const uint32_t tS = tmem_base + (uint32_t)(128 * g);
           const uint64_t a0 = ptx::umma_desc_ns(sm0 + T6_AEXP + g * 8192, 128, 512);
@@ -325,6 +326,7 @@ attention_tc3_kernel(const __half* __restrict__ qkvh, const __half* __restrict__
           const bool near = t5_far(i0 + g * T5_BQ, t) == 0;
           if (near && ruse > 0) ptx::mbar_wait_lean<WM>(&bar_RF, (uint32_t)(ruse - 1) & 1u);
           ptx::tc_fence_after();
+          T6_STAMP(3, t, 2 * g);
           ptx::mma_f16_ss(tS, a0, bk, IDESC_S, 0u);
           ptx::mma_f16_ss(tS, a0 + (256 >> 4), bk + (256 >> 4), IDESC_S, 1u);
           if (near) {
@@ -333,6 +335,7 @@ attention_tc3_kernel(const __half* __restrict__ qkvh, const __half* __restrict__
             ++ruse;
           }
           ptx::tc_commit(&bar_S[g]);
+          T6_STAMP(3, t, 2 * g + 1);
         }
       }
     }
@@ -348,10 +351,12 @@ attention_tc3_kernel(const __half* __restrict__ qkvh, const __half* __restrict__
           const uint32_t tP = tmem_base + (uint32_t)(128 * g + 64), tO = tmem_base + (uint32_t)(128 * g + 96);
           ptx::mbar_wait_lean<WM>(&bar_P[g], (uint32_t)t & 1u);
           ptx::tc_fence_after();
+          T6_STAMP(4, t, 2 * g);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
             if (ks < nks) ptx::mma_f16_ts(tO, tP + (uint32_t)(ks * 8), bv + (uint64_t)((ks * 256) >> 4), IDESC_O, (t | ks) ? 1u : 0u);
           ptx::tc_commit(&bar_O[g]);
+          T6_STAMP(4, t, 2 * g + 1);
         }
         ptx::tc_commit(&empty_bar[slot]);
       }
@@ -388,8 +393,10 @@ attention_tc3_kernel(const __half* __restrict__ qkvh, const __half* __restrict__
       constexpr int NK = decltype(nk_tag)::value;
       constexpr bool FAR = decltype(far_tag)::value;
       constexpr int NWR = NK == 64 ? 64 : 40;
+      if (q4 == 0) T6_STAMP(gi, t, 0);
       ptx::mbar_wait_lean<WM>(bS, (uint32_t)t & 1u);
       ptx::tc_fence_after();
+      if (q4 == 0) T6_STAMP(gi, t, 1);
       if (!FAR) {
         uint32_t w[64];
         ptx::tmem_ld32_pack16<0>(tR, w);
@@ -397,6 +404,7 @@ attention_tc3_kernel(const __half* __restrict__ qkvh, const __half* __restrict__
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         ptx::mbar_arrive(&bar_RF);       // R may go to the next group
+        if (q4 == 0) T6_STAMP(gi, t, 2);
 #pragma unroll
         for (int q = 0; q < NWR / 4; ++q)
           asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(myrow + q * 16), "r"(w[4 * q]), "r"(w[4 * q + 1]), "r"(w[4 * q + 2]), "r"(w[4 * q + 3]) : "memory");
@@ -411,6 +419,7 @@ attention_tc3_kernel(const __half* __restrict__ qkvh, const __half* __restrict__
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       ptx::mbar_arrive(bF);              // S sits in registers: the next tile's MMA 1 may overwrite it
+      if (q4 == 0) T6_STAMP(gi, t, 3);
       float s[NK];
       if (FAR) {
 #pragma unroll
@@ -447,10 +456,12 @@ attention_tc3_kernel(const __half* __restrict__ qkvh, const __half* __restrict__
         if ((N1 & 1) == 0) mx = fmaxf(mx, a[N1 - 1]);
         if (FAR) mx += cadd;
       }
+      if (q4 == 0) T6_STAMP(gi, t, 4);
       if (t > 0) {
         ptx::mbar_wait_lean<WM>(bO, (uint32_t)(t - 1) & 1u);
         ptx::tc_fence_after();
       }
+      if (q4 == 0) T6_STAMP(gi, t, 5);
       if (t == 0) {
         m = mx;
       } else {
@@ -481,10 +492,12 @@ attention_tc3_kernel(const __half* __restrict__ qkvh, const __half* __restrict__
         pw[p + 1] = *reinterpret_cast<const uint32_t*>(&h1);
       }
       l += (la.x + la.y) + (lb.x + lb.y);
+      if (q4 == 0) T6_STAMP(gi, t, 6);
       if (NK == 64) ptx::tmem_st32(tP, pw); else ptx::tmem_st8u(tP, pw);
       ptx::tmem_st_wait5();
       ptx::tc_fence_before();
       ptx::mbar_arrive(bP);
+      if (q4 == 0) T6_STAMP(gi, t, 7);
     };
     if (i0g + par >= n) {                // every query row of this warp lies past the sequence: keep the protocol, skip the work
       for (int t = 0; t < ntiles; ++t) {
@@ -523,8 +536,8 @@ attention_tc3_kernel(const __half* __restrict__ qkvh, const __half* __restrict__
   if (warp == T6_W_LOAD) ptx::tmem_dealloc(tmem_base, 512);
 }
 
-#ifdef T5_TRACE
-extern "C" int seb200_t5_trace(long long* host) { return (int)cudaMemcpyFromSymbol(host, t5_trace, sizeof(t5_trace)); }
+#ifdef T6_TRACE
+extern "C" int seb200_t6_trace(long long* host) { return (int)cudaMemcpyFromSymbol(host, t6_trace, sizeof(t6_trace)); }
 #endif
 
 int attention_tc_launch(const __half* qkvh, const __half* Eh, const SebSeq* seq, float* out, cudaStream_t st) {

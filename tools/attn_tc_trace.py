@@ -1,4 +1,4 @@
-"""Per-tile clock64 trace of one CTA of the tcgen05 attention kernel (debug build libseb200_trace.so, -DT5_TRACE=<block>)."""
+"""Per-tile clock64 trace of one CTA of the tcgen05 attention kernel (debug build libseb200_trace.so, tools/build_trace_lib.sh)."""
 import ctypes as C, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -7,7 +7,7 @@ from se_b200 import ops, _lib
 _lib._LIB_PATH = os.path.join(os.path.dirname(_lib._LIB_PATH), "libseb200_trace.so")
 torch.manual_seed(0)
 dev = "cuda"
-B, T, Fh = 16, 641, 101
+B, T, Fh = int(os.environ.get("PROF_B", "64")), int(os.environ.get("PROF_T", "641")), 101
 M = B * T * Fh
 inp_h = (torch.randn(M, 192, device=dev) * 0.7).to(torch.float16)
 emb = torch.randn(1025, 16, device=dev); emb_h = ops.pack_rel_pos(emb)
@@ -16,14 +16,20 @@ out = torch.zeros(M, 64, device=dev)
 for _ in range(3):
     ops.attention(inp_h, emb, seq, out, 3, emb_h)
 torch.cuda.synchronize()
-buf = (C.c_longlong * (2 * 16 * 8))()
+buf = (C.c_longlong * (6 * 16 * 8))()
 lib = _lib.load()
-lib.seb200_t5_trace.argtypes = [C.POINTER(C.c_longlong)]
-print("rc", lib.seb200_t5_trace(buf))
-tr = torch.tensor(list(buf)).view(2, 16, 8)
-t0 = int(tr[0, 0, 0])
-print("softmax warp 0 (rel clk): tile: wantS gotS  F_arrive  preO  gotO  preStWait  P_arrive | control: wantF gotF mma1_issued gotP mma3_issued")
-for t in range(11):
-    a = [int(v) - t0 if int(v) else -1 for v in tr[0, t, :7]]
-    c = [int(v) - t0 if int(v) else -1 for v in tr[1, t, :5]]
-    print(t, a, "|", c)
+lib.seb200_t6_trace.argtypes = [C.POINTER(C.c_longlong)]
+print("rc", lib.seb200_t6_trace(buf))
+tr = torch.tensor(list(buf)).view(6, 16, 8)
+t0 = int(tr[tr > 0].min())
+nt = (T + 63) // 64
+for g in range(3):
+    print(f"softmax group {g} warp 0 (clk since start): tile: wantS gotS R_read S_read max gotO exp_done P_arrive")
+    for t in range(nt):
+        print(" ", t, [int(v) - t0 if int(v) else -1 for v in tr[g, t]])
+print("MMA 1 issuer: tile: [ready(g) committed(g)] x 3, full_bar")
+for t in range(nt):
+    print(" ", t, [int(v) - t0 if int(v) else -1 for v in tr[3, t, :7]])
+print("MMA 3 issuer: tile: [gotP(g) committed(g)] x 3")
+for t in range(nt):
+    print(" ", t, [int(v) - t0 if int(v) else -1 for v in tr[4, t, :6]])
