@@ -10,6 +10,8 @@ Public surface (mirrors the reference's interface for this path):
 * ``shard_slice`` / ``enhance_sharded``                     batch sharding across ranks (inference has no collective)
 * ``TSCNet.train()`` + ``forward`` + ``loss.backward()``      core/function.py:218-277: training.py; ``allreduce_gradients``
   = the DDP exchange of main_gan.py:168-171 as one flat all-reduce
+* ``MetricLabelPipeline`` / ``batch_pesq``                   models/discriminator.py:17-32: the PESQ label batches of the discriminator
+  step as an asynchronous host pipeline (side-stream copies + worker pool); ``discriminator.Discriminator`` is the stock-PyTorch module
 * ``tsc_diffusion.TSCNet(num_channel, num_features, noise_schedule)``   models/tsc_diffusion.py:43-90
 * ``diffusion.predict_tsc`` / ``DiffusionEnhancerB200``      inference_diffuse.py:231-267 (reverse process on the same kernels)
 
@@ -19,7 +21,8 @@ from .generator import TSCNet
 from .dsp import batch_stft, compressed_stft, normalize_batch, uncompressed_istft
 from .enhancer import EnhancerB200
 from .sharding import enhance_sharded, shard_slice
-from . import ops, packing, _lib, tsc_diffusion, diffusion, train_ops, training
+from . import ops, packing, _lib, tsc_diffusion, diffusion, train_ops, training, metric_labels
+from .metric_labels import MetricLabelPipeline, batch_pesq
 from .training import allreduce_gradients
 from .diffusion import DiffusionEnhancerB200, predict_tsc
 
@@ -37,4 +40,4 @@ def load_model(model_path, device="cuda"):
 
 
 __all__ = ["TSCNet", "compressed_stft", "uncompressed_istft", "normalize_batch", "batch_stft", "EnhancerB200", "load_model", "shard_slice",
-           "enhance_sharded", "ops", "packing", "tsc_diffusion", "diffusion", "DiffusionEnhancerB200", "predict_tsc", "training", "train_ops", "allreduce_gradients"]
+           "enhance_sharded", "ops", "packing", "tsc_diffusion", "diffusion", "DiffusionEnhancerB200", "predict_tsc", "training", "train_ops", "allreduce_gradients", "metric_labels", "MetricLabelPipeline", "batch_pesq"]

@@ -1,0 +1,134 @@
+"""PESQ label pipeline of the metric discriminator, host side.
+
+The reference scores every (clean, estimate) pair of a batch with the `pesq` C extension through a joblib process pool, synchronously, up to three
+times per training step (/root/reference/models/discriminator.py:17-32 `pesq_loss` / `batch_pesq`, called at core/function.py:287,293,300 after a
+blocking `.cpu().numpy()` of the waveforms).  On a B200 the generator step takes tens of milliseconds, so those synchronous CPU batches -- not the
+discriminator's 0.21 GFLOP -- are what a real training run waits for.  This module keeps the reference's arithmetic and failure rule
+(score -1 when the scorer raises; label = (score - 1) / 3.5) and changes the plumbing:
+
+* `MetricLabelPipeline.submit(clean, est)` copies the waveforms device -> pinned host memory on a side stream (the compute stream is never blocked)
+  and hands the pairs to a worker pool; it returns at once;
+* `MetricLabelPipeline.result(handle)` blocks only for what is still outstanding and returns the label tensor on the requested device;
+* `batch_pesq(clean_list, noisy_list)` is the reference's synchronous call on top of the same pool (drop-in for models/discriminator.py:26-32).
+
+The scorer is a plain callable `score_fn(sr, clean_1d, est_1d) -> float`.  By default it is `pesq.pesq(sr, c, n, 'wb')`; the `pesq` wheel is not part
+of this image, so constructing a pipeline without a scorer raises ImportError there instead of producing made-up labels.
+"""
+from __future__ import annotations
+
+import concurrent.futures as cf
+import os
+import threading
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+ScoreFn = Callable[[int, np.ndarray, np.ndarray], float]
+
+
+def _default_score_fn() -> ScoreFn:
+    try:
+        from pesq import pesq  # type: ignore
+    except Exception as e:  # noqa: BLE001
+        raise ImportError("metric_labels: the `pesq` package is not installed; pass score_fn=callable(sr, clean, est) -> float") from e
+    return lambda sr, c, n: pesq(sr, c, n, "wb")
+
+
+def _guarded(score_fn: ScoreFn, sr: int, c: np.ndarray, n: np.ndarray) -> float:
+    """pesq_loss (discriminator.py:17-23): any exception of the scorer (silent crops make PESQ raise) becomes the score -1"""
+    try:
+        return float(score_fn(sr, c, n))
+    except Exception:  # noqa: BLE001
+        return -1.0
+
+
+class _Handle:
+    __slots__ = ("futures", "event", "host", "n")
+
+    def __init__(self):
+        self.futures: List[cf.Future] = []
+        self.event: Optional[torch.cuda.Event] = None
+        self.host = None
+        self.n = 0
+
+
+class MetricLabelPipeline:
+    """Asynchronous `batch_pesq`: submit() right after the generator forward, result() where the discriminator loss needs the labels."""
+
+    def __init__(self, score_fn: Optional[ScoreFn] = None, sr: int = 16000, workers: Optional[int] = None):
+        self.score_fn = score_fn if score_fn is not None else _default_score_fn()
+        self.sr = int(sr)
+        self.workers = int(workers) if workers else max(1, (os.cpu_count() or 2) - 1)
+        # threads, not processes: the PESQ extension and numpy scorers release the GIL in their inner loops, and the waveforms never get pickled
+        self._pool = cf.ThreadPoolExecutor(max_workers=self.workers, thread_name_prefix="seb200-metric")
+        self._copy_stream = None
+        self._lock = threading.Lock()
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def _stage(self, x: torch.Tensor, h: _Handle) -> torch.Tensor:
+        """detach + copy to host without blocking the caller's stream: CUDA tensors go through pinned memory on a side stream"""
+        x = x.detach()
+        if not x.is_cuda:
+            return x.to(torch.float32).contiguous()
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=x.device)
+        host = torch.empty(x.shape, dtype=torch.float32, pin_memory=True)
+        self._copy_stream.wait_stream(torch.cuda.current_stream(x.device))
+        with torch.cuda.stream(self._copy_stream):
+            host.copy_(x.to(torch.float32), non_blocking=True)
+            x.record_stream(self._copy_stream)
+        return host
+
+    def submit(self, clean: torch.Tensor, est: torch.Tensor) -> _Handle:
+        """clean, est: [B, L] waveforms (any device); est may be shorter than clean (the reference crops clean to est's length, function.py:283-285)"""
+        if clean.dim() != 2 or est.dim() != 2 or clean.shape[0] != est.shape[0]:
+            raise ValueError("metric_labels.submit: clean and est must be [B, L] with the same B")
+        h = _Handle()
+        length = min(clean.shape[-1], est.shape[-1])
+        hc, he = self._stage(clean[:, :length], h), self._stage(est[:, :length], h)
+        h.host, h.n = (hc, he), clean.shape[0]
+        if clean.is_cuda or est.is_cuda:
+            h.event = torch.cuda.Event()
+            h.event.record(self._copy_stream)
+        ev = h.event
+
+        def job(b: int) -> float:
+            if ev is not None:
+                ev.synchronize()               # the copies of this batch have landed (blocks this worker only)
+            return _guarded(self.score_fn, self.sr, hc[b].numpy(), he[b].numpy())
+
+        h.futures = [self._pool.submit(job, b) for b in range(h.n)]
+        return h
+
+    def result(self, h: _Handle, device=None) -> torch.Tensor:
+        """labels (score - 1) / 3.5 as float32 [B] (discriminator.py:29-32); a failed pair carries (-1 - 1) / 3.5 like the reference"""
+        scores = np.array([f.result() for f in h.futures], dtype=np.float64)
+        labels = torch.from_numpy(((scores - 1.0) / 3.5).astype(np.float32))
+        return labels.to(device) if device is not None else labels
+
+    def failed(self, h: _Handle) -> np.ndarray:
+        """mask of the pairs whose scorer raised (the reference keeps them; a caller may want to drop the batch)"""
+        return np.array([f.result() == -1.0 for f in h.futures])
+
+    def close(self):
+        self._pool.shutdown(wait=True)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+_shared: Optional[MetricLabelPipeline] = None
+
+
+def batch_pesq(clean: Sequence[np.ndarray], noisy: Sequence[np.ndarray], score_fn: Optional[ScoreFn] = None, device="cuda") -> torch.Tensor:
+    """The reference's synchronous call (models/discriminator.py:26-32): lists of 1-D numpy waveforms in, label tensor on `device` out."""
+    global _shared
+    if _shared is None or (score_fn is not None and _shared.score_fn is not score_fn):
+        _shared = MetricLabelPipeline(score_fn)
+    c = torch.from_numpy(np.stack([np.asarray(x, dtype=np.float32) for x in clean]))
+    n = torch.from_numpy(np.stack([np.asarray(x, dtype=np.float32) for x in noisy]))
+    return _shared.result(_shared.submit(c, n), device=device)

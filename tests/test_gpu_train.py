@@ -533,3 +533,20 @@ def test_two_gpu_syncbn_and_flat_allreduce_equal_single_process(engine):
            os.path.join(root, "tools", "train_ddp_check.py"), engine]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_metric_label_pipeline_from_device_tensors():
+    """the PESQ label batches of the discriminator step (models/discriminator.py:17-32, core/function.py:283-300) submitted from CUDA
+    tensors: copies run on a side stream into pinned memory while the compute stream keeps going; labels equal the synchronous rule"""
+    import numpy as np
+    score = lambda sr, c, n: 1.0 + 3.5 * max(float(np.dot(c, n) / (np.linalg.norm(c) * np.linalg.norm(n) + 1e-12)), 0.0)
+    clean = torch.randn(4, 32000, device=DEV)
+    est = (clean + 0.3 * torch.randn_like(clean))[:, :31900]
+    with se_b200.MetricLabelPipeline(score, workers=4) as pipe:
+        h = pipe.submit(clean, est)
+        busy = torch.randn(4096, 4096, device=DEV) @ torch.randn(4096, 4096, device=DEV)      # the compute stream is not blocked by the submit
+        clean.add_(1.0)                                                                     # later writes to the source do not reach the staged copy
+        lab = pipe.result(h, device=DEV)
+    clean.sub_(1.0)
+    want = torch.tensor([(score(16000, clean[b, :31900].cpu().numpy(), est[b].cpu().numpy()) - 1) / 3.5 for b in range(4)], device=DEV)
+    assert lab.is_cuda and torch.allclose(lab, want, atol=1e-5) and torch.isfinite(busy).all()

@@ -5,6 +5,7 @@ import re
 import subprocess
 import sys
 
+import numpy as np
 import pytest
 import torch
 
@@ -320,3 +321,60 @@ def test_training_dropout_sites_match_the_test_generator():
     import synth
     from se_b200 import training
     assert training.dropout_sites() == synth.dropout_sites() and len(training.dropout_sites()) == 40
+
+
+# ------------------------------------------------------------------------------------------------ PESQ label pipeline (host side)
+def _toy_score(sr, c, n):
+    """stand-in scorer with PESQ's range (1 .. 4.5), monotone in the correlation of the pair; raises on a silent reference like the real one"""
+    if float(np.abs(c).max()) == 0.0:
+        raise RuntimeError("silent")
+    r = float(np.dot(c, n) / (np.linalg.norm(c) * np.linalg.norm(n) + 1e-12))
+    return 1.0 + 3.5 * max(r, 0.0)
+
+
+def test_metric_label_pipeline_matches_reference_rule():
+    """batch_pesq (models/discriminator.py:17-32): label = (score - 1) / 3.5, a raising scorer counts as -1, order preserved, asynchronous submit"""
+    import time
+    from se_b200 import MetricLabelPipeline, batch_pesq
+    g = torch.Generator().manual_seed(0)
+    clean = torch.randn(6, 4000, generator=g)
+    est = clean[:, :3900] + 0.5 * torch.randn(6, 3900, generator=g)          # shorter than clean: cropped like core/function.py:283-285
+    clean[4] = 0.0                                                            # silent reference -> scorer raises -> -1
+    with MetricLabelPipeline(_toy_score, workers=3) as pipe:
+        h = pipe.submit(clean, est)
+        lab = pipe.result(h)
+        assert lab.dtype == torch.float32 and lab.shape == (6,)
+        want = [(_toy_score(16000, clean[b, :3900].numpy(), est[b].numpy()) - 1) / 3.5 if b != 4 else (-1.0 - 1.0) / 3.5 for b in range(6)]
+        assert torch.allclose(lab, torch.tensor(want, dtype=torch.float32), atol=1e-6)
+        assert list(pipe.failed(h)) == [False, False, False, False, True, False]
+        # submit does not wait for the scorer
+        slow = lambda sr, c, n: (time.sleep(0.2), 2.0)[1]
+        pipe.score_fn = slow
+        t0 = time.perf_counter()
+        h2 = pipe.submit(clean, est)
+        assert time.perf_counter() - t0 < 0.1
+        assert torch.allclose(pipe.result(h2), torch.full((6,), (2.0 - 1) / 3.5))
+    # the synchronous reference-shaped call
+    out = batch_pesq(list(clean[:3].numpy()), list(clean[:3].numpy()), score_fn=_toy_score, device="cpu")
+    assert torch.allclose(out, torch.ones(3), atol=1e-6)
+
+
+def test_metric_label_pipeline_needs_a_scorer_without_pesq():
+    import importlib.util
+    from se_b200 import MetricLabelPipeline
+    if importlib.util.find_spec("pesq") is None:
+        with pytest.raises(ImportError):
+            MetricLabelPipeline()
+
+
+def test_discriminator_state_dict_and_shapes():
+    """models/discriminator.py:35-62: same keys as the reference module (spectral-norm parametrisation included), one score in (0, 1) per pair"""
+    from se_b200.discriminator import Discriminator
+    d = Discriminator(ndf=16)
+    keys = set(d.state_dict().keys())
+    for i in (0, 3, 6, 9):
+        assert {f"layers.{i}.weight_orig", f"layers.{i}.weight_u", f"layers.{i}.weight_v"} <= keys
+    assert any(k.endswith(".slope") for k in keys)
+    x = torch.rand(2, 1, 201, 81)
+    y = d(x, x)
+    assert y.shape == (2, 1) and float(y.min()) > 0 and float(y.max()) < 1
