@@ -74,10 +74,11 @@ class MetricLabelPipeline:
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=x.device)
         host = torch.empty(x.shape, dtype=torch.float32, pin_memory=True)
+        snap = x.to(torch.float32, copy=True)      # private device snapshot on the caller's stream (0.5 MB per batch): later in-place writes to x cannot race the copy
         self._copy_stream.wait_stream(torch.cuda.current_stream(x.device))
         with torch.cuda.stream(self._copy_stream):
-            host.copy_(x.to(torch.float32), non_blocking=True)
-            x.record_stream(self._copy_stream)
+            host.copy_(snap, non_blocking=True)
+            snap.record_stream(self._copy_stream)
         return host
 
     def submit(self, clean: torch.Tensor, est: torch.Tensor) -> _Handle:
