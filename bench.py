@@ -459,17 +459,6 @@ def train_config(args, world):
             "l2": "per-step working set ~10 GB of saved activations >> 126 MB L2; no flush needed"}
 
 
-def lsd_score(sr, c, n):
-    """stand-in for pesq(sr, clean, est, 'wb') (absent from the image): log-spectral distance over 32 ms frames mapped onto PESQ's 1 .. 4.5 range"""
-    import numpy as np
-    nf = (len(c) - 512) // 256 + 1
-    idx = np.arange(512)[None, :] + 256 * np.arange(nf)[:, None]
-    w = np.hanning(512).astype(np.float32)
-    C, N = np.abs(np.fft.rfft(c[idx] * w)) ** 2, np.abs(np.fft.rfft(n[idx] * w)) ** 2
-    lsd = float(np.mean(np.sqrt(np.mean((10 * np.log10(C + 1e-8) - 10 * np.log10(N + 1e-8)) ** 2, axis=1))))
-    return 4.5 - 3.5 * min(lsd / 20.0, 1.0)
-
-
 def _gan_step(se_b200, model, disc, opt_g, opt_d, batch, cfg, args_ns, world, mse, timers=None, labels=None):
     """one iteration of train_gan (core/function.py:206-317, arch scp) on the CUDA generator; `timers`: dict of (start, end) event lists"""
     import torch.nn.functional as F
@@ -560,7 +549,8 @@ def run_train(args):
     cfg = types.SimpleNamespace(N_FFT=400, HOP_SAMPLES=100)
     args_ns = types.SimpleNamespace(gpu=local)
 
-    labels = se_b200.MetricLabelPipeline(lsd_score, workers=min(12, max(2, (os.cpu_count() or 4) // max(world, 1))))
+    labels = se_b200.MetricLabelPipeline(se_b200.metric_labels.log_spectral_score, workers=min(12, max(2, (os.cpu_count() or 4) // max(world, 1))), backend="process")
+    labels.warm_up()
 
     def step(timers=None):
         return _gan_step(se_b200, model, disc_run, opt_g, opt_d, host, cfg, args_ns, world, mse, timers, labels)
@@ -622,6 +612,7 @@ def run_train(args):
             except Exception as exc:  # noqa: BLE001
                 line["gpu_eager_baseline"] = {"unavailable": repr(exc)[:200]}
         print(json.dumps(line), flush=True)
+    labels.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -11,6 +11,10 @@ discriminator's 0.21 GFLOP -- are what a real training run waits for.  This modu
 * `MetricLabelPipeline.result(handle)` blocks only for what is still outstanding and returns the label tensor on the requested device;
 * `batch_pesq(clean_list, noisy_list)` is the reference's synchronous call on top of the same pool (drop-in for models/discriminator.py:26-32).
 
+Workers are threads by default; `backend="process"` uses a spawned process pool like the reference's joblib workers (the scorer must then be
+picklable): a numpy scorer in threads competes with the training loop for the GIL while it launches ~1000 kernels per step (measured: +12 ms on a
+78 ms step with threads, +1 ms with processes).  Pinned staging buffers are recycled: a fresh cudaHostAlloc per batch costs milliseconds.
+
 The scorer is a plain callable `score_fn(sr, clean_1d, est_1d) -> float`.  By default it is `pesq.pesq(sr, c, n, 'wb')`; the `pesq` wheel is not part
 of this image, so constructing a pipeline without a scorer raises ImportError there instead of producing made-up labels.
 """
@@ -44,26 +48,48 @@ def _guarded(score_fn: ScoreFn, sr: int, c: np.ndarray, n: np.ndarray) -> float:
 
 
 class _Handle:
-    __slots__ = ("futures", "event", "host", "n")
+    __slots__ = ("futures", "event", "host", "n", "pinned")
 
     def __init__(self):
         self.futures: List[cf.Future] = []
         self.event: Optional[torch.cuda.Event] = None
         self.host = None
         self.n = 0
+        self.pinned: List[torch.Tensor] = []
+
+
+def log_spectral_score(sr: int, c: np.ndarray, n: np.ndarray) -> float:
+    """A stand-in scorer with PESQ's range for machines without the `pesq` wheel (bench.py --config 4): log-spectral distance over 32 ms frames
+    mapped onto 1 .. 4.5.  It is NOT PESQ; it exists so that the pipeline can be exercised and timed end to end."""
+    nf = (len(c) - 512) // 256 + 1
+    if nf < 1 or float(np.abs(c).max()) == 0.0:
+        raise ValueError("silent or too short reference")
+    idx = np.arange(512)[None, :] + 256 * np.arange(nf)[:, None]
+    w = np.hanning(512).astype(np.float32)
+    C, N = np.abs(np.fft.rfft(c[idx] * w)) ** 2, np.abs(np.fft.rfft(n[idx] * w)) ** 2
+    lsd = float(np.mean(np.sqrt(np.mean((10 * np.log10(C + 1e-8) - 10 * np.log10(N + 1e-8)) ** 2, axis=1))))
+    return 4.5 - 3.5 * min(lsd / 20.0, 1.0)
 
 
 class MetricLabelPipeline:
     """Asynchronous `batch_pesq`: submit() right after the generator forward, result() where the discriminator loss needs the labels."""
 
-    def __init__(self, score_fn: Optional[ScoreFn] = None, sr: int = 16000, workers: Optional[int] = None):
+    def __init__(self, score_fn: Optional[ScoreFn] = None, sr: int = 16000, workers: Optional[int] = None, backend: str = "thread"):
         self.score_fn = score_fn if score_fn is not None else _default_score_fn()
         self.sr = int(sr)
         self.workers = int(workers) if workers else max(1, (os.cpu_count() or 2) - 1)
-        # threads, not processes: the PESQ extension and numpy scorers release the GIL in their inner loops, and the waveforms never get pickled
+        if backend not in ("thread", "process"):
+            raise ValueError("metric_labels: backend must be 'thread' or 'process'")
+        self.backend = backend
+        # waiter threads: block on the copy event of a batch (never the training loop), then score in place or hand the pair to a worker process
         self._pool = cf.ThreadPoolExecutor(max_workers=self.workers, thread_name_prefix="seb200-metric")
+        self._procs = None
+        if backend == "process":
+            import multiprocessing as mp
+            self._procs = cf.ProcessPoolExecutor(max_workers=self.workers, mp_context=mp.get_context("spawn"))
         self._copy_stream = None
         self._lock = threading.Lock()
+        self._free = {}                     # shape -> pinned buffers ready for reuse
 
     # ------------------------------------------------------------------------------------------------------------------
     def _stage(self, x: torch.Tensor, h: _Handle) -> torch.Tensor:
@@ -73,7 +99,12 @@ class MetricLabelPipeline:
             return x.to(torch.float32).contiguous()
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=x.device)
-        host = torch.empty(x.shape, dtype=torch.float32, pin_memory=True)
+        with self._lock:
+            free = self._free.get(tuple(x.shape))
+            host = free.pop() if free else None
+        if host is None:
+            host = torch.empty(x.shape, dtype=torch.float32, pin_memory=True)
+        h.pinned.append(host)
         snap = x.to(torch.float32, copy=True)      # private device snapshot on the caller's stream (0.5 MB per batch): later in-place writes to x cannot race the copy
         self._copy_stream.wait_stream(torch.cuda.current_stream(x.device))
         with torch.cuda.stream(self._copy_stream):
@@ -96,7 +127,9 @@ class MetricLabelPipeline:
 
         def job(b: int) -> float:
             if ev is not None:
-                ev.synchronize()               # the copies of this batch have landed (blocks this worker only)
+                ev.synchronize()               # the copies of this batch have landed (blocks this waiter only)
+            if self._procs is not None:
+                return self._procs.submit(_guarded, self.score_fn, self.sr, hc[b].numpy(), he[b].numpy()).result()
             return _guarded(self.score_fn, self.sr, hc[b].numpy(), he[b].numpy())
 
         h.futures = [self._pool.submit(job, b) for b in range(h.n)]
@@ -105,6 +138,11 @@ class MetricLabelPipeline:
     def result(self, h: _Handle, device=None) -> torch.Tensor:
         """labels (score - 1) / 3.5 as float32 [B] (discriminator.py:29-32); a failed pair carries (-1 - 1) / 3.5 like the reference"""
         scores = np.array([f.result() for f in h.futures], dtype=np.float64)
+        if h.pinned:
+            with self._lock:
+                for buf in h.pinned:
+                    self._free.setdefault(tuple(buf.shape), []).append(buf)
+            h.pinned = []
         labels = torch.from_numpy(((scores - 1.0) / 3.5).astype(np.float32))
         return labels.to(device) if device is not None else labels
 
@@ -112,8 +150,17 @@ class MetricLabelPipeline:
         """mask of the pairs whose scorer raised (the reference keeps them; a caller may want to drop the batch)"""
         return np.array([f.result() == -1.0 for f in h.futures])
 
+    def warm_up(self):
+        """start the worker processes (spawn + imports take seconds) before the first timed step"""
+        if self._procs is not None:
+            z = np.zeros(1024, dtype=np.float32)
+            for f in [self._procs.submit(_guarded, self.score_fn, self.sr, z, z) for _ in range(self.workers)]:
+                f.result()
+
     def close(self):
         self._pool.shutdown(wait=True)
+        if self._procs is not None:
+            self._procs.shutdown(wait=True)
 
     def __enter__(self):
         return self

@@ -378,3 +378,17 @@ def test_discriminator_state_dict_and_shapes():
     x = torch.rand(2, 1, 201, 81)
     y = d(x, x)
     assert y.shape == (2, 1) and float(y.min()) > 0 and float(y.max()) < 1
+
+
+def test_metric_label_pipeline_process_backend():
+    """worker processes (spawn) like the reference's joblib pool: same labels as the in-process scorer"""
+    from se_b200 import MetricLabelPipeline
+    from se_b200.metric_labels import log_spectral_score
+    g = torch.Generator().manual_seed(1)
+    clean = torch.randn(3, 8000, generator=g)
+    est = clean + 0.2 * torch.randn(3, 8000, generator=g)
+    with MetricLabelPipeline(log_spectral_score, workers=1, backend="process") as pipe:
+        pipe.warm_up()
+        lab = pipe.result(pipe.submit(clean, est))
+    want = torch.tensor([(log_spectral_score(16000, clean[b].numpy(), est[b].numpy()) - 1) / 3.5 for b in range(3)], dtype=torch.float32)
+    assert torch.allclose(lab, want, atol=1e-6)
