@@ -22,6 +22,7 @@ from __future__ import annotations
 
 import concurrent.futures as cf
 import os
+import queue
 import threading
 from typing import Callable, List, Optional, Sequence
 
@@ -81,15 +82,38 @@ class MetricLabelPipeline:
         if backend not in ("thread", "process"):
             raise ValueError("metric_labels: backend must be 'thread' or 'process'")
         self.backend = backend
-        # waiter threads: block on the copy event of a batch (never the training loop), then score in place or hand the pair to a worker process
-        self._pool = cf.ThreadPoolExecutor(max_workers=self.workers, thread_name_prefix="seb200-metric")
-        self._procs = None
         if backend == "process":
             import multiprocessing as mp
-            self._procs = cf.ProcessPoolExecutor(max_workers=self.workers, mp_context=mp.get_context("spawn"))
+            self._pool = cf.ProcessPoolExecutor(max_workers=self.workers, mp_context=mp.get_context("spawn"))
+        else:
+            self._pool = cf.ThreadPoolExecutor(max_workers=self.workers, thread_name_prefix="seb200-metric")
+        # ONE dispatcher thread sleeps on each batch's copy event (a blocking-sync event: no spinning core, never the training loop) and then hands
+        # the pairs to the pool -- a dozen threads spinning in cudaEventSynchronize took cores from the thread that launches the step's kernels
+        self._q: "queue.Queue" = queue.Queue()
+        self._dispatcher = threading.Thread(target=self._dispatch, name="seb200-metric-dispatch", daemon=True)
+        self._dispatcher.start()
         self._copy_stream = None
         self._lock = threading.Lock()
         self._free = {}                     # shape -> pinned buffers ready for reuse
+        self._label_ring: List[torch.Tensor] = []
+        self._label_next = 0
+
+    def _dispatch(self):
+        while True:
+            item = self._q.get()
+            if item is None:
+                return
+            ev, hc, he, outs = item
+            try:
+                if ev is not None:
+                    ev.synchronize()
+                for b, out in enumerate(outs):
+                    inner = self._pool.submit(_guarded, self.score_fn, self.sr, hc[b].numpy(), he[b].numpy())
+                    inner.add_done_callback(lambda f, out=out: out.set_exception(f.exception()) if f.exception() else out.set_result(f.result()))
+            except Exception as e:  # noqa: BLE001
+                for out in outs:
+                    if not out.done():
+                        out.set_exception(e)
 
     # ------------------------------------------------------------------------------------------------------------------
     def _stage(self, x: torch.Tensor, h: _Handle) -> torch.Tensor:
@@ -121,18 +145,10 @@ class MetricLabelPipeline:
         hc, he = self._stage(clean[:, :length], h), self._stage(est[:, :length], h)
         h.host, h.n = (hc, he), clean.shape[0]
         if clean.is_cuda or est.is_cuda:
-            h.event = torch.cuda.Event()
+            h.event = torch.cuda.Event(blocking=True)
             h.event.record(self._copy_stream)
-        ev = h.event
-
-        def job(b: int) -> float:
-            if ev is not None:
-                ev.synchronize()               # the copies of this batch have landed (blocks this waiter only)
-            if self._procs is not None:
-                return self._procs.submit(_guarded, self.score_fn, self.sr, hc[b].numpy(), he[b].numpy()).result()
-            return _guarded(self.score_fn, self.sr, hc[b].numpy(), he[b].numpy())
-
-        h.futures = [self._pool.submit(job, b) for b in range(h.n)]
+        h.futures = [cf.Future() for _ in range(h.n)]
+        self._q.put((h.event, hc, he, h.futures))
         return h
 
     def result(self, h: _Handle, device=None) -> torch.Tensor:
@@ -144,7 +160,15 @@ class MetricLabelPipeline:
                     self._free.setdefault(tuple(buf.shape), []).append(buf)
             h.pinned = []
         labels = torch.from_numpy(((scores - 1.0) / 3.5).astype(np.float32))
-        return labels.to(device) if device is not None else labels
+        if device is None or torch.device(device).type != "cuda":
+            return labels.to(device) if device is not None else labels
+        # pinned ring + asynchronous copy: a pageable H2D copy would block the host until the stream has drained (three sync points per step)
+        if not self._label_ring or self._label_ring[0].numel() < labels.numel():
+            self._label_ring = [torch.empty(max(labels.numel(), 64), dtype=torch.float32, pin_memory=True) for _ in range(16)]
+        buf = self._label_ring[self._label_next % 16][:labels.numel()]
+        self._label_next += 1
+        buf.copy_(labels)
+        return buf.to(device, non_blocking=True)
 
     def failed(self, h: _Handle) -> np.ndarray:
         """mask of the pairs whose scorer raised (the reference keeps them; a caller may want to drop the batch)"""
@@ -152,15 +176,15 @@ class MetricLabelPipeline:
 
     def warm_up(self):
         """start the worker processes (spawn + imports take seconds) before the first timed step"""
-        if self._procs is not None:
+        if self.backend == "process":
             z = np.zeros(1024, dtype=np.float32)
-            for f in [self._procs.submit(_guarded, self.score_fn, self.sr, z, z) for _ in range(self.workers)]:
+            for f in [self._pool.submit(_guarded, self.score_fn, self.sr, z, z) for _ in range(self.workers)]:
                 f.result()
 
     def close(self):
+        self._q.put(None)
+        self._dispatcher.join()
         self._pool.shutdown(wait=True)
-        if self._procs is not None:
-            self._procs.shutdown(wait=True)
 
     def __enter__(self):
         return self
