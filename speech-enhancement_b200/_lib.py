@@ -13,6 +13,8 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libseb200.so")
+if os.environ.get("SEB200_LIB_SUFFIX"):      # development switch: experiment builds of tools/build_variant_lib.sh
+    _LIB_PATH = os.path.join(_HERE, "libseb200_" + os.environ["SEB200_LIB_SUFFIX"] + ".so")
 
 LOAD_ROWS, LOAD_ROWS_LN, LOAD_CONV, LOAD_HANKEL, LOAD_CONV_SPLIT, LOAD_ROWS2, LOAD_CONV_ADJ, LOAD_ROWS_F16 = 0, 1, 2, 3, 4, 5, 6, 7
 EPI_BIAS, EPI_SWISH, EPI_GLU, EPI_RESID, EPI_SUBPIXEL, EPI_COMPRESS, EPI_QKV_F16, EPI_GATE, EPI_RESID_SCALE, EPI_GLU_F16 = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9

@@ -4,7 +4,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import se_b200
 from se_b200 import ops, _lib
-_lib._LIB_PATH = os.path.join(os.path.dirname(_lib._LIB_PATH), "libseb200_trace.so")
+_lib._LIB_PATH = os.path.join(os.path.dirname(_lib._LIB_PATH), "libseb200_" + os.environ.get("SEB200_LIB_SUFFIX", "trace") + ".so")
 torch.manual_seed(0)
 dev = "cuda"
 B, T, Fh = int(os.environ.get("PROF_B", "64")), int(os.environ.get("PROF_T", "641")), 101
