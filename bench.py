@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--clip-seconds", type=float, default=None)
     ap.add_argument("--engine", default=None, help="tcgen05 (default) | simt")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fixed-labels", action="store_true", help="--config 4: fixed label tensors instead of the metric-label pipeline (A/B of the pipeline's cost)")
     ap.add_argument("--train", action="store_true", help="BASELINE configs[4]: generator + metric discriminator training step (same as --config 4)")
     ap.add_argument("--graphs", action="store_true", help="replay a captured CUDA graph per step (small-batch latency mode)")
     ap.add_argument("--cpu-sample-clips", type=int, default=4, help="clips of the batch the CPU legs time per step (4 x 4 s ~ 8 s of CPU work on 16 cores); "
@@ -454,8 +455,9 @@ def train_config(args, world):
                         f"clips per GPU, gradient all-reduce over {world} GPU(s) (BASELINE configs[4])",
             "batch_per_gpu": args.batch, "clip_seconds": args.clip_seconds, "frames": int(args.clip_seconds * SR) // 100 + 1,
             "parallelism": f"data-parallel x{world} (SyncBatchNorm statistics + one flat 7.34 MB gradient all-reduce; discriminator under DistributedDataParallel)",
-            "generator_engine": args.engine or "tcgen05_f32", "optimizer": "AdamW (fused)", "pesq_labels": "three label batches per step through se_b200.MetricLabelPipeline (side-stream D2H + worker pool, models/discriminator.py:17-32); the scorer is a "
-                           "log-spectral-distance stand-in with PESQ's range because the pesq wheel is not in the image (SURVEY 8d cfg 5)",
+            "generator_engine": args.engine or "tcgen05_f32", "optimizer": "AdamW (fused)", "pesq_labels": ("fixed label tensors (--fixed-labels)" if args.fixed_labels else
+                            "three label batches per step through se_b200.MetricLabelPipeline (side-stream D2H + worker processes, models/discriminator.py:17-32); the scorer is a "
+                            "log-spectral-distance stand-in with PESQ's range because the pesq wheel is not in the image (SURVEY 8d cfg 5)"),
             "l2": "per-step working set ~10 GB of saved activations >> 126 MB L2; no flush needed"}
 
 
@@ -549,8 +551,10 @@ def run_train(args):
     cfg = types.SimpleNamespace(N_FFT=400, HOP_SAMPLES=100)
     args_ns = types.SimpleNamespace(gpu=local)
 
-    labels = se_b200.MetricLabelPipeline(se_b200.metric_labels.log_spectral_score, workers=min(12, max(2, (os.cpu_count() or 4) // max(world, 1))), backend="process")
-    labels.warm_up()
+    labels = None
+    if not args.fixed_labels:
+        labels = se_b200.MetricLabelPipeline(se_b200.metric_labels.log_spectral_score, workers=min(6, max(2, (os.cpu_count() or 4) // (2 * max(world, 1)))), backend="process")
+        labels.warm_up()
 
     def step(timers=None):
         return _gan_step(se_b200, model, disc_run, opt_g, opt_d, host, cfg, args_ns, world, mse, timers, labels)
@@ -612,7 +616,8 @@ def run_train(args):
             except Exception as exc:  # noqa: BLE001
                 line["gpu_eager_baseline"] = {"unavailable": repr(exc)[:200]}
         print(json.dumps(line), flush=True)
-    labels.close()
+    if labels is not None:
+        labels.close()
     if world > 1:
         dist.destroy_process_group()
 
