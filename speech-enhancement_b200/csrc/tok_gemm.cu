@@ -31,6 +31,13 @@ template <int NT, int KCH, int EK, bool AH = false> constexpr int tg_smem_bytes(
   return 1024 + tg_slots<KCH, AH>() * tg_xslot<KCH, AH>() + KCH * 2 * NT * 128 + TG_EPI_WARPS * tg_stg<EK>() + 2 * 64 * 4 + NT * 4;
 }
 
+#ifdef TG_TRACE
+__device__ long long tg_trace[4][24][4];     // [role: row warp 0, MMA issuer, epilogue warp 0, copy warp][tile][event] clock64 stamps of CTA TG_TRACE (debug builds only)
+#define TG_STAMP(role, it, ev) do { if (blockIdx.x == TG_TRACE && (it) < 24 && lane == 0) tg_trace[role][it][ev] = clock64(); } while (0)
+#else
+#define TG_STAMP(role, it, ev) do { } while (0)
+#endif
+
 namespace ptx {
 __device__ __forceinline__ void tg_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -93,7 +100,9 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs 
     for (int it = 0; it < my_tiles; ++it) {
       const int slot = it % NSLOT, s2 = it & 1;
       const uint8_t* xr = sX + slot * XSLOT + row * PITCH;
+      if (warp == 0) TG_STAMP(0, it, 0);
       ptx::mbar_wait(&x_full[slot], (uint32_t)(it / NSLOT) & 1u);
+      if (warp == 0) TG_STAMP(0, it, 1);
       float mean = 0.f, rstd = 1.f;
       if (LK == SEB_LOAD_ROWS_LN) {     // shifted one-pass statistics, four partial sums (short dependency chains)
         float2 ps[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, pq[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
@@ -108,6 +117,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs 
       }
       ptx::mbar_wait(&xa_empty[s2], ((uint32_t)(it >> 1) & 1u) ^ 1u);
       ptx::tc_fence_after();
+      if (warp == 0) TG_STAMP(0, it, 2);
       const uint32_t xa = lane_base + (uint32_t)(s2 * K);
 #pragma unroll
       for (int c16 = 0; c16 < K / 16; ++c16) {          // 16 k-values -> 8 hi + 8 lo packed columns
@@ -143,6 +153,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs 
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       ptx::tc_fence_before();
       ptx::mbar_arrive(&xa_full[s2]);
+      if (warp == 0) TG_STAMP(0, it, 3);
     }
   } else if (warp < TG_W_MMA) {
     // ================= epilogue warps: TMEM -> warp-private smem transpose -> coalesced functor =================
@@ -176,8 +187,11 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs 
           res[i8] = (ch * 4 < CPW && m < g.M) ? *reinterpret_cast<const float4*>(g.resid + (long long)m * g.ldr + n) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
+      if (ew == 0) TG_STAMP(2, it, 0);
       ptx::mbar_wait(&acc_full[ab], use & 1u);
       ptx::tc_fence_after();
+      if (ew == 0) TG_STAMP(2, it, 1);
+      if (ew == 0 && it > 0) TG_STAMP(2, it - 1, 3);
       const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + T_ACC + (uint32_t)(ab * NT + cgi * CPW);
       if (tg_packed<EK>()) {
         // element-wise part in the accumulator's own thread = row layout (bias, GLU / fp16 scaling), THEN the transpose: the
@@ -198,7 +212,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs 
               for (int i = 0; i < 8; ++i) v[j + i] = t8[i];
             }
           }
-          if (c0 + 32 >= CPW) { ptx::tc_fence_before(); ptx::mbar_arrive(&acc_empty[ab]); }     // accumulator fully read
+          if (c0 + 32 >= CPW) { ptx::tc_fence_before(); ptx::mbar_arrive(&acc_empty[ab]); if (ew == 0) TG_STAMP(2, it, 2); }     // accumulator fully read
           const float* rb = nullptr;               // gate: this row's group bias (diffusion-step projection), L1-resident
           if (EK == SEB_EPI_GATE && g.resid) {
             const int mr = m0 + wq * 32 + lane;
@@ -342,9 +356,12 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs 
         const int s2 = it & 1;
         const int ab = ACC2 ? (it & 1) : 0;
         const uint32_t use = ACC2 ? (uint32_t)(it >> 1) : (uint32_t)it;
+        TG_STAMP(1, it, 0);
         ptx::mbar_wait(&xa_full[s2], (uint32_t)(it >> 1) & 1u);
+        TG_STAMP(1, it, 1);
         ptx::mbar_wait(&acc_empty[ab], (use & 1u) ^ 1u);
         ptx::tc_fence_after();
+        TG_STAMP(1, it, 2);
         const uint32_t d_tmem = tmem_base + T_ACC + (uint32_t)(ab * NT);
         const uint32_t a_hi0 = tmem_base + (uint32_t)(s2 * K), a_lo0 = a_hi0 + (uint32_t)(K / 2);
 #pragma unroll
@@ -361,6 +378,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs 
         }
         ptx::tc_commit(&xa_empty[s2]);
         ptx::tc_commit(&acc_full[ab]);
+        TG_STAMP(1, it, 3);
       }
     }
   } else {
@@ -377,7 +395,9 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs 
       for (int it = 0; it < my_tiles; ++it) {
         const int m0 = ((int)blockIdx.x + it * (int)gridDim.x) * BM;
         const int slot = it % NSLOT;
+        TG_STAMP(3, it, 0);
         ptx::mbar_wait(&x_empty[slot], ((uint32_t)(it / NSLOT) & 1u) ^ 1u);
+        TG_STAMP(3, it, 1);
         const uint32_t dst0 = ptx::smem_u32(sX) + slot * XSLOT;
 #pragma unroll 8
         for (int kk = 0; kk < BM * NCH / 32; ++kk) {
@@ -391,6 +411,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs 
                        ::"r"(dst0 + r * PITCH + ((c ^ (r & 7)) << 4)), "l"(src), "r"(m < g.M ? 16u : 0u) : "memory");
         }
         asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(ptx::smem_u32(&x_full[slot])) : "memory");
+        TG_STAMP(3, it, 2);
       }
     }
   }
@@ -400,6 +421,10 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs 
     ptx::tmem_dealloc(tmem_base, 512);
   }
 }
+
+#ifdef TG_TRACE
+extern "C" int seb200_tg_trace(long long* host) { return (int)cudaMemcpyFromSymbol(host, tg_trace, sizeof(tg_trace)); }
+#endif
 
 template <int NT, int KCH, int LK, int EK>
 static int launch_tok(const SebGemm* s, const GemmArgs& g, cudaStream_t st) {
