@@ -159,6 +159,9 @@ __device__ __forceinline__ float ex2f(float x) {
 }
 }  // namespace ptx
 
+#ifdef T6_CTATIME
+__device__ long long t6_cta[65536][3];       // per CTA (debug builds only): clock64 at entry, clock64 at exit, SM id
+#endif
 #ifdef T6_TRACE
 __device__ long long t6_trace[6][16][8];     // [role][tile][event] clock64 stamps of one CTA (debug builds only, tools/build_trace_lib.sh): roles 0..2 = softmax warp 0 of group g, 3 = MMA 1 issuer, 4 = MMA 3 issuer
 #define T6_STAMP(role, t, ev) do { if (blockIdx.x == T6_TRACE && (t) < 16 && lane == 0) t6_trace[role][t][ev] = clock64(); } while (0)
@@ -200,6 +203,9 @@ attention_tc3_kernel(const __half* __restrict__ qkvh, const __half* __restrict__
   extern __shared__ uint8_t t5_smraw[];
   __shared__ uint64_t bar_S[T6_G], bar_F[T6_G], bar_P[T6_G], bar_O[T6_G], bar_RF, full_bar[T6_STAGES], empty_bar[T6_STAGES];
   __shared__ uint32_t tmem_base_s;
+#ifdef T6_CTATIME
+  const long long cta_t0 = clock64();
+#endif
   const uint32_t sm0 = (ptx::smem_u32(t5_smraw) + 127u) & ~127u;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int qb = blockIdx.x % nqb, sh = blockIdx.x / nqb;
@@ -534,8 +540,18 @@ attention_tc3_kernel(const __half* __restrict__ qkvh, const __half* __restrict__
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == T6_W_LOAD) ptx::tmem_dealloc(tmem_base, 512);
+#ifdef T6_CTATIME
+  if (threadIdx.x == 0 && blockIdx.x < 65536) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    t6_cta[blockIdx.x][0] = cta_t0; t6_cta[blockIdx.x][1] = clock64(); t6_cta[blockIdx.x][2] = smid;
+  }
+#endif
 }
 
+#ifdef T6_CTATIME
+extern "C" int seb200_t6_cta(long long* host) { return (int)cudaMemcpyFromSymbol(host, t6_cta, sizeof(t6_cta)); }
+#endif
 #ifdef T6_TRACE
 extern "C" int seb200_t6_trace(long long* host) { return (int)cudaMemcpyFromSymbol(host, t6_trace, sizeof(t6_trace)); }
 #endif
