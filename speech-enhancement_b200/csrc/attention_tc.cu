@@ -163,7 +163,7 @@ __device__ __forceinline__ float ex2f(float x) {
 __device__ long long t6_cta[65536][3];       // per CTA (debug builds only): clock64 at entry, clock64 at exit, SM id
 #endif
 #ifdef T6_TRACE
-__device__ long long t6_trace[6][16][8];     // [role][tile][event] clock64 stamps of one CTA (debug builds only, tools/build_trace_lib.sh): roles 0..2 = softmax warp 0 of group g, 3 = MMA 1 issuer, 4 = MMA 3 issuer
+__device__ long long t6_trace[6][16][8];     // [role][tile][event] clock64 stamps of one CTA (debug builds only): roles 0..2 = softmax warp 0 of group g, 3 = MMA 1 issuer, 4 = MMA 3 issuer, 5 = loader
 #define T6_STAMP(role, t, ev) do { if (blockIdx.x == T6_TRACE && (t) < 16 && lane == 0) t6_trace[role][t][ev] = clock64(); } while (0)
 #else
 #define T6_STAMP(role, t, ev) do { } while (0)
@@ -187,6 +187,9 @@ __device__ __forceinline__ long long t5_seq_base(const SebSeq& sq, int seq) {
 //   TMEM: group g: S 128g | P 128g + 64 | O 128g + 96;  R 384..511 (shared, handed on through the R-free barrier)
 // The strict (tile, group) order of the R users also staggers the three groups by a third of a tile period, so their LSU-,
 // MUFU- and TMEM-bound phases interleave instead of colliding.
+// Fringe key (kfr = 1 when n = 64 k + 1, the model's frame counts): the last key does not get a tile of its own; every thread computes its score on
+// the FMA pipe before the loop (q . k + q . e from rows loaded ahead of the set-up barrier) and starts the online softmax from it: m = score, l = 1,
+// O = v through tcgen05.st, first P . V with accumulate.
 // ------------------------------------------------------------------------------------------------------------------------
 constexpr int T6_G = 3, T6_BQ = T6_G * T5_BQ;
 constexpr int T6_W_LOAD = 4 * T6_G, T6_W_MMA1 = T6_W_LOAD + 1, T6_W_MMA3 = T6_W_LOAD + 2, T6_THREADS = (T6_W_MMA3 + 1) * 32;     // 480
@@ -197,9 +200,11 @@ constexpr int T6_RSCR = T6_STAGE0 + T6_STAGES * T6_STAGE;
 constexpr int T6_SMEM = T6_RSCR + T6_G * 128 * T5_RPITCH + 128;
 constexpr uint32_t T6_TR = 384;
 
+
 template <int WM>
 __global__ void __launch_bounds__(T6_THREADS, 1)
-attention_tc3_kernel(const __half* __restrict__ qkvh, const __half* __restrict__ Eh, const SebSeq sq, int nqb, float* __restrict__ out) {
+attention_tc3_kernel(const __half* __restrict__ qkvh, const __half* __restrict__ Eh, const SebSeq sq, int nqb, int nq, int ntiles, int kfr,
+                     float* __restrict__ out) {
   extern __shared__ uint8_t t5_smraw[];
   __shared__ uint64_t bar_S[T6_G], bar_F[T6_G], bar_P[T6_G], bar_O[T6_G], bar_RF, full_bar[T6_STAGES], empty_bar[T6_STAGES];
   __shared__ uint32_t tmem_base_s;
@@ -212,8 +217,8 @@ attention_tc3_kernel(const __half* __restrict__ qkvh, const __half* __restrict__
   const int hp = sh & 1, seq = sh >> 1;
   const int n = sq.n, i0 = qb * T6_BQ;
   const long long base = t5_seq_base(sq, seq);
-  const int ntiles = (n + T5_KT - 1) / T5_KT;
-  const int ng = min(T6_G, (n - i0 + T5_BQ - 1) / T5_BQ);              // live groups of this CTA
+  const int nt = n - kfr;                                               // keys covered by the tiles; keys nt .. n - 1 are the fringe (see attention_tc_launch)
+  const int ng = min(T6_G, (nq - i0 + T5_BQ - 1) / T5_BQ);              // live groups of this CTA
   const __half* seq0 = qkvh + base * T5_ROWH;
 
   if (tid == 0) {
@@ -246,7 +251,7 @@ attention_tc3_kernel(const __half* __restrict__ qkvh, const __half* __restrict__
       const __half* src0 = kv_lane + (long long)j0 * key_stride_h;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const bool ok = key0 + 8 * k < n;
+        const bool ok = key0 + 8 * k < nt;
         const __half* src = ok ? src0 + (long long)(8 * k) * key_stride_h : seq0;
         ptx::cp16z(st + k_dst + (uint32_t)(k * 512), src, ok ? 16u : 0u);
         ptx::cp16z(st + v_dst + (uint32_t)(k * 128), ok ? src + 64 : seq0, ok ? 16u : 0u);
@@ -270,14 +275,23 @@ attention_tc3_kernel(const __half* __restrict__ qkvh, const __half* __restrict__
 
   const int gi = warp >> 2, q4 = warp & 3;                 // softmax warps: query group, TMEM lane quadrant
   const int i0g = i0 + gi * T5_BQ;
+  uint4 qlo = make_uint4(0u, 0u, 0u, 0u), qhi = qlo;
+  uint4 fk0 = qlo, fk1 = qlo, fv0 = qlo, fv1 = qlo, fe0 = qlo, fe1 = qlo;      // fringe key: its k / v rows and this row's table row, in flight across the set-up barrier
   if (warp < T6_W_LOAD && gi < ng) {
     // ---- operand rows of this thread: Aexp (q in its head's slot) and Q (k order permuted like the fragment-ordered E table)
     const int hl = q4 >> 1, par = q4 & 1, r = tid & 127;
     const int i = i0g + 2 * lane + par;
-    uint4 qlo = make_uint4(0u, 0u, 0u, 0u), qhi = qlo;
-    if (i < n) {
+    if (i < nq) {
       const uint4* qp = reinterpret_cast<const uint4*>(seq0 + (long long)i * key_stride_h + (2 * hp + hl) * T5_D);
       qlo = __ldg(qp); qhi = __ldg(qp + 1);
+    }
+    if (kfr > 0) {
+      const uint4* kp = reinterpret_cast<const uint4*>(seq0 + (long long)nt * key_stride_h + 64 + (2 * hp + hl) * T5_D);
+      fk0 = __ldg(kp); fk1 = __ldg(kp + 1); fv0 = __ldg(kp + 8); fv1 = __ldg(kp + 9);         // v row = k row + 64 halfs
+      int d = i - nt;
+      d = d < -T5_MAXPOS ? -T5_MAXPOS : (d > T5_MAXPOS ? T5_MAXPOS : d);
+      const uint4* ep = reinterpret_cast<const uint4*>(Eh + (d + T5_MAXPOS) * T5_D);
+      fe0 = __ldg(ep); fe1 = __ldg(ep + 1);
     }
     const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
     const uint32_t arow = sm0 + T6_AEXP + (uint32_t)(gi * 8192 + (r >> 3) * 512 + (r & 7) * 16);
@@ -352,7 +366,8 @@ attention_tc3_kernel(const __half* __restrict__ qkvh, const __half* __restrict__
       for (int t = 0; t < ntiles; ++t) {
         const int slot = t % T6_STAGES;
         const uint64_t bv = ptx::umma_desc_ns(sm0 + T6_STAGE0 + (uint32_t)(slot * T6_STAGE) + T6_VS, 128, 1024);
-        const int nks = (n - t * T5_KT <= 16) ? 1 : 4;
+        const int nks = (nt - t * T5_KT <= 16) ? 1 : 4;
+        const uint32_t acc0 = (t > 0 || kfr > 0) ? 1u : 0u;          // with fringe keys the accumulator starts from their contribution
         for (int g = 0; g < ng; ++g) {
           const uint32_t tP = tmem_base + (uint32_t)(128 * g + 64), tO = tmem_base + (uint32_t)(128 * g + 96);
           ptx::mbar_wait_lean<WM>(&bar_P[g], (uint32_t)t & 1u);
@@ -360,7 +375,7 @@ attention_tc3_kernel(const __half* __restrict__ qkvh, const __half* __restrict__
           T6_STAMP(4, t, 2 * g);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
-            if (ks < nks) ptx::mma_f16_ts(tO, tP + (uint32_t)(ks * 8), bv + (uint64_t)((ks * 256) >> 4), IDESC_O, (t | ks) ? 1u : 0u);
+            if (ks < nks) ptx::mma_f16_ts(tO, tP + (uint32_t)(ks * 8), bv + (uint64_t)((ks * 256) >> 4), IDESC_O, ks ? 1u : acc0);
           ptx::tc_commit(&bar_O[g]);
           T6_STAMP(4, t, 2 * g + 1);
         }
@@ -378,21 +393,46 @@ attention_tc3_kernel(const __half* __restrict__ qkvh, const __half* __restrict__
     uint64_t* const bS = &bar_S[gi]; uint64_t* const bF = &bar_F[gi]; uint64_t* const bP = &bar_P[gi]; uint64_t* const bO = &bar_O[gi];
     float m = 0.f, l = 0.f;
     float c_hi = 0.f, c_lo = 0.f;
-    if (n > T5_MAXPOS) {
-      const uint32_t qw = sm0 + T6_QPL + (uint32_t)(gi * 4096 + ((tid & 127) >> 3) * 256 + (tid & 7) * 16);
+    {
+      const uint32_t qperm[8] = {qlo.x, qhi.x, qlo.y, qhi.y, qlo.z, qhi.z, qlo.w, qhi.w};      // k order of the fragment-ordered table rows
+      auto dot_e = [&](const __half* erow) {                  // q . (one row of the packed table), fp32
+        const uint4 e0 = __ldg(reinterpret_cast<const uint4*>(erow)), e1 = __ldg(reinterpret_cast<const uint4*>(erow) + 1);
+        const uint32_t ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+        float acc = 0.f;
 #pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        uint4 qv;
-        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(qv.x), "=r"(qv.y), "=r"(qv.z), "=r"(qv.w) : "r"(qw + ch * 128) : "memory");
-        const uint4 eh = __ldg(reinterpret_cast<const uint4*>(Eh + 2 * T5_MAXPOS * T5_D) + ch), el = __ldg(reinterpret_cast<const uint4*>(Eh) + ch);
-        const uint32_t qq[4] = {qv.x, qv.y, qv.z, qv.w}, hh[4] = {eh.x, eh.y, eh.z, eh.w}, ll[4] = {el.x, el.y, el.z, el.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float2 qf = __half22float2(*reinterpret_cast<const __half2*>(&qq[k]));
-          const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hh[k])), lf = __half22float2(*reinterpret_cast<const __half2*>(&ll[k]));
-          c_hi = fmaf(qf.x, hf.x, fmaf(qf.y, hf.y, c_hi));
-          c_lo = fmaf(qf.x, lf.x, fmaf(qf.y, lf.y, c_lo));
+        for (int k = 0; k < 8; ++k) {
+          const float2 qf = __half22float2(*reinterpret_cast<const __half2*>(&qperm[k])), ef = __half22float2(*reinterpret_cast<const __half2*>(&ee[k]));
+          acc = fmaf(qf.x, ef.x, fmaf(qf.y, ef.y, acc));
         }
+        return acc;
+      };
+      if (n > T5_MAXPOS) {
+        c_hi = dot_e(Eh + 2 * T5_MAXPOS * T5_D);
+        c_lo = dot_e(Eh);
+      }
+      if (kfr > 0) {
+        // ---- fringe key nt = n - 1: the online softmax starts from it (m, l and the O accumulator), computed on the FMA pipe from the rows
+        // loaded before the set-up barrier
+        const uint32_t qnat[8] = {qlo.x, qlo.y, qlo.z, qlo.w, qhi.x, qhi.y, qhi.z, qhi.w};
+        const uint32_t kk[8] = {fk0.x, fk0.y, fk0.z, fk0.w, fk1.x, fk1.y, fk1.z, fk1.w}, vv[8] = {fv0.x, fv0.y, fv0.z, fv0.w, fv1.x, fv1.y, fv1.z, fv1.w};
+        const uint32_t ee[8] = {fe0.x, fe0.y, fe0.z, fe0.w, fe1.x, fe1.y, fe1.z, fe1.w};
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float2 qf = __half22float2(*reinterpret_cast<const __half2*>(&qnat[k])), kf = __half22float2(*reinterpret_cast<const __half2*>(&kk[k]));
+          const float2 qp2 = __half22float2(*reinterpret_cast<const __half2*>(&qperm[k])), ef = __half22float2(*reinterpret_cast<const __half2*>(&ee[k]));
+          acc = fmaf(qf.x, kf.x, fmaf(qf.y, kf.y, fmaf(qp2.x, ef.x, fmaf(qp2.y, ef.y, acc))));
+        }
+        m = acc;                             // the single fringe score is its own maximum: p = 1
+        l = 1.f;
+        uint32_t ow[16];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float2 vf = __half22float2(*reinterpret_cast<const __half2*>(&vv[k]));
+          ow[2 * k] = __float_as_uint(vf.x); ow[2 * k + 1] = __float_as_uint(vf.y);
+        }
+        ptx::tmem_st16(tO + (uint32_t)(hl * 16), ow);
+        ptx::tmem_st_wait5();
       }
     }
     auto tile_body = [&](auto nk_tag, auto far_tag, int t, float cadd) {
@@ -443,7 +483,7 @@ attention_tc3_kernel(const __half* __restrict__ qkvh, const __half* __restrict__
           s[2 * p + 1] = ptx::fhadd((unsigned short)(x[p + 1] & 0xffffu), __uint_as_float(sb[2 * p + 1]));
         }
       }
-      const int rem = n - t * T5_KT;
+      const int rem = nt - t * T5_KT;
       if (rem < NK) {
 #pragma unroll
         for (int jj = 0; jj < NK; ++jj)
@@ -468,7 +508,7 @@ attention_tc3_kernel(const __half* __restrict__ qkvh, const __half* __restrict__
         ptx::tc_fence_after();
       }
       if (q4 == 0) T6_STAMP(gi, t, 5);
-      if (t == 0) {
+      if (t == 0 && kfr == 0) {
         m = mx;
       } else {
         const bool need = mx > m + T5_LAZY;
@@ -505,7 +545,7 @@ attention_tc3_kernel(const __half* __restrict__ qkvh, const __half* __restrict__
       ptx::mbar_arrive(bP);
       if (q4 == 0) T6_STAMP(gi, t, 7);
     };
-    if (i0g + par >= n) {                // every query row of this warp lies past the sequence: keep the protocol, skip the work
+    if (i0g + par >= nq) {               // every query row of this warp lies past the sequence: keep the protocol, skip the work
       for (int t = 0; t < ntiles; ++t) {
         ptx::mbar_wait_lean<WM>(bS, (uint32_t)t & 1u);
         if (t5_far(i0g, t) == 0) ptx::mbar_arrive(&bar_RF);
@@ -516,7 +556,7 @@ attention_tc3_kernel(const __half* __restrict__ qkvh, const __half* __restrict__
     } else {
       for (int t = 0; t < ntiles; ++t) {
         const int far = t5_far(i0g, t);
-        const bool tail = n - t * T5_KT <= 16;
+        const bool tail = nt - t * T5_KT <= 16;
         if (far && tail) tile_body(std::integral_constant<int, 16>{}, std::true_type{}, t, far > 0 ? c_hi : c_lo);
         else if (far) tile_body(std::integral_constant<int, 64>{}, std::true_type{}, t, far > 0 ? c_hi : c_lo);
         else if (tail) tile_body(std::integral_constant<int, 16>{}, std::false_type{}, t, 0.f);
@@ -528,7 +568,7 @@ attention_tc3_kernel(const __half* __restrict__ qkvh, const __half* __restrict__
     uint32_t o[16];
     ptx::tmem_ld16(tO + (uint32_t)(hl * 16), o);
     ptx::tmem_ld_wait();
-    if (i < n) {
+    if (i < nq) {
       const float inv = 1.0f / l;
       float* op = out + (base + (long long)i * sq.pos_stride) * 64 + (2 * hp + hl) * T5_D;
 #pragma unroll
@@ -549,6 +589,7 @@ attention_tc3_kernel(const __half* __restrict__ qkvh, const __half* __restrict__
 #endif
 }
 
+
 #ifdef T6_CTATIME
 extern "C" int seb200_t6_cta(long long* host) { return (int)cudaMemcpyFromSymbol(host, t6_cta, sizeof(t6_cta)); }
 #endif
@@ -563,10 +604,15 @@ int attention_tc_launch(const __half* qkvh, const __half* Eh, const SebSeq* seq,
     if (e != cudaSuccess) { set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     attr_done.set();
   }
-  const int nqb3 = (seq->n + T6_BQ - 1) / T6_BQ;
-  const long long nb3 = (long long)seq->nseq * 2 * nqb3;
-  SEB_REQUIRE(nb3 < 2147483647LL, SEB_EINVAL, "attention: grid too large");
-  attention_tc3_kernel<0><<<(unsigned)nb3, T6_THREADS, T6_SMEM, st>>>(qkvh, Eh, *seq, nqb3, out);
+  const int n = seq->n;
+  // The model's frame counts are 64 k + 1 (T = L / 100 + 1): instead of a last key tile holding ONE key, that key enters the threads' initial
+  // softmax state (m, l, O) on the FMA pipe -- one synchronisation round less per CTA (-2 % at n = 641, profiles/r2/attention_latency_analysis.txt)
+  const int kfr = (n > T5_KT && n % T5_KT == 1) ? 1 : 0;
+  const int ntiles = (n - kfr + T5_KT - 1) / T5_KT;
+  const int nqb = (n + T6_BQ - 1) / T6_BQ;
+  const long long nb = (long long)seq->nseq * 2 * nqb;
+  SEB_REQUIRE(nb < 2147483647LL, SEB_EINVAL, "attention: grid too large");
+  attention_tc3_kernel<0><<<(unsigned)nb, T6_THREADS, T6_SMEM, st>>>(qkvh, Eh, *seq, nqb, n, ntiles, kfr, out);
   SEB_CHECK_LAUNCH("attention_tc3_kernel");
   return 0;
 }

@@ -376,7 +376,7 @@ def _attention_core_ref(qkv_seq, emb):
 
 @pytest.mark.parametrize("variant", [1, 0, 3])     # 3 = the tcgen05 / TMEM kernel (attention_tc.cu)
 @pytest.mark.parametrize("axis,B,T,Fh", [("freq", 2, 5, 101), ("time", 1, 150, 3), ("time", 1, 700, 2), ("freq", 1, 3, 64),
-                                          ("time", 1, 641, 2), ("time", 2, 97, 1), ("time", 1, 3, 2), ("freq", 1, 2, 9), ("time", 1, 40, 1), ("time", 1, 1400, 1)])     # 641 = 10 x 64 + 1: the 16-key tail body, 3-warp CTAs; 1400 > 2*512 + 128: far-field (clamped) tiles take the constant shortcut
+                                          ("time", 1, 641, 2), ("time", 1, 129, 2), ("time", 1, 128, 2), ("time", 1, 1409, 1), ("time", 1, 65, 1), ("time", 2, 97, 1), ("time", 1, 3, 2), ("freq", 1, 2, 9), ("time", 1, 40, 1), ("time", 1, 1400, 1)])     # 641 = 10 x 64 + 1, 129, 65, 1409 (far-field tiles): the last key enters the tcgen05 kernel's initial softmax state; 16-key tail body, 3-warp CTAs (mma.sync kernel); 1400 > 2*512 + 128: far-field (clamped) tiles take the constant shortcut
 def test_attention(variant, axis, B, T, Fh):
     qkv = rnd(B, T, Fh, 192, seed=80, scale=1.5)
     emb = rnd(1025, 16, seed=81)
