@@ -6,13 +6,18 @@
 // These are HBM-bound (2.7 - 4.2 GB per launch for ~0.1 TFLOP); round-1 profiles had them at 34 - 50 % of the HBM peak
 // because at most one tile's loads were in flight per SM (register-staged loaders) and the A operand made a shared-memory
 // round trip.  v3 follows the fused feed-forward kernel:
-//   copy warp     : cp.async 16-byte chunks of the next tiles' raw fp32 rows into a swizzled staging ring (2 - 3 tiles =
-//                   64 - 128 KB in flight per SM, no registers involved); loads the whole weight image once (resident)
+//   copy warp     : the next tiles' raw fp32 rows into a swizzled staging ring (2 - 3 tiles = 64 - 128 KB in flight per SM, no registers
+//                   involved); loads the whole weight image once (resident).  Contiguous 64-float rows (q|k|v, GLU, out-projection) arrive by
+//                   tensor-map TMA: ONE thread issues two cp.async.bulk.tensor (left / right 128-byte halves of 128 rows, SWIZZLE_128B, rows past M
+//                   zero-filled by the hardware) per tile instead of 2048 cp.async with their address arithmetic (12 % of the kernel's
+//                   instructions); the other shapes (K = 128, fp16 rows, two sources) keep the cp.async path
 //   4 row warps   : thread = row.  staged row -> [LayerNorm] -> bf16 hi|lo -> tcgen05.st into XA[s] (tensor memory)
 //   MMA issuer    : ACC[ab] = XA[s] . W^T, A operand from TMEM (`[a_tmem]` form), 3-product split
 //   16 epilogue warps : tcgen05.ld -> warp-private smem transpose -> the engine's epilogue functors, coalesced stores
 #include "gemm_engine.cuh"
+#include <cuda.h>          // CUtensorMap (types only: the encoder comes through cudaGetDriverEntryPoint, libcuda is not linked)
 #include <stdlib.h>
+#include <string.h>
 
 namespace seb {
 
@@ -52,8 +57,11 @@ __device__ __forceinline__ void tg_tmem_st8(uint32_t taddr, const uint32_t* r) {
 }
 }  // namespace ptx
 
-template <int NT, int KCH, int LK, int EK>
-__global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs g, const uint8_t* __restrict__ w_tc) {
+template <int KCH, int LK> constexpr bool tg_tma() { return KCH == 1 && (LK == SEB_LOAD_ROWS || LK == SEB_LOAD_ROWS_LN); }
+
+template <int NT, int KCH, int LK, int EK, bool TMA = false>
+__global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs g, const uint8_t* __restrict__ w_tc, const __grid_constant__ CUtensorMap tmx) {
+  static_assert(!TMA || tg_tma<KCH, LK>(), "the TMA staging path covers contiguous 64-float rows");
   static_assert(NT % 64 == 0 && NT <= 256 && (KCH == 1 || KCH == 2), "unsupported token GEMM shape");
   static_assert(LK == SEB_LOAD_ROWS || LK == SEB_LOAD_ROWS_F16 || (LK == SEB_LOAD_ROWS_LN && KCH == 1) || (LK == SEB_LOAD_ROWS2 && KCH == 2),
                 "loader: plain rows (fp32 or fp16), LayerNorm over 64 features, or two 64-wide sources side by side");
@@ -77,7 +85,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs 
   const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (tid == 0) {
-    for (int i = 0; i < NSLOT; ++i) { ptx::mbar_init(&x_full[i], 32); ptx::mbar_init(&x_empty[i], TG_ROW_WARPS * 32); }
+    for (int i = 0; i < NSLOT; ++i) { ptx::mbar_init(&x_full[i], TMA ? 1 : 32); ptx::mbar_init(&x_empty[i], TG_ROW_WARPS * 32); }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&xa_full[i], TG_ROW_WARPS * 32); ptx::mbar_init(&xa_empty[i], 1);
       ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], TG_EPI_WARPS * 32);
@@ -99,17 +107,19 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs 
     const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
     for (int it = 0; it < my_tiles; ++it) {
       const int slot = it % NSLOT, s2 = it & 1;
-      const uint8_t* xr = sX + slot * XSLOT + row * PITCH;
+      // TMA layout: two [128 rows x 128 B] halves per slot, 16-byte chunk XOR (row & 7) inside each 128-byte row (SWIZZLE_128B)
+      const uint8_t* xr = sX + slot * XSLOT + row * (TMA ? 128 : PITCH);
+      auto chunk = [&](int c) -> const uint8_t* { return TMA ? xr + ((c >> 3) << 14) + (((c & 7) ^ sw) << 4) : xr + ((c ^ sw) << 4); };
       if (warp == 0) TG_STAMP(0, it, 0);
       ptx::mbar_wait(&x_full[slot], (uint32_t)(it / NSLOT) & 1u);
       if (warp == 0) TG_STAMP(0, it, 1);
       float mean = 0.f, rstd = 1.f;
       if (LK == SEB_LOAD_ROWS_LN) {     // shifted one-pass statistics, four partial sums (short dependency chains)
         float2 ps[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, pq[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-        const float x0 = reinterpret_cast<const float4*>(xr + ((0 ^ sw) << 4))->x;
+        const float x0 = reinterpret_cast<const float4*>(chunk(0))->x;
         const float2 nx0 = make_float2(-x0, -x0);
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) stats_acc4(*reinterpret_cast<const float4*>(xr + ((c ^ sw) << 4)), nx0, ps[c & 1], pq[c & 1]);
+        for (int c = 0; c < NCH; ++c) stats_acc4(*reinterpret_cast<const float4*>(chunk(c)), nx0, ps[c & 1], pq[c & 1]);
         const float md = ((ps[0].x + ps[0].y) + (ps[1].x + ps[1].y)) * (1.0f / 64.0f);
         const float var = fmaxf(((pq[0].x + pq[0].y) + (pq[1].x + pq[1].y)) * (1.0f / 64.0f) - md * md, 0.f);
         rstd = 1.0f / sqrtf(var + 1e-5f);
@@ -138,7 +148,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs 
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int c = c16 * 4 + j;
-            const float4 v = *reinterpret_cast<const float4*>(xr + ((c ^ sw) << 4));
+            const float4 v = *reinterpret_cast<const float4*>(chunk(c));
             float2 y01 = make_float2(v.x, v.y), y23 = make_float2(v.z, v.w);
             if (LK == SEB_LOAD_ROWS_LN)
               ln_apply4(v, mean, rstd, *reinterpret_cast<const float4*>(sG + c * 4), *reinterpret_cast<const float4*>(sBt + c * 4), y01, y23);
@@ -392,6 +402,25 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs 
       }
       const float* src0 = g.a[0];
       const float* src1 = (LK == SEB_LOAD_ROWS2) ? g.a[1] : nullptr;
+      if (TMA) {
+        if (lane == 0) {
+          asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmx)) : "memory");
+          for (int it = 0; it < my_tiles; ++it) {
+            const int m0 = ((int)blockIdx.x + it * (int)gridDim.x) * BM;
+            const int slot = it % NSLOT;
+            TG_STAMP(3, it, 0);
+            ptx::mbar_wait(&x_empty[slot], ((uint32_t)(it / NSLOT) & 1u) ^ 1u);
+            TG_STAMP(3, it, 1);
+            const uint32_t dst0 = ptx::smem_u32(sX) + slot * XSLOT, bar = ptx::smem_u32(&x_full[slot]);
+            ptx::mbar_arrive_expect_tx(&x_full[slot], (uint32_t)XSLOT);
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+              asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                           ::"r"(dst0 + (uint32_t)(h << 14)), "l"(reinterpret_cast<uint64_t>(&tmx)), "r"(0), "r"(h), "r"(m0), "r"(bar) : "memory");
+            TG_STAMP(3, it, 2);
+          }
+        }
+      } else
       for (int it = 0; it < my_tiles; ++it) {
         const int m0 = ((int)blockIdx.x + it * (int)gridDim.x) * BM;
         const int slot = it % NSLOT;
@@ -426,14 +455,38 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs 
 extern "C" int seb200_tg_trace(long long* host) { return (int)cudaMemcpyFromSymbol(host, tg_trace, sizeof(tg_trace)); }
 #endif
 
+typedef CUresult (*tg_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tg_encode_fn tg_encoder() {
+  static tg_encode_fn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return reinterpret_cast<tg_encode_fn>(p);
+  }();
+  return fn;
+}
+// x [M, 64] fp32, contiguous rows, as (32 floats, 2 halves of a row, M rows); box = one 128-byte half of 128 rows, SWIZZLE_128B
+static bool tg_make_map(CUtensorMap* tm, const float* x, int M) {
+  tg_encode_fn enc = tg_encoder();
+  if (!enc) return false;
+  const cuuint64_t dims[3] = {32, 2, (cuuint64_t)M};
+  const cuuint64_t strides[2] = {128, 256};
+  const cuuint32_t box[3] = {32, 1, (cuuint32_t)BM}, estr[3] = {1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int NT, int KCH, int LK, int EK>
 static int launch_tok(const SebGemm* s, const GemmArgs& g, cudaStream_t st) {
   static PerDeviceOnce attr_done;
   static int num_sms = 0;
+  static const bool no_tma = getenv("SEB200_TOK_NO_TMA") && atoi(getenv("SEB200_TOK_NO_TMA")) != 0;      // A/B switch
   constexpr int SMEM = tg_smem_bytes<NT, KCH, EK, LK == SEB_LOAD_ROWS_F16>();
   static_assert(SMEM + 256 <= 232448, "token GEMM: shared memory over the 227 KB per-CTA limit");
   if (!attr_done.done()) {
     cudaError_t e = cudaFuncSetAttribute(tok_gemm_kernel<NT, KCH, LK, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (tg_tma<KCH, LK>() && e == cudaSuccess) e = cudaFuncSetAttribute(tok_gemm_kernel<NT, KCH, LK, EK, tg_tma<KCH, LK>()>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) { set_error("tok gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     int dev = 0;
     cudaGetDevice(&dev);
@@ -442,7 +495,14 @@ static int launch_tok(const SebGemm* s, const GemmArgs& g, cudaStream_t st) {
   }
   const long long ntiles = ((long long)s->M + BM - 1) / BM;
   dim3 grid((unsigned)(ntiles < num_sms ? ntiles : num_sms));
-  tok_gemm_kernel<NT, KCH, LK, EK><<<grid, TG_THREADS, SMEM, st>>>(g, reinterpret_cast<const uint8_t*>(s->w_tc));
+  CUtensorMap tm;
+  if (tg_tma<KCH, LK>() && !no_tma && g.lda == 64 && aligned16(g.a[0]) && tg_make_map(&tm, g.a[0], g.M)) {
+    tok_gemm_kernel<NT, KCH, LK, EK, tg_tma<KCH, LK>()><<<grid, TG_THREADS, SMEM, st>>>(g, reinterpret_cast<const uint8_t*>(s->w_tc), tm);
+    SEB_CHECK_LAUNCH("tok_gemm_kernel<tma>");
+    return 0;
+  }
+  memset(&tm, 0, sizeof(tm));
+  tok_gemm_kernel<NT, KCH, LK, EK><<<grid, TG_THREADS, SMEM, st>>>(g, reinterpret_cast<const uint8_t*>(s->w_tc), tm);
   SEB_CHECK_LAUNCH("tok_gemm_kernel");
   return 0;
 }
