@@ -57,7 +57,8 @@ __device__ __forceinline__ void tg_tmem_st8(uint32_t taddr, const uint32_t* r) {
 }
 }  // namespace ptx
 
-template <int KCH, int LK> constexpr bool tg_tma() { return KCH == 1 && (LK == SEB_LOAD_ROWS || LK == SEB_LOAD_ROWS_LN); }
+// rows of 256 bytes: 64 floats (K = 64) or 128 halfs (K = 128, fp16 rows)
+template <int KCH, int LK> constexpr bool tg_tma() { return (KCH == 1 && (LK == SEB_LOAD_ROWS || LK == SEB_LOAD_ROWS_LN)) || (KCH == 2 && LK == SEB_LOAD_ROWS_F16); }
 
 template <int NT, int KCH, int LK, int EK, bool TMA = false>
 __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs g, const uint8_t* __restrict__ w_tc, const __grid_constant__ CUtensorMap tmx) {
@@ -136,7 +137,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tok_gemm_kernel(const GemmArgs 
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
             const int c = c16 * 2 + j;
-            const uint4 h = *reinterpret_cast<const uint4*>(xr + ((c ^ sw) << 4));
+            const uint4 h = *reinterpret_cast<const uint4*>(chunk(c));
             const uint32_t w4[4] = {h.x, h.y, h.z, h.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -496,7 +497,7 @@ static int launch_tok(const SebGemm* s, const GemmArgs& g, cudaStream_t st) {
   const long long ntiles = ((long long)s->M + BM - 1) / BM;
   dim3 grid((unsigned)(ntiles < num_sms ? ntiles : num_sms));
   CUtensorMap tm;
-  if (tg_tma<KCH, LK>() && !no_tma && g.lda == 64 && aligned16(g.a[0]) && tg_make_map(&tm, g.a[0], g.M)) {
+  if (tg_tma<KCH, LK>() && !no_tma && g.lda == (LK == SEB_LOAD_ROWS_F16 ? 128 : 64) && aligned16(g.a[0]) && tg_make_map(&tm, g.a[0], g.M)) {
     tok_gemm_kernel<NT, KCH, LK, EK, tg_tma<KCH, LK>()><<<grid, TG_THREADS, SMEM, st>>>(g, reinterpret_cast<const uint8_t*>(s->w_tc), tm);
     SEB_CHECK_LAUNCH("tok_gemm_kernel<tma>");
     return 0;

@@ -28,6 +28,12 @@ elif which == "out":
     res = torch.randn(M, 64, device=dev)
     run = lambda: ops.gemm(loader=LOAD_ROWS, epilogue=EPI_RESID, M=M, w=w, a=[x], lda=64, resid=res, ldr=64, out=res, ldo=64, engine="tcgen05")
     gb = 3 * 4 * 64 * M / 1e9
+elif which == "pw2":
+    w = packing.pack_weight(torch.randn(64, 128) * 0.12, 64, torch.randn(64) * 0.1).to(dev)
+    xh = torch.randn(M, 128, device=dev).to(torch.float16)
+    res = torch.randn(M, 64, device=dev)
+    run = lambda: ops.gemm(loader=LOAD_ROWS_F16, epilogue=EPI_RESID, M=M, w=w, a=[xh], lda=128, resid=res, ldr=64, out=res, ldo=64, engine="tcgen05")
+    gb = (2 * 128 + 2 * 4 * 64) * M / 1e9
 else:
     raise SystemExit("unknown GEMM")
 for _ in range(3):
