@@ -2,12 +2,13 @@
 called through the C ABI.  Both main loops of the GEMM engine are exercised: `simt` (fp32 FFMA) and `tcgen05`
 (split-bf16 tensor path); the tensor-core attention is checked against the oracle and against the SIMT variant."""
 import math
+import os
 
 import pytest
 import torch
 import torch.nn.functional as F
 
-from conftest import rel_max, rel_l2
+from conftest import ROOT, rel_max, rel_l2
 from oracle import tscnet_oracle as O, weights
 
 import se_b200
@@ -470,3 +471,48 @@ def test_dwconv_bn_swish_fp16_io(axis, B, T, Fh, in_dtype):
     h = F.batch_norm(h, sd[f"{p}.5.running_mean"], sd[f"{p}.5.running_var"], sd[f"{p}.5.weight"], sd[f"{p}.5.bias"], False, 0.0, 1e-5)
     ref = from_seq((h * torch.sigmoid(h)).transpose(1, 2))
     assert rel_max(y.float().cpu(), ref) < 1e-3
+
+
+def test_token_gemm_tma_and_cp_async_staging_are_bit_identical(tmp_path):
+    """the token GEMMs stage contiguous 256-byte rows by tensor-map TMA (default) or by cp.async (SEB200_TOK_NO_TMA=1, read once per process): same
+    arithmetic on the same values, so the two paths must agree bit for bit -- including the hardware zero fill of the rows past M (M = 777, 129)"""
+    import subprocess
+    import sys
+    script = r'''
+import sys, torch
+sys.path.insert(0, %r)
+import se_b200
+from se_b200 import ops, packing
+from se_b200._lib import EPI_GLU, EPI_QKV_F16, EPI_RESID, LOAD_ROWS, LOAD_ROWS_LN, LOAD_ROWS_F16
+torch.manual_seed(3)
+dev = "cuda"
+outs = []
+for M in (777, 129, 4096):
+    x = torch.randn(M, 64, device=dev) * 2 + 0.3
+    g, be = torch.rand(64, device=dev) + 0.5, torch.randn(64, device=dev) * 0.1
+    wq = packing.pack_weight(torch.randn(192, 64) * 0.17, 192, None).to(dev)
+    o1 = torch.empty(M, 192, device=dev, dtype=torch.float16)
+    ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_QKV_F16, M=M, w=wq, a=[x], lda=64, ln=(g, be), out=o1, ldo=192, engine="tcgen05")
+    wi, bi = packing.glu_interleave(torch.randn(256, 64) * 0.17, torch.randn(256) * 0.1)
+    o2 = torch.empty(M, 128, device=dev)
+    ops.gemm(loader=LOAD_ROWS_LN, epilogue=EPI_GLU, M=M, w=packing.pack_weight(wi, 256, bi).to(dev), a=[x], lda=64, ln=(g, be), out=o2, ldo=128, engine="tcgen05")
+    o3 = torch.randn(M, 64, device=dev)
+    ops.gemm(loader=LOAD_ROWS, epilogue=EPI_RESID, M=M, w=packing.pack_weight(torch.randn(64, 64) * 0.17, 64, torch.randn(64) * 0.1).to(dev), a=[x], lda=64,
+             resid=o3, ldr=64, out=o3, ldo=64, engine="tcgen05")
+    v = torch.randn(M, 128, device=dev).to(torch.float16)
+    o4 = torch.randn(M, 64, device=dev)
+    ops.gemm(loader=LOAD_ROWS_F16, epilogue=EPI_RESID, M=M, w=packing.pack_weight(torch.randn(64, 128) * 0.12, 64, torch.randn(64) * 0.1).to(dev), a=[v], lda=128,
+             resid=o4, ldr=64, out=o4, ldo=64, engine="tcgen05")
+    outs += [o1.float().cpu(), o2.cpu(), o3.cpu(), o4.cpu()]
+torch.save(outs, sys.argv[1])
+''' % ROOT
+    files = []
+    for flag in ("0", "1"):
+        f = str(tmp_path / f"tok_{flag}.pt")
+        env = dict(os.environ, SEB200_TOK_NO_TMA=flag)
+        r = subprocess.run([sys.executable, "-c", script, f], env=env, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        files.append(torch.load(f))
+    assert len(files[0]) == 12
+    for a, b in zip(*files):
+        assert torch.isfinite(a).all() and torch.equal(a, b)
