@@ -14,6 +14,7 @@
 // are [Cout, Cin, kt, kf] while K runs (tap, slot, channel)) -- typically straight into the flat gradient buffer the all-reduce sends.
 #include "gemm_engine.cuh"
 #include "mma_tf32.cuh"
+#include <stdlib.h>
 
 namespace seb {
 
@@ -25,33 +26,45 @@ constexpr int WG_LD = 72;            // padded row length (words): the fragment 
 // into (hi, lo) TF32 planes ONCE when they are staged (every element is read by two or four warps), so the main loop is pure LDS + MMA.
 // Every 32-row step accumulates in a fresh tensor-core accumulator that is then added to the running sum with IEEE fp32 adds: the long
 // reduction over 10^4 .. 10^5 rows never sits inside the tensor pipe's accumulator.
-template <int LK>
+// KC = 64-wide K chunks per CTA.  With KC = 2 (every K that is a multiple of 128: the convolutions, the feed-forward's second layer) the staged G rows
+// serve twice the tensor work: half the G loads / splits / stores and half the block barriers per MMA.
+template <int KC> constexpr int wg_smem_bytes() { return (2 + 2 * KC) * WG_ROWS * WG_LD * 4; }
+
+template <int LK, int KC>
 __global__ void __launch_bounds__(256) wgrad_kernel(const GemmArgs g, const float* __restrict__ G, long long ldg, int N, int rows_per_split,
                                                     float* __restrict__ partial, float* __restrict__ partial_b) {
-  __shared__ __align__(16) uint32_t Gh[WG_ROWS][WG_LD], Gl[WG_ROWS][WG_LD], Ah[WG_ROWS][WG_LD], Al[WG_ROWS][WG_LD];
+  extern __shared__ __align__(16) uint32_t wg_sm[];
+  typedef uint32_t (*Plane)[WG_LD];
+  Plane Gh = reinterpret_cast<Plane>(wg_sm), Gl = Gh + WG_ROWS;
+  Plane Ah[KC], Al[KC];
+#pragma unroll
+  for (int j = 0; j < KC; ++j) { Ah[j] = Gl + (1 + 2 * j) * WG_ROWS; Al[j] = Gl + (2 + 2 * j) * WG_ROWS; }
   const int tid = threadIdx.x, sub = tid & 7, rloc = tid >> 3;      // staging: 8 lanes per row, 8 floats each
   const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
-  const int wn = (warp >> 2) * 32, wk = (warp & 3) * 16;            // this warp's 32 x 16 block of the tile
-  const int split = blockIdx.x, kc = blockIdx.y, n0 = blockIdx.z * 64;
+  const int wn = (warp >> 2) * 32, wk = (warp & 3) * 16;            // this warp's 32 x 16 block of every 64 x 64 tile
+  const int split = blockIdx.x, kc = blockIdx.y * KC, n0 = blockIdx.z * 64;
   const int m_lo = split * rows_per_split;
   const int m_hi = min(g.M, m_lo + rows_per_split);
-  float acc[2][2][4];
+  float acc[KC][2][2][4];
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
+  for (int q = 0; q < KC; ++q)
 #pragma unroll
-    for (int j = 0; j < 2; ++j)
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[q][i][j][e] = 0.f;
   float bsum = 0.f;
   const bool want_bias = partial_b != nullptr && kc == 0;
 
   // software pipeline: the global loads of step i + 1 are issued before the MMAs of step i, so their latency hides behind the tensor work
-  float v[8], gv[8];
+  float v[KC][8], gv[8];
   auto fetch = [&](int m0) {
     const int m = m0 + rloc;
     typename Loader<LK>::Row row;
     Loader<LK>::init_row(g, (m0 < m_hi && m < m_hi) ? m : g.M, row);       // rows past the split read as zeros
-    Loader<LK>::load(g, row, kc, sub, v);
+#pragma unroll
+    for (int j = 0; j < KC; ++j) Loader<LK>::load(g, row, kc + j, sub, v[j]);
 #pragma unroll
     for (int i = 0; i < 8; ++i) gv[i] = 0.f;
     if (m0 < m_hi && m < m_hi && n0 + sub * 8 < N) {
@@ -66,11 +79,14 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const GemmArgs g, const floa
     {
       uint32_t h[8], l[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) tf32::split(v[i], h[i], l[i]);
-      *reinterpret_cast<uint4*>(&Ah[rloc][sub * 8]) = make_uint4(h[0], h[1], h[2], h[3]);       // 16-byte stores: conflict-free per quarter warp
-      *reinterpret_cast<uint4*>(&Ah[rloc][sub * 8 + 4]) = make_uint4(h[4], h[5], h[6], h[7]);
-      *reinterpret_cast<uint4*>(&Al[rloc][sub * 8]) = make_uint4(l[0], l[1], l[2], l[3]);
-      *reinterpret_cast<uint4*>(&Al[rloc][sub * 8 + 4]) = make_uint4(l[4], l[5], l[6], l[7]);
+      for (int j = 0; j < KC; ++j) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tf32::split(v[j][i], h[i], l[i]);
+        *reinterpret_cast<uint4*>(&Ah[j][rloc][sub * 8]) = make_uint4(h[0], h[1], h[2], h[3]);       // 16-byte stores: conflict-free per quarter warp
+        *reinterpret_cast<uint4*>(&Ah[j][rloc][sub * 8 + 4]) = make_uint4(h[4], h[5], h[6], h[7]);
+        *reinterpret_cast<uint4*>(&Al[j][rloc][sub * 8]) = make_uint4(l[0], l[1], l[2], l[3]);
+        *reinterpret_cast<uint4*>(&Al[j][rloc][sub * 8 + 4]) = make_uint4(l[4], l[5], l[6], l[7]);
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) tf32::split(gv[i], h[i], l[i]);
       *reinterpret_cast<uint4*>(&Gh[rloc][sub * 8]) = make_uint4(h[0], h[1], h[2], h[3]);
@@ -80,13 +96,15 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const GemmArgs g, const floa
     }
     __syncthreads();
     fetch(m0 + WG_ROWS);                                             // next step's operands (all lanes call it: the LayerNorm loader shuffles)
-    float c[2][2][4];
+    float c[KC][2][2][4];
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
+    for (int q = 0; q < KC; ++q)
 #pragma unroll
-      for (int j = 0; j < 2; ++j)
+      for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) c[i][j][e] = 0.f;
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) c[q][i][j][e] = 0.f;
 #pragma unroll
     for (int ks = 0; ks < WG_ROWS / 8; ++ks) {
       const int r0 = ks * 8 + tq, r1 = r0 + 4;
@@ -98,23 +116,27 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const GemmArgs g, const floa
         al[mt][0] = Gl[r0][c0]; al[mt][1] = Gl[r0][c0 + 8]; al[mt][2] = Gl[r1][c0]; al[mt][3] = Gl[r1][c0 + 8];
       }
 #pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-        const int c0 = wk + nt * 8 + gq;
-        const uint32_t bh[2] = {Ah[r0][c0], Ah[r1][c0]}, bl[2] = {Al[r0][c0], Al[r1][c0]};
+      for (int q = 0; q < KC; ++q)
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          tf32::mma(c[mt][nt], al[mt], bh);
-          tf32::mma(c[mt][nt], ah[mt], bl);
-          tf32::mma(c[mt][nt], ah[mt], bh);
+        for (int nt = 0; nt < 2; ++nt) {
+          const int c0 = wk + nt * 8 + gq;
+          const uint32_t bh[2] = {Ah[q][r0][c0], Ah[q][r1][c0]}, bl[2] = {Al[q][r0][c0], Al[q][r1][c0]};
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            tf32::mma(c[q][mt][nt], al[mt], bh);
+            tf32::mma(c[q][mt][nt], ah[mt], bl);
+            tf32::mma(c[q][mt][nt], ah[mt], bh);
+          }
         }
-      }
     }
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
+    for (int q = 0; q < KC; ++q)
 #pragma unroll
-      for (int j = 0; j < 2; ++j)
+      for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) acc[i][j][e] += c[i][j][e];
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[q][i][j][e] += c[q][i][j][e];
     if (want_bias && tid < 64) {
       float b = 0.f;
 #pragma unroll 8
@@ -124,15 +146,17 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const GemmArgs g, const floa
   }
   const int K = g.K;
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+  for (int q = 0; q < KC; ++q)
 #pragma unroll
-    for (int nt = 0; nt < 2; ++nt)
+    for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-      for (int e = 0; e < 4; e += 2) {
-        const int n = n0 + wn + mt * 16 + gq + ((e >> 1) << 3);
-        const int k = kc * 64 + wk + nt * 8 + tq * 2;
-        if (n < N) *reinterpret_cast<float2*>(partial + ((long long)split * N + n) * K + k) = make_float2(acc[mt][nt][e], acc[mt][nt][e + 1]);
-      }
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; e += 2) {
+          const int n = n0 + wn + mt * 16 + gq + ((e >> 1) << 3);
+          const int k = (kc + q) * 64 + wk + nt * 8 + tq * 2;
+          if (n < N) *reinterpret_cast<float2*>(partial + ((long long)split * N + n) * K + k) = make_float2(acc[q][mt][nt][e], acc[q][mt][nt][e + 1]);
+        }
   if (want_bias && tid < 64 && n0 + tid < N) partial_b[(long long)split * N + n0 + tid] = bsum;
 }
 
@@ -172,10 +196,16 @@ static GemmArgs wg_args(const SebGemm* s) {
 
 using namespace seb;
 
+// SEB200_WGRAD_KC1=1 keeps one K chunk per CTA everywhere (A/B measurements of the two-chunk form)
+static int wg_kc(int K) {
+  static const bool kc1 = getenv("SEB200_WGRAD_KC1") && atoi(getenv("SEB200_WGRAD_KC1")) != 0;
+  return (!kc1 && K % 128 == 0) ? 2 : 1;
+}
+
 // Number of row splits seb200_wgrad uses for (M, N, K): enough CTAs for two waves of 148 SMs, at least 256 rows per split.
 extern "C" int seb200_wgrad_splits(int M, int N, int K) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
-  const int tiles = (K / 64) * ((N + 63) / 64);
+  const int tiles = (K / (64 * wg_kc(K))) * ((N + 63) / 64);      // two K chunks per CTA when K allows (wgrad_kernel<.., 2>)
   int S = (2 * 148 + tiles - 1) / tiles;
   const int maxS = (M + 255) / 256;
   if (S > maxS) S = maxS;
@@ -211,12 +241,26 @@ extern "C" int seb200_wgrad(const SebGemm* a, const float* g_out, long long ldg,
   const GemmArgs g = wg_args(a);
   float* partial = workspace;
   float* partial_b = db ? workspace + (long long)S * N * a->K : nullptr;
-  dim3 grid(S, a->K / 64, N / 64);
+  const int KC = wg_kc(a->K);
+  dim3 grid(S, a->K / (64 * KC), N / 64);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  static PerDeviceOnce attr_done;
+  if (!attr_done.done()) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<SEB_LOAD_ROWS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg_smem_bytes<2>());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_kernel<SEB_LOAD_CONV, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg_smem_bytes<2>());
+    if (e != cudaSuccess) { set_error("wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    attr_done.set();
+  }
   switch (a->loader) {
-    case SEB_LOAD_ROWS:    wgrad_kernel<SEB_LOAD_ROWS><<<grid, 256, 0, st>>>(g, g_out, ldg, N, rows_per_split, partial, partial_b); break;
-    case SEB_LOAD_ROWS_LN: wgrad_kernel<SEB_LOAD_ROWS_LN><<<grid, 256, 0, st>>>(g, g_out, ldg, N, rows_per_split, partial, partial_b); break;
-    case SEB_LOAD_CONV:    wgrad_kernel<SEB_LOAD_CONV><<<grid, 256, 0, st>>>(g, g_out, ldg, N, rows_per_split, partial, partial_b); break;
+    case SEB_LOAD_ROWS:
+      if (KC == 2) wgrad_kernel<SEB_LOAD_ROWS, 2><<<grid, 256, wg_smem_bytes<2>(), st>>>(g, g_out, ldg, N, rows_per_split, partial, partial_b);
+      else wgrad_kernel<SEB_LOAD_ROWS, 1><<<grid, 256, wg_smem_bytes<1>(), st>>>(g, g_out, ldg, N, rows_per_split, partial, partial_b);
+      break;
+    case SEB_LOAD_ROWS_LN: wgrad_kernel<SEB_LOAD_ROWS_LN, 1><<<grid, 256, wg_smem_bytes<1>(), st>>>(g, g_out, ldg, N, rows_per_split, partial, partial_b); break;
+    case SEB_LOAD_CONV:
+      if (KC == 2) wgrad_kernel<SEB_LOAD_CONV, 2><<<grid, 256, wg_smem_bytes<2>(), st>>>(g, g_out, ldg, N, rows_per_split, partial, partial_b);
+      else wgrad_kernel<SEB_LOAD_CONV, 1><<<grid, 256, wg_smem_bytes<1>(), st>>>(g, g_out, ldg, N, rows_per_split, partial, partial_b);
+      break;
     default: set_error("wgrad: loader %d is not supported", a->loader); return SEB_EUNSUPPORTED;
   }
   SEB_CHECK_LAUNCH("wgrad_kernel");
