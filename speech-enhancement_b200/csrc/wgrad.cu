@@ -26,39 +26,48 @@ constexpr int WG_LD = 72;            // padded row length (words): the fragment 
 // into (hi, lo) TF32 planes ONCE when they are staged (every element is read by two or four warps), so the main loop is pure LDS + MMA.
 // Every 32-row step accumulates in a fresh tensor-core accumulator that is then added to the running sum with IEEE fp32 adds: the long
 // reduction over 10^4 .. 10^5 rows never sits inside the tensor pipe's accumulator.
-// KC = 64-wide K chunks per CTA.  With KC = 2 (every K that is a multiple of 128: the convolutions, the feed-forward's second layer) the staged G rows
-// serve twice the tensor work: half the G loads / splits / stores and half the block barriers per MMA.
-template <int KC> constexpr int wg_smem_bytes() { return (2 + 2 * KC) * WG_ROWS * WG_LD * 4; }
+// KC = 64-wide K chunks per CTA, NC = 64-wide n-tiles per CTA.  With KC = 2 (every K that is a multiple of 128: the convolutions, the feed-forward's
+// second layer) the staged G rows serve twice the tensor work: half the G loads / splits / stores and half the block barriers per MMA; with NC = 2
+// (K = 64 and N a multiple of 128: q|k|v, the feed-forward's first layer, the GLU pointwise conv) the same holds for the staged input rows --
+// whose fetch includes the fused LayerNorm.
+template <int KC, int NC> constexpr int wg_smem_bytes() { return (2 * NC + 2 * KC) * WG_ROWS * WG_LD * 4; }
 
-template <int LK, int KC>
+template <int LK, int KC, int NC>
 __global__ void __launch_bounds__(256) wgrad_kernel(const GemmArgs g, const float* __restrict__ G, long long ldg, int N, int rows_per_split,
                                                     float* __restrict__ partial, float* __restrict__ partial_b) {
+  static_assert(KC * NC <= 2, "one operand may be doubled");
   extern __shared__ __align__(16) uint32_t wg_sm[];
   typedef uint32_t (*Plane)[WG_LD];
-  Plane Gh = reinterpret_cast<Plane>(wg_sm), Gl = Gh + WG_ROWS;
-  Plane Ah[KC], Al[KC];
+  Plane Gh[NC], Gl[NC], Ah[KC], Al[KC];
+  {
+    Plane p0 = reinterpret_cast<Plane>(wg_sm);
 #pragma unroll
-  for (int j = 0; j < KC; ++j) { Ah[j] = Gl + (1 + 2 * j) * WG_ROWS; Al[j] = Gl + (2 + 2 * j) * WG_ROWS; }
+    for (int j = 0; j < NC; ++j) { Gh[j] = p0 + (2 * j) * WG_ROWS; Gl[j] = p0 + (2 * j + 1) * WG_ROWS; }
+#pragma unroll
+    for (int j = 0; j < KC; ++j) { Ah[j] = p0 + (2 * NC + 2 * j) * WG_ROWS; Al[j] = p0 + (2 * NC + 2 * j + 1) * WG_ROWS; }
+  }
   const int tid = threadIdx.x, sub = tid & 7, rloc = tid >> 3;      // staging: 8 lanes per row, 8 floats each
   const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
   const int wn = (warp >> 2) * 32, wk = (warp & 3) * 16;            // this warp's 32 x 16 block of every 64 x 64 tile
-  const int split = blockIdx.x, kc = blockIdx.y * KC, n0 = blockIdx.z * 64;
+  const int split = blockIdx.x, kc = blockIdx.y * KC, n0 = blockIdx.z * (64 * NC);
   const int m_lo = split * rows_per_split;
   const int m_hi = min(g.M, m_lo + rows_per_split);
-  float acc[KC][2][2][4];
+  float acc[NC][KC][2][2][4];
 #pragma unroll
-  for (int q = 0; q < KC; ++q)
+  for (int nn = 0; nn < NC; ++nn)
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
+    for (int q = 0; q < KC; ++q)
 #pragma unroll
-      for (int j = 0; j < 2; ++j)
+      for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) acc[q][i][j][e] = 0.f;
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[nn][q][i][j][e] = 0.f;
   float bsum = 0.f;
   const bool want_bias = partial_b != nullptr && kc == 0;
 
   // software pipeline: the global loads of step i + 1 are issued before the MMAs of step i, so their latency hides behind the tensor work
-  float v[KC][8], gv[8];
+  float v[KC][8], gv[NC][8];
   auto fetch = [&](int m0) {
     const int m = m0 + rloc;
     typename Loader<LK>::Row row;
@@ -66,11 +75,14 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const GemmArgs g, const floa
 #pragma unroll
     for (int j = 0; j < KC; ++j) Loader<LK>::load(g, row, kc + j, sub, v[j]);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) gv[i] = 0.f;
-    if (m0 < m_hi && m < m_hi && n0 + sub * 8 < N) {
-      const float* gp = G + (long long)m * ldg + n0 + sub * 8;
-      const float4 g0 = ldg4(gp), g1 = ldg4(gp + 4);
-      gv[0] = g0.x; gv[1] = g0.y; gv[2] = g0.z; gv[3] = g0.w; gv[4] = g1.x; gv[5] = g1.y; gv[6] = g1.z; gv[7] = g1.w;
+    for (int nn = 0; nn < NC; ++nn) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) gv[nn][i] = 0.f;
+      if (m0 < m_hi && m < m_hi && n0 + nn * 64 + sub * 8 < N) {
+        const float* gp = G + (long long)m * ldg + n0 + nn * 64 + sub * 8;
+        const float4 g0 = ldg4(gp), g1 = ldg4(gp + 4);
+        gv[nn][0] = g0.x; gv[nn][1] = g0.y; gv[nn][2] = g0.z; gv[nn][3] = g0.w; gv[nn][4] = g1.x; gv[nn][5] = g1.y; gv[nn][6] = g1.z; gv[nn][7] = g1.w;
+      }
     }
   };
   fetch(m_lo);
@@ -88,33 +100,40 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const GemmArgs g, const floa
         *reinterpret_cast<uint4*>(&Al[j][rloc][sub * 8 + 4]) = make_uint4(l[4], l[5], l[6], l[7]);
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) tf32::split(gv[i], h[i], l[i]);
-      *reinterpret_cast<uint4*>(&Gh[rloc][sub * 8]) = make_uint4(h[0], h[1], h[2], h[3]);
-      *reinterpret_cast<uint4*>(&Gh[rloc][sub * 8 + 4]) = make_uint4(h[4], h[5], h[6], h[7]);
-      *reinterpret_cast<uint4*>(&Gl[rloc][sub * 8]) = make_uint4(l[0], l[1], l[2], l[3]);
-      *reinterpret_cast<uint4*>(&Gl[rloc][sub * 8 + 4]) = make_uint4(l[4], l[5], l[6], l[7]);
+      for (int nn = 0; nn < NC; ++nn) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tf32::split(gv[nn][i], h[i], l[i]);
+        *reinterpret_cast<uint4*>(&Gh[nn][rloc][sub * 8]) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(&Gh[nn][rloc][sub * 8 + 4]) = make_uint4(h[4], h[5], h[6], h[7]);
+        *reinterpret_cast<uint4*>(&Gl[nn][rloc][sub * 8]) = make_uint4(l[0], l[1], l[2], l[3]);
+        *reinterpret_cast<uint4*>(&Gl[nn][rloc][sub * 8 + 4]) = make_uint4(l[4], l[5], l[6], l[7]);
+      }
     }
     __syncthreads();
     fetch(m0 + WG_ROWS);                                             // next step's operands (all lanes call it: the LayerNorm loader shuffles)
-    float c[KC][2][2][4];
+    float c[NC][KC][2][2][4];
 #pragma unroll
-    for (int q = 0; q < KC; ++q)
+    for (int nn = 0; nn < NC; ++nn)
 #pragma unroll
-      for (int i = 0; i < 2; ++i)
+      for (int q = 0; q < KC; ++q)
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
+        for (int i = 0; i < 2; ++i)
 #pragma unroll
-          for (int e = 0; e < 4; ++e) c[q][i][j][e] = 0.f;
+          for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) c[nn][q][i][j][e] = 0.f;
 #pragma unroll
     for (int ks = 0; ks < WG_ROWS / 8; ++ks) {
       const int r0 = ks * 8 + tq, r1 = r0 + 4;
-      uint32_t ah[2][4], al[2][4];
+      uint32_t ah[NC][2][4], al[NC][2][4];
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        const int c0 = wn + mt * 16 + gq;
-        ah[mt][0] = Gh[r0][c0]; ah[mt][1] = Gh[r0][c0 + 8]; ah[mt][2] = Gh[r1][c0]; ah[mt][3] = Gh[r1][c0 + 8];
-        al[mt][0] = Gl[r0][c0]; al[mt][1] = Gl[r0][c0 + 8]; al[mt][2] = Gl[r1][c0]; al[mt][3] = Gl[r1][c0 + 8];
-      }
+      for (int nn = 0; nn < NC; ++nn)
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          const int c0 = wn + mt * 16 + gq;
+          ah[nn][mt][0] = Gh[nn][r0][c0]; ah[nn][mt][1] = Gh[nn][r0][c0 + 8]; ah[nn][mt][2] = Gh[nn][r1][c0]; ah[nn][mt][3] = Gh[nn][r1][c0 + 8];
+          al[nn][mt][0] = Gl[nn][r0][c0]; al[nn][mt][1] = Gl[nn][r0][c0 + 8]; al[nn][mt][2] = Gl[nn][r1][c0]; al[nn][mt][3] = Gl[nn][r1][c0 + 8];
+        }
 #pragma unroll
       for (int q = 0; q < KC; ++q)
 #pragma unroll
@@ -122,42 +141,50 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const GemmArgs g, const floa
           const int c0 = wk + nt * 8 + gq;
           const uint32_t bh[2] = {Ah[q][r0][c0], Ah[q][r1][c0]}, bl[2] = {Al[q][r0][c0], Al[q][r1][c0]};
 #pragma unroll
-          for (int mt = 0; mt < 2; ++mt) {
-            tf32::mma(c[q][mt][nt], al[mt], bh);
-            tf32::mma(c[q][mt][nt], ah[mt], bl);
-            tf32::mma(c[q][mt][nt], ah[mt], bh);
-          }
+          for (int nn = 0; nn < NC; ++nn)
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+              tf32::mma(c[nn][q][mt][nt], al[nn][mt], bh);
+              tf32::mma(c[nn][q][mt][nt], ah[nn][mt], bl);
+              tf32::mma(c[nn][q][mt][nt], ah[nn][mt], bh);
+            }
         }
     }
 #pragma unroll
-    for (int q = 0; q < KC; ++q)
+    for (int nn = 0; nn < NC; ++nn)
 #pragma unroll
-      for (int i = 0; i < 2; ++i)
+      for (int q = 0; q < KC; ++q)
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
+        for (int i = 0; i < 2; ++i)
 #pragma unroll
-          for (int e = 0; e < 4; ++e) acc[q][i][j][e] += c[q][i][j][e];
-    if (want_bias && tid < 64) {
+          for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[nn][q][i][j][e] += c[nn][q][i][j][e];
+    if (want_bias && tid < 64 * NC) {
+      const int col = tid & 63;
+      const Plane gh = (tid >> 6) ? Gh[NC - 1] : Gh[0], gl = (tid >> 6) ? Gl[NC - 1] : Gl[0];      // selects, not a dynamic index into the pointer arrays
       float b = 0.f;
 #pragma unroll 8
-      for (int r = 0; r < WG_ROWS; ++r) b += __uint_as_float(Gh[r][tid]) + __uint_as_float(Gl[r][tid]);
+      for (int r = 0; r < WG_ROWS; ++r) b += __uint_as_float(gh[r][col]) + __uint_as_float(gl[r][col]);
       bsum += b;
     }
   }
   const int K = g.K;
 #pragma unroll
-  for (int q = 0; q < KC; ++q)
+  for (int nn = 0; nn < NC; ++nn)
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int q = 0; q < KC; ++q)
 #pragma unroll
-      for (int nt = 0; nt < 2; ++nt)
+      for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int e = 0; e < 4; e += 2) {
-          const int n = n0 + wn + mt * 16 + gq + ((e >> 1) << 3);
-          const int k = (kc + q) * 64 + wk + nt * 8 + tq * 2;
-          if (n < N) *reinterpret_cast<float2*>(partial + ((long long)split * N + n) * K + k) = make_float2(acc[q][mt][nt][e], acc[q][mt][nt][e + 1]);
-        }
-  if (want_bias && tid < 64 && n0 + tid < N) partial_b[(long long)split * N + n0 + tid] = bsum;
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; e += 2) {
+            const int n = n0 + nn * 64 + wn + mt * 16 + gq + ((e >> 1) << 3);
+            const int k = (kc + q) * 64 + wk + nt * 8 + tq * 2;
+            if (n < N) *reinterpret_cast<float2*>(partial + ((long long)split * N + n) * K + k) = make_float2(acc[nn][q][mt][nt][e], acc[nn][q][mt][nt][e + 1]);
+          }
+  if (want_bias && tid < 64 * NC && n0 + tid < N) partial_b[(long long)split * N + n0 + tid] = bsum;
 }
 
 // dW[n, k] = sum_s partial[s][n][k] -> dw[n * sn + (k / n1) * s0 + (k % n1) * s1] for k < k_logical;  db[n] = sum_s partial_b[s][n]
@@ -201,11 +228,15 @@ static int wg_kc(int K) {
   static const bool kc1 = getenv("SEB200_WGRAD_KC1") && atoi(getenv("SEB200_WGRAD_KC1")) != 0;
   return (!kc1 && K % 128 == 0) ? 2 : 1;
 }
+static int wg_nc(int N, int K) {
+  static const bool kc1 = getenv("SEB200_WGRAD_KC1") && atoi(getenv("SEB200_WGRAD_KC1")) != 0;
+  return (!kc1 && wg_kc(K) == 1 && N % 128 == 0) ? 2 : 1;
+}
 
 // Number of row splits seb200_wgrad uses for (M, N, K): enough CTAs for two waves of 148 SMs, at least 256 rows per split.
 extern "C" int seb200_wgrad_splits(int M, int N, int K) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
-  const int tiles = (K / (64 * wg_kc(K))) * ((N + 63) / 64);      // two K chunks per CTA when K allows (wgrad_kernel<.., 2>)
+  const int tiles = (K / (64 * wg_kc(K))) * (((N + 63) / 64) / wg_nc(N, K));      // two K chunks or two n-tiles per CTA when the shape allows
   int S = (2 * 148 + tiles - 1) / tiles;
   const int maxS = (M + 255) / 256;
   if (S > maxS) S = maxS;
@@ -241,28 +272,33 @@ extern "C" int seb200_wgrad(const SebGemm* a, const float* g_out, long long ldg,
   const GemmArgs g = wg_args(a);
   float* partial = workspace;
   float* partial_b = db ? workspace + (long long)S * N * a->K : nullptr;
-  const int KC = wg_kc(a->K);
-  dim3 grid(S, a->K / (64 * KC), N / 64);
+  const int KC = wg_kc(a->K), NC = wg_nc(N, a->K);
+  dim3 grid(S, a->K / (64 * KC), N / (64 * NC));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   static PerDeviceOnce attr_done;
   if (!attr_done.done()) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<SEB_LOAD_ROWS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg_smem_bytes<2>());
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_kernel<SEB_LOAD_CONV, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg_smem_bytes<2>());
+    cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<SEB_LOAD_ROWS, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg_smem_bytes<2, 1>());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_kernel<SEB_LOAD_CONV, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg_smem_bytes<2, 1>());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_kernel<SEB_LOAD_ROWS, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg_smem_bytes<1, 2>());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_kernel<SEB_LOAD_ROWS_LN, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg_smem_bytes<1, 2>());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_kernel<SEB_LOAD_CONV, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg_smem_bytes<1, 2>());
     if (e != cudaSuccess) { set_error("wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     attr_done.set();
   }
+#define SEB_WG_LAUNCH(LK, KCV, NCV) wgrad_kernel<LK, KCV, NCV><<<grid, 256, wg_smem_bytes<KCV, NCV>(), st>>>(g, g_out, ldg, N, rows_per_split, partial, partial_b)
   switch (a->loader) {
     case SEB_LOAD_ROWS:
-      if (KC == 2) wgrad_kernel<SEB_LOAD_ROWS, 2><<<grid, 256, wg_smem_bytes<2>(), st>>>(g, g_out, ldg, N, rows_per_split, partial, partial_b);
-      else wgrad_kernel<SEB_LOAD_ROWS, 1><<<grid, 256, wg_smem_bytes<1>(), st>>>(g, g_out, ldg, N, rows_per_split, partial, partial_b);
+      if (KC == 2) SEB_WG_LAUNCH(SEB_LOAD_ROWS, 2, 1); else if (NC == 2) SEB_WG_LAUNCH(SEB_LOAD_ROWS, 1, 2); else SEB_WG_LAUNCH(SEB_LOAD_ROWS, 1, 1);
       break;
-    case SEB_LOAD_ROWS_LN: wgrad_kernel<SEB_LOAD_ROWS_LN, 1><<<grid, 256, wg_smem_bytes<1>(), st>>>(g, g_out, ldg, N, rows_per_split, partial, partial_b); break;
+    case SEB_LOAD_ROWS_LN:
+      if (NC == 2) SEB_WG_LAUNCH(SEB_LOAD_ROWS_LN, 1, 2); else SEB_WG_LAUNCH(SEB_LOAD_ROWS_LN, 1, 1);
+      break;
     case SEB_LOAD_CONV:
-      if (KC == 2) wgrad_kernel<SEB_LOAD_CONV, 2><<<grid, 256, wg_smem_bytes<2>(), st>>>(g, g_out, ldg, N, rows_per_split, partial, partial_b);
-      else wgrad_kernel<SEB_LOAD_CONV, 1><<<grid, 256, wg_smem_bytes<1>(), st>>>(g, g_out, ldg, N, rows_per_split, partial, partial_b);
+      if (KC == 2) SEB_WG_LAUNCH(SEB_LOAD_CONV, 2, 1); else if (NC == 2) SEB_WG_LAUNCH(SEB_LOAD_CONV, 1, 2); else SEB_WG_LAUNCH(SEB_LOAD_CONV, 1, 1);
       break;
     default: set_error("wgrad: loader %d is not supported", a->loader); return SEB_EUNSUPPORTED;
   }
+#undef SEB_WG_LAUNCH
   SEB_CHECK_LAUNCH("wgrad_kernel");
   const long long total = (long long)N * a->K + (db ? N : 0);
   wgrad_finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, partial_b, S, N, a->K, k_logical, n1, sn, s0, s1, dw, db);
