@@ -282,14 +282,17 @@ __global__ void __launch_bounds__(256) attention_de_finish_kernel(const float* _
 // ------------------------------------------------------------------------------------------------------------------------------------
 // backward, key-major: dK, dV (into dqkv[:, 64:192])
 // ------------------------------------------------------------------------------------------------------------------------------------
-constexpr int TAK_SMEM = (4 * TA_B * TA_LD + 128 * TA_LD + TA_B * TA_RLD + TA_B * TA_PLD + 2 * TA_B) * 4;
+// The E window shares the memory of the transposed P / dS tile: it is dead once every warp has its R rows (second block barrier of a tile) and Ts is
+// first written after that barrier; 72 KB instead of 82 KB lets three CTAs (12 warps) share an SM instead of two.
+constexpr int TAK_SMEM = (4 * TA_B * TA_LD + TA_B * TA_RLD + TA_B * TA_PLD + 2 * TA_B) * 4;
+static_assert(TA_B * TA_PLD >= 128 * TA_LD, "the E window must fit inside the transposed tile");
 
 __global__ void __launch_bounds__(128) attention_bwd_k_kernel(const float* __restrict__ qkv, const float* __restrict__ E, const SebSeq sq, int nkt,
                                                              const float* __restrict__ lse, const float* __restrict__ Dg, const float* __restrict__ d_o,
                                                              float* __restrict__ dqkv) {
   extern __shared__ __align__(16) float ta_sm[];
-  float* Qs = ta_sm; float* dOs = Qs + TA_B * TA_LD; float* Ks = dOs + TA_B * TA_LD; float* Vs = Ks + TA_B * TA_LD; float* Es = Vs + TA_B * TA_LD;
-  float* Rs = Es + 128 * TA_LD; float* Ts = Rs + TA_B * TA_RLD; float* Ls = Ts + TA_B * TA_PLD; float* Ds = Ls + TA_B;
+  float* Qs = ta_sm; float* dOs = Qs + TA_B * TA_LD; float* Ks = dOs + TA_B * TA_LD; float* Vs = Ks + TA_B * TA_LD;
+  float* Rs = Vs + TA_B * TA_LD; float* Ts = Rs + TA_B * TA_RLD; float* Es = Ts; float* Ls = Ts + TA_B * TA_PLD; float* Ds = Ls + TA_B;
   const int warp = threadIdx.x >> 5;
   const int kt = blockIdx.x % nkt, sh = blockIdx.x / nkt, h = sh & 3, seq = sh >> 2;
   const int n = sq.n, j0 = kt * TA_B;
