@@ -14,7 +14,7 @@ emb = torch.randn(1025, 16, device=dev); emb_h = ops.pack_rel_pos(emb)
 seq = ops.make_seq(B * Fh, T, Fh, T * Fh, Fh)
 out = torch.zeros(M, 64, device=dev)
 for _ in range(3):
-    ops.attention(inp_h, emb, seq, out, 3, emb_h)
+    ops.attention(inp_h, emb, seq, out, int(os.environ.get("TRACE_VARIANT", "3")), emb_h)
 torch.cuda.synchronize()
 buf = (C.c_longlong * (6 * 16 * 8))()
 lib = _lib.load()
@@ -27,6 +27,8 @@ for g in range(3):
     print(f"softmax group {g} warp 0 (clk since start): tile: wantS gotS R_read S_read max gotO exp_done P_arrive")
     for t in range(nt):
         print(" ", t, [int(v) - t0 if int(v) else -1 for v in tr[g, t]])
+    d = [[int(tr[g, t, e + 1]) - int(tr[g, t, e]) for e in range(7)] + [int(tr[g, t + 1, 0]) - int(tr[g, t, 0])] for t in range(2, nt - 2)]
+    print("  mean phase lengths over the inner tiles (7 phases, tile period):", [sum(c) // len(c) for c in zip(*d)])
 print("MMA 1 issuer: tile: [ready(g) committed(g)] x 3, full_bar")
 for t in range(nt):
     print(" ", t, [int(v) - t0 if int(v) else -1 for v in tr[3, t, :7]])
