@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--clip-seconds", type=float, default=None)
     ap.add_argument("--engine", default=None, help="tcgen05 (default) | simt")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--disc-ddp", action="store_true", help="--config 4, N > 1: keep the metric discriminator under torch's DistributedDataParallel (main_gan.py:168-171) instead of one "
+                    "flat all-reduce of its 0.73 MB of gradients after its own backward (A/B of the wrapper's cost: buffer broadcasts + bucket hooks on four forward calls per step)")
     ap.add_argument("--fixed-labels", action="store_true", help="--config 4: fixed label tensors instead of the metric-label pipeline (A/B of the pipeline's cost)")
     ap.add_argument("--train", action="store_true", help="BASELINE configs[4]: generator + metric discriminator training step (same as --config 4)")
     ap.add_argument("--graphs", action="store_true", help="replay a captured CUDA graph per step (small-batch latency mode)")
@@ -454,14 +456,15 @@ def train_config(args, world):
     return {"workload": f"GAN training step (generator + metric discriminator fwd/bwd, arch scp: consistency-preserving losses), {args.batch} x {args.clip_seconds:g} s "
                         f"clips per GPU, gradient all-reduce over {world} GPU(s) (BASELINE configs[4])",
             "batch_per_gpu": args.batch, "clip_seconds": args.clip_seconds, "frames": int(args.clip_seconds * SR) // 100 + 1,
-            "parallelism": f"data-parallel x{world} (SyncBatchNorm statistics + one flat 7.34 MB gradient all-reduce; discriminator under DistributedDataParallel)",
+            "parallelism": f"data-parallel x{world} (SyncBatchNorm statistics + one flat 7.34 MB gradient all-reduce; discriminator: " +
+                           ("DistributedDataParallel)" if args.disc_ddp else "one coalesced 0.73 MB gradient all-reduce after its backward)"),
             "generator_engine": args.engine or "tcgen05_f32", "optimizer": "AdamW (fused)", "pesq_labels": ("fixed label tensors (--fixed-labels)" if args.fixed_labels else
                             "three label batches per step through se_b200.MetricLabelPipeline (side-stream D2H + worker processes, models/discriminator.py:17-32); the scorer is a "
                             "log-spectral-distance stand-in with PESQ's range because the pesq wheel is not in the image (SURVEY 8d cfg 5)"),
             "l2": "per-step working set ~10 GB of saved activations >> 126 MB L2; no flush needed"}
 
 
-def _gan_step(se_b200, model, disc, opt_g, opt_d, batch, cfg, args_ns, world, mse, timers=None, labels=None):
+def _gan_step(se_b200, model, disc, opt_g, opt_d, batch, cfg, args_ns, world, mse, timers=None, labels=None, disc_sync=None):
     """one iteration of train_gan (core/function.py:206-317, arch scp) on the CUDA generator; `timers`: dict of (start, end) event lists"""
     import torch.nn.functional as F
 
@@ -511,6 +514,8 @@ def _gan_step(se_b200, model, disc, opt_g, opt_d, batch, cfg, args_ns, world, ms
     d_loss = mse(disc(clean_mag, est_mag.detach()).flatten(), q_e) + mse(disc(clean_mag, clean_mag).flatten(), q_c) + \
         mse(disc(clean_mag, noisy_spec.abs().unsqueeze(1)).flatten(), q_n)
     d_loss.backward()
+    if disc_sync is not None:                      # data-parallel exchange of the discriminator step: one coalesced all-reduce (mean) of its gradients
+        se_b200.allreduce_gradients(disc_sync)
     opt_d.step()
     tick("disc")
     return loss.detach(), d_loss.detach()
@@ -541,7 +546,8 @@ def run_train(args):
     st = se_b200.training._state(model)
     if args.engine:
         st.engine = args.engine
-    disc_run = nn.parallel.DistributedDataParallel(disc, device_ids=[local]) if world > 1 else disc
+    disc_run = nn.parallel.DistributedDataParallel(disc, device_ids=[local]) if (world > 1 and args.disc_ddp) else disc
+    disc_sync = disc if (world > 1 and not args.disc_ddp) else None     # identical replicas (same seed, same updates): no buffer broadcast needed
     opt_g = torch.optim.AdamW(model.parameters(), lr=5e-4, fused=True)
     opt_d = torch.optim.AdamW(disc.parameters(), lr=1e-3, fused=True)
     mse = nn.MSELoss()
@@ -557,7 +563,7 @@ def run_train(args):
         labels.warm_up()
 
     def step(timers=None):
-        return _gan_step(se_b200, model, disc_run, opt_g, opt_d, host, cfg, args_ns, world, mse, timers, labels)
+        return _gan_step(se_b200, model, disc_run, opt_g, opt_d, host, cfg, args_ns, world, mse, timers, labels, disc_sync)
 
     def barrier():
         torch.cuda.synchronize()
@@ -588,6 +594,12 @@ def run_train(args):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     clocks = sampler.stop() if rank == 0 else None
+    spread = None
+    if world > 1:                                   # the replicas must still be identical: largest difference of a parameter checksum across ranks (generator, discriminator)
+        cs = torch.stack([sum(p.detach().double().abs().sum() for p in m.parameters()) for m in (model, disc)])
+        both = torch.cat([cs, -cs])
+        dist.all_reduce(both, op=dist.ReduceOp.MAX)
+        spread = [float((both[i] + both[i + 2]) / both[i].abs().clamp_min(1e-30)) for i in range(2)]
     if rank == 0:
         ms = float(ms[0])
         audio_s = world * B * args.clip_seconds * args.steps
@@ -606,7 +618,9 @@ def run_train(args):
                 "gpu_launches": int(launches),
                 "phases_ms": {k: round(v, 3) for k, v in phases.items()},
                 "collective": {"gradient_allreduce_bytes": 1834833 * 4, "allreduce_ms": round(phases["allreduce"], 3),
-                               "syncbn_allreduces_per_step": 16 if world > 1 else 0, "limiting": "latency (7.34 MB + 16 x 2 KB): NCCL launch + NVLS one-shot"},
+                               "syncbn_allreduces_per_step": 16 if world > 1 else 0, "limiting": "latency (7.34 MB + 16 x 2 KB): NCCL launch + NVLS one-shot",
+                               "discriminator": "DistributedDataParallel" if (world > 1 and args.disc_ddp) else ("one coalesced all-reduce" if world > 1 else None),
+                               "replica_checksum_spread_rel": spread},
                 "roofline": {"kernel": "generator backward (all kernels)", "bound": "tensor", "achieved": bwd_tf, "peak": pk["tflops"], "unit": "TFLOP/s",
                              "frac": bwd_tf / pk["tflops"], "traffic": None, "peak_source": pk["src"], "ms": phases["gen_bwd"]},
                 "losses": {"generator": float(g_loss), "discriminator": float(d_loss)}}
