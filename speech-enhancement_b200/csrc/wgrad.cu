@@ -30,7 +30,10 @@ constexpr int WG_LD = 72;            // padded row length (words): the fragment 
 // second layer) the staged G rows serve twice the tensor work: half the G loads / splits / stores and half the block barriers per MMA; with NC = 2
 // (K = 64 and N a multiple of 128: q|k|v, the feed-forward's first layer, the GLU pointwise conv) the same holds for the staged input rows --
 // whose fetch includes the fused LayerNorm.
-template <int KC, int NC> constexpr int wg_smem_bytes() { return (2 * NC + 2 * KC) * WG_ROWS * WG_LD * 4; }
+// Two staging sets: the (hi, lo) planes of step i + 1 are written while the MMAs of step i read the other set -- one block barrier per step and the
+// split / store work overlaps the tensor work of the CTA's other warps (one set: two barriers per step, tensor pipe 30 - 36 % busy, profiles/r2/ncu_full_wgrad.txt).
+template <int KC, int NC> constexpr int wg_stage_rows() { return (2 * NC + 2 * KC) * WG_ROWS; }
+template <int KC, int NC> constexpr int wg_smem_bytes() { return 2 * wg_stage_rows<KC, NC>() * WG_LD * 4; }
 
 template <int LK, int KC, int NC>
 __global__ void __launch_bounds__(256) wgrad_kernel(const GemmArgs g, const float* __restrict__ G, long long ldg, int N, int rows_per_split,
@@ -85,32 +88,34 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const GemmArgs g, const floa
       }
     }
   };
-  fetch(m_lo);
-  for (int m0 = m_lo; m0 < m_hi; m0 += WG_ROWS) {
-    __syncthreads();                                                 // previous step's reads are done
-    {
-      uint32_t h[8], l[8];
+  constexpr int STG = wg_stage_rows<KC, NC>();
+  auto store_stage = [&](int so) {                                   // split the fetched rows into (hi, lo) TF32 planes of the staging set at row offset so
+    uint32_t h[8], l[8];
 #pragma unroll
-      for (int j = 0; j < KC; ++j) {
+    for (int j = 0; j < KC; ++j) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) tf32::split(v[j][i], h[i], l[i]);
-        *reinterpret_cast<uint4*>(&Ah[j][rloc][sub * 8]) = make_uint4(h[0], h[1], h[2], h[3]);       // 16-byte stores: conflict-free per quarter warp
-        *reinterpret_cast<uint4*>(&Ah[j][rloc][sub * 8 + 4]) = make_uint4(h[4], h[5], h[6], h[7]);
-        *reinterpret_cast<uint4*>(&Al[j][rloc][sub * 8]) = make_uint4(l[0], l[1], l[2], l[3]);
-        *reinterpret_cast<uint4*>(&Al[j][rloc][sub * 8 + 4]) = make_uint4(l[4], l[5], l[6], l[7]);
-      }
-#pragma unroll
-      for (int nn = 0; nn < NC; ++nn) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) tf32::split(gv[nn][i], h[i], l[i]);
-        *reinterpret_cast<uint4*>(&Gh[nn][rloc][sub * 8]) = make_uint4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<uint4*>(&Gh[nn][rloc][sub * 8 + 4]) = make_uint4(h[4], h[5], h[6], h[7]);
-        *reinterpret_cast<uint4*>(&Gl[nn][rloc][sub * 8]) = make_uint4(l[0], l[1], l[2], l[3]);
-        *reinterpret_cast<uint4*>(&Gl[nn][rloc][sub * 8 + 4]) = make_uint4(l[4], l[5], l[6], l[7]);
-      }
+      for (int i = 0; i < 8; ++i) tf32::split(v[j][i], h[i], l[i]);
+      *reinterpret_cast<uint4*>(&Ah[j][so + rloc][sub * 8]) = make_uint4(h[0], h[1], h[2], h[3]);       // 16-byte stores: conflict-free per quarter warp
+      *reinterpret_cast<uint4*>(&Ah[j][so + rloc][sub * 8 + 4]) = make_uint4(h[4], h[5], h[6], h[7]);
+      *reinterpret_cast<uint4*>(&Al[j][so + rloc][sub * 8]) = make_uint4(l[0], l[1], l[2], l[3]);
+      *reinterpret_cast<uint4*>(&Al[j][so + rloc][sub * 8 + 4]) = make_uint4(l[4], l[5], l[6], l[7]);
     }
-    __syncthreads();
-    fetch(m0 + WG_ROWS);                                             // next step's operands (all lanes call it: the LayerNorm loader shuffles)
+#pragma unroll
+    for (int nn = 0; nn < NC; ++nn) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) tf32::split(gv[nn][i], h[i], l[i]);
+      *reinterpret_cast<uint4*>(&Gh[nn][so + rloc][sub * 8]) = make_uint4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<uint4*>(&Gh[nn][so + rloc][sub * 8 + 4]) = make_uint4(h[4], h[5], h[6], h[7]);
+      *reinterpret_cast<uint4*>(&Gl[nn][so + rloc][sub * 8]) = make_uint4(l[0], l[1], l[2], l[3]);
+      *reinterpret_cast<uint4*>(&Gl[nn][so + rloc][sub * 8 + 4]) = make_uint4(l[4], l[5], l[6], l[7]);
+    }
+  };
+  fetch(m_lo);
+  store_stage(0);
+  __syncthreads();
+  int so = 0;                                                        // row offset of the staging set the MMAs of this step read
+  for (int m0 = m_lo; m0 < m_hi; m0 += WG_ROWS, so ^= STG) {
+    fetch(m0 + WG_ROWS);                                             // next step's operands (all lanes call it: the LayerNorm loader shuffles); in flight across the MMAs
     float c[NC][KC][2][2][4];
 #pragma unroll
     for (int nn = 0; nn < NC; ++nn)
@@ -124,7 +129,7 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const GemmArgs g, const floa
             for (int e = 0; e < 4; ++e) c[nn][q][i][j][e] = 0.f;
 #pragma unroll
     for (int ks = 0; ks < WG_ROWS / 8; ++ks) {
-      const int r0 = ks * 8 + tq, r1 = r0 + 4;
+      const int r0 = so + ks * 8 + tq, r1 = r0 + 4;
       uint32_t ah[NC][2][4], al[NC][2][4];
 #pragma unroll
       for (int nn = 0; nn < NC; ++nn)
@@ -165,9 +170,11 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const GemmArgs g, const floa
       const Plane gh = (tid >> 6) ? Gh[NC - 1] : Gh[0], gl = (tid >> 6) ? Gl[NC - 1] : Gl[0];      // selects, not a dynamic index into the pointer arrays
       float b = 0.f;
 #pragma unroll 8
-      for (int r = 0; r < WG_ROWS; ++r) b += __uint_as_float(gh[r][col]) + __uint_as_float(gl[r][col]);
+      for (int r = 0; r < WG_ROWS; ++r) b += __uint_as_float(gh[so + r][col]) + __uint_as_float(gl[so + r][col]);
       bsum += b;
     }
+    store_stage(so ^ STG);                                           // the other set: its readers finished before the previous barrier
+    __syncthreads();
   }
   const int K = g.K;
 #pragma unroll
@@ -282,6 +289,9 @@ extern "C" int seb200_wgrad(const SebGemm* a, const float* g_out, long long ldg,
     if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_kernel<SEB_LOAD_ROWS, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg_smem_bytes<1, 2>());
     if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_kernel<SEB_LOAD_ROWS_LN, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg_smem_bytes<1, 2>());
     if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_kernel<SEB_LOAD_CONV, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg_smem_bytes<1, 2>());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_kernel<SEB_LOAD_ROWS, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg_smem_bytes<1, 1>());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_kernel<SEB_LOAD_ROWS_LN, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg_smem_bytes<1, 1>());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_kernel<SEB_LOAD_CONV, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg_smem_bytes<1, 1>());
     if (e != cudaSuccess) { set_error("wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     attr_done.set();
   }
