@@ -14,6 +14,7 @@
 //   * key-major    (CTA = 64 keys, loops over query tiles):   dK and dV from the transposed tile S^T = K Q^T (+ the same R tile).
 // qkv is the fp32 projection [tokens, 192] = (q | k | v), heads 4 x 16; token addressing through SebSeq like every conformer kernel.
 #include "mma_tf32.cuh"
+#include <type_traits>
 
 namespace seb {
 
@@ -48,16 +49,22 @@ __device__ __forceinline__ void ta_load_window(float* Es, const float* E, int db
 // R rows of this warp: Rs[16 warp + r][w] = q_r . E_win[w] for the window columns its 16 queries can address: a query row il reads
 // columns il - jl + 63 in [il, il + 63], so the warp needs w in [16 warp, 16 warp + 79] -- 10 of the 16 n-tiles
 constexpr int TA_BAND = 80;
-__device__ __forceinline__ void ta_rel_rows(const float* Qs, const float* Es, float* Rs, int warp) {
+// FR: the key tile has only nl < 64 live keys (local j < nl), so a row reads columns il - jl + 63 >= il + 64 - nl: band n-tiles below nt_first = (64 - nl) / 8 are never read
+template <bool FR>
+__device__ __forceinline__ void ta_rel_rows(const float* Qs, const float* Es, float* Rs, int warp, int nt_first) {
   float acc[1][10][4];
   tf32::zero(acc);
-  tf32::warp_gemm<1, 10>(acc, 2, [&](int r, int k) { return Qs[(warp * 16 + r) * TA_LD + k]; },
-                         [&](int k, int c) { return Es[(warp * 16 + c) * TA_LD + k]; });
+  tf32::warp_gemm_fr<FR, 1, 10>(acc, 2, 0, 2, nt_first, 10, [&](int r, int k) { return Qs[(warp * 16 + r) * TA_LD + k]; },
+                                [&](int k, int c) { return Es[(warp * 16 + c) * TA_LD + k]; });
 #pragma unroll
   for (int nt = 0; nt < 10; ++nt)
+    if (!FR || nt >= nt_first) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) Rs[(warp * 16 + tf32::c_row(0, e)) * TA_RLD + warp * 16 + tf32::c_col(nt, e)] = acc[0][nt][e];
+      for (int e = 0; e < 4; ++e) Rs[(warp * 16 + tf32::c_row(0, e)) * TA_RLD + warp * 16 + tf32::c_col(nt, e)] = acc[0][nt][e];
+    }
 }
+// live keys / rows of the 64-wide tile at t0 and the n-tile counts that go with them
+__device__ __forceinline__ int ta_live(int n, int t0) { return n - t0 < TA_B ? n - t0 : TA_B; }
 
 // ------------------------------------------------------------------------------------------------------------------------------------
 // forward: out [tokens, 64], lse [tokens, 4]
@@ -77,27 +84,28 @@ __global__ void __launch_bounds__(128) attention_train_fwd_kernel(const float* _
   float m[2] = {TA_NEG, TA_NEG}, l[2] = {0.f, 0.f};
   float o[1][2][4];
   tf32::zero(o);
-  for (int j0 = 0; j0 < n; j0 += TA_B) {
-    __syncthreads();
-    ta_load_tile(Ks, qkv, base, sq.pos_stride, TA_ROW, 64 + h * TA_D, j0, n);
-    ta_load_tile(Vs, qkv, base, sq.pos_stride, TA_ROW, 128 + h * TA_D, j0, n);
-    ta_load_window(Es, E, i0 - j0 - 63);
-    __syncthreads();
-    ta_rel_rows(Qs, Es, Rs, warp);
+  const bool warp_live = i0 + warp * 16 < n;             // a warp whose 16 query rows all lie past the sequence only keeps the barriers
+  // one key tile; FR: fewer than 64 live keys (n = 64 k + 1, the model's frame counts, leaves ONE in the last tile) -- the dead n-tiles / k-steps are skipped
+  auto tile = [&](auto fr_tag, int j0) {
+    constexpr bool FR = decltype(fr_tag)::value;
+    const int nl = ta_live(n, j0), nth = (nl + 7) >> 3, ntf = (TA_B - nl) >> 3;
+    ta_rel_rows<FR>(Qs, Es, Rs, warp, ntf);
     __syncwarp();
     float s[1][8][4];
     tf32::zero(s);
-    tf32::warp_gemm<1, 8>(s, 2, [&](int r, int k) { return Qs[(warp * 16 + r) * TA_LD + k]; }, [&](int k, int c) { return Ks[c * TA_LD + k]; });
+    tf32::warp_gemm_fr<FR, 1, 8>(s, 2, 0, 2, 0, nth, [&](int r, int k) { return Qs[(warp * 16 + r) * TA_LD + k]; }, [&](int k, int c) { return Ks[c * TA_LD + k]; });
     float mx[2] = {TA_NEG, TA_NEG};
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
+      if (!FR || nt < nth) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int il = warp * 16 + tf32::c_row(0, e), jl = tf32::c_col(nt, e);
-        float v = TA_SCALE * (s[0][nt][e] + Rs[il * TA_RLD + il - jl + 63]);
-        if (j0 + jl >= n) v = TA_NEG;
-        s[0][nt][e] = v;
-        mx[e >> 1] = fmaxf(mx[e >> 1], v);
+        for (int e = 0; e < 4; ++e) {
+          const int il = warp * 16 + tf32::c_row(0, e), jl = tf32::c_col(nt, e);
+          float v = TA_SCALE * (s[0][nt][e] + Rs[il * TA_RLD + il - jl + 63]);
+          if (j0 + jl >= n) v = TA_NEG;
+          s[0][nt][e] = v;
+          mx[e >> 1] = fmaxf(mx[e >> 1], v);
+        }
       }
     float corr[2];
 #pragma unroll
@@ -111,19 +119,32 @@ __global__ void __launch_bounds__(128) attention_train_fwd_kernel(const float* _
     }
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
+      if (!FR || nt < nth) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float p = expf(s[0][nt][e] - m[e >> 1]);
-        l[e >> 1] += p;
-        const int il = warp * 16 + tf32::c_row(0, e);
-        Rs[il * TA_RLD + il - tf32::c_col(nt, e) + 63] = p;          // P[i, j] replaces the R entry it was built from (same skewed slot)
+        for (int e = 0; e < 4; ++e) {
+          const float p = expf(s[0][nt][e] - m[e >> 1]);
+          l[e >> 1] += p;
+          const int il = warp * 16 + tf32::c_row(0, e);
+          Rs[il * TA_RLD + il - tf32::c_col(nt, e) + 63] = p;          // P[i, j] replaces the R entry it was built from (same skewed slot)
+        }
       }
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
       for (int e = 0; e < 4; ++e) o[0][nt][e] *= corr[e >> 1];
     __syncwarp();
-    tf32::warp_gemm<1, 2>(o, 8, [&](int r, int k) { return Rs[(warp * 16 + r) * TA_RLD + warp * 16 + r - k + 63]; }, [&](int k, int c) { return Vs[k * TA_LD + c]; });
+    tf32::warp_gemm_fr<FR, 1, 2>(o, 8, 0, nth, 0, 2, [&](int r, int k) { return Rs[(warp * 16 + r) * TA_RLD + warp * 16 + r - k + 63]; },
+                                 [&](int k, int c) { return Vs[k * TA_LD + c]; });
+  };
+  for (int j0 = 0; j0 < n; j0 += TA_B) {
+    __syncthreads();
+    ta_load_tile(Ks, qkv, base, sq.pos_stride, TA_ROW, 64 + h * TA_D, j0, n);
+    ta_load_tile(Vs, qkv, base, sq.pos_stride, TA_ROW, 128 + h * TA_D, j0, n);
+    ta_load_window(Es, E, i0 - j0 - 63);
+    __syncthreads();
+    if (warp_live) {
+      if (n - j0 >= TA_B) tile(std::false_type{}, j0); else tile(std::true_type{}, j0);
+    }
   }
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -191,29 +212,30 @@ __global__ void __launch_bounds__(128) attention_bwd_q_kernel(const float* __res
     }
     float dq[1][2][4];
     tf32::zero(dq);
-    for (int j0 = 0; j0 < n; j0 += TA_B) {
-      __syncthreads();                                  // previous tile's dE GEMM has read Rs / Qs; Ks / Vs / Es are free
-      ta_load_tile(Ks, qkv, base, sq.pos_stride, TA_ROW, 64 + h * TA_D, j0, n);
-      ta_load_tile(Vs, qkv, base, sq.pos_stride, TA_ROW, 128 + h * TA_D, j0, n);
-      const int dbase = i0 - j0 - 63;
-      ta_load_window(Es, E, dbase);
-      __syncthreads();
-      ta_rel_rows(Qs, Es, Rs, warp);
+    const int nr = ta_live(n, i0);                      // live query rows of this tile
+    const bool warp_live = warp * 16 < nr;              // a warp whose 16 query rows all lie past the sequence skips its row-owned work
+    // the row-owned part of one key tile; FR: fewer than 64 live keys -- the dead n-tiles / k-steps are skipped
+    auto tile_rows = [&](auto fr_tag, int j0) {
+      constexpr bool FR = decltype(fr_tag)::value;
+      const int nl = ta_live(n, j0), nth = (nl + 7) >> 3, ntf = (TA_B - nl) >> 3;
+      ta_rel_rows<FR>(Qs, Es, Rs, warp, ntf);
       __syncwarp();
       float s[1][8][4], dp[1][8][4];
       tf32::zero(s);
       tf32::zero(dp);
-      tf32::warp_gemm<1, 8>(s, 2, [&](int r, int k) { return Qs[(warp * 16 + r) * TA_LD + k]; }, [&](int k, int c) { return Ks[c * TA_LD + k]; });
-      tf32::warp_gemm<1, 8>(dp, 2, [&](int r, int k) { return dOs[(warp * 16 + r) * TA_LD + k]; }, [&](int k, int c) { return Vs[c * TA_LD + k]; });
+      tf32::warp_gemm_fr<FR, 1, 8>(s, 2, 0, 2, 0, nth, [&](int r, int k) { return Qs[(warp * 16 + r) * TA_LD + k]; }, [&](int k, int c) { return Ks[c * TA_LD + k]; });
+      tf32::warp_gemm_fr<FR, 1, 8>(dp, 2, 0, 2, 0, nth, [&](int r, int k) { return dOs[(warp * 16 + r) * TA_LD + k]; }, [&](int k, int c) { return Vs[c * TA_LD + k]; });
       // dS' = scale * P * (dP - D); keep it in s
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt)
+        if (!FR || nt < nth) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int rl = warp * 16 + tf32::c_row(0, e), jl = tf32::c_col(nt, e);
-          const float v = TA_SCALE * (s[0][nt][e] + Rs[rl * TA_RLD + rl - jl + 63]);
-          const float p = (j0 + jl < n && i0 + rl < n) ? expf(v - Ls[rl]) : 0.f;
-          s[0][nt][e] = TA_SCALE * p * (dp[0][nt][e] - Ds[rl]);
+          for (int e = 0; e < 4; ++e) {
+            const int rl = warp * 16 + tf32::c_row(0, e), jl = tf32::c_col(nt, e);
+            const float v = TA_SCALE * (s[0][nt][e] + Rs[rl * TA_RLD + rl - jl + 63]);
+            const float p = (j0 + jl < n && i0 + rl < n) ? expf(v - Ls[rl]) : 0.f;
+            s[0][nt][e] = TA_SCALE * p * (dp[0][nt][e] - Ds[rl]);
+          }
         }
       __syncwarp();                                     // every lane has read its R entries: the rows can be overwritten by dR
       // own rows of dR (the banded matrix dR[i, w] = dS'[i, i - w + 63]): clear the warp's band, then scatter
@@ -222,36 +244,58 @@ __global__ void __launch_bounds__(128) attention_bwd_q_kernel(const float* __res
       __syncwarp();
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt)
+        if (!FR || nt < nth) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int rl = warp * 16 + tf32::c_row(0, e);
-          Rs[rl * TA_RLD + rl - tf32::c_col(nt, e) + 63] = s[0][nt][e];
+          for (int e = 0; e < 4; ++e) {
+            const int rl = warp * 16 + tf32::c_row(0, e);
+            Rs[rl * TA_RLD + rl - tf32::c_col(nt, e) + 63] = s[0][nt][e];
+          }
         }
       __syncwarp();
-      // dQ += dS' K (dS'[i, j] read back from its skewed slot) + dR E_win (only the warp's band of window columns is non-zero)
-      tf32::warp_gemm<1, 2>(dq, 8, [&](int r, int k) { return Rs[(warp * 16 + r) * TA_RLD + warp * 16 + r - k + 63]; }, [&](int k, int c) { return Ks[k * TA_LD + c]; });
-      tf32::warp_gemm<1, 2>(dq, TA_BAND / 8, [&](int r, int k) { return Rs[(warp * 16 + r) * TA_RLD + warp * 16 + k]; },
-                            [&](int k, int c) { return Es[(warp * 16 + k) * TA_LD + c]; });
+      // dQ += dS' K (dS'[i, j] read back from its skewed slot) + dR E_win (only the warp's band of window columns is non-zero; with nl live keys only its n-tiles from ntf on)
+      tf32::warp_gemm_fr<FR, 1, 2>(dq, 8, 0, nth, 0, 2, [&](int r, int k) { return Rs[(warp * 16 + r) * TA_RLD + warp * 16 + r - k + 63]; },
+                                   [&](int k, int c) { return Ks[k * TA_LD + c]; });
+      tf32::warp_gemm_fr<FR, 1, 2>(dq, TA_BAND / 8, ntf, TA_BAND / 8, 0, 2, [&](int r, int k) { return Rs[(warp * 16 + r) * TA_RLD + warp * 16 + k]; },
+                                   [&](int k, int c) { return Es[(warp * 16 + k) * TA_LD + c]; });
+    };
+    for (int j0 = 0; j0 < n; j0 += TA_B) {
+      __syncthreads();                                  // previous tile's dE GEMM has read Rs / Qs; Ks / Vs / Es are free
+      ta_load_tile(Ks, qkv, base, sq.pos_stride, TA_ROW, 64 + h * TA_D, j0, n);
+      ta_load_tile(Vs, qkv, base, sq.pos_stride, TA_ROW, 128 + h * TA_D, j0, n);
+      const int dbase = i0 - j0 - 63;
+      ta_load_window(Es, E, dbase);
+      __syncthreads();
+      const int nl = ta_live(n, j0);
+      if (warp_live) {
+        if (nl == TA_B) tile_rows(std::false_type{}, j0); else tile_rows(std::true_type{}, j0);
+      } else {                                          // dead rows: their dR band must read as zero in the dE GEMM below (it may hold the previous item's values)
+        for (int idx = threadIdx.x & 31; idx < 16 * (TA_BAND / 4); idx += 32)
+          *reinterpret_cast<float4*>(Rs + (warp * 16 + idx / (TA_BAND / 4)) * TA_RLD + warp * 16 + (idx % (TA_BAND / 4)) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       __syncthreads();                                  // all 64 rows of dR are in place
       {
-        // dE_win[w] = sum_i dR[i, w] q_i for this warp's 32 window rows; dR[i, w] != 0 only for w - 63 <= i <= w
+        // dE_win[w] = sum_i dR[i, w] q_i for this warp's 32 window rows; dR[i, w] != 0 only for w - 63 <= i <= w, i < nr and w >= i + 64 - nl
         const int k_lo = warp == 3 ? 32 : 0, k_n = (warp == 0 || warp == 3) ? 4 : 8;
-        float de[2][2][4];
-        tf32::zero(de);
-        tf32::warp_gemm<2, 2>(de, k_n, [&](int r, int k) { return Rs[(k_lo + k) * TA_RLD + warp * 32 + r]; }, [&](int k, int c) { return Qs[(k_lo + k) * TA_LD + c]; });
+        int k_hi = (nr - k_lo + 7) >> 3;                // k-steps that still hold live query rows
+        k_hi = k_hi < 0 ? 0 : (k_hi > k_n ? k_n : k_hi);
+        if (warp * 32 + 31 >= TA_B - nl && k_hi > 0) {
+          float de[2][2][4];
+          tf32::zero(de);
+          tf32::warp_gemm_range<2, 2>(de, 0, k_hi, 0, 2, [&](int r, int k) { return Rs[(k_lo + k) * TA_RLD + warp * 32 + r]; }, [&](int k, int c) { return Qs[(k_lo + k) * TA_LD + c]; });
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+          for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-          for (int nt = 0; nt < 2; ++nt)
+            for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int w = warp * 32 + tf32::c_row(mt, e);
-              if (w < 127) {
-                int d = dbase + w;
-                d = d < -emax ? -emax : (d > emax ? emax : d);          // |d| <= n - 1 wherever dR is non-zero; the clamp only acts at +-512
-                atomicAdd(dEt + (d + emax) * TA_D + tf32::c_col(nt, e), de[mt][nt][e]);
+              for (int e = 0; e < 4; ++e) {
+                const int w = warp * 32 + tf32::c_row(mt, e);
+                if (w < 127) {
+                  int d = dbase + w;
+                  d = d < -emax ? -emax : (d > emax ? emax : d);          // |d| <= n - 1 wherever dR is non-zero; the clamp only acts at +-512
+                  atomicAdd(dEt + (d + emax) * TA_D + tf32::c_col(nt, e), de[mt][nt][e]);
+                }
               }
-            }
+        }
       }
     }
 #pragma unroll
@@ -302,6 +346,43 @@ __global__ void __launch_bounds__(128) attention_bwd_k_kernel(const float* __res
   float dk[1][2][4], dv[1][2][4];
   tf32::zero(dk);
   tf32::zero(dv);
+  const int nlk = ta_live(n, j0);                       // live keys of this CTA's tile
+  const bool key_live = warp * 16 < nlk;                // a warp whose 16 keys all lie past the sequence only keeps the barriers (and its share of the R rows)
+  // the key-owned part of one query tile; FR: fewer than 64 live queries (n = 64 k + 1 leaves ONE in the last tile) -- the dead n-tiles / k-steps are skipped
+  auto tile_keys = [&](auto fr_tag, int i0) {
+    constexpr bool FR = decltype(fr_tag)::value;
+    const int nth = (ta_live(n, i0) + 7) >> 3;
+    // S^T[j, i] = k_j . q_i;  dP^T[j, i] = v_j . dO_i   (rows = this warp's 16 keys, columns = the 64 queries)
+    float st[1][8][4], dpt[1][8][4];
+    tf32::zero(st);
+    tf32::zero(dpt);
+    tf32::warp_gemm_fr<FR, 1, 8>(st, 2, 0, 2, 0, nth, [&](int r, int k) { return Ks[(warp * 16 + r) * TA_LD + k]; }, [&](int k, int c) { return Qs[c * TA_LD + k]; });
+    tf32::warp_gemm_fr<FR, 1, 8>(dpt, 2, 0, 2, 0, nth, [&](int r, int k) { return Vs[(warp * 16 + r) * TA_LD + k]; }, [&](int k, int c) { return dOs[c * TA_LD + k]; });
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+      if (!FR || nt < nth) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int jl = warp * 16 + tf32::c_row(0, e), il = tf32::c_col(nt, e);
+          const float v = TA_SCALE * (st[0][nt][e] + Rs[il * TA_RLD + il - jl + 63]);
+          const float p = (j0 + jl < n && i0 + il < n) ? expf(v - Ls[il]) : 0.f;
+          st[0][nt][e] = p;
+          dpt[0][nt][e] = TA_SCALE * p * (dpt[0][nt][e] - Ds[il]);
+          Ts[jl * TA_PLD + il] = p;
+        }
+      }
+    __syncwarp();
+    tf32::warp_gemm_fr<FR, 1, 2>(dv, 8, 0, nth, 0, 2, [&](int r, int k) { return Ts[(warp * 16 + r) * TA_PLD + k]; }, [&](int k, int c) { return dOs[k * TA_LD + c]; });
+    __syncwarp();
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+      if (!FR || nt < nth) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) Ts[(warp * 16 + tf32::c_row(0, e)) * TA_PLD + tf32::c_col(nt, e)] = dpt[0][nt][e];
+      }
+    __syncwarp();
+    tf32::warp_gemm_fr<FR, 1, 2>(dk, 8, 0, nth, 0, 2, [&](int r, int k) { return Ts[(warp * 16 + r) * TA_PLD + k]; }, [&](int k, int c) { return Qs[k * TA_LD + c]; });
+  };
   for (int i0 = 0; i0 < n; i0 += TA_B) {
     __syncthreads();
     ta_load_tile(Qs, qkv, base, sq.pos_stride, TA_ROW, h * TA_D, i0, n);
@@ -314,34 +395,14 @@ __global__ void __launch_bounds__(128) attention_bwd_k_kernel(const float* __res
       Ds[threadIdx.x] = i < n ? Dg[tok * 4 + h] : 0.f;
     }
     __syncthreads();
-    ta_rel_rows(Qs, Es, Rs, warp);                      // warp w: R rows of queries 16 w .. + 15
+    const int nrq = ta_live(n, i0);                     // live query rows of this tile
+    if (warp * 16 < nrq) {                              // warp w: R rows of queries 16 w .. + 15 (skipped when they all lie past the sequence)
+      if (nlk == TA_B) ta_rel_rows<false>(Qs, Es, Rs, warp, 0); else ta_rel_rows<true>(Qs, Es, Rs, warp, (TA_B - nlk) >> 3);
+    }
     __syncthreads();                                    // the transposed tile below reads every query row
-    // S^T[j, i] = k_j . q_i;  dP^T[j, i] = v_j . dO_i   (rows = this warp's 16 keys, columns = the 64 queries)
-    float st[1][8][4], dpt[1][8][4];
-    tf32::zero(st);
-    tf32::zero(dpt);
-    tf32::warp_gemm<1, 8>(st, 2, [&](int r, int k) { return Ks[(warp * 16 + r) * TA_LD + k]; }, [&](int k, int c) { return Qs[c * TA_LD + k]; });
-    tf32::warp_gemm<1, 8>(dpt, 2, [&](int r, int k) { return Vs[(warp * 16 + r) * TA_LD + k]; }, [&](int k, int c) { return dOs[c * TA_LD + k]; });
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int jl = warp * 16 + tf32::c_row(0, e), il = tf32::c_col(nt, e);
-        const float v = TA_SCALE * (st[0][nt][e] + Rs[il * TA_RLD + il - jl + 63]);
-        const float p = (j0 + jl < n && i0 + il < n) ? expf(v - Ls[il]) : 0.f;
-        st[0][nt][e] = p;
-        dpt[0][nt][e] = TA_SCALE * p * (dpt[0][nt][e] - Ds[il]);
-        Ts[jl * TA_PLD + il] = p;
-      }
-    __syncwarp();
-    tf32::warp_gemm<1, 2>(dv, 8, [&](int r, int k) { return Ts[(warp * 16 + r) * TA_PLD + k]; }, [&](int k, int c) { return dOs[k * TA_LD + c]; });
-    __syncwarp();
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) Ts[(warp * 16 + tf32::c_row(0, e)) * TA_PLD + tf32::c_col(nt, e)] = dpt[0][nt][e];
-    __syncwarp();
-    tf32::warp_gemm<1, 2>(dk, 8, [&](int r, int k) { return Ts[(warp * 16 + r) * TA_PLD + k]; }, [&](int k, int c) { return Qs[k * TA_LD + c]; });
+    if (key_live) {
+      if (nrq == TA_B) tile_keys(std::false_type{}, i0); else tile_keys(std::true_type{}, i0);
+    }
   }
 #pragma unroll
   for (int nt = 0; nt < 2; ++nt)

@@ -59,6 +59,44 @@ __device__ __forceinline__ void warp_gemm(float (&acc)[MT][NT][4], int KS, FA a_
   }
 }
 
+// the same product restricted to the k-steps [ks_lo, ks_hi) and the n-tiles [nt_lo, nt_hi): fringe tiles (a sequence length of 64 k + 1 leaves ONE live
+// row / column in the last tile) skip the dead part of the tensor work; the bounds are warp-uniform, the accumulator indexing stays static
+template <int MT, int NT, class FA, class FB>
+__device__ __forceinline__ void warp_gemm_range(float (&acc)[MT][NT][4], int ks_lo, int ks_hi, int nt_lo, int nt_hi, FA a_at, FB b_at) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  for (int ks = ks_lo; ks < ks_hi; ++ks) {
+    const int k0 = ks * 8;
+    uint32_t ah[MT][4], al[MT][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      split(a_at(mt * 16 + g, k0 + t), ah[mt][0], al[mt][0]);
+      split(a_at(mt * 16 + g + 8, k0 + t), ah[mt][1], al[mt][1]);
+      split(a_at(mt * 16 + g, k0 + t + 4), ah[mt][2], al[mt][2]);
+      split(a_at(mt * 16 + g + 8, k0 + t + 4), ah[mt][3], al[mt][3]);
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      if (nt >= nt_lo && nt < nt_hi) {
+        uint32_t bh[2], bl[2];
+        split(b_at(k0 + t, nt * 8 + g), bh[0], bl[0]);
+        split(b_at(k0 + t + 4, nt * 8 + g), bh[1], bl[1]);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          mma(acc[mt][nt], al[mt], bh);
+          mma(acc[mt][nt], ah[mt], bl);
+          mma(acc[mt][nt], ah[mt], bh);
+        }
+      }
+    }
+  }
+}
+// FR = false: the full product (KS k-steps, every n-tile), exactly warp_gemm; FR = true: the restricted one
+template <bool FR, int MT, int NT, class FA, class FB>
+__device__ __forceinline__ void warp_gemm_fr(float (&acc)[MT][NT][4], int KS, int ks_lo, int ks_hi, int nt_lo, int nt_hi, FA a_at, FB b_at) {
+  if (FR) warp_gemm_range<MT, NT>(acc, ks_lo, ks_hi, nt_lo, nt_hi, a_at, b_at);
+  else warp_gemm<MT, NT>(acc, KS, a_at, b_at);
+}
+
 template <int MT, int NT>
 __device__ __forceinline__ void zero(float (&acc)[MT][NT][4]) {
 #pragma unroll
