@@ -215,6 +215,227 @@ __global__ void __launch_bounds__(256) wgrad_finish_kernel(const float* __restri
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------------
+// tcgen05 form (default): the same split-M contraction with the tensor work on tcgen05 / tensor memory.  Both operands have the reduction index m as
+// their slow index (G [m][n], A [m][k]), i.e. both are MN-MAJOR UMMA operands: a 32-row step is staged as three bf16 planes (hi | mid | lo, 2^-25
+// operand error) in the no-swizzle canonical layout (8 rows x 16 bytes core matrices; 8 consecutive features of one row = one 16-byte store), and one
+// thread issues 12 tcgen05.mma (M = 128, N = 64, K = 16; the six products of the three-plane split, hi x hi in its own accumulator) per step while the
+// CTA's 256 threads fetch, split and store the next one.  X is the 128-wide side, Y the 64-wide side:
+//   MODE 0 (K a multiple of 128, or N = 64):  X = two 64-wide K chunks of the layer input, Y = 64 gradient columns   D[k, n]
+//   MODE 1 (K = 64, N a multiple of 128):     X = 128 gradient columns, Y = the layer input                          D[n, k]
+// The tensor pipe's fp32 accumulation truncates (section 4b of DESIGN.md): every WT_FLUSH steps (256 rows, 16 MMAs into the hi x hi accumulator) the
+// accumulators are read back and added to a shared-memory fp32 tile with IEEE adds; the split partials go through the same finish kernel as before.
+// ------------------------------------------------------------------------------------------------------------------------------------
+constexpr int WT_ROWS = 32;
+constexpr int WT_SBO = WT_ROWS * 16 + 16;            // bytes between 8-feature blocks (+16: the eight lanes of a row store to different bank groups)
+constexpr int WT_XP = 16 * WT_SBO, WT_YP = 8 * WT_SBO;
+constexpr int WT_STAGE = 3 * WT_XP + 3 * WT_YP;      // 38016 bytes
+constexpr int WT_ACC_LD = 65;                        // fp32 accumulator tile [128][65] (thread = row: conflict-free)
+constexpr int WT_FLUSH = 8;
+constexpr int WT_SMEM = 2 * WT_STAGE + 128 * WT_ACC_LD * 4 + 128;
+
+__device__ __forceinline__ uint64_t wt_desc(uint32_t smem_addr) {      // no-swizzle MN-major operand: lbo = next 8 rows along K (128 bytes), sbo = next 8 features
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(128 >> 4) << 16;
+  d |= (uint64_t)(WT_SBO >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+__device__ __forceinline__ void wt_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <int LK, int MODE>
+__global__ void __launch_bounds__(256, 2) wgrad_tc_kernel(const GemmArgs g, const float* __restrict__ G, long long ldg, int N, int rows_per_split,
+                                                          float* __restrict__ partial, float* __restrict__ partial_b) {
+  extern __shared__ __align__(16) uint8_t wt_raw[];
+  __shared__ uint64_t mma_done[2], acc_bar;
+  __shared__ uint32_t tmem_base_s;
+  const uint32_t sm0 = (ptx::smem_u32(wt_raw) + 127u) & ~127u;
+  float* accs = reinterpret_cast<float*>(wt_raw + (sm0 - ptx::smem_u32(wt_raw)) + 2 * WT_STAGE);      // [128][WT_ACC_LD]; the bias scratch [32][128] reuses it at the end
+  const int tid = threadIdx.x, warp = tid >> 5, sub = tid & 7, rloc = tid >> 3;
+  const int split = blockIdx.x;
+  const int kc = MODE == 0 ? 2 * blockIdx.y : blockIdx.y;                  // first 64-wide K chunk of this CTA
+  const int n0 = blockIdx.z * (MODE == 0 ? 64 : 128);
+  const int m_lo = split * rows_per_split;
+  const int m_hi = min(g.M, m_lo + rows_per_split);
+  const int nsteps = (m_hi - m_lo + WT_ROWS - 1) / WT_ROWS;
+  const bool want_bias = partial_b != nullptr && kc == 0;
+  if (tid == 0) {
+    ptx::mbar_init(&mma_done[0], 1); ptx::mbar_init(&mma_done[1], 1); ptx::mbar_init(&acc_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0) ptx::tmem_alloc(&tmem_base_s, 128);
+  if (tid < 128) {
+#pragma unroll 8
+    for (int y = 0; y < 64; ++y) accs[tid * WT_ACC_LD + y] = 0.f;
+  }
+  // the second X chunk of MODE 0 is empty when K is not a multiple of 128 (K = 64 / 192): its planes stay zero
+  const bool x1_live = MODE == 1 || (kc + 1) * 64 < g.K;
+  if (!x1_live) {
+    for (int i = tid; i < 2 * 3 * 8 * (WT_SBO / 16); i += 256) {
+      const int b = i / (3 * 8 * (WT_SBO / 16)), r = i % (3 * 8 * (WT_SBO / 16));
+      const int pl = r / (8 * (WT_SBO / 16)), q = r % (8 * (WT_SBO / 16));
+      *reinterpret_cast<uint4*>(wt_raw + (sm0 - ptx::smem_u32(wt_raw)) + b * WT_STAGE + pl * WT_XP + 8 * WT_SBO + q * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  float xv[2][8], yv[8];
+  float bsum[MODE == 0 ? 1 : 2][8];
+#pragma unroll
+  for (int j = 0; j < (MODE == 0 ? 1 : 2); ++j)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) bsum[j][i] = 0.f;
+  auto ld_g = [&](int m, bool ok, int col, float (&v)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    if (ok && col < N) {
+      const float* gp = G + (long long)m * ldg + col;
+      const float4 g0 = ldg4(gp), g1 = ldg4(gp + 4);
+      v[0] = g0.x; v[1] = g0.y; v[2] = g0.z; v[3] = g0.w; v[4] = g1.x; v[5] = g1.y; v[6] = g1.z; v[7] = g1.w;
+    }
+  };
+  auto fetch = [&](int m0) {
+    const int m = m0 + rloc;
+    const bool ok = m0 < m_hi && m < m_hi;
+    typename Loader<LK>::Row row;
+    Loader<LK>::init_row(g, ok ? m : g.M, row);                            // rows past the split read as zeros
+    if (MODE == 0) {
+      Loader<LK>::load(g, row, kc, sub, xv[0]);
+      if (x1_live) Loader<LK>::load(g, row, kc + 1, sub, xv[1]);
+      ld_g(m, ok, n0 + sub * 8, yv);
+    } else {
+      ld_g(m, ok, n0 + sub * 8, xv[0]);
+      ld_g(m, ok, n0 + 64 + sub * 8, xv[1]);
+      Loader<LK>::load(g, row, kc, sub, yv);
+    }
+  };
+  auto store8 = [&](uint32_t base, uint32_t plane_bytes, const float (&v)[8]) {      // three bf16 planes of 8 features of row rloc
+    uint4 hi, mid, lo;
+    split3_bf16x2(v[0], v[1], hi.x, mid.x, lo.x);
+    split3_bf16x2(v[2], v[3], hi.y, mid.y, lo.y);
+    split3_bf16x2(v[4], v[5], hi.z, mid.z, lo.z);
+    split3_bf16x2(v[6], v[7], hi.w, mid.w, lo.w);
+    const uint32_t a = base + (uint32_t)((rloc >> 3) * 128 + (rloc & 7) * 16);
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a + plane_bytes), "r"(mid.x), "r"(mid.y), "r"(mid.z), "r"(mid.w) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a + 2 * plane_bytes), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w) : "memory");
+  };
+  auto store_stage = [&](int b) {
+    const uint32_t st = sm0 + (uint32_t)(b * WT_STAGE);
+    store8(st + (uint32_t)(sub * WT_SBO), WT_XP, xv[0]);
+    if (x1_live) store8(st + (uint32_t)((8 + sub) * WT_SBO), WT_XP, xv[1]);
+    store8(st + 3 * WT_XP + (uint32_t)(sub * WT_SBO), WT_YP, yv);
+    if (want_bias) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (MODE == 0) bsum[0][i] += yv[i];
+        else { bsum[0][i] += xv[0][i]; bsum[MODE == 0 ? 0 : 1][i] += xv[1][i]; }
+      }
+    }
+  };
+  fetch(m_lo);
+  store_stage(0);
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  int nflush = 0;
+  for (int i = 0; i < nsteps; ++i) {
+    const int b = i & 1;
+    const bool flush = (i % WT_FLUSH == WT_FLUSH - 1) || i == nsteps - 1;
+    fetch(m_lo + (i + 1) * WT_ROWS);                                       // next step's operands: in flight across the tensor work (all lanes call it: the LayerNorm loader shuffles)
+    if (tid == 0) {
+      const uint32_t st = sm0 + (uint32_t)(b * WT_STAGE);
+      const uint32_t first = (i % WT_FLUSH == 0) ? 0u : 1u;
+#pragma unroll
+      for (int k = 0; k < WT_ROWS / 16; ++k) {
+        const uint32_t off = (uint32_t)(k * 256);
+        const uint64_t xh = wt_desc(st + off), xm = wt_desc(st + WT_XP + off), xl = wt_desc(st + 2 * WT_XP + off);
+        const uint64_t yh = wt_desc(st + 3 * WT_XP + off), ym = wt_desc(st + 3 * WT_XP + WT_YP + off), yl = wt_desc(st + 3 * WT_XP + 2 * WT_YP + off);
+        const uint32_t acc2 = tmem_base + 64u, f = (k == 0) ? first : 1u;
+        ptx::mma_bf16(acc2, xl, yh, IDESC, f);                             // smallest terms first
+        ptx::mma_bf16(acc2, xh, yl, IDESC, 1u);
+        ptx::mma_bf16(acc2, xm, ym, IDESC, 1u);
+        ptx::mma_bf16(acc2, xm, yh, IDESC, 1u);
+        ptx::mma_bf16(acc2, xh, ym, IDESC, 1u);
+        ptx::mma_bf16(tmem_base, xh, yh, IDESC, f);
+      }
+      ptx::tc_commit(&mma_done[b]);
+      if (flush) ptx::tc_commit(&acc_bar);
+    }
+    if (flush && tid < 128) {                                              // thread = accumulator lane = X feature
+      ptx::mbar_wait(&acc_bar, (uint32_t)nflush & 1u);
+      ptx::tc_fence_after();
+      const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16);
+      float* arow = accs + tid * WT_ACC_LD;
+#pragma unroll
+      for (int c = 0; c < 64; c += 16) {
+        float v1[16], v2[16];
+        wt_ld16(ta + (uint32_t)c, v1);
+        wt_ld16(ta + 64u + (uint32_t)c, v2);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) arow[c + e] += v1[e] + v2[e];
+      }
+      ptx::tc_fence_before();
+    }
+    if (flush) ++nflush;
+    if (i > 0) ptx::mbar_wait(&mma_done[b ^ 1], (uint32_t)((i - 1) >> 1) & 1u);        // the MMAs that read the other staging set are done
+    store_stage(b ^ 1);
+    ptx::fence_proxy_async_smem();
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+  }
+  // ---- partial tile: MODE 0  D[x = k, y = n] -> partial[split][n0 + y][kc * 64 + x];  MODE 1  D[x = n, y = k] -> partial[split][n0 + x][kc * 64 + y]
+  const int K = g.K;
+  if (tid < 128) {
+    const float* arow = accs + tid * WT_ACC_LD;
+    if (MODE == 0) {
+      const int k = kc * 64 + tid;
+      if (k < K) {
+#pragma unroll 8
+        for (int y = 0; y < 64; ++y) partial[((long long)split * N + n0 + y) * K + k] = arow[y];
+      }
+    } else {
+      const int n = n0 + tid;
+      if (n < N) {
+        float* dst = partial + ((long long)split * N + n) * K + kc * 64;
+#pragma unroll
+        for (int y = 0; y < 64; y += 4) *reinterpret_cast<float4*>(dst + y) = make_float4(arow[y], arow[y + 1], arow[y + 2], arow[y + 3]);
+      }
+    }
+  }
+  if (want_bias) {                                                          // column sums of the gradient rows this CTA staged: 32 row partials per column, summed in a fixed order
+    __syncthreads();
+    float* bs = accs;                                                       // [32][128]
+#pragma unroll
+    for (int j = 0; j < (MODE == 0 ? 1 : 2); ++j)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) bs[rloc * 128 + j * 64 + sub * 8 + e] = bsum[j][e];
+    __syncthreads();
+    const int ncol = MODE == 0 ? 64 : 128;
+    if (tid < ncol && n0 + tid < N) {
+      float t = 0.f;
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) t += bs[r * 128 + tid];
+      partial_b[(long long)split * N + n0 + tid] = t;
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem_base, 128);
+}
+
 static GemmArgs wg_args(const SebGemm* s) {
   GemmArgs g;
   for (int i = 0; i < 4; ++i) g.a[i] = s->a[i];
@@ -241,9 +462,17 @@ static int wg_nc(int N, int K) {
 }
 
 // Number of row splits seb200_wgrad uses for (M, N, K): enough CTAs for two waves of 148 SMs, at least 256 rows per split.
+// SEB200_WGRAD_MMASYNC=1 selects the mma.sync (3xTF32) kernel instead of the tcgen05 one (A/B measurements, cross-check)
+static bool wg_mmasync() {
+  static const bool v = getenv("SEB200_WGRAD_MMASYNC") && atoi(getenv("SEB200_WGRAD_MMASYNC")) != 0;
+  return v;
+}
+static int wt_mode(int N, int K) { return (K == 64 && N % 128 == 0) ? 1 : 0; }       // wgrad_tc_kernel: which operand is the 128-wide side
+
 extern "C" int seb200_wgrad_splits(int M, int N, int K) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
-  const int tiles = (K / (64 * wg_kc(K))) * (((N + 63) / 64) / wg_nc(N, K));      // two K chunks or two n-tiles per CTA when the shape allows
+  const int tiles = !wg_mmasync() ? (wt_mode(N, K) ? (N / 128) * (K / 64) : ((K + 127) / 128) * ((N + 63) / 64))
+                                  : (K / (64 * wg_kc(K))) * (((N + 63) / 64) / wg_nc(N, K));      // two K chunks or two n-tiles per CTA when the shape allows
   int S = (2 * 148 + tiles - 1) / tiles;
   const int maxS = (M + 255) / 256;
   if (S > maxS) S = maxS;
@@ -279,9 +508,36 @@ extern "C" int seb200_wgrad(const SebGemm* a, const float* g_out, long long ldg,
   const GemmArgs g = wg_args(a);
   float* partial = workspace;
   float* partial_b = db ? workspace + (long long)S * N * a->K : nullptr;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!wg_mmasync()) {
+    static PerDeviceOnce tc_attr_done;
+    if (!tc_attr_done.done()) {
+      cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<SEB_LOAD_ROWS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_tc_kernel<SEB_LOAD_ROWS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_tc_kernel<SEB_LOAD_ROWS_LN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_tc_kernel<SEB_LOAD_ROWS_LN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_tc_kernel<SEB_LOAD_CONV, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM);
+      if (e != cudaSuccess) { set_error("wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+      tc_attr_done.set();
+    }
+    const int mode = wt_mode(N, a->K);
+    dim3 tgrid(S, mode ? a->K / 64 : (a->K + 127) / 128, mode ? N / 128 : N / 64);
+#define SEB_WT_LAUNCH(LK, MD) wgrad_tc_kernel<LK, MD><<<tgrid, 256, WT_SMEM, st>>>(g, g_out, ldg, N, rows_per_split, partial, partial_b)
+    switch (a->loader) {
+      case SEB_LOAD_ROWS: if (mode) SEB_WT_LAUNCH(SEB_LOAD_ROWS, 1); else SEB_WT_LAUNCH(SEB_LOAD_ROWS, 0); break;
+      case SEB_LOAD_ROWS_LN: if (mode) SEB_WT_LAUNCH(SEB_LOAD_ROWS_LN, 1); else SEB_WT_LAUNCH(SEB_LOAD_ROWS_LN, 0); break;
+      case SEB_LOAD_CONV: SEB_WT_LAUNCH(SEB_LOAD_CONV, 0); break;
+      default: set_error("wgrad: loader %d is not supported", a->loader); return SEB_EUNSUPPORTED;
+    }
+#undef SEB_WT_LAUNCH
+    SEB_CHECK_LAUNCH("wgrad_tc_kernel");
+    const long long total_tc = (long long)N * a->K + (db ? N : 0);
+    wgrad_finish_kernel<<<(unsigned)((total_tc + 255) / 256), 256, 0, st>>>(partial, partial_b, S, N, a->K, k_logical, n1, sn, s0, s1, dw, db);
+    SEB_CHECK_LAUNCH("wgrad_finish_kernel");
+    return 0;
+  }
   const int KC = wg_kc(a->K), NC = wg_nc(N, a->K);
   dim3 grid(S, a->K / (64 * KC), N / (64 * NC));
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   static PerDeviceOnce attr_done;
   if (!attr_done.done()) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<SEB_LOAD_ROWS, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg_smem_bytes<2, 1>());

@@ -1,0 +1,4 @@
+#!/bin/bash
+# tcgen05 weight-gradient kernel: parity tests (both engines' callers), then the training profile / bench
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_train.py -q -p no:cacheprovider -x -k "wgrad or conv_forward or subpixel" 2>&1 | grep -E "passed|failed|Error|assert|rel_max" | cut -c1-300 | tail -12
