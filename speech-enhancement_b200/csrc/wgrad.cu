@@ -219,8 +219,8 @@ __global__ void __launch_bounds__(256) wgrad_finish_kernel(const float* __restri
 // tcgen05 form (default): the same split-M contraction with the tensor work on tcgen05 / tensor memory.  Both operands have the reduction index m as
 // their slow index (G [m][n], A [m][k]), i.e. both are MN-MAJOR UMMA operands: a 32-row step is staged as three bf16 planes (hi | mid | lo, 2^-25
 // operand error) in the no-swizzle canonical layout (8 rows x 16 bytes core matrices; 8 consecutive features of one row = one 16-byte store), and one
-// thread issues 12 tcgen05.mma (M = 128, N = 64, K = 16; the six products of the three-plane split, hi x hi in its own accumulator) per step while the
-// CTA's 256 threads fetch, split and store the next one.  X is the 128-wide side, Y the 64-wide side:
+// thread of a ninth warp issues 12 tcgen05.mma (M = 128, N = 64, K = 16; the six products of the three-plane split, hi x hi in its own accumulator) per step
+// as soon as the eight staging warps have filled a set (full / mma_done mbarriers per set, no block barrier in the loop).  X is the 128-wide side, Y the 64-wide side:
 //   MODE 0 (K a multiple of 128, or N = 64):  X = two 64-wide K chunks of the layer input, Y = 64 gradient columns   D[k, n]
 //   MODE 1 (K = 64, N a multiple of 128):     X = 128 gradient columns, Y = the layer input                          D[n, k]
 // The tensor pipe's fp32 accumulation truncates (section 4b of DESIGN.md): every WT_FLUSH steps (256 rows, 16 MMAs into the hi x hi accumulator) the
@@ -254,10 +254,10 @@ __device__ __forceinline__ void wt_ld16(uint32_t taddr, float (&v)[16]) {
 }
 
 template <int LK, int MODE>
-__global__ void __launch_bounds__(256, 2) wgrad_tc_kernel(const GemmArgs g, const float* __restrict__ G, long long ldg, int N, int rows_per_split,
+__global__ void __launch_bounds__(288, 2) wgrad_tc_kernel(const GemmArgs g, const float* __restrict__ G, long long ldg, int N, int rows_per_split,
                                                           float* __restrict__ partial, float* __restrict__ partial_b) {
   extern __shared__ __align__(16) uint8_t wt_raw[];
-  __shared__ uint64_t mma_done[2], acc_bar;
+  __shared__ uint64_t full_bar[2], mma_done[2], acc_bar, acc_free;
   __shared__ uint32_t tmem_base_s;
   const uint32_t sm0 = (ptx::smem_u32(wt_raw) + 127u) & ~127u;
   float* accs = reinterpret_cast<float*>(wt_raw + (sm0 - ptx::smem_u32(wt_raw)) + 2 * WT_STAGE);      // [128][WT_ACC_LD]; the bias scratch [32][128] reuses it at the end
@@ -271,6 +271,7 @@ __global__ void __launch_bounds__(256, 2) wgrad_tc_kernel(const GemmArgs g, cons
   const bool want_bias = partial_b != nullptr && kc == 0;
   if (tid == 0) {
     ptx::mbar_init(&mma_done[0], 1); ptx::mbar_init(&mma_done[1], 1); ptx::mbar_init(&acc_bar, 1);
+    ptx::mbar_init(&full_bar[0], 256); ptx::mbar_init(&full_bar[1], 256); ptx::mbar_init(&acc_free, 128);
     ptx::fence_barrier_init();
   }
   if (warp == 0) ptx::tmem_alloc(&tmem_base_s, 128);
@@ -281,11 +282,12 @@ __global__ void __launch_bounds__(256, 2) wgrad_tc_kernel(const GemmArgs g, cons
   // the second X chunk of MODE 0 is empty when K is not a multiple of 128 (K = 64 / 192): its planes stay zero
   const bool x1_live = MODE == 1 || (kc + 1) * 64 < g.K;
   if (!x1_live) {
-    for (int i = tid; i < 2 * 3 * 8 * (WT_SBO / 16); i += 256) {
+    for (int i = tid; i < 2 * 3 * 8 * (WT_SBO / 16); i += 288) {
       const int b = i / (3 * 8 * (WT_SBO / 16)), r = i % (3 * 8 * (WT_SBO / 16));
       const int pl = r / (8 * (WT_SBO / 16)), q = r % (8 * (WT_SBO / 16));
       *reinterpret_cast<uint4*>(wt_raw + (sm0 - ptx::smem_u32(wt_raw)) + b * WT_STAGE + pl * WT_XP + 8 * WT_SBO + q * 16) = make_uint4(0u, 0u, 0u, 0u);
     }
+    ptx::fence_proxy_async_smem();
   }
   float xv[2][8], yv[8];
   float bsum[MODE == 0 ? 1 : 2][8];
@@ -341,61 +343,72 @@ __global__ void __launch_bounds__(256, 2) wgrad_tc_kernel(const GemmArgs g, cons
       }
     }
   };
-  fetch(m_lo);
-  store_stage(0);
-  ptx::fence_proxy_async_smem();
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  int nflush = 0;
-  for (int i = 0; i < nsteps; ++i) {
-    const int b = i & 1;
-    const bool flush = (i % WT_FLUSH == WT_FLUSH - 1) || i == nsteps - 1;
-    fetch(m_lo + (i + 1) * WT_ROWS);                                       // next step's operands: in flight across the tensor work (all lanes call it: the LayerNorm loader shuffles)
-    if (tid == 0) {
-      const uint32_t st = sm0 + (uint32_t)(b * WT_STAGE);
-      const uint32_t first = (i % WT_FLUSH == 0) ? 0u : 1u;
+  auto is_flush = [&](int i) { return (i % WT_FLUSH == WT_FLUSH - 1) || i == nsteps - 1; };
+  if (warp == 8) {
+    // ================= MMA issuer (one thread): step i as soon as its staging set is full =================
+    if (tid == 256) {
+      for (int i = 0; i < nsteps; ++i) {
+        const int b = i & 1;
+        ptx::mbar_wait(&full_bar[b], (uint32_t)(i >> 1) & 1u);
+        if (i > 0 && i % WT_FLUSH == 0) ptx::mbar_wait(&acc_free, (uint32_t)(i / WT_FLUSH - 1) & 1u);      // the previous run's accumulators have been read
+        ptx::tc_fence_after();
+        const uint32_t st = sm0 + (uint32_t)(b * WT_STAGE);
+        const uint32_t first = (i % WT_FLUSH == 0) ? 0u : 1u;
 #pragma unroll
-      for (int k = 0; k < WT_ROWS / 16; ++k) {
-        const uint32_t off = (uint32_t)(k * 256);
-        const uint64_t xh = wt_desc(st + off), xm = wt_desc(st + WT_XP + off), xl = wt_desc(st + 2 * WT_XP + off);
-        const uint64_t yh = wt_desc(st + 3 * WT_XP + off), ym = wt_desc(st + 3 * WT_XP + WT_YP + off), yl = wt_desc(st + 3 * WT_XP + 2 * WT_YP + off);
-        const uint32_t acc2 = tmem_base + 64u, f = (k == 0) ? first : 1u;
-        ptx::mma_bf16(acc2, xl, yh, IDESC, f);                             // smallest terms first
-        ptx::mma_bf16(acc2, xh, yl, IDESC, 1u);
-        ptx::mma_bf16(acc2, xm, ym, IDESC, 1u);
-        ptx::mma_bf16(acc2, xm, yh, IDESC, 1u);
-        ptx::mma_bf16(acc2, xh, ym, IDESC, 1u);
-        ptx::mma_bf16(tmem_base, xh, yh, IDESC, f);
+        for (int k = 0; k < WT_ROWS / 16; ++k) {
+          const uint32_t off = (uint32_t)(k * 256);
+          const uint64_t xh = wt_desc(st + off), xm = wt_desc(st + WT_XP + off), xl = wt_desc(st + 2 * WT_XP + off);
+          const uint64_t yh = wt_desc(st + 3 * WT_XP + off), ym = wt_desc(st + 3 * WT_XP + WT_YP + off), yl = wt_desc(st + 3 * WT_XP + 2 * WT_YP + off);
+          const uint32_t acc2 = tmem_base + 64u, f = (k == 0) ? first : 1u;
+          ptx::mma_bf16(acc2, xl, yh, IDESC, f);                             // smallest terms first
+          ptx::mma_bf16(acc2, xh, yl, IDESC, 1u);
+          ptx::mma_bf16(acc2, xm, ym, IDESC, 1u);
+          ptx::mma_bf16(acc2, xm, yh, IDESC, 1u);
+          ptx::mma_bf16(acc2, xh, ym, IDESC, 1u);
+          ptx::mma_bf16(tmem_base, xh, yh, IDESC, f);
+        }
+        ptx::tc_commit(&mma_done[b]);
+        if (is_flush(i)) ptx::tc_commit(&acc_bar);
       }
-      ptx::tc_commit(&mma_done[b]);
-      if (flush) ptx::tc_commit(&acc_bar);
     }
-    if (flush && tid < 128) {                                              // thread = accumulator lane = X feature
-      ptx::mbar_wait(&acc_bar, (uint32_t)nflush & 1u);
-      ptx::tc_fence_after();
-      const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16);
-      float* arow = accs + tid * WT_ACC_LD;
+  } else {
+    // ================= staging warps: fetch -> split -> store, one step ahead of the tensor work; warps 0 - 3 also flush the accumulators =================
+    fetch(m_lo);
+    int nflush = 0;
+    for (int i = 0; i < nsteps; ++i) {
+      const int b = i & 1;
+      if (i >= 2) ptx::mbar_wait(&mma_done[b], (uint32_t)((i - 2) >> 1) & 1u);          // the MMAs that read this staging set (step i - 2) are done
+      store_stage(b);
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(&full_bar[b]);
+      if (i + 1 < nsteps) fetch(m_lo + (i + 1) * WT_ROWS);                    // next step's operands: in flight across the waits below (all lanes call it: the LayerNorm loader shuffles)
+      if (is_flush(i)) {
+        if (tid < 128) {                                                      // thread = accumulator lane = X feature
+          ptx::mbar_wait(&acc_bar, (uint32_t)nflush & 1u);
+          ptx::tc_fence_after();
+          const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16);
+          float* arow = accs + tid * WT_ACC_LD;
 #pragma unroll
-      for (int c = 0; c < 64; c += 16) {
-        float v1[16], v2[16];
-        wt_ld16(ta + (uint32_t)c, v1);
-        wt_ld16(ta + 64u + (uint32_t)c, v2);
+          for (int c = 0; c < 64; c += 16) {
+            float v1[16], v2[16];
+            wt_ld16(ta + (uint32_t)c, v1);
+            wt_ld16(ta + 64u + (uint32_t)c, v2);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) arow[c + e] += v1[e] + v2[e];
+            for (int e = 0; e < 16; ++e) arow[c + e] += v1[e] + v2[e];
+          }
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&acc_free);
+        }
+        ++nflush;
       }
-      ptx::tc_fence_before();
     }
-    if (flush) ++nflush;
-    if (i > 0) ptx::mbar_wait(&mma_done[b ^ 1], (uint32_t)((i - 1) >> 1) & 1u);        // the MMAs that read the other staging set are done
-    store_stage(b ^ 1);
-    ptx::fence_proxy_async_smem();
-    ptx::tc_fence_before();
-    __syncthreads();
-    ptx::tc_fence_after();
   }
+  __syncthreads();
   // ---- partial tile: MODE 0  D[x = k, y = n] -> partial[split][n0 + y][kc * 64 + x];  MODE 1  D[x = n, y = k] -> partial[split][n0 + x][kc * 64 + y]
   const int K = g.K;
   if (tid < 128) {
@@ -522,7 +535,7 @@ extern "C" int seb200_wgrad(const SebGemm* a, const float* g_out, long long ldg,
     }
     const int mode = wt_mode(N, a->K);
     dim3 tgrid(S, mode ? a->K / 64 : (a->K + 127) / 128, mode ? N / 128 : N / 64);
-#define SEB_WT_LAUNCH(LK, MD) wgrad_tc_kernel<LK, MD><<<tgrid, 256, WT_SMEM, st>>>(g, g_out, ldg, N, rows_per_split, partial, partial_b)
+#define SEB_WT_LAUNCH(LK, MD) wgrad_tc_kernel<LK, MD><<<tgrid, 288, WT_SMEM, st>>>(g, g_out, ldg, N, rows_per_split, partial, partial_b)
     switch (a->loader) {
       case SEB_LOAD_ROWS: if (mode) SEB_WT_LAUNCH(SEB_LOAD_ROWS, 1); else SEB_WT_LAUNCH(SEB_LOAD_ROWS, 0); break;
       case SEB_LOAD_ROWS_LN: if (mode) SEB_WT_LAUNCH(SEB_LOAD_ROWS_LN, 1); else SEB_WT_LAUNCH(SEB_LOAD_ROWS_LN, 0); break;
