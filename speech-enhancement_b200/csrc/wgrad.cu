@@ -20,23 +20,35 @@
 namespace seb {
 
 // dW[n, k] = sum_s partial[s][n][k] -> dw[n * sn + (k / n1) * s0 + (k % n1) * s1] for k < k_logical;  db[n] = sum_s partial_b[s][n]
+// CTA = 64 elements x 4 split lanes: lane q sums the splits p = q (mod 4), the four lane sums are added in lane order through shared memory (one thread per
+// element walking up to 148 splits was a serial chain of dependent-latency loads: 21 us per call, 79 calls per step).  Fixed order: deterministic.
 __global__ void __launch_bounds__(256) wgrad_finish_kernel(const float* __restrict__ partial, const float* __restrict__ partial_b, int S, int N, int K,
                                                            int k_logical, int n1, long long sn, long long s0, long long s1,
                                                            float* __restrict__ dw, float* __restrict__ db) {
+  __shared__ float sm[4][64];
   const long long total = (long long)N * K;
-  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (idx < total) {
-    const int n = (int)(idx / K), k = (int)(idx - (long long)n * K);
-    if (k < k_logical) {
-      float s = 0.f;
-      for (int p = 0; p < S; ++p) s += partial[(long long)p * total + idx];
-      dw[(long long)n * sn + (long long)(k / n1) * s0 + (long long)(k % n1) * s1] = s;
+  const int e = threadIdx.x & 63, q = threadIdx.x >> 6;
+  const long long idx = (long long)blockIdx.x * 64 + e;
+  const float* src = nullptr;
+  long long stride = 0;
+  if (idx < total) { src = partial + idx; stride = total; }
+  else if (db != nullptr && idx < total + N) { src = partial_b + (idx - total); stride = N; }
+  float a0 = 0.f, a1 = 0.f;
+  if (src) {
+    int p = q;
+    for (; p + 4 < S; p += 8) { a0 += src[(long long)p * stride]; a1 += src[(long long)(p + 4) * stride]; }
+    if (p < S) a0 += src[(long long)p * stride];
+  }
+  sm[q][e] = a0 + a1;
+  __syncthreads();
+  if (q == 0 && src) {
+    const float s = (sm[0][e] + sm[1][e]) + (sm[2][e] + sm[3][e]);
+    if (idx < total) {
+      const int n = (int)(idx / K), k = (int)(idx - (long long)n * K);
+      if (k < k_logical) dw[(long long)n * sn + (long long)(k / n1) * s0 + (long long)(k % n1) * s1] = s;
+    } else {
+      db[(int)(idx - total)] = s;
     }
-  } else if (db != nullptr && idx < total + N) {
-    const int n = (int)(idx - total);
-    float s = 0.f;
-    for (int p = 0; p < S; ++p) s += partial_b[(long long)p * N + n];
-    db[n] = s;
   }
 }
 
@@ -354,7 +366,7 @@ extern "C" int seb200_wgrad(const SebGemm* a, const float* g_out, long long ldg,
     SEB_CHECK_LAUNCH("wgrad_tc_kernel");
   }
   const long long total = (long long)N * a->K + (db ? N : 0);
-  wgrad_finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, partial_b, S, N, a->K, k_logical, n1, sn, s0, s1, dw, db);
+  wgrad_finish_kernel<<<(unsigned)((total + 63) / 64), 256, 0, st>>>(partial, partial_b, S, N, a->K, k_logical, n1, sn, s0, s1, dw, db);
   SEB_CHECK_LAUNCH("wgrad_finish_kernel");
   return 0;
 }
