@@ -12,8 +12,8 @@
 // partial[s][n][k]; seb200_wgrad_finish sums the S partials in a fixed order (deterministic, no atomics) and scatters them through a two-level index
 // map into the parameter's own layout (conv weights are [Cout, Cin, kt, kf] while K runs (tap, slot, channel)) -- typically straight into the flat
 // gradient buffer the all-reduce sends.  (Until round 2, session 3 this contraction ran on 3xTF32 mma.sync: tools/experiments/wgrad_mmasync_3xtf32_kernel.cu.txt,
-// 15.9 ms per training step against 10.0 ms.  What bounds the tcgen05 form is the L2: every K tile of a layer re-reads the gradient rows, and the
-// conv gather reads each slot once per tap -- ~3.9 TB/s at 4 x 2 s; a second register set for the loads changed nothing.)
+// 15.9 ms per training step against 10.0 ms.  What bounds the tcgen05 form is shared-memory traffic -- 37 KB of plane stores + 72 KB of operand reads by the
+// six products per 32-row step, L1 / shared pipe 57 - 73 % busy -- next to the latency of the loads; a second register set for the loads changed nothing.)
 #include "gemm_engine.cuh"
 #include <stdlib.h>
 
