@@ -56,11 +56,11 @@ __global__ void __launch_bounds__(256) wgrad_finish_kernel(const float* __restri
 // The split-M contraction with the tensor work on tcgen05 / tensor memory.  Both operands have the reduction index m as
 // their slow index (G [m][n], A [m][k]), i.e. both are MN-MAJOR UMMA operands: a 32-row step is staged as three bf16 planes (hi | mid | lo, 2^-25
 // operand error) in the no-swizzle canonical layout (8 rows x 16 bytes core matrices; 8 consecutive features of one row = one 16-byte store), and one
-// thread of a ninth warp issues 12 tcgen05.mma (M = 128, N = 64, K = 16; the six products of the three-plane split, hi x hi in its own accumulator) per step
+// thread of a ninth warp issues 6 tcgen05.mma (M = 128, K = 16, N = 192 / 128 / 64: the six products of the three-plane split, hi x hi in its own accumulator) per step
 // as soon as the eight staging warps have filled a set (full / mma_done mbarriers per set, no block barrier in the loop).  X is the 128-wide side, Y the 64-wide side:
 //   MODE 0 (K a multiple of 128, or N = 64):  X = two 64-wide K chunks of the layer input, Y = 64 gradient columns   D[k, n]
 //   MODE 1 (K = 64, N a multiple of 128):     X = 128 gradient columns, Y = the layer input                          D[n, k]
-// The tensor pipe's fp32 accumulation truncates (section 4b of DESIGN.md): every WT_FLUSH steps (256 rows, 16 MMAs into the hi x hi accumulator) the
+// The tensor pipe's fp32 accumulation truncates (section 4b of DESIGN.md): every WT_FLUSH steps (256 rows, 16 MMAs into each accumulator) the
 // accumulators are read back and added to a shared-memory fp32 tile with IEEE adds; the split partials go through the same finish kernel as before.
 // ------------------------------------------------------------------------------------------------------------------------------------
 constexpr int WT_ROWS = 32;
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(288, 2) wgrad_tc_kernel(const GemmArgs g, cons
     ptx::mbar_init(&full_bar[0], 256); ptx::mbar_init(&full_bar[1], 256); ptx::mbar_init(&acc_free, 128);
     ptx::fence_barrier_init();
   }
-  if (warp == 0) ptx::tmem_alloc(&tmem_base_s, 128);
+  if (warp == 0) ptx::tmem_alloc(&tmem_base_s, 256);
   if (tid < 128) {
 #pragma unroll 8
     for (int y = 0; y < 64; ++y) accs[tid * WT_ACC_LD + y] = 0.f;
@@ -184,7 +184,8 @@ __global__ void __launch_bounds__(288, 2) wgrad_tc_kernel(const GemmArgs g, cons
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
-  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  constexpr uint32_t IDESC_B = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 4) << 24);      // f32 accumulate, bf16 x bf16, both operands MN-major, M = 128
+  constexpr uint32_t IDESC_N192 = IDESC_B | ((uint32_t)(192 >> 3) << 17), IDESC_N128 = IDESC_B | ((uint32_t)(128 >> 3) << 17), IDESC_N64 = IDESC_B | ((uint32_t)(64 >> 3) << 17);
   auto is_flush = [&](int i) { return (i % WT_FLUSH == WT_FLUSH - 1) || i == nsteps - 1; };
   if (warp == 8) {
     // ================= MMA issuer (one thread): step i as soon as its staging set is full =================
@@ -199,15 +200,15 @@ __global__ void __launch_bounds__(288, 2) wgrad_tc_kernel(const GemmArgs g, cons
 #pragma unroll
         for (int k = 0; k < WT_ROWS / 16; ++k) {
           const uint32_t off = (uint32_t)(k * 256);
+          // the three Y planes are consecutive 8-block groups of ONE MN-major operand, so an N = 192 / 128 / 64 instruction multiplies an X plane with
+          // [Y_hi | Y_mid | Y_lo] / [Y_hi | Y_mid] / [Y_hi] in one read of that X plane (three instead of six operand reads of X per k-step); the column
+          // bases make the equal-magnitude terms land in the same accumulator: A0 = hi.hi | A1 = hi.mid + mid.hi | A2 = hi.lo + mid.mid + lo.hi
           const uint64_t xh = wt_desc(st + off), xm = wt_desc(st + WT_XP + off), xl = wt_desc(st + 2 * WT_XP + off);
-          const uint64_t yh = wt_desc(st + 3 * WT_XP + off), ym = wt_desc(st + 3 * WT_XP + WT_YP + off), yl = wt_desc(st + 3 * WT_XP + 2 * WT_YP + off);
-          const uint32_t acc2 = tmem_base + 64u, f = (k == 0) ? first : 1u;
-          ptx::mma_bf16(acc2, xl, yh, IDESC, f);                             // smallest terms first
-          ptx::mma_bf16(acc2, xh, yl, IDESC, 1u);
-          ptx::mma_bf16(acc2, xm, ym, IDESC, 1u);
-          ptx::mma_bf16(acc2, xm, yh, IDESC, 1u);
-          ptx::mma_bf16(acc2, xh, ym, IDESC, 1u);
-          ptx::mma_bf16(tmem_base, xh, yh, IDESC, f);
+          const uint64_t yh = wt_desc(st + 3 * WT_XP + off);
+          const uint32_t f = (k == 0) ? first : 1u;
+          ptx::mma_bf16(tmem_base, xh, yh, IDESC_N192, f);
+          ptx::mma_bf16(tmem_base + 64u, xm, yh, IDESC_N128, 1u);
+          ptx::mma_bf16(tmem_base + 128u, xl, yh, IDESC_N64, 1u);
         }
         ptx::tc_commit(&mma_done[b]);
         if (is_flush(i)) ptx::tc_commit(&acc_bar);
@@ -232,11 +233,12 @@ __global__ void __launch_bounds__(288, 2) wgrad_tc_kernel(const GemmArgs g, cons
           float* arow = accs + tid * WT_ACC_LD;
 #pragma unroll
           for (int c = 0; c < 64; c += 16) {
-            float v1[16], v2[16];
-            wt_ld16(ta + (uint32_t)c, v1);
-            wt_ld16(ta + 64u + (uint32_t)c, v2);
+            float v0[16], v1[16], v2[16];
+            wt_ld16(ta + (uint32_t)c, v0);
+            wt_ld16(ta + 64u + (uint32_t)c, v1);
+            wt_ld16(ta + 128u + (uint32_t)c, v2);
 #pragma unroll
-            for (int e = 0; e < 16; ++e) arow[c + e] += v1[e] + v2[e];
+            for (int e = 0; e < 16; ++e) arow[c + e] += (v2[e] + v1[e]) + v0[e];
           }
           ptx::tc_fence_before();
           ptx::mbar_arrive(&acc_free);
@@ -283,7 +285,7 @@ __global__ void __launch_bounds__(288, 2) wgrad_tc_kernel(const GemmArgs g, cons
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 0) ptx::tmem_dealloc(tmem_base, 128);
+  if (warp == 0) ptx::tmem_dealloc(tmem_base, 256);
 }
 
 static GemmArgs wg_args(const SebGemm* s) {
