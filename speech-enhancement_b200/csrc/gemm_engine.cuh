@@ -517,8 +517,13 @@ gemm_tc_kernel(const GemmArgs g, const uint8_t* __restrict__ w_tc) {
   // epilogue adds them.  The tensor pipe's fp32 accumulation truncates, so every MMA that lands in an accumulator costs ~half an ulp OF THAT
   // ACCUMULATOR, biased toward zero: with all six products in one accumulator a K = 1536 conv took 576 such steps (1.8e-5 of peak after the
   // whole generator); split this way the large accumulator sees K / 16 steps and the small one's ulp is 2^-8 of it.
+  // NT == 64 with three planes (the training step's convolutions, data gradients and projections) folds the weight planes into N: they are consecutive
+  // 64-row groups of ONE K-major operand, so a_hi x [w_hi | w_mid | w_lo] (N = 192), a_mid x [w_hi | w_mid] (N = 128) and a_lo x w_hi (N = 64) are three
+  // instructions instead of six per k-step, every A plane is read from shared memory once instead of 3 / 2 / 1 times, and the column bases make the
+  // equal-magnitude terms share THREE accumulators: hi.hi | hi.mid + mid.hi | hi.lo + mid.mid + lo.hi.
+  constexpr bool FOLD = NPL == 3 && NT == 64;
   constexpr uint32_t ACC_COLS = tc_tmem_cols<NT>();
-  constexpr uint32_t TMEM_COLS = (NPL == 3 ? 2 : 1) * ACC_COLS;
+  constexpr uint32_t TMEM_COLS = FOLD ? 256 : (NPL == 3 ? 2 : 1) * ACC_COLS;
   static_assert(TMEM_COLS <= 512, "two accumulators exceed tensor memory");
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -599,7 +604,13 @@ gemm_tc_kernel(const GemmArgs g, const uint8_t* __restrict__ w_tc) {
         if (j < ncols) {
           float v[8];
           ptx::tmem_ld8(taddr + c0 + j, v);
-          if (NPL == 3) {
+          if (FOLD) {
+            float v2[8], v3[8];
+            ptx::tmem_ld8(taddr + 64 + c0 + j, v2);
+            ptx::tmem_ld8(taddr + 128 + c0 + j, v3);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += v3[i] + v2[i];
+          } else if (NPL == 3) {
             float v2[8];
             ptx::tmem_ld8(taddr + ACC_COLS + c0 + j, v2);
 #pragma unroll
@@ -639,7 +650,14 @@ gemm_tc_kernel(const GemmArgs g, const uint8_t* __restrict__ w_tc) {
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
           const uint64_t ko = (uint64_t)((k * 32) >> 4);   // 16 bf16 = 32 bytes along K inside the swizzle row
-          if (NPL == 3) {
+          if (FOLD) {
+            constexpr uint32_t IDB = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BM >> 4) << 24);
+            const uint32_t first = (kc | k) ? 1u : 0u;
+            const uint64_t a_mid = ptx::umma_desc_sw128(base + TC_A_BYTES);
+            ptx::mma_bf16(tmem_base, a_hi + ko, w_hi + ko, IDB | ((uint32_t)(192 >> 3) << 17), first);
+            ptx::mma_bf16(tmem_base + 64u, a_mid + ko, w_hi + ko, IDB | ((uint32_t)(128 >> 3) << 17), 1u);
+            ptx::mma_bf16(tmem_base + 128u, a_lo + ko, w_hi + ko, IDB | ((uint32_t)(64 >> 3) << 17), 1u);
+          } else if (NPL == 3) {
             const uint32_t first = (kc | k) ? 1u : 0u;
             const uint32_t acc2 = tmem_base + ACC_COLS;                                    // cross terms: their own accumulator (see above)
             const uint64_t a_mid = ptx::umma_desc_sw128(base + TC_A_BYTES);
