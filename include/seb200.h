@@ -215,6 +215,14 @@ long long seb200_train_workspace_floats(void);
  * Conv2d weights [Cout, Cin, kt, kf] in the engine's K order (tap, cin) and their per-slot adjoints (csrc/pack_dev.cu). */
 int seb200_pack_weights_device(const float* w, int N, int K, int n1, long long sn, long long s0, long long s1, int tc_ntile, int planes,
                                void* w_tc, float* w_simt, void* stream);
+/* The same for njobs images in ceil(njobs / 24) launches: `jobs` is a HOST array of descriptors holding the arguments above (device pointers).
+ * A training step re-packs 176 images after every optimizer step (core/function.py:277 changes the parameters in place). */
+typedef struct SebPackJob {
+  const float* w; void* w_tc; float* w_simt;
+  long long sn, s0, s1;
+  int N, K, n1, tc_ntile, planes, reserved;
+} SebPackJob;
+int seb200_pack_weights_device_batch(const SebPackJob* jobs, int njobs, void* stream);
 
 /* dW[n, k] = sum_m g_out[m, n] * A[m, k], db[n] = sum_m g_out[m, n]: `a` is the FORWARD GEMM's descriptor (loader ROWS / ROWS_LN / CONV, a[],
  * lda, ln_*, conv geometry, M, K; weight / output fields ignored), g_out [M, N] with row stride ldg, N a multiple of 64 (<= 256).

@@ -51,6 +51,13 @@ class SebSeq(C.Structure):
                 ("outer_stride", C.c_longlong), ("pos_stride", C.c_longlong)]
 
 
+class SebPackJob(C.Structure):
+    """one job of seb200_pack_weights_device_batch (include/seb200.h): device pointers + the index map of seb200_pack_weights_device"""
+    _fields_ = [("w", C.c_void_p), ("w_tc", C.c_void_p), ("w_simt", C.c_void_p),
+                ("sn", C.c_longlong), ("s0", C.c_longlong), ("s1", C.c_longlong),
+                ("N", C.c_int), ("K", C.c_int), ("n1", C.c_int), ("tc_ntile", C.c_int), ("planes", C.c_int), ("reserved", C.c_int)]
+
+
 _SIGS = {
     "seb200_gemm": [C.POINTER(SebGemm), C.c_int, _fp],
     "seb200_ffn_fused": [C.POINTER(SebFfn), _fp],
@@ -84,6 +91,7 @@ _SIGS = {
     "seb200_diffusion_update": [_fp, _fp, C.c_longlong, _fp, _fp, C.c_int, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float, _fp, _fp, _fp],
     # ---- training step
     "seb200_pack_weights_device": [_fp, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int, C.c_int, _fp, _fp, _fp],
+    "seb200_pack_weights_device_batch": [C.POINTER(SebPackJob), C.c_int, _fp],
     "seb200_wgrad": [C.POINTER(SebGemm), _fp, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_longlong, C.c_longlong, _fp, _fp, _fp, C.c_longlong, _fp],
     "seb200_dropout_mask": [_fp, C.c_longlong, C.c_float, C.c_ulonglong, C.c_ulonglong, _fp],
     "seb200_swish_dropout": [_fp, _fp, C.c_float, _fp, C.c_longlong, _fp],

@@ -67,6 +67,22 @@ def pack_device(pw: PackedWeight, w: torch.Tensor, N: int, K: int, n1: int, sn: 
           "seb200_pack_weights_device")
 
 
+def pack_job(pw: PackedWeight, w: torch.Tensor, N: int, K: int, n1: int, sn: int, s0: int, s1: int, w_offset: int = 0):
+    """the same request as pack_device as a job descriptor for pack_device_batch"""
+    if w.dtype != torch.float32 or not w.is_cuda or not w.is_contiguous():
+        raise RuntimeError("pack_device reads contiguous CUDA float32 parameters")
+    return _lib.SebPackJob(w.data_ptr() + 4 * w_offset, ptr(pw.w_tc) if pw.w_tc.numel() else None, ptr(pw.w_simt) if pw.w_simt.numel() else None,
+                           sn, s0, s1, N, K, n1, pw.tc_ntile, pw.planes, 0)
+
+
+def pack_device_batch(jobs):
+    """every job of the list in ceil(len / 24) launches (a training step re-packs 176 images)"""
+    if not jobs:
+        return
+    arr = (_lib.SebPackJob * len(jobs))(*jobs)
+    check(_lib.load().seb200_pack_weights_device_batch(arr, len(jobs), stream_ptr()), "seb200_pack_weights_device_batch")
+
+
 # ---- weight gradients ---------------------------------------------------------------------------------------------------------------
 def wgrad(*, loader: int, M: int, K: int, a: Sequence[torch.Tensor], g_out: torch.Tensor, ldg: int, N: int, dw: torch.Tensor, db: Optional[torch.Tensor],
           index_map, lda: int = 0, ln=None, conv: Optional[dict] = None, k_logical: Optional[int] = None, label: str = "wgrad"):

@@ -144,8 +144,10 @@ class TrainState:
     def pack(self, prm, device):
         """device-side packing of every GEMM weight for this step: forward image + the dgrad image(s)"""
         W = self.images(device)
-        lin = lambda pw, w, N, K: T.pack_device(pw, w, N, K, K, K, 0, 1)                    # W [N, K]
-        linT = lambda pw, w, N, K: T.pack_device(pw, w, K, N, N, 1, 0, K)                   # W^T [K, N] from W [N, K]
+        jobs = []                                                                            # one batched launch sequence at the end (176 images: 8 launches)
+        job = lambda *a, **k: jobs.append(T.pack_job(*a, **k))
+        lin = lambda pw, w, N, K: job(pw, w, N, K, K, K, 0, 1)                               # W [N, K]
+        linT = lambda pw, w, N, K: job(pw, w, K, N, N, 1, 0, K)                              # W^T [K, N] from W [N, K]
         for i in range(1, 5):
             for ax in ("time", "freq"):
                 p = f"TSCB_{i}.{ax}_conformer"
@@ -168,16 +170,17 @@ class TrainState:
             for i in range(1, 5):
                 w = prm[f"{blk}.conv{i}.weight"]                                               # (64, 64 i, 2, 3)
                 cin = 64 * i
-                T.pack_device(W[f"{blk}.conv{i}"], w, 64, 6 * cin, cin, cin * 6, 1, 6)         # K order (tap, cin)
+                job(W[f"{blk}.conv{i}"], w, 64, 6 * cin, cin, cin * 6, 1, 6)         # K order (tap, cin)
                 for j in range(i):                                                             # adjoint of slot j: W'[ci, (tap, co)] = w[co, 64 j + ci, tap]
-                    T.pack_device(W[f"{blk}.conv{i}.adj{j}"], w, 64, 384, 64, 6, 1, cin * 6, w_offset=64 * j * 6)
+                    job(W[f"{blk}.conv{i}.adj{j}"], w, 64, 384, 64, 6, 1, cin * 6, w_offset=64 * j * 6)
         w = prm["dense_encoder.conv_2.0.weight"]                                               # (64, 64, 1, 3)
-        T.pack_device(W["dense_encoder.conv_2"], w, 64, 192, 64, 192, 1, 3)
-        T.pack_device(W["dense_encoder.conv_2.adj"], w, 64, 192, 64, 3, 1, 192)
+        job(W["dense_encoder.conv_2"], w, 64, 192, 64, 192, 1, 3)
+        job(W["dense_encoder.conv_2.adj"], w, 64, 192, 64, 3, 1, 192)
         for d in ("mask_decoder", "complex_decoder"):
             w = prm[f"{d}.sub_pixel.conv.weight"]                                              # (128, 64, 1, 3)
-            T.pack_device(W[f"{d}.sub_pixel"], w, 128, 192, 64, 192, 1, 3)
-            T.pack_device(W[f"{d}.sub_pixel.adj"], w, 64, 384, 128, 3, 1, 192)                  # W'[ci, (kf, co)] = w[co, ci, kf]
+            job(W[f"{d}.sub_pixel"], w, 128, 192, 64, 192, 1, 3)
+            job(W[f"{d}.sub_pixel.adj"], w, 64, 384, 128, 3, 1, 192)                  # W'[ci, (kf, co)] = w[co, ci, kf]
+        T.pack_device_batch(jobs)
         return W
 
     # ---- per-shape activation buffers ---------------------------------------------------------------------------------------------------

@@ -43,6 +43,28 @@ def test_device_packer_matches_host_packer_bit_for_bit(N, K, ntile, planes):
     assert torch.equal(pw.w_tc.cpu(), ref.w_tc) and torch.equal(pw.w_simt.cpu(), ref.w_simt)
 
 
+def test_device_packer_batch_matches_single_jobs():
+    """seb200_pack_weights_device_batch (one launch per 24 jobs) writes the same bytes as one seb200_pack_weights_device call per image: 30 jobs of mixed
+    shapes, plane counts and index maps (plain, transposed, conv K order with an offset into the parameter)"""
+    shapes = [(64, 64, 64, 3), (256, 64, 256, 3), (64, 256, 64, 3), (192, 64, 192, 3), (64, 128, 64, 2), (128, 192, 128, 3)]
+    jobs, singles = [], []
+    for i in range(30):
+        N, K, ntile, planes = shapes[i % len(shapes)]
+        w = rnd(N, K, seed=300 + i)
+        a, b = T.alloc_packed(N, K, ntile, planes, DEV, True, i % 2 == 0), T.alloc_packed(N, K, ntile, planes, DEV, True, i % 2 == 0)
+        if i % 3 == 0:      # transposed source through the index map
+            wt = w.t().contiguous()
+            args = (wt, N, K, K, 1, 0, N)
+        else:
+            args = (w, N, K, K, K, 0, 1)
+        T.pack_device(a, *args)
+        jobs.append(T.pack_job(b, *args))
+        singles.append((a, b, args[0]))
+    T.pack_device_batch(jobs)
+    for a, b, _ in singles:
+        assert torch.equal(a.w_tc, b.w_tc) and torch.equal(a.w_simt, b.w_simt)
+
+
 @pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("N,K,M", [(64, 64, 300), (256, 64, 1000), (64, 256, 777), (128, 64, 129), (64, 192, 400)])
 def test_train_gemm_rows_fp32_grade(engine, N, K, M):
